@@ -1,0 +1,79 @@
+"""ctypes binding of libgcp_b200.so (include/gcp_b200.h).  Fails loudly when the library is missing: the
+package has no CPU path."""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_int, c_size_t, c_uint8, c_uint64, c_void_p
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libgcp_b200.so"
+
+GCP_OK = 0
+GCP_ERR_BAD_ARG = -1
+GCP_ERR_CUDA = -2
+GCP_ERR_NO_DEVICE = -3
+GCP_ERR_CONSTANTS = -4
+GCP_ERR_ALLOC = -5
+
+FMT_CANONICAL = 0
+FMT_MONTGOMERY = 1
+
+STATUS_OK = 0
+STATUS_NONCANONICAL = 1
+STATUS_KEY_RANGE = 2
+STATUS_NOT_BOOLEAN = 3
+STATUS_OFF_CURVE = 4
+STATUS_ZERO_DENOM = 5
+
+_u8p = POINTER(c_uint8)
+
+# name -> (restype, argtypes).  Must list every symbol include/gcp_b200.h declares (tests check this).
+SIGNATURES = {
+    "gcp_device_count": (c_int, []),
+    "gcp_ctx_create": (c_int, [c_int, c_char_p, POINTER(c_void_p)]),
+    "gcp_ctx_destroy": (None, [c_void_p]),
+    "gcp_last_error": (c_char_p, [c_void_p]),
+    "gcp_ctx_device": (c_int, [c_void_p]),
+    "gcp_ctx_launch_count": (c_uint64, [c_void_p]),
+    "gcp_poseidon_hash": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_int]),
+    "gcp_poseidon_hash_dev": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_int, c_void_p]),
+    "gcp_poseidon_multihash": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_int]),
+    "gcp_poseidon_multihash_dev": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_int, c_void_p]),
+    "gcp_smt_verify": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    "gcp_smt_verify_dev": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                   c_void_p]),
+    "gcp_smt_verify_inclusion": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_int]),
+    "gcp_smt_verify_exclusion": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+}
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"gcp_b200 error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built: there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = os.environ.get("GCP_B200_LIB", str(LIB_PATH))
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{path} not found: build it with `python -m gnark_crypto_primitives_b200.build` "
+            "(this package has no CPU implementation)")
+    lib = ctypes.CDLL(path)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib

@@ -1,0 +1,477 @@
+// C ABI of the engine (include/gcp_b200.h): context, constant tables, device memory pools, and the
+// host-buffer entry points (chunked, double-buffered H2D -> kernels -> D2H pipelines on two streams).
+// There is no CPU compute path here: every value is produced by the kernels in kernels.cu.
+#include "../../include/gcp_b200.h"
+#include "kernels.h"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace gcp;
+
+namespace {
+
+constexpr uint32_t BLOB_MAGIC = 0x32425350u;  // 'PSB2', written by oracle/gen_constants.py
+constexpr int N_SLOTS = 48;
+
+thread_local std::string g_create_error;
+
+std::string library_dir() {
+  Dl_info info;
+  if (dladdr((void*)&gcp_ctx_create, &info) && info.dli_fname) {
+    std::string p(info.dli_fname);
+    size_t k = p.find_last_of('/');
+    return k == std::string::npos ? std::string(".") : p.substr(0, k);
+  }
+  return ".";
+}
+
+}  // namespace
+
+struct gcp_ctx {
+  int device = 0;
+  std::mutex mu;
+  std::string err;
+  cudaStream_t stream[2] = {nullptr, nullptr};
+  u32* d_tables = nullptr;
+  PoseidonTable tab[18];  // index by t
+  struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+  } slot[N_SLOTS];
+  uint64_t launches = 0;
+
+  int fail(int code, const std::string& msg) {
+    err = msg;
+    return code;
+  }
+  int cuda_fail(cudaError_t e, const char* what) {
+    err = std::string(what) + ": " + cudaGetErrorString(e);
+    return GCP_ERR_CUDA;
+  }
+  // grow-only device buffer
+  void* buf(int s, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (slot[s].cap >= bytes) return slot[s].p;
+    if (slot[s].p) cudaFree(slot[s].p);
+    slot[s].p = nullptr;
+    slot[s].cap = 0;
+    size_t cap = bytes + bytes / 8;
+    if (cudaMalloc(&slot[s].p, cap) != cudaSuccess) {
+      cudaGetLastError();
+      if (cudaMalloc(&slot[s].p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+      }
+      cap = bytes;
+    }
+    slot[s].cap = cap;
+    return slot[s].p;
+  }
+};
+
+#define CU(call, what)                                   \
+  do {                                                   \
+    cudaError_t e_ = (call);                             \
+    if (e_ != cudaSuccess) return ctx->cuda_fail(e_, what); \
+  } while (0)
+
+extern "C" {
+
+int gcp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+const char* gcp_last_error(const gcp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+int gcp_ctx_device(const gcp_ctx* ctx) { return ctx ? ctx->device : -1; }
+uint64_t gcp_ctx_launch_count(const gcp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void gcp_ctx_destroy(gcp_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (auto& s : ctx->stream)
+    if (s) {
+      cudaStreamSynchronize(s);
+      cudaStreamDestroy(s);
+    }
+  for (auto& b : ctx->slot)
+    if (b.p) cudaFree(b.p);
+  if (ctx->d_tables) cudaFree(ctx->d_tables);
+  delete ctx;
+}
+
+int gcp_ctx_create(int device, const char* constants_path, gcp_ctx** out) {
+  if (!out) {
+    g_create_error = "out is NULL";
+    return GCP_ERR_BAD_ARG;
+  }
+  *out = nullptr;
+  int ndev = gcp_device_count();
+  if (ndev <= 0) {
+    g_create_error = "no CUDA device visible (this engine has no CPU fallback)";
+    return GCP_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= ndev) {
+    g_create_error = "device index out of range";
+    return GCP_ERR_BAD_ARG;
+  }
+  // ---- read the constant blob ----------------------------------------------------------------
+  std::string path;
+  if (constants_path && *constants_path)
+    path = constants_path;
+  else if (const char* env = getenv("GCP_B200_CONSTANTS"))
+    path = env;
+  else
+    path = library_dir() + "/data/poseidon_bn254.bin";
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) {
+    g_create_error = "cannot open Poseidon constant blob: " + path;
+    return GCP_ERR_CONSTANTS;
+  }
+  std::vector<unsigned char> blob;
+  {
+    fseek(f, 0, SEEK_END);
+    long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    blob.resize(sz > 0 ? (size_t)sz : 0);
+    size_t got = blob.empty() ? 0 : fread(blob.data(), 1, blob.size(), f);
+    fclose(f);
+    if (got != blob.size() || blob.size() < 16 + 16 * 40) {
+      g_create_error = "short read on constant blob: " + path;
+      return GCP_ERR_CONSTANTS;
+    }
+  }
+  uint32_t hdr[4];
+  memcpy(hdr, blob.data(), 16);
+  if (hdr[0] != BLOB_MAGIC || hdr[1] != 1 || hdr[2] != 16) {
+    g_create_error = "bad constant blob header: " + path;
+    return GCP_ERR_CONSTANTS;
+  }
+  const size_t base = 16 + 16 * 40;
+  const size_t n_elems = (blob.size() - base) / 32;
+
+  gcp_ctx* ctx = new gcp_ctx();
+  ctx->device = device;
+  auto bail = [&](int code) {
+    g_create_error = ctx->err;
+    gcp_ctx_destroy(ctx);
+    return code;
+  };
+  cudaError_t e;
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(ctx->cuda_fail(e, "cudaSetDevice"));
+  for (auto& s : ctx->stream)
+    if ((e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)) != cudaSuccess)
+      return bail(ctx->cuda_fail(e, "cudaStreamCreate"));
+  if ((e = cudaMalloc(&ctx->d_tables, n_elems * 32)) != cudaSuccess) return bail(ctx->cuda_fail(e, "cudaMalloc tables"));
+  if ((e = cudaMemcpyAsync(ctx->d_tables, blob.data() + base, n_elems * 32, cudaMemcpyHostToDevice, ctx->stream[0])) !=
+      cudaSuccess)
+    return bail(ctx->cuda_fail(e, "upload tables"));
+  if ((e = launch_to_mont(ctx->d_tables, n_elems, ctx->stream[0])) != cudaSuccess)
+    return bail(ctx->cuda_fail(e, "to_mont kernel (is this an sm_100a device?)"));
+  ctx->launches++;
+  for (int i = 0; i < 16; i++) {
+    uint32_t d[10];
+    memcpy(d, blob.data() + 16 + 40 * i, 40);
+    int t = (int)d[0];
+    if (t != i + 2 || (size_t)d[8] + d[9] > n_elems) return bail(ctx->fail(GCP_ERR_CONSTANTS, "bad constant directory"));
+    PoseidonTable& pt = ctx->tab[t];
+    pt.t = t;
+    pt.RP = (int)d[1];
+    pt.C = ctx->d_tables + (size_t)d[2] * 8;
+    pt.S = ctx->d_tables + (size_t)d[4] * 8;
+    pt.M = ctx->d_tables + (size_t)d[6] * 8;
+    pt.P = ctx->d_tables + (size_t)d[8] * 8;
+    // the constant-memory kernels assume C | S | M | P are contiguous in that order
+    if (d[4] != d[2] + d[3] || d[6] != d[4] + d[5] || d[8] != d[6] + d[7])
+      return bail(ctx->fail(GCP_ERR_CONSTANTS, "constant tables not contiguous"));
+  }
+  if ((e = upload_const_tables(ctx->tab[3].C, ctx->tab[4].C, ctx->stream[0])) != cudaSuccess)
+    return bail(ctx->cuda_fail(e, "constant-memory upload"));
+  if ((e = cudaStreamSynchronize(ctx->stream[0])) != cudaSuccess) return bail(ctx->cuda_fail(e, "ctx init sync"));
+  *out = ctx;
+  return GCP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Poseidon
+// ---------------------------------------------------------------------------------------------------
+static int poseidon_hash_dev_locked(gcp_ctx* ctx, const void* d_in, int arity, size_t n, void* d_out,
+                                    uint8_t* d_status, int fmt, cudaStream_t st) {
+  if (arity < 1 || arity > 16) return ctx->fail(GCP_ERR_BAD_ARG, "bad inputs provided");  // poseidon.go:41-43
+  if (fmt != GCP_FMT_CANONICAL && fmt != GCP_FMT_MONTGOMERY) return ctx->fail(GCP_ERR_BAD_ARG, "bad element format");
+  if (n == 0) return GCP_OK;
+  if (!d_in || !d_out) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  if (d_status) CU(cudaMemsetAsync(d_status, 0, n, st), "memset status");
+  CU(launch_poseidon(ctx->tab[arity + 1], (const u32*)d_in, (u32*)d_out, d_status, n, 1, (size_t)arity, 0, 1, fmt, fmt,
+                     1, st),
+     "poseidon kernel");
+  ctx->launches++;
+  return GCP_OK;
+}
+
+// MultiHash (poseidon.go:54-91): 16-wide chunks, then the hash of the chunk hashes, recursively.
+// scratch slots 0/1 hold the intermediate levels (Montgomery form).
+static int poseidon_multihash_dev_locked(gcp_ctx* ctx, const void* d_in, int len, size_t n, void* d_out,
+                                         uint8_t* d_status, int fmt, cudaStream_t st, int slot_base) {
+  if (len < 1) return ctx->fail(GCP_ERR_BAD_ARG, "bad inputs provided");
+  if (len > 4096) return ctx->fail(GCP_ERR_BAD_ARG, "the maximum number of inputs supported is 4096");
+  if (len <= 16) return poseidon_hash_dev_locked(ctx, d_in, len, n, d_out, d_status, fmt, st);
+  if (fmt != GCP_FMT_CANONICAL && fmt != GCP_FMT_MONTGOMERY) return ctx->fail(GCP_ERR_BAD_ARG, "bad element format");
+  if (n == 0) return GCP_OK;
+  if (!d_in || !d_out) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  if (d_status) CU(cudaMemsetAsync(d_status, 0, n, st), "memset status");
+  const u32* cur = (const u32*)d_in;
+  int cur_len = len;
+  int cur_fmt = fmt;
+  int level = 0;
+  while (cur_len > 16) {
+    int full = cur_len / 16, rem = cur_len % 16;
+    int nchunks = full + (rem ? 1 : 0);
+    u32* nxt = (u32*)ctx->buf(slot_base + (level & 1), n * (size_t)nchunks * 32);
+    if (!nxt) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed (multihash scratch)");
+    CU(launch_poseidon(ctx->tab[17], cur, nxt, d_status, n, full, (size_t)cur_len, 16, (size_t)nchunks, cur_fmt,
+                       GCP_FMT_MONTGOMERY, 0, st),
+       "poseidon kernel (chunks)");
+    ctx->launches++;
+    if (rem) {
+      CU(launch_poseidon(ctx->tab[rem + 1], cur + (size_t)full * 16 * 8, nxt + (size_t)full * 8, d_status, n, 1,
+                         (size_t)cur_len, 0, (size_t)nchunks, cur_fmt, GCP_FMT_MONTGOMERY, 0, st),
+         "poseidon kernel (tail chunk)");
+      ctx->launches++;
+    }
+    cur = nxt;
+    cur_len = nchunks;
+    cur_fmt = GCP_FMT_MONTGOMERY;
+    level++;
+  }
+  CU(launch_poseidon(ctx->tab[cur_len + 1], cur, (u32*)d_out, d_status, n, 1, (size_t)cur_len, 0, 1, cur_fmt, fmt, 1, st),
+     "poseidon kernel (final)");
+  ctx->launches++;
+  return GCP_OK;
+}
+
+int gcp_poseidon_hash_dev(gcp_ctx* ctx, const void* d_in, int arity, size_t n, void* d_out, uint8_t* d_status, int fmt,
+                          void* stream) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  return poseidon_hash_dev_locked(ctx, d_in, arity, n, d_out, d_status, fmt, (cudaStream_t)stream);
+}
+
+int gcp_poseidon_multihash_dev(gcp_ctx* ctx, const void* d_in, int len, size_t n, void* d_out, uint8_t* d_status,
+                               int fmt, void* stream) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  return poseidon_multihash_dev_locked(ctx, d_in, len, n, d_out, d_status, fmt, (cudaStream_t)stream, 0);
+}
+
+// Host-buffer form: chunks of items, two streams alternate so that the copy of chunk k+1 overlaps the kernels of chunk k.
+static int poseidon_host(gcp_ctx* ctx, const void* in, int len, size_t n, void* out, uint8_t* status, int fmt,
+                         bool multi) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  if (len < 1 || len > (multi ? 4096 : 16))
+    return ctx->fail(GCP_ERR_BAD_ARG, multi ? "the maximum number of inputs supported is 4096" : "bad inputs provided");
+  if (n == 0) return GCP_OK;
+  if (!in || !out) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  const size_t item_bytes = (size_t)len * 32;
+  size_t chunk = std::max<size_t>(1, std::min<size_t>(n, ((size_t)256 << 20) / item_bytes));
+  int rc = GCP_OK;
+  size_t k = 0;
+  for (size_t off = 0; off < n && rc == GCP_OK; off += chunk, k++) {
+    size_t m = std::min(chunk, n - off);
+    int s = (int)(k & 1);
+    cudaStream_t st = ctx->stream[s];
+    void* d_in = ctx->buf(4 + s * 3 + 0, m * item_bytes);
+    void* d_out = ctx->buf(4 + s * 3 + 1, m * 32);
+    uint8_t* d_st = (uint8_t*)ctx->buf(4 + s * 3 + 2, m);
+    if (!d_in || !d_out || !d_st) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+    CU(cudaMemcpyAsync(d_in, (const char*)in + off * item_bytes, m * item_bytes, cudaMemcpyHostToDevice, st), "H2D");
+    rc = multi ? poseidon_multihash_dev_locked(ctx, d_in, len, m, d_out, d_st, fmt, st, 38 + s * 2)
+               : poseidon_hash_dev_locked(ctx, d_in, len, m, d_out, d_st, fmt, st);
+    if (rc != GCP_OK) break;
+    CU(cudaMemcpyAsync((char*)out + off * 32, d_out, m * 32, cudaMemcpyDeviceToHost, st), "D2H");
+    if (status) CU(cudaMemcpyAsync(status + off, d_st, m, cudaMemcpyDeviceToHost, st), "D2H status");
+  }
+  cudaError_t e0 = cudaStreamSynchronize(ctx->stream[0]);
+  cudaError_t e1 = cudaStreamSynchronize(ctx->stream[1]);
+  if (rc != GCP_OK) return rc;
+  if (e0 != cudaSuccess) return ctx->cuda_fail(e0, "stream sync");
+  if (e1 != cudaSuccess) return ctx->cuda_fail(e1, "stream sync");
+  return GCP_OK;
+}
+
+int gcp_poseidon_hash(gcp_ctx* ctx, const void* in, int arity, size_t n, void* out, uint8_t* status, int fmt) {
+  return poseidon_host(ctx, in, arity, n, out, status, fmt, false);
+}
+
+int gcp_poseidon_multihash(gcp_ctx* ctx, const void* in, int len, size_t n, void* out, uint8_t* status, int fmt) {
+  return poseidon_host(ctx, in, len, n, out, status, fmt, true);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SMT
+// ---------------------------------------------------------------------------------------------------
+static int smt_check_args(gcp_ctx* ctx, int n_levels, size_t n, const void* roots, const void* siblings,
+                          const void* old_keys, const void* old_values, const void* keys, const void* values,
+                          const uint8_t* flags, const uint8_t* status, int fmt) {
+  if (n_levels < 2 || n_levels > 253) return ctx->fail(GCP_ERR_BAD_ARG, "n_levels must be in [2, 253]");
+  if (fmt != GCP_FMT_CANONICAL && fmt != GCP_FMT_MONTGOMERY) return ctx->fail(GCP_ERR_BAD_ARG, "bad element format");
+  if (n == 0) return GCP_OK;
+  if (!roots || !siblings || !keys || !values || !flags || !status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  if ((old_keys == nullptr) != (old_values == nullptr))
+    return ctx->fail(GCP_ERR_BAD_ARG, "old_keys and old_values must both be given or both be NULL");
+  return GCP_OK;
+}
+
+static int smt_verify_dev_locked(gcp_ctx* ctx, int n_levels, size_t n, const void* d_roots, int shared_root,
+                                 const void* d_siblings, const void* d_old_keys, const void* d_old_values,
+                                 const uint8_t* d_is_old0, const void* d_keys, const void* d_values,
+                                 const uint8_t* d_fnc, const uint8_t* d_enabled, uint8_t* d_flags, uint8_t* d_status,
+                                 void* d_out_roots, int fmt, cudaStream_t st, int leaf_slot) {
+  int rc = smt_check_args(ctx, n_levels, n, d_roots, d_siblings, d_old_keys, d_old_values, d_keys, d_values, d_flags,
+                          d_status, fmt);
+  if (rc != GCP_OK || n == 0) return rc;
+  SmtArgs a;
+  a.n_levels = n_levels;
+  a.n = n;
+  a.roots = (const u32*)d_roots;
+  a.root_stride = shared_root ? 0 : 8;
+  a.siblings = (const u32*)d_siblings;
+  a.old_keys = (const u32*)d_old_keys;
+  a.old_values = (const u32*)d_old_values;
+  a.is_old0 = d_is_old0;
+  a.keys = (const u32*)d_keys;
+  a.values = (const u32*)d_values;
+  a.fnc = d_fnc;
+  a.enabled = d_enabled;
+  a.leaf = (u32*)ctx->buf(leaf_slot, n * 32);
+  if (!a.leaf) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed (leaf scratch)");
+  a.flags = d_flags;
+  a.status = d_status;
+  a.out_roots = (u32*)d_out_roots;
+  a.mont = fmt;
+  CU(launch_smt_verify(a, st), "smt kernels");
+  ctx->launches += 2;
+  return GCP_OK;
+}
+
+int gcp_smt_verify_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_roots, int shared_root,
+                       const void* d_siblings, const void* d_old_keys, const void* d_old_values,
+                       const uint8_t* d_is_old0, const void* d_keys, const void* d_values, const uint8_t* d_fnc,
+                       const uint8_t* d_enabled, uint8_t* d_out_flags, uint8_t* d_out_status, void* d_out_roots,
+                       int fmt, void* stream) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  return smt_verify_dev_locked(ctx, n_levels, n, d_roots, shared_root, d_siblings, d_old_keys, d_old_values, d_is_old0,
+                               d_keys, d_values, d_fnc, d_enabled, d_out_flags, d_out_status, d_out_roots, fmt,
+                               (cudaStream_t)stream, 2);
+}
+
+int gcp_smt_verify(gcp_ctx* ctx, int n_levels, size_t n, const void* roots, int shared_root, const void* siblings,
+                   const void* old_keys, const void* old_values, const uint8_t* is_old0, const void* keys,
+                   const void* values, const uint8_t* fnc, const uint8_t* enabled, uint8_t* out_flags,
+                   uint8_t* out_status, void* out_roots, int fmt) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  int rc = smt_check_args(ctx, n_levels, n, roots, siblings, old_keys, old_values, keys, values, out_flags, out_status,
+                          fmt);
+  if (rc != GCP_OK || n == 0) return rc;
+  const size_t sib_bytes = (size_t)n_levels * 32;
+  size_t chunk = std::max<size_t>(1, std::min<size_t>(n, ((size_t)192 << 20) / sib_bytes));
+  if (const char* env = getenv("GCP_B200_SMT_CHUNK")) {
+    long v = atol(env);
+    if (v > 0) chunk = std::min<size_t>(n, (size_t)v);
+  }
+  // a shared root is uploaded once
+  void* d_shared_root = nullptr;
+  if (shared_root) {
+    d_shared_root = ctx->buf(3, 32);
+    if (!d_shared_root) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+    CU(cudaMemcpy(d_shared_root, roots, 32, cudaMemcpyHostToDevice), "H2D root");
+  }
+  size_t k = 0;
+  for (size_t off = 0; off < n && rc == GCP_OK; off += chunk, k++) {
+    size_t m = std::min(chunk, n - off);
+    int s = (int)(k & 1);
+    cudaStream_t st = ctx->stream[s];
+    const int b = 10 + s * 14;
+    void* d_sib = ctx->buf(b + 0, m * sib_bytes);
+    void* d_roots = shared_root ? d_shared_root : ctx->buf(b + 1, m * 32);
+    void* d_keys = ctx->buf(b + 2, m * 32);
+    void* d_vals = ctx->buf(b + 3, m * 32);
+    void* d_okeys = old_keys ? ctx->buf(b + 4, m * 32) : nullptr;
+    void* d_ovals = old_keys ? ctx->buf(b + 5, m * 32) : nullptr;
+    uint8_t* d_is0 = is_old0 ? (uint8_t*)ctx->buf(b + 6, m) : nullptr;
+    uint8_t* d_fnc = fnc ? (uint8_t*)ctx->buf(b + 7, m) : nullptr;
+    uint8_t* d_en = enabled ? (uint8_t*)ctx->buf(b + 8, m) : nullptr;
+    uint8_t* d_flags = (uint8_t*)ctx->buf(b + 9, m);
+    uint8_t* d_status = (uint8_t*)ctx->buf(b + 10, m);
+    void* d_oroots = out_roots ? ctx->buf(b + 11, m * 32) : nullptr;
+    if (!d_sib || !d_roots || !d_keys || !d_vals || !d_flags || !d_status || (old_keys && (!d_okeys || !d_ovals)) ||
+        (is_old0 && !d_is0) || (fnc && !d_fnc) || (enabled && !d_en) || (out_roots && !d_oroots))
+      return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+    CU(cudaMemcpyAsync(d_sib, (const char*)siblings + off * sib_bytes, m * sib_bytes, cudaMemcpyHostToDevice, st), "H2D");
+    if (!shared_root) CU(cudaMemcpyAsync(d_roots, (const char*)roots + off * 32, m * 32, cudaMemcpyHostToDevice, st), "H2D");
+    CU(cudaMemcpyAsync(d_keys, (const char*)keys + off * 32, m * 32, cudaMemcpyHostToDevice, st), "H2D");
+    CU(cudaMemcpyAsync(d_vals, (const char*)values + off * 32, m * 32, cudaMemcpyHostToDevice, st), "H2D");
+    if (old_keys) {
+      CU(cudaMemcpyAsync(d_okeys, (const char*)old_keys + off * 32, m * 32, cudaMemcpyHostToDevice, st), "H2D");
+      CU(cudaMemcpyAsync(d_ovals, (const char*)old_values + off * 32, m * 32, cudaMemcpyHostToDevice, st), "H2D");
+    }
+    if (is_old0) CU(cudaMemcpyAsync(d_is0, is_old0 + off, m, cudaMemcpyHostToDevice, st), "H2D");
+    if (fnc) CU(cudaMemcpyAsync(d_fnc, fnc + off, m, cudaMemcpyHostToDevice, st), "H2D");
+    if (enabled) CU(cudaMemcpyAsync(d_en, enabled + off, m, cudaMemcpyHostToDevice, st), "H2D");
+    rc = smt_verify_dev_locked(ctx, n_levels, m, d_roots, shared_root, d_sib, d_okeys, d_ovals, d_is0, d_keys, d_vals,
+                               d_fnc, d_en, d_flags, d_status, d_oroots, fmt, st, b + 12);
+    if (rc != GCP_OK) break;
+    CU(cudaMemcpyAsync(out_flags + off, d_flags, m, cudaMemcpyDeviceToHost, st), "D2H");
+    CU(cudaMemcpyAsync(out_status + off, d_status, m, cudaMemcpyDeviceToHost, st), "D2H");
+    if (out_roots) CU(cudaMemcpyAsync((char*)out_roots + off * 32, d_oroots, m * 32, cudaMemcpyDeviceToHost, st), "D2H");
+  }
+  cudaError_t e0 = cudaStreamSynchronize(ctx->stream[0]);
+  cudaError_t e1 = cudaStreamSynchronize(ctx->stream[1]);
+  if (rc != GCP_OK) return rc;
+  if (e0 != cudaSuccess) return ctx->cuda_fail(e0, "stream sync");
+  if (e1 != cudaSuccess) return ctx->cuda_fail(e1, "stream sync");
+  return GCP_OK;
+}
+
+int gcp_smt_verify_inclusion(gcp_ctx* ctx, int n_levels, size_t n, const void* roots, int shared_root,
+                             const void* siblings, const void* keys, const void* values, uint8_t* out_flags,
+                             uint8_t* out_status, void* out_roots, int fmt) {
+  // verifier.go:29-43: Verifier(enabled=1, root, siblings, key, value, isOld0=0, key, value, fnc=0)
+  return gcp_smt_verify(ctx, n_levels, n, roots, shared_root, siblings, nullptr, nullptr, nullptr, keys, values, nullptr,
+                        nullptr, out_flags, out_status, out_roots, fmt);
+}
+
+int gcp_smt_verify_exclusion(gcp_ctx* ctx, int n_levels, size_t n, const void* roots, int shared_root,
+                             const void* siblings, const void* old_keys, const void* old_values,
+                             const uint8_t* is_old0, const void* keys, uint8_t* out_flags, uint8_t* out_status,
+                             void* out_roots, int fmt) {
+  // verifier.go:66-81: Verifier(enabled=1, root, siblings, oldKey, oldValue, isOld0, key, value=0, fnc=1)
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  if (n == 0) return GCP_OK;
+  std::vector<uint8_t> ones(n, 1);
+  std::vector<uint8_t> zeros(n * 32, 0);  // value = 0 in either element format
+  return gcp_smt_verify(ctx, n_levels, n, roots, shared_root, siblings, old_keys, old_values, is_old0, keys, zeros.data(),
+                        ones.data(), nullptr, out_flags, out_status, out_roots, fmt);
+}
+
+}  // extern "C"

@@ -1,0 +1,397 @@
+// BN254 scalar field Fr on sm_100a: 8 x 32-bit limbs, Montgomery form (R = 2^256), values kept
+// "lazy" in [0, 2r) between operations and made canonical only at the engine boundary.
+//
+// Design ("Fr arithmetic"):
+//  * Every 32x32->64 product is one IMAD.WIDE.U32 whose 64-bit accumulator is an aligned register
+//    pair.  A product a[j]*b[i] lands at limb i+j; pairs that start on an even limb live in the
+//    E accumulator, pairs that start on an odd limb in the O accumulator, so no pair ever needs
+//    re-alignment.  ptxas fuses each `mad.lo.cc / madc.hi.cc` pair below into
+//    IMAD.WIDE.U32[.X] with predicate carry-in/out (checked with cuobjdump).
+//  * A row (one multiplier word times 4 same-parity multiplicand words) is one 4-deep carry chain;
+//    the carry that leaves a chain is counted into a small K limb instead of rippling upwards.
+//  * The 512-bit value is   sum e[p] * 2^(64p)  +  sum o[p] * 2^(64p+32)  +  sum k[q] * 2^(32(q+8)).
+//    Several products may be accumulated before ONE Montgomery reduction (lazy dot products:
+//    Poseidon's matrix rows cost t*64 + 72 wide multiplies instead of t*136).
+//
+// Value semantics follow gnark's test engine: every api.Add/Mul/Sub is exact arithmetic mod r
+// (/root/reference SURVEY appendix A); r literal at hash/emulated/bn254/mimc7/constants.go:18.
+#pragma once
+#include <cstdint>
+
+namespace gcp {
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+struct Fr {
+  u32 v[8];
+};
+
+// r, 2r, -r^-1 mod 2^32, R mod r, R^2 mod r (little-endian 32-bit limbs)
+#define GCP_P0 0xf0000001u
+#define GCP_P1 0x43e1f593u
+#define GCP_P2 0x79b97091u
+#define GCP_P3 0x2833e848u
+#define GCP_P4 0x8181585du
+#define GCP_P5 0xb85045b6u
+#define GCP_P6 0xe131a029u
+#define GCP_P7 0x30644e72u
+#define GCP_NP 0xefffffffu
+
+__device__ __constant__ const u32 FR_P[8] = {GCP_P0, GCP_P1, GCP_P2, GCP_P3, GCP_P4, GCP_P5, GCP_P6, GCP_P7};
+__device__ __constant__ const u32 FR_2P[8] = {0xe0000002u, 0x87c3eb27u, 0xf372e122u, 0x5067d090u,
+                                              0x0302b0bau, 0x70a08b6du, 0xc2634053u, 0x60c89ce5u};
+__device__ __constant__ const u32 FR_ONE[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u,
+                                               0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};  // R mod r
+__device__ __constant__ const u32 FR_R2[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u,
+                                              0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};   // R^2 mod r
+
+// ------------------------------------------------------------------------------------------
+// 512-bit lazy accumulator
+// ------------------------------------------------------------------------------------------
+struct Wide {
+  u64 e[8];  // e[p]: limbs 2p, 2p+1
+  u64 o[7];  // o[p]: limbs 2p+1, 2p+2
+  u32 k[8];  // k[q]: carry count at limb 8+q
+};
+
+__device__ __forceinline__ void wide_zero(Wide& w) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) w.e[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 7; i++) w.o[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) w.k[i] = 0;
+}
+
+__device__ __forceinline__ u32 lo32(u64 x) { return (u32)x; }
+__device__ __forceinline__ u32 hi32(u64 x) { return (u32)(x >> 32); }
+
+// (p0..p3) += {x0,x1,x2,x3} * y as one carry chain over four consecutive 64-bit pairs; carry -> kc.
+__device__ __forceinline__ void chain4(u64& p0, u64& p1, u64& p2, u64& p3, u32& kc, u32 x0, u32 x1, u32 x2, u32 x3,
+                                       u32 y) {
+  asm("{\n\t"
+      ".reg .u32 l0, h0, l1, h1, l2, h2, l3, h3;\n\t"
+      "mov.b64 {l0, h0}, %0;\n\t"
+      "mov.b64 {l1, h1}, %1;\n\t"
+      "mov.b64 {l2, h2}, %2;\n\t"
+      "mov.b64 {l3, h3}, %3;\n\t"
+      "mad.lo.cc.u32 l0, %5, %9, l0;\n\t"
+      "madc.hi.cc.u32 h0, %5, %9, h0;\n\t"
+      "madc.lo.cc.u32 l1, %6, %9, l1;\n\t"
+      "madc.hi.cc.u32 h1, %6, %9, h1;\n\t"
+      "madc.lo.cc.u32 l2, %7, %9, l2;\n\t"
+      "madc.hi.cc.u32 h2, %7, %9, h2;\n\t"
+      "madc.lo.cc.u32 l3, %8, %9, l3;\n\t"
+      "madc.hi.cc.u32 h3, %8, %9, h3;\n\t"
+      "addc.u32 %4, %4, 0;\n\t"
+      "mov.b64 %0, {l0, h0};\n\t"
+      "mov.b64 %1, {l1, h1};\n\t"
+      "mov.b64 %2, {l2, h2};\n\t"
+      "mov.b64 %3, {l3, h3};\n\t"
+      "}"
+      : "+l"(p0), "+l"(p1), "+l"(p2), "+l"(p3), "+r"(kc)
+      : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y));
+}
+
+// Same chain, carry-out discarded (used where the carry is provably zero: it would land at limb 16).
+__device__ __forceinline__ void chain4_nc(u64& p0, u64& p1, u64& p2, u64& p3, u32 x0, u32 x1, u32 x2, u32 x3, u32 y) {
+  asm("{\n\t"
+      ".reg .u32 l0, h0, l1, h1, l2, h2, l3, h3;\n\t"
+      "mov.b64 {l0, h0}, %0;\n\t"
+      "mov.b64 {l1, h1}, %1;\n\t"
+      "mov.b64 {l2, h2}, %2;\n\t"
+      "mov.b64 {l3, h3}, %3;\n\t"
+      "mad.lo.cc.u32 l0, %4, %8, l0;\n\t"
+      "madc.hi.cc.u32 h0, %4, %8, h0;\n\t"
+      "madc.lo.cc.u32 l1, %5, %8, l1;\n\t"
+      "madc.hi.cc.u32 h1, %5, %8, h1;\n\t"
+      "madc.lo.cc.u32 l2, %6, %8, l2;\n\t"
+      "madc.hi.cc.u32 h2, %6, %8, h2;\n\t"
+      "madc.lo.cc.u32 l3, %7, %8, l3;\n\t"
+      "madc.hi.u32 h3, %7, %8, h3;\n\t"
+      "mov.b64 %0, {l0, h0};\n\t"
+      "mov.b64 %1, {l1, h1};\n\t"
+      "mov.b64 %2, {l2, h2};\n\t"
+      "mov.b64 %3, {l3, h3};\n\t"
+      "}"
+      : "+l"(p0), "+l"(p1), "+l"(p2), "+l"(p3)
+      : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y));
+}
+
+// w += x * y * 2^(32*I)   (x: 8 limbs, y: one limb).  Products x[j]*y land at limb I+j.
+template <int I>
+__device__ __forceinline__ void mac_row(Wide& w, const u32 (&x)[8], u32 y) {
+  if constexpr (I % 2 == 0) {
+    constexpr int P = I / 2;
+    // even j -> even limb I+j -> E pairs P..P+3, carry at limb I+8
+    chain4(w.e[P], w.e[P + 1], w.e[P + 2], w.e[P + 3], w.k[I], x[0], x[2], x[4], x[6], y);
+    // odd j -> odd limb I+j -> O pairs P..P+3, carry at limb I+9
+    if constexpr (I + 1 < 8)
+      chain4(w.o[P], w.o[P + 1], w.o[P + 2], w.o[P + 3], w.k[I + 1], x[1], x[3], x[5], x[7], y);
+    else
+      chain4_nc(w.o[P], w.o[P + 1], w.o[P + 2], w.o[P + 3], x[1], x[3], x[5], x[7], y);
+  } else {
+    constexpr int PE = (I + 1) / 2, PO = (I - 1) / 2;
+    // even j -> odd limb I+j -> O pairs PO..PO+3, carry at limb I+8
+    chain4(w.o[PO], w.o[PO + 1], w.o[PO + 2], w.o[PO + 3], w.k[I], x[0], x[2], x[4], x[6], y);
+    // odd j -> even limb I+j -> E pairs PE..PE+3, carry at limb I+9
+    if constexpr (I + 1 < 8)
+      chain4(w.e[PE], w.e[PE + 1], w.e[PE + 2], w.e[PE + 3], w.k[I + 1], x[1], x[3], x[5], x[7], y);
+    else
+      chain4_nc(w.e[PE], w.e[PE + 1], w.e[PE + 2], w.e[PE + 3], x[1], x[3], x[5], x[7], y);
+  }
+}
+
+template <int I>
+__device__ __forceinline__ u32 wide_limb_e(const Wide& w) {  // limb I of the E accumulator
+  return (I % 2 == 0) ? lo32(w.e[I / 2]) : hi32(w.e[I / 2]);
+}
+template <int I>
+__device__ __forceinline__ u32 wide_limb_o(const Wide& w) {  // limb I (>= 1) of the O accumulator
+  return (I % 2 == 1) ? lo32(w.o[(I - 1) / 2]) : hi32(w.o[(I - 1) / 2]);
+}
+
+// w += a * b (full 8x8 schoolbook, 64 wide multiplies)
+__device__ __forceinline__ void wide_mac(Wide& w, const u32 (&a)[8], const u32 (&b)[8]) {
+  mac_row<0>(w, a, b[0]);
+  mac_row<1>(w, a, b[1]);
+  mac_row<2>(w, a, b[2]);
+  mac_row<3>(w, a, b[3]);
+  mac_row<4>(w, a, b[4]);
+  mac_row<5>(w, a, b[5]);
+  mac_row<6>(w, a, b[6]);
+  mac_row<7>(w, a, b[7]);
+}
+
+// w += a * R  (places a at limbs 8..15; adds a Montgomery-form constant to a pending dot product)
+__device__ __forceinline__ void wide_add_hi(Wide& w, const u32 (&a)[8]) {
+  // the E pairs 4..7 hold limbs 8..15; add as four 64-bit values with carries counted into k
+  asm("{\n\t"
+      ".reg .u32 l0, h0, l1, h1, l2, h2, l3, h3;\n\t"
+      "mov.b64 {l0, h0}, %0;\n\t"
+      "mov.b64 {l1, h1}, %1;\n\t"
+      "mov.b64 {l2, h2}, %2;\n\t"
+      "mov.b64 {l3, h3}, %3;\n\t"
+      "add.cc.u32 l0, l0, %4;\n\t"
+      "addc.cc.u32 h0, h0, %5;\n\t"
+      "addc.cc.u32 l1, l1, %6;\n\t"
+      "addc.cc.u32 h1, h1, %7;\n\t"
+      "addc.cc.u32 l2, l2, %8;\n\t"
+      "addc.cc.u32 h2, h2, %9;\n\t"
+      "addc.cc.u32 l3, l3, %10;\n\t"
+      "addc.u32 h3, h3, %11;\n\t"
+      "mov.b64 %0, {l0, h0};\n\t"
+      "mov.b64 %1, {l1, h1};\n\t"
+      "mov.b64 %2, {l2, h2};\n\t"
+      "mov.b64 %3, {l3, h3};\n\t"
+      "}"
+      : "+l"(w.e[4]), "+l"(w.e[5]), "+l"(w.e[6]), "+l"(w.e[7])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+}
+
+template <int I>
+__device__ __forceinline__ void redc_row(Wide& w, u32& c) {
+  const u32 P[8] = {GCP_P0, GCP_P1, GCP_P2, GCP_P3, GCP_P4, GCP_P5, GCP_P6, GCP_P7};
+  u32 s;
+  if constexpr (I == 0)
+    s = wide_limb_e<0>(w);
+  else
+    s = wide_limb_e<I>(w) + wide_limb_o<I>(w) + c;
+  u32 m = s * GCP_NP;
+  mac_row<I>(w, P, m);
+  // limb I of E + O + c is now 0 mod 2^32; it is either 0 or exactly 2^32
+  u32 t;
+  if constexpr (I == 0)
+    t = wide_limb_e<0>(w);
+  else
+    t = wide_limb_e<I>(w) | wide_limb_o<I>(w) | c;
+  c = (t != 0) ? 1u : 0u;
+}
+
+// Montgomery reduction: r = w / 2^256 mod r, not fully reduced.
+// Bound: r < w / 2^256 + r_mod.  For every call site in this engine w < 6.2 r^2 + r*2^256, so r < 3.2 r_mod < 2^256.
+__device__ __forceinline__ void wide_redc(Wide& w, u32 (&r)[8]) {
+  u32 c = 0;
+  redc_row<0>(w, c);
+  redc_row<1>(w, c);
+  redc_row<2>(w, c);
+  redc_row<3>(w, c);
+  redc_row<4>(w, c);
+  redc_row<5>(w, c);
+  redc_row<6>(w, c);
+  redc_row<7>(w, c);
+  // r = E[8..15] + O[8..15] + K[8..15] + c
+  u32 e8 = wide_limb_e<8>(w), e9 = wide_limb_e<9>(w), e10 = wide_limb_e<10>(w), e11 = wide_limb_e<11>(w);
+  u32 e12 = wide_limb_e<12>(w), e13 = wide_limb_e<13>(w), e14 = wide_limb_e<14>(w), e15 = wide_limb_e<15>(w);
+  u32 o8 = wide_limb_o<8>(w), o9 = wide_limb_o<9>(w), o10 = wide_limb_o<10>(w), o11 = wide_limb_o<11>(w);
+  u32 o12 = wide_limb_o<12>(w), o13 = wide_limb_o<13>(w), o14 = wide_limb_o<14>(w);
+  asm("{\n\t"
+      ".reg .u32 t;\n\t"
+      "add.cc.u32 t, %8, 0xffffffff;\n\t"  // carry flag := c
+      "addc.cc.u32 %0, %9, %17;\n\t"
+      "addc.cc.u32 %1, %10, %18;\n\t"
+      "addc.cc.u32 %2, %11, %19;\n\t"
+      "addc.cc.u32 %3, %12, %20;\n\t"
+      "addc.cc.u32 %4, %13, %21;\n\t"
+      "addc.cc.u32 %5, %14, %22;\n\t"
+      "addc.cc.u32 %6, %15, %23;\n\t"
+      "addc.u32 %7, %16, 0;\n\t"
+      "}"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(c), "r"(e8), "r"(e9), "r"(e10), "r"(e11), "r"(e12), "r"(e13), "r"(e14), "r"(e15), "r"(o8), "r"(o9),
+        "r"(o10), "r"(o11), "r"(o12), "r"(o13), "r"(o14));
+  asm("add.cc.u32 %0, %0, %8;\n\t"
+      "addc.cc.u32 %1, %1, %9;\n\t"
+      "addc.cc.u32 %2, %2, %10;\n\t"
+      "addc.cc.u32 %3, %3, %11;\n\t"
+      "addc.cc.u32 %4, %4, %12;\n\t"
+      "addc.cc.u32 %5, %5, %13;\n\t"
+      "addc.cc.u32 %6, %6, %14;\n\t"
+      "addc.u32 %7, %7, %15;\n\t"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+      : "r"(w.k[0]), "r"(w.k[1]), "r"(w.k[2]), "r"(w.k[3]), "r"(w.k[4]), "r"(w.k[5]), "r"(w.k[6]), "r"(w.k[7]));
+}
+
+// ------------------------------------------------------------------------------------------
+// 256-bit helpers
+// ------------------------------------------------------------------------------------------
+// r = a - b, returns borrow (1 if a < b)
+__device__ __forceinline__ u32 sub256(u32 (&r)[8], const u32 (&a)[8], const u32 (&b)[8]) {
+  u32 borrow;
+  asm("sub.cc.u32 %0, %9, %17;\n\t"
+      "subc.cc.u32 %1, %10, %18;\n\t"
+      "subc.cc.u32 %2, %11, %19;\n\t"
+      "subc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\t"
+      "subc.cc.u32 %5, %14, %22;\n\t"
+      "subc.cc.u32 %6, %15, %23;\n\t"
+      "subc.cc.u32 %7, %16, %24;\n\t"
+      "subc.u32 %8, 0, 0;\n\t"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(borrow)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]), "r"(b[1]),
+        "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+  return borrow & 1u;
+}
+
+__device__ __forceinline__ void add256(u32 (&r)[8], const u32 (&a)[8], const u32 (&b)[8]) {
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;\n\t"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]), "r"(b[1]),
+        "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+}
+
+// a := a - m if a >= m  (a < 2m on entry)
+__device__ __forceinline__ void cond_sub(u32 (&a)[8], const u32 (&m)[8]) {
+  u32 t[8];
+  u32 borrow = sub256(t, a, m);
+#pragma unroll
+  for (int i = 0; i < 8; i++) a[i] = borrow ? a[i] : t[i];
+}
+
+#define GCP_2P_LIMBS {0xe0000002u, 0x87c3eb27u, 0xf372e122u, 0x5067d090u, 0x0302b0bau, 0x70a08b6du, 0xc2634053u, 0x60c89ce5u}
+#define GCP_P_LIMBS {GCP_P0, GCP_P1, GCP_P2, GCP_P3, GCP_P4, GCP_P5, GCP_P6, GCP_P7}
+
+// ------------------------------------------------------------------------------------------
+// Fr operations on lazy Montgomery values (all inputs < 2r unless stated, all outputs < 2r)
+// ------------------------------------------------------------------------------------------
+// r = a * b / R.  inputs < 2r  =>  output < 1.76 r  (4 r^2 / 2^256 + r)
+__device__ __forceinline__ void fr_mul(u32 (&r)[8], const u32 (&a)[8], const u32 (&b)[8]) {
+  Wide w;
+  wide_zero(w);
+  wide_mac(w, a, b);
+  wide_redc(w, r);
+}
+
+__device__ __forceinline__ void fr_sqr(u32 (&r)[8], const u32 (&a)[8]) { fr_mul(r, a, a); }
+
+// r = a + b mod 2r
+__device__ __forceinline__ void fr_add(u32 (&r)[8], const u32 (&a)[8], const u32 (&b)[8]) {
+  const u32 P2[8] = GCP_2P_LIMBS;
+  add256(r, a, b);  // < 4r < 2^256
+  cond_sub(r, P2);
+}
+
+// r = a - b mod 2r
+__device__ __forceinline__ void fr_sub(u32 (&r)[8], const u32 (&a)[8], const u32 (&b)[8]) {
+  const u32 P2[8] = GCP_2P_LIMBS;
+  u32 t[8], u[8];
+  u32 borrow = sub256(t, a, b);
+  add256(u, t, P2);
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = borrow ? u[i] : t[i];
+}
+
+// r = -a mod 2r   (a < 2r; 0 stays 0... as 2r - a which is congruent)
+__device__ __forceinline__ void fr_neg(u32 (&r)[8], const u32 (&a)[8]) {
+  const u32 P2[8] = GCP_2P_LIMBS;
+  sub256(r, P2, a);  // in (0, 2r]; 2r only when a == 0
+  cond_sub(r, P2);
+}
+
+__device__ __forceinline__ void fr_double(u32 (&r)[8], const u32 (&a)[8]) { fr_add(r, a, a); }
+
+// lazy (< 4r) -> canonical [0, r)
+__device__ __forceinline__ void fr_canon(u32 (&a)[8]) {
+  const u32 P2[8] = GCP_2P_LIMBS;
+  const u32 P1[8] = GCP_P_LIMBS;
+  cond_sub(a, P2);
+  cond_sub(a, P1);
+}
+
+// standard canonical integer -> lazy Montgomery
+__device__ __forceinline__ void fr_to_mont(u32 (&r)[8], const u32 (&a)[8]) {
+  const u32 R2[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
+  fr_mul(r, a, R2);
+}
+
+// lazy Montgomery -> canonical standard integer
+__device__ __forceinline__ void fr_from_mont(u32 (&r)[8], const u32 (&a)[8]) {
+  Wide w;
+  wide_zero(w);
+#pragma unroll
+  for (int p = 0; p < 4; p++) w.e[p] = ((u64)a[2 * p + 1] << 32) | a[2 * p];
+  wide_redc(w, r);  // < a / 2^256 + r <= r  (a < 2^256)
+  const u32 P1[8] = GCP_P_LIMBS;
+  cond_sub(r, P1);
+}
+
+__device__ __forceinline__ bool fr_is_canonical(const u32 (&a)[8]) {  // a < r
+  const u32 P1[8] = GCP_P_LIMBS;
+  u32 t[8];
+  return sub256(t, a, P1) != 0;
+}
+
+__device__ __forceinline__ bool is_zero256(const u32 (&a)[8]) {
+  return (a[0] | a[1] | a[2] | a[3] | a[4] | a[5] | a[6] | a[7]) == 0;
+}
+
+__device__ __forceinline__ bool eq256(const u32 (&a)[8], const u32 (&b)[8]) {
+  u32 d = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) d |= a[i] ^ b[i];
+  return d == 0;
+}
+
+// 128-bit vectorised global access of one 32-byte element (address must be 16-byte aligned)
+__device__ __forceinline__ void load_fr(u32 (&r)[8], const void* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 x = __ldg(q), y = __ldg(q + 1);
+  r[0] = x.x; r[1] = x.y; r[2] = x.z; r[3] = x.w;
+  r[4] = y.x; r[5] = y.y; r[6] = y.z; r[7] = y.w;
+}
+
+__device__ __forceinline__ void store_fr(void* p, const u32 (&a)[8]) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+  q[0] = make_uint4(a[0], a[1], a[2], a[3]);
+  q[1] = make_uint4(a[4], a[5], a[6], a[7]);
+}
+
+}  // namespace gcp

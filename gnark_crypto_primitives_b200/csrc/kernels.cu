@@ -1,0 +1,176 @@
+// All device code of the engine lives in this one translation unit (the constant-memory tables are shared by
+// the Poseidon, SMT and ElGamal kernels without relocatable device code).  Host-side launch wrappers only;
+// the C ABI, chunking and memory pools are in capi.cu.
+#include "fr.cuh"
+#include "poseidon.cuh"
+#include "smt.cuh"
+#include "kernels.h"
+
+namespace gcp {
+
+// ---------------------------------------------------------------------------------------------------
+// setup kernels
+// ---------------------------------------------------------------------------------------------------
+__global__ void to_mont_kernel(u32* elems, size_t n) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  u32 x[8], m[8];
+  load_fr(x, elems + idx * 8);
+  fr_to_mont(m, x);
+  fr_canon(m);
+  store_fr(elems + idx * 8, m);
+}
+
+cudaError_t launch_to_mont(u32* d_elems, size_t n, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  to_mont_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(d_elems, n);
+  return cudaGetLastError();
+}
+
+cudaError_t upload_const_tables(const u32* d_t3, const u32* d_t4, cudaStream_t stream) {
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_pos3, d_t3, sizeof(u32) * POS3_ELEMS * 8, 0, cudaMemcpyDeviceToDevice, stream);
+  if (e != cudaSuccess) return e;
+  return cudaMemcpyToSymbolAsync(c_pos4, d_t4, sizeof(u32) * POS4_ELEMS * 8, 0, cudaMemcpyDeviceToDevice, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Poseidon batch kernels.  One thread per hash.
+// Addressing (in elements): input j of hash (item, chunk) at in[item*in_item_stride + chunk*in_chunk_stride + j],
+// output at out[item*out_item_stride + chunk]; a plain batch is chunks_per_item = 1.
+// ---------------------------------------------------------------------------------------------------
+struct HashGeom {
+  size_t total;            // n_items * chunks_per_item
+  int chunks_per_item;
+  size_t in_item_stride, in_chunk_stride, out_item_stride;
+  int in_mont, out_mont;   // element format on each side (intermediate MultiHash levels stay Montgomery)
+  int final_level;         // zero the output of items whose status is set
+};
+
+template <int T>
+__global__ void __launch_bounds__(128) poseidon_fixed_kernel(const u32* __restrict__ in, u32* __restrict__ out,
+                                                              u8* __restrict__ status, HashGeom g) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g.total) return;
+  size_t item = idx / g.chunks_per_item;
+  int chunk = (int)(idx - item * g.chunks_per_item);
+  const u32* src = in + (item * g.in_item_stride + (size_t)chunk * g.in_chunk_stride) * 8;
+  u32 s[T][8];
+  bool ok = true;
+#pragma unroll
+  for (int l = 0; l < 8; l++) s[0][l] = 0;
+#pragma unroll
+  for (int j = 1; j < T; j++) {
+    u32 x[8];
+    load_fr(x, src + (j - 1) * 8);
+    ok = ok && fr_is_canonical(x);
+    if (g.in_mont) {
+#pragma unroll
+      for (int l = 0; l < 8; l++) s[j][l] = x[l];
+    } else {
+      fr_to_mont(s[j], x);
+    }
+  }
+  u32 h[8];
+  poseidon_permute_const<T>(s, h);
+  if (g.out_mont) {
+    fr_canon(h);
+  } else {
+    u32 t[8];
+    fr_from_mont(t, h);
+#pragma unroll
+    for (int l = 0; l < 8; l++) h[l] = t[l];
+  }
+  if (status) {
+    if (!ok) status[item] = GCP_STATUS_NONCANONICAL;
+    if (g.final_level && (!ok || status[item] != GCP_STATUS_OK)) {
+#pragma unroll
+      for (int l = 0; l < 8; l++) h[l] = 0;
+    }
+  }
+  store_fr(out + (item * g.out_item_stride + chunk) * 8, h);
+}
+
+__global__ void __launch_bounds__(128) poseidon_generic_kernel(PoseidonTable tab, const u32* __restrict__ in,
+                                                                u32* __restrict__ out, u8* __restrict__ status,
+                                                                HashGeom g) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g.total) return;
+  size_t item = idx / g.chunks_per_item;
+  int chunk = (int)(idx - item * g.chunks_per_item);
+  const u32* src = in + (item * g.in_item_stride + (size_t)chunk * g.in_chunk_stride) * 8;
+  u32 s[POSEIDON_MAX_T][8], n[POSEIDON_MAX_T][8];
+  bool ok = true;
+#pragma unroll
+  for (int l = 0; l < 8; l++) s[0][l] = 0;
+#pragma unroll 1
+  for (int j = 1; j < tab.t; j++) {
+    u32 x[8], m[8];
+    load_fr(x, src + (j - 1) * 8);
+    ok = ok && fr_is_canonical(x);
+    if (g.in_mont) {
+#pragma unroll
+      for (int l = 0; l < 8; l++) m[l] = x[l];
+    } else {
+      fr_to_mont(m, x);
+    }
+#pragma unroll
+    for (int l = 0; l < 8; l++) s[j][l] = m[l];
+  }
+  u32 h[8];
+  poseidon_permute_generic(s, n, h, tab);
+  if (g.out_mont) {
+    fr_canon(h);
+  } else {
+    u32 t[8];
+    fr_from_mont(t, h);
+#pragma unroll
+    for (int l = 0; l < 8; l++) h[l] = t[l];
+  }
+  if (status) {
+    if (!ok) status[item] = GCP_STATUS_NONCANONICAL;
+    if (g.final_level && (!ok || status[item] != GCP_STATUS_OK)) {
+#pragma unroll
+      for (int l = 0; l < 8; l++) h[l] = 0;
+    }
+  }
+  store_fr(out + (item * g.out_item_stride + chunk) * 8, h);
+}
+
+cudaError_t launch_poseidon(const PoseidonTable& tab, const u32* in, u32* out, u8* status, size_t n_items,
+                            int chunks_per_item, size_t in_item_stride, size_t in_chunk_stride,
+                            size_t out_item_stride, int in_mont, int out_mont, int final_level,
+                            cudaStream_t stream) {
+  HashGeom g;
+  g.total = n_items * (size_t)chunks_per_item;
+  g.chunks_per_item = chunks_per_item;
+  g.in_item_stride = in_item_stride;
+  g.in_chunk_stride = in_chunk_stride;
+  g.out_item_stride = out_item_stride;
+  g.in_mont = in_mont;
+  g.out_mont = out_mont;
+  g.final_level = final_level;
+  if (g.total == 0) return cudaSuccess;
+  unsigned blocks = (unsigned)((g.total + 127) / 128);
+  if (tab.t == 3)
+    poseidon_fixed_kernel<3><<<blocks, 128, 0, stream>>>(in, out, status, g);
+  else if (tab.t == 4)
+    poseidon_fixed_kernel<4><<<blocks, 128, 0, stream>>>(in, out, status, g);
+  else
+    poseidon_generic_kernel<<<blocks, 128, 0, stream>>>(tab, in, out, status, g);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SMT
+// ---------------------------------------------------------------------------------------------------
+cudaError_t launch_smt_verify(const SmtArgs& a, cudaStream_t stream) {
+  if (a.n == 0) return cudaSuccess;
+  unsigned blocks = (unsigned)((a.n + 127) / 128);
+  smt_leaf_kernel<<<blocks, 128, 0, stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  smt_path_kernel<<<blocks, 128, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace gcp

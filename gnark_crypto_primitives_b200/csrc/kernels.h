@@ -1,0 +1,60 @@
+// Internal launch interface between the C-ABI host layer (capi.cu) and the device translation unit (kernels.cu).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace gcp {
+
+typedef uint8_t u8;
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+// per-item status codes (mirrored in include/gcp_b200.h)
+enum : u8 {
+  GCP_STATUS_OK = 0,
+  GCP_STATUS_NONCANONICAL = 1,  // an input element >= r
+  GCP_STATUS_KEY_RANGE = 2,     // SMT key >= 2^n_levels (tree/smt/utils.go:11-13)
+  GCP_STATUS_NOT_BOOLEAN = 3,   // enabled / fnc / isOld0 not in {0,1}
+  GCP_STATUS_OFF_CURVE = 4,     // public key fails AssertIsOnCurve (elgamal/encrypt.go:49)
+  GCP_STATUS_ZERO_DENOM = 5,    // Edwards addition denominator is 0 (only reachable off-curve)
+};
+
+struct PoseidonTable {  // one per t, device pointers into the global-memory copy
+  const u32* C;
+  const u32* S;
+  const u32* M;
+  const u32* P;
+  int RP;
+  int t;
+};
+
+struct SmtArgs {
+  int n_levels;
+  size_t n;
+  const u32* roots;      // n x 8 or 1 x 8 (root_stride = 0)
+  size_t root_stride;    // in u32 words: 8 or 0
+  const u32* siblings;   // n x n_levels x 8, root -> leaf
+  const u32* old_keys;   // n x 8 or nullptr (inclusion form: old == new)
+  const u32* old_values; // n x 8 or nullptr
+  const u8* is_old0;     // n or nullptr (0)
+  const u32* keys;       // n x 8
+  const u32* values;     // n x 8 (ignored when fnc = 1: the gadget hashes value but never uses it)
+  const u8* fnc;         // n or nullptr (0 = inclusion)
+  const u8* enabled;     // n or nullptr (1)
+  u32* leaf;             // n x 8 scratch: leaf hash selected by the state machine, lazy Montgomery
+  u8* flags;             // n
+  u8* status;            // n
+  u32* out_roots;        // n x 8 or nullptr: recomputed level[0], canonical
+  int mont;              // element format: 0 canonical integers, 1 gnark-crypto Montgomery memory
+};
+
+cudaError_t launch_to_mont(u32* d_elems, size_t n, cudaStream_t stream);
+cudaError_t upload_const_tables(const u32* d_t3, const u32* d_t4, cudaStream_t stream);
+cudaError_t launch_poseidon(const PoseidonTable& tab, const u32* in, u32* out, u8* status, size_t n_items,
+                            int chunks_per_item, size_t in_item_stride, size_t in_chunk_stride,
+                            size_t out_item_stride, int in_mont, int out_mont, int final_level,
+                            cudaStream_t stream);
+cudaError_t launch_smt_verify(const SmtArgs& a, cudaStream_t stream);
+
+}  // namespace gcp

@@ -1,0 +1,301 @@
+// Poseidon permutation over BN254 Fr (circomlib "optimized" schedule), device side.
+//
+// Computes exactly the value of (*Poseidon).Sum, /root/reference/hash/native/bn254/poseidon/poseidon.go:116-183:
+//   state = [0, in...] ; ark(C,0) ; 3 x {sigma all, ark, mix(M)} ; sigma all, ark, mix(P) ;
+//   RP x {sigma(s0), +C, s0' = <S[0..t), state>, s_k += s0 * S[t+k-1]} ; 3 x {sigma all, ark, mix(M)} ;
+//   sigma all ; out = <M[.][0], state>
+// with mix(i) = sum_j m[j][i] * in[j]  (poseidon.go:213-224) and the table sizes of constants.go.
+// All arithmetic is exact mod r, so any evaluation order yields the same canonical output; here every
+// matrix row is ONE lazy dot product (t*64 wide multiplies + one 72-multiply Montgomery reduction).
+//
+// Table layout (device, Montgomery form, canonical): C[8t+RP] | S[(2t-1)RP] | M[t*t] | P[t*t], each element
+// 8 x u32.  M and P are stored as in the reference: element (j,i) at j*t+i.
+#pragma once
+#include "fr.cuh"
+#include "kernels.h"
+
+namespace gcp {
+
+
+constexpr int POSEIDON_RP[16] = {56, 57, 56, 60, 60, 63, 64, 63, 60, 66, 60, 65, 70, 60, 64, 68};  // poseidon.go:119
+
+// Constant-memory copies for the two hot widths: t=3 (Hash2, SMT node) and t=4 (Hash1, SMT leaf).
+constexpr int POS3_ELEMS = (8 * 3 + 57) + 5 * 57 + 9 + 9;  // 384
+constexpr int POS4_ELEMS = (8 * 4 + 56) + 7 * 56 + 16 + 16;  // 512
+__device__ __constant__ u32 c_pos3[POS3_ELEMS * 8];
+__device__ __constant__ u32 c_pos4[POS4_ELEMS * 8];
+
+template <int T>
+struct ConstTab;
+template <>
+struct ConstTab<3> {
+  static constexpr int RP = 57;
+  __device__ static __forceinline__ const u32* base() { return c_pos3; }
+};
+template <>
+struct ConstTab<4> {
+  static constexpr int RP = 56;
+  __device__ static __forceinline__ const u32* base() { return c_pos4; }
+};
+
+__device__ __forceinline__ void load_const(u32 (&r)[8], const u32* p) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = p[i];
+}
+
+// x <- x^5   (poseidon.go:199-203)
+__device__ __forceinline__ void sigma(u32 (&x)[8]) {
+  u32 x2[8], x4[8];
+  fr_sqr(x2, x);
+  fr_sqr(x4, x2);
+  fr_mul(x, x4, x);
+}
+
+// Register-resident permutation for small T with tables in constant memory.
+// in/out: lazy Montgomery. s[0] must be the capacity element (0).
+template <int T>
+__device__ __forceinline__ void poseidon_permute_const(u32 (&s)[T][8], u32 (&out)[8]) {
+  constexpr int RP = ConstTab<T>::RP;
+  const u32* C = ConstTab<T>::base();
+  const u32* S = C + (8 * T + RP) * 8;
+  const u32* M = S + (2 * T - 1) * RP * 8;
+  const u32* P = M + T * T * 8;
+  u32 cst[8];
+
+  // ark(C, 0)
+#pragma unroll
+  for (int j = 0; j < T; j++) {
+    load_const(cst, C + j * 8);
+    fr_add(s[j], s[j], cst);
+  }
+
+  // full rounds: sigma, ark, mix(mat)
+  auto full_round = [&](const u32* crow, const u32* mat) {
+#pragma unroll
+    for (int j = 0; j < T; j++) {
+      sigma(s[j]);
+      load_const(cst, crow + j * 8);
+      fr_add(s[j], s[j], cst);
+    }
+    u32 n[T][8];
+#pragma unroll
+    for (int i = 0; i < T; i++) {
+      Wide w;
+      wide_zero(w);
+#pragma unroll
+      for (int j = 0; j < T; j++) {
+        load_const(cst, mat + (j * T + i) * 8);
+        wide_mac(w, s[j], cst);
+      }
+      wide_redc(w, n[i]);
+      const u32 P2[8] = GCP_2P_LIMBS;
+      cond_sub(n[i], P2);
+    }
+#pragma unroll
+    for (int i = 0; i < T; i++)
+#pragma unroll
+      for (int l = 0; l < 8; l++) s[i][l] = n[i][l];
+  };
+
+#pragma unroll 1
+  for (int r = 0; r < 3; r++) full_round(C + (r + 1) * T * 8, M);
+  full_round(C + 4 * T * 8, P);
+
+  // partial rounds
+#pragma unroll 1
+  for (int r = 0; r < RP; r++) {
+    sigma(s[0]);
+    load_const(cst, C + (5 * T + r) * 8);
+    fr_add(s[0], s[0], cst);
+    const u32* srow = S + (2 * T - 1) * r * 8;
+    Wide w;
+    wide_zero(w);
+#pragma unroll
+    for (int j = 0; j < T; j++) {
+      load_const(cst, srow + j * 8);
+      wide_mac(w, s[j], cst);
+    }
+    u32 n0[8];
+    wide_redc(w, n0);
+    const u32 P2[8] = GCP_2P_LIMBS;
+    cond_sub(n0, P2);
+#pragma unroll
+    for (int k = 1; k < T; k++) {
+      load_const(cst, srow + (T + k - 1) * 8);
+      u32 prod[8];
+      fr_mul(prod, s[0], cst);
+      fr_add(s[k], s[k], prod);
+    }
+#pragma unroll
+    for (int l = 0; l < 8; l++) s[0][l] = n0[l];
+  }
+
+#pragma unroll 1
+  for (int r = 0; r < 3; r++) full_round(C + ((5 + r) * T + RP) * 8, M);
+
+  // last: sigma all, out = column 0 of M
+  Wide w;
+  wide_zero(w);
+#pragma unroll
+  for (int j = 0; j < T; j++) {
+    sigma(s[j]);
+    load_const(cst, M + (j * T) * 8);
+    wide_mac(w, s[j], cst);
+  }
+  wide_redc(w, out);
+  const u32 P2[8] = GCP_2P_LIMBS;
+  cond_sub(out, P2);
+}
+
+// Hash2 (tree/smt/hash.go:21-27): Poseidon(l, r), lazy Montgomery in and out.
+__device__ __forceinline__ void poseidon_hash2(u32 (&out)[8], const u32 (&l)[8], const u32 (&r)[8]) {
+  u32 s[3][8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    s[0][i] = 0;
+    s[1][i] = l[i];
+    s[2][i] = r[i];
+  }
+  poseidon_permute_const<3>(s, out);
+}
+
+// Poseidon(a, b, c) — Hash1 (tree/smt/hash.go:10-19) is poseidon_hash3(key, value, 1).
+__device__ __forceinline__ void poseidon_hash3(u32 (&out)[8], const u32 (&a)[8], const u32 (&b)[8],
+                                               const u32 (&c)[8]) {
+  u32 s[4][8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    s[0][i] = 0;
+    s[1][i] = a[i];
+    s[2][i] = b[i];
+    s[3][i] = c[i];
+  }
+  poseidon_permute_const<4>(s, out);
+}
+
+}  // namespace gcp
+
+// ------------------------------------------------------------------------------------------
+// Generic width (t = 2..17): tables in global memory, state in per-thread local arrays.
+// Used for every arity other than 2 and 3 and by MultiHash (16-input chunks are t = 17).
+// ------------------------------------------------------------------------------------------
+namespace gcp {
+
+constexpr int POSEIDON_MAX_T = 17;
+constexpr int LAZY_DOT_MAX = 5;  // terms (< 2r)*(< r) per reduction so that the result is < 2.9 r (see fr.cuh bounds)
+
+__device__ __forceinline__ void load_global_const(u32 (&r)[8], const u32* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 x = __ldg(q), y = __ldg(q + 1);
+  r[0] = x.x; r[1] = x.y; r[2] = x.z; r[3] = x.w;
+  r[4] = y.x; r[5] = y.y; r[6] = y.z; r[7] = y.w;
+}
+
+// out = sum_j coef[j * stride] * s[j]  over j in [0, t)   (lazy Montgomery, < 2r)
+__device__ __noinline__ void generic_dot(u32 (&out)[8], const u32 (*s)[8], const u32* coef, int stride, int t) {
+  const u32 P2[8] = GCP_2P_LIMBS;
+  u32 total[8];
+#pragma unroll
+  for (int l = 0; l < 8; l++) total[l] = 0;
+#pragma unroll 1
+  for (int j0 = 0; j0 < t; j0 += LAZY_DOT_MAX) {
+    Wide w;
+    wide_zero(w);
+    int j1 = min(t, j0 + LAZY_DOT_MAX);
+#pragma unroll 1
+    for (int j = j0; j < j1; j++) {
+      u32 c[8], x[8];
+      load_global_const(c, coef + (size_t)j * stride * 8);
+#pragma unroll
+      for (int l = 0; l < 8; l++) x[l] = s[j][l];
+      wide_mac(w, x, c);
+    }
+    u32 part[8];
+    wide_redc(w, part);
+    cond_sub(part, P2);
+    fr_add(total, total, part);
+  }
+#pragma unroll
+  for (int l = 0; l < 8; l++) out[l] = total[l];
+}
+
+__device__ __noinline__ void generic_sigma_ark(u32 (&x)[8], const u32* c) {
+  u32 k[8];
+  sigma(x);
+  load_global_const(k, c);
+  fr_add(x, x, k);
+}
+
+// s[0..t) in, lazy Montgomery, s[0] = 0.  Result in out.  poseidon.go:116-183.
+__device__ __forceinline__ void poseidon_permute_generic(u32 (*s)[8], u32 (*n)[8], u32 (&out)[8],
+                                                         const PoseidonTable& tab) {
+  const int t = tab.t, rp = tab.RP;
+  u32 x[8], k[8];
+#pragma unroll 1
+  for (int j = 0; j < t; j++) {
+    load_global_const(k, tab.C + j * 8);
+#pragma unroll
+    for (int l = 0; l < 8; l++) x[l] = s[j][l];
+    fr_add(x, x, k);
+#pragma unroll
+    for (int l = 0; l < 8; l++) s[j][l] = x[l];
+  }
+#pragma unroll 1
+  for (int fr = 0; fr < 8; fr++) {
+    if (fr == 4) {
+#pragma unroll 1
+      for (int r = 0; r < rp; r++) {
+#pragma unroll
+        for (int l = 0; l < 8; l++) x[l] = s[0][l];
+        generic_sigma_ark(x, tab.C + (5 * t + r) * 8);
+#pragma unroll
+        for (int l = 0; l < 8; l++) s[0][l] = x[l];
+        const u32* srow = tab.S + (size_t)(2 * t - 1) * r * 8;
+        u32 n0[8];
+        generic_dot(n0, s, srow, 1, t);
+#pragma unroll 1
+        for (int kk = 1; kk < t; kk++) {
+          u32 prod[8], y[8];
+          load_global_const(k, srow + (t + kk - 1) * 8);
+          fr_mul(prod, x, k);
+#pragma unroll
+          for (int l = 0; l < 8; l++) y[l] = s[kk][l];
+          fr_add(y, y, prod);
+#pragma unroll
+          for (int l = 0; l < 8; l++) s[kk][l] = y[l];
+        }
+#pragma unroll
+        for (int l = 0; l < 8; l++) s[0][l] = n0[l];
+      }
+    }
+    // sigma on every element; rounds 0..6 are followed by ark + mix, round 7 by the column-0 output
+    const u32* crow = (fr < 4) ? tab.C + (fr + 1) * t * 8 : tab.C + ((fr + 1) * t + rp) * 8;
+#pragma unroll 1
+    for (int j = 0; j < t; j++) {
+#pragma unroll
+      for (int l = 0; l < 8; l++) x[l] = s[j][l];
+      if (fr < 7)
+        generic_sigma_ark(x, crow + j * 8);
+      else
+        sigma(x);
+#pragma unroll
+      for (int l = 0; l < 8; l++) s[j][l] = x[l];
+    }
+    if (fr == 7) break;
+    const u32* mat = (fr == 3) ? tab.P : tab.M;
+#pragma unroll 1
+    for (int i = 0; i < t; i++) {
+      u32 y[8];
+      generic_dot(y, s, mat + i * 8, t, t);  // sum_j mat[j*t+i] * s[j]
+#pragma unroll
+      for (int l = 0; l < 8; l++) n[i][l] = y[l];
+    }
+#pragma unroll 1
+    for (int i = 0; i < t; i++)
+#pragma unroll
+      for (int l = 0; l < 8; l++) s[i][l] = n[i][l];
+  }
+  generic_dot(out, s, tab.M, t, t);  // column 0: sum_j M[j*t+0] * s[j]
+}
+
+}  // namespace gcp

@@ -1,0 +1,218 @@
+"""Engine: one context per GPU over the C ABI (include/gcp_b200.h).
+
+Host-side data are numpy arrays of 32-byte little-endian field elements (dtype uint8, last axis 32); the
+device-level methods (`*_dev`) take torch CUDA tensors (or raw device pointers) and a stream, and are what
+bench.py times for resident-data throughput.  Nothing here computes field arithmetic on the CPU.
+"""
+import ctypes
+from ctypes import c_void_p
+
+import numpy as np
+
+from . import _lib
+from ._lib import EngineError, FMT_CANONICAL, FMT_MONTGOMERY
+
+R = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+
+
+def ints_to_elems(values) -> np.ndarray:
+    """Iterable of Python ints (each < 2^256) -> (n, 32) uint8, little-endian."""
+    values = list(values)
+    buf = b"".join(int(v).to_bytes(32, "little") for v in values)
+    return np.frombuffer(buf, dtype=np.uint8).reshape(len(values), 32).copy()
+
+
+def elems_to_ints(arr) -> list:
+    a = np.ascontiguousarray(arr, dtype=np.uint8).reshape(-1, 32)
+    raw = a.tobytes()
+    return [int.from_bytes(raw[32 * i:32 * i + 32], "little") for i in range(a.shape[0])]
+
+
+def _as_elems(arr, n_expected=None, name="array"):
+    a = np.ascontiguousarray(arr)
+    if a.dtype != np.uint8:
+        if a.dtype == np.uint64 and a.shape[-1] == 4:
+            a = a.view(np.uint8)
+        else:
+            raise TypeError(f"{name}: expected uint8[..., 32] (or uint64[..., 4]) field elements, got {a.dtype}")
+    if a.shape[-1] != 32:
+        raise ValueError(f"{name}: last axis must be 32 bytes")
+    if n_expected is not None and a.size != n_expected * 32:
+        raise ValueError(f"{name}: expected {n_expected} elements, got {a.size // 32}")
+    return a
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    return c_void_p(a.ctypes.data)
+
+
+def _dptr(t):
+    """torch tensor / int / None -> device pointer."""
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return c_void_p(t)
+    return c_void_p(t.data_ptr())
+
+
+def _u8(arr, n, name):
+    if arr is None:
+        return None
+    a = np.ascontiguousarray(arr, dtype=np.uint8)
+    if a.size != n:
+        raise ValueError(f"{name}: expected {n} bytes")
+    return a
+
+
+class Engine:
+    def __init__(self, device: int = 0, constants_path: str = None):
+        self._lib = _lib.load()
+        h = c_void_p()
+        rc = self._lib.gcp_ctx_create(int(device), constants_path.encode() if constants_path else None, ctypes.byref(h))
+        if rc != 0:
+            msg = self._lib.gcp_last_error(None)
+            raise EngineError(rc, msg.decode() if msg else "gcp_ctx_create failed")
+        self._h = h
+        self.device = int(device)
+
+    # -- lifecycle ----------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gcp_ctx_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self._lib.gcp_last_error(self._h)
+            raise EngineError(rc, msg.decode() if msg else "")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.gcp_ctx_launch_count(self._h))
+
+    @staticmethod
+    def _stream(stream):
+        if stream is None:
+            return None
+        if isinstance(stream, int):
+            return c_void_p(stream)
+        return c_void_p(stream.cuda_stream)  # torch.cuda.Stream
+
+    # -- Poseidon -----------------------------------------------------------------------------------
+    def poseidon_hash(self, inputs, fmt=FMT_CANONICAL):
+        """inputs: (n, arity, 32) uint8 -> (digests (n, 32) uint8, status (n,) uint8).  poseidon.go:38-45."""
+        a = _as_elems(inputs, name="inputs")
+        if a.ndim != 3:
+            raise ValueError("inputs must have shape (n, arity, 32)")
+        n, arity = a.shape[0], a.shape[1]
+        out = np.empty((n, 32), dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.gcp_poseidon_hash(self._h, _ptr(a), arity, n, _ptr(out), _ptr(status), fmt))
+        return out, status
+
+    def poseidon_multihash(self, inputs, fmt=FMT_CANONICAL):
+        """inputs: (n, len, 32) uint8, 1 <= len <= 4096.  poseidon.go:54-91."""
+        a = _as_elems(inputs, name="inputs")
+        if a.ndim != 3:
+            raise ValueError("inputs must have shape (n, len, 32)")
+        n, ln = a.shape[0], a.shape[1]
+        out = np.empty((n, 32), dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.gcp_poseidon_multihash(self._h, _ptr(a), ln, n, _ptr(out), _ptr(status), fmt))
+        return out, status
+
+    def poseidon_hash_dev(self, d_in, arity, n, d_out, d_status=None, fmt=FMT_CANONICAL, stream=None):
+        self._check(self._lib.gcp_poseidon_hash_dev(self._h, _dptr(d_in), arity, n, _dptr(d_out), _dptr(d_status), fmt,
+                                                    self._stream(stream)))
+
+    def poseidon_multihash_dev(self, d_in, length, n, d_out, d_status=None, fmt=FMT_CANONICAL, stream=None):
+        self._check(self._lib.gcp_poseidon_multihash_dev(self._h, _dptr(d_in), length, n, _dptr(d_out),
+                                                         _dptr(d_status), fmt, self._stream(stream)))
+
+    # -- SMT ----------------------------------------------------------------------------------------
+    def smt_verify(self, roots, siblings, keys, values, old_keys=None, old_values=None, is_old0=None, fnc=None,
+                   enabled=None, want_roots=False, fmt=FMT_CANONICAL):
+        """smt.Verifier (tree/smt/verifier.go:102-121) over a batch.
+
+        siblings: (n, n_levels, 32); roots: (n, 32) or (32,)/(1, 32) for one shared root; keys/values: (n, 32).
+        Returns (flags, status[, roots]).
+        """
+        sib = _as_elems(siblings, name="siblings")
+        if sib.ndim != 3:
+            raise ValueError("siblings must have shape (n, n_levels, 32)")
+        n, n_levels = sib.shape[0], sib.shape[1]
+        r = _as_elems(roots, name="roots")
+        shared = 1 if r.size == 32 and n != 1 else 0
+        if not shared:
+            r = _as_elems(r, n, "roots")
+        k = _as_elems(keys, n, "keys")
+        v = _as_elems(values, n, "values")
+        ok = _as_elems(old_keys, n, "old_keys") if old_keys is not None else None
+        ov = _as_elems(old_values, n, "old_values") if old_values is not None else None
+        i0 = _u8(is_old0, n, "is_old0")
+        fn = _u8(fnc, n, "fnc")
+        en = _u8(enabled, n, "enabled")
+        flags = np.empty(n, dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        oroots = np.empty((n, 32), dtype=np.uint8) if want_roots else None
+        self._check(self._lib.gcp_smt_verify(self._h, n_levels, n, _ptr(r), shared, _ptr(sib), _ptr(ok), _ptr(ov),
+                                             _ptr(i0), _ptr(k), _ptr(v), _ptr(fn), _ptr(en), _ptr(flags), _ptr(status),
+                                             _ptr(oroots), fmt))
+        return (flags, status, oroots) if want_roots else (flags, status)
+
+    def smt_verify_inclusion(self, roots, siblings, keys, values, want_roots=False, fmt=FMT_CANONICAL):
+        """smt.InclusionVerifier (tree/smt/verifier.go:29-43)."""
+        sib = _as_elems(siblings, name="siblings")
+        n, n_levels = sib.shape[0], sib.shape[1]
+        r = _as_elems(roots, name="roots")
+        shared = 1 if r.size == 32 and n != 1 else 0
+        k = _as_elems(keys, n, "keys")
+        v = _as_elems(values, n, "values")
+        flags = np.empty(n, dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        oroots = np.empty((n, 32), dtype=np.uint8) if want_roots else None
+        self._check(self._lib.gcp_smt_verify_inclusion(self._h, n_levels, n, _ptr(r), shared, _ptr(sib), _ptr(k),
+                                                       _ptr(v), _ptr(flags), _ptr(status), _ptr(oroots), fmt))
+        return (flags, status, oroots) if want_roots else (flags, status)
+
+    def smt_verify_exclusion(self, roots, siblings, old_keys, old_values, is_old0, keys, want_roots=False,
+                             fmt=FMT_CANONICAL):
+        """smt.ExclusionVerifier (tree/smt/verifier.go:66-81)."""
+        sib = _as_elems(siblings, name="siblings")
+        n, n_levels = sib.shape[0], sib.shape[1]
+        r = _as_elems(roots, name="roots")
+        shared = 1 if r.size == 32 and n != 1 else 0
+        ok = _as_elems(old_keys, n, "old_keys")
+        ov = _as_elems(old_values, n, "old_values")
+        i0 = _u8(is_old0, n, "is_old0")
+        k = _as_elems(keys, n, "keys")
+        flags = np.empty(n, dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        oroots = np.empty((n, 32), dtype=np.uint8) if want_roots else None
+        self._check(self._lib.gcp_smt_verify_exclusion(self._h, n_levels, n, _ptr(r), shared, _ptr(sib), _ptr(ok),
+                                                       _ptr(ov), _ptr(i0), _ptr(k), _ptr(flags), _ptr(status),
+                                                       _ptr(oroots), fmt))
+        return (flags, status, oroots) if want_roots else (flags, status)
+
+    def smt_verify_dev(self, n_levels, n, d_roots, shared_root, d_siblings, d_keys, d_values, d_flags, d_status,
+                       d_old_keys=None, d_old_values=None, d_is_old0=None, d_fnc=None, d_enabled=None,
+                       d_out_roots=None, fmt=FMT_CANONICAL, stream=None):
+        self._check(self._lib.gcp_smt_verify_dev(self._h, n_levels, n, _dptr(d_roots), int(bool(shared_root)),
+                                                 _dptr(d_siblings), _dptr(d_old_keys), _dptr(d_old_values),
+                                                 _dptr(d_is_old0), _dptr(d_keys), _dptr(d_values), _dptr(d_fnc),
+                                                 _dptr(d_enabled), _dptr(d_flags), _dptr(d_status),
+                                                 _dptr(d_out_roots), fmt, self._stream(stream)))

@@ -1,0 +1,107 @@
+/* gcp_b200.h — C ABI of the B200 batch engine for the data-parallel core of
+ * vocdoni/gnark-crypto-primitives.  This is the drop-in boundary: what a Go (cgo) caller, the
+ * C++ mirror in gcp_b200.hpp and the Python ctypes mirror bind.  The reference has no FFI of its
+ * own; every entry point below cites the Go gadget / helper whose VALUES it reproduces bit-exactly.
+ *
+ * Conventions
+ *  - Field element (BN254 Fr): 32 bytes, little-endian.  GCP_FMT_CANONICAL: the integer itself, < r.
+ *    GCP_FMT_MONTGOMERY: gnark-crypto fr.Element memory ([4]uint64 limbs, Montgomery, R = 2^256), so a
+ *    Go caller can pass unsafe.Pointer(&elems[0]) of a []fr.Element unchanged.
+ *  - Point: X then Y (64 bytes).  Ciphertext: C1.X, C1.Y, C2.X, C2.Y (128 bytes), the order of
+ *    (*Ciphertext).Serialize, elgamal/ciphertext.go:98-105.
+ *  - All arrays are flat and caller-owned; the engine never keeps a host pointer after returning
+ *    (cgo pointer rules).  `*_dev` variants take device pointers and a cudaStream_t (as void*), enqueue
+ *    work and return without synchronising; the plain variants take host pointers and block.
+ *  - Return value: 0 on success, negative gcp_error on an engine fault (bad argument, CUDA error);
+ *    gcp_last_error() gives the message.  A per-item `status` byte is non-zero where the reference
+ *    would have failed an ASSERTION (solver error), while `flag` outputs carry the gadget's 0/1 result;
+ *    an invalid proof is flag 0 / status 0, never an error.
+ *  - Thread safety: calls on one gcp_ctx are serialised internally; use one ctx per GPU.
+ *  - There is no CPU fallback: without a CUDA device gcp_ctx_create fails.
+ */
+#ifndef GCP_B200_H
+#define GCP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gcp_ctx gcp_ctx;
+
+enum gcp_error {
+  GCP_OK = 0,
+  GCP_ERR_BAD_ARG = -1,
+  GCP_ERR_CUDA = -2,
+  GCP_ERR_NO_DEVICE = -3,
+  GCP_ERR_CONSTANTS = -4,
+  GCP_ERR_ALLOC = -5
+};
+
+enum gcp_format { GCP_FMT_CANONICAL = 0, GCP_FMT_MONTGOMERY = 1 };
+
+/* per-item status bytes */
+enum gcp_status {
+  GCP_STATUS_OK = 0,
+  GCP_STATUS_NONCANONICAL = 1, /* an input element >= r */
+  GCP_STATUS_KEY_RANGE = 2,    /* SMT key >= 2^n_levels: lowBits/ToBinary assertion, tree/smt/utils.go:11-13 */
+  GCP_STATUS_NOT_BOOLEAN = 3,  /* enabled / fnc / isOld0 outside {0,1}: api.Select / api.And assertions */
+  GCP_STATUS_OFF_CURVE = 4,    /* AssertIsOnCurve(pubKey), elgamal/encrypt.go:49 */
+  GCP_STATUS_ZERO_DENOM = 5    /* Edwards addition denominator 0 (reachable only with off-curve inputs) */
+};
+
+/* ---- context ------------------------------------------------------------------------------------ */
+int gcp_device_count(void);
+/* Loads the Poseidon tables (constants_path == NULL: the blob next to the library, data/poseidon_bn254.bin),
+ * builds the fixed-base tables on the device, creates streams and staging pools. */
+int gcp_ctx_create(int device, const char* constants_path, gcp_ctx** out);
+void gcp_ctx_destroy(gcp_ctx* ctx);
+const char* gcp_last_error(const gcp_ctx* ctx); /* ctx may be NULL: error of the last failed gcp_ctx_create */
+int gcp_ctx_device(const gcp_ctx* ctx);
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
+uint64_t gcp_ctx_launch_count(const gcp_ctx* ctx);
+
+/* ---- Poseidon: hash/native/bn254/poseidon/poseidon.go ------------------------------------------- */
+/* poseidon.Hash (poseidon.go:38-45, Sum :116-183): n independent hashes of `arity` inputs each.
+ * in: n*arity elements, out: n elements.  arity outside 1..16 -> GCP_ERR_BAD_ARG ("bad inputs provided"). */
+int gcp_poseidon_hash(gcp_ctx* ctx, const void* in, int arity, size_t n, void* out, uint8_t* status, int fmt);
+int gcp_poseidon_hash_dev(gcp_ctx* ctx, const void* d_in, int arity, size_t n, void* d_out, uint8_t* d_status,
+                          int fmt, void* stream);
+/* poseidon.MultiHash (poseidon.go:54-91): n independent multi-hashes of `len` inputs each, 1 <= len <= 4096. */
+int gcp_poseidon_multihash(gcp_ctx* ctx, const void* in, int len, size_t n, void* out, uint8_t* status, int fmt);
+int gcp_poseidon_multihash_dev(gcp_ctx* ctx, const void* d_in, int len, size_t n, void* d_out, uint8_t* d_status,
+                               int fmt, void* stream);
+
+/* ---- SMT: tree/smt/verifier.go ------------------------------------------------------------------ */
+/* smt.Verifier (verifier.go:102-121) -> VerifierWithLeafHashFlag (:171-242), n proofs of n_levels siblings.
+ *   roots: n elements, or 1 element when shared_root != 0
+ *   siblings: n * n_levels elements, root -> leaf, zero padded (Assignment.Siblings, wrapper.go:20-31)
+ *   old_keys/old_values: n elements each (NULL,NULL => old leaf == new leaf, the InclusionVerifier form)
+ *   is_old0, fnc, enabled: n bytes each or NULL (defaults 0, 0, 1)
+ *   out_flags, out_status: n bytes each;  out_roots: n elements or NULL (the recomputed level[0])
+ * n_levels must be in [2, 253]. */
+int gcp_smt_verify(gcp_ctx* ctx, int n_levels, size_t n, const void* roots, int shared_root, const void* siblings,
+                   const void* old_keys, const void* old_values, const uint8_t* is_old0, const void* keys,
+                   const void* values, const uint8_t* fnc, const uint8_t* enabled, uint8_t* out_flags,
+                   uint8_t* out_status, void* out_roots, int fmt);
+int gcp_smt_verify_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_roots, int shared_root,
+                       const void* d_siblings, const void* d_old_keys, const void* d_old_values,
+                       const uint8_t* d_is_old0, const void* d_keys, const void* d_values, const uint8_t* d_fnc,
+                       const uint8_t* d_enabled, uint8_t* d_out_flags, uint8_t* d_out_status, void* d_out_roots,
+                       int fmt, void* stream);
+/* smt.InclusionVerifier (verifier.go:29-43). */
+int gcp_smt_verify_inclusion(gcp_ctx* ctx, int n_levels, size_t n, const void* roots, int shared_root,
+                             const void* siblings, const void* keys, const void* values, uint8_t* out_flags,
+                             uint8_t* out_status, void* out_roots, int fmt);
+/* smt.ExclusionVerifier (verifier.go:66-81). */
+int gcp_smt_verify_exclusion(gcp_ctx* ctx, int n_levels, size_t n, const void* roots, int shared_root,
+                             const void* siblings, const void* old_keys, const void* old_values,
+                             const uint8_t* is_old0, const void* keys, uint8_t* out_flags, uint8_t* out_status,
+                             void* out_roots, int fmt);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCP_B200_H */

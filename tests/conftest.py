@@ -1,0 +1,22 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def engine():
+    """One engine (context on cuda:0) per test session.  No skip-on-missing: GPU tests must fail loudly."""
+    import gnark_crypto_primitives_b200 as g
+
+    eng = g.Engine(0)
+    yield eng
+    eng.close()

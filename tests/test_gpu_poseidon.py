@@ -1,0 +1,109 @@
+"""GPU parity: Poseidon through the C ABI vs the oracle (bit-exact)."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import poseidon as opos
+from oracle.field import R
+from tests.util import elems, ints
+
+pytestmark = pytest.mark.gpu
+
+KAT = {  # public circomlib vectors
+    (1,): 18586133768512220936620570745912940619677854269274689475585506675881198879027,
+    (1, 2): 7853200120776062878684798364095072458815029376092732009249414926327459813530,
+    (1, 2, 3): 6542985608222806190361240322586112750744169038454362455181422643027100751666,
+    (1, 2, 3, 4): 18821383157269793795438455681495246036402687001665670618754263018637548127333,
+    tuple(range(1, 17)): 9989051620750914585850546081941653841776809718687451684622678807385399211877,
+}
+
+
+def test_known_answers(engine):
+    for inp, want in KAT.items():
+        out, st = engine.poseidon_hash(elems(inp).reshape(1, len(inp), 32))
+        assert st[0] == 0
+        assert ints(out)[0] == want, inp
+    # reference fixed input, hash/native/bn254/poseidon/poseidon_test.go:39
+    out, _ = engine.poseidon_hash(elems([297262668938251460872476410954775437897592223497]).reshape(1, 1, 32))
+    assert ints(out)[0] == 21099541378821686330832093407308585959971016892597585818017774528142419287929
+
+
+@pytest.mark.parametrize("arity", list(range(1, 17)))
+def test_hash_matches_oracle_all_arities(engine, arity):
+    rng = random.Random(0xB200 + arity)
+    n = 64 if arity <= 3 else 16
+    rows = [[rng.randrange(R) for _ in range(arity)] for _ in range(n)]
+    rows[0] = [0] * arity
+    rows[1] = [R - 1] * arity
+    rows[2] = list(range(1, arity + 1))
+    out, st = engine.poseidon_hash(elems([x for r in rows for x in r]).reshape(n, arity, 32))
+    assert not st.any()
+    assert ints(out) == [opos.hash(r) for r in rows]
+
+
+def test_config1_batch_1024_two_inputs(engine):
+    """BASELINE config 1: 1024 two-input hashes (the Hash2 shape of the SMT path)."""
+    rng = random.Random(0xB200)
+    rows = [[rng.randrange(R), rng.randrange(R)] for _ in range(1024)]
+    out, st = engine.poseidon_hash(elems([x for r in rows for x in r]).reshape(1024, 2, 32))
+    assert not st.any()
+    assert ints(out) == [opos.hash(r) for r in rows]
+
+
+def test_noncanonical_input_sets_status(engine):
+    rows = [[1, 2], [R, 5], [3, 2**256 - 1], [7, 8]]
+    out, st = engine.poseidon_hash(elems([x for r in rows for x in r]).reshape(4, 2, 32))
+    assert list(st) == [0, 1, 1, 0]
+    got = ints(out)
+    assert got[0] == opos.hash([1, 2]) and got[3] == opos.hash([7, 8])
+    assert got[1] == 0 and got[2] == 0
+
+
+def test_bad_arity_is_an_error(engine):
+    import gnark_crypto_primitives_b200 as g
+
+    with pytest.raises(g.EngineError) as e:
+        engine.poseidon_hash(np.zeros((2, 17, 32), dtype=np.uint8))
+    assert "bad inputs provided" in str(e.value)  # poseidon.go:41-43
+    with pytest.raises(g.EngineError):
+        engine.poseidon_multihash(np.zeros((1, 4097, 32), dtype=np.uint8))
+    out, st = engine.poseidon_hash(np.zeros((0, 2, 32), dtype=np.uint8))
+    assert out.shape == (0, 32)
+
+
+@pytest.mark.parametrize("length", [1, 16, 17, 32, 33, 60, 255, 256, 257, 300])
+def test_multihash_matches_oracle(engine, length):
+    rng = random.Random(length)
+    n = 3
+    rows = [[rng.randrange(R) for _ in range(length)] for _ in range(n)]
+    rows[0] = list(range(1, length + 1))
+    out, st = engine.poseidon_multihash(elems([x for r in rows for x in r]).reshape(n, length, 32))
+    assert not st.any()
+    assert ints(out) == [opos.multihash(r) for r in rows]
+
+
+def test_multihash_1_to_60_regression(engine):
+    # inputs of hash/emulated/bn254/poseidon/poseidon_test.go:85-88
+    out, _ = engine.poseidon_multihash(elems(range(1, 61)).reshape(1, 60, 32))
+    assert ints(out)[0] == 10383247944466245790564312669548703973436539043614368627989218605970689057797
+
+
+def test_multihash_4096(engine):
+    rng = random.Random(4096)
+    row = [rng.randrange(R) for _ in range(4096)]
+    out, st = engine.poseidon_multihash(elems(row).reshape(1, 4096, 32))
+    assert ints(out)[0] == opos.multihash(row)
+
+
+def test_montgomery_format_roundtrip(engine):
+    """GCP_FMT_MONTGOMERY takes gnark-crypto fr.Element memory (x * 2^256 mod r) and returns the same form."""
+    import gnark_crypto_primitives_b200 as g
+
+    rng = random.Random(5)
+    rows = [[rng.randrange(R), rng.randrange(R)] for _ in range(33)]
+    mont = [[x * (1 << 256) % R for x in r] for r in rows]
+    out, st = engine.poseidon_hash(elems([x for r in mont for x in r]).reshape(33, 2, 32), fmt=g.FMT_MONTGOMERY)
+    assert not st.any()
+    rinv = pow(1 << 256, -1, R)
+    assert [v * rinv % R for v in ints(out)] == [opos.hash(r) for r in rows]
