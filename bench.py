@@ -1,0 +1,357 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the B200 batch engine.
+
+Workload (BASELINE.json configs[1]): arbo/circomlib SMT inclusion-proof verification, 160-level Poseidon
+tree, 2^20 synthetic "dense" proofs per GPU (siblings[0..158] non-zero, siblings[159] = 0,
+every 16th proof corrupted).  A step = one pass of the verifier over the whole batch.
+
+  python bench.py --gpus N --steps K --warmup W            # N > 1: launched under torchrun, one rank per GPU
+  python bench.py --impl reference ...                      # CPU arm: oracle/c port of the reference on host cores
+
+Prints ONE JSON line (rank 0).  `value` = proofs/s with inputs resident in HBM (CUDA events, max over ranks);
+`e2e` = the same metric through the host-buffer C ABI (gcp_smt_verify_inclusion) with pinned host buffers,
+H2D and D2H copies inside the timed region.  `roofline` is against the integer-multiply pipe measured live by
+gcp_probe_imad_wide (this path is integer-compute-bound); the HBM view is in `roofline.hbm`.
+oracle/ is used here only as the checker (sampled parity) and as the measured CPU baseline.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_LEVELS = 160
+METRIC = "smt_inclusion_proofs_per_s"
+UNIT = "proofs/s"
+# executed work model of the kernels (DESIGN.md "Kernels"): 32x32->64 multiply-adds per hash
+W_MUL, W_DOT3, W_DOT4, W_REDC = 64, 64, 64, 64
+FR_MUL_WIDE = 128       # 64 (a*b) + 64 (m*p) IMAD.WIDE.U32; + 8 IMAD (m = t*n') counted separately as half-rate-free
+# reference field-mul counts: 594 per Hash2, 772 per Hash1
+REF_MULS_T3, REF_MULS_T4 = 594, 772
+
+
+def wide_per_hash(t, rp):
+    """IMAD.WIDE.U32 executed per permutation by poseidon_permute_const<T> (fr.cuh / poseidon.cuh)."""
+    full_sigma = 8 * t * 3 * FR_MUL_WIDE                 # 8 full rounds, x^5 = 3 multiplies
+    dense_mix = 7 * t * (t * 64 + 64) + (t * 64 + 64)    # 7 matrix mixes + last column, lazy dot: t*64 + one reduction
+    partial = rp * (3 * FR_MUL_WIDE + (t * 64 + 64) + (t - 1) * FR_MUL_WIDE)
+    return full_sigma + dense_mix + partial
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log2-proofs", type=int, default=20, help="proofs per GPU per step (default 2^20)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------
+# synthetic inputs (device side, seeded)
+# ------------------------------------------------------------------------------------------------------
+def rand_elems(torch, n, gen, nonzero=False):
+    """n canonical field elements as (n, 8) int32 limbs: uniform below 2^252 (< r)."""
+    lo = torch.randint(0, 2 ** 31 - 1, (n, 8), dtype=torch.int32, device="cuda", generator=gen)
+    hi = torch.randint(0, 2, (n, 8), dtype=torch.int32, device="cuda", generator=gen)
+    x = lo | (hi << 31)
+    x[:, 7] &= 0x0FFFFFFF
+    if nonzero:
+        x[:, 0] |= 1
+    return x
+
+
+def make_batch(torch, eng, n, seed):
+    """Dense distribution; roots come from one untimed engine pass (out_roots), then every 16th proof is corrupted."""
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(seed)
+    sib = rand_elems(torch, n * N_LEVELS, gen, nonzero=True).view(n, N_LEVELS, 8)
+    sib[:, N_LEVELS - 1, :] = 0
+    keys = rand_elems(torch, n, gen)
+    keys[:, 5:] = 0                                   # key < 2^160
+    vals = rand_elems(torch, n, gen)
+    roots = torch.zeros((n, 8), dtype=torch.int32, device="cuda")
+    flags = torch.empty(n, dtype=torch.uint8, device="cuda")
+    status = torch.empty(n, dtype=torch.uint8, device="cuda")
+    tmp_roots = torch.empty((n, 8), dtype=torch.int32, device="cuda")
+    eng.smt_verify_dev(N_LEVELS, n, roots, False, sib, keys, vals, flags, status, d_out_roots=tmp_roots,
+                       stream=torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    roots.copy_(tmp_roots)
+    bad = torch.arange(0, n, 16, device="cuda")
+    kind = bad % 4
+    roots[bad[kind == 0], 0] ^= 1                                          # wrong root
+    sib[bad[kind == 1], 7, 1] ^= 4                                         # one sibling changed
+    vals[bad[kind == 2], 0] ^= 2                                           # wrong value
+    sib[bad[kind == 3], N_LEVELS - 1, 0] = 5                               # siblings[n-1] != 0
+    expect = torch.ones(n, dtype=torch.uint8, device="cuda")
+    expect[bad] = 0
+    return dict(sib=sib, keys=keys, vals=vals, roots=roots, flags=flags, status=status, expect=expect)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU every 200 ms while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+                getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+            }
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            while not self._stop_evt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = get_reasons(h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                self._stop_evt.wait(0.2)
+        except Exception as exc:  # clocks are evidence, not a dependency
+            self.reasons.add(f"sampler_error:{type(exc).__name__}")
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm / baseline: the oracle's C port of the reference path, literal (hashes all 160 levels + 2 leaves)
+# ------------------------------------------------------------------------------------------------------
+def cpu_sample_inputs(n, seed):
+    rng = np.random.default_rng(seed)
+    sib = rng.integers(0, 256, size=(n, N_LEVELS, 32), dtype=np.uint8)
+    sib[:, :, 31] &= 0x0F
+    sib[:, :, 0] |= 1
+    sib[:, N_LEVELS - 1, :] = 0
+    keys = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    keys[:, 20:] = 0
+    vals = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    vals[:, 31] &= 0x0F
+    roots = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    roots[:, 31] &= 0x0F
+    return roots, sib, keys, vals
+
+
+def run_cpu(n, threads, seed=7):
+    from oracle import cport
+    roots, sib, keys, vals = cpu_sample_inputs(n, seed)
+    t0 = time.perf_counter()
+    cport.smt_verify(roots, sib, keys, vals, literal=True, threads=threads)
+    return n / (time.perf_counter() - t0)
+
+
+def reference_arm(args):
+    from oracle import cport
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = cport.default_threads()
+    n = 1 << 13                                     # bounded sample of the same workload per step
+    run_cpu(256, threads)                           # page the library in
+    for _ in range(args.warmup):
+        run_cpu(n, threads)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        run_cpu(n, threads, seed=100 + s)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    sample = f"{n} dense 160-level proofs per step (literal gadget schedule: 160 Hash2 + 2 Hash1 per proof)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64 (4x64-bit Montgomery limbs, BN254 Fr)", "data": "synthetic",
+        "config": {"workload": "smt_inclusion_dense_160_levels", "n_levels": N_LEVELS, "proofs_per_step": n,
+                   "note": "Go reference cannot run here (no toolchain); this is oracle/c, a C port of its plain-field path"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import gnark_crypto_primitives_b200 as g
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(0)
+    dev_index = torch.cuda.current_device()
+    eng = g.Engine(dev_index)
+    n = 1 << args.log2_proofs
+    stream = torch.cuda.current_stream()
+
+    batch = make_batch(torch, eng, n, seed=0xB200 + rank)
+
+    def step():
+        eng.smt_verify_dev(N_LEVELS, n, batch["roots"], False, batch["sib"], batch["keys"], batch["vals"],
+                           batch["flags"], batch["status"], stream=stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    peak_wide = eng.probe_imad_wide()               # roofline denominator, measured on this GPU now
+    for _ in range(max(args.warmup, 0)):
+        step()
+    barrier()
+    sampler = ClockSampler(dev_index)
+    sampler.start()
+    launches0 = eng.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    launches = eng.launch_count - launches0
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * n / (ms_step * 1e-3)
+
+    # correctness of what was timed: flags vs the construction, and a sample vs the oracle
+    ok_flags = bool((batch["flags"] == batch["expect"]).all().item()) and not bool(batch["status"].any().item())
+    parity = None
+    if rank == 0:
+        from oracle import cport
+        idx = torch.arange(0, n, max(1, n // 96), device="cuda")[:96]
+        f, s, _ = cport.smt_verify(batch["roots"][idx].cpu().numpy().view(np.uint8),
+                                   batch["sib"][idx].cpu().numpy().view(np.uint8).reshape(len(idx), N_LEVELS, 32),
+                                   batch["keys"][idx].cpu().numpy().view(np.uint8),
+                                   batch["vals"][idx].cpu().numpy().view(np.uint8), literal=True,
+                                   threads=cport.default_threads())
+        parity = bool((f == batch["flags"][idx].cpu().numpy()).all() and (s == batch["status"][idx].cpu().numpy()).all())
+
+    # ---- end-to-end through the host-buffer C ABI, pinned host memory --------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h = {k: torch.empty(batch[k].shape, dtype=batch[k].dtype).pin_memory() for k in ("sib", "keys", "vals", "roots")}
+        for k in h:
+            h[k].copy_(batch[k])
+        torch.cuda.synchronize()
+        hn = {k: v.numpy().view(np.uint8).reshape(v.shape[:-1] + (32,)) for k, v in h.items()}
+        out_flags = torch.empty(n, dtype=torch.uint8).pin_memory().numpy()
+        out_status = torch.empty(n, dtype=torch.uint8).pin_memory().numpy()
+        lib, hctx = eng._lib, eng._h
+
+        def e2e_step():
+            rc = lib.gcp_smt_verify_inclusion(hctx, N_LEVELS, n, hn["roots"].ctypes.data, 0, hn["sib"].ctypes.data,
+                                              hn["keys"].ctypes.data, hn["vals"].ctypes.data, out_flags.ctypes.data,
+                                              out_status.ctypes.data, None, g.FMT_CANONICAL)
+            if rc != 0:
+                raise RuntimeError(lib.gcp_last_error(hctx))
+
+        e2e_step()                                  # warm: device pools allocate on first use
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 2))
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h2d = n * (N_LEVELS + 3) * 32
+        d2h = 2 * n
+        e2e = {"value": world * n * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "steps": e2e_steps, "flags_ok": bool((out_flags == batch["expect"].cpu().numpy()).all())}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample) -----------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import cport
+        threads = cport.default_threads()
+        run_cpu(256, threads)
+        m = 1 << 14
+        v = run_cpu(m, threads)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"{m} dense 160-level proofs, literal gadget schedule (160 Hash2 + 2 Hash1 each), oracle/c on all host cores"}
+
+    if rank == 0:
+        w3 = wide_per_hash(3, 57)
+        w4 = wide_per_hash(4, 56)
+        wide_per_proof = (N_LEVELS - 1) * (w3 + FR_MUL_WIDE) + w4 + 4 * FR_MUL_WIDE   # + to/from Montgomery conversions
+        achieved = wide_per_proof * n / (ms_step * 1e-3)                               # per GPU
+        alg_bytes = n * ((N_LEVELS + 3) * 32 + 2)
+        hbm_peak = 6550.1
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                hbm_peak = float(json.load(fh)["hbm_gbs"])
+            hbm_src = "MEASURED_PEAKS.json"
+        except Exception:
+            hbm_src = "fallback"
+        roofline = {
+            "bound": "int-pipe", "achieved": achieved / 1e12, "peak": peak_wide / 1e12, "unit": "T IMAD.WIDE.U32/s",
+            "frac": achieved / peak_wide if peak_wide else None, "traffic": None,
+            "peak_source": "gcp_probe_imad_wide, measured in this run (32 lanes/clk/SM)",
+            "kernel": "smt_path_kernel", "wide_mul_per_proof": wide_per_proof,
+            "useful_fr_mul_per_proof_reference": (N_LEVELS - 1) * REF_MULS_T3 + REF_MULS_T4,
+            "hbm": {"bound": "hbm", "achieved": alg_bytes / (ms_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": alg_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                    "algorithmic_bytes_per_launch": alg_bytes},
+        }
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 (8x32-bit Montgomery limbs, BN254 Fr)", "data": "synthetic",
+            "config": {"workload": "smt_inclusion_dense_160_levels", "n_levels": N_LEVELS, "proofs_per_gpu": n,
+                       "distribution": "dense: 159 non-zero siblings, every 16th proof corrupted", "parallelism":
+                       f"{world} x independent shards, no data-path collective", "l2": "inputs (5.5 GB per GPU) exceed L2"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu_baseline, "checks": {"flags_match_construction": ok_flags, "sample_matches_oracle": parity},
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()

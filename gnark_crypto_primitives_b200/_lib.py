@@ -35,6 +35,7 @@ SIGNATURES = {
     "gcp_last_error": (c_char_p, [c_void_p]),
     "gcp_ctx_device": (c_int, [c_void_p]),
     "gcp_ctx_launch_count": (c_uint64, [c_void_p]),
+    "gcp_probe_imad_wide": (c_int, [c_void_p, POINTER(ctypes.c_double)]),
     "gcp_poseidon_hash": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_int]),
     "gcp_poseidon_hash_dev": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_int, c_void_p]),
     "gcp_poseidon_multihash": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_int]),

@@ -204,6 +204,36 @@ int gcp_ctx_create(int device, const char* constants_path, gcp_ctx** out) {
   return GCP_OK;
 }
 
+int gcp_probe_imad_wide(gcp_ctx* ctx, double* wide_mul_per_s) {
+  if (!ctx || !wide_mul_per_s) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  int sms = 0;
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device), "device attribute");
+  const int blocks = sms * 8;
+  u32* d_out = (u32*)ctx->buf(42, (size_t)blocks * 256 * 4);
+  if (!d_out) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+  cudaStream_t st = ctx->stream[0];
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0), "event");
+  CU(cudaEventCreate(&e1), "event");
+  double best = 0;
+  for (int it = 0; it < 6; it++) {  // first launches warm the clocks up
+    CU(cudaEventRecord(e0, st), "event record");
+    double ops = launch_imad_probe(d_out, blocks, 17u + it, st);
+    ctx->launches++;
+    CU(cudaEventRecord(e1, st), "event record");
+    CU(cudaEventSynchronize(e1), "imad probe kernel");
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1), "event elapsed");
+    if (it >= 2 && ms > 0) best = std::max(best, ops / (ms * 1e-3));
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *wide_mul_per_s = best;
+  return GCP_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Poseidon
 // ---------------------------------------------------------------------------------------------------

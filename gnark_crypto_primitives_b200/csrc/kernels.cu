@@ -33,6 +33,44 @@ cudaError_t upload_const_tables(const u32* d_t3, const u32* d_t4, cudaStream_t s
   return cudaMemcpyToSymbolAsync(c_pos4, d_t4, sizeof(u32) * POS4_ELEMS * 8, 0, cudaMemcpyDeviceToDevice, stream);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Integer-pipe probe: the multiplier's row primitive (4 IMAD.WIDE.U32[.X] + carry capture) on 8 independent
+// accumulator sets per thread, no memory traffic.  Its rate is the roofline denominator bench.py reports against
+// (same measurement as bench_micro/imad_peak.cu, "chain4").
+// ---------------------------------------------------------------------------------------------------
+constexpr int PROBE_ITERS = 2048;
+constexpr int PROBE_CHAINS = 4;
+__global__ void __launch_bounds__(256) imad_probe_kernel(u32* out, u32 seed) {
+  u64 acc[PROBE_CHAINS][4];
+  u32 kc[PROBE_CHAINS];
+  u32 x0 = seed * 2654435761u + threadIdx.x, x1 = x0 ^ 0x9e3779b9u, x2 = x0 + 0x7f4a7c15u, x3 = ~x0;
+#pragma unroll
+  for (int c = 0; c < PROBE_CHAINS; c++) {
+    kc[c] = 0;
+#pragma unroll
+    for (int p = 0; p < 4; p++) acc[c][p] = ((u64)(blockIdx.x + c) << 32) | (threadIdx.x * 4 + p);
+  }
+#pragma unroll 1
+  for (int it = 0; it < PROBE_ITERS; it++) {
+#pragma unroll
+    for (int rep = 0; rep < 4; rep++) {
+#pragma unroll
+      for (int c = 0; c < PROBE_CHAINS; c++) chain4(acc[c][0], acc[c][1], acc[c][2], acc[c][3], kc[c], x0, x1, x2, x3, lo32(acc[c][rep]));
+    }
+  }
+  u32 r = 0;
+#pragma unroll
+  for (int c = 0; c < PROBE_CHAINS; c++) r ^= kc[c] ^ lo32(acc[c][0]) ^ hi32(acc[c][1]) ^ lo32(acc[c][2]) ^ hi32(acc[c][3]);
+  out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+// returns the number of wide multiplies one launch executes
+double launch_imad_probe(u32* d_out, int blocks, u32 seed, cudaStream_t stream) {
+  imad_probe_kernel<<<blocks, 256, 0, stream>>>(d_out, seed);
+  return (double)blocks * 256.0 * PROBE_ITERS * 4 * PROBE_CHAINS * 4;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Poseidon batch kernels.  One thread per hash.
 // Addressing (in elements): input j of hash (item, chunk) at in[item*in_item_stride + chunk*in_chunk_stride + j],

@@ -55,6 +55,7 @@ cudaError_t launch_poseidon(const PoseidonTable& tab, const u32* in, u32* out, u
                             int chunks_per_item, size_t in_item_stride, size_t in_chunk_stride,
                             size_t out_item_stride, int in_mont, int out_mont, int final_level,
                             cudaStream_t stream);
+double launch_imad_probe(u32* d_out, int blocks, u32 seed, cudaStream_t stream);
 cudaError_t launch_smt_verify(const SmtArgs& a, cudaStream_t stream);
 
 }  // namespace gcp

@@ -112,6 +112,12 @@ class Engine:
             return c_void_p(stream)
         return c_void_p(stream.cuda_stream)  # torch.cuda.Stream
 
+    def probe_imad_wide(self) -> float:
+        """Sustained IMAD.WIDE.U32 multiply-adds per second on this GPU (roofline denominator)."""
+        v = ctypes.c_double(0.0)
+        self._check(self._lib.gcp_probe_imad_wide(self._h, ctypes.byref(v)))
+        return float(v.value)
+
     # -- Poseidon -----------------------------------------------------------------------------------
     def poseidon_hash(self, inputs, fmt=FMT_CANONICAL):
         """inputs: (n, arity, 32) uint8 -> (digests (n, 32) uint8, status (n,) uint8).  poseidon.go:38-45."""

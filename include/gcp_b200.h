@@ -63,6 +63,10 @@ int gcp_ctx_device(const gcp_ctx* ctx);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 uint64_t gcp_ctx_launch_count(const gcp_ctx* ctx);
 
+/* Measures this GPU's integer-multiply pipe: sustained 32x32+64 multiply-adds per second (IMAD.WIDE.U32 carry
+ * chains, the multiplier's own row primitive, no memory traffic).  bench.py uses it as the roofline denominator. */
+int gcp_probe_imad_wide(gcp_ctx* ctx, double* wide_mul_per_s);
+
 /* ---- Poseidon: hash/native/bn254/poseidon/poseidon.go ------------------------------------------- */
 /* poseidon.Hash (poseidon.go:38-45, Sum :116-183): n independent hashes of `arity` inputs each.
  * in: n*arity elements, out: n elements.  arity outside 1..16 -> GCP_ERR_BAD_ARG ("bad inputs provided"). */

@@ -1,0 +1,47 @@
+"""CPU: the C-ABI library loads and exports every symbol include/gcp_b200.h declares (no compute calls)."""
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "gcp_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gcp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gnark_crypto_primitives_b200 import _lib, build
+
+    build.build_library()
+    lib = _lib.load()
+    names = declared_symbols()
+    assert len(names) >= 14
+    for name in names:
+        assert hasattr(lib, name), name
+        assert name in _lib.SIGNATURES, f"{name} missing from the ctypes signature table"
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_no_device_is_a_loud_error():
+    import gnark_crypto_primitives_b200 as g
+    from gnark_crypto_primitives_b200 import _lib
+
+    lib = _lib.load()
+    if lib.gcp_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(g.EngineError) as e:
+        g.Engine(0)
+    assert e.value.code == _lib.GCP_ERR_NO_DEVICE and "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_oracle():
+    """The product path may not import, link or execute anything under oracle/ (comments may mention it)."""
+    pkg = ROOT / "gnark_crypto_primitives_b200"
+    pat = re.compile(r"^\s*(from\s+oracle|import\s+oracle)|liboracle|oracle_[a-z_]+\s*\(|cport", re.M)
+    for path in list(pkg.glob("*.py")) + list((pkg / "csrc").glob("*")):
+        if path.suffix in (".py", ".cu", ".cuh", ".h"):
+            assert not pat.search(path.read_text()), path
