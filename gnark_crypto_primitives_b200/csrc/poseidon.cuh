@@ -53,6 +53,24 @@ __device__ __forceinline__ void sigma(u32 (&x)[8]) {
 
 // Register-resident permutation for small T with tables in constant memory.
 // in/out: lazy Montgomery. s[0] must be the capacity element (0).
+//
+// Code-size discipline: the whole permutation is ONE loop over the 8 + RP rounds and contains exactly three
+// multiplier bodies - (a) the S-box multiply, run 3x per element, (b) one lazy dot-product row (T products + one
+// reduction), run T times per full round and once per partial round, (c) the rank-1 update multiply of the
+// partial rounds.  Elements are brought to position 0 by rotating the register file instead of unrolling over
+// the state index.  The first version unrolled every round body (~260 KB of SASS) and was bound by instruction
+// fetch (ncu: stall_no_instruction, icc hit rate 89 %); this one is ~20 KB and stays in the instruction cache.
+template <int T>
+__device__ __forceinline__ void rotate_left(u32 (&s)[T][8]) {
+#pragma unroll
+  for (int l = 0; l < 8; l++) {
+    u32 t0 = s[0][l];
+#pragma unroll
+    for (int j = 0; j + 1 < T; j++) s[j][l] = s[j + 1][l];
+    s[T - 1][l] = t0;
+  }
+}
+
 template <int T>
 __device__ __forceinline__ void poseidon_permute_const(u32 (&s)[T][8], u32 (&out)[8]) {
   constexpr int RP = ConstTab<T>::RP;
@@ -60,6 +78,7 @@ __device__ __forceinline__ void poseidon_permute_const(u32 (&s)[T][8], u32 (&out
   const u32* S = C + (8 * T + RP) * 8;
   const u32* M = S + (2 * T - 1) * RP * 8;
   const u32* P = M + T * T * 8;
+  const u32 P2[8] = GCP_2P_LIMBS;
   u32 cst[8];
 
   // ark(C, 0)
@@ -69,82 +88,84 @@ __device__ __forceinline__ void poseidon_permute_const(u32 (&s)[T][8], u32 (&out
     fr_add(s[j], s[j], cst);
   }
 
-  // full rounds: sigma, ark, mix(mat)
-  auto full_round = [&](const u32* crow, const u32* mat) {
+  u32 n[T][8];
+#pragma unroll 1
+  for (int r = 0; r < 8 + RP; r++) {
+    const bool full = (r < 4) || (r >= 4 + RP);
+    const bool last = (r == 7 + RP);
+    // round constants added after the S-box: full rounds c[(r+1)T + j] (first half), c[(r+1)T + RP - ... ] (second
+    // half, poseidon.go:172), partial rounds c[5T + (r-4)] (poseidon.go:154); none in the last round.
+    const u32* crow = (r < 4) ? C + (r + 1) * T * 8 : (full ? C + ((r - RP + 1) * T + RP) * 8 : C + (5 * T + (r - 4)) * 8);
+    const int nsig = full ? T : 1;
+#pragma unroll 1
+    for (int k = 0; k < nsig; k++) {
+      // (a) S-box on s[0]: y = x*x, y = y*y, y = y*x   (poseidon.go:199-203)
+      u32 y[8];
 #pragma unroll
-    for (int j = 0; j < T; j++) {
-      sigma(s[j]);
-      load_const(cst, crow + j * 8);
-      fr_add(s[j], s[j], cst);
+      for (int l = 0; l < 8; l++) y[l] = s[0][l];
+#pragma unroll 1
+      for (int it = 0; it < 3; it++) {
+        u32 b[8];
+#pragma unroll
+        for (int l = 0; l < 8; l++) b[l] = (it < 2) ? y[l] : s[0][l];
+        fr_mul(y, y, b);
+      }
+      if (!last) {
+        load_const(cst, crow + k * 8);
+        fr_add(y, y, cst);
+      }
+#pragma unroll
+      for (int l = 0; l < 8; l++) s[0][l] = y[l];
+      if (full) rotate_left<T>(s);
     }
-    u32 n[T][8];
-#pragma unroll
-    for (int i = 0; i < T; i++) {
+    // (b) matrix rows as lazy dot products: full rounds n_i = sum_j m[j][i] s_j (M, or P after round 3), the last
+    // round only column 0; partial rounds the single row n = sum_j S[(2T-1)pr + j] s_j.
+    const u32* coef = full ? ((r == 3) ? P : M) : S + (2 * T - 1) * (r - 4) * 8;
+    const int jstride = full ? T * 8 : 8;
+    const int nrows = (full && !last) ? T : 1;
+#pragma unroll 1
+    for (int i = 0; i < nrows; i++) {
       Wide w;
       wide_zero(w);
 #pragma unroll
       for (int j = 0; j < T; j++) {
-        load_const(cst, mat + (j * T + i) * 8);
+        load_const(cst, coef + j * jstride + i * 8);
         wide_mac(w, s[j], cst);
       }
-      wide_redc(w, n[i]);
-      const u32 P2[8] = GCP_2P_LIMBS;
-      cond_sub(n[i], P2);
+      rotate_left<T>(n);
+      wide_redc(w, n[T - 1]);
+      cond_sub(n[T - 1], P2);
     }
+    if (full) {
+      if (!last) {
 #pragma unroll
-    for (int i = 0; i < T; i++)
+        for (int j = 0; j < T; j++)
 #pragma unroll
-      for (int l = 0; l < 8; l++) s[i][l] = n[i][l];
-  };
-
+          for (int l = 0; l < 8; l++) s[j][l] = n[j][l];
+      }
+    } else {
+      // (c) s_k += s_0 * S[(2T-1)pr + T + k - 1], k = 1..T-1, with the post-S-box s_0 (poseidon.go:162-164)
+      const u32* srow = S + ((2 * T - 1) * (r - 4) + T) * 8;
+      u32 s0[8];
+#pragma unroll
+      for (int l = 0; l < 8; l++) {
+        s0[l] = s[0][l];
+        s[0][l] = n[T - 1][l];
+      }
+      rotate_left<T>(s);  // s = (s_1, ..., s_{T-1}, n0)
 #pragma unroll 1
-  for (int r = 0; r < 3; r++) full_round(C + (r + 1) * T * 8, M);
-  full_round(C + 4 * T * 8, P);
-
-  // partial rounds
-#pragma unroll 1
-  for (int r = 0; r < RP; r++) {
-    sigma(s[0]);
-    load_const(cst, C + (5 * T + r) * 8);
-    fr_add(s[0], s[0], cst);
-    const u32* srow = S + (2 * T - 1) * r * 8;
-    Wide w;
-    wide_zero(w);
-#pragma unroll
-    for (int j = 0; j < T; j++) {
-      load_const(cst, srow + j * 8);
-      wide_mac(w, s[j], cst);
+      for (int k = 1; k < T; k++) {
+        u32 prod[8];
+        load_const(cst, srow + (k - 1) * 8);
+        fr_mul(prod, s0, cst);
+        fr_add(s[0], s[0], prod);
+        rotate_left<T>(s);
+      }
+      // after T-1 more rotations: s = (n0, s_1', ..., s_{T-1}')
     }
-    u32 n0[8];
-    wide_redc(w, n0);
-    const u32 P2[8] = GCP_2P_LIMBS;
-    cond_sub(n0, P2);
-#pragma unroll
-    for (int k = 1; k < T; k++) {
-      load_const(cst, srow + (T + k - 1) * 8);
-      u32 prod[8];
-      fr_mul(prod, s[0], cst);
-      fr_add(s[k], s[k], prod);
-    }
-#pragma unroll
-    for (int l = 0; l < 8; l++) s[0][l] = n0[l];
   }
-
-#pragma unroll 1
-  for (int r = 0; r < 3; r++) full_round(C + ((5 + r) * T + RP) * 8, M);
-
-  // last: sigma all, out = column 0 of M
-  Wide w;
-  wide_zero(w);
 #pragma unroll
-  for (int j = 0; j < T; j++) {
-    sigma(s[j]);
-    load_const(cst, M + (j * T) * 8);
-    wide_mac(w, s[j], cst);
-  }
-  wide_redc(w, out);
-  const u32 P2[8] = GCP_2P_LIMBS;
-  cond_sub(out, P2);
+  for (int l = 0; l < 8; l++) out[l] = n[T - 1][l];
 }
 
 // Hash2 (tree/smt/hash.go:21-27): Poseidon(l, r), lazy Montgomery in and out.
