@@ -35,40 +35,55 @@ cudaError_t upload_const_tables(const u32* d_t3, const u32* d_t4, cudaStream_t s
 
 
 // ---------------------------------------------------------------------------------------------------
-// Integer-pipe probe: the multiplier's row primitive (4 IMAD.WIDE.U32[.X] + carry capture) on 8 independent
-// accumulator sets per thread, no memory traffic.  Its rate is the roofline denominator bench.py reports against
-// (same measurement as bench_micro/imad_peak.cu, "chain4").
+// Integer-pipe probe: carry-chained IMAD.WIDE.U32 / IMAD.WIDE.U32.X pairs on 8 independent accumulator sets per
+// thread, no memory traffic.  Its rate is the roofline denominator bench.py reports against (same measurement as
+// bench_micro/imad_peak.cu, "wide_cc_pair_chain": 32 lanes/clk/SM, about 9.0 T/s on a B200 at 1.9 GHz).
 // ---------------------------------------------------------------------------------------------------
-constexpr int PROBE_ITERS = 2048;
-constexpr int PROBE_CHAINS = 4;
+constexpr int PROBE_ITERS = 4096;
+constexpr int PROBE_CHAINS = 8;
 __global__ void __launch_bounds__(256) imad_probe_kernel(u32* out, u32 seed) {
-  u64 acc[PROBE_CHAINS][4];
-  u32 kc[PROBE_CHAINS];
-  u32 x0 = seed * 2654435761u + threadIdx.x, x1 = x0 ^ 0x9e3779b9u, x2 = x0 + 0x7f4a7c15u, x3 = ~x0;
+  // PROBE_CHAINS independent pairs of 64-bit accumulators; each step is IMAD.WIDE.U32 (carry out) followed by
+  // IMAD.WIDE.U32.X (carry in): exactly the two instruction forms the multiplier rows are made of.
+  u64 a0[PROBE_CHAINS], a1[PROBE_CHAINS];
+  u32 x = seed * 2654435761u + threadIdx.x, y = x ^ 0x9e3779b9u;
 #pragma unroll
   for (int c = 0; c < PROBE_CHAINS; c++) {
-    kc[c] = 0;
-#pragma unroll
-    for (int p = 0; p < 4; p++) acc[c][p] = ((u64)(blockIdx.x + c) << 32) | (threadIdx.x * 4 + p);
+    a0[c] = ((u64)(blockIdx.x + c) << 32) | (threadIdx.x * 4 + c);
+    a1[c] = a0[c] * 0x9e3779b97f4a7c15ull;
   }
 #pragma unroll 1
-  for (int it = 0; it < PROBE_ITERS; it++) {
+  for (int it = 0; it < PROBE_ITERS / 4; it++) {
 #pragma unroll
     for (int rep = 0; rep < 4; rep++) {
 #pragma unroll
-      for (int c = 0; c < PROBE_CHAINS; c++) chain4(acc[c][0], acc[c][1], acc[c][2], acc[c][3], kc[c], x0, x1, x2, x3, lo32(acc[c][rep]));
+      for (int c = 0; c < PROBE_CHAINS; c++) {
+        asm volatile(
+            "{\n\t"
+            ".reg .u32 l0, h0, l1, h1;\n\t"
+            "mov.b64 {l0, h0}, %0;\n\t"
+            "mov.b64 {l1, h1}, %1;\n\t"
+            "mad.lo.cc.u32 l0, h1, %2, l0;\n\t"
+            "madc.hi.cc.u32 h0, h1, %2, h0;\n\t"
+            "madc.lo.cc.u32 l1, l0, %3, l1;\n\t"
+            "madc.hi.u32 h1, l0, %3, h1;\n\t"
+            "mov.b64 %0, {l0, h0};\n\t"
+            "mov.b64 %1, {l1, h1};\n\t"
+            "}"
+            : "+l"(a0[c]), "+l"(a1[c])
+            : "r"(x), "r"(y));
+      }
     }
   }
   u32 r = 0;
 #pragma unroll
-  for (int c = 0; c < PROBE_CHAINS; c++) r ^= kc[c] ^ lo32(acc[c][0]) ^ hi32(acc[c][1]) ^ lo32(acc[c][2]) ^ hi32(acc[c][3]);
+  for (int c = 0; c < PROBE_CHAINS; c++) r ^= lo32(a0[c]) ^ hi32(a0[c]) ^ lo32(a1[c]) ^ hi32(a1[c]);
   out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
 // returns the number of wide multiplies one launch executes
 double launch_imad_probe(u32* d_out, int blocks, u32 seed, cudaStream_t stream) {
   imad_probe_kernel<<<blocks, 256, 0, stream>>>(d_out, seed);
-  return (double)blocks * 256.0 * PROBE_ITERS * 4 * PROBE_CHAINS * 4;
+  return (double)blocks * 256.0 * PROBE_ITERS * PROBE_CHAINS * 2;
 }
 
 // ---------------------------------------------------------------------------------------------------
