@@ -49,6 +49,16 @@ SIGNATURES = {
                                          c_void_p, c_void_p, c_void_p, c_int]),
     "gcp_smt_verify_exclusion": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    "gcp_elgamal_fixed_base_mul": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_int]),
+    "gcp_elgamal_fixed_base_mul_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_int, c_void_p]),
+    "gcp_elgamal_encrypt": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_int]),
+    "gcp_elgamal_encrypt_dev": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p,
+                                        c_int, c_void_p]),
+    "gcp_elgamal_add": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_int]),
+    "gcp_elgamal_add_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_int, c_void_p]),
+    "gcp_elgamal_neg": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_int]),
+    "gcp_elgamal_tally": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_int]),
+    "gcp_elgamal_tally_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_int, c_void_p]),
 }
 
 _lib = None

@@ -19,7 +19,7 @@ using namespace gcp;
 namespace {
 
 constexpr uint32_t BLOB_MAGIC = 0x32425350u;  // 'PSB2', written by oracle/gen_constants.py
-constexpr int N_SLOTS = 48;
+constexpr int N_SLOTS = 72;
 
 thread_local std::string g_create_error;
 
@@ -47,6 +47,16 @@ struct gcp_ctx {
     size_t cap = 0;
   } slot[N_SLOTS];
   uint64_t launches = 0;
+  int sm_count = 0;
+  // ElGamal: Niels tables of G and of the cached shared public key
+  u32* d_tabG = nullptr;
+  u32* d_tabPK = nullptr;
+  u32* d_fb_ext = nullptr;    // extended-coordinate scratch for table construction
+  u32* d_base_xy = nullptr;   // 16 words: base point being tabulated
+  u32* d_flagG = nullptr;     // 1 word
+  u32* d_flagPK = nullptr;    // 1 word: cached key is canonical and on the curve
+  unsigned char pk_cached[64];
+  int pk_cached_fmt = -1;     // -1: no key cached
 
   int fail(int code, const std::string& msg) {
     err = msg;
@@ -109,6 +119,8 @@ void gcp_ctx_destroy(gcp_ctx* ctx) {
   for (auto& b : ctx->slot)
     if (b.p) cudaFree(b.p);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
+  for (u32* p : {ctx->d_tabG, ctx->d_tabPK, ctx->d_fb_ext, ctx->d_base_xy, ctx->d_flagG, ctx->d_flagPK})
+    if (p) cudaFree(p);
   delete ctx;
 }
 
@@ -199,7 +211,26 @@ int gcp_ctx_create(int device, const char* constants_path, gcp_ctx** out) {
   }
   if ((e = upload_const_tables(ctx->tab[3].C, ctx->tab[4].C, ctx->stream[0])) != cudaSuccess)
     return bail(ctx->cuda_fail(e, "constant-memory upload"));
+  // fixed-base table of the generator G (elgamal/mul.go:26-72 restated with wider windows), built on the device
+  if ((e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess)
+    return bail(ctx->cuda_fail(e, "device attribute"));
+  if ((e = cudaMalloc(&ctx->d_tabG, fb_table_bytes())) != cudaSuccess ||
+      (e = cudaMalloc(&ctx->d_tabPK, fb_table_bytes())) != cudaSuccess ||
+      (e = cudaMalloc(&ctx->d_fb_ext, fb_ext_scratch_bytes())) != cudaSuccess ||
+      (e = cudaMalloc(&ctx->d_base_xy, 64)) != cudaSuccess || (e = cudaMalloc(&ctx->d_flagG, 4)) != cudaSuccess ||
+      (e = cudaMalloc(&ctx->d_flagPK, 4)) != cudaSuccess)
+    return bail(ctx->cuda_fail(e, "cudaMalloc fixed-base tables"));
+  if ((e = upload_generator(ctx->d_base_xy, ctx->stream[0])) != cudaSuccess ||
+      (e = launch_fb_table_build(ctx->d_base_xy, 0, ctx->d_fb_ext, ctx->d_tabG, ctx->d_flagG, ctx->stream[0])) != cudaSuccess)
+    return bail(ctx->cuda_fail(e, "fixed-base table build"));
+  ctx->launches += 3;
   if ((e = cudaStreamSynchronize(ctx->stream[0])) != cudaSuccess) return bail(ctx->cuda_fail(e, "ctx init sync"));
+  {
+    u32 flag = 0;
+    if ((e = cudaMemcpy(&flag, ctx->d_flagG, 4, cudaMemcpyDeviceToHost)) != cudaSuccess)
+      return bail(ctx->cuda_fail(e, "read generator flag"));
+    if (!flag) return bail(ctx->fail(GCP_ERR_CONSTANTS, "generator self-check failed (not on curve)"));
+  }
   *out = ctx;
   return GCP_OK;
 }
@@ -502,6 +533,263 @@ int gcp_smt_verify_exclusion(gcp_ctx* ctx, int n_levels, size_t n, const void* r
   std::vector<uint8_t> zeros(n * 32, 0);  // value = 0 in either element format
   return gcp_smt_verify(ctx, n_levels, n, roots, shared_root, siblings, old_keys, old_values, is_old0, keys, zeros.data(),
                         ones.data(), nullptr, out_flags, out_status, out_roots, fmt);
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// ElGamal
+// ---------------------------------------------------------------------------------------------------
+static int check_fmt(gcp_ctx* ctx, int fmt) {
+  if (fmt != GCP_FMT_CANONICAL && fmt != GCP_FMT_MONTGOMERY) return ctx->fail(GCP_ERR_BAD_ARG, "bad element format");
+  return GCP_OK;
+}
+
+// Make d_tabPK the table of the given shared public key (64 bytes, host or device memory).
+static int ensure_pk_table(gcp_ctx* ctx, const void* pk, bool pk_on_device, int fmt, cudaStream_t st) {
+  unsigned char host_pk[64];
+  if (pk_on_device) {
+    CU(cudaMemcpyAsync(host_pk, pk, 64, cudaMemcpyDeviceToHost, st), "D2H public key");
+    CU(cudaStreamSynchronize(st), "D2H public key");
+  } else {
+    memcpy(host_pk, pk, 64);
+  }
+  if (ctx->pk_cached_fmt == fmt && memcmp(host_pk, ctx->pk_cached, 64) == 0) return GCP_OK;
+  ctx->pk_cached_fmt = -1;
+  // the previous table may still be in use by work queued on the other stream
+  CU(cudaStreamSynchronize(ctx->stream[0]), "stream sync");
+  CU(cudaStreamSynchronize(ctx->stream[1]), "stream sync");
+  CU(cudaMemcpyAsync(ctx->d_base_xy, host_pk, 64, cudaMemcpyHostToDevice, st), "H2D public key");
+  CU(launch_fb_table_build(ctx->d_base_xy, fmt, ctx->d_fb_ext, ctx->d_tabPK, ctx->d_flagPK, st), "public-key table build");
+  ctx->launches += 3;
+  CU(cudaStreamSynchronize(st), "public-key table build");
+  memcpy(ctx->pk_cached, host_pk, 64);
+  ctx->pk_cached_fmt = fmt;
+  return GCP_OK;
+}
+
+static int fixed_base_dev_locked(gcp_ctx* ctx, const void* d_scalars, size_t n, void* d_out, uint8_t* d_status, int fmt,
+                                 cudaStream_t st, int xyz_slot) {
+  int rc = check_fmt(ctx, fmt);
+  if (rc != GCP_OK || n == 0) return rc;
+  if (!d_scalars || !d_out || !d_status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  u32* xyz = (u32*)ctx->buf(xyz_slot, n * 96);
+  if (!xyz) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+  CU(launch_fixed_base_mul(ctx->d_tabG, (const u32*)d_scalars, n, xyz, d_status, fmt, st), "fixed-base kernel");
+  CU(launch_normalize(xyz, n, (u32*)d_out, d_status, 1, fmt, st), "normalize kernel");
+  ctx->launches += 2;
+  return GCP_OK;
+}
+
+static int encrypt_dev_locked(gcp_ctx* ctx, const void* d_pk, int pk_per_item, const void* d_k, const void* d_m, size_t n,
+                              void* d_out, uint8_t* d_status, int fmt, cudaStream_t st, int xyz_slot) {
+  int rc = check_fmt(ctx, fmt);
+  if (rc != GCP_OK || n == 0) return rc;
+  if (!d_pk || !d_k || !d_m || !d_out || !d_status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  u32* xyz = (u32*)ctx->buf(xyz_slot, n * 192);
+  if (!xyz) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+  if (pk_per_item)
+    CU(launch_encrypt_per_key(ctx->d_tabG, (const u32*)d_pk, (const u32*)d_k, (const u32*)d_m, n, xyz, d_status, fmt, st),
+       "encrypt kernel");
+  else
+    CU(launch_encrypt_shared(ctx->d_tabG, ctx->d_tabPK, ctx->d_flagPK, (const u32*)d_k, (const u32*)d_m, n, xyz, d_status,
+                             fmt, st),
+       "encrypt kernel");
+  CU(launch_normalize(xyz, 2 * n, (u32*)d_out, d_status, 2, fmt, st), "normalize kernel");
+  ctx->launches += 2;
+  return GCP_OK;
+}
+
+static int add_dev_locked(gcp_ctx* ctx, const void* d_a, const void* d_b, size_t n, void* d_out, uint8_t* d_status,
+                          int fmt, cudaStream_t st, int xyz_slot) {
+  int rc = check_fmt(ctx, fmt);
+  if (rc != GCP_OK || n == 0) return rc;
+  if (!d_a || !d_b || !d_out || !d_status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  u32* xyz = (u32*)ctx->buf(xyz_slot, n * 192);
+  if (!xyz) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+  CU(cudaMemsetAsync(d_status, 0, n, st), "memset status");
+  CU(launch_ct_add((const u32*)d_a, (const u32*)d_b, n, xyz, d_status, fmt, st), "ciphertext add kernel");
+  CU(launch_normalize(xyz, 2 * n, (u32*)d_out, d_status, 2, fmt, st), "normalize kernel");
+  ctx->launches += 2;
+  return GCP_OK;
+}
+
+static int tally_dev_locked(gcp_ctx* ctx, const void* d_ct, size_t n_ballots, int n_fields, void* d_out,
+                            uint8_t* d_status, int fmt, cudaStream_t st, int slot_base) {
+  int rc = check_fmt(ctx, fmt);
+  if (rc != GCP_OK) return rc;
+  if (n_fields < 1 || n_fields > 64) return ctx->fail(GCP_ERR_BAD_ARG, "n_fields must be in [1, 64]");
+  if (!d_out || !d_status || (n_ballots && !d_ct)) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  int n_blocks = tally_max_blocks(n_ballots, n_fields, ctx->sm_count);
+  const int cols = n_fields * 2;
+  u32* partials = (u32*)ctx->buf(slot_base, (size_t)n_blocks * cols * 128);
+  u32* bad = (u32*)ctx->buf(slot_base + 1, (size_t)n_fields * 4);
+  u32* xyz = (u32*)ctx->buf(slot_base + 2, (size_t)cols * 96);
+  if (!partials || !bad || !xyz) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+  CU(launch_tally((const u32*)d_ct, n_ballots, n_fields, n_blocks, partials, bad, xyz, d_status, fmt, st), "tally kernels");
+  CU(launch_normalize(xyz, (size_t)cols, (u32*)d_out, d_status, 2, fmt, st), "normalize kernel");
+  ctx->launches += 3;
+  return GCP_OK;
+}
+
+int gcp_elgamal_fixed_base_mul_dev(gcp_ctx* ctx, const void* d_scalars, size_t n, void* d_out_points, uint8_t* d_status,
+                                   int fmt, void* stream) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  return fixed_base_dev_locked(ctx, d_scalars, n, d_out_points, d_status, fmt, (cudaStream_t)stream, 43);
+}
+
+int gcp_elgamal_encrypt_dev(gcp_ctx* ctx, const void* d_pub_key, int pk_per_item, const void* d_k, const void* d_m,
+                            size_t n, void* d_out_ct, uint8_t* d_status, int fmt, void* stream) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  if (n && !pk_per_item) {
+    if (!d_pub_key) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+    int rc = ensure_pk_table(ctx, d_pub_key, true, fmt, (cudaStream_t)stream);
+    if (rc != GCP_OK) return rc;
+  }
+  return encrypt_dev_locked(ctx, d_pub_key, pk_per_item, d_k, d_m, n, d_out_ct, d_status, fmt, (cudaStream_t)stream, 43);
+}
+
+int gcp_elgamal_add_dev(gcp_ctx* ctx, const void* d_a, const void* d_b, size_t n, void* d_out, uint8_t* d_status, int fmt,
+                        void* stream) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  return add_dev_locked(ctx, d_a, d_b, n, d_out, d_status, fmt, (cudaStream_t)stream, 43);
+}
+
+int gcp_elgamal_tally_dev(gcp_ctx* ctx, const void* d_ct, size_t n_ballots, int n_fields, void* d_out, uint8_t* d_status,
+                          int fmt, void* stream) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  return tally_dev_locked(ctx, d_ct, n_ballots, n_fields, d_out, d_status, fmt, (cudaStream_t)stream, 44);
+}
+
+// Generic host-buffer pipeline for the per-item ElGamal calls.
+//   kind 0: fixed-base (in0 = scalars 32 B)            -> 64 B
+//   kind 1: encrypt    (in0 = k 32 B, in1 = m 32 B, optional per-item pk 64 B) -> 128 B
+//   kind 2: add        (in0 = a 128 B, in1 = b 128 B)  -> 128 B
+//   kind 3: neg        (in0 = a 128 B)                 -> 128 B
+static int elgamal_host(gcp_ctx* ctx, int kind, const void* pk, int pk_per_item, const void* in0, const void* in1,
+                        size_t n, void* out, uint8_t* status, int fmt) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  int rc = check_fmt(ctx, fmt);
+  if (rc != GCP_OK || n == 0) return rc;
+  if (!in0 || !out || !status || ((kind == 1 || kind == 2) && !in1) || (kind == 1 && !pk))
+    return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  const size_t in0_b = (kind <= 1) ? 32 : 128, in1_b = (kind == 1) ? 32 : (kind == 2 ? 128 : 0);
+  const size_t out_b = (kind == 0) ? 64 : 128;
+  if (kind == 1 && !pk_per_item) {
+    rc = ensure_pk_table(ctx, pk, false, fmt, ctx->stream[0]);
+    if (rc != GCP_OK) return rc;
+  }
+  size_t chunk = std::min<size_t>(n, (size_t)1 << 20);
+  size_t k = 0;
+  for (size_t off = 0; off < n && rc == GCP_OK; off += chunk, k++) {
+    size_t m = std::min(chunk, n - off);
+    int s = (int)(k & 1);
+    cudaStream_t st = ctx->stream[s];
+    const int b = 48 + s * 8;
+    void* d0 = ctx->buf(b + 0, m * in0_b);
+    void* d1 = in1_b ? ctx->buf(b + 1, m * in1_b) : nullptr;
+    void* dpk = (kind == 1 && pk_per_item) ? ctx->buf(b + 2, m * 64) : nullptr;
+    void* dout = ctx->buf(b + 3, m * out_b);
+    uint8_t* dst = (uint8_t*)ctx->buf(b + 4, m);
+    if (!d0 || (in1_b && !d1) || (kind == 1 && pk_per_item && !dpk) || !dout || !dst)
+      return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+    CU(cudaMemcpyAsync(d0, (const char*)in0 + off * in0_b, m * in0_b, cudaMemcpyHostToDevice, st), "H2D");
+    if (in1_b) CU(cudaMemcpyAsync(d1, (const char*)in1 + off * in1_b, m * in1_b, cudaMemcpyHostToDevice, st), "H2D");
+    if (dpk) CU(cudaMemcpyAsync(dpk, (const char*)pk + off * 64, m * 64, cudaMemcpyHostToDevice, st), "H2D");
+    switch (kind) {
+      case 0: rc = fixed_base_dev_locked(ctx, d0, m, dout, dst, fmt, st, b + 5); break;
+      case 1: rc = encrypt_dev_locked(ctx, pk_per_item ? dpk : (const void*)ctx->d_base_xy, pk_per_item, d0, d1, m, dout, dst, fmt, st, b + 5); break;
+      case 2: rc = add_dev_locked(ctx, d0, d1, m, dout, dst, fmt, st, b + 5); break;
+      default:
+        CU(cudaMemsetAsync(dst, 0, m, st), "memset status");
+        CU(launch_ct_neg((const u32*)d0, m, (u32*)dout, dst, st), "neg kernel");
+        ctx->launches++;
+        break;
+    }
+    if (rc != GCP_OK) break;
+    CU(cudaMemcpyAsync((char*)out + off * out_b, dout, m * out_b, cudaMemcpyDeviceToHost, st), "D2H");
+    CU(cudaMemcpyAsync(status + off, dst, m, cudaMemcpyDeviceToHost, st), "D2H");
+  }
+  cudaError_t e0 = cudaStreamSynchronize(ctx->stream[0]);
+  cudaError_t e1 = cudaStreamSynchronize(ctx->stream[1]);
+  if (rc != GCP_OK) return rc;
+  if (e0 != cudaSuccess) return ctx->cuda_fail(e0, "stream sync");
+  if (e1 != cudaSuccess) return ctx->cuda_fail(e1, "stream sync");
+  return GCP_OK;
+}
+
+int gcp_elgamal_fixed_base_mul(gcp_ctx* ctx, const void* scalars, size_t n, void* out_points, uint8_t* status, int fmt) {
+  return elgamal_host(ctx, 0, nullptr, 0, scalars, nullptr, n, out_points, status, fmt);
+}
+int gcp_elgamal_encrypt(gcp_ctx* ctx, const void* pub_key, int pk_per_item, const void* k, const void* m, size_t n,
+                        void* out_ct, uint8_t* status, int fmt) {
+  return elgamal_host(ctx, 1, pub_key, pk_per_item, k, m, n, out_ct, status, fmt);
+}
+int gcp_elgamal_add(gcp_ctx* ctx, const void* a, const void* b, size_t n, void* out, uint8_t* status, int fmt) {
+  return elgamal_host(ctx, 2, nullptr, 0, a, b, n, out, status, fmt);
+}
+int gcp_elgamal_neg(gcp_ctx* ctx, const void* a, size_t n, void* out, uint8_t* status, int fmt) {
+  return elgamal_host(ctx, 3, nullptr, 0, a, nullptr, n, out, status, fmt);
+}
+
+// Tally over host-resident ciphertexts: chunks are reduced on the device as they arrive; the per-chunk partial
+// ciphertexts are themselves tallied at the end (addition is associative, so the result does not depend on chunking).
+int gcp_elgamal_tally(gcp_ctx* ctx, const void* ct, size_t n_ballots, int n_fields, void* out, uint8_t* status, int fmt) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  int rc = check_fmt(ctx, fmt);
+  if (rc != GCP_OK) return rc;
+  if (n_fields < 1 || n_fields > 64) return ctx->fail(GCP_ERR_BAD_ARG, "n_fields must be in [1, 64]");
+  if (!out || !status || (n_ballots && !ct)) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  const size_t ballot_b = (size_t)n_fields * 128;
+  size_t chunk = std::max<size_t>(1, std::min<size_t>(std::max<size_t>(n_ballots, 1), ((size_t)256 << 20) / ballot_b));
+  size_t n_chunks = n_ballots ? (n_ballots + chunk - 1) / chunk : 1;
+  u32* d_parts = (u32*)ctx->buf(64, n_chunks * ballot_b);
+  uint8_t* d_part_status = (uint8_t*)ctx->buf(65, n_chunks * n_fields);
+  void* d_out = ctx->buf(66, ballot_b);
+  uint8_t* d_status = (uint8_t*)ctx->buf(67, n_fields);
+  if (!d_parts || !d_part_status || !d_out || !d_status) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+  for (size_t c = 0; c < n_chunks; c++) {
+    size_t off = c * chunk, m = n_ballots ? std::min(chunk, n_ballots - off) : 0;
+    int s = (int)(c & 1);
+    cudaStream_t st = ctx->stream[s];
+    void* d_ct = ctx->buf(48 + s * 8, std::max<size_t>(m, 1) * ballot_b);
+    if (!d_ct) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+    if (m) CU(cudaMemcpyAsync(d_ct, (const char*)ct + off * ballot_b, m * ballot_b, cudaMemcpyHostToDevice, st), "H2D");
+    rc = tally_dev_locked(ctx, d_ct, m, n_fields, (char*)d_parts + c * ballot_b, d_part_status + c * n_fields, fmt, st,
+                          48 + s * 8 + 1);
+    if (rc != GCP_OK) return rc;
+  }
+  CU(cudaStreamSynchronize(ctx->stream[0]), "stream sync");
+  CU(cudaStreamSynchronize(ctx->stream[1]), "stream sync");
+  cudaStream_t st = ctx->stream[0];
+  if (n_chunks == 1) {
+    CU(cudaMemcpyAsync(out, d_parts, ballot_b, cudaMemcpyDeviceToHost, st), "D2H");
+    CU(cudaMemcpyAsync(status, d_part_status, n_fields, cudaMemcpyDeviceToHost, st), "D2H");
+    CU(cudaStreamSynchronize(st), "stream sync");
+    return GCP_OK;
+  }
+  rc = tally_dev_locked(ctx, d_parts, n_chunks, n_fields, d_out, d_status, fmt, st, 49);
+  if (rc != GCP_OK) return rc;
+  std::vector<uint8_t> part_status(n_chunks * n_fields);
+  CU(cudaMemcpyAsync(out, d_out, ballot_b, cudaMemcpyDeviceToHost, st), "D2H");
+  CU(cudaMemcpyAsync(status, d_status, n_fields, cudaMemcpyDeviceToHost, st), "D2H");
+  CU(cudaMemcpyAsync(part_status.data(), d_part_status, part_status.size(), cudaMemcpyDeviceToHost, st), "D2H");
+  CU(cudaStreamSynchronize(st), "stream sync");
+  for (size_t c = 0; c < n_chunks; c++)
+    for (int f = 0; f < n_fields; f++)
+      if (part_status[c * n_fields + f] && !status[f]) status[f] = part_status[c * n_fields + f];
+  return GCP_OK;
 }
 
 }  // extern "C"

@@ -1,0 +1,474 @@
+// ElGamal over the a = -1 BN254 twisted Edwards curve: fixed-base tables, encrypt, ciphertext add, tally.
+//
+// Values reproduced (file:line under /root/reference):
+//   FixedBaseScalarMulBN254  elgamal/mul.go:76-166   == [s]G for s in [0, r)  (64 4-bit windows over table
+//                            mul.go:26-72; zero nibbles skipped, window 0 initialises)
+//   (*Ciphertext).Encrypt    elgamal/encrypt.go:42-64  C1 = [k]G, C2 = [m]G + [k]PK, AssertIsOnCurve(PK)
+//   EncryptedZero            elgamal/encrypt.go:72-94  == Encrypt(k, 0)
+//   (*Ciphertext).Add        elgamal/ciphertext.go:24-32 component-wise curve.Add;  Neg :37-46
+//   tally                    left fold of Add from NewCiphertext (ciphertext.go:16-19) — caller's loop
+// All of these are group elements given by exact field arithmetic, so any addition order / window width yields
+// the same canonical affine coordinates.  This file uses WBITS-bit windows over precomputed Niels tables
+// (tab[w][d-1] = [d * 2^(WBITS*w)] B) for both G and a shared public key, accumulates in extended coordinates,
+// and converts to affine with chunked Montgomery batch inversion (one Fermat inversion per BATCH_INV points).
+#pragma once
+#include "edwards.cuh"
+#include "kernels.h"
+
+namespace gcp {
+
+constexpr int FB_WBITS = 8;
+constexpr int FB_WINDOWS = (256 + FB_WBITS - 1) / FB_WBITS;      // 32
+constexpr int FB_ENTRIES = (1 << FB_WBITS) - 1;                  // 255 non-identity digits
+constexpr size_t FB_TABLE_WORDS = (size_t)FB_WINDOWS * FB_ENTRIES * 24;  // u32 words per table (96 B entries)
+constexpr int BATCH_INV = 16;
+
+// ---- table construction (one-time per base point) ------------------------------------------------------
+// step 1: ext[w * FB_ENTRIES + 0] = [2^(WBITS*w)] B.  base: affine standard-form (x, y), 16 words.
+// flag[0] = 1 if B is on the curve and canonical, else 0.
+__global__ void fb_table_bases_kernel(const u32* __restrict__ base, int base_mont, u32* __restrict__ ext, u32* __restrict__ flag) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= FB_WINDOWS) return;
+  u32 xs[8], ys[8], x[8], y[8];
+  load_fr(xs, base);
+  load_fr(ys, base + 8);
+  bool ok = fr_is_canonical(xs) && fr_is_canonical(ys);
+  if (base_mont) {
+    fr_copy(x, xs);
+    fr_copy(y, ys);
+  } else {
+    fr_to_mont(x, xs);
+    fr_to_mont(y, ys);
+  }
+  ok = ok && ed_is_on_curve(x, y);
+  if (w == 0) flag[0] = ok ? 1u : 0u;
+  ExtPoint p;
+  if (ok)
+    ext_from_affine(p, x, y);
+  else
+    ext_identity(p);  // keeps every later kernel well defined; results are masked by the flag
+#pragma unroll 1
+  for (int i = 0; i < w * FB_WBITS; i++) ext_double(p);
+  u32* o = ext + (size_t)w * FB_ENTRIES * 32;
+  store_fr(o, p.X);
+  store_fr(o + 8, p.Y);
+  store_fr(o + 16, p.Z);
+  store_fr(o + 24, p.T);
+}
+
+// step 2: ext[w][d-1] = [d] ext[w][0] for d = 2..FB_ENTRIES (double-and-add on d)
+__global__ void fb_table_fill_kernel(u32* __restrict__ ext) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= FB_WINDOWS * FB_ENTRIES) return;
+  int w = idx / FB_ENTRIES, d = idx % FB_ENTRIES + 1;
+  if (d == 1) return;
+  ExtPoint b, acc;
+  const u32* s = ext + (size_t)w * FB_ENTRIES * 32;
+  load_fr(b.X, s);
+  load_fr(b.Y, s + 8);
+  load_fr(b.Z, s + 16);
+  load_fr(b.T, s + 24);
+  ext_identity(acc);
+#pragma unroll 1
+  for (int bit = FB_WBITS - 1; bit >= 0; bit--) {
+    ext_double(acc);
+    if ((d >> bit) & 1) ext_add(acc, b);
+  }
+  u32* o = ext + (size_t)idx * 32;
+  store_fr(o, acc.X);
+  store_fr(o + 8, acc.Y);
+  store_fr(o + 16, acc.Z);
+  store_fr(o + 24, acc.T);
+}
+
+// step 3: extended -> Niels (y-x, y+x, 2dxy), canonical Montgomery.  (step 2 must have completed: separate launch)
+__global__ void fb_table_niels_kernel(const u32* __restrict__ ext, u32* __restrict__ tab) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= FB_WINDOWS * FB_ENTRIES) return;
+  const u32* s = ext + (size_t)idx * 32;
+  u32 X[8], Y[8], Z[8], zi[8], x[8], y[8], t[8];
+  const u32 d2[8] = GCP_ED_2D_MONT;
+  load_fr(X, s);
+  load_fr(Y, s + 8);
+  load_fr(Z, s + 16);
+  fr_inv(zi, Z);
+  fr_mul(x, X, zi);
+  fr_mul(y, Y, zi);
+  NielsPoint n;
+  fr_sub(n.ymx, y, x);
+  fr_add(n.ypx, y, x);
+  fr_mul(t, x, y);
+  fr_mul(n.t2d, t, d2);
+  fr_canon(n.ymx);
+  fr_canon(n.ypx);
+  fr_canon(n.t2d);
+  u32* o = tab + (size_t)idx * 24;
+  store_fr(o, n.ymx);
+  store_fr(o + 8, n.ypx);
+  store_fr(o + 16, n.t2d);
+}
+
+// acc += [k] B using B's table; k is a 256-bit integer (canonical Fr element used as an integer)
+__device__ __forceinline__ void fixed_base_accumulate(ExtPoint& acc, const u32 (&k)[8], const u32* __restrict__ tab) {
+#pragma unroll 1
+  for (int w = 0; w < FB_WINDOWS; w++) {
+    u32 d = scalar_window<FB_WBITS>(k, w);
+    if (d != 0) {
+      NielsPoint n;
+      load_niels(n, tab + ((size_t)w * FB_ENTRIES + (d - 1)) * 24);
+      ext_add_niels(acc, n);
+    }
+  }
+}
+
+__device__ __forceinline__ void store_ext_xyz(u32* o, const ExtPoint& p) {
+  store_fr(o, p.X);
+  store_fr(o + 8, p.Y);
+  store_fr(o + 16, p.Z);
+}
+
+__device__ __forceinline__ void load_scalar(u32 (&k)[8], bool& canonical, const u32* p, int mont) {
+  u32 x[8];
+  load_fr(x, p);
+  canonical = canonical && fr_is_canonical(x);
+  if (mont)
+    fr_from_mont(k, x);  // scalars are integers: leave Montgomery form
+  else
+    fr_copy(k, x);
+}
+
+// ---- [s]G -------------------------------------------------------------------------------------------------
+// out_xyz: n x 24 words (X, Y, Z).  status: n bytes.
+__global__ void __launch_bounds__(128) fixed_base_mul_kernel(const u32* __restrict__ tabG, const u32* __restrict__ scalars,
+                                                             size_t n, u32* __restrict__ out_xyz, u8* __restrict__ status,
+                                                             int mont) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  bool canon = true;
+  u32 k[8];
+  load_scalar(k, canon, scalars + idx * 8, mont);
+  ExtPoint acc;
+  ext_identity(acc);
+  if (canon) fixed_base_accumulate(acc, k, tabG);
+  store_ext_xyz(out_xyz + idx * 24, acc);
+  status[idx] = canon ? GCP_STATUS_OK : GCP_STATUS_NONCANONICAL;
+}
+
+// ---- Encrypt with one shared public key (the election key) ----------------------------------------------------
+// out_xyz: n x 2 x 24 words: C1 = [k]G, C2 = [k]PK + [m]G as (X, Y, Z).
+__global__ void __launch_bounds__(128) encrypt_shared_kernel(const u32* __restrict__ tabG, const u32* __restrict__ tabPK,
+                                                             const u32* __restrict__ pk_flag, const u32* __restrict__ ks,
+                                                             const u32* __restrict__ ms, size_t n, u32* __restrict__ out_xyz,
+                                                             u8* __restrict__ status, int mont) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  bool canon = true;
+  u32 k[8], m[8];
+  load_scalar(k, canon, ks + idx * 8, mont);
+  load_scalar(m, canon, ms + idx * 8, mont);
+  bool pk_ok = pk_flag[0] != 0;
+  ExtPoint c1, c2;
+  ext_identity(c1);
+  ext_identity(c2);
+  if (canon && pk_ok) {
+    fixed_base_accumulate(c1, k, tabG);   // encrypt.go:52
+    fixed_base_accumulate(c2, k, tabPK);  // encrypt.go:55
+    fixed_base_accumulate(c2, m, tabG);   // encrypt.go:58,61
+  }
+  store_ext_xyz(out_xyz + idx * 48, c1);
+  store_ext_xyz(out_xyz + idx * 48 + 24, c2);
+  status[idx] = !canon ? GCP_STATUS_NONCANONICAL : (!pk_ok ? GCP_STATUS_OFF_CURVE : GCP_STATUS_OK);
+}
+
+// ---- Encrypt with a public key per item: [k]PK by double-and-add -------------------------------------------------
+__global__ void __launch_bounds__(128) encrypt_per_key_kernel(const u32* __restrict__ tabG, const u32* __restrict__ pks,
+                                                              const u32* __restrict__ ks, const u32* __restrict__ ms, size_t n,
+                                                              u32* __restrict__ out_xyz, u8* __restrict__ status, int mont) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  bool canon = true;
+  u32 k[8], m[8], px[8], py[8], xs[8], ys[8];
+  load_scalar(k, canon, ks + idx * 8, mont);
+  load_scalar(m, canon, ms + idx * 8, mont);
+  load_fr(xs, pks + idx * 16);
+  load_fr(ys, pks + idx * 16 + 8);
+  canon = canon && fr_is_canonical(xs) && fr_is_canonical(ys);
+  if (mont) {
+    fr_copy(px, xs);
+    fr_copy(py, ys);
+  } else {
+    fr_to_mont(px, xs);
+    fr_to_mont(py, ys);
+  }
+  bool pk_ok = canon && ed_is_on_curve(px, py);
+  ExtPoint c1, c2;
+  ext_identity(c1);
+  ext_identity(c2);
+  if (pk_ok) {
+    fixed_base_accumulate(c1, k, tabG);
+    ExtPoint base;
+    ext_from_affine(base, px, py);
+#pragma unroll 1
+    for (int bit = 253; bit >= 0; bit--) {  // k < r < 2^254
+      ext_double(c2);
+      if ((k[bit >> 5] >> (bit & 31)) & 1u) ext_add(c2, base);
+    }
+    fixed_base_accumulate(c2, m, tabG);
+  }
+  store_ext_xyz(out_xyz + idx * 48, c1);
+  store_ext_xyz(out_xyz + idx * 48 + 24, c2);
+  status[idx] = !canon ? GCP_STATUS_NONCANONICAL : (!pk_ok ? GCP_STATUS_OFF_CURVE : GCP_STATUS_OK);
+}
+
+// ---- (X, Y, Z) -> canonical affine, Montgomery batch inversion over BATCH_INV points per thread ----------------
+// xyz: n_points x 24 words; out: n_points x 16 words.  status (optional) is indexed by point / pts_per_item.
+__global__ void __launch_bounds__(128) normalize_kernel(const u32* __restrict__ xyz, size_t n_points, u32* __restrict__ out,
+                                                        u8* __restrict__ status, int pts_per_item, int mont) {
+  size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  if (tid >= n_points) return;
+  u32 pre[BATCH_INV][8];  // prefix products (local memory)
+  u32 acc[8];
+  fr_set_one(acc);
+  int cnt = 0;
+#pragma unroll 1
+  for (int j = 0; j < BATCH_INV; j++) {
+    size_t p = tid + (size_t)j * stride;
+    if (p >= n_points) break;
+    u32 z[8];
+    load_fr(z, xyz + p * 24 + 16);
+    u32 zc[8];
+    fr_copy(zc, z);
+    fr_canon(zc);
+    if (is_zero256(zc)) {  // zero denominator: flag it and keep the batch invertible
+      if (status) status[p / pts_per_item] = GCP_STATUS_ZERO_DENOM;
+      fr_set_one(z);
+    }
+    fr_mul(acc, acc, z);
+#pragma unroll
+    for (int l = 0; l < 8; l++) pre[j][l] = acc[l];
+    cnt++;
+  }
+  u32 inv[8];
+  fr_inv(inv, acc);
+#pragma unroll 1
+  for (int j = cnt - 1; j >= 0; j--) {
+    size_t p = tid + (size_t)j * stride;
+    u32 z[8], zi[8], X[8], Y[8], x[8], y[8];
+    load_fr(z, xyz + p * 24 + 16);
+    {
+      u32 zc[8];
+      fr_copy(zc, z);
+      fr_canon(zc);
+      if (is_zero256(zc)) fr_set_one(z);
+    }
+    if (j > 0) {
+      u32 prev[8];
+#pragma unroll
+      for (int l = 0; l < 8; l++) prev[l] = pre[j - 1][l];
+      fr_mul(zi, inv, prev);   // 1 / z_j
+      fr_mul(inv, inv, z);     // 1 / (z_0 ... z_{j-1})
+    } else {
+      fr_copy(zi, inv);
+    }
+    load_fr(X, xyz + p * 24);
+    load_fr(Y, xyz + p * 24 + 8);
+    fr_mul(x, X, zi);
+    fr_mul(y, Y, zi);
+    u32 ox[8], oy[8];
+    if (mont) {
+      fr_copy(ox, x);
+      fr_copy(oy, y);
+      fr_canon(ox);
+      fr_canon(oy);
+    } else {
+      fr_from_mont(ox, x);
+      fr_from_mont(oy, y);
+    }
+    bool bad = status && status[p / pts_per_item] != GCP_STATUS_OK;
+    if (bad) {
+      fr_set_zero(ox);
+      fr_set_zero(oy);
+    }
+    store_fr(out + p * 16, ox);
+    store_fr(out + p * 16 + 8, oy);
+  }
+}
+
+// ---- Ciphertext.Add / Neg, element-wise ------------------------------------------------------------------------
+__device__ __forceinline__ void load_affine_ext(ExtPoint& p, bool& canonical, const u32* src, int mont) {
+  u32 xs[8], ys[8], x[8], y[8];
+  load_fr(xs, src);
+  load_fr(ys, src + 8);
+  canonical = canonical && fr_is_canonical(xs) && fr_is_canonical(ys);
+  if (mont) {
+    fr_copy(x, xs);
+    fr_copy(y, ys);
+  } else {
+    fr_to_mont(x, xs);
+    fr_to_mont(y, ys);
+  }
+  ext_from_affine(p, x, y);
+}
+
+// a, b: n x 32 words (ciphertexts); out_xyz: n x 2 x 24 words
+__global__ void __launch_bounds__(128) ct_add_kernel(const u32* __restrict__ a, const u32* __restrict__ b, size_t n,
+                                                     u32* __restrict__ out_xyz, u8* __restrict__ status, int mont) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 2 * n) return;  // one thread per point
+  bool canon = true;
+  ExtPoint p, q;
+  load_affine_ext(p, canon, a + idx * 16, mont);
+  load_affine_ext(q, canon, b + idx * 16, mont);
+  ext_add(p, q);  // ciphertext.go:29-30
+  if (!canon) {
+    ext_identity(p);
+    status[idx / 2] = GCP_STATUS_NONCANONICAL;  // benign race: both halves write the same value
+  }
+  store_ext_xyz(out_xyz + idx * 24, p);
+}
+
+// Neg: (x, y) -> (-x, y) (ciphertext.go:37-46); pure element-wise, canonical in/out
+__global__ void ct_neg_kernel(const u32* __restrict__ a, size_t n_points, u32* __restrict__ out, u8* __restrict__ status) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_points) return;
+  const u32 P1[8] = GCP_P_LIMBS;
+  u32 x[8], y[8], nx[8];
+  load_fr(x, a + idx * 16);
+  load_fr(y, a + idx * 16 + 8);
+  bool canon = fr_is_canonical(x) && fr_is_canonical(y);
+  if (is_zero256(x))
+    fr_set_zero(nx);
+  else
+    sub256(nx, P1, x);  // valid in both element formats: negation commutes with the Montgomery map
+  if (!canon) {
+    fr_set_zero(nx);
+    fr_set_zero(y);
+    status[idx / 2] = GCP_STATUS_NONCANONICAL;
+  }
+  store_fr(out + idx * 16, nx);
+  store_fr(out + idx * 16 + 8, y);
+}
+
+// ---- Tally: sum over ballots of ct[ballot][field], per field ----------------------------------------------------
+// Each thread owns one (field, point-half) column and strides over ballots; block tree-reduction in shared
+// memory; one partial (X, Y, Z, T) per (block, field, half) to `partials` [gridDim.x][n_fields*2][32 words].
+constexpr int TALLY_THREADS = 128;
+
+__global__ void __launch_bounds__(TALLY_THREADS) tally_partial_kernel(const u32* __restrict__ ct, size_t n_ballots, int n_fields,
+                                                                      u32* __restrict__ partials, u32* __restrict__ bad_count,
+                                                                      int mont) {
+  extern __shared__ u32 smem[];  // TALLY_THREADS x 32 words
+  const int cols = n_fields * 2;                       // point columns per ballot
+  const int rows_per_block = TALLY_THREADS / cols;     // ballots processed concurrently by one block
+  const int col = threadIdx.x % cols, row = threadIdx.x / cols;
+  const bool active = row < rows_per_block;
+  const u32 d2r3[8] = GCP_ED_2D_R3;
+  const u32 r2[8] = GCP_FR_R2;
+  ExtPoint acc;
+  ext_identity(acc);
+  u32 bad = 0;
+  if (active) {
+    size_t b = (size_t)blockIdx.x * rows_per_block + row;
+    size_t bstride = (size_t)gridDim.x * rows_per_block;
+#pragma unroll 1
+    for (; b < n_ballots; b += bstride) {
+      const u32* src = ct + (b * cols + col) * 16;
+      u32 xs[8], ys[8];
+      load_fr(xs, src);
+      load_fr(ys, src + 8);
+      if (!(fr_is_canonical(xs) && fr_is_canonical(ys))) {
+        bad = 1;
+        continue;
+      }
+      NielsPoint n;
+      u32 t[8];
+      if (mont) {
+        const u32 d2[8] = GCP_ED_2D_MONT;
+        fr_sub(n.ymx, ys, xs);
+        fr_add(n.ypx, ys, xs);
+        fr_mul(t, xs, ys);
+        fr_mul(n.t2d, t, d2);
+      } else {
+        // standard-form inputs: (y -/+ x) * R^2 / R, and x*y/R * (2d R^3) / R = 2dxy R  (4 multiplies, no to_mont)
+        u32 s[8];
+        fr_sub(s, ys, xs);
+        fr_mul(n.ymx, s, r2);
+        fr_add(s, ys, xs);
+        fr_mul(n.ypx, s, r2);
+        fr_mul(t, xs, ys);
+        fr_mul(n.t2d, t, d2r3);
+      }
+      ext_add_niels(acc, n);
+    }
+  }
+  if (bad) atomicAdd(bad_count + col / 2, 1u);
+  // tree reduction over the rows of each column
+  u32* mine = smem + threadIdx.x * 32;
+#pragma unroll
+  for (int l = 0; l < 8; l++) {
+    mine[l] = acc.X[l];
+    mine[8 + l] = acc.Y[l];
+    mine[16 + l] = acc.Z[l];
+    mine[24 + l] = acc.T[l];
+  }
+  __syncthreads();
+  int live = rows_per_block;
+  while (live > 1) {
+    int half = (live + 1) / 2;
+    if (active && row < live / 2) {
+      const u32* other = smem + (threadIdx.x + half * cols) * 32;
+      ExtPoint q;
+#pragma unroll
+      for (int l = 0; l < 8; l++) {
+        q.X[l] = other[l];
+        q.Y[l] = other[8 + l];
+        q.Z[l] = other[16 + l];
+        q.T[l] = other[24 + l];
+      }
+      ext_add(acc, q);
+    }
+    __syncthreads();
+    if (active && row < live / 2) {
+#pragma unroll
+      for (int l = 0; l < 8; l++) {
+        mine[l] = acc.X[l];
+        mine[8 + l] = acc.Y[l];
+        mine[16 + l] = acc.Z[l];
+        mine[24 + l] = acc.T[l];
+      }
+    }
+    __syncthreads();
+    live = half;
+  }
+  if (active && row == 0) {
+    u32* o = partials + ((size_t)blockIdx.x * cols + col) * 32;
+    store_fr(o, acc.X);
+    store_fr(o + 8, acc.Y);
+    store_fr(o + 16, acc.Z);
+    store_fr(o + 24, acc.T);
+  }
+}
+
+// Second stage: one thread per column adds the per-block partials; writes (X, Y, Z) for normalize_kernel.
+__global__ void tally_final_kernel(const u32* __restrict__ partials, int n_blocks, int cols, u32* __restrict__ out_xyz,
+                                   const u32* __restrict__ bad_count, u8* __restrict__ status) {
+  int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= cols) return;
+  ExtPoint acc;
+  ext_identity(acc);
+#pragma unroll 1
+  for (int b = 0; b < n_blocks; b++) {
+    const u32* s = partials + ((size_t)b * cols + col) * 32;
+    ExtPoint q;
+    load_fr(q.X, s);
+    load_fr(q.Y, s + 8);
+    load_fr(q.Z, s + 16);
+    load_fr(q.T, s + 24);
+    ext_add(acc, q);
+  }
+  store_ext_xyz(out_xyz + (size_t)col * 24, acc);
+  if ((col & 1) == 0) status[col / 2] = bad_count[col / 2] ? GCP_STATUS_NONCANONICAL : GCP_STATUS_OK;
+}
+
+}  // namespace gcp

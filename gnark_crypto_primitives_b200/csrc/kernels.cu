@@ -4,7 +4,10 @@
 #include "fr.cuh"
 #include "poseidon.cuh"
 #include "smt.cuh"
+#include "elgamal.cuh"
 #include "kernels.h"
+
+#include <algorithm>
 
 namespace gcp {
 
@@ -223,6 +226,89 @@ cudaError_t launch_smt_verify(const SmtArgs& a, cudaStream_t stream) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   smt_path_kernel<<<blocks, 128, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ElGamal
+// ---------------------------------------------------------------------------------------------------
+size_t fb_table_bytes() { return FB_TABLE_WORDS * sizeof(u32); }
+size_t fb_ext_scratch_bytes() { return (size_t)FB_WINDOWS * FB_ENTRIES * 32 * sizeof(u32); }
+
+static inline unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+cudaError_t launch_fb_table_build(const u32* d_base_xy, int base_mont, u32* d_ext, u32* d_tab, u32* d_flag,
+                                  cudaStream_t stream) {
+  fb_table_bases_kernel<<<1, FB_WINDOWS, 0, stream>>>(d_base_xy, base_mont, d_ext, d_flag);
+  const int total = FB_WINDOWS * FB_ENTRIES;
+  fb_table_fill_kernel<<<blocks_for(total, 64), 64, 0, stream>>>(d_ext);
+  fb_table_niels_kernel<<<blocks_for(total, 64), 64, 0, stream>>>(d_ext, d_tab);
+  return cudaGetLastError();
+}
+
+cudaError_t upload_generator(u32* d_xy, cudaStream_t stream) {
+  static const u32 g[16] = {0xfe553f9fu, 0xf1f9195au, 0xe6f2a277u, 0x377c749au, 0xc199e94cu, 0x8a4eb7a4u, 0x6ce19d35u, 0x1561ff83u,
+                            0x872d7d8bu, 0x4b3c257au, 0xb9e13377u, 0xfce0051fu, 0xd16bf9edu, 0x25572e1cu, 0xf7a0b249u, 0x25797203u};
+  return cudaMemcpyAsync(d_xy, g, sizeof(g), cudaMemcpyHostToDevice, stream);
+}
+
+cudaError_t launch_fixed_base_mul(const u32* tabG, const u32* scalars, size_t n, u32* out_xyz, u8* status, int mont,
+                                  cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  fixed_base_mul_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(tabG, scalars, n, out_xyz, status, mont);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_encrypt_shared(const u32* tabG, const u32* tabPK, const u32* pk_flag, const u32* ks, const u32* ms,
+                                  size_t n, u32* out_xyz, u8* status, int mont, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  encrypt_shared_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(tabG, tabPK, pk_flag, ks, ms, n, out_xyz, status, mont);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_encrypt_per_key(const u32* tabG, const u32* pks, const u32* ks, const u32* ms, size_t n, u32* out_xyz,
+                                   u8* status, int mont, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  encrypt_per_key_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(tabG, pks, ks, ms, n, out_xyz, status, mont);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_normalize(const u32* xyz, size_t n_points, u32* out, u8* status, int pts_per_item, int mont,
+                             cudaStream_t stream) {
+  if (n_points == 0) return cudaSuccess;
+  size_t threads = (n_points + BATCH_INV - 1) / BATCH_INV;
+  normalize_kernel<<<blocks_for(threads, 128), 128, 0, stream>>>(xyz, n_points, out, status, pts_per_item, mont);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ct_add(const u32* a, const u32* b, size_t n, u32* out_xyz, u8* status, int mont, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  ct_add_kernel<<<blocks_for(2 * n, 128), 128, 0, stream>>>(a, b, n, out_xyz, status, mont);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ct_neg(const u32* a, size_t n, u32* out, u8* status, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  ct_neg_kernel<<<blocks_for(2 * n, 128), 128, 0, stream>>>(a, 2 * n, out, status);
+  return cudaGetLastError();
+}
+
+int tally_max_blocks(size_t n_ballots, int n_fields, int sm_count) {
+  int rows = TALLY_THREADS / (n_fields * 2);
+  size_t need = (n_ballots + rows - 1) / rows;
+  size_t cap = (size_t)sm_count * 8;
+  return (int)std::max<size_t>(1, std::min(need, cap));
+}
+
+// partials: n_blocks x (n_fields*2) x 32 words; bad_count: n_fields words (zeroed here); out_xyz: n_fields*2 x 24 words
+cudaError_t launch_tally(const u32* ct, size_t n_ballots, int n_fields, int n_blocks, u32* partials, u32* bad_count,
+                         u32* out_xyz, u8* status, int mont, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(bad_count, 0, sizeof(u32) * n_fields, stream);
+  if (e != cudaSuccess) return e;
+  tally_partial_kernel<<<n_blocks, TALLY_THREADS, TALLY_THREADS * 32 * sizeof(u32), stream>>>(ct, n_ballots, n_fields, partials,
+                                                                                              bad_count, mont);
+  const int cols = n_fields * 2;
+  tally_final_kernel<<<blocks_for(cols, 32), 32, 0, stream>>>(partials, n_blocks, cols, out_xyz, bad_count, status);
   return cudaGetLastError();
 }
 

@@ -58,4 +58,24 @@ cudaError_t launch_poseidon(const PoseidonTable& tab, const u32* in, u32* out, u
 double launch_imad_probe(u32* d_out, int blocks, u32 seed, cudaStream_t stream);
 cudaError_t launch_smt_verify(const SmtArgs& a, cudaStream_t stream);
 
+// ElGamal (elgamal.cuh)
+size_t fb_table_bytes();
+size_t fb_ext_scratch_bytes();
+cudaError_t upload_generator(u32* d_xy, cudaStream_t stream);
+cudaError_t launch_fb_table_build(const u32* d_base_xy, int base_mont, u32* d_ext, u32* d_tab, u32* d_flag,
+                                  cudaStream_t stream);
+cudaError_t launch_fixed_base_mul(const u32* tabG, const u32* scalars, size_t n, u32* out_xyz, u8* status, int mont,
+                                  cudaStream_t stream);
+cudaError_t launch_encrypt_shared(const u32* tabG, const u32* tabPK, const u32* pk_flag, const u32* ks, const u32* ms,
+                                  size_t n, u32* out_xyz, u8* status, int mont, cudaStream_t stream);
+cudaError_t launch_encrypt_per_key(const u32* tabG, const u32* pks, const u32* ks, const u32* ms, size_t n, u32* out_xyz,
+                                   u8* status, int mont, cudaStream_t stream);
+cudaError_t launch_normalize(const u32* xyz, size_t n_points, u32* out, u8* status, int pts_per_item, int mont,
+                             cudaStream_t stream);
+cudaError_t launch_ct_add(const u32* a, const u32* b, size_t n, u32* out_xyz, u8* status, int mont, cudaStream_t stream);
+cudaError_t launch_ct_neg(const u32* a, size_t n, u32* out, u8* status, cudaStream_t stream);
+int tally_max_blocks(size_t n_ballots, int n_fields, int sm_count);
+cudaError_t launch_tally(const u32* ct, size_t n_ballots, int n_fields, int n_blocks, u32* partials, u32* bad_count,
+                         u32* out_xyz, u8* status, int mont, cudaStream_t stream);
+
 }  // namespace gcp

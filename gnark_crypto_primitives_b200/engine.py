@@ -222,3 +222,76 @@ class Engine:
                                                  _dptr(d_is_old0), _dptr(d_keys), _dptr(d_values), _dptr(d_fnc),
                                                  _dptr(d_enabled), _dptr(d_flags), _dptr(d_status),
                                                  _dptr(d_out_roots), fmt, self._stream(stream)))
+
+    # -- ElGamal ------------------------------------------------------------------------------------
+    def elgamal_fixed_base_mul(self, scalars, fmt=FMT_CANONICAL):
+        """FixedBaseScalarMulBN254 (elgamal/mul.go:76-166): (n, 32) scalars -> ((n, 2, 32) points, status)."""
+        s = _as_elems(scalars, name="scalars").reshape(-1, 32)
+        n = s.shape[0]
+        out = np.empty((n, 2, 32), dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.gcp_elgamal_fixed_base_mul(self._h, _ptr(s), n, _ptr(out), _ptr(status), fmt))
+        return out, status
+
+    def elgamal_encrypt(self, pub_key, k, m, fmt=FMT_CANONICAL):
+        """(*Ciphertext).Encrypt (elgamal/encrypt.go:42-64).  pub_key: (2, 32) shared or (n, 2, 32) per item.
+        Returns ((n, 4, 32) ciphertexts in Serialize order, status)."""
+        kk = _as_elems(k, name="k").reshape(-1, 32)
+        n = kk.shape[0]
+        mm = _as_elems(m, n, "m").reshape(-1, 32)
+        pk = _as_elems(pub_key, name="pub_key")
+        per_item = 0 if pk.size == 64 and (n != 1 or pk.ndim <= 2) else 1
+        if per_item and pk.size != n * 64:
+            raise ValueError("pub_key must be one point or n points")
+        out = np.empty((n, 4, 32), dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.gcp_elgamal_encrypt(self._h, _ptr(pk), per_item, _ptr(kk), _ptr(mm), n, _ptr(out),
+                                                  _ptr(status), fmt))
+        return out, status
+
+    def elgamal_add(self, a, b, fmt=FMT_CANONICAL):
+        """(*Ciphertext).Add (elgamal/ciphertext.go:24-32), element-wise: (n, 4, 32) x2 -> (n, 4, 32)."""
+        aa = _as_elems(a, name="a").reshape(-1, 4, 32)
+        n = aa.shape[0]
+        bb = _as_elems(b, n * 4, "b").reshape(-1, 4, 32)
+        out = np.empty((n, 4, 32), dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.gcp_elgamal_add(self._h, _ptr(aa), _ptr(bb), n, _ptr(out), _ptr(status), fmt))
+        return out, status
+
+    def elgamal_neg(self, a, fmt=FMT_CANONICAL):
+        """(*Ciphertext).Neg (elgamal/ciphertext.go:37-46)."""
+        aa = _as_elems(a, name="a").reshape(-1, 4, 32)
+        n = aa.shape[0]
+        out = np.empty((n, 4, 32), dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.gcp_elgamal_neg(self._h, _ptr(aa), n, _ptr(out), _ptr(status), fmt))
+        return out, status
+
+    def elgamal_tally(self, ct, fmt=FMT_CANONICAL):
+        """Fold of Ciphertext.Add over ballots per field: (n_ballots, n_fields, 4, 32) -> ((n_fields, 4, 32), status)."""
+        c = _as_elems(ct, name="ct")
+        if c.ndim != 4 or c.shape[2] != 4:
+            raise ValueError("ct must have shape (n_ballots, n_fields, 4, 32)")
+        nb, nf = c.shape[0], c.shape[1]
+        out = np.empty((nf, 4, 32), dtype=np.uint8)
+        status = np.empty(nf, dtype=np.uint8)
+        self._check(self._lib.gcp_elgamal_tally(self._h, _ptr(c), nb, nf, _ptr(out), _ptr(status), fmt))
+        return out, status
+
+    def elgamal_encrypt_dev(self, d_pub_key, pk_per_item, d_k, d_m, n, d_out, d_status, fmt=FMT_CANONICAL, stream=None):
+        self._check(self._lib.gcp_elgamal_encrypt_dev(self._h, _dptr(d_pub_key), int(bool(pk_per_item)), _dptr(d_k),
+                                                      _dptr(d_m), n, _dptr(d_out), _dptr(d_status), fmt,
+                                                      self._stream(stream)))
+
+    def elgamal_fixed_base_mul_dev(self, d_scalars, n, d_out, d_status, fmt=FMT_CANONICAL, stream=None):
+        self._check(self._lib.gcp_elgamal_fixed_base_mul_dev(self._h, _dptr(d_scalars), n, _dptr(d_out),
+                                                             _dptr(d_status), fmt, self._stream(stream)))
+
+    def elgamal_add_dev(self, d_a, d_b, n, d_out, d_status, fmt=FMT_CANONICAL, stream=None):
+        self._check(self._lib.gcp_elgamal_add_dev(self._h, _dptr(d_a), _dptr(d_b), n, _dptr(d_out), _dptr(d_status), fmt,
+                                                  self._stream(stream)))
+
+    def elgamal_tally_dev(self, d_ct, n_ballots, n_fields, d_out, d_status, fmt=FMT_CANONICAL, stream=None):
+        self._check(self._lib.gcp_elgamal_tally_dev(self._h, _dptr(d_ct), n_ballots, n_fields, _dptr(d_out),
+                                                    _dptr(d_status), fmt, self._stream(stream)))

@@ -105,6 +105,34 @@ int gcp_smt_verify_exclusion(gcp_ctx* ctx, int n_levels, size_t n, const void* r
                              const uint8_t* is_old0, const void* keys, uint8_t* out_flags, uint8_t* out_status,
                              void* out_roots, int fmt);
 
+/* ---- ElGamal over the a = -1 BN254 twisted Edwards curve: elgamal/ ------------------------------------ */
+/* FixedBaseScalarMulBN254 (elgamal/mul.go:76-166): out[i] = [scalars[i]] G, scalars are Fr elements used as
+ * integers in [0, r).  out_points: n x (X, Y). */
+int gcp_elgamal_fixed_base_mul(gcp_ctx* ctx, const void* scalars, size_t n, void* out_points, uint8_t* status, int fmt);
+int gcp_elgamal_fixed_base_mul_dev(gcp_ctx* ctx, const void* d_scalars, size_t n, void* d_out_points,
+                                   uint8_t* d_status, int fmt, void* stream);
+/* (*Ciphertext).Encrypt (elgamal/encrypt.go:42-64): C1 = [k]G, C2 = [m]G + [k]pubKey.  m = 0 gives EncryptedZero
+ * (encrypt.go:72-94).  pub_key: one point (pk_per_item = 0, the election key; its window table is cached in the
+ * context) or n points.  status 4 where AssertIsOnCurve(pubKey) would fail.  out_ct: n x (C1.X, C1.Y, C2.X, C2.Y). */
+int gcp_elgamal_encrypt(gcp_ctx* ctx, const void* pub_key, int pk_per_item, const void* k, const void* m, size_t n,
+                        void* out_ct, uint8_t* status, int fmt);
+int gcp_elgamal_encrypt_dev(gcp_ctx* ctx, const void* d_pub_key, int pk_per_item, const void* d_k, const void* d_m,
+                            size_t n, void* d_out_ct, uint8_t* d_status, int fmt, void* stream);
+/* (*Ciphertext).Add (elgamal/ciphertext.go:24-32), element-wise over n ciphertext pairs; inputs are not checked to
+ * be on the curve (as in the reference); status 5 where an addition denominator is zero. */
+int gcp_elgamal_add(gcp_ctx* ctx, const void* a, const void* b, size_t n, void* out, uint8_t* status, int fmt);
+int gcp_elgamal_add_dev(gcp_ctx* ctx, const void* d_a, const void* d_b, size_t n, void* d_out, uint8_t* d_status,
+                        int fmt, void* stream);
+/* (*Ciphertext).Neg (elgamal/ciphertext.go:37-46). */
+int gcp_elgamal_neg(gcp_ctx* ctx, const void* a, size_t n, void* out, uint8_t* status, int fmt);
+/* Tally: per field f, the fold of Ciphertext.Add over ct[0..n_ballots)[f] starting from NewCiphertext
+ * (ciphertext.go:16-32).  ct: n_ballots x n_fields ciphertexts; out: n_fields ciphertexts; status: n_fields bytes.
+ * Inputs must be curve points (outputs of Encrypt); the reduction order is unspecified, which is exact for group
+ * elements.  Multi-GPU: tally each shard, all-gather the n_fields partial ciphertexts, tally the gathered array. */
+int gcp_elgamal_tally(gcp_ctx* ctx, const void* ct, size_t n_ballots, int n_fields, void* out, uint8_t* status, int fmt);
+int gcp_elgamal_tally_dev(gcp_ctx* ctx, const void* d_ct, size_t n_ballots, int n_fields, void* d_out,
+                          uint8_t* d_status, int fmt, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,182 @@
+"""GPU parity: ElGamal (fixed-base, encrypt, add, neg, tally) through the C ABI vs the oracle (bit-exact points)."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import cport
+from oracle import edwards as ed
+from oracle import elgamal as eg
+from oracle.field import R
+from tests.util import elems, ints
+
+pytestmark = pytest.mark.gpu
+
+PK_D = 0xB200
+PK = ed.scalar_mul(ed.G, PK_D)
+
+
+def ct_ints(arr):
+    return [ints(c) for c in arr]
+
+
+def test_fixed_base_matches_reference_window_semantics(engine):
+    rng = random.Random(1)
+    ks = [0, 1, 2, 15, 16, 255, 256, 12345, 67890, ed.ORDER - 1, ed.ORDER, ed.ORDER + 1, R - 1, (1 << 253) + 7] + \
+        [rng.randrange(R) for _ in range(50)]
+    out, st = engine.elgamal_fixed_base_mul(elems(ks))
+    assert not st.any()
+    assert [tuple(ints(p)) for p in out] == [eg.fixed_base_scalar_mul(k) for k in ks]  # mul.go:76-166 restated
+    assert tuple(ints(out[0])) == ed.IDENTITY
+
+
+def test_encrypt_compatibility_vector(engine):
+    """elgamal/encrypt_test.go:144-159: PubKey = G, k = 12345, m = 67890."""
+    out, st = engine.elgamal_encrypt(elems(ed.G), elems([12345]), elems([67890]))
+    assert not st.any()
+    assert ints(out[0]) == [19918712023960437102123786886411468478902094248734671506464346041569881874462,
+                            13276557205153692030187527501273228448057533426731746626187331221465573305487,
+                            839909438842816078619007291947839299631027001100725795038371896036563634986,
+                            2683297034354865619026157779551553408927035959921603566752318144387126273226]
+    # EncryptedZero(k) == Encrypt(k, 0)  (encrypt_test.go:125-139)
+    z, _ = engine.elgamal_encrypt(elems(ed.G), elems([12345]), elems([0]))
+    assert ints(z[0]) == eg.serialize(eg.encrypted_zero(ed.G, 12345))
+
+
+def test_encrypt_with_specific_data(engine):
+    """elgamal/encrypt_test.go:180-217: fixed pubkey, k1..k3 (two above the subgroup order), m = 0."""
+    pk = (18604149248430057540085528196797394191454458259161233471314599389622530831795,
+          1988784568828097512630242539176296837964596457792502130892628909648459248949)
+    ks = [855131146298194990003384743709896434741839908245,
+          5883442530210657871581412827617735506655215369087356134218551734599178232070,
+          3979028711588105728532079493967382119023185938755564152610807942458151212832]
+    out, st = engine.elgamal_encrypt(elems(pk), elems(ks), elems([0, 0, 0]))
+    assert not st.any()
+    assert ct_ints(out) == [eg.serialize(eg.encrypt(pk, k, 0)) for k in ks]
+
+
+def test_encrypt_shared_key_batch(engine):
+    rng = random.Random(2)
+    n = 300
+    ks = [rng.randrange(R) for _ in range(n)]
+    ms = [rng.randrange(1 << 16) for _ in range(n)]
+    ks[:4] = [0, 1, R - 1, ed.ORDER]
+    ms[:4] = [0, R - 1, 1, rng.randrange(R)]
+    out, st = engine.elgamal_encrypt(elems(PK), elems(ks), elems(ms))
+    assert not st.any()
+    want, wst = cport.elgamal_encrypt(elems(PK), elems(ks), elems(ms), threads=8)
+    assert not wst.any() and (out == want).all()
+    for i in (0, 1, 2, 3, 17):
+        assert ints(out[i]) == eg.serialize(eg.encrypt(PK, ks[i], ms[i]))
+
+
+def test_encrypt_per_item_keys_and_failures(engine):
+    rng = random.Random(3)
+    n = 12
+    pks = [ed.scalar_mul(ed.G, 5 + i) for i in range(n)]
+    ks = [rng.randrange(R) for _ in range(n)]
+    ms = [rng.randrange(1 << 16) for _ in range(n)]
+    pks[3] = (1, 2)            # off curve -> AssertIsOnCurve fails (encrypt.go:49)
+    ks[5] = R                  # non-canonical scalar
+    pks[7] = (R + 1, pks[7][1])
+    out, st = engine.elgamal_encrypt(elems([c for p in pks for c in p]).reshape(n, 2, 32), elems(ks), elems(ms))
+    assert [int(s) for s in st] == [0, 0, 0, 4, 0, 1, 0, 1, 0, 0, 0, 0]
+    for i in range(n):
+        if st[i] == 0:
+            assert ints(out[i]) == eg.serialize(eg.encrypt(pks[i], ks[i], ms[i])), i
+    # shared off-curve key: every item is flagged
+    out2, st2 = engine.elgamal_encrypt(elems((1, 2)), elems(ks[:3]), elems(ms[:3]))
+    assert [int(s) for s in st2] == [4, 4, 4]
+    # and the cache recovers when a good key follows
+    out3, st3 = engine.elgamal_encrypt(elems(PK), elems(ks[:3]), elems(ms[:3]))
+    assert not st3.any() and ints(out3[0]) == eg.serialize(eg.encrypt(PK, ks[0], ms[0]))
+
+
+def test_add_neg_elementwise(engine):
+    rng = random.Random(4)
+    n = 40
+    a = [eg.encrypt(PK, rng.randrange(R), rng.randrange(100)) for _ in range(n)]
+    b = [eg.encrypt(PK, rng.randrange(R), rng.randrange(100)) for _ in range(n)]
+    b[0] = a[0]                                   # doubling through the unified law
+    b[1] = eg.ct_neg(a[1])                        # sum = identity
+    a[2] = eg.new_ciphertext()                    # identity operand (ciphertext.go:16-19)
+    fa = elems([x for c in a for x in eg.serialize(c)]).reshape(n, 4, 32)
+    fb = elems([x for c in b for x in eg.serialize(c)]).reshape(n, 4, 32)
+    out, st = engine.elgamal_add(fa, fb)
+    assert not st.any()
+    assert ct_ints(out) == [eg.serialize(eg.ct_add(x, y)) for x, y in zip(a, b)]
+    assert ints(out[1]) == [0, 1, 0, 1]
+    neg, st = engine.elgamal_neg(fa)
+    assert not st.any() and ct_ints(neg) == [eg.serialize(eg.ct_neg(x)) for x in a]
+    back, _ = engine.elgamal_neg(neg)
+    assert (back == fa).all()
+
+
+def test_add_does_not_require_curve_points(engine):
+    """ciphertext.go:24-32 performs no on-curve check: garbage in, the same deterministic garbage out."""
+    rng = random.Random(5)
+    pts = [[rng.randrange(R) for _ in range(4)] for _ in range(6)]
+    qts = [[rng.randrange(R) for _ in range(4)] for _ in range(6)]
+    out, st = engine.elgamal_add(elems([x for p in pts for x in p]).reshape(6, 4, 32),
+                                 elems([x for p in qts for x in p]).reshape(6, 4, 32))
+    assert not st.any()
+    for i in range(6):
+        a = ((pts[i][0], pts[i][1]), (pts[i][2], pts[i][3]))
+        b = ((qts[i][0], qts[i][1]), (qts[i][2], qts[i][3]))
+        assert ints(out[i]) == eg.serialize(eg.ct_add(a, b))
+
+
+@pytest.mark.parametrize("n_ballots,n_fields", [(1, 1), (7, 3), (64, 8), (333, 8), (50, 64), (0, 4)])
+def test_tally_matches_fold(engine, n_ballots, n_fields):
+    rng = random.Random(n_ballots * 100 + n_fields)
+    n = n_ballots * n_fields
+    ks = [rng.randrange(R) for _ in range(n)]
+    ms = [rng.randrange(1 << 16) for _ in range(n)]
+    if n:
+        cts, st = cport.elgamal_encrypt(elems(PK), elems(ks), elems(ms), threads=8)
+        cts = cts.reshape(n_ballots, n_fields, 4, 32)
+    else:
+        cts = np.zeros((0, n_fields, 4, 32), np.uint8)
+    out, st = engine.elgamal_tally(cts)
+    assert not st.any()
+    # closed form: sum Encrypt(pk, k_i, m_i) == Encrypt(pk, sum k_i mod l, sum m_i mod l) for pk in <G>
+    for f in range(n_fields):
+        ksum = sum(ks[b * n_fields + f] for b in range(n_ballots)) % ed.ORDER
+        msum = sum(ms[b * n_fields + f] for b in range(n_ballots)) % ed.ORDER
+        assert ints(out[f]) == eg.serialize(eg.encrypt(PK, ksum, msum)), f
+    if n:
+        want, _ = cport.elgamal_tally(cts)
+        assert (out == want).all()
+
+
+def test_tally_is_shard_invariant(engine):
+    """Multi-GPU rule: tally(shards' partials) == tally(all) bit for bit (associativity)."""
+    rng = random.Random(77)
+    nb, nf = 96, 8
+    ks = [rng.randrange(R) for _ in range(nb * nf)]
+    ms = [rng.randrange(1 << 16) for _ in range(nb * nf)]
+    cts, _ = cport.elgamal_encrypt(elems(PK), elems(ks), elems(ms), threads=8)
+    cts = cts.reshape(nb, nf, 4, 32)
+    whole, _ = engine.elgamal_tally(cts)
+    for shards in (2, 3, 8):
+        parts = [engine.elgamal_tally(c)[0] for c in np.array_split(cts, shards)]
+        again, _ = engine.elgamal_tally(np.stack(parts))
+        assert (again == whole).all()
+
+
+def test_montgomery_format(engine):
+    import gnark_crypto_primitives_b200 as g
+
+    rng = random.Random(6)
+    M = 1 << 256
+    ks = [rng.randrange(R) for _ in range(5)]
+    ms = [rng.randrange(1000) for _ in range(5)]
+    to_m = lambda xs: elems([x * M % R for x in xs])
+    out, st = engine.elgamal_encrypt(to_m(PK), to_m(ks), to_m(ms), fmt=g.FMT_MONTGOMERY)
+    assert not st.any()
+    rinv = pow(M, -1, R)
+    got = [[v * rinv % R for v in ints(c)] for c in out]
+    assert got == [eg.serialize(eg.encrypt(PK, k, m)) for k, m in zip(ks, ms)]
+    tal, st = engine.elgamal_tally(out.reshape(5, 1, 4, 32), fmt=g.FMT_MONTGOMERY)
+    want = eg.serialize(eg.tally([eg.encrypt(PK, k, m) for k, m in zip(ks, ms)]))
+    assert [v * rinv % R for v in ints(tal[0])] == want
