@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--log2-proofs", type=int, default=20, help="proofs per GPU per step (default 2^20)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     return ap.parse_args()
 
 
@@ -96,6 +97,85 @@ def make_batch(torch, eng, n, seed):
     expect = torch.ones(n, dtype=torch.uint8, device="cuda")
     expect[bad] = 0
     return dict(sib=sib, keys=keys, vals=vals, roots=roots, flags=flags, status=status, expect=expect)
+
+
+def measure_extras(torch, dist, eng, g, world, rank):
+    """Poseidon Hash2 batch (config 1 shape), ElGamal encrypt and the sharded tally with its all-gather (config 3
+    shape, reduced to 2^20 ballots x 8 fields per GPU).  CUDA events on the launching stream, max over ranks."""
+    from gnark_crypto_primitives_b200 import dist as gdist
+
+    stream = torch.cuda.current_stream()
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(0xE16A + rank)
+
+    def timed(fn, iters=3, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(iters):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    out = {}
+    n = 1 << 22
+    inp = rand_elems(torch, 2 * n, gen)
+    dig = torch.empty((n, 8), dtype=torch.int32, device="cuda")
+    st = torch.empty(n, dtype=torch.uint8, device="cuda")
+    ms = timed(lambda: eng.poseidon_hash_dev(inp, 2, n, dig, st, stream=stream))
+    out["poseidon_hash2_per_s"] = world * n / (ms * 1e-3)
+    out["poseidon_hash2_batch"] = n
+    del inp, dig
+
+    # ElGamal: pk = [0xB200]G computed on the device by the fixed-base kernel
+    sk = torch.zeros((1, 8), dtype=torch.int32, device="cuda")
+    sk[0, 0] = 0xB200
+    pk = torch.empty((1, 2, 32), dtype=torch.uint8, device="cuda")
+    st1 = torch.empty(1, dtype=torch.uint8, device="cuda")
+    eng.elgamal_fixed_base_mul_dev(sk, 1, pk, st1, stream=stream)
+    n = 1 << 20
+    k = rand_elems(torch, n, gen)
+    m = rand_elems(torch, n, gen)
+    m[:, 1:] = 0
+    m[:, 0] &= 0xFFFF
+    ct = torch.empty((n, 4, 32), dtype=torch.uint8, device="cuda")
+    st = torch.empty(n, dtype=torch.uint8, device="cuda")
+    ms = timed(lambda: eng.elgamal_encrypt_dev(pk, False, k, m, n, ct, st, stream=stream))
+    out["elgamal_encrypt_per_s"] = world * n / (ms * 1e-3)
+    out["elgamal_encrypt_batch"] = n
+    enc_ok = not bool(st.any().item())
+
+    n_fields, n_ballots = 8, 1 << 20
+    ballots = ct.view(n // n_fields, n_fields, 4, 32).repeat((n_ballots * n_fields // n, 1, 1, 1)).contiguous()
+    tally_fn = gdist.engine_tally_fn(eng, stream)
+    result = {}
+
+    def tally_step():
+        result["t"] = gdist.sharded_tally(ballots, n_fields, tally_fn)
+
+    ms = timed(tally_step)
+    out["elgamal_tally_ciphertexts_per_s"] = world * n_ballots * n_fields / (ms * 1e-3)
+    out["elgamal_tally_shape"] = f"{n_ballots} ballots x {n_fields} fields per GPU, all_gather of {n_fields * 128} B per rank"
+    out["elgamal_tally_ms"] = ms
+    # shard-invariance check of what was timed: every rank holds the same global tally
+    if world > 1:
+        mine = result["t"].view(-1).to(torch.int32).sum().reshape(1).to(torch.float64)
+        lo, hi = mine.clone(), mine.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        out["tally_identical_on_all_ranks"] = bool(lo.item() == hi.item())
+    out["encrypt_status_clean"] = enc_ok
+    return out
 
 
 class ClockSampler(threading.Thread):
@@ -302,6 +382,11 @@ def main():
         e2e = {"value": world * n * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "steps": e2e_steps, "flags_ok": bool((out_flags == batch["expect"].cpu().numpy()).all())}
 
+    # ---- the other kernels of the path, device-resident, short runs (reported as extras; not the headline) -----
+    extras = None
+    if not args.no_extras:
+        extras = measure_extras(torch, dist, eng, g, world, rank)
+
     # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample) -----------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -330,6 +415,7 @@ def main():
             "bound": "int-pipe", "achieved": achieved / 1e12, "peak": peak_wide / 1e12, "unit": "T IMAD.WIDE.U32/s",
             "frac": achieved / peak_wide if peak_wide else None, "traffic": None,
             "peak_source": "gcp_probe_imad_wide, measured in this run (32 lanes/clk/SM)",
+            "peak_nominal_at_sampled_clock": (148 * 32 * clocks["sm_mhz"] * 1e6 / 1e12) if clocks.get("sm_mhz") else None,
             "kernel": "smt_path_kernel", "wide_mul_per_proof": wide_per_proof,
             "useful_fr_mul_per_proof_reference": (N_LEVELS - 1) * REF_MULS_T3 + REF_MULS_T4,
             "hbm": {"bound": "hbm", "achieved": alg_bytes / (ms_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -344,7 +430,7 @@ def main():
                        "distribution": "dense: 159 non-zero siblings, every 16th proof corrupted", "parallelism":
                        f"{world} x independent shards, no data-path collective", "l2": "inputs (5.5 GB per GPU) exceed L2"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "checks": {"flags_match_construction": ok_flags, "sample_matches_oracle": parity},
+            "cpu_baseline": cpu_baseline, "extras": extras, "checks": {"flags_match_construction": ok_flags, "sample_matches_oracle": parity},
         }
         print(json.dumps(out))
     if world > 1:

@@ -249,7 +249,7 @@ int gcp_probe_imad_wide(gcp_ctx* ctx, double* wide_mul_per_s) {
   CU(cudaEventCreate(&e0), "event");
   CU(cudaEventCreate(&e1), "event");
   double best = 0;
-  for (int it = 0; it < 6; it++) {  // first launches warm the clocks up
+  for (int it = 0; it < 10; it++) {  // ~9 ms per launch; the first launches warm the clocks up, best of the rest
     CU(cudaEventRecord(e0, st), "event record");
     double ops = launch_imad_probe(d_out, blocks, 17u + it, st);
     ctx->launches++;

@@ -450,15 +450,17 @@ __global__ void __launch_bounds__(TALLY_THREADS) tally_partial_kernel(const u32*
   }
 }
 
-// Second stage: one thread per column adds the per-block partials; writes (X, Y, Z) for normalize_kernel.
-__global__ void tally_final_kernel(const u32* __restrict__ partials, int n_blocks, int cols, u32* __restrict__ out_xyz,
-                                   const u32* __restrict__ bad_count, u8* __restrict__ status) {
-  int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= cols) return;
+// Second stage: one block per column; threads stride over the per-block partials, then a shared-memory tree.
+// Writes (X, Y, Z) for normalize_kernel.
+__global__ void __launch_bounds__(TALLY_THREADS) tally_final_kernel(const u32* __restrict__ partials, int n_blocks, int cols,
+                                                                    u32* __restrict__ out_xyz, const u32* __restrict__ bad_count,
+                                                                    u8* __restrict__ status) {
+  __shared__ u32 smem[TALLY_THREADS * 32];
+  const int col = blockIdx.x;
   ExtPoint acc;
   ext_identity(acc);
 #pragma unroll 1
-  for (int b = 0; b < n_blocks; b++) {
+  for (int b = threadIdx.x; b < n_blocks; b += TALLY_THREADS) {
     const u32* s = partials + ((size_t)b * cols + col) * 32;
     ExtPoint q;
     load_fr(q.X, s);
@@ -467,8 +469,40 @@ __global__ void tally_final_kernel(const u32* __restrict__ partials, int n_block
     load_fr(q.T, s + 24);
     ext_add(acc, q);
   }
-  store_ext_xyz(out_xyz + (size_t)col * 24, acc);
-  if ((col & 1) == 0) status[col / 2] = bad_count[col / 2] ? GCP_STATUS_NONCANONICAL : GCP_STATUS_OK;
+  u32* mine = smem + threadIdx.x * 32;
+  int live = min(n_blocks, TALLY_THREADS);
+  if (live < 1) live = 1;
+#pragma unroll 1
+  while (true) {
+#pragma unroll
+    for (int l = 0; l < 8; l++) {
+      mine[l] = acc.X[l];
+      mine[8 + l] = acc.Y[l];
+      mine[16 + l] = acc.Z[l];
+      mine[24 + l] = acc.T[l];
+    }
+    __syncthreads();
+    if (live <= 1) break;
+    int half = (live + 1) / 2;
+    if ((int)threadIdx.x < live / 2) {
+      const u32* other = smem + (threadIdx.x + half) * 32;
+      ExtPoint q;
+#pragma unroll
+      for (int l = 0; l < 8; l++) {
+        q.X[l] = other[l];
+        q.Y[l] = other[8 + l];
+        q.Z[l] = other[16 + l];
+        q.T[l] = other[24 + l];
+      }
+      ext_add(acc, q);
+    }
+    __syncthreads();
+    live = half;
+  }
+  if (threadIdx.x == 0) {
+    store_ext_xyz(out_xyz + (size_t)col * 24, acc);
+    if ((col & 1) == 0) status[col / 2] = bad_count[col / 2] ? GCP_STATUS_NONCANONICAL : GCP_STATUS_OK;
+  }
 }
 
 }  // namespace gcp

@@ -42,7 +42,7 @@ cudaError_t upload_const_tables(const u32* d_t3, const u32* d_t4, cudaStream_t s
 // thread, no memory traffic.  Its rate is the roofline denominator bench.py reports against (same measurement as
 // bench_micro/imad_peak.cu, "wide_cc_pair_chain": 32 lanes/clk/SM, about 9.0 T/s on a B200 at 1.9 GHz).
 // ---------------------------------------------------------------------------------------------------
-constexpr int PROBE_ITERS = 4096;
+constexpr int PROBE_ITERS = 16384;
 constexpr int PROBE_CHAINS = 8;
 __global__ void __launch_bounds__(256) imad_probe_kernel(u32* out, u32 seed) {
   // PROBE_CHAINS independent pairs of 64-bit accumulators; each step is IMAD.WIDE.U32 (carry out) followed by
@@ -308,7 +308,7 @@ cudaError_t launch_tally(const u32* ct, size_t n_ballots, int n_fields, int n_bl
   tally_partial_kernel<<<n_blocks, TALLY_THREADS, TALLY_THREADS * 32 * sizeof(u32), stream>>>(ct, n_ballots, n_fields, partials,
                                                                                               bad_count, mont);
   const int cols = n_fields * 2;
-  tally_final_kernel<<<blocks_for(cols, 32), 32, 0, stream>>>(partials, n_blocks, cols, out_xyz, bad_count, status);
+  tally_final_kernel<<<cols, TALLY_THREADS, 0, stream>>>(partials, n_blocks, cols, out_xyz, bad_count, status);
   return cudaGetLastError();
 }
 
