@@ -59,6 +59,10 @@ SIGNATURES = {
     "gcp_elgamal_neg": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_int]),
     "gcp_elgamal_tally": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_int]),
     "gcp_elgamal_tally_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "gcp_elgamal_encrypt_tally": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p,
+                                          c_int]),
+    "gcp_elgamal_encrypt_tally_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p,
+                                              c_void_p, c_int, c_void_p]),
 }
 
 _lib = None

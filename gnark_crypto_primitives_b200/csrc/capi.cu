@@ -668,6 +668,104 @@ int gcp_elgamal_tally_dev(gcp_ctx* ctx, const void* d_ct, size_t n_ballots, int 
   return tally_dev_locked(ctx, d_ct, n_ballots, n_fields, d_out, d_status, fmt, (cudaStream_t)stream, 44);
 }
 
+static int encrypt_tally_dev_locked(gcp_ctx* ctx, const void* d_k, const void* d_m, size_t n_ballots, int n_fields,
+                                    void* d_out, uint8_t* d_status, int fmt, cudaStream_t st, int slot_base) {
+  int n_blocks = tally_max_blocks(n_ballots, n_fields, ctx->sm_count);
+  const int cols = n_fields * 2;
+  u32* partials = (u32*)ctx->buf(slot_base, (size_t)n_blocks * cols * 128);
+  u32* bad = (u32*)ctx->buf(slot_base + 1, (size_t)n_fields * 4);
+  u32* xyz = (u32*)ctx->buf(slot_base + 2, (size_t)cols * 96);
+  if (!partials || !bad || !xyz) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+  CU(launch_encrypt_tally(ctx->d_tabG, ctx->d_tabPK, (const u32*)d_k, (const u32*)d_m, n_ballots, n_fields, n_blocks,
+                          partials, bad, xyz, d_status, fmt, st),
+     "encrypt-tally kernels");
+  CU(launch_normalize(xyz, (size_t)cols, (u32*)d_out, d_status, 2, fmt, st), "normalize kernel");
+  ctx->launches += 3;
+  return GCP_OK;
+}
+
+static int encrypt_tally_check(gcp_ctx* ctx, const void* pk, const void* k, const void* m, size_t n_ballots,
+                               int n_fields, const void* out, const void* status, int fmt) {
+  int rc = check_fmt(ctx, fmt);
+  if (rc != GCP_OK) return rc;
+  if (n_fields < 1 || n_fields > 64) return ctx->fail(GCP_ERR_BAD_ARG, "n_fields must be in [1, 64]");
+  if (!pk || !out || !status || (n_ballots && (!k || !m))) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  return GCP_OK;
+}
+
+int gcp_elgamal_encrypt_tally_dev(gcp_ctx* ctx, const void* d_pub_key, const void* d_k, const void* d_m,
+                                  size_t n_ballots, int n_fields, void* d_out, uint8_t* d_status, int fmt,
+                                  void* stream) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  int rc = encrypt_tally_check(ctx, d_pub_key, d_k, d_m, n_ballots, n_fields, d_out, d_status, fmt);
+  if (rc != GCP_OK) return rc;
+  rc = ensure_pk_table(ctx, d_pub_key, true, fmt, (cudaStream_t)stream);
+  if (rc != GCP_OK) return rc;
+  return encrypt_tally_dev_locked(ctx, d_k, d_m, n_ballots, n_fields, d_out, d_status, fmt, (cudaStream_t)stream, 44);
+}
+
+// Host form: scalars are streamed in chunks, each chunk is encrypted and reduced on the device, and the per-chunk
+// partial ciphertexts are tallied at the end.  status[f] = 4 for every field when the key is off the curve.
+int gcp_elgamal_encrypt_tally(gcp_ctx* ctx, const void* pub_key, const void* k, const void* m, size_t n_ballots,
+                              int n_fields, void* out, uint8_t* status, int fmt) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  int rc = encrypt_tally_check(ctx, pub_key, k, m, n_ballots, n_fields, out, status, fmt);
+  if (rc != GCP_OK) return rc;
+  rc = ensure_pk_table(ctx, pub_key, false, fmt, ctx->stream[0]);
+  if (rc != GCP_OK) return rc;
+  u32 pk_ok = 0;
+  CU(cudaMemcpy(&pk_ok, ctx->d_flagPK, 4, cudaMemcpyDeviceToHost), "read key flag");
+  const size_t ballot_in = (size_t)n_fields * 32, ballot_ct = (size_t)n_fields * 128;
+  size_t chunk = std::max<size_t>(1, std::min<size_t>(std::max<size_t>(n_ballots, 1), ((size_t)128 << 20) / ballot_in));
+  size_t n_chunks = n_ballots ? (n_ballots + chunk - 1) / chunk : 1;
+  u32* d_parts = (u32*)ctx->buf(64, n_chunks * ballot_ct);
+  uint8_t* d_part_status = (uint8_t*)ctx->buf(65, n_chunks * n_fields);
+  void* d_out = ctx->buf(66, ballot_ct);
+  uint8_t* d_status = (uint8_t*)ctx->buf(67, n_fields);
+  if (!d_parts || !d_part_status || !d_out || !d_status) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+  for (size_t c = 0; c < n_chunks; c++) {
+    size_t off = c * chunk, cnt = n_ballots ? std::min(chunk, n_ballots - off) : 0;
+    int s = (int)(c & 1);
+    cudaStream_t st = ctx->stream[s];
+    void* dk = ctx->buf(48 + s * 8, std::max<size_t>(cnt, 1) * ballot_in);
+    void* dm = ctx->buf(48 + s * 8 + 4, std::max<size_t>(cnt, 1) * ballot_in);
+    if (!dk || !dm) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+    if (cnt) {
+      CU(cudaMemcpyAsync(dk, (const char*)k + off * ballot_in, cnt * ballot_in, cudaMemcpyHostToDevice, st), "H2D");
+      CU(cudaMemcpyAsync(dm, (const char*)m + off * ballot_in, cnt * ballot_in, cudaMemcpyHostToDevice, st), "H2D");
+    }
+    rc = encrypt_tally_dev_locked(ctx, dk, dm, cnt, n_fields, (char*)d_parts + c * ballot_ct, d_part_status + c * n_fields,
+                                  fmt, st, 48 + s * 8 + 1);
+    if (rc != GCP_OK) return rc;
+  }
+  CU(cudaStreamSynchronize(ctx->stream[0]), "stream sync");
+  CU(cudaStreamSynchronize(ctx->stream[1]), "stream sync");
+  cudaStream_t st = ctx->stream[0];
+  const void* d_final = d_parts;
+  const uint8_t* d_final_status = d_part_status;
+  if (n_chunks > 1) {
+    rc = tally_dev_locked(ctx, d_parts, n_chunks, n_fields, d_out, d_status, fmt, st, 49);
+    if (rc != GCP_OK) return rc;
+    d_final = d_out;
+    d_final_status = d_status;
+  }
+  std::vector<uint8_t> part_status(n_chunks * n_fields);
+  CU(cudaMemcpyAsync(out, d_final, ballot_ct, cudaMemcpyDeviceToHost, st), "D2H");
+  CU(cudaMemcpyAsync(status, d_final_status, n_fields, cudaMemcpyDeviceToHost, st), "D2H");
+  CU(cudaMemcpyAsync(part_status.data(), d_part_status, part_status.size(), cudaMemcpyDeviceToHost, st), "D2H");
+  CU(cudaStreamSynchronize(st), "stream sync");
+  for (int f = 0; f < n_fields; f++) {
+    for (size_t c = 0; c < n_chunks; c++)
+      if (part_status[c * n_fields + f] && !status[f]) status[f] = part_status[c * n_fields + f];
+    if (!pk_ok) status[f] = (uint8_t)gcp::GCP_STATUS_OFF_CURVE;
+  }
+  return GCP_OK;
+}
+
 // Generic host-buffer pipeline for the per-item ElGamal calls.
 //   kind 0: fixed-base (in0 = scalars 32 B)            -> 64 B
 //   kind 1: encrypt    (in0 = k 32 B, in1 = m 32 B, optional per-item pk 64 B) -> 128 B

@@ -355,6 +355,48 @@ __global__ void ct_neg_kernel(const u32* __restrict__ a, size_t n_points, u32* _
 // memory; one partial (X, Y, Z, T) per (block, field, half) to `partials` [gridDim.x][n_fields*2][32 words].
 constexpr int TALLY_THREADS = 128;
 
+// Tree reduction over the rows of each column in shared memory (TALLY_THREADS x 32 words); result in row 0's acc.
+__device__ __forceinline__ void block_reduce_columns(ExtPoint& acc, u32* smem, int cols, int rows_per_block, int row, bool active) {
+  u32* mine = smem + threadIdx.x * 32;
+#pragma unroll
+  for (int l = 0; l < 8; l++) {
+    mine[l] = acc.X[l];
+    mine[8 + l] = acc.Y[l];
+    mine[16 + l] = acc.Z[l];
+    mine[24 + l] = acc.T[l];
+  }
+  __syncthreads();
+  int live = rows_per_block;
+#pragma unroll 1
+  while (live > 1) {
+    int half = (live + 1) / 2;
+    if (active && row < live / 2) {
+      const u32* other = smem + (threadIdx.x + half * cols) * 32;
+      ExtPoint q;
+#pragma unroll
+      for (int l = 0; l < 8; l++) {
+        q.X[l] = other[l];
+        q.Y[l] = other[8 + l];
+        q.Z[l] = other[16 + l];
+        q.T[l] = other[24 + l];
+      }
+      ext_add(acc, q);
+    }
+    __syncthreads();
+    if (active && row < live / 2) {
+#pragma unroll
+      for (int l = 0; l < 8; l++) {
+        mine[l] = acc.X[l];
+        mine[8 + l] = acc.Y[l];
+        mine[16 + l] = acc.Z[l];
+        mine[24 + l] = acc.T[l];
+      }
+    }
+    __syncthreads();
+    live = half;
+  }
+}
+
 __global__ void __launch_bounds__(TALLY_THREADS) tally_partial_kernel(const u32* __restrict__ ct, size_t n_ballots, int n_fields,
                                                                       u32* __restrict__ partials, u32* __restrict__ bad_count,
                                                                       int mont) {
@@ -403,44 +445,55 @@ __global__ void __launch_bounds__(TALLY_THREADS) tally_partial_kernel(const u32*
     }
   }
   if (bad) atomicAdd(bad_count + col / 2, 1u);
-  // tree reduction over the rows of each column
-  u32* mine = smem + threadIdx.x * 32;
-#pragma unroll
-  for (int l = 0; l < 8; l++) {
-    mine[l] = acc.X[l];
-    mine[8 + l] = acc.Y[l];
-    mine[16 + l] = acc.Z[l];
-    mine[24 + l] = acc.T[l];
+  block_reduce_columns(acc, smem, cols, rows_per_block, row, active);
+  if (active && row == 0) {
+    u32* o = partials + ((size_t)blockIdx.x * cols + col) * 32;
+    store_fr(o, acc.X);
+    store_fr(o + 8, acc.Y);
+    store_fr(o + 16, acc.Z);
+    store_fr(o + 24, acc.T);
   }
-  __syncthreads();
-  int live = rows_per_block;
-  while (live > 1) {
-    int half = (live + 1) / 2;
-    if (active && row < live / 2) {
-      const u32* other = smem + (threadIdx.x + half * cols) * 32;
-      ExtPoint q;
-#pragma unroll
-      for (int l = 0; l < 8; l++) {
-        q.X[l] = other[l];
-        q.Y[l] = other[8 + l];
-        q.Z[l] = other[16 + l];
-        q.T[l] = other[24 + l];
+}
+
+// Fused Encrypt + tally (the ciphertexts are never materialised): thread (row, col) strides over ballots and adds
+// [k]G into the C1 column or [k]PK + [m]G into the C2 column of its field; same reduction as tally_partial_kernel.
+// ks / ms: n_ballots x n_fields scalars.  bad_count[f] counts non-canonical scalars of field f.
+__global__ void __launch_bounds__(TALLY_THREADS) encrypt_tally_partial_kernel(const u32* __restrict__ tabG, const u32* __restrict__ tabPK,
+                                                                              const u32* __restrict__ ks, const u32* __restrict__ ms,
+                                                                              size_t n_ballots, int n_fields, u32* __restrict__ partials,
+                                                                              u32* __restrict__ bad_count, int mont) {
+  extern __shared__ u32 smem[];
+  const int cols = n_fields * 2;
+  const int rows_per_block = TALLY_THREADS / cols;
+  const int col = threadIdx.x % cols, row = threadIdx.x / cols;
+  const bool active = row < rows_per_block;
+  const int field = col >> 1, half = col & 1;
+  ExtPoint acc;
+  ext_identity(acc);
+  u32 bad = 0;
+  if (active) {
+    size_t b = (size_t)blockIdx.x * rows_per_block + row;
+    size_t bstride = (size_t)gridDim.x * rows_per_block;
+#pragma unroll 1
+    for (; b < n_ballots; b += bstride) {
+      bool canon = true;
+      u32 k[8], m[8];
+      load_scalar(k, canon, ks + (b * n_fields + field) * 8, mont);
+      load_scalar(m, canon, ms + (b * n_fields + field) * 8, mont);
+      if (!canon) {
+        bad = 1;
+        continue;
       }
-      ext_add(acc, q);
-    }
-    __syncthreads();
-    if (active && row < live / 2) {
-#pragma unroll
-      for (int l = 0; l < 8; l++) {
-        mine[l] = acc.X[l];
-        mine[8 + l] = acc.Y[l];
-        mine[16 + l] = acc.Z[l];
-        mine[24 + l] = acc.T[l];
+      if (half == 0) {
+        fixed_base_accumulate(acc, k, tabG);
+      } else {
+        fixed_base_accumulate(acc, k, tabPK);
+        fixed_base_accumulate(acc, m, tabG);
       }
     }
-    __syncthreads();
-    live = half;
   }
+  if (bad) atomicAdd(bad_count + field, 1u);
+  block_reduce_columns(acc, smem, cols, rows_per_block, row, active);
   if (active && row == 0) {
     u32* o = partials + ((size_t)blockIdx.x * cols + col) * 32;
     store_fr(o, acc.X);

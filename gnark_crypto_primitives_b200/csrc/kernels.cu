@@ -48,9 +48,12 @@ __global__ void __launch_bounds__(256) imad_probe_kernel(u32* out, u32 seed) {
   // PROBE_CHAINS independent pairs of 64-bit accumulators; each step is IMAD.WIDE.U32 (carry out) followed by
   // IMAD.WIDE.U32.X (carry in): exactly the two instruction forms the multiplier rows are made of.
   u64 a0[PROBE_CHAINS], a1[PROBE_CHAINS];
+  u32 mult[PROBE_CHAINS];
   u32 x = seed * 2654435761u + threadIdx.x, y = x ^ 0x9e3779b9u;
 #pragma unroll
   for (int c = 0; c < PROBE_CHAINS; c++) {
+    mult[c] = x + c * 0x9e3779b9u;
+    asm volatile("xor.b32 %0, %0, %1;" : "+r"(mult[c]) : "r"(seed));
     a0[c] = ((u64)(blockIdx.x + c) << 32) | (threadIdx.x * 4 + c);
     a1[c] = a0[c] * 0x9e3779b97f4a7c15ull;
   }
@@ -65,21 +68,21 @@ __global__ void __launch_bounds__(256) imad_probe_kernel(u32* out, u32 seed) {
             ".reg .u32 l0, h0, l1, h1;\n\t"
             "mov.b64 {l0, h0}, %0;\n\t"
             "mov.b64 {l1, h1}, %1;\n\t"
-            "mad.lo.cc.u32 l0, h1, %2, l0;\n\t"
-            "madc.hi.cc.u32 h0, h1, %2, h0;\n\t"
-            "madc.lo.cc.u32 l1, l0, %3, l1;\n\t"
-            "madc.hi.u32 h1, l0, %3, h1;\n\t"
+            "mad.lo.cc.u32 l0, %4, %2, l0;\n\t"
+            "madc.hi.cc.u32 h0, %4, %2, h0;\n\t"
+            "madc.lo.cc.u32 l1, %4, %3, l1;\n\t"
+            "madc.hi.u32 h1, %4, %3, h1;\n\t"
             "mov.b64 %0, {l0, h0};\n\t"
             "mov.b64 %1, {l1, h1};\n\t"
             "}"
             : "+l"(a0[c]), "+l"(a1[c])
-            : "r"(x), "r"(y));
+            : "r"(x), "r"(y), "r"(mult[c]));
       }
     }
   }
   u32 r = 0;
 #pragma unroll
-  for (int c = 0; c < PROBE_CHAINS; c++) r ^= lo32(a0[c]) ^ hi32(a0[c]) ^ lo32(a1[c]) ^ hi32(a1[c]);
+  for (int c = 0; c < PROBE_CHAINS; c++) r ^= lo32(a0[c]) ^ hi32(a0[c]) ^ lo32(a1[c]) ^ hi32(a1[c]) ^ mult[c];
   out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
@@ -307,6 +310,18 @@ cudaError_t launch_tally(const u32* ct, size_t n_ballots, int n_fields, int n_bl
   if (e != cudaSuccess) return e;
   tally_partial_kernel<<<n_blocks, TALLY_THREADS, TALLY_THREADS * 32 * sizeof(u32), stream>>>(ct, n_ballots, n_fields, partials,
                                                                                               bad_count, mont);
+  const int cols = n_fields * 2;
+  tally_final_kernel<<<cols, TALLY_THREADS, 0, stream>>>(partials, n_blocks, cols, out_xyz, bad_count, status);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_encrypt_tally(const u32* tabG, const u32* tabPK, const u32* ks, const u32* ms, size_t n_ballots,
+                                 int n_fields, int n_blocks, u32* partials, u32* bad_count, u32* out_xyz, u8* status, int mont,
+                                 cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(bad_count, 0, sizeof(u32) * n_fields, stream);
+  if (e != cudaSuccess) return e;
+  encrypt_tally_partial_kernel<<<n_blocks, TALLY_THREADS, TALLY_THREADS * 32 * sizeof(u32), stream>>>(
+      tabG, tabPK, ks, ms, n_ballots, n_fields, partials, bad_count, mont);
   const int cols = n_fields * 2;
   tally_final_kernel<<<cols, TALLY_THREADS, 0, stream>>>(partials, n_blocks, cols, out_xyz, bad_count, status);
   return cudaGetLastError();

@@ -295,3 +295,23 @@ class Engine:
     def elgamal_tally_dev(self, d_ct, n_ballots, n_fields, d_out, d_status, fmt=FMT_CANONICAL, stream=None):
         self._check(self._lib.gcp_elgamal_tally_dev(self._h, _dptr(d_ct), n_ballots, n_fields, _dptr(d_out),
                                                     _dptr(d_status), fmt, self._stream(stream)))
+
+    def elgamal_encrypt_tally(self, pub_key, k, m, fmt=FMT_CANONICAL):
+        """Fused Encrypt + tally.  k, m: (n_ballots, n_fields, 32) -> ((n_fields, 4, 32), status (n_fields,))."""
+        kk = _as_elems(k, name="k")
+        if kk.ndim != 3:
+            raise ValueError("k must have shape (n_ballots, n_fields, 32)")
+        nb, nf = kk.shape[0], kk.shape[1]
+        mm = _as_elems(m, nb * nf, "m")
+        pk = _as_elems(pub_key, 2, "pub_key")
+        out = np.empty((nf, 4, 32), dtype=np.uint8)
+        status = np.empty(nf, dtype=np.uint8)
+        self._check(self._lib.gcp_elgamal_encrypt_tally(self._h, _ptr(pk), _ptr(kk), _ptr(mm), nb, nf, _ptr(out),
+                                                        _ptr(status), fmt))
+        return out, status
+
+    def elgamal_encrypt_tally_dev(self, d_pub_key, d_k, d_m, n_ballots, n_fields, d_out, d_status, fmt=FMT_CANONICAL,
+                                  stream=None):
+        self._check(self._lib.gcp_elgamal_encrypt_tally_dev(self._h, _dptr(d_pub_key), _dptr(d_k), _dptr(d_m), n_ballots,
+                                                            n_fields, _dptr(d_out), _dptr(d_status), fmt,
+                                                            self._stream(stream)))

@@ -133,6 +133,16 @@ int gcp_elgamal_tally(gcp_ctx* ctx, const void* ct, size_t n_ballots, int n_fiel
 int gcp_elgamal_tally_dev(gcp_ctx* ctx, const void* d_ct, size_t n_ballots, int n_fields, void* d_out,
                           uint8_t* d_status, int fmt, void* stream);
 
+/* Fused Encrypt + tally: out[f] = sum over ballots of Encrypt(pub_key, k[b][f], m[b][f]) without materialising
+ * the ciphertexts (the config-3 shape: 2^24 ballots x 8 fields would be 17 GB of ciphertexts).  k, m: n_ballots x
+ * n_fields scalars; out: n_fields ciphertexts; status: n_fields bytes (4 everywhere if the key is off the curve,
+ * 1 for a field that saw a non-canonical scalar; such items are left out of the sum). */
+int gcp_elgamal_encrypt_tally(gcp_ctx* ctx, const void* pub_key, const void* k, const void* m, size_t n_ballots,
+                              int n_fields, void* out, uint8_t* status, int fmt);
+int gcp_elgamal_encrypt_tally_dev(gcp_ctx* ctx, const void* d_pub_key, const void* d_k, const void* d_m,
+                                  size_t n_ballots, int n_fields, void* d_out, uint8_t* d_status, int fmt,
+                                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -180,3 +180,25 @@ def test_montgomery_format(engine):
     tal, st = engine.elgamal_tally(out.reshape(5, 1, 4, 32), fmt=g.FMT_MONTGOMERY)
     want = eg.serialize(eg.tally([eg.encrypt(PK, k, m) for k, m in zip(ks, ms)]))
     assert [v * rinv % R for v in ints(tal[0])] == want
+
+
+def test_fused_encrypt_tally(engine):
+    rng = random.Random(8)
+    for nb, nf in ((1, 1), (9, 8), (200, 3), (0, 2)):
+        ks = [rng.randrange(R) for _ in range(nb * nf)]
+        ms = [rng.randrange(1 << 16) for _ in range(nb * nf)]
+        k = elems(ks).reshape(nb, nf, 32)
+        m = elems(ms).reshape(nb, nf, 32)
+        out, st = engine.elgamal_encrypt_tally(elems(PK), k, m)
+        assert not st.any()
+        for f in range(nf):
+            ksum = sum(ks[b * nf + f] for b in range(nb)) % ed.ORDER
+            msum = sum(ms[b * nf + f] for b in range(nb)) % ed.ORDER
+            assert ints(out[f]) == eg.serialize(eg.encrypt(PK, ksum, msum))
+        if nb:
+            cts, _ = engine.elgamal_encrypt(elems(PK), k.reshape(-1, 32), m.reshape(-1, 32))
+            tal, _ = engine.elgamal_tally(cts.reshape(nb, nf, 4, 32))
+            assert (tal == out).all()
+    # off-curve key: every field flagged
+    out, st = engine.elgamal_encrypt_tally(elems((1, 2)), elems([1, 2]).reshape(1, 2, 32), elems([3, 4]).reshape(1, 2, 32))
+    assert [int(s) for s in st] == [4, 4]
