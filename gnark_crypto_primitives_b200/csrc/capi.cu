@@ -19,7 +19,7 @@ using namespace gcp;
 namespace {
 
 constexpr uint32_t BLOB_MAGIC = 0x32425350u;  // 'PSB2', written by oracle/gen_constants.py
-constexpr int N_SLOTS = 72;
+constexpr int N_SLOTS = 80;
 
 thread_local std::string g_create_error;
 
@@ -887,6 +887,45 @@ int gcp_elgamal_tally(gcp_ctx* ctx, const void* ct, size_t n_ballots, int n_fiel
   for (size_t c = 0; c < n_chunks; c++)
     for (int f = 0; f < n_fields; f++)
       if (part_status[c * n_fields + f] && !status[f]) status[f] = part_status[c * n_fields + f];
+  return GCP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Keccak address derivation
+// ---------------------------------------------------------------------------------------------------
+int gcp_keccak_address_dev(gcp_ctx* ctx, const void* d_pub_xy_be, size_t n, void* d_out_addr, void* stream) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  if (n == 0) return GCP_OK;
+  if (!d_pub_xy_be || !d_out_addr) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  CU(launch_keccak_address((const u8*)d_pub_xy_be, n, (u8*)d_out_addr, (cudaStream_t)stream), "keccak kernel");
+  ctx->launches++;
+  return GCP_OK;
+}
+
+int gcp_keccak_address(gcp_ctx* ctx, const void* pub_xy_be, size_t n, void* out_addr) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  if (n == 0) return GCP_OK;
+  if (!pub_xy_be || !out_addr) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  const size_t chunk = (size_t)1 << 22;
+  size_t k = 0;
+  for (size_t off = 0; off < n; off += chunk, k++) {
+    size_t m = std::min(chunk, n - off);
+    int s = (int)(k & 1);
+    cudaStream_t st = ctx->stream[s];
+    void* d_in = ctx->buf(68 + s * 2, m * 64);
+    void* d_out = ctx->buf(69 + s * 2, m * 20);
+    if (!d_in || !d_out) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+    CU(cudaMemcpyAsync(d_in, (const char*)pub_xy_be + off * 64, m * 64, cudaMemcpyHostToDevice, st), "H2D");
+    CU(launch_keccak_address((const u8*)d_in, m, (u8*)d_out, st), "keccak kernel");
+    ctx->launches++;
+    CU(cudaMemcpyAsync((char*)out_addr + off * 20, d_out, m * 20, cudaMemcpyDeviceToHost, st), "D2H");
+  }
+  CU(cudaStreamSynchronize(ctx->stream[0]), "stream sync");
+  CU(cudaStreamSynchronize(ctx->stream[1]), "stream sync");
   return GCP_OK;
 }
 

@@ -5,6 +5,7 @@
 #include "poseidon.cuh"
 #include "smt.cuh"
 #include "elgamal.cuh"
+#include "keccak.cuh"
 #include "kernels.h"
 
 #include <algorithm>
@@ -324,6 +325,12 @@ cudaError_t launch_encrypt_tally(const u32* tabG, const u32* tabPK, const u32* k
       tabG, tabPK, ks, ms, n_ballots, n_fields, partials, bad_count, mont);
   const int cols = n_fields * 2;
   tally_final_kernel<<<cols, TALLY_THREADS, 0, stream>>>(partials, n_blocks, cols, out_xyz, bad_count, status);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_keccak_address(const u8* in, size_t n, u8* out, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  keccak_address_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(in, n, out);
   return cudaGetLastError();
 }
 

@@ -77,6 +77,7 @@ cudaError_t launch_ct_neg(const u32* a, size_t n, u32* out, u8* status, cudaStre
 cudaError_t launch_encrypt_tally(const u32* tabG, const u32* tabPK, const u32* ks, const u32* ms, size_t n_ballots,
                                  int n_fields, int n_blocks, u32* partials, u32* bad_count, u32* out_xyz, u8* status, int mont,
                                  cudaStream_t stream);
+cudaError_t launch_keccak_address(const u8* in, size_t n, u8* out, cudaStream_t stream);
 int tally_max_blocks(size_t n_ballots, int n_fields, int sm_count);
 cudaError_t launch_tally(const u32* ct, size_t n_ballots, int n_fields, int n_blocks, u32* partials, u32* bad_count,
                          u32* out_xyz, u8* status, int mont, cudaStream_t stream);

@@ -315,3 +315,15 @@ class Engine:
         self._check(self._lib.gcp_elgamal_encrypt_tally_dev(self._h, _dptr(d_pub_key), _dptr(d_k), _dptr(d_m), n_ballots,
                                                             n_fields, _dptr(d_out), _dptr(d_status), fmt,
                                                             self._stream(stream)))
+
+    # -- Ethereum address ---------------------------------------------------------------------------
+    def keccak_address(self, pub_xy_be):
+        """DeriveAddress (ecc/secp256k1/ecdsa/address.go:14-40): (n, 64) uint8 X_be||Y_be -> (n, 20) uint8."""
+        a = np.ascontiguousarray(pub_xy_be, dtype=np.uint8).reshape(-1, 64)
+        n = a.shape[0]
+        out = np.empty((n, 20), dtype=np.uint8)
+        self._check(self._lib.gcp_keccak_address(self._h, _ptr(a), n, _ptr(out)))
+        return out
+
+    def keccak_address_dev(self, d_in, n, d_out, stream=None):
+        self._check(self._lib.gcp_keccak_address_dev(self._h, _dptr(d_in), n, _dptr(d_out), self._stream(stream)))

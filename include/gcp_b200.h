@@ -143,6 +143,12 @@ int gcp_elgamal_encrypt_tally_dev(gcp_ctx* ctx, const void* d_pub_key, const voi
                                   size_t n_ballots, int n_fields, void* d_out, uint8_t* d_status, int fmt,
                                   void* stream);
 
+/* ---- Ethereum address: ecc/secp256k1/ecdsa/address.go:14-40 ------------------------------------------- */
+/* DeriveAddress: out_addr[i] = Keccak256_legacy(pub_xy_be[i])[12:32], pub_xy_be[i] = X (32 bytes big-endian) ||
+ * Y (32 bytes big-endian).  out_addr: n x 20 bytes (the bytes U8ToVar packs big-endian into one variable). */
+int gcp_keccak_address(gcp_ctx* ctx, const void* pub_xy_be, size_t n, void* out_addr);
+int gcp_keccak_address_dev(gcp_ctx* ctx, const void* d_pub_xy_be, size_t n, void* d_out_addr, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
