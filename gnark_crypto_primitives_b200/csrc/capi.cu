@@ -668,7 +668,7 @@ int gcp_elgamal_tally_dev(gcp_ctx* ctx, const void* d_ct, size_t n_ballots, int 
   return tally_dev_locked(ctx, d_ct, n_ballots, n_fields, d_out, d_status, fmt, (cudaStream_t)stream, 44);
 }
 
-static int encrypt_tally_dev_locked(gcp_ctx* ctx, const void* d_k, const void* d_m, size_t n_ballots, int n_fields,
+static int encrypt_tally_dev_locked(gcp_ctx* ctx, const void* d_k, const void* d_m, const uint8_t* d_mask, size_t n_ballots, int n_fields,
                                     void* d_out, uint8_t* d_status, int fmt, cudaStream_t st, int slot_base) {
   int n_blocks = tally_max_blocks(n_ballots, n_fields, ctx->sm_count);
   const int cols = n_fields * 2;
@@ -676,7 +676,7 @@ static int encrypt_tally_dev_locked(gcp_ctx* ctx, const void* d_k, const void* d
   u32* bad = (u32*)ctx->buf(slot_base + 1, (size_t)n_fields * 4);
   u32* xyz = (u32*)ctx->buf(slot_base + 2, (size_t)cols * 96);
   if (!partials || !bad || !xyz) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
-  CU(launch_encrypt_tally(ctx->d_tabG, ctx->d_tabPK, (const u32*)d_k, (const u32*)d_m, n_ballots, n_fields, n_blocks,
+  CU(launch_encrypt_tally(ctx->d_tabG, ctx->d_tabPK, (const u32*)d_k, (const u32*)d_m, d_mask, n_ballots, n_fields, n_blocks,
                           partials, bad, xyz, d_status, fmt, st),
      "encrypt-tally kernels");
   CU(launch_normalize(xyz, (size_t)cols, (u32*)d_out, d_status, 2, fmt, st), "normalize kernel");
@@ -703,7 +703,7 @@ int gcp_elgamal_encrypt_tally_dev(gcp_ctx* ctx, const void* d_pub_key, const voi
   if (rc != GCP_OK) return rc;
   rc = ensure_pk_table(ctx, d_pub_key, true, fmt, (cudaStream_t)stream);
   if (rc != GCP_OK) return rc;
-  return encrypt_tally_dev_locked(ctx, d_k, d_m, n_ballots, n_fields, d_out, d_status, fmt, (cudaStream_t)stream, 44);
+  return encrypt_tally_dev_locked(ctx, d_k, d_m, nullptr, n_ballots, n_fields, d_out, d_status, fmt, (cudaStream_t)stream, 44);
 }
 
 // Host form: scalars are streamed in chunks, each chunk is encrypted and reduced on the device, and the per-chunk
@@ -738,7 +738,7 @@ int gcp_elgamal_encrypt_tally(gcp_ctx* ctx, const void* pub_key, const void* k, 
       CU(cudaMemcpyAsync(dk, (const char*)k + off * ballot_in, cnt * ballot_in, cudaMemcpyHostToDevice, st), "H2D");
       CU(cudaMemcpyAsync(dm, (const char*)m + off * ballot_in, cnt * ballot_in, cudaMemcpyHostToDevice, st), "H2D");
     }
-    rc = encrypt_tally_dev_locked(ctx, dk, dm, cnt, n_fields, (char*)d_parts + c * ballot_ct, d_part_status + c * n_fields,
+    rc = encrypt_tally_dev_locked(ctx, dk, dm, nullptr, cnt, n_fields, (char*)d_parts + c * ballot_ct, d_part_status + c * n_fields,
                                   fmt, st, 48 + s * 8 + 1);
     if (rc != GCP_OK) return rc;
   }
@@ -888,6 +888,31 @@ int gcp_elgamal_tally(gcp_ctx* ctx, const void* ct, size_t n_ballots, int n_fiel
     for (int f = 0; f < n_fields; f++)
       if (part_status[c * n_fields + f] && !status[f]) status[f] = part_status[c * n_fields + f];
   return GCP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// End-to-end ballot batch (BASELINE config 5): census inclusion proof + ballot encryption + aggregation
+// ---------------------------------------------------------------------------------------------------
+// Per voter: smt.InclusionVerifier on the census proof, then Encrypt of the voter's n_fields values; the ciphertexts
+// of voters whose proof verified (flag 1, status 0) are folded with Ciphertext.Add.  The fold lives in the
+// reference's caller (davinci-node); here it is the masked fused encrypt-tally kernel, so no ciphertext is stored.
+int gcp_ballot_batch_dev(gcp_ctx* ctx, int n_levels, size_t n_voters, const void* d_roots, int shared_root,
+                         const void* d_siblings, const void* d_keys, const void* d_values, const void* d_pub_key,
+                         const void* d_k, const void* d_m, int n_fields, uint8_t* d_flags, uint8_t* d_status,
+                         void* d_tally, uint8_t* d_tally_status, int fmt, void* stream) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = encrypt_tally_check(ctx, d_pub_key, d_k, d_m, n_voters, n_fields, d_tally, d_tally_status, fmt);
+  if (rc != GCP_OK) return rc;
+  rc = ensure_pk_table(ctx, d_pub_key, true, fmt, st);
+  if (rc != GCP_OK) return rc;
+  rc = smt_verify_dev_locked(ctx, n_levels, n_voters, d_roots, shared_root, d_siblings, nullptr, nullptr, nullptr, d_keys,
+                             d_values, nullptr, nullptr, d_flags, d_status, nullptr, fmt, st, 2);
+  if (rc != GCP_OK) return rc;
+  // flags are 0 wherever status != 0 (smt_path_kernel), so the flag array is the admission mask
+  return encrypt_tally_dev_locked(ctx, d_k, d_m, d_flags, n_voters, n_fields, d_tally, d_tally_status, fmt, st, 44);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -458,10 +458,11 @@ __global__ void __launch_bounds__(TALLY_THREADS) tally_partial_kernel(const u32*
 // Fused Encrypt + tally (the ciphertexts are never materialised): thread (row, col) strides over ballots and adds
 // [k]G into the C1 column or [k]PK + [m]G into the C2 column of its field; same reduction as tally_partial_kernel.
 // ks / ms: n_ballots x n_fields scalars.  bad_count[f] counts non-canonical scalars of field f.
+// mask (optional): n_ballots bytes, a ballot is summed only where mask[b] != 0.
 __global__ void __launch_bounds__(TALLY_THREADS) encrypt_tally_partial_kernel(const u32* __restrict__ tabG, const u32* __restrict__ tabPK,
                                                                               const u32* __restrict__ ks, const u32* __restrict__ ms,
-                                                                              size_t n_ballots, int n_fields, u32* __restrict__ partials,
-                                                                              u32* __restrict__ bad_count, int mont) {
+                                                                              const u8* __restrict__ mask, size_t n_ballots, int n_fields,
+                                                                              u32* __restrict__ partials, u32* __restrict__ bad_count, int mont) {
   extern __shared__ u32 smem[];
   const int cols = n_fields * 2;
   const int rows_per_block = TALLY_THREADS / cols;
@@ -476,6 +477,7 @@ __global__ void __launch_bounds__(TALLY_THREADS) encrypt_tally_partial_kernel(co
     size_t bstride = (size_t)gridDim.x * rows_per_block;
 #pragma unroll 1
     for (; b < n_ballots; b += bstride) {
+      if (mask && mask[b] == 0) continue;  // ballot not admitted (e.g. census proof flag 0)
       bool canon = true;
       u32 k[8], m[8];
       load_scalar(k, canon, ks + (b * n_fields + field) * 8, mont);

@@ -74,8 +74,8 @@ cudaError_t launch_normalize(const u32* xyz, size_t n_points, u32* out, u8* stat
                              cudaStream_t stream);
 cudaError_t launch_ct_add(const u32* a, const u32* b, size_t n, u32* out_xyz, u8* status, int mont, cudaStream_t stream);
 cudaError_t launch_ct_neg(const u32* a, size_t n, u32* out, u8* status, cudaStream_t stream);
-cudaError_t launch_encrypt_tally(const u32* tabG, const u32* tabPK, const u32* ks, const u32* ms, size_t n_ballots,
-                                 int n_fields, int n_blocks, u32* partials, u32* bad_count, u32* out_xyz, u8* status, int mont,
+cudaError_t launch_encrypt_tally(const u32* tabG, const u32* tabPK, const u32* ks, const u32* ms, const u8* mask,
+                                 size_t n_ballots, int n_fields, int n_blocks, u32* partials, u32* bad_count, u32* out_xyz, u8* status, int mont,
                                  cudaStream_t stream);
 cudaError_t launch_keccak_address(const u8* in, size_t n, u8* out, cudaStream_t stream);
 int tally_max_blocks(size_t n_ballots, int n_fields, int sm_count);

@@ -327,3 +327,11 @@ class Engine:
 
     def keccak_address_dev(self, d_in, n, d_out, stream=None):
         self._check(self._lib.gcp_keccak_address_dev(self._h, _dptr(d_in), n, _dptr(d_out), self._stream(stream)))
+
+    # -- end-to-end ballot batch (config 5) ---------------------------------------------------------
+    def ballot_batch_dev(self, n_levels, n_voters, d_roots, shared_root, d_siblings, d_keys, d_values, d_pub_key, d_k,
+                         d_m, n_fields, d_flags, d_status, d_tally, d_tally_status, fmt=FMT_CANONICAL, stream=None):
+        self._check(self._lib.gcp_ballot_batch_dev(self._h, n_levels, n_voters, _dptr(d_roots), int(bool(shared_root)),
+                                                   _dptr(d_siblings), _dptr(d_keys), _dptr(d_values), _dptr(d_pub_key),
+                                                   _dptr(d_k), _dptr(d_m), n_fields, _dptr(d_flags), _dptr(d_status),
+                                                   _dptr(d_tally), _dptr(d_tally_status), fmt, self._stream(stream)))

@@ -143,6 +143,16 @@ int gcp_elgamal_encrypt_tally_dev(gcp_ctx* ctx, const void* d_pub_key, const voi
                                   size_t n_ballots, int n_fields, void* d_out, uint8_t* d_status, int fmt,
                                   void* stream);
 
+/* ---- End-to-end ballot batch (BASELINE config 5) ------------------------------------------------------- */
+/* Per voter v: flag[v] = smt.InclusionVerifier(census proof v) (tree/smt/verifier.go:29-43); the tally is the fold of
+ * Ciphertext.Add (elgamal/ciphertext.go:24-32) over Encrypt(pub_key, k[v][f], m[v][f]) (elgamal/encrypt.go:42-64) of
+ * the voters with flag 1.  Device buffers only (2^26 voters x 5.2 KB of proofs do not fit host or one GPU: callers
+ * stream chunks and tally the per-chunk results with gcp_elgamal_tally_dev). */
+int gcp_ballot_batch_dev(gcp_ctx* ctx, int n_levels, size_t n_voters, const void* d_roots, int shared_root,
+                         const void* d_siblings, const void* d_keys, const void* d_values, const void* d_pub_key,
+                         const void* d_k, const void* d_m, int n_fields, uint8_t* d_flags, uint8_t* d_status,
+                         void* d_tally, uint8_t* d_tally_status, int fmt, void* stream);
+
 /* ---- Ethereum address: ecc/secp256k1/ecdsa/address.go:14-40 ------------------------------------------- */
 /* DeriveAddress: out_addr[i] = Keccak256_legacy(pub_xy_be[i])[12:32], pub_xy_be[i] = X (32 bytes big-endian) ||
  * Y (32 bytes big-endian).  out_addr: n x 20 bytes (the bytes U8ToVar packs big-endian into one variable). */
