@@ -455,7 +455,12 @@ int gcp_smt_verify(gcp_ctx* ctx, int n_levels, size_t n, const void* roots, int 
                           fmt);
   if (rc != GCP_OK || n == 0) return rc;
   const size_t sib_bytes = (size_t)n_levels * 32;
-  size_t chunk = std::max<size_t>(1, std::min<size_t>(n, ((size_t)192 << 20) / sib_bytes));
+  // chunk = a whole number of resident-thread waves of smt_path_kernel (5 blocks x 128 threads per SM), about 1 GB of
+  // siblings, so that a chunk's launch fills the machine; two chunks are in flight on the two streams
+  const size_t wave = (size_t)ctx->sm_count * 5 * 128;
+  size_t chunk = std::max<size_t>(1, ((size_t)1 << 30) / sib_bytes);
+  if (chunk > wave) chunk -= chunk % wave;
+  chunk = std::min(chunk, n);
   if (const char* env = getenv("GCP_B200_SMT_CHUNK")) {
     long v = atol(env);
     if (v > 0) chunk = std::min<size_t>(n, (size_t)v);

@@ -17,9 +17,14 @@
 
 namespace gcp {
 
-constexpr int FB_WBITS = 8;
-constexpr int FB_WINDOWS = (256 + FB_WBITS - 1) / FB_WBITS;      // 32
-constexpr int FB_ENTRIES = (1 << FB_WBITS) - 1;                  // 255 non-identity digits
+// Signed fixed windows: a scalar is recoded into FB_WINDOWS digits in [-2^(w-1)+1, 2^(w-1)]; the table holds the
+// positive multiples only (negating a Niels point is a swap and one field negation).  w = 14: 19 windows x 8192
+// entries x 96 B = 14.9 MB per base, so the tables of G and of the election key stay L2-resident (126 MB) while a
+// scalar multiplication costs 19 mixed additions (the reference's 4-bit table, mul.go:26-72, needs up to 63).
+constexpr int FB_WBITS = 14;
+constexpr int FB_WINDOWS = (256 + FB_WBITS - 1) / FB_WBITS;      // 19 (266 bits >= 254-bit scalars + recoding carry)
+constexpr int FB_HALF = 1 << (FB_WBITS - 1);
+constexpr int FB_ENTRIES = FB_HALF;                              // digits 1 .. 2^(w-1)
 constexpr size_t FB_TABLE_WORDS = (size_t)FB_WINDOWS * FB_ENTRIES * 24;  // u32 words per table (96 B entries)
 constexpr int BATCH_INV = 16;
 
@@ -56,7 +61,7 @@ __global__ void fb_table_bases_kernel(const u32* __restrict__ base, int base_mon
   store_fr(o + 24, p.T);
 }
 
-// step 2: ext[w][d-1] = [d] ext[w][0] for d = 2..FB_ENTRIES (double-and-add on d)
+// step 2: ext[w][d-1] = [d] ext[w][0] for d = 2..FB_ENTRIES (double-and-add on d, FB_WBITS bits: d <= 2^(w-1))
 __global__ void fb_table_fill_kernel(u32* __restrict__ ext) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= FB_WINDOWS * FB_ENTRIES) return;
@@ -108,14 +113,27 @@ __global__ void fb_table_niels_kernel(const u32* __restrict__ ext, u32* __restri
   store_fr(o + 16, n.t2d);
 }
 
-// acc += [k] B using B's table; k is a 256-bit integer (canonical Fr element used as an integer)
+// acc += [k] B using B's table; k is an integer < 2^254 (a canonical Fr element used as an integer)
 __device__ __forceinline__ void fixed_base_accumulate(ExtPoint& acc, const u32 (&k)[8], const u32* __restrict__ tab) {
+  u32 carry = 0;
 #pragma unroll 1
   for (int w = 0; w < FB_WINDOWS; w++) {
-    u32 d = scalar_window<FB_WBITS>(k, w);
+    u32 raw = scalar_window<FB_WBITS>(k, w) + carry;
+    bool neg = raw > (u32)FB_HALF;
+    u32 d = neg ? ((1u << FB_WBITS) - raw) : raw;
+    carry = neg ? 1u : 0u;
     if (d != 0) {
       NielsPoint n;
-      load_niels(n, tab + ((size_t)w * FB_ENTRIES + (d - 1)) * 24);
+      const u32* e = tab + ((size_t)w * FB_ENTRIES + (d - 1)) * 24;
+      if (neg) {  // -(x, y) = (-x, y): swaps y-x and y+x, negates 2dxy
+        load_fr(n.ypx, e);
+        load_fr(n.ymx, e + 8);
+        u32 t[8];
+        load_fr(t, e + 16);
+        fr_neg(n.t2d, t);
+      } else {
+        load_niels(n, e);
+      }
       ext_add_niels(acc, n);
     }
   }
@@ -155,29 +173,33 @@ __global__ void __launch_bounds__(128) fixed_base_mul_kernel(const u32* __restri
 }
 
 // ---- Encrypt with one shared public key (the election key) ----------------------------------------------------
-// out_xyz: n x 2 x 24 words: C1 = [k]G, C2 = [k]PK + [m]G as (X, Y, Z).
+// One thread per POINT (2n threads): threads [0, n) compute C1 = [k]G, threads [n, 2n) compute C2 = [k]PK + [m]G
+// (whole warps take the same branch), as (X, Y, Z) into out_xyz (n x 2 x 24 words).  Both halves validate k and m.
 __global__ void __launch_bounds__(128) encrypt_shared_kernel(const u32* __restrict__ tabG, const u32* __restrict__ tabPK,
                                                              const u32* __restrict__ pk_flag, const u32* __restrict__ ks,
                                                              const u32* __restrict__ ms, size_t n, u32* __restrict__ out_xyz,
                                                              u8* __restrict__ status, int mont) {
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n) return;
+  size_t pidx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pidx >= 2 * n) return;
+  const bool second = pidx >= n;
+  size_t idx = second ? pidx - n : pidx;
   bool canon = true;
   u32 k[8], m[8];
   load_scalar(k, canon, ks + idx * 8, mont);
   load_scalar(m, canon, ms + idx * 8, mont);
   bool pk_ok = pk_flag[0] != 0;
-  ExtPoint c1, c2;
-  ext_identity(c1);
-  ext_identity(c2);
+  ExtPoint c;
+  ext_identity(c);
   if (canon && pk_ok) {
-    fixed_base_accumulate(c1, k, tabG);   // encrypt.go:52
-    fixed_base_accumulate(c2, k, tabPK);  // encrypt.go:55
-    fixed_base_accumulate(c2, m, tabG);   // encrypt.go:58,61
+    if (!second) {
+      fixed_base_accumulate(c, k, tabG);   // encrypt.go:52
+    } else {
+      fixed_base_accumulate(c, k, tabPK);  // encrypt.go:55
+      fixed_base_accumulate(c, m, tabG);   // encrypt.go:58,61
+    }
   }
-  store_ext_xyz(out_xyz + idx * 48, c1);
-  store_ext_xyz(out_xyz + idx * 48 + 24, c2);
-  status[idx] = !canon ? GCP_STATUS_NONCANONICAL : (!pk_ok ? GCP_STATUS_OFF_CURVE : GCP_STATUS_OK);
+  store_ext_xyz(out_xyz + (idx * 2 + (second ? 1 : 0)) * 24, c);
+  if (!second) status[idx] = !canon ? GCP_STATUS_NONCANONICAL : (!pk_ok ? GCP_STATUS_OFF_CURVE : GCP_STATUS_OK);
 }
 
 // ---- Encrypt with a public key per item: [k]PK by double-and-add -------------------------------------------------

@@ -243,7 +243,7 @@ static inline unsigned blocks_for(size_t n, int threads) { return (unsigned)((n 
 
 cudaError_t launch_fb_table_build(const u32* d_base_xy, int base_mont, u32* d_ext, u32* d_tab, u32* d_flag,
                                   cudaStream_t stream) {
-  fb_table_bases_kernel<<<1, FB_WINDOWS, 0, stream>>>(d_base_xy, base_mont, d_ext, d_flag);
+  fb_table_bases_kernel<<<1, 32, 0, stream>>>(d_base_xy, base_mont, d_ext, d_flag);
   const int total = FB_WINDOWS * FB_ENTRIES;
   fb_table_fill_kernel<<<blocks_for(total, 64), 64, 0, stream>>>(d_ext);
   fb_table_niels_kernel<<<blocks_for(total, 64), 64, 0, stream>>>(d_ext, d_tab);
@@ -266,7 +266,7 @@ cudaError_t launch_fixed_base_mul(const u32* tabG, const u32* scalars, size_t n,
 cudaError_t launch_encrypt_shared(const u32* tabG, const u32* tabPK, const u32* pk_flag, const u32* ks, const u32* ms,
                                   size_t n, u32* out_xyz, u8* status, int mont, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
-  encrypt_shared_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(tabG, tabPK, pk_flag, ks, ms, n, out_xyz, status, mont);
+  encrypt_shared_kernel<<<blocks_for(2 * n, 128), 128, 0, stream>>>(tabG, tabPK, pk_flag, ks, ms, n, out_xyz, status, mont);
   return cudaGetLastError();
 }
 
