@@ -31,16 +31,18 @@ METRIC = "smt_inclusion_proofs_per_s"
 UNIT = "proofs/s"
 # executed work model of the kernels (DESIGN.md "Kernels"): 32x32->64 multiply-adds per hash
 W_MUL, W_DOT3, W_DOT4, W_REDC = 64, 64, 64, 64
-FR_MUL_WIDE = 128       # 64 (a*b) + 64 (m*p) IMAD.WIDE.U32; + 8 IMAD (m = t*n') counted separately as half-rate-free
+FR_MUL_WIDE = 128       # 64 (a*b) + 64 (m*p) IMAD.WIDE.U32 (+ 8 plain IMAD for m = t*n', not counted)
+FR_SQR_WIDE = 100       # 36 (a^2, doubled cross terms folded into the multiplicand) + 64 (m*p)
 # reference field-mul counts: 594 per Hash2, 772 per Hash1
 REF_MULS_T3, REF_MULS_T4 = 594, 772
 
 
 def wide_per_hash(t, rp):
     """IMAD.WIDE.U32 executed per permutation by poseidon_permute_const<T> (fr.cuh / poseidon.cuh)."""
-    full_sigma = 8 * t * 3 * FR_MUL_WIDE                 # 8 full rounds, x^5 = 3 multiplies
+    sbox = 2 * FR_SQR_WIDE + FR_MUL_WIDE                 # x^5 = two squarings and one multiply
+    full_sigma = 8 * t * sbox                            # 8 full rounds
     dense_mix = 7 * t * (t * 64 + 64) + (t * 64 + 64)    # 7 matrix mixes + last column, lazy dot: t*64 + one reduction
-    partial = rp * (3 * FR_MUL_WIDE + (t * 64 + 64) + (t - 1) * FR_MUL_WIDE)
+    partial = rp * (sbox + (t * 64 + 64) + (t - 1) * FR_MUL_WIDE)
     return full_sigma + dense_mix + partial
 
 

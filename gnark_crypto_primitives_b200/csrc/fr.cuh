@@ -119,6 +119,70 @@ __device__ __forceinline__ void chain4_nc(u64& p0, u64& p1, u64& p2, u64& p3, u3
       : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y));
 }
 
+// Shorter chains for the squaring rows (same structure as chain4).
+__device__ __forceinline__ void chain3(u64& p0, u64& p1, u64& p2, u32& kc, u32 x0, u32 x1, u32 x2, u32 y) {
+  asm("{\n\t"
+      ".reg .u32 l0, h0, l1, h1, l2, h2;\n\t"
+      "mov.b64 {l0, h0}, %0;\n\t"
+      "mov.b64 {l1, h1}, %1;\n\t"
+      "mov.b64 {l2, h2}, %2;\n\t"
+      "mad.lo.cc.u32 l0, %4, %7, l0;\n\t"
+      "madc.hi.cc.u32 h0, %4, %7, h0;\n\t"
+      "madc.lo.cc.u32 l1, %5, %7, l1;\n\t"
+      "madc.hi.cc.u32 h1, %5, %7, h1;\n\t"
+      "madc.lo.cc.u32 l2, %6, %7, l2;\n\t"
+      "madc.hi.cc.u32 h2, %6, %7, h2;\n\t"
+      "addc.u32 %3, %3, 0;\n\t"
+      "mov.b64 %0, {l0, h0};\n\t"
+      "mov.b64 %1, {l1, h1};\n\t"
+      "mov.b64 %2, {l2, h2};\n\t"
+      "}"
+      : "+l"(p0), "+l"(p1), "+l"(p2), "+r"(kc)
+      : "r"(x0), "r"(x1), "r"(x2), "r"(y));
+}
+
+__device__ __forceinline__ void chain2(u64& p0, u64& p1, u32& kc, u32 x0, u32 x1, u32 y) {
+  asm("{\n\t"
+      ".reg .u32 l0, h0, l1, h1;\n\t"
+      "mov.b64 {l0, h0}, %0;\n\t"
+      "mov.b64 {l1, h1}, %1;\n\t"
+      "mad.lo.cc.u32 l0, %3, %5, l0;\n\t"
+      "madc.hi.cc.u32 h0, %3, %5, h0;\n\t"
+      "madc.lo.cc.u32 l1, %4, %5, l1;\n\t"
+      "madc.hi.cc.u32 h1, %4, %5, h1;\n\t"
+      "addc.u32 %2, %2, 0;\n\t"
+      "mov.b64 %0, {l0, h0};\n\t"
+      "mov.b64 %1, {l1, h1};\n\t"
+      "}"
+      : "+l"(p0), "+l"(p1), "+r"(kc)
+      : "r"(x0), "r"(x1), "r"(y));
+}
+
+__device__ __forceinline__ void chain1(u64& p0, u32& kc, u32 x0, u32 y) {
+  asm("{\n\t"
+      ".reg .u32 l0, h0;\n\t"
+      "mov.b64 {l0, h0}, %0;\n\t"
+      "mad.lo.cc.u32 l0, %2, %3, l0;\n\t"
+      "madc.hi.cc.u32 h0, %2, %3, h0;\n\t"
+      "addc.u32 %1, %1, 0;\n\t"
+      "mov.b64 %0, {l0, h0};\n\t"
+      "}"
+      : "+l"(p0), "+r"(kc)
+      : "r"(x0), "r"(y));
+}
+
+__device__ __forceinline__ void chain1_nc(u64& p0, u32 x0, u32 y) {
+  asm("{\n\t"
+      ".reg .u32 l0, h0;\n\t"
+      "mov.b64 {l0, h0}, %0;\n\t"
+      "mad.lo.cc.u32 l0, %1, %2, l0;\n\t"
+      "madc.hi.u32 h0, %1, %2, h0;\n\t"
+      "mov.b64 %0, {l0, h0};\n\t"
+      "}"
+      : "+l"(p0)
+      : "r"(x0), "r"(y));
+}
+
 // w += x * y * 2^(32*I)   (x: 8 limbs, y: one limb).  Products x[j]*y land at limb I+j.
 template <int I>
 __device__ __forceinline__ void mac_row(Wide& w, const u32 (&x)[8], u32 y) {
@@ -162,6 +226,41 @@ __device__ __forceinline__ void wide_mac(Wide& w, const u32 (&a)[8], const u32 (
   mac_row<5>(w, a, b[5]);
   mac_row<6>(w, a, b[6]);
   mac_row<7>(w, a, b[7]);
+}
+
+// w += a^2 for a < 2^255 (every lazy value is < 2r < 2^255): 36 wide multiplies instead of 64.
+// a^2 = sum_i a_i * M_i * 2^(64 i) with M_i = a_i + 2 * (a >> 32(i+1)) * 2^32, whose limbs are
+// (a_i, a_{i+1} << 1, (2a)_{i+2}, ..., (2a)_7): the doubling of the cross terms is folded into the multiplicand.
+__device__ __forceinline__ void wide_sqr(Wide& w, const u32 (&a)[8]) {
+  u32 d[8], e[8];  // d = limbs of 2a, e_j = a_j << 1
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    e[j] = a[j] << 1;
+    d[j] = (j == 0) ? e[0] : __funnelshift_l(a[j - 1], a[j], 1);
+  }
+  // row 0 (limb offset 0): M = (a0, e1, d2, d3, d4, d5, d6, d7)
+  chain4(w.e[0], w.e[1], w.e[2], w.e[3], w.k[0], a[0], d[2], d[4], d[6], a[0]);
+  chain4(w.o[0], w.o[1], w.o[2], w.o[3], w.k[1], e[1], d[3], d[5], d[7], a[0]);
+  // row 1 (offset 2): M = (a1, e2, d3, d4, d5, d6, d7)
+  chain4(w.e[1], w.e[2], w.e[3], w.e[4], w.k[2], a[1], d[3], d[5], d[7], a[1]);
+  chain3(w.o[1], w.o[2], w.o[3], w.k[1], e[2], d[4], d[6], a[1]);
+  // row 2 (offset 4): M = (a2, e3, d4, d5, d6, d7)
+  chain3(w.e[2], w.e[3], w.e[4], w.k[2], a[2], d[4], d[6], a[2]);
+  chain3(w.o[2], w.o[3], w.o[4], w.k[3], e[3], d[5], d[7], a[2]);
+  // row 3 (offset 6): M = (a3, e4, d5, d6, d7)
+  chain3(w.e[3], w.e[4], w.e[5], w.k[4], a[3], d[5], d[7], a[3]);
+  chain2(w.o[3], w.o[4], w.k[3], e[4], d[6], a[3]);
+  // row 4 (offset 8): M = (a4, e5, d6, d7)
+  chain2(w.e[4], w.e[5], w.k[4], a[4], d[6], a[4]);
+  chain2(w.o[4], w.o[5], w.k[5], e[5], d[7], a[4]);
+  // row 5 (offset 10): M = (a5, e6, d7)
+  chain2(w.e[5], w.e[6], w.k[6], a[5], d[7], a[5]);
+  chain1(w.o[5], w.k[5], e[6], a[5]);
+  // row 6 (offset 12): M = (a6, e7)
+  chain1(w.e[6], w.k[6], a[6], a[6]);
+  chain1(w.o[6], w.k[7], e[7], a[6]);
+  // row 7 (offset 14): M = (a7)
+  chain1_nc(w.e[7], a[7], a[7]);
 }
 
 // w += a * R  (places a at limbs 8..15; adds a Montgomery-form constant to a pending dot product)
@@ -310,7 +409,13 @@ __device__ __forceinline__ void fr_mul(u32 (&r)[8], const u32 (&a)[8], const u32
   wide_redc(w, r);
 }
 
-__device__ __forceinline__ void fr_sqr(u32 (&r)[8], const u32 (&a)[8]) { fr_mul(r, a, a); }
+// r = a * a / R, a < 2r
+__device__ __forceinline__ void fr_sqr(u32 (&r)[8], const u32 (&a)[8]) {
+  Wide w;
+  wide_zero(w);
+  wide_sqr(w, a);
+  wide_redc(w, r);
+}
 
 // r = a + b mod 2r
 __device__ __forceinline__ void fr_add(u32 (&r)[8], const u32 (&a)[8], const u32 (&b)[8]) {

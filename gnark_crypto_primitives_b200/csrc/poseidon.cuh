@@ -54,8 +54,8 @@ __device__ __forceinline__ void sigma(u32 (&x)[8]) {
 // Register-resident permutation for small T with tables in constant memory.
 // in/out: lazy Montgomery. s[0] must be the capacity element (0).
 //
-// Code-size discipline: the whole permutation is ONE loop over the 8 + RP rounds and contains exactly three
-// multiplier bodies - (a) the S-box multiply, run 3x per element, (b) one lazy dot-product row (T products + one
+// Code-size discipline: the whole permutation is ONE loop over the 8 + RP rounds and contains exactly four
+// multiplier bodies - (a) the S-box squaring (run twice) and multiply per element, (b) one lazy dot-product row (T products + one
 // reduction), run T times per full round and once per partial round, (c) the rank-1 update multiply of the
 // partial rounds.  Elements are brought to position 0 by rotating the register file instead of unrolling over
 // the state index.  The first version unrolled every round body (~260 KB of SASS) and was bound by instruction
@@ -104,12 +104,8 @@ __device__ __forceinline__ void poseidon_permute_const(u32 (&s)[T][8], u32 (&out
 #pragma unroll
       for (int l = 0; l < 8; l++) y[l] = s[0][l];
 #pragma unroll 1
-      for (int it = 0; it < 3; it++) {
-        u32 b[8];
-#pragma unroll
-        for (int l = 0; l < 8; l++) b[l] = (it < 2) ? y[l] : s[0][l];
-        fr_mul(y, y, b);
-      }
+      for (int it = 0; it < 2; it++) fr_sqr(y, y);
+      fr_mul(y, y, s[0]);
       if (!last) {
         load_const(cst, crow + k * 8);
         fr_add(y, y, cst);
