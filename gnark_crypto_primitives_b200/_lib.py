@@ -24,6 +24,7 @@ STATUS_KEY_RANGE = 2
 STATUS_NOT_BOOLEAN = 3
 STATUS_OFF_CURVE = 4
 STATUS_ZERO_DENOM = 5
+STATUS_ASSERTION = 6
 
 _u8p = POINTER(c_uint8)
 
@@ -67,6 +68,10 @@ SIGNATURES = {
     "gcp_keccak_address_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "gcp_ballot_batch_dev": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "gcp_smt_process": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    "gcp_smt_process_dev": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
 }
 
 _lib = None

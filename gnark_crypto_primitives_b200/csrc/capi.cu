@@ -541,6 +541,91 @@ int gcp_smt_verify_exclusion(gcp_ctx* ctx, int n_levels, size_t n, const void* r
 }
 
 
+// smt.Processor (tree/smt/processor.go:10-72) over a batch
+static int smt_process_check(gcp_ctx* ctx, int n_levels, size_t n, const void* a, const void* b, const void* c,
+                             const void* d, const void* e, const void* f, const void* g, const void* h, const void* i,
+                             const void* j, const void* k, int fmt) {
+  if (n_levels < 2 || n_levels > 253) return ctx->fail(GCP_ERR_BAD_ARG, "n_levels must be in [2, 253]");
+  if (fmt != GCP_FMT_CANONICAL && fmt != GCP_FMT_MONTGOMERY) return ctx->fail(GCP_ERR_BAD_ARG, "bad element format");
+  if (n && (!a || !b || !c || !d || !e || !f || !g || !h || !i || !j || !k)) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  return GCP_OK;
+}
+
+int gcp_smt_process_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_old_roots, const void* d_siblings,
+                        const void* d_old_keys, const void* d_old_values, const uint8_t* d_is_old0,
+                        const void* d_new_keys, const void* d_new_values, const uint8_t* d_fnc0, const uint8_t* d_fnc1,
+                        void* d_new_roots, uint8_t* d_status, int fmt, void* stream) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  int rc = smt_process_check(ctx, n_levels, n, d_old_roots, d_siblings, d_old_keys, d_old_values, d_is_old0, d_new_keys,
+                             d_new_values, d_fnc0, d_fnc1, d_new_roots, d_status, fmt);
+  if (rc != GCP_OK || n == 0) return rc;
+  SmtProcessArgs a;
+  a.n_levels = n_levels;
+  a.n = n;
+  a.old_roots = (const u32*)d_old_roots;
+  a.siblings = (const u32*)d_siblings;
+  a.old_keys = (const u32*)d_old_keys;
+  a.old_values = (const u32*)d_old_values;
+  a.is_old0 = d_is_old0;
+  a.new_keys = (const u32*)d_new_keys;
+  a.new_values = (const u32*)d_new_values;
+  a.fnc0 = d_fnc0;
+  a.fnc1 = d_fnc1;
+  a.new_roots = (u32*)d_new_roots;
+  a.status = d_status;
+  a.mont = fmt;
+  CU(launch_smt_process(a, (cudaStream_t)stream), "smt process kernel");
+  ctx->launches++;
+  return GCP_OK;
+}
+
+int gcp_smt_process(gcp_ctx* ctx, int n_levels, size_t n, const void* old_roots, const void* siblings,
+                    const void* old_keys, const void* old_values, const uint8_t* is_old0, const void* new_keys,
+                    const void* new_values, const uint8_t* fnc0, const uint8_t* fnc1, void* new_roots, uint8_t* status,
+                    int fmt) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = smt_process_check(ctx, n_levels, n, old_roots, siblings, old_keys, old_values, is_old0, new_keys, new_values,
+                               fnc0, fnc1, new_roots, status, fmt);
+    if (rc != GCP_OK || n == 0) return rc;
+  }
+  const size_t sib_bytes = (size_t)n_levels * 32;
+  size_t chunk = std::max<size_t>(1, std::min<size_t>(n, ((size_t)256 << 20) / sib_bytes));
+  for (size_t off = 0; off < n; off += chunk) {
+    size_t m = std::min(chunk, n - off);
+    void *d_sib, *d_e[5];
+    uint8_t* d_b[4];
+    {
+      std::lock_guard<std::mutex> lk(ctx->mu);
+      CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+      d_sib = ctx->buf(10, m * sib_bytes);
+      for (int q = 0; q < 5; q++) d_e[q] = ctx->buf(11 + q, m * 32);
+      void* d_out = ctx->buf(16, m * 32);
+      for (int q = 0; q < 4; q++) d_b[q] = (uint8_t*)ctx->buf(17 + q, m);
+      if (!d_sib || !d_out || !d_e[0] || !d_e[1] || !d_e[2] || !d_e[3] || !d_e[4] || !d_b[0] || !d_b[1] || !d_b[2] || !d_b[3])
+        return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+      cudaStream_t st = ctx->stream[0];
+      const void* src_e[5] = {old_roots, old_keys, old_values, new_keys, new_values};
+      const uint8_t* src_b[3] = {is_old0, fnc0, fnc1};
+      CU(cudaMemcpyAsync(d_sib, (const char*)siblings + off * sib_bytes, m * sib_bytes, cudaMemcpyHostToDevice, st), "H2D");
+      for (int q = 0; q < 5; q++)
+        CU(cudaMemcpyAsync(d_e[q], (const char*)src_e[q] + off * 32, m * 32, cudaMemcpyHostToDevice, st), "H2D");
+      for (int q = 0; q < 3; q++) CU(cudaMemcpyAsync(d_b[q], src_b[q] + off, m, cudaMemcpyHostToDevice, st), "H2D");
+    }
+    int rc = gcp_smt_process_dev(ctx, n_levels, m, d_e[0], d_sib, d_e[1], d_e[2], d_b[0], d_e[3], d_e[4], d_b[1], d_b[2],
+                                 ctx->slot[16].p, d_b[3], fmt, ctx->stream[0]);
+    if (rc != GCP_OK) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaMemcpyAsync((char*)new_roots + off * 32, ctx->slot[16].p, m * 32, cudaMemcpyDeviceToHost, ctx->stream[0]), "D2H");
+    CU(cudaMemcpyAsync(status + off, d_b[3], m, cudaMemcpyDeviceToHost, ctx->stream[0]), "D2H");
+    CU(cudaStreamSynchronize(ctx->stream[0]), "stream sync");
+  }
+  return GCP_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // ElGamal
 // ---------------------------------------------------------------------------------------------------

@@ -30,20 +30,6 @@ struct NielsPoint {  // affine point prepared for mixed addition: (y - x, y + x,
   u32 ymx[8], ypx[8], t2d[8];
 };
 
-__device__ __forceinline__ void fr_copy(u32 (&r)[8], const u32 (&a)[8]) {
-#pragma unroll
-  for (int l = 0; l < 8; l++) r[l] = a[l];
-}
-__device__ __forceinline__ void fr_set_zero(u32 (&r)[8]) {
-#pragma unroll
-  for (int l = 0; l < 8; l++) r[l] = 0;
-}
-__device__ __forceinline__ void fr_set_one(u32 (&r)[8]) {
-  const u32 one[8] = GCP_FR_ONE_MONT;
-#pragma unroll
-  for (int l = 0; l < 8; l++) r[l] = one[l];
-}
-
 __device__ __forceinline__ void ext_identity(ExtPoint& p) {
   fr_set_zero(p.X);
   fr_set_one(p.Y);

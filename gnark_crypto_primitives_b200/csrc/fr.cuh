@@ -485,6 +485,20 @@ __device__ __forceinline__ bool eq256(const u32 (&a)[8], const u32 (&b)[8]) {
   return d == 0;
 }
 
+__device__ __forceinline__ void fr_copy(u32 (&r)[8], const u32 (&a)[8]) {
+#pragma unroll
+  for (int l = 0; l < 8; l++) r[l] = a[l];
+}
+__device__ __forceinline__ void fr_set_zero(u32 (&r)[8]) {
+#pragma unroll
+  for (int l = 0; l < 8; l++) r[l] = 0;
+}
+__device__ __forceinline__ void fr_set_one(u32 (&r)[8]) {
+  const u32 one[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};  // R mod r
+#pragma unroll
+  for (int l = 0; l < 8; l++) r[l] = one[l];
+}
+
 // 128-bit vectorised global access of one 32-byte element (address must be 16-byte aligned)
 __device__ __forceinline__ void load_fr(u32 (&r)[8], const void* p) {
   const uint4* q = reinterpret_cast<const uint4*>(p);

@@ -233,6 +233,12 @@ cudaError_t launch_smt_verify(const SmtArgs& a, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+cudaError_t launch_smt_process(const SmtProcessArgs& a, cudaStream_t stream) {
+  if (a.n == 0) return cudaSuccess;
+  smt_process_kernel<<<(unsigned)((a.n + 127) / 128), 128, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------------
 // ElGamal
 // ---------------------------------------------------------------------------------------------------

@@ -18,6 +18,7 @@ enum : u8 {
   GCP_STATUS_NOT_BOOLEAN = 3,   // enabled / fnc / isOld0 not in {0,1}
   GCP_STATUS_OFF_CURVE = 4,     // public key fails AssertIsOnCurve (elgamal/encrypt.go:49)
   GCP_STATUS_ZERO_DENOM = 5,    // Edwards addition denominator is 0 (only reachable off-curve)
+  GCP_STATUS_ASSERTION = 6,     // an AssertIsEqual of the gadget fails (SMT processor: old root, LevIns, states, key rule)
 };
 
 struct PoseidonTable {  // one per t, device pointers into the global-memory copy
@@ -49,6 +50,23 @@ struct SmtArgs {
   int mont;              // element format: 0 canonical integers, 1 gnark-crypto Montgomery memory
 };
 
+struct SmtProcessArgs {
+  int n_levels;
+  size_t n;
+  const u32* old_roots;   // n x 8
+  const u32* siblings;    // n x n_levels x 8
+  const u32* old_keys;    // n x 8
+  const u32* old_values;  // n x 8
+  const u8* is_old0;      // n
+  const u32* new_keys;    // n x 8
+  const u32* new_values;  // n x 8
+  const u8* fnc0;         // n
+  const u8* fnc1;         // n
+  u32* new_roots;         // n x 8
+  u8* status;             // n
+  int mont;
+};
+
 cudaError_t launch_to_mont(u32* d_elems, size_t n, cudaStream_t stream);
 cudaError_t upload_const_tables(const u32* d_t3, const u32* d_t4, cudaStream_t stream);
 cudaError_t launch_poseidon(const PoseidonTable& tab, const u32* in, u32* out, u8* status, size_t n_items,
@@ -57,6 +75,7 @@ cudaError_t launch_poseidon(const PoseidonTable& tab, const u32* in, u32* out, u
                             cudaStream_t stream);
 double launch_imad_probe(u32* d_out, int blocks, u32 seed, cudaStream_t stream);
 cudaError_t launch_smt_verify(const SmtArgs& a, cudaStream_t stream);
+cudaError_t launch_smt_process(const SmtProcessArgs& a, cudaStream_t stream);
 
 // ElGamal (elgamal.cuh)
 size_t fb_table_bytes();

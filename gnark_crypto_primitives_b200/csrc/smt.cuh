@@ -204,4 +204,204 @@ __global__ void __launch_bounds__(128) smt_path_kernel(SmtArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Processor: state transition (insert / update / delete / nop), values of smt.Processor
+// (/root/reference/tree/smt/processor.go:10-72, processor_sm.go:7-17, processor_level.go:10-27).
+//
+// For boolean selectors the six-state machine reduces to (checked against the literal oracle in tests/):
+//   enabled = fnc0 | fnc1 ;  lidx as in the verifier ;  LevIns asserts siblings[n-1] == 0 when enabled
+//   levels < lidx            : top   -> old_i = H(sw(b_i; old_{i+1}, sib_i)),  new_i = H(sw(b_i; new_{i+1}, sib_i))
+//   level lidx, fnc0 = 0     : upd   -> old = hash1Old, new = hash1New                        (update)
+//   level lidx, fnc0 = 1, isOld0 : old0 -> old = 0, new = hash1New                          (insert into an empty slot)
+//   level lidx.., fnc0 = 1, !isOld0 : bot while the old and new key bits agree (old = hash1Old, new = H(sw(b_i; new_{i+1}, 0))),
+//                              new1 at the first level j where they differ (old = hash1Old, new = H(sw(b_j; hash1New, hash1Old)))
+//   b_i = bit i of the NEW key.  The final-state assertion fails when no terminal state is reached (keys equal).
+//   topL/topR = fnc0 & fnc1 ? (new_0, old_0) : (old_0, new_0) ;  assert oldRoot == topL ;  newRoot = enabled ? topR : oldRoot
+//   assert !(!fnc0 & fnc1 & oldKey != newKey)
+// Assertion failures are reported as status GCP_STATUS_ASSERTION with newRoot = 0.
+// ---------------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ bool key_in_range(const u32 (&ki)[8], int n_levels) {
+  u32 hi = 0;
+#pragma unroll
+  for (int l = 0; l < 8; l++) {
+    int lo_bit = l * 32;
+    if (n_levels <= lo_bit)
+      hi |= ki[l];
+    else if (n_levels < lo_bit + 32)
+      hi |= ki[l] >> (n_levels - lo_bit);
+  }
+  return hi == 0;
+}
+
+__global__ void __launch_bounds__(128) smt_process_kernel(SmtProcessArgs a) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.n) return;
+  const int n = a.n_levels;
+  const u32 fnc0 = a.fnc0[idx], fnc1 = a.fnc1[idx], is0 = a.is_old0[idx];
+  u8 st = GCP_STATUS_OK;
+  if ((fnc0 | fnc1 | is0) > 1u) st = GCP_STATUS_NOT_BOOLEAN;
+  const bool enabled = (fnc0 | fnc1) != 0;
+
+  bool canon = true;
+  u32 okey[8], oval[8], nkey[8], nval[8], oroot[8];
+  load_elem(okey, canon, a.old_keys + idx * 8, a.mont);
+  load_elem(oval, canon, a.old_values + idx * 8, a.mont);
+  load_elem(nkey, canon, a.new_keys + idx * 8, a.mont);
+  load_elem(nval, canon, a.new_values + idx * 8, a.mont);
+  load_fr(oroot, a.old_roots + idx * 8);
+  canon = canon && fr_is_canonical(oroot);
+  const u32* sib = a.siblings + idx * (size_t)n * 8;
+  u32 ok_int[8], nk_int[8];
+  key_integer(ok_int, a.old_keys + idx * 8, a.mont);
+  key_integer(nk_int, a.new_keys + idx * 8, a.mont);
+
+  // sibling scan from the leaf end: canonical check, siblings[n-1] == 0, lidx
+  bool last_zero = true;
+  int lidx = 0;
+  {
+    bool found = false;
+    for (int i = n - 1; i >= 0; i--) {
+      u32 x[8];
+      load_fr(x, sib + (size_t)i * 8);
+      canon = canon && fr_is_canonical(x);
+      bool nz = !is_zero256(x);
+      if (i == n - 1) {
+        last_zero = !nz;
+      } else if (nz && !found) {
+        found = true;
+        lidx = i + 1;
+      }
+    }
+  }
+  if (st == GCP_STATUS_OK && !canon) st = GCP_STATUS_NONCANONICAL;
+  if (st == GCP_STATUS_OK && !(key_in_range(ok_int, n) && key_in_range(nk_int, n))) st = GCP_STATUS_KEY_RANGE;
+  if (st == GCP_STATUS_OK && enabled && !last_zero) st = GCP_STATUS_ASSERTION;  // LevIns (lev_ins.go:16-20)
+  bool keys_equal = eq256(ok_int, nk_int);
+  if (st == GCP_STATUS_OK && fnc0 == 0u && fnc1 == 1u && !keys_equal) st = GCP_STATUS_ASSERTION;  // processor.go:64-70
+
+  // terminal level of the state machine
+  int jterm = lidx;
+  if (st == GCP_STATUS_OK && enabled && fnc0 == 1u && is0 == 0u) {
+    jterm = -1;
+    for (int i = lidx; i < n; i++) {
+      u32 x = ((ok_int[i >> 5] ^ nk_int[i >> 5]) >> (i & 31)) & 1u;
+      if (x) {
+        jterm = i;
+        break;
+      }
+    }
+    if (jterm < 0) st = GCP_STATUS_ASSERTION;  // no terminal state: processor.go:47
+  }
+
+  u32 out[8];
+#pragma unroll
+  for (int l = 0; l < 8; l++) out[l] = 0;
+  if (st == GCP_STATUS_OK) {
+    if (!enabled) {
+      load_fr(out, a.old_roots + idx * 8);  // nop: newRoot = oldRoot
+    } else {
+      // leaf hashes (one inlined copy of the t = 4 permutation)
+      u32 h1old[8], h1new[8], one[8];
+#pragma unroll
+      for (int l = 0; l < 8; l++) one[l] = FR_ONE[l];
+#pragma unroll 1
+      for (int h = 0; h < 2; h++) {
+        u32 kk[8], vv[8], res[8];
+#pragma unroll
+        for (int l = 0; l < 8; l++) {
+          kk[l] = h ? nkey[l] : okey[l];
+          vv[l] = h ? nval[l] : oval[l];
+        }
+        poseidon_hash3(res, kk, vv, one);
+#pragma unroll
+        for (int l = 0; l < 8; l++) {
+          if (h)
+            h1new[l] = res[l];
+          else
+            h1old[l] = res[l];
+        }
+      }
+      const bool is_upd = (fnc0 == 0u), is_old0 = (fnc0 == 1u && is0 == 1u);
+      u32 acc_old[8], acc_new[8], zero[8];
+#pragma unroll
+      for (int l = 0; l < 8; l++) zero[l] = 0;
+      // terminal level
+      if (is_upd) {
+        fr_copy(acc_old, h1old);
+        fr_copy(acc_new, h1new);
+      } else if (is_old0) {
+        fr_copy(acc_old, zero);
+        fr_copy(acc_new, h1new);
+      } else {
+        fr_copy(acc_old, h1old);
+        fr_copy(acc_new, h1new);  // becomes H(sw(b_j; hash1New, hash1Old)) in the first loop iteration below
+      }
+      // walk up: i = jterm (new1 only), jterm-1 .. lidx (bot), lidx-1 .. 0 (top); one inlined copy of Hash2
+      const int start = (is_upd || is_old0) ? lidx - 1 : jterm;
+      for (int i = start; i >= 0; i--) {
+        const u32 bit = (nk_int[i >> 5] >> (i & 31)) & 1u;
+        const bool top = i < lidx;
+        u32 s[8];
+        if (top) {
+          u32 x[8];
+          load_fr(x, sib + (size_t)i * 8);
+          if (a.mont)
+            fr_copy(s, x);
+          else
+            fr_to_mont(s, x);
+        }
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+          if (h == 0 && !top) continue;  // the old chain only hashes on top levels
+          u32 child[8], other[8];
+          if (h == 0) {
+            fr_copy(child, acc_old);
+            fr_copy(other, s);
+          } else {
+            fr_copy(child, acc_new);
+            if (top)
+              fr_copy(other, s);
+            else if (i == jterm)
+              fr_copy(other, h1old);
+            else
+              fr_copy(other, zero);
+          }
+          u32 lft[8], rgt[8], res[8];
+#pragma unroll
+          for (int l = 0; l < 8; l++) {
+            lft[l] = bit ? other[l] : child[l];
+            rgt[l] = bit ? child[l] : other[l];
+          }
+          poseidon_hash2(res, lft, rgt);
+          if (h == 0)
+            fr_copy(acc_old, res);
+          else
+            fr_copy(acc_new, res);
+        }
+      }
+      u32 old_c[8], new_c[8];
+      if (a.mont) {
+        fr_copy(old_c, acc_old);
+        fr_copy(new_c, acc_new);
+        fr_canon(old_c);
+        fr_canon(new_c);
+      } else {
+        fr_from_mont(old_c, acc_old);
+        fr_from_mont(new_c, acc_new);
+      }
+      const bool both = (fnc0 & fnc1) != 0;
+      bool match = both ? eq256(new_c, oroot) : eq256(old_c, oroot);  // ForceEqualIfEnabled, processor.go:60
+      if (!match) {
+        st = GCP_STATUS_ASSERTION;
+      } else {
+#pragma unroll
+        for (int l = 0; l < 8; l++) out[l] = both ? old_c[l] : new_c[l];
+      }
+    }
+  }
+  store_fr(a.new_roots + idx * 8, out);
+  a.status[idx] = st;
+}
+
 }  // namespace gcp

@@ -335,3 +335,22 @@ class Engine:
                                                    _dptr(d_siblings), _dptr(d_keys), _dptr(d_values), _dptr(d_pub_key),
                                                    _dptr(d_k), _dptr(d_m), n_fields, _dptr(d_flags), _dptr(d_status),
                                                    _dptr(d_tally), _dptr(d_tally_status), fmt, self._stream(stream)))
+
+    # -- SMT processor ------------------------------------------------------------------------------
+    def smt_process(self, old_roots, siblings, old_keys, old_values, is_old0, new_keys, new_values, fnc0, fnc1,
+                    fmt=FMT_CANONICAL):
+        """smt.Processor (tree/smt/processor.go:10-72) over a batch -> (new_roots (n, 32), status (n,))."""
+        sib = _as_elems(siblings, name="siblings")
+        if sib.ndim != 3:
+            raise ValueError("siblings must have shape (n, n_levels, 32)")
+        n, n_levels = sib.shape[0], sib.shape[1]
+        args = [_as_elems(x, n, nm) for x, nm in ((old_roots, "old_roots"), (old_keys, "old_keys"),
+                                                  (old_values, "old_values"), (new_keys, "new_keys"),
+                                                  (new_values, "new_values"))]
+        i0, f0, f1 = _u8(is_old0, n, "is_old0"), _u8(fnc0, n, "fnc0"), _u8(fnc1, n, "fnc1")
+        out = np.empty((n, 32), dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.gcp_smt_process(self._h, n_levels, n, _ptr(args[0]), _ptr(sib), _ptr(args[1]),
+                                              _ptr(args[2]), _ptr(i0), _ptr(args[3]), _ptr(args[4]), _ptr(f0), _ptr(f1),
+                                              _ptr(out), _ptr(status), fmt))
+        return out, status

@@ -49,7 +49,8 @@ enum gcp_status {
   GCP_STATUS_KEY_RANGE = 2,    /* SMT key >= 2^n_levels: lowBits/ToBinary assertion, tree/smt/utils.go:11-13 */
   GCP_STATUS_NOT_BOOLEAN = 3,  /* enabled / fnc / isOld0 outside {0,1}: api.Select / api.And assertions */
   GCP_STATUS_OFF_CURVE = 4,    /* AssertIsOnCurve(pubKey), elgamal/encrypt.go:49 */
-  GCP_STATUS_ZERO_DENOM = 5    /* Edwards addition denominator 0 (reachable only with off-curve inputs) */
+  GCP_STATUS_ZERO_DENOM = 5,   /* Edwards addition denominator 0 (reachable only with off-curve inputs) */
+  GCP_STATUS_ASSERTION = 6     /* an AssertIsEqual of the gadget fails (SMT processor, decryption checks) */
 };
 
 /* ---- context ------------------------------------------------------------------------------------ */
@@ -104,6 +105,19 @@ int gcp_smt_verify_exclusion(gcp_ctx* ctx, int n_levels, size_t n, const void* r
                              const void* siblings, const void* old_keys, const void* old_values,
                              const uint8_t* is_old0, const void* keys, uint8_t* out_flags, uint8_t* out_status,
                              void* out_roots, int fmt);
+
+/* smt.Processor (tree/smt/processor.go:10-72): state transition of n independent trees/proofs.
+ * fnc = (fnc0, fnc1): (1,0) insert, (0,1) update, (1,1) delete, (0,0) nop.  Output: new_roots (n elements).
+ * The gadget ASSERTS (old root matches the proof, LevIns, final state, update keeps the key, isOld0 boolean), so a
+ * failing item gets status 6 (or 2/3/1) and new_root = 0. */
+int gcp_smt_process(gcp_ctx* ctx, int n_levels, size_t n, const void* old_roots, const void* siblings,
+                    const void* old_keys, const void* old_values, const uint8_t* is_old0, const void* new_keys,
+                    const void* new_values, const uint8_t* fnc0, const uint8_t* fnc1, void* new_roots, uint8_t* status,
+                    int fmt);
+int gcp_smt_process_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_old_roots, const void* d_siblings,
+                        const void* d_old_keys, const void* d_old_values, const uint8_t* d_is_old0,
+                        const void* d_new_keys, const void* d_new_values, const uint8_t* d_fnc0, const uint8_t* d_fnc1,
+                        void* d_new_roots, uint8_t* d_status, int fmt, void* stream);
 
 /* ---- ElGamal over the a = -1 BN254 twisted Edwards curve: elgamal/ ------------------------------------ */
 /* FixedBaseScalarMulBN254 (elgamal/mul.go:76-166): out[i] = [scalars[i]] G, scalars are Fr elements used as

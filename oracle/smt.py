@@ -226,3 +226,78 @@ class Tree:
         if node[1] == key:
             return dict(exists=True, old_key=key, old_value=node[2], is_old0=0, siblings=sibs)
         return dict(exists=False, old_key=node[1], old_value=node[2], is_old0=0, siblings=sibs)
+
+
+# --------------------------------------------------------------------------------------
+# Processor (state transition: insert / update / delete / nop)
+# --------------------------------------------------------------------------------------
+STATUS_ASSERTION = 6  # an AssertIsEqual of the processor gadget fails (old root mismatch, LevIns, states, key rule)
+
+
+def processor_sm(xor, is0, lev_ins, fnc0, prev_top, prev_old0, prev_bot, prev_new1, prev_na, prev_upd):
+    """processor_sm.go:7-17."""
+    aux1 = prev_top * lev_ins % R
+    aux2 = aux1 * fnc0 % R
+    st_top = (prev_top - aux1) % R
+    st_old0 = aux2 * is0 % R
+    st_new1 = (aux2 - st_old0 + prev_bot) * xor % R
+    st_bot = (1 - xor) * ((aux2 - st_old0 + prev_bot) % R) % R
+    st_upd = (aux1 - aux2) % R
+    st_na = (prev_new1 + prev_old0 + prev_na + prev_upd) % R
+    return st_top, st_old0, st_bot, st_new1, st_na, st_upd
+
+
+def processor_level(st_top, st_old0, st_bot, st_new1, st_upd, sibling, old1leaf, new1leaf, newlrbit, old_child, new_child):
+    """processor_level.go:10-27 (both Hash2 calls evaluated, as in the gadget)."""
+    l, r_ = (sibling, old_child) if newlrbit else (old_child, sibling)            # Switcher
+    old_proof_hash = hash2(l, r_)
+    old_root = (old1leaf * ((st_bot + st_new1 + st_upd) % R) + old_proof_hash * st_top) % R
+    a = (new_child * ((st_top + st_bot) % R) + new1leaf * st_new1) % R
+    b = (sibling * st_top + old1leaf * st_new1) % R
+    l, r_ = (b, a) if newlrbit else (a, b)
+    new_proof_hash = hash2(l, r_)
+    new_root = (new_proof_hash * ((st_top + st_bot + st_new1) % R) + new1leaf * ((st_old0 + st_upd) % R)) % R
+    return old_root, new_root
+
+
+def processor(old_root, siblings, old_key, old_value, is_old0, new_key, new_value, fnc0, fnc1):
+    """processor.go:10-72 -> (new_root, status).  fnc = (1,0) insert, (0,1) update, (1,1) delete, (0,0) nop."""
+    n = len(siblings)
+    vals = [old_root, old_key, old_value, new_key, new_value] + list(siblings)
+    if any(not (0 <= int(v) < R) for v in vals):
+        return 0, STATUS_NONCANONICAL
+    if any(b not in (0, 1) for b in (is_old0, fnc0, fnc1)):
+        return 0, STATUS_NOT_BOOLEAN                                   # AssertIsBoolean / api.Select / api.And
+    if (old_key >> n) or (new_key >> n):
+        return 0, STATUS_KEY_RANGE                                     # lowBits, processor.go:23-24
+    hash1_old = hash1(old_key, old_value)
+    hash1_new = hash1(new_key, new_value)
+    enabled = (fnc0 + fnc1 - fnc0 * fnc1) % R
+    valid, lev_ins = lev_ins_flag(enabled, siblings)                   # LevIns asserts valid == 1 (lev_ins.go:16-20)
+    if valid != 1:
+        return 0, STATUS_ASSERTION
+    xors = [((old_key >> i) & 1) ^ ((new_key >> i) & 1) for i in range(n)]
+    st = []
+    prev = (enabled, 0, 0, 0, (1 - enabled) % R, 0)
+    for i in range(n):
+        prev = processor_sm(xors[i], is_old0, lev_ins[i], fnc0, *prev)
+        st.append(prev)
+    top, old0, bot, new1, na, upd = st[-1]
+    if (na + new1 + old0 + upd) % R != 1:                              # processor.go:47
+        return 0, STATUS_ASSERTION
+    old_lv, new_lv = [0] * n, [0] * n
+    for i in range(n - 1, -1, -1):
+        oc = old_lv[i + 1] if i < n - 1 else 0
+        nc = new_lv[i + 1] if i < n - 1 else 0
+        t, o0, b, n1, _, u = st[i]
+        old_lv[i], new_lv[i] = processor_level(t, o0, b, n1, u, siblings[i], hash1_old, hash1_new,
+                                               (new_key >> i) & 1, oc, nc)
+    both = fnc0 * fnc1
+    top_l, top_r = (new_lv[0], old_lv[0]) if both else (old_lv[0], new_lv[0])   # Switcher(fnc0*fnc1, old, new)
+    if enabled and old_root != top_l:                                  # ForceEqualIfEnabled, processor.go:60
+        return 0, STATUS_ASSERTION
+    new_root = (enabled * ((top_r - old_root) % R) + old_root) % R
+    keys_equal = 1 if old_key == new_key else 0
+    if (1 - fnc0) * fnc1 * (1 - keys_equal) != 0:                      # processor.go:64-70
+        return 0, STATUS_ASSERTION
+    return new_root, STATUS_OK

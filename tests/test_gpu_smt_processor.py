@@ -1,0 +1,102 @@
+"""GPU parity: smt.Processor (insert / update / delete / nop) through the C ABI vs the literal oracle."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import smt as osmt
+from oracle.field import R
+from tests.util import elems, ints
+
+pytestmark = pytest.mark.gpu
+
+
+def run(engine, cases, n_levels):
+    n = len(cases)
+    out, st = engine.smt_process(
+        elems(c["old_root"] for c in cases), elems([s for c in cases for s in c["siblings"]]).reshape(n, n_levels, 32),
+        elems(c["old_key"] for c in cases), elems(c["old_value"] for c in cases),
+        np.array([c["is_old0"] for c in cases], np.uint8), elems(c["new_key"] for c in cases),
+        elems(c["new_value"] for c in cases), np.array([c["fnc0"] for c in cases], np.uint8),
+        np.array([c["fnc1"] for c in cases], np.uint8))
+    want = [osmt.processor(c["old_root"], c["siblings"], c["old_key"], c["old_value"], c["is_old0"], c["new_key"],
+                           c["new_value"], c["fnc0"], c["fnc1"]) for c in cases]
+    return ints(out), [int(s) for s in st], want
+
+
+@pytest.mark.parametrize("n_levels", [8, 32, 160])
+def test_insert_update_delete_on_a_growing_tree(engine, n_levels):
+    rng = random.Random(n_levels)
+    tree = osmt.Tree(n_levels)
+    cases, expect_roots = [], []
+    keys = []
+    for step in range(40):
+        k = rng.getrandbits(n_levels)
+        while k in keys:
+            k = rng.getrandbits(n_levels)
+        v = rng.randrange(R)
+        old_root = tree.root()
+        p = tree.gen_proof(k)
+        tree.add(k, v)
+        keys.append(k)
+        base = dict(old_root=old_root, siblings=p["siblings"], old_key=p["old_key"], old_value=p["old_value"],
+                    is_old0=p["is_old0"], new_key=k, new_value=v)
+        cases.append(dict(base, fnc0=1, fnc1=0))                                   # insert
+        expect_roots.append(tree.root())
+        cases.append(dict(base, old_root=tree.root(), fnc0=1, fnc1=1))             # delete = mirror of insert
+        expect_roots.append(old_root)
+        cases.append(dict(base, fnc0=0, fnc1=0))                                   # nop
+        expect_roots.append(old_root)
+    for k in keys[:12]:                                                            # updates
+        old_root = tree.root()
+        p = tree.gen_proof(k)
+        v2 = rng.randrange(R)
+        tree.add(k, v2)
+        cases.append(dict(old_root=old_root, siblings=p["siblings"], old_key=k, old_value=p["old_value"], is_old0=0,
+                          new_key=k, new_value=v2, fnc0=0, fnc1=1))
+        expect_roots.append(tree.root())
+    roots, status, want = run(engine, cases, n_levels)
+    assert [(r, s) for r, s in zip(roots, status)] == want
+    if n_levels >= 32:   # with 8-bit keys some leaves sit at depth n_levels, which LevIns rejects (status 6) by design
+        assert status == [0] * len(cases)
+        assert roots == expect_roots
+    else:
+        assert all(r == e for r, e, s in zip(roots, expect_roots, status) if s == 0) and status.count(0) > 100
+
+
+def test_assertion_failures(engine):
+    rng = random.Random(9)
+    n_levels = 16
+    tree = osmt.Tree(n_levels)
+    for _ in range(6):
+        tree.add(rng.getrandbits(n_levels), rng.randrange(R))
+    k = rng.getrandbits(n_levels)
+    p = tree.gen_proof(k)
+    assert not p["exists"]
+    good = dict(old_root=tree.root(), siblings=p["siblings"], old_key=p["old_key"], old_value=p["old_value"],
+                is_old0=p["is_old0"], new_key=k, new_value=5, fnc0=1, fnc1=0)
+    existing = tree.gen_proof(p["old_key"]) if not p["is_old0"] else None
+    cases = [
+        dict(good),
+        dict(good, old_root=(good["old_root"] + 1) % R),                 # old root does not match the proof
+        dict(good, is_old0=2),                                           # processor_test.go:60-61
+        dict(good, fnc0=2),
+        dict(good, new_key=k | (1 << n_levels)),                         # lowBits
+        dict(good, siblings=list(p["siblings"][:-1]) + [7]),             # LevIns: siblings[n-1] != 0
+        dict(good, new_value=R),
+        dict(good, fnc0=0, fnc1=1),                                      # update with a different key
+    ]
+    if existing is not None:
+        ek = p["old_key"]
+        cases.append(dict(old_root=tree.root(), siblings=existing["siblings"], old_key=ek, old_value=existing["old_value"],
+                          is_old0=0, new_key=ek, new_value=9, fnc0=1, fnc1=0))   # inserting an existing key
+    roots, status, want = run(engine, cases, n_levels)
+    assert [(r, s) for r, s in zip(roots, status)] == want
+    assert status[0] == 0 and status[1] == 6 and status[2] == 3 and status[3] == 3 and status[4] == 2
+    assert status[5] == 6 and status[6] == 1 and status[7] == 6
+    if existing is not None:
+        assert status[8] == 6
+    # reference's own valid case (processor_test.go:46-57): everything zero, nop
+    z = dict(old_root=0, siblings=[0, 0, 0, 0], old_key=0, old_value=0, is_old0=0, new_key=0, new_value=0, fnc0=0, fnc1=0)
+    roots, status, want = run(engine, [z, dict(z, is_old0=2)], 4)
+    assert (roots, status) == ([0, 0], [0, 3]) and want == [(0, 0), (0, 3)]
