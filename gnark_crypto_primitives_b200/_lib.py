@@ -72,6 +72,11 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     "gcp_smt_process_dev": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "gcp_elgamal_assert_decrypt": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_int]),
+    "gcp_elgamal_verify_decryption_proof": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                    c_size_t, c_void_p, c_void_p, c_int]),
+    "gcp_te_to_rte": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "gcp_rte_to_te": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
 }
 
 _lib = None

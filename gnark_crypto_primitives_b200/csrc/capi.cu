@@ -1006,6 +1006,107 @@ int gcp_ballot_batch_dev(gcp_ctx* ctx, int n_levels, size_t n_voters, const void
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Decryption checks and coordinate conversion: host-buffer forms, one chunk
+// ---------------------------------------------------------------------------------------------------
+namespace {
+struct Upload {
+  const void* host;
+  size_t bytes_per_item;
+};
+}  // namespace
+
+// uploads `ins` (slot 70.. on stream 0), returns device pointers
+static int upload_all(gcp_ctx* ctx, const Upload* ins, int n_ins, size_t n, void** d_ptrs) {
+  for (int i = 0; i < n_ins; i++) {
+    d_ptrs[i] = ctx->buf(70 + i, n * ins[i].bytes_per_item);
+    if (!d_ptrs[i]) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+    CU(cudaMemcpyAsync(d_ptrs[i], ins[i].host, n * ins[i].bytes_per_item, cudaMemcpyHostToDevice, ctx->stream[0]), "H2D");
+  }
+  return GCP_OK;
+}
+
+int gcp_elgamal_assert_decrypt(gcp_ctx* ctx, const void* ct, const void* priv_keys, const void* msgs, size_t n,
+                               uint8_t* out_flags, uint8_t* status, int fmt) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  int rc = check_fmt(ctx, fmt);
+  if (rc != GCP_OK || n == 0) return rc;
+  if (!ct || !priv_keys || !msgs || !out_flags || !status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  Upload ins[3] = {{ct, 128}, {priv_keys, 32}, {msgs, 32}};
+  void* d[3];
+  rc = upload_all(ctx, ins, 3, n, d);
+  if (rc != GCP_OK) return rc;
+  uint8_t* d_flags = (uint8_t*)ctx->buf(77, n);
+  uint8_t* d_status = (uint8_t*)ctx->buf(78, n);
+  if (!d_flags || !d_status) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+  cudaStream_t st = ctx->stream[0];
+  CU(launch_assert_decrypt(ctx->d_tabG, (const u32*)d[0], (const u32*)d[1], (const u32*)d[2], n, d_flags, d_status, fmt, st),
+     "assert-decrypt kernel");
+  ctx->launches++;
+  CU(cudaMemcpyAsync(out_flags, d_flags, n, cudaMemcpyDeviceToHost, st), "D2H");
+  CU(cudaMemcpyAsync(status, d_status, n, cudaMemcpyDeviceToHost, st), "D2H");
+  CU(cudaStreamSynchronize(st), "stream sync");
+  return GCP_OK;
+}
+
+int gcp_elgamal_verify_decryption_proof(gcp_ctx* ctx, const void* pub_keys, const void* ct, const void* msgs,
+                                        const void* a1, const void* a2, const void* z, size_t n, uint8_t* out_flags,
+                                        uint8_t* status, int fmt) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  int rc = check_fmt(ctx, fmt);
+  if (rc != GCP_OK || n == 0) return rc;
+  if (!pub_keys || !ct || !msgs || !a1 || !a2 || !z || !out_flags || !status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  Upload ins[6] = {{pub_keys, 64}, {ct, 128}, {msgs, 32}, {a1, 64}, {a2, 64}, {z, 32}};
+  void* d[6];
+  rc = upload_all(ctx, ins, 6, n, d);
+  if (rc != GCP_OK) return rc;
+  uint8_t* d_flags = (uint8_t*)ctx->buf(77, n);
+  uint8_t* d_status = (uint8_t*)ctx->buf(78, n);
+  if (!d_flags || !d_status) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+  cudaStream_t st = ctx->stream[0];
+  CU(launch_decryption_proof(ctx->d_tabG, ctx->tab[13], (const u32*)d[0], (const u32*)d[1], (const u32*)d[2], (const u32*)d[3],
+                             (const u32*)d[4], (const u32*)d[5], n, d_flags, d_status, fmt, st),
+     "decryption-proof kernel");
+  ctx->launches++;
+  CU(cudaMemcpyAsync(out_flags, d_flags, n, cudaMemcpyDeviceToHost, st), "D2H");
+  CU(cudaMemcpyAsync(status, d_status, n, cudaMemcpyDeviceToHost, st), "D2H");
+  CU(cudaStreamSynchronize(st), "stream sync");
+  return GCP_OK;
+}
+
+static int te_rte_host(gcp_ctx* ctx, const void* in, size_t n_points, void* out, uint8_t* status, int to_rte) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  if (n_points == 0) return GCP_OK;
+  if (!in || !out || !status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  Upload ins[1] = {{in, 64}};
+  void* d[1];
+  int rc = upload_all(ctx, ins, 1, n_points, d);
+  if (rc != GCP_OK) return rc;
+  void* d_out = ctx->buf(76, n_points * 64);
+  uint8_t* d_status = (uint8_t*)ctx->buf(78, n_points);
+  if (!d_out || !d_status) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+  cudaStream_t st = ctx->stream[0];
+  CU(launch_te_rte((const u32*)d[0], n_points, (u32*)d_out, d_status, to_rte, st), "te/rte kernel");
+  ctx->launches++;
+  CU(cudaMemcpyAsync(out, d_out, n_points * 64, cudaMemcpyDeviceToHost, st), "D2H");
+  CU(cudaMemcpyAsync(status, d_status, n_points, cudaMemcpyDeviceToHost, st), "D2H");
+  CU(cudaStreamSynchronize(st), "stream sync");
+  return GCP_OK;
+}
+
+int gcp_te_to_rte(gcp_ctx* ctx, const void* points, size_t n_points, void* out, uint8_t* status) {
+  return te_rte_host(ctx, points, n_points, out, status, 1);
+}
+int gcp_rte_to_te(gcp_ctx* ctx, const void* points, size_t n_points, void* out, uint8_t* status) {
+  return te_rte_host(ctx, points, n_points, out, status, 0);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Keccak address derivation
 // ---------------------------------------------------------------------------------------------------
 int gcp_keccak_address_dev(gcp_ctx* ctx, const void* d_pub_xy_be, size_t n, void* d_out_addr, void* stream) {

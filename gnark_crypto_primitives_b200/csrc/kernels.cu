@@ -6,6 +6,7 @@
 #include "smt.cuh"
 #include "elgamal.cuh"
 #include "keccak.cuh"
+#include "proofs.cuh"
 #include "kernels.h"
 
 #include <algorithm>
@@ -337,6 +338,27 @@ cudaError_t launch_encrypt_tally(const u32* tabG, const u32* tabPK, const u32* k
 cudaError_t launch_keccak_address(const u8* in, size_t n, u8* out, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
   keccak_address_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(in, n, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_assert_decrypt(const u32* tabG, const u32* cts, const u32* privs, const u32* msgs, size_t n, u8* flags,
+                                  u8* status, int mont, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  assert_decrypt_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(tabG, cts, privs, msgs, n, flags, status, mont);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_decryption_proof(const u32* tabG, const PoseidonTable& tab13, const u32* pks, const u32* cts,
+                                    const u32* msgs, const u32* a1s, const u32* a2s, const u32* zs, size_t n, u8* flags,
+                                    u8* status, int mont, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  decryption_proof_kernel<<<blocks_for(n, 64), 64, 0, stream>>>(tabG, tab13, pks, cts, msgs, a1s, a2s, zs, n, flags, status, mont);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_te_rte(const u32* in, size_t n_points, u32* out, u8* status, int to_rte, cudaStream_t stream) {
+  if (n_points == 0) return cudaSuccess;
+  te_rte_kernel<<<blocks_for(n_points, 256), 256, 0, stream>>>(in, n_points, out, status, to_rte);
   return cudaGetLastError();
 }
 

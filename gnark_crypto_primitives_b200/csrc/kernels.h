@@ -97,6 +97,12 @@ cudaError_t launch_encrypt_tally(const u32* tabG, const u32* tabPK, const u32* k
                                  size_t n_ballots, int n_fields, int n_blocks, u32* partials, u32* bad_count, u32* out_xyz, u8* status, int mont,
                                  cudaStream_t stream);
 cudaError_t launch_keccak_address(const u8* in, size_t n, u8* out, cudaStream_t stream);
+cudaError_t launch_assert_decrypt(const u32* tabG, const u32* cts, const u32* privs, const u32* msgs, size_t n, u8* flags,
+                                  u8* status, int mont, cudaStream_t stream);
+cudaError_t launch_decryption_proof(const u32* tabG, const PoseidonTable& tab13, const u32* pks, const u32* cts,
+                                    const u32* msgs, const u32* a1s, const u32* a2s, const u32* zs, size_t n, u8* flags,
+                                    u8* status, int mont, cudaStream_t stream);
+cudaError_t launch_te_rte(const u32* in, size_t n_points, u32* out, u8* status, int to_rte, cudaStream_t stream);
 int tally_max_blocks(size_t n_ballots, int n_fields, int sm_count);
 cudaError_t launch_tally(const u32* ct, size_t n_ballots, int n_fields, int n_blocks, u32* partials, u32* bad_count,
                          u32* out_xyz, u8* status, int mont, cudaStream_t stream);

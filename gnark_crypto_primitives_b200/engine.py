@@ -354,3 +354,47 @@ class Engine:
                                               _ptr(args[2]), _ptr(i0), _ptr(args[3]), _ptr(args[4]), _ptr(f0), _ptr(f1),
                                               _ptr(out), _ptr(status), fmt))
         return out, status
+
+    # -- decryption checks, coordinate conversion ----------------------------------------------------
+    def elgamal_assert_decrypt(self, ct, priv_keys, msgs, fmt=FMT_CANONICAL):
+        """(*Ciphertext).AssertDecrypt (elgamal/ciphertext.go:50-67) -> (flags, status)."""
+        c = _as_elems(ct, name="ct").reshape(-1, 4, 32)
+        n = c.shape[0]
+        p = _as_elems(priv_keys, n, "priv_keys")
+        m = _as_elems(msgs, n, "msgs")
+        flags = np.empty(n, dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.gcp_elgamal_assert_decrypt(self._h, _ptr(c), _ptr(p), _ptr(m), n, _ptr(flags),
+                                                         _ptr(status), fmt))
+        return flags, status
+
+    def elgamal_verify_decryption_proof(self, pub_keys, ct, msgs, a1, a2, z, fmt=FMT_CANONICAL):
+        """DecryptionProof.Verify (elgamal/ciphertext.go:124-168) -> (flags, status)."""
+        c = _as_elems(ct, name="ct").reshape(-1, 4, 32)
+        n = c.shape[0]
+        pk = _as_elems(pub_keys, 2 * n, "pub_keys")
+        m = _as_elems(msgs, n, "msgs")
+        p1 = _as_elems(a1, 2 * n, "a1")
+        p2 = _as_elems(a2, 2 * n, "a2")
+        zz = _as_elems(z, n, "z")
+        flags = np.empty(n, dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.gcp_elgamal_verify_decryption_proof(self._h, _ptr(pk), _ptr(c), _ptr(m), _ptr(p1), _ptr(p2),
+                                                                  _ptr(zz), n, _ptr(flags), _ptr(status), fmt))
+        return flags, status
+
+    def te_to_rte(self, points):
+        """format.FromTEtoRTE (ecc/format/twistededwards.go:42-48): (n, 2, 32) -> ((n, 2, 32), status)."""
+        return self._te_rte(points, self._lib.gcp_te_to_rte)
+
+    def rte_to_te(self, points):
+        """format.FromRTEtoTE (ecc/format/twistededwards.go:29-37)."""
+        return self._te_rte(points, self._lib.gcp_rte_to_te)
+
+    def _te_rte(self, points, fn):
+        p = _as_elems(points, name="points").reshape(-1, 2, 32)
+        n = p.shape[0]
+        out = np.empty((n, 2, 32), dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        self._check(fn(self._h, _ptr(p), n, _ptr(out), _ptr(status)))
+        return out, status

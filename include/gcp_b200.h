@@ -157,6 +157,21 @@ int gcp_elgamal_encrypt_tally_dev(gcp_ctx* ctx, const void* d_pub_key, const voi
                                   size_t n_ballots, int n_fields, void* d_out, uint8_t* d_status, int fmt,
                                   void* stream);
 
+/* (*Ciphertext).AssertDecrypt (elgamal/ciphertext.go:50-67): flag[i] = 1 iff C1, C2 are on the curve (else status 4)
+ * and C2 - [priv]C1 == [m]G. */
+int gcp_elgamal_assert_decrypt(gcp_ctx* ctx, const void* ct, const void* priv_keys, const void* msgs, size_t n,
+                               uint8_t* out_flags, uint8_t* status, int fmt);
+/* DecryptionProof.Verify (elgamal/ciphertext.go:124-168) with hFn = poseidon.MultiHash: flag[i] = 1 iff
+ * z*G == A1 + e*P and z*C1 == A2 + e*D, D = C2 - [msg]G, e = MultiHash(P, P, C1, D, A1, A2); status 4 if any of
+ * P, C1, C2, A1, A2 is off the curve.  pub_keys, a1, a2: n points; ct: n ciphertexts; msgs, z: n elements. */
+int gcp_elgamal_verify_decryption_proof(gcp_ctx* ctx, const void* pub_keys, const void* ct, const void* msgs,
+                                        const void* a1, const void* a2, const void* z, size_t n, uint8_t* out_flags,
+                                        uint8_t* status, int fmt);
+/* format.FromTEtoRTE / FromRTEtoTE (ecc/format/twistededwards.go:29-48): x' = x * (-f) resp. x / (-f), y unchanged,
+ * between circom/iden3 BabyJubJub (a = 168700) and gnark's a = -1 form.  Works in either element format. */
+int gcp_te_to_rte(gcp_ctx* ctx, const void* points, size_t n_points, void* out, uint8_t* status);
+int gcp_rte_to_te(gcp_ctx* ctx, const void* points, size_t n_points, void* out, uint8_t* status);
+
 /* ---- End-to-end ballot batch (BASELINE config 5) ------------------------------------------------------- */
 /* Per voter v: flag[v] = smt.InclusionVerifier(census proof v) (tree/smt/verifier.go:29-43); the tally is the fold of
  * Ciphertext.Add (elgamal/ciphertext.go:24-32) over Encrypt(pub_key, k[v][f], m[v][f]) (elgamal/encrypt.go:42-64) of
