@@ -77,6 +77,7 @@ SIGNATURES = {
                                                     c_size_t, c_void_p, c_void_p, c_int]),
     "gcp_te_to_rte": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "gcp_rte_to_te": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "gcp_eddsa_verify": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_int]),
 }
 
 _lib = None

@@ -1077,6 +1077,32 @@ int gcp_elgamal_verify_decryption_proof(gcp_ctx* ctx, const void* pub_keys, cons
   return GCP_OK;
 }
 
+int gcp_eddsa_verify(gcp_ctx* ctx, const void* pub_keys_te, const void* sig_r_te, const void* sig_s, const void* msgs,
+                     size_t n, uint8_t* out_flags, uint8_t* status, int fmt) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  int rc = check_fmt(ctx, fmt);
+  if (rc != GCP_OK || n == 0) return rc;
+  if (!pub_keys_te || !sig_r_te || !sig_s || !msgs || !out_flags || !status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  Upload ins[4] = {{pub_keys_te, 64}, {sig_r_te, 64}, {sig_s, 32}, {msgs, 32}};
+  void* d[4];
+  rc = upload_all(ctx, ins, 4, n, d);
+  if (rc != GCP_OK) return rc;
+  uint8_t* d_flags = (uint8_t*)ctx->buf(77, n);
+  uint8_t* d_status = (uint8_t*)ctx->buf(78, n);
+  if (!d_flags || !d_status) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+  cudaStream_t st = ctx->stream[0];
+  CU(launch_eddsa_verify(ctx->d_tabG, ctx->tab[6], (const u32*)d[0], (const u32*)d[1], (const u32*)d[2], (const u32*)d[3], n,
+                         d_flags, d_status, fmt, st),
+     "eddsa kernel");
+  ctx->launches++;
+  CU(cudaMemcpyAsync(out_flags, d_flags, n, cudaMemcpyDeviceToHost, st), "D2H");
+  CU(cudaMemcpyAsync(status, d_status, n, cudaMemcpyDeviceToHost, st), "D2H");
+  CU(cudaStreamSynchronize(st), "stream sync");
+  return GCP_OK;
+}
+
 static int te_rte_host(gcp_ctx* ctx, const void* in, size_t n_points, void* out, uint8_t* status, int to_rte) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);

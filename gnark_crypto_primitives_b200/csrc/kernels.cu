@@ -362,4 +362,12 @@ cudaError_t launch_te_rte(const u32* in, size_t n_points, u32* out, u8* status, 
   return cudaGetLastError();
 }
 
+cudaError_t launch_eddsa_verify(const u32* tabG, const PoseidonTable& tab6, const u32* pub_a, const u32* sig_r,
+                                const u32* sig_s, const u32* msgs, size_t n, u8* flags, u8* status, int mont,
+                                cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  eddsa_verify_kernel<<<blocks_for(n, 64), 64, 0, stream>>>(tabG, tab6, pub_a, sig_r, sig_s, msgs, n, flags, status, mont);
+  return cudaGetLastError();
+}
+
 }  // namespace gcp

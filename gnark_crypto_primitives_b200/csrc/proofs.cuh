@@ -7,6 +7,7 @@
 #include "edwards.cuh"
 #include "elgamal.cuh"
 #include "poseidon.cuh"
+#include "smt.cuh"
 
 namespace gcp {
 
@@ -156,6 +157,56 @@ __global__ void __launch_bounds__(64) decryption_proof_kernel(const u32* __restr
       ok = ok && ext_equal(ed, zc1);
       flag = ok ? 1 : 0;
     }
+  }
+  flags[idx] = flag;
+  status[idx] = st;
+}
+
+// ---- EdDSA-Poseidon IsValid (/root/reference/ecc/bn254/eddsa/verifier.go:55-88) ---------------------------------------
+// A, R in TE (circom/iden3) coordinates; h = Poseidon(R.x, R.y, A.x, A.y, msg) on those coordinates (t = 6);
+// A' = RTE(A), R' = RTE(R) asserted on the a = -1 curve; flag = ([S]G == 8*[h]A' + R')  (rteB8 == G, constants.go:11-18).
+__global__ void __launch_bounds__(64) eddsa_verify_kernel(const u32* __restrict__ tabG, PoseidonTable tab6,
+                                                          const u32* __restrict__ pub_a, const u32* __restrict__ sig_r,
+                                                          const u32* __restrict__ sig_s, const u32* __restrict__ msgs, size_t n,
+                                                          u8* __restrict__ flags, u8* __restrict__ status, int mont) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const u32 negf[8] = {0xc9603c7bu, 0x5c62c8e0u, 0x8fabc7f1u, 0xf8382911u, 0x6aa07f4du, 0x7d53da81u, 0x6ba06ab6u, 0x1da7c5b3u};
+  bool canon = true;
+  u32 st6[POSEIDON_MAX_T][8], scratch[POSEIDON_MAX_T][8];
+  u32 s_int[8];
+  // state: [0], R.x, R.y, A.x, A.y, msg (lazy Montgomery)
+  load_elem(st6[1], canon, sig_r + idx * 16, mont);
+  load_elem(st6[2], canon, sig_r + idx * 16 + 8, mont);
+  load_elem(st6[3], canon, pub_a + idx * 16, mont);
+  load_elem(st6[4], canon, pub_a + idx * 16 + 8, mont);
+  load_elem(st6[5], canon, msgs + idx * 8, mont);
+  load_scalar(s_int, canon, sig_s + idx * 8, mont);
+  fr_set_zero(st6[0]);
+  // RTE conversion: x * (-f); y unchanged
+  u32 ax[8], ay[8], rx[8], ry[8];
+  fr_mul(rx, st6[1], negf);
+  fr_copy(ry, st6[2]);
+  fr_mul(ax, st6[3], negf);
+  fr_copy(ay, st6[4]);
+  bool on_curve = ed_is_on_curve(ax, ay) && ed_is_on_curve(rx, ry);  // PointToRTE, verifier.go:46
+  u8 st = !canon ? GCP_STATUS_NONCANONICAL : (!on_curve ? GCP_STATUS_OFF_CURVE : GCP_STATUS_OK);
+  u8 flag = 0;
+  if (st == GCP_STATUS_OK) {
+    u32 h_m[8], h[8];
+    poseidon_permute_generic(st6, scratch, h_m, tab6);
+    fr_from_mont(h, h_m);
+    ExtPoint left, a, r, r1;
+    ext_identity(left);
+    fixed_base_accumulate(left, s_int, tabG);  // [S] rteB8
+    ext_from_affine(a, ax, ay);
+    ext_from_affine(r, rx, ry);
+    ext_scalar_mul(r1, a, h);
+    ext_double(r1);
+    ext_double(r1);
+    ext_double(r1);
+    ext_add(r1, r);
+    flag = ext_equal(left, r1) ? 1 : 0;
   }
   flags[idx] = flag;
   status[idx] = st;

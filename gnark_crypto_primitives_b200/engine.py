@@ -398,3 +398,16 @@ class Engine:
         status = np.empty(n, dtype=np.uint8)
         self._check(fn(self._h, _ptr(p), n, _ptr(out), _ptr(status)))
         return out, status
+
+    def eddsa_verify(self, pub_keys_te, sig_r_te, sig_s, msgs, fmt=FMT_CANONICAL):
+        """eddsa.Verifier.IsValid (ecc/bn254/eddsa/verifier.go:55-88) -> (flags, status)."""
+        s = _as_elems(sig_s, name="sig_s").reshape(-1, 32)
+        n = s.shape[0]
+        a = _as_elems(pub_keys_te, 2 * n, "pub_keys_te")
+        r = _as_elems(sig_r_te, 2 * n, "sig_r_te")
+        m = _as_elems(msgs, n, "msgs")
+        flags = np.empty(n, dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.gcp_eddsa_verify(self._h, _ptr(a), _ptr(r), _ptr(s), _ptr(m), n, _ptr(flags), _ptr(status),
+                                               fmt))
+        return flags, status

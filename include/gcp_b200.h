@@ -167,6 +167,11 @@ int gcp_elgamal_assert_decrypt(gcp_ctx* ctx, const void* ct, const void* priv_ke
 int gcp_elgamal_verify_decryption_proof(gcp_ctx* ctx, const void* pub_keys, const void* ct, const void* msgs,
                                         const void* a1, const void* a2, const void* z, size_t n, uint8_t* out_flags,
                                         uint8_t* status, int fmt);
+/* EdDSA-Poseidon Verifier.IsValid (ecc/bn254/eddsa/verifier.go:55-88): public key A and signature point R in
+ * circom/iden3 TE coordinates, S already reduced mod the subgroup order (types.go:37-49).  flag[i] = the gadget's
+ * result; status 4 where PointToRTE's AssertIsOnCurve would fail. */
+int gcp_eddsa_verify(gcp_ctx* ctx, const void* pub_keys_te, const void* sig_r_te, const void* sig_s, const void* msgs,
+                     size_t n, uint8_t* out_flags, uint8_t* status, int fmt);
 /* format.FromTEtoRTE / FromRTEtoTE (ecc/format/twistededwards.go:29-48): x' = x * (-f) resp. x / (-f), y unchanged,
  * between circom/iden3 BabyJubJub (a = 168700) and gnark's a = -1 form.  Works in either element format. */
 int gcp_te_to_rte(gcp_ctx* ctx, const void* points, size_t n_points, void* out, uint8_t* status);

@@ -102,3 +102,26 @@ def test_te_rte_roundtrip_and_constants(engine):
     assert (back == flat).all()
     bad, st = engine.te_to_rte(elems([R, 1]).reshape(1, 2, 32))
     assert int(st[0]) == 1
+
+
+def test_eddsa_poseidon_verifier(engine):
+    from oracle import eddsa as oeddsa
+
+    rng = random.Random(53)
+    items = []
+    for i in range(9):
+        msg = rng.getrandbits(248)                                  # 31 random bytes, verifier_test.go:44
+        a, r, s = oeddsa.sign(rng.randrange(1, ed.ORDER), rng.randrange(1, ed.ORDER), msg)
+        if i % 3 == 1:
+            msg ^= 1
+        if i % 3 == 2:
+            s = (s + 1) % ed.ORDER
+        items.append((a, r, s, msg))
+    items.append(((1, 2), items[0][1], items[0][2], items[0][3]))   # A off curve -> PointToRTE assertion
+    n = len(items)
+    flags, status = engine.eddsa_verify(elems([c for it in items for c in it[0]]), elems([c for it in items for c in it[1]]),
+                                        elems(it[2] for it in items), elems(it[3] for it in items))
+    want = [oeddsa.is_valid(*it) for it in items]
+    assert [int(f) for f in flags] == [w[0] for w in want]
+    assert [int(s) == 0 for s in status] == [w[1] for w in want]
+    assert [w[0] for w in want] == [1, 0, 0, 1, 0, 0, 1, 0, 0, 0] and int(status[-1]) == 4

@@ -209,3 +209,46 @@ def test_keccak_public_vectors():
     gy = 0x483ADA7726A3C4655DA4FBFC0E1108A8FD17B448A68554199C47D08FFB10D4B8
     assert keccak.derive_address(gx.to_bytes(32, "big") + gy.to_bytes(32, "big")).hex() == \
         "7e5f4552091a69125d5dfcb7b8c2659029395bdf"
+
+
+# ---- SMT processor / EdDSA ---------------------------------------------------------------------
+def test_processor_against_tree_transitions():
+    import random
+
+    rng = random.Random(5)
+    n = 32
+    tree = smt.Tree(n)
+    keys = []
+    for _ in range(25):
+        k, v = rng.getrandbits(n), rng.randrange(R)
+        old_root, p = tree.root(), tree.gen_proof(k)
+        tree.add(k, v)
+        keys.append(k)
+        new_root = tree.root()
+        args = (p["siblings"], p["old_key"], p["old_value"], p["is_old0"], k, v)
+        assert smt.processor(old_root, *args, 1, 0) == (new_root, 0)          # insert
+        assert smt.processor(new_root, *args, 1, 1) == (old_root, 0)          # delete mirrors insert
+        assert smt.processor(old_root, *args, 0, 0) == (old_root, 0)          # nop
+        assert smt.processor((old_root + 1) % R, *args, 1, 0) == (0, smt.STATUS_ASSERTION)
+    for k in keys[:8]:
+        old_root, p = tree.root(), tree.gen_proof(k)
+        v2 = rng.randrange(R)
+        tree.add(k, v2)
+        assert smt.processor(old_root, p["siblings"], k, p["old_value"], 0, k, v2, 0, 1) == (tree.root(), 0)   # update
+    # processor_test.go:46-71: all-zero nop is valid, IsOld0 = 2 is rejected
+    assert smt.processor(0, [0, 0, 0, 0], 0, 0, 0, 0, 0, 0, 0) == (0, 0)
+    assert smt.processor(0, [0, 0, 0, 0], 0, 0, 2, 0, 0, 0, 0) == (0, smt.STATUS_NOT_BOOLEAN)
+
+
+def test_eddsa_oracle_self_consistency():
+    from oracle import eddsa
+
+    a, r, s = eddsa.sign(123456789, 987654321, 42)
+    assert eddsa.is_valid(a, r, s, 42) == (1, True)
+    assert eddsa.is_valid(a, r, s, 43) == (0, True)
+    assert eddsa.is_valid(a, r, s + 1, 42) == (0, True)
+    assert eddsa.is_valid((1, 2), r, s, 42) == (0, False)
+    # rteB8 (ecc/bn254/eddsa/constants.go:11-18) is gnark's base point
+    b8 = (5299619240641551281634865583518297030282874472190772894086521144482721001553,
+          16950150798460657717958625567821834550301663161624707787222815936182638968203)
+    assert ed.te_to_rte(*b8) == ed.G
