@@ -230,6 +230,12 @@ cudaError_t launch_smt_verify(const SmtArgs& a, cudaStream_t stream) {
   smt_leaf_kernel<<<blocks, 128, 0, stream>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  // 5 resident blocks x 36 KB of staging tiles per SM: ask for the large shared-memory carve-out
+  static bool carveout_set = false;
+  if (!carveout_set) {
+    cudaFuncSetAttribute(smt_path_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    carveout_set = true;
+  }
   smt_path_kernel<<<blocks, 128, 0, stream>>>(a);
   return cudaGetLastError();
 }

@@ -113,53 +113,110 @@ __global__ void __launch_bounds__(128) smt_leaf_kernel(SmtArgs a) {
 }
 
 // Pass 2: walk the sibling array from the leaf end: skip the zero tail, then fold Hash2 up to the root.
+//
+// Sibling staging: a warp owns 32 consecutive proofs (lane = proof).  The proof-major array gives every proof
+// SMT_CH consecutive levels as one contiguous, 128-byte aligned run, so the warp streams a chunk of SMT_CH levels
+// for all its 32 proofs with 8 cp.async instructions of 32 x 16 B, each covering four whole 128-byte lines
+// (coalesced, vectorised, every fetched sector used), into a double-buffered shared-memory tile; rows are padded
+// to 144 B so that each lane's LDS.128 reads of its own row are bank-conflict free.  The next chunk is in flight
+// while the current one is hashed, so HBM latency never reaches the integer pipe.
+constexpr int SMT_CH = 4;                       // levels per staged chunk: 4 x 32 B = one 128-byte line per proof
+constexpr int SMT_ROW_WORDS = SMT_CH * 8 + 4;   // 36 words = 144 B row stride
+constexpr int SMT_WARPS = 4;                    // 128 threads per block
+
+__device__ __forceinline__ void smt_stage_chunk(u32* tile, const u32* __restrict__ siblings, size_t warp_base, size_t n_total,
+                                                int n_levels, int chunk, int lane) {
+  const int part = lane & 7;                    // 16-byte piece of the 128-byte run
+  const int level = chunk * SMT_CH + (part >> 1);
+#pragma unroll
+  for (int t = 0; t < 8; t++) {
+    const int p = t * 4 + (lane >> 3);          // proof within the warp
+    u32* dst = tile + p * SMT_ROW_WORDS + part * 4;
+    const size_t proof = warp_base + p;
+    if (proof < n_total && level < n_levels) {
+      const u32* src = siblings + (proof * (size_t)n_levels + (size_t)chunk * SMT_CH) * 8 + part * 4;
+      unsigned saddr = (unsigned)__cvta_generic_to_shared(dst);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(src) : "memory");
+    } else {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(128) smt_path_kernel(SmtArgs a) {
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= a.n) return;
+  __shared__ __align__(16) u32 tiles[2][SMT_WARPS][32 * SMT_ROW_WORDS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t warp_base = (size_t)blockIdx.x * blockDim.x + warp * 32;
+  if (warp_base >= a.n) return;                 // whole warp out of range
+  const size_t idx = warp_base + lane;
+  const bool in_range = idx < a.n;
+  const size_t sidx = in_range ? idx : a.n - 1; // out-of-range lanes shadow the last proof and store nothing
   const int n = a.n_levels;
-  u8 st = a.status[idx];
-  u32 fnc = a.fnc ? a.fnc[idx] : 0u;
-  u32 is0 = a.is_old0 ? a.is_old0[idx] : 0u;
-  u32 en = a.enabled ? a.enabled[idx] : 1u;
-  const u32* sib = a.siblings + idx * (size_t)n * 8;
+  u8 st = a.status[sidx];
+  u32 fnc = a.fnc ? a.fnc[sidx] : 0u;
+  u32 is0 = a.is_old0 ? a.is_old0[sidx] : 0u;
+  u32 en = a.enabled ? a.enabled[sidx] : 1u;
 
   u32 acc[8];
-  load_fr(acc, a.leaf + idx * 8);
+  load_fr(acc, a.leaf + sidx * 8);
   u32 key[8];
-  key_integer(key, a.keys + idx * 8, a.mont);
+  key_integer(key, a.keys + sidx * 8, a.mont);
 
-  bool live = (st == GCP_STATUS_OK) && (en == 1u);
+  const bool live = in_range && (st == GCP_STATUS_OK) && (en == 1u);
   bool canon = true;
   bool last_zero = true;
   bool started = false;  // true once a non-zero sibling among [0, n-2] has been seen (i < lidx from then on)
-  for (int i = n - 1; i >= 0; i--) {
-    if (!live) break;
-    u32 x[8];
-    load_fr(x, sib + (size_t)i * 8);
-    canon = canon && fr_is_canonical(x);
-    bool nz = !is_zero256(x);
-    if (i == n - 1) {
-      last_zero = !nz;  // LevInsFlag rule 1; this sibling never takes part in the fold
-      continue;
-    }
-    started = started || nz;
-    if (!started) continue;
-    u32 s[8];
-    if (a.mont) {
-#pragma unroll
-      for (int l = 0; l < 8; l++) s[l] = x[l];
+  const int n_chunks = (n + SMT_CH - 1) / SMT_CH;
+  smt_stage_chunk(tiles[(n_chunks - 1) & 1][warp], a.siblings, warp_base, a.n, n, n_chunks - 1, lane);
+#pragma unroll 1
+  for (int c = n_chunks - 1; c >= 0; c--) {
+    if (c > 0) {
+      smt_stage_chunk(tiles[(c - 1) & 1][warp], a.siblings, warp_base, a.n, n, c - 1, lane);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
     } else {
-      fr_to_mont(s, x);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    u32 bit = (key[i >> 5] >> (i & 31)) & 1u;
-    u32 lft[8], rgt[8];
+    __syncwarp();
+    const u32* row = tiles[c & 1][warp] + lane * SMT_ROW_WORDS;
+    const int hi = min(n, c * SMT_CH + SMT_CH) - 1;
+#pragma unroll 1
+    for (int i = hi; i >= c * SMT_CH; i--) {
+      if (!live) continue;
+      u32 x[8];
+      {
+        const uint4* q = reinterpret_cast<const uint4*>(row + (i - c * SMT_CH) * 8);
+        uint4 v0 = q[0], v1 = q[1];
+        x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
+        x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+      }
+      canon = canon && fr_is_canonical(x);
+      bool nz = !is_zero256(x);
+      if (i == n - 1) {
+        last_zero = !nz;  // LevInsFlag rule 1; this sibling never takes part in the fold
+        continue;
+      }
+      started = started || nz;
+      if (!started) continue;
+      u32 s[8];
+      if (a.mont) {
 #pragma unroll
-    for (int l = 0; l < 8; l++) {  // Switcher (utils.go:50-56)
-      lft[l] = bit ? s[l] : acc[l];
-      rgt[l] = bit ? acc[l] : s[l];
+        for (int l = 0; l < 8; l++) s[l] = x[l];
+      } else {
+        fr_to_mont(s, x);
+      }
+      u32 bit = (key[i >> 5] >> (i & 31)) & 1u;
+      u32 lft[8], rgt[8];
+#pragma unroll
+      for (int l = 0; l < 8; l++) {  // Switcher (utils.go:50-56)
+        lft[l] = bit ? s[l] : acc[l];
+        rgt[l] = bit ? acc[l] : s[l];
+      }
+      poseidon_hash2(acc, lft, rgt);
     }
-    poseidon_hash2(acc, lft, rgt);
+    __syncwarp();  // everyone is done with this buffer before it is refilled two chunks later
   }
+  if (!in_range) return;
 
   u8 flag = 0;
   u32 root_c[8];
