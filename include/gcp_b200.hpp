@@ -1,0 +1,152 @@
+// gcp_b200.hpp — header-only C++ mirror of the reference's Go-facing names over the C ABI (gcp_b200.h).
+// Same names, argument meaning and error behaviour as vocdoni/gnark-crypto-primitives, but batched:
+//   poseidon::Hash / MultiHash        hash/native/bn254/poseidon/poseidon.go:38,54
+//   smt::InclusionVerifier / ExclusionVerifier / Verifier / Processor   tree/smt/verifier.go:29,66,102, processor.go:10
+//   elgamal::Encrypt / Add / Neg / Tally / FixedBaseScalarMulBN254       elgamal/encrypt.go:42, ciphertext.go:24,37, mul.go:76
+// Errors of the reference ("bad inputs provided", ...) surface as gcp::Error; per-item assertion failures as status
+// bytes; flags as the gadget's 0/1 result.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "gcp_b200.h"
+
+namespace gcp {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+using Element = std::array<uint8_t, 32>;  // little-endian; canonical integer or gnark-crypto Montgomery memory
+
+class Engine {
+ public:
+  explicit Engine(int device = 0, const char* constants_path = nullptr) {
+    int rc = gcp_ctx_create(device, constants_path, &ctx_);
+    if (rc != GCP_OK) throw Error(rc, gcp_last_error(nullptr));
+  }
+  ~Engine() { gcp_ctx_destroy(ctx_); }
+  Engine(const Engine&) = delete;
+  Engine& operator=(const Engine&) = delete;
+  gcp_ctx* raw() const { return ctx_; }
+  void check(int rc) const {
+    if (rc != GCP_OK) throw Error(rc, gcp_last_error(ctx_));
+  }
+
+ private:
+  gcp_ctx* ctx_ = nullptr;
+};
+
+struct Batch {
+  std::vector<uint8_t> values;  // n x (elements) x 32 bytes
+  std::vector<uint8_t> status;  // n
+  std::vector<uint8_t> flags;   // n (verifiers only)
+};
+
+namespace poseidon {
+// n rows of `arity` inputs -> n digests.  arity outside 1..16 throws "bad inputs provided" (poseidon.go:41-43).
+inline Batch Hash(const Engine& e, const uint8_t* inputs, int arity, size_t n, int fmt = GCP_FMT_CANONICAL) {
+  Batch b;
+  b.values.resize(n * 32);
+  b.status.resize(n);
+  e.check(gcp_poseidon_hash(e.raw(), inputs, arity, n, b.values.data(), b.status.data(), fmt));
+  return b;
+}
+inline Batch MultiHash(const Engine& e, const uint8_t* inputs, int len, size_t n, int fmt = GCP_FMT_CANONICAL) {
+  Batch b;
+  b.values.resize(n * 32);
+  b.status.resize(n);
+  e.check(gcp_poseidon_multihash(e.raw(), inputs, len, n, b.values.data(), b.status.data(), fmt));
+  return b;
+}
+}  // namespace poseidon
+
+namespace smt {
+inline Batch InclusionVerifier(const Engine& e, int n_levels, size_t n, const uint8_t* roots, bool shared_root,
+                               const uint8_t* siblings, const uint8_t* keys, const uint8_t* values,
+                               int fmt = GCP_FMT_CANONICAL) {
+  Batch b;
+  b.flags.resize(n);
+  b.status.resize(n);
+  e.check(gcp_smt_verify_inclusion(e.raw(), n_levels, n, roots, shared_root, siblings, keys, values, b.flags.data(),
+                                   b.status.data(), nullptr, fmt));
+  return b;
+}
+inline Batch ExclusionVerifier(const Engine& e, int n_levels, size_t n, const uint8_t* roots, bool shared_root,
+                               const uint8_t* siblings, const uint8_t* old_keys, const uint8_t* old_values,
+                               const uint8_t* is_old0, const uint8_t* keys, int fmt = GCP_FMT_CANONICAL) {
+  Batch b;
+  b.flags.resize(n);
+  b.status.resize(n);
+  e.check(gcp_smt_verify_exclusion(e.raw(), n_levels, n, roots, shared_root, siblings, old_keys, old_values, is_old0, keys,
+                                   b.flags.data(), b.status.data(), nullptr, fmt));
+  return b;
+}
+inline Batch Verifier(const Engine& e, int n_levels, size_t n, const uint8_t* enabled, const uint8_t* roots, bool shared_root,
+                      const uint8_t* siblings, const uint8_t* old_keys, const uint8_t* old_values, const uint8_t* is_old0,
+                      const uint8_t* keys, const uint8_t* values, const uint8_t* fnc, int fmt = GCP_FMT_CANONICAL) {
+  Batch b;
+  b.flags.resize(n);
+  b.status.resize(n);
+  e.check(gcp_smt_verify(e.raw(), n_levels, n, roots, shared_root, siblings, old_keys, old_values, is_old0, keys, values, fnc,
+                         enabled, b.flags.data(), b.status.data(), nullptr, fmt));
+  return b;
+}
+// returns the new roots in `values`
+inline Batch Processor(const Engine& e, int n_levels, size_t n, const uint8_t* old_roots, const uint8_t* siblings,
+                       const uint8_t* old_keys, const uint8_t* old_values, const uint8_t* is_old0, const uint8_t* new_keys,
+                       const uint8_t* new_values, const uint8_t* fnc0, const uint8_t* fnc1, int fmt = GCP_FMT_CANONICAL) {
+  Batch b;
+  b.values.resize(n * 32);
+  b.status.resize(n);
+  e.check(gcp_smt_process(e.raw(), n_levels, n, old_roots, siblings, old_keys, old_values, is_old0, new_keys, new_values, fnc0,
+                          fnc1, b.values.data(), b.status.data(), fmt));
+  return b;
+}
+}  // namespace smt
+
+namespace elgamal {
+// ciphertexts are 4 elements in Serialize() order: C1.X, C1.Y, C2.X, C2.Y (ciphertext.go:98-105)
+inline Batch Encrypt(const Engine& e, const uint8_t* pub_key, bool pk_per_item, const uint8_t* k, const uint8_t* m, size_t n,
+                     int fmt = GCP_FMT_CANONICAL) {
+  Batch b;
+  b.values.resize(n * 128);
+  b.status.resize(n);
+  e.check(gcp_elgamal_encrypt(e.raw(), pub_key, pk_per_item, k, m, n, b.values.data(), b.status.data(), fmt));
+  return b;
+}
+inline Batch FixedBaseScalarMulBN254(const Engine& e, const uint8_t* scalars, size_t n, int fmt = GCP_FMT_CANONICAL) {
+  Batch b;
+  b.values.resize(n * 64);
+  b.status.resize(n);
+  e.check(gcp_elgamal_fixed_base_mul(e.raw(), scalars, n, b.values.data(), b.status.data(), fmt));
+  return b;
+}
+inline Batch Add(const Engine& e, const uint8_t* x, const uint8_t* y, size_t n, int fmt = GCP_FMT_CANONICAL) {
+  Batch b;
+  b.values.resize(n * 128);
+  b.status.resize(n);
+  e.check(gcp_elgamal_add(e.raw(), x, y, n, b.values.data(), b.status.data(), fmt));
+  return b;
+}
+inline Batch Neg(const Engine& e, const uint8_t* x, size_t n, int fmt = GCP_FMT_CANONICAL) {
+  Batch b;
+  b.values.resize(n * 128);
+  b.status.resize(n);
+  e.check(gcp_elgamal_neg(e.raw(), x, n, b.values.data(), b.status.data(), fmt));
+  return b;
+}
+inline Batch Tally(const Engine& e, const uint8_t* ct, size_t n_ballots, int n_fields, int fmt = GCP_FMT_CANONICAL) {
+  Batch b;
+  b.values.resize((size_t)n_fields * 128);
+  b.status.resize(n_fields);
+  e.check(gcp_elgamal_tally(e.raw(), ct, n_ballots, n_fields, b.values.data(), b.status.data(), fmt));
+  return b;
+}
+}  // namespace elgamal
+
+}  // namespace gcp
