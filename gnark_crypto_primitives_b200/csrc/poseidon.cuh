@@ -128,7 +128,7 @@ __device__ __forceinline__ void poseidon_permute_const(u32 (&s)[T][8], u32 (&out
         load_const(cst, coef + j * jstride + i * 8);
         wide_mac(w, s[j], cst);
       }
-      rotate_left<T>(n);
+      if (full) rotate_left<T>(n);  // a partial round has a single row: it lands in n[T-1] directly
       wide_redc(w, n[T - 1]);
       cond_sub(n[T - 1], P2);
     }
@@ -140,24 +140,18 @@ __device__ __forceinline__ void poseidon_permute_const(u32 (&s)[T][8], u32 (&out
           for (int l = 0; l < 8; l++) s[j][l] = n[j][l];
       }
     } else {
-      // (c) s_k += s_0 * S[(2T-1)pr + T + k - 1], k = 1..T-1, with the post-S-box s_0 (poseidon.go:162-164)
+      // (c) s_k += s_0 * S[(2T-1)pr + T + k - 1], k = 1..T-1, with the post-S-box s_0 (poseidon.go:162-164);
+      // unrolled over k (T-1 multiplier bodies) so that no register rotation is needed in the hot loop
       const u32* srow = S + ((2 * T - 1) * (r - 4) + T) * 8;
-      u32 s0[8];
 #pragma unroll
-      for (int l = 0; l < 8; l++) {
-        s0[l] = s[0][l];
-        s[0][l] = n[T - 1][l];
-      }
-      rotate_left<T>(s);  // s = (s_1, ..., s_{T-1}, n0)
-#pragma unroll 1
       for (int k = 1; k < T; k++) {
         u32 prod[8];
         load_const(cst, srow + (k - 1) * 8);
-        fr_mul(prod, s0, cst);
-        fr_add(s[0], s[0], prod);
-        rotate_left<T>(s);
+        fr_mul(prod, s[0], cst);
+        fr_add(s[k], s[k], prod);
       }
-      // after T-1 more rotations: s = (n0, s_1', ..., s_{T-1}')
+#pragma unroll
+      for (int l = 0; l < 8; l++) s[0][l] = n[T - 1][l];
     }
   }
 #pragma unroll
