@@ -420,14 +420,42 @@ static int smt_verify_dev_locked(gcp_ctx* ctx, int n_levels, size_t n, const voi
   a.values = (const u32*)d_values;
   a.fnc = d_fnc;
   a.enabled = d_enabled;
-  a.leaf = (u32*)ctx->buf(leaf_slot, n * 32);
-  if (!a.leaf) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed (leaf scratch)");
+  // one scratch slot: leaf hashes | perm | lidx | info | hist | cursor
+  const size_t off_perm = n * 32, off_lidx = off_perm + n * 4, off_info = off_lidx + ((n * 2 + 15) & ~(size_t)15);
+  const size_t off_hist = off_info + ((n + 15) & ~(size_t)15), off_cur = off_hist + 1024, total = off_cur + 1024;
+  char* scratch = (char*)ctx->buf(leaf_slot, total);
+  if (!scratch) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed (smt scratch)");
+  a.leaf = (u32*)scratch;
+  SmtScratch sc;
+  sc.perm = (u32*)(scratch + off_perm);
+  sc.lidx = (u16*)(scratch + off_lidx);
+  sc.info = (u8*)(scratch + off_info);
+  sc.hist = (u32*)(scratch + off_hist);
+  sc.cursor = (u32*)(scratch + off_cur);
+  if (n > 0xffffffffull) return ctx->fail(GCP_ERR_BAD_ARG, "at most 2^32 - 1 proofs per call");
   a.flags = d_flags;
   a.status = d_status;
   a.out_roots = (u32*)d_out_roots;
   a.mont = fmt;
-  CU(launch_smt_verify(a, st), "smt kernels");
-  ctx->launches += 2;
+  CU(launch_smt_verify(a, sc, ctx->sm_count, st), "smt kernels");
+  ctx->launches += 5;
+  return GCP_OK;
+}
+
+// Proof-streaming scan on its own (the HBM-bound pass of the verifier): per proof lidx = number of path levels that
+// carry a hash (1 + index of the last non-zero sibling among [0, n-2]) and an info byte (bit 0: siblings[n-1] == 0,
+// bit 1: every sibling canonical).
+int gcp_smt_scan_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_siblings, uint16_t* d_lidx, uint8_t* d_info,
+                     void* stream) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  if (n_levels < 2 || n_levels > 253) return ctx->fail(GCP_ERR_BAD_ARG, "n_levels must be in [2, 253]");
+  if (n == 0) return GCP_OK;
+  if (!d_siblings || !d_lidx || !d_info) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  CU(launch_smt_scan((const u32*)d_siblings, n, n_levels, d_lidx, d_info, nullptr, ctx->sm_count, (cudaStream_t)stream),
+     "smt scan kernel");
+  ctx->launches++;
   return GCP_OK;
 }
 

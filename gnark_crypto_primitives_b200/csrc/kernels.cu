@@ -224,19 +224,36 @@ cudaError_t launch_poseidon(const PoseidonTable& tab, const u32* in, u32* out, u
 // ---------------------------------------------------------------------------------------------------
 // SMT
 // ---------------------------------------------------------------------------------------------------
-cudaError_t launch_smt_verify(const SmtArgs& a, cudaStream_t stream) {
+cudaError_t launch_smt_scan(const u32* siblings, size_t n, int n_levels, u16* lidx, u8* info, u32* hist, int sm_count,
+                            cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  size_t warps_needed = n;
+  unsigned blocks = (unsigned)std::min<size_t>((warps_needed + 7) / 8, (size_t)sm_count * 8);
+  smt_scan_kernel<<<blocks, 256, 0, stream>>>(siblings, n, n_levels, lidx, info, hist);
+  return cudaGetLastError();
+}
+
+// scan (HBM-bound) -> counting sort by path length -> leaf hashes -> path fold
+cudaError_t launch_smt_verify(const SmtArgs& a, const SmtScratch& sc, int sm_count, cudaStream_t stream) {
   if (a.n == 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(sc.hist, 0, 256 * sizeof(u32), stream);
+  if (e != cudaSuccess) return e;
+  e = launch_smt_scan(a.siblings, a.n, a.n_levels, sc.lidx, sc.info, sc.hist, sm_count, stream);
+  if (e != cudaSuccess) return e;
+  smt_sort_prefix_kernel<<<1, 256, 0, stream>>>(sc.hist, sc.cursor);
+  unsigned blocks256 = (unsigned)((a.n + 255) / 256);
+  smt_sort_scatter_kernel<<<blocks256, 256, 0, stream>>>(sc.lidx, a.n, sc.cursor, sc.perm);
   unsigned blocks = (unsigned)((a.n + 127) / 128);
   smt_leaf_kernel<<<blocks, 128, 0, stream>>>(a);
-  cudaError_t e = cudaGetLastError();
+  e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  // 5 resident blocks x 36 KB of staging tiles per SM: ask for the large shared-memory carve-out
+  // 4-5 resident blocks x 36 KB of staging tiles per SM: ask for the large shared-memory carve-out
   static bool carveout_set = false;
   if (!carveout_set) {
     cudaFuncSetAttribute(smt_path_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     carveout_set = true;
   }
-  smt_path_kernel<<<blocks, 128, 0, stream>>>(a);
+  smt_path_kernel<<<blocks, 128, 0, stream>>>(a, sc.perm, sc.lidx, sc.info);
   return cudaGetLastError();
 }
 

@@ -7,6 +7,7 @@
 namespace gcp {
 
 typedef uint8_t u8;
+typedef uint16_t u16;
 typedef uint32_t u32;
 typedef uint64_t u64;
 
@@ -74,7 +75,17 @@ cudaError_t launch_poseidon(const PoseidonTable& tab, const u32* in, u32* out, u
                             size_t out_item_stride, int in_mont, int out_mont, int final_level,
                             cudaStream_t stream);
 double launch_imad_probe(u32* d_out, int blocks, u32 seed, cudaStream_t stream);
-cudaError_t launch_smt_verify(const SmtArgs& a, cudaStream_t stream);
+// scratch: perm (n x u32), lidx (n x u16), info (n x u8), hist (256 x u32), cursor (256 x u32)
+struct SmtScratch {
+  u32* perm;
+  u16* lidx;
+  u8* info;
+  u32* hist;
+  u32* cursor;
+};
+cudaError_t launch_smt_verify(const SmtArgs& a, const SmtScratch& sc, int sm_count, cudaStream_t stream);
+cudaError_t launch_smt_scan(const u32* siblings, size_t n, int n_levels, u16* lidx, u8* info, u32* hist, int sm_count,
+                            cudaStream_t stream);
 cudaError_t launch_smt_process(const SmtProcessArgs& a, cudaStream_t stream);
 
 // ElGamal (elgamal.cuh)

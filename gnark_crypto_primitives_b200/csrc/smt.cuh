@@ -112,29 +112,134 @@ __global__ void __launch_bounds__(128) smt_leaf_kernel(SmtArgs a) {
   a.status[idx] = st;
 }
 
-// Pass 2: walk the sibling array from the leaf end: skip the zero tail, then fold Hash2 up to the root.
+// ---------------------------------------------------------------------------------------------------------
+// Pass 0 (HBM-bound): stream the whole sibling array once and reduce every proof to
+//   lidx (1 + index of the last non-zero sibling among [0, n-2]), "siblings[n-1] == 0", "every sibling < r".
+// One warp per proof, lane = one 16-byte piece: a warp-wide LDG.128 covers 512 contiguous bytes (four whole
+// 128-byte lines), all loads of a proof are issued before the first use.  This is the proof-streaming kernel whose
+// achieved GB/s is reported against the measured HBM copy bandwidth.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SMT_SCAN_MAX_ITERS = 16;  // 253 levels * 2 pieces / 32 lanes, rounded up
+constexpr u32 SMT_INFO_LAST_ZERO = 1u, SMT_INFO_CANONICAL = 2u;
+
+__global__ void __launch_bounds__(256) smt_scan_kernel(const u32* __restrict__ siblings, size_t n, int n_levels,
+                                                       u16* __restrict__ lidx_out, u8* __restrict__ info_out,
+                                                       u32* __restrict__ hist) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp_global = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const int pieces = n_levels * 2;                      // 16-byte pieces per proof
+  const int iters = (pieces + 31) >> 5;
+  // r as two 128-bit halves, most significant limb last
+  const u32 r_lo[4] = {GCP_P0, GCP_P1, GCP_P2, GCP_P3}, r_hi[4] = {GCP_P4, GCP_P5, GCP_P6, GCP_P7};
+  for (size_t proof = warp_global; proof < n; proof += n_warps) {
+    const uint4* base = reinterpret_cast<const uint4*>(siblings + proof * (size_t)n_levels * 8);
+    uint4 v[SMT_SCAN_MAX_ITERS];
+#pragma unroll
+    for (int it = 0; it < SMT_SCAN_MAX_ITERS; it++) {
+      int piece = it * 32 + lane;
+      v[it] = (it < iters && piece < pieces) ? __ldcs(base + piece) : make_uint4(0, 0, 0, 0);
+    }
+    int last_nz = -1;          // highest non-zero sibling index among [0, n-2]
+    bool last_zero = true, canon = true;
+    const unsigned full = 0xffffffffu;
+    const bool high = (lane & 1) != 0;                  // odd lanes hold limbs 4..7 of a sibling
+#pragma unroll
+    for (int it = 0; it < SMT_SCAN_MAX_ITERS; it++) {
+      if (it < iters) {
+        const uint4 x = v[it];
+        const bool nz = (x.x | x.y | x.z | x.w) != 0;
+        // bit p of m <-> piece p non-zero; sibling k of this iteration owns pieces 2k, 2k+1
+        const unsigned m = __ballot_sync(full, nz);
+        unsigned nz_mask = (m | (m >> 1)) & 0x55555555u;
+        const int sib_in_iter = min(16, n_levels - it * 16);
+        if (sib_in_iter < 16) nz_mask &= (1u << (2 * sib_in_iter)) - 1u;
+        // canonical: only a top limb >= the top limb of r can make a sibling >= r; the full compare runs in that rare case
+        const unsigned suspects = __ballot_sync(full, high && x.w >= GCP_P7);
+        if (suspects) {
+          const u32 w[4] = {x.x, x.y, x.z, x.w};
+          const u32* ref = high ? r_hi : r_lo;
+          bool lt = false, eq = true;
+#pragma unroll
+          for (int l = 3; l >= 0; l--) {
+            lt = lt || (eq && w[l] < ref[l]);
+            eq = eq && (w[l] == ref[l]);
+          }
+          bool o_lt = __shfl_xor_sync(full, lt, 1);
+          bool o_eq = __shfl_xor_sync(full, eq, 1);
+          bool sib_lt = o_lt || (o_eq && lt);           // on even lanes: hi < r_hi, or hi == r_hi and lo < r_lo
+          bool valid = !high && (it * 16 + (lane >> 1)) < n_levels;
+          if (__ballot_sync(full, valid && !sib_lt)) canon = false;
+        }
+        if (it * 16 + 15 >= n_levels - 1) {             // this iteration contains sibling n-1
+          int k = (n_levels - 1) - it * 16;
+          if (k >= 0 && k < 16) {
+            if (nz_mask & (1u << (2 * k))) last_zero = false;
+            nz_mask &= ~(1u << (2 * k));
+          }
+        }
+        if (nz_mask) last_nz = it * 16 + ((31 - __clz(nz_mask)) >> 1);
+      }
+    }
+    if (lane == 0) {
+      int lidx = last_nz + 1;
+      lidx_out[proof] = (u16)lidx;
+      info_out[proof] = (u8)((last_zero ? SMT_INFO_LAST_ZERO : 0u) | (canon ? SMT_INFO_CANONICAL : 0u));
+      if (hist) atomicAdd(hist + lidx, 1u);
+    }
+  }
+}
+
+// Counting sort of proof indices by lidx, longest paths first: exclusive prefix over 256 bins (one block), then scatter.
+__global__ void smt_sort_prefix_kernel(const u32* __restrict__ hist, u32* __restrict__ cursor) {
+  __shared__ u32 sh[256];
+  int t = threadIdx.x;
+  sh[t] = hist[255 - t];                                // descending lidx
+  __syncthreads();
+  if (t == 0) {
+    u32 acc = 0;
+    for (int i = 0; i < 256; i++) {
+      u32 c = sh[i];
+      sh[i] = acc;
+      acc += c;
+    }
+  }
+  __syncthreads();
+  cursor[255 - t] = sh[t];
+}
+
+__global__ void smt_sort_scatter_kernel(const u16* __restrict__ lidx, size_t n, u32* __restrict__ cursor, u32* __restrict__ perm) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  u32 pos = atomicAdd(cursor + lidx[idx], 1u);
+  perm[pos] = (u32)idx;
+}
+
+// Pass 2: fold Hash2 from level lidx-1 up to the root.
 //
-// Sibling staging: a warp owns 32 consecutive proofs (lane = proof).  The proof-major array gives every proof
-// SMT_CH consecutive levels as one contiguous, 128-byte aligned run, so the warp streams a chunk of SMT_CH levels
-// for all its 32 proofs with 8 cp.async instructions of 32 x 16 B, each covering four whole 128-byte lines
-// (coalesced, vectorised, every fetched sector used), into a double-buffered shared-memory tile; rows are padded
-// to 144 B so that each lane's LDS.128 reads of its own row are bank-conflict free.  The next chunk is in flight
-// while the current one is hashed, so HBM latency never reaches the integer pipe.
+// Proofs are visited through `perm` (sorted by lidx), so the 32 proofs of a warp have (nearly) equal path lengths:
+// no divergence over the path length and no reads of the zero tail.  Sibling staging: the proof-major array gives
+// every proof SMT_CH consecutive levels as one contiguous, 128-byte aligned run, so the warp streams a chunk of SMT_CH
+// levels for all its 32 proofs with 8 cp.async instructions of 32 x 16 B, each covering four whole 128-byte lines
+// (vectorised, every fetched sector used), into a double-buffered shared-memory tile; rows are padded to 144 B so that
+// each lane's LDS.128 reads of its own row are bank-conflict free.  The next chunk is in flight while the current one
+// is hashed, so HBM latency never reaches the integer pipe.
 constexpr int SMT_CH = 4;                       // levels per staged chunk: 4 x 32 B = one 128-byte line per proof
 constexpr int SMT_ROW_WORDS = SMT_CH * 8 + 4;   // 36 words = 144 B row stride
 constexpr int SMT_WARPS = 4;                    // 128 threads per block
 
-__device__ __forceinline__ void smt_stage_chunk(u32* tile, const u32* __restrict__ siblings, size_t warp_base, size_t n_total,
+__device__ __forceinline__ void smt_stage_chunk(u32* tile, const u32* __restrict__ siblings, u32 my_proof, bool my_valid,
                                                 int n_levels, int chunk, int lane) {
   const int part = lane & 7;                    // 16-byte piece of the 128-byte run
   const int level = chunk * SMT_CH + (part >> 1);
 #pragma unroll
   for (int t = 0; t < 8; t++) {
-    const int p = t * 4 + (lane >> 3);          // proof within the warp
+    const int p = t * 4 + (lane >> 3);          // slot within the warp
+    const u32 proof = __shfl_sync(0xffffffffu, my_proof, p);
+    const bool valid = __shfl_sync(0xffffffffu, my_valid, p);
     u32* dst = tile + p * SMT_ROW_WORDS + part * 4;
-    const size_t proof = warp_base + p;
-    if (proof < n_total && level < n_levels) {
-      const u32* src = siblings + (proof * (size_t)n_levels + (size_t)chunk * SMT_CH) * 8 + part * 4;
+    if (valid && level < n_levels) {
+      const u32* src = siblings + ((size_t)proof * (size_t)n_levels + (size_t)chunk * SMT_CH) * 8 + part * 4;
       unsigned saddr = (unsigned)__cvta_generic_to_shared(dst);
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(src) : "memory");
     } else {
@@ -144,35 +249,41 @@ __device__ __forceinline__ void smt_stage_chunk(u32* tile, const u32* __restrict
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(128) smt_path_kernel(SmtArgs a) {
+__global__ void __launch_bounds__(128) smt_path_kernel(SmtArgs a, const u32* __restrict__ perm, const u16* __restrict__ lidx_arr,
+                                                       const u8* __restrict__ info_arr) {
   __shared__ __align__(16) u32 tiles[2][SMT_WARPS][32 * SMT_ROW_WORDS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t warp_base = (size_t)blockIdx.x * blockDim.x + warp * 32;
   if (warp_base >= a.n) return;                 // whole warp out of range
-  const size_t idx = warp_base + lane;
-  const bool in_range = idx < a.n;
-  const size_t sidx = in_range ? idx : a.n - 1; // out-of-range lanes shadow the last proof and store nothing
+  const bool in_range = warp_base + lane < a.n;
+  const size_t idx = in_range ? perm[warp_base + lane] : 0;
   const int n = a.n_levels;
-  u8 st = a.status[sidx];
-  u32 fnc = a.fnc ? a.fnc[sidx] : 0u;
-  u32 is0 = a.is_old0 ? a.is_old0[sidx] : 0u;
-  u32 en = a.enabled ? a.enabled[sidx] : 1u;
+  u8 st = in_range ? a.status[idx] : (u8)GCP_STATUS_NONCANONICAL;
+  u32 fnc = a.fnc ? a.fnc[idx] : 0u;
+  u32 is0 = a.is_old0 ? a.is_old0[idx] : 0u;
+  u32 en = a.enabled ? a.enabled[idx] : 1u;
+  const u32 info = in_range ? info_arr[idx] : 0u;
+  const int lidx = in_range ? (int)lidx_arr[idx] : 0;
 
   u32 acc[8];
-  load_fr(acc, a.leaf + sidx * 8);
+  load_fr(acc, a.leaf + idx * 8);
   u32 key[8];
-  key_integer(key, a.keys + sidx * 8, a.mont);
+  key_integer(key, a.keys + idx * 8, a.mont);
 
-  const bool live = in_range && (st == GCP_STATUS_OK) && (en == 1u);
-  bool canon = true;
-  bool last_zero = true;
-  bool started = false;  // true once a non-zero sibling among [0, n-2] has been seen (i < lidx from then on)
-  const int n_chunks = (n + SMT_CH - 1) / SMT_CH;
-  smt_stage_chunk(tiles[(n_chunks - 1) & 1][warp], a.siblings, warp_base, a.n, n, n_chunks - 1, lane);
+  const bool canon = (info & SMT_INFO_CANONICAL) != 0;
+  const bool last_zero = (info & SMT_INFO_LAST_ZERO) != 0;
+  const bool live = in_range && (st == GCP_STATUS_OK) && (en == 1u) && canon;
+  // the warp walks chunks from its longest live path downwards
+  int my_top = live ? lidx : 0;
+  int warp_top = my_top;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) warp_top = max(warp_top, __shfl_xor_sync(0xffffffffu, warp_top, o));
+  const int first_chunk = (warp_top + SMT_CH - 1) / SMT_CH - 1;   // chunk holding level warp_top - 1 (or -1: nothing to hash)
+  if (first_chunk >= 0) smt_stage_chunk(tiles[first_chunk & 1][warp], a.siblings, (u32)idx, live, n, first_chunk, lane);
 #pragma unroll 1
-  for (int c = n_chunks - 1; c >= 0; c--) {
+  for (int c = first_chunk; c >= 0; c--) {
     if (c > 0) {
-      smt_stage_chunk(tiles[(c - 1) & 1][warp], a.siblings, warp_base, a.n, n, c - 1, lane);
+      smt_stage_chunk(tiles[(c - 1) & 1][warp], a.siblings, (u32)idx, live, n, c - 1, lane);
       asm volatile("cp.async.wait_group 1;" ::: "memory");
     } else {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -182,7 +293,7 @@ __global__ void __launch_bounds__(128) smt_path_kernel(SmtArgs a) {
     const int hi = min(n, c * SMT_CH + SMT_CH) - 1;
 #pragma unroll 1
     for (int i = hi; i >= c * SMT_CH; i--) {
-      if (!live) continue;
+      if (!live || i >= lidx) continue;
       u32 x[8];
       {
         const uint4* q = reinterpret_cast<const uint4*>(row + (i - c * SMT_CH) * 8);
@@ -190,14 +301,6 @@ __global__ void __launch_bounds__(128) smt_path_kernel(SmtArgs a) {
         x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
         x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
       }
-      canon = canon && fr_is_canonical(x);
-      bool nz = !is_zero256(x);
-      if (i == n - 1) {
-        last_zero = !nz;  // LevInsFlag rule 1; this sibling never takes part in the fold
-        continue;
-      }
-      started = started || nz;
-      if (!started) continue;
       u32 s[8];
       if (a.mont) {
 #pragma unroll

@@ -411,3 +411,8 @@ class Engine:
         self._check(self._lib.gcp_eddsa_verify(self._h, _ptr(a), _ptr(r), _ptr(s), _ptr(m), n, _ptr(flags), _ptr(status),
                                                fmt))
         return flags, status
+
+    def smt_scan_dev(self, n_levels, n, d_siblings, d_lidx, d_info, stream=None):
+        """HBM-bound proof-streaming pass: lidx (uint16) and info (uint8) per proof."""
+        self._check(self._lib.gcp_smt_scan_dev(self._h, n_levels, n, _dptr(d_siblings), _dptr(d_lidx), _dptr(d_info),
+                                               self._stream(stream)))

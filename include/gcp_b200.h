@@ -96,6 +96,11 @@ int gcp_smt_verify_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_roots
                        const uint8_t* d_is_old0, const void* d_keys, const void* d_values, const uint8_t* d_fnc,
                        const uint8_t* d_enabled, uint8_t* d_out_flags, uint8_t* d_out_status, void* d_out_roots,
                        int fmt, void* stream);
+/* The proof-streaming pass of the verifier on its own (LevInsFlag's inputs, lev_ins.go:43-77): per proof
+ * lidx = 1 + index of the last non-zero sibling among [0, n-2] (0 if none) and info (bit 0: siblings[n-1] == 0,
+ * bit 1: every sibling < r).  HBM-bound: reads n * n_levels * 32 bytes once with coalesced 128-bit loads. */
+int gcp_smt_scan_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_siblings, uint16_t* d_lidx, uint8_t* d_info,
+                     void* stream);
 /* smt.InclusionVerifier (verifier.go:29-43). */
 int gcp_smt_verify_inclusion(gcp_ctx* ctx, int n_levels, size_t n, const void* roots, int shared_root,
                              const void* siblings, const void* keys, const void* values, uint8_t* out_flags,

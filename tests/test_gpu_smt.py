@@ -208,3 +208,38 @@ def test_bad_arguments(engine):
     with pytest.raises(g.EngineError):
         engine.smt_verify_inclusion(np.zeros((1, 32), np.uint8), np.zeros((1, 254, 32), np.uint8),
                                     np.zeros((1, 32), np.uint8), np.zeros((1, 32), np.uint8))
+
+
+def test_scan_kernel_reports_path_length_and_flags(engine):
+    """gcp_smt_scan_dev: lidx / siblings[n-1]==0 / canonical per proof, for ragged level counts."""
+    torch = pytest.importorskip("torch")
+    rng = random.Random(2024)
+    for n_levels in (2, 5, 16, 17, 33, 160, 253):
+        n = 67
+        rows, want_lidx, want_info = [], [], []
+        for i in range(n):
+            L = rng.randint(0, n_levels - 1)
+            sib = [0 if rng.random() < 0.2 else rng.randrange(1, R) for _ in range(L)]
+            if L:
+                sib[L - 1] = rng.randrange(1, R)
+            sib += [0] * (n_levels - L)
+            info = 3
+            if i % 5 == 1:
+                sib[n_levels - 1] = 9                 # siblings[n-1] != 0
+                info &= ~1
+            if i % 7 == 2:
+                sib[rng.randrange(n_levels)] = R + rng.randrange(3)   # not canonical (r, r+1, r+2)
+                info &= ~2
+            if sib[n_levels - 1] != 0:
+                info &= ~1
+            last = max([j for j in range(n_levels - 1) if sib[j] != 0], default=-1)
+            rows.append(sib)
+            want_lidx.append(last + 1)
+            want_info.append(info)
+        d = torch.from_numpy(elems([x for r_ in rows for x in r_]).reshape(n, n_levels, 32)).cuda()
+        lidx = torch.empty(n, dtype=torch.int16, device="cuda")
+        info = torch.empty(n, dtype=torch.uint8, device="cuda")
+        engine.smt_scan_dev(n_levels, n, d, lidx, info, stream=torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        assert lidx.cpu().tolist() == want_lidx, n_levels
+        assert info.cpu().tolist() == want_info, n_levels
