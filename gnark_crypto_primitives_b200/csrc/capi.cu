@@ -422,7 +422,7 @@ static int smt_verify_dev_locked(gcp_ctx* ctx, int n_levels, size_t n, const voi
   a.enabled = d_enabled;
   // one scratch slot: leaf hashes | perm | lidx | info | hist | cursor
   const size_t off_perm = n * 32, off_lidx = off_perm + n * 4, off_info = off_lidx + ((n * 2 + 15) & ~(size_t)15);
-  const size_t off_hist = off_info + ((n + 15) & ~(size_t)15), off_cur = off_hist + 1024, total = off_cur + 1024;
+  const size_t off_hist = off_info + ((n + 15) & ~(size_t)15), off_cur = off_hist + 1024, total = off_cur + 1040;
   char* scratch = (char*)ctx->buf(leaf_slot, total);
   if (!scratch) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed (smt scratch)");
   a.leaf = (u32*)scratch;

@@ -240,7 +240,7 @@ cudaError_t launch_smt_verify(const SmtArgs& a, const SmtScratch& sc, int sm_cou
   if (e != cudaSuccess) return e;
   e = launch_smt_scan(a.siblings, a.n, a.n_levels, sc.lidx, sc.info, sc.hist, sm_count, stream);
   if (e != cudaSuccess) return e;
-  smt_sort_prefix_kernel<<<1, 256, 0, stream>>>(sc.hist, sc.cursor);
+  smt_sort_prefix_kernel<<<1, 256, 0, stream>>>(sc.hist, sc.cursor, (u32)a.n);
   unsigned blocks256 = (unsigned)((a.n + 255) / 256);
   smt_sort_scatter_kernel<<<blocks256, 256, 0, stream>>>(sc.lidx, a.n, sc.cursor, sc.perm);
   unsigned blocks = (unsigned)((a.n + 127) / 128);

@@ -191,18 +191,20 @@ __global__ void __launch_bounds__(256) smt_scan_kernel(const u32* __restrict__ s
 }
 
 // Counting sort of proof indices by lidx, longest paths first: exclusive prefix over 256 bins (one block), then scatter.
-__global__ void smt_sort_prefix_kernel(const u32* __restrict__ hist, u32* __restrict__ cursor) {
+__global__ void smt_sort_prefix_kernel(const u32* __restrict__ hist, u32* __restrict__ cursor, u32 n) {
   __shared__ u32 sh[256];
   int t = threadIdx.x;
   sh[t] = hist[255 - t];                                // descending lidx
   __syncthreads();
   if (t == 0) {
-    u32 acc = 0;
+    u32 acc = 0, uniform = 0;
     for (int i = 0; i < 256; i++) {
       u32 c = sh[i];
+      if (c == n) uniform = 1;                          // every proof has the same path length: keep memory order
       sh[i] = acc;
       acc += c;
     }
+    cursor[256] = uniform;
   }
   __syncthreads();
   cursor[255 - t] = sh[t];
@@ -211,6 +213,10 @@ __global__ void smt_sort_prefix_kernel(const u32* __restrict__ hist, u32* __rest
 __global__ void smt_sort_scatter_kernel(const u16* __restrict__ lidx, size_t n, u32* __restrict__ cursor, u32* __restrict__ perm) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
+  if (cursor[256]) {
+    perm[idx] = (u32)idx;
+    return;
+  }
   u32 pos = atomicAdd(cursor + lidx[idx], 1u);
   perm[pos] = (u32)idx;
 }
