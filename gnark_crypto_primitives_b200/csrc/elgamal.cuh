@@ -26,7 +26,7 @@ constexpr int FB_WINDOWS = (256 + FB_WBITS - 1) / FB_WBITS;      // 19 (266 bits
 constexpr int FB_HALF = 1 << (FB_WBITS - 1);
 constexpr int FB_ENTRIES = FB_HALF;                              // digits 1 .. 2^(w-1)
 constexpr size_t FB_TABLE_WORDS = (size_t)FB_WINDOWS * FB_ENTRIES * 24;  // u32 words per table (96 B entries)
-constexpr int BATCH_INV = 16;
+constexpr int BATCH_INV = 32;
 
 // ---- table construction (one-time per base point) ------------------------------------------------------
 // step 1: ext[w * FB_ENTRIES + 0] = [2^(WBITS*w)] B.  base: affine standard-form (x, y), 16 words.
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(128) fixed_base_mul_kernel(const u32* __restri
 // ---- Encrypt with one shared public key (the election key) ----------------------------------------------------
 // One thread per POINT (2n threads): threads [0, n) compute C1 = [k]G, threads [n, 2n) compute C2 = [k]PK + [m]G
 // (whole warps take the same branch), as (X, Y, Z) into out_xyz (n x 2 x 24 words).  Both halves validate k and m.
-__global__ void __launch_bounds__(128) encrypt_shared_kernel(const u32* __restrict__ tabG, const u32* __restrict__ tabPK,
+__global__ void __launch_bounds__(128, 4) encrypt_shared_kernel(const u32* __restrict__ tabG, const u32* __restrict__ tabPK,
                                                              const u32* __restrict__ pk_flag, const u32* __restrict__ ks,
                                                              const u32* __restrict__ ms, size_t n, u32* __restrict__ out_xyz,
                                                              u8* __restrict__ status, int mont) {
@@ -191,11 +191,16 @@ __global__ void __launch_bounds__(128) encrypt_shared_kernel(const u32* __restri
   ExtPoint c;
   ext_identity(c);
   if (canon && pk_ok) {
-    if (!second) {
-      fixed_base_accumulate(c, k, tabG);   // encrypt.go:52
-    } else {
-      fixed_base_accumulate(c, k, tabPK);  // encrypt.go:55
-      fixed_base_accumulate(c, m, tabG);   // encrypt.go:58,61
+    // C1 = [k]G (encrypt.go:52); C2 = [k]PK (:55) + [m]G (:58,61).  One inlined copy of the window loop / mixed
+    // addition serves all three: three copies (~80 KB of SASS) made the kernel instruction-fetch bound.
+    const int n_pass = second ? 2 : 1;
+#pragma unroll 1
+    for (int pass = 0; pass < n_pass; pass++) {
+      const u32* tab = (second && pass == 0) ? tabPK : tabG;
+      u32 sc[8];
+#pragma unroll
+      for (int l = 0; l < 8; l++) sc[l] = (pass == 0) ? k[l] : m[l];
+      fixed_base_accumulate(c, sc, tab);
     }
   }
   store_ext_xyz(out_xyz + (idx * 2 + (second ? 1 : 0)) * 24, c);
@@ -378,6 +383,7 @@ __global__ void ct_neg_kernel(const u32* __restrict__ a, size_t n_points, u32* _
 constexpr int TALLY_THREADS = 128;
 
 // Tree reduction over the rows of each column in shared memory (TALLY_THREADS x 32 words); result in row 0's acc.
+// A thread's partner `h` rows further down is thread threadIdx.x + h * cols.
 __device__ __forceinline__ void block_reduce_columns(ExtPoint& acc, u32* smem, int cols, int rows_per_block, int row, bool active) {
   u32* mine = smem + threadIdx.x * 32;
 #pragma unroll
@@ -481,16 +487,20 @@ __global__ void __launch_bounds__(TALLY_THREADS) tally_partial_kernel(const u32*
 // [k]G into the C1 column or [k]PK + [m]G into the C2 column of its field; same reduction as tally_partial_kernel.
 // ks / ms: n_ballots x n_fields scalars.  bad_count[f] counts non-canonical scalars of field f.
 // mask (optional): n_ballots bytes, a ballot is summed only where mask[b] != 0.
-__global__ void __launch_bounds__(TALLY_THREADS) encrypt_tally_partial_kernel(const u32* __restrict__ tabG, const u32* __restrict__ tabPK,
+__global__ void __launch_bounds__(TALLY_THREADS, 4) encrypt_tally_partial_kernel(const u32* __restrict__ tabG, const u32* __restrict__ tabPK,
                                                                               const u32* __restrict__ ks, const u32* __restrict__ ms,
                                                                               const u8* __restrict__ mask, size_t n_ballots, int n_fields,
                                                                               u32* __restrict__ partials, u32* __restrict__ bad_count, int mont) {
   extern __shared__ u32 smem[];
+  // thread layout: the first half of the block (whole warps) computes C1 columns, the second half C2 columns, so a
+  // warp never mixes the two branches; inside a half, thread = row * n_fields + field
+  constexpr int HALF_THREADS = TALLY_THREADS / 2;
   const int cols = n_fields * 2;
-  const int rows_per_block = TALLY_THREADS / cols;
-  const int col = threadIdx.x % cols, row = threadIdx.x / cols;
+  const int half = threadIdx.x / HALF_THREADS;
+  const int th = threadIdx.x % HALF_THREADS;
+  const int rows_per_block = HALF_THREADS / n_fields;
+  const int field = th % n_fields, row = th / n_fields;
   const bool active = row < rows_per_block;
-  const int field = col >> 1, half = col & 1;
   ExtPoint acc;
   ext_identity(acc);
   u32 bad = 0;
@@ -508,18 +518,21 @@ __global__ void __launch_bounds__(TALLY_THREADS) encrypt_tally_partial_kernel(co
         bad = 1;
         continue;
       }
-      if (half == 0) {
-        fixed_base_accumulate(acc, k, tabG);
-      } else {
-        fixed_base_accumulate(acc, k, tabPK);
-        fixed_base_accumulate(acc, m, tabG);
+      const int n_pass = half ? 2 : 1;       // one inlined copy of the window loop (see encrypt_shared_kernel)
+#pragma unroll 1
+      for (int pass = 0; pass < n_pass; pass++) {
+        const u32* tab = (half && pass == 0) ? tabPK : tabG;
+        u32 sc[8];
+#pragma unroll
+        for (int l = 0; l < 8; l++) sc[l] = (pass == 0) ? k[l] : m[l];
+        fixed_base_accumulate(acc, sc, tab);
       }
     }
   }
   if (bad) atomicAdd(bad_count + field, 1u);
-  block_reduce_columns(acc, smem, cols, rows_per_block, row, active);
+  block_reduce_columns(acc, smem, n_fields, rows_per_block, row, active);
   if (active && row == 0) {
-    u32* o = partials + ((size_t)blockIdx.x * cols + col) * 32;
+    u32* o = partials + ((size_t)blockIdx.x * cols + field * 2 + half) * 32;
     store_fr(o, acc.X);
     store_fr(o + 8, acc.Y);
     store_fr(o + 16, acc.Z);

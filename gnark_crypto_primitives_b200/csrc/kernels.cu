@@ -328,7 +328,7 @@ cudaError_t launch_ct_neg(const u32* a, size_t n, u32* out, u8* status, cudaStre
 }
 
 int tally_max_blocks(size_t n_ballots, int n_fields, int sm_count) {
-  int rows = TALLY_THREADS / (n_fields * 2);
+  int rows = (TALLY_THREADS / 2) / n_fields;  // same for both layouts: 128 / (2 n_fields) == 64 / n_fields
   size_t need = (n_ballots + rows - 1) / rows;
   size_t cap = (size_t)sm_count * 8;
   return (int)std::max<size_t>(1, std::min(need, cap));

@@ -53,3 +53,10 @@ for lognb in (17, 20):
     o = torch.empty_like(a); s2 = torch.empty(na, dtype=torch.uint8, device="cuda")
     ms = timeit(lambda: eng.elgamal_add_dev(a, b, na, o, s2, stream=st))
     print(f"ct add n={na}: {ms:.2f} ms  {na/ms/1e3:.1f} M add/s", flush=True)
+# fused encrypt + tally (config 3 shape)
+for lognb in (20,):
+    nb = 1 << lognb
+    k = rand_elems(nb * nf, gen); m = rand_elems(nb * nf, gen, bits=16)
+    tout = torch.empty((nf, 4, 8), dtype=torch.int32, device="cuda"); tst = torch.empty(nf, dtype=torch.uint8, device="cuda")
+    ms = timeit(lambda: eng.elgamal_encrypt_tally_dev(pk, k, m, nb, nf, tout, tst, stream=st))
+    print(f"encrypt_tally n_ballots=2^{lognb} x {nf}: {ms:.2f} ms  {nb*nf/ms/1e3:.1f} M enc/s  bad={int(tst.sum())}", flush=True)
