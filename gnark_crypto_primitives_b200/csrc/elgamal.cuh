@@ -425,7 +425,7 @@ __device__ __forceinline__ void block_reduce_columns(ExtPoint& acc, u32* smem, i
   }
 }
 
-__global__ void __launch_bounds__(TALLY_THREADS) tally_partial_kernel(const u32* __restrict__ ct, size_t n_ballots, int n_fields,
+__global__ void __launch_bounds__(TALLY_THREADS, 4) tally_partial_kernel(const u32* __restrict__ ct, size_t n_ballots, int n_fields,
                                                                       u32* __restrict__ partials, u32* __restrict__ bad_count,
                                                                       int mont) {
   extern __shared__ u32 smem[];  // TALLY_THREADS x 32 words
@@ -433,42 +433,51 @@ __global__ void __launch_bounds__(TALLY_THREADS) tally_partial_kernel(const u32*
   const int rows_per_block = TALLY_THREADS / cols;     // ballots processed concurrently by one block
   const int col = threadIdx.x % cols, row = threadIdx.x / cols;
   const bool active = row < rows_per_block;
-  const u32 d2r3[8] = GCP_ED_2D_R3;
-  const u32 r2[8] = GCP_FR_R2;
   ExtPoint acc;
   ext_identity(acc);
   u32 bad = 0;
   if (active) {
     size_t b = (size_t)blockIdx.x * rows_per_block + row;
-    size_t bstride = (size_t)gridDim.x * rows_per_block;
+    const size_t bstride = (size_t)gridDim.x * rows_per_block;
+    // software pipeline: the next ballot's point is in flight while the current one is added
+    u32 nx[8], ny[8];
+    if (b < n_ballots) {
+      const u32* src = ct + (b * cols + col) * 16;
+      load_fr(nx, src);
+      load_fr(ny, src + 8);
+    }
 #pragma unroll 1
     for (; b < n_ballots; b += bstride) {
-      const u32* src = ct + (b * cols + col) * 16;
       u32 xs[8], ys[8];
-      load_fr(xs, src);
-      load_fr(ys, src + 8);
+      fr_copy(xs, nx);
+      fr_copy(ys, ny);
+      if (b + bstride < n_ballots) {
+        const u32* src = ct + ((b + bstride) * cols + col) * 16;
+        load_fr(nx, src);
+        load_fr(ny, src + 8);
+      }
       if (!(fr_is_canonical(xs) && fr_is_canonical(ys))) {
         bad = 1;
         continue;
       }
-      NielsPoint n;
-      u32 t[8];
-      if (mont) {
-        const u32 d2[8] = GCP_ED_2D_MONT;
-        fr_sub(n.ymx, ys, xs);
-        fr_add(n.ypx, ys, xs);
-        fr_mul(t, xs, ys);
-        fr_mul(n.t2d, t, d2);
-      } else {
-        // standard-form inputs: (y -/+ x) * R^2 / R, and x*y/R * (2d R^3) / R = 2dxy R  (4 multiplies, no to_mont)
-        u32 s[8];
-        fr_sub(s, ys, xs);
-        fr_mul(n.ymx, s, r2);
-        fr_add(s, ys, xs);
-        fr_mul(n.ypx, s, r2);
-        fr_mul(t, xs, ys);
-        fr_mul(n.t2d, t, d2r3);
+      // Niels form (y - x, y + x, 2dxy) in Montgomery representation.  Standard-form inputs: (y -/+ x) * R^2 / R and
+      // x*y/R * (2d R^3) / R = 2dxy R; Montgomery inputs: the same two multiplier bodies with R and 2dR instead.
+      const u32 c_lin_std[8] = GCP_FR_R2, c_lin_mont[8] = GCP_FR_ONE_MONT;
+      const u32 c_t_std[8] = GCP_ED_2D_R3, c_t_mont[8] = GCP_ED_2D_MONT;
+      u32 c_lin[8], c_t[8];
+#pragma unroll
+      for (int l = 0; l < 8; l++) {
+        c_lin[l] = mont ? c_lin_mont[l] : c_lin_std[l];
+        c_t[l] = mont ? c_t_mont[l] : c_t_std[l];
       }
+      NielsPoint n;
+      u32 t[8], sm[8];
+      fr_sub(sm, ys, xs);
+      fr_mul(n.ymx, sm, c_lin);
+      fr_add(sm, ys, xs);
+      fr_mul(n.ypx, sm, c_lin);
+      fr_mul(t, xs, ys);
+      fr_mul(n.t2d, t, c_t);
       ext_add_niels(acc, n);
     }
   }
