@@ -253,7 +253,7 @@ cudaError_t launch_smt_verify(const SmtArgs& a, const SmtScratch& sc, int sm_cou
     cudaFuncSetAttribute(smt_path_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     carveout_set = true;
   }
-  smt_path_kernel<<<blocks, 128, 0, stream>>>(a, sc.perm, sc.lidx, sc.info);
+  smt_path_kernel<<<(unsigned)((a.n + SMT_WARPS * 32 - 1) / (SMT_WARPS * 32)), SMT_WARPS * 32, 0, stream>>>(a, sc.perm, sc.lidx, sc.info);
   return cudaGetLastError();
 }
 

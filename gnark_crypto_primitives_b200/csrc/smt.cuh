@@ -232,7 +232,7 @@ __global__ void smt_sort_scatter_kernel(const u16* __restrict__ lidx, size_t n, 
 // is hashed, so HBM latency never reaches the integer pipe.
 constexpr int SMT_CH = 4;                       // levels per staged chunk: 4 x 32 B = one 128-byte line per proof
 constexpr int SMT_ROW_WORDS = SMT_CH * 8 + 4;   // 36 words = 144 B row stride
-constexpr int SMT_WARPS = 4;                    // 128 threads per block
+constexpr int SMT_WARPS = 4;                    // 128 threads per block (64 and 256 measured slower / do not fit static smem)
 
 __device__ __forceinline__ void smt_stage_chunk(u32* tile, const u32* __restrict__ siblings, u32 my_proof, bool my_valid,
                                                 int n_levels, int chunk, int lane) {
@@ -255,7 +255,7 @@ __device__ __forceinline__ void smt_stage_chunk(u32* tile, const u32* __restrict
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(128) smt_path_kernel(SmtArgs a, const u32* __restrict__ perm, const u16* __restrict__ lidx_arr,
+__global__ void __launch_bounds__(SMT_WARPS * 32) smt_path_kernel(SmtArgs a, const u32* __restrict__ perm, const u16* __restrict__ lidx_arr,
                                                        const u8* __restrict__ info_arr) {
   __shared__ __align__(16) u32 tiles[2][SMT_WARPS][32 * SMT_ROW_WORDS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
