@@ -1,4 +1,10 @@
-// NOTE: written against include/gcp_b200.h; never compiled (no Go toolchain in the build environment).
+// Package gcpb200 is the cgo binding of the B200 batch engine (include/gcp_b200.h) for Go callers of
+// vocdoni/gnark-crypto-primitives: witness generation and batch verification code can hand whole slices of
+// fr.Element to the GPU and get back exactly the values the gadgets would constrain.
+//
+// NOTE: written against the header; it has never been compiled — there is no Go toolchain in the build
+// environment (see INTEGRATION.md).  It is deliberately thin and mechanical: flat slices in, flat slices out,
+// no Go pointer is retained by the C side (cgo pointer rules), every call blocks until results are written.
 package gcpb200
 
 /*
@@ -10,50 +16,166 @@ import "C"
 
 import (
 	"errors"
+	"fmt"
 	"unsafe"
 
 	"github.com/consensys/gnark-crypto/ecc/bn254/fr"
 )
 
+// Status bytes (per item): non-zero where the reference gadget would fail an assertion.
+const (
+	StatusOK           = 0
+	StatusNonCanonical = 1
+	StatusKeyRange     = 2 // tree/smt/utils.go:11-13
+	StatusNotBoolean   = 3
+	StatusOffCurve     = 4 // elgamal/encrypt.go:49
+	StatusZeroDenom    = 5
+	StatusAssertion    = 6 // tree/smt/processor.go assertions
+)
+
+// Engine owns one GPU context. Goroutines may share it (calls are serialised inside the library); use one Engine
+// per GPU for parallelism.
 type Engine struct{ ctx *C.gcp_ctx }
 
+// New creates a context on the given CUDA device. There is no CPU fallback: without a GPU this fails.
 func New(device int) (*Engine, error) {
 	var ctx *C.gcp_ctx
 	if rc := C.gcp_ctx_create(C.int(device), nil, &ctx); rc != 0 {
-		return nil, errors.New(C.GoString(C.gcp_last_error(nil)))
+		return nil, fmt.Errorf("gcp_ctx_create: %s", C.GoString(C.gcp_last_error(nil)))
 	}
 	return &Engine{ctx}, nil
 }
+
 func (e *Engine) Close() { C.gcp_ctx_destroy(e.ctx) }
 
-// BatchHash mirrors poseidon.Hash (hash/native/bn254/poseidon/poseidon.go:38) over n rows of `arity` inputs.
-// []fr.Element memory is passed unchanged: GCP_FMT_MONTGOMERY is gnark-crypto's own representation.
-func (e *Engine) BatchHash(in []fr.Element, arity int) ([]fr.Element, error) {
-	n := len(in) / arity
-	out := make([]fr.Element, n)
-	status := make([]byte, n)
-	rc := C.gcp_poseidon_hash(e.ctx, unsafe.Pointer(&in[0]), C.int(arity), C.size_t(n),
-		unsafe.Pointer(&out[0]), (*C.uint8_t)(&status[0]), C.GCP_FMT_MONTGOMERY)
-	if rc != 0 {
-		return nil, errors.New(C.GoString(C.gcp_last_error(e.ctx))) // "bad inputs provided" for arity 0 or > 16
+func (e *Engine) err(rc C.int) error {
+	if rc == 0 {
+		return nil
 	}
-	return out, nil
+	return errors.New(C.GoString(C.gcp_last_error(e.ctx)))
 }
 
-// BatchInclusionVerify mirrors smt.InclusionVerifier (tree/smt/verifier.go:29) over n Assignment records
-// (tree/smt/wrapper.go:20-31) flattened by the caller: siblings is n*levels elements, root->leaf, zero padded.
-func (e *Engine) BatchInclusionVerify(levels int, roots, siblings, keys, values []fr.Element) (flags, status []byte, err error) {
-	n := len(keys)
+func elemPtr(s []fr.Element) unsafe.Pointer {
+	if len(s) == 0 {
+		return nil
+	}
+	return unsafe.Pointer(&s[0]) // fr.Element is [4]uint64 Montgomery limbs: GCP_FMT_MONTGOMERY memory
+}
+
+func bytePtr(s []byte) *C.uint8_t {
+	if len(s) == 0 {
+		return nil
+	}
+	return (*C.uint8_t)(unsafe.Pointer(&s[0]))
+}
+
+// BatchHash mirrors poseidon.Hash (hash/native/bn254/poseidon/poseidon.go:38) over len(in)/arity rows.
+// arity outside 1..16 returns the reference's error "bad inputs provided".
+func (e *Engine) BatchHash(in []fr.Element, arity int) (out []fr.Element, status []byte, err error) {
+	if arity <= 0 || len(in)%arity != 0 {
+		return nil, nil, errors.New("bad inputs provided")
+	}
+	n := len(in) / arity
+	out, status = make([]fr.Element, n), make([]byte, n)
+	err = e.err(C.gcp_poseidon_hash(e.ctx, elemPtr(in), C.int(arity), C.size_t(n), elemPtr(out), bytePtr(status),
+		C.GCP_FMT_MONTGOMERY))
+	return
+}
+
+// BatchMultiHash mirrors poseidon.MultiHash (poseidon.go:54) over rows of `length` inputs (1..4096).
+func (e *Engine) BatchMultiHash(in []fr.Element, length int) (out []fr.Element, status []byte, err error) {
+	if length <= 0 || len(in)%length != 0 {
+		return nil, nil, errors.New("bad inputs provided")
+	}
+	n := len(in) / length
+	out, status = make([]fr.Element, n), make([]byte, n)
+	err = e.err(C.gcp_poseidon_multihash(e.ctx, elemPtr(in), C.int(length), C.size_t(n), elemPtr(out), bytePtr(status),
+		C.GCP_FMT_MONTGOMERY))
+	return
+}
+
+// Proofs is the flattened form of []smt.Assignment (tree/smt/wrapper.go:20-31): Siblings holds n*Levels elements,
+// root -> leaf, zero padded; Roots holds n elements or a single shared root.
+type Proofs struct {
+	Levels    int
+	Roots     []fr.Element
+	Siblings  []fr.Element
+	OldKeys   []fr.Element // nil for plain inclusion proofs
+	OldValues []fr.Element
+	IsOld0    []byte
+	Keys      []fr.Element
+	Values    []fr.Element
+	Fnc       []byte // nil: inclusion (0)
+	Enabled   []byte // nil: 1
+}
+
+// BatchVerify mirrors smt.Verifier (tree/smt/verifier.go:102); with OldKeys == nil it is smt.InclusionVerifier (:29).
+// flags[i] is the gadget's 0/1 result; status[i] != 0 means the gadget would have failed an assertion.
+func (e *Engine) BatchVerify(p *Proofs) (flags, status []byte, err error) {
+	n := len(p.Keys)
 	flags, status = make([]byte, n), make([]byte, n)
 	shared := 0
-	if len(roots) == 1 && n != 1 {
+	if len(p.Roots) == 1 && n != 1 {
 		shared = 1
 	}
-	rc := C.gcp_smt_verify_inclusion(e.ctx, C.int(levels), C.size_t(n), unsafe.Pointer(&roots[0]), C.int(shared),
-		unsafe.Pointer(&siblings[0]), unsafe.Pointer(&keys[0]), unsafe.Pointer(&values[0]),
-		(*C.uint8_t)(&flags[0]), (*C.uint8_t)(&status[0]), nil, C.GCP_FMT_MONTGOMERY)
-	if rc != 0 {
-		return nil, nil, errors.New(C.GoString(C.gcp_last_error(e.ctx)))
-	}
-	return flags, status, nil
+	err = e.err(C.gcp_smt_verify(e.ctx, C.int(p.Levels), C.size_t(n), elemPtr(p.Roots), C.int(shared), elemPtr(p.Siblings),
+		elemPtr(p.OldKeys), elemPtr(p.OldValues), bytePtr(p.IsOld0), elemPtr(p.Keys), elemPtr(p.Values), bytePtr(p.Fnc),
+		bytePtr(p.Enabled), bytePtr(flags), bytePtr(status), nil, C.GCP_FMT_MONTGOMERY))
+	return
+}
+
+// BatchProcess mirrors smt.Processor (tree/smt/processor.go:10): fnc (1,0) insert, (0,1) update, (1,1) delete, (0,0) nop.
+func (e *Engine) BatchProcess(levels int, oldRoots, siblings, oldKeys, oldValues []fr.Element, isOld0 []byte,
+	newKeys, newValues []fr.Element, fnc0, fnc1 []byte) (newRoots []fr.Element, status []byte, err error) {
+	n := len(newKeys)
+	newRoots, status = make([]fr.Element, n), make([]byte, n)
+	err = e.err(C.gcp_smt_process(e.ctx, C.int(levels), C.size_t(n), elemPtr(oldRoots), elemPtr(siblings), elemPtr(oldKeys),
+		elemPtr(oldValues), bytePtr(isOld0), elemPtr(newKeys), elemPtr(newValues), bytePtr(fnc0), bytePtr(fnc1),
+		elemPtr(newRoots), bytePtr(status), C.GCP_FMT_MONTGOMERY))
+	return
+}
+
+// BatchEncrypt mirrors (*Ciphertext).Encrypt (elgamal/encrypt.go:42) with one shared public key (X, Y).
+// Ciphertexts come back as 4 elements each in Serialize() order: C1.X, C1.Y, C2.X, C2.Y (ciphertext.go:98-105).
+func (e *Engine) BatchEncrypt(pubKey [2]fr.Element, k, m []fr.Element) (ct []fr.Element, status []byte, err error) {
+	n := len(k)
+	ct, status = make([]fr.Element, 4*n), make([]byte, n)
+	err = e.err(C.gcp_elgamal_encrypt(e.ctx, unsafe.Pointer(&pubKey[0]), 0, elemPtr(k), elemPtr(m), C.size_t(n), elemPtr(ct),
+		bytePtr(status), C.GCP_FMT_MONTGOMERY))
+	return
+}
+
+// CiphertextAdd mirrors (*Ciphertext).Add (elgamal/ciphertext.go:24), element-wise over n pairs.
+func (e *Engine) CiphertextAdd(a, b []fr.Element) (out []fr.Element, status []byte, err error) {
+	n := len(a) / 4
+	out, status = make([]fr.Element, 4*n), make([]byte, n)
+	err = e.err(C.gcp_elgamal_add(e.ctx, elemPtr(a), elemPtr(b), C.size_t(n), elemPtr(out), bytePtr(status),
+		C.GCP_FMT_MONTGOMERY))
+	return
+}
+
+// Tally folds Ciphertext.Add over ballots per field: ct is nBallots x nFields ciphertexts.
+func (e *Engine) Tally(ct []fr.Element, nFields int) (out []fr.Element, status []byte, err error) {
+	nBallots := len(ct) / (4 * nFields)
+	out, status = make([]fr.Element, 4*nFields), make([]byte, nFields)
+	err = e.err(C.gcp_elgamal_tally(e.ctx, elemPtr(ct), C.size_t(nBallots), C.int(nFields), elemPtr(out), bytePtr(status),
+		C.GCP_FMT_MONTGOMERY))
+	return
+}
+
+// EncryptTally encrypts nBallots x nFields values under one key and returns only the nFields aggregated ciphertexts.
+func (e *Engine) EncryptTally(pubKey [2]fr.Element, k, m []fr.Element, nFields int) (out []fr.Element, status []byte, err error) {
+	nBallots := len(k) / nFields
+	out, status = make([]fr.Element, 4*nFields), make([]byte, nFields)
+	err = e.err(C.gcp_elgamal_encrypt_tally(e.ctx, unsafe.Pointer(&pubKey[0]), elemPtr(k), elemPtr(m), C.size_t(nBallots),
+		C.int(nFields), elemPtr(out), bytePtr(status), C.GCP_FMT_MONTGOMERY))
+	return
+}
+
+// DeriveAddresses mirrors ecdsa.DeriveAddress (ecc/secp256k1/ecdsa/address.go:14): pub is n x 64 bytes X_be||Y_be.
+func (e *Engine) DeriveAddresses(pub []byte) (addr []byte, err error) {
+	n := len(pub) / 64
+	addr = make([]byte, 20*n)
+	err = e.err(C.gcp_keccak_address(e.ctx, unsafe.Pointer(bytePtr(pub)), C.size_t(n), unsafe.Pointer(bytePtr(addr))))
+	return
 }
