@@ -202,3 +202,19 @@ def test_fused_encrypt_tally(engine):
     # off-curve key: every field flagged
     out, st = engine.elgamal_encrypt_tally(elems((1, 2)), elems([1, 2]).reshape(1, 2, 32), elems([3, 4]).reshape(1, 2, 32))
     assert [int(s) for s in st] == [4, 4]
+
+
+def test_field_edge_patterns_through_curve_arithmetic(engine):
+    """Ciphertext.Add on carry-hostile coordinates (no on-curve check in the reference) vs the C oracle."""
+    from tests.test_gpu_poseidon import _edge_values
+
+    vals = _edge_values()
+    n = len(vals)
+    a = elems([vals[(i * k + k) % n] for i in range(n) for k in (1, 3, 5, 7)]).reshape(n, 4, 32)
+    b = elems([vals[(i * k + 2 * k + 1) % n] for i in range(n) for k in (11, 13, 17, 19)]).reshape(n, 4, 32)
+    out, st = engine.elgamal_add(a, b)
+    want, wst = cport.elgamal_add(a, b, threads=8)
+    assert (st == wst).all()
+    ok = st == 0
+    assert ok.sum() > n // 2
+    assert (out[ok] == want[ok]).all()

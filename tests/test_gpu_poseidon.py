@@ -107,3 +107,55 @@ def test_montgomery_format_roundtrip(engine):
     assert not st.any()
     rinv = pow(1 << 256, -1, R)
     assert [v * rinv % R for v in ints(out)] == [opos.hash(r) for r in rows]
+
+
+def _edge_values():
+    """Field elements with carry-hostile limb patterns: runs of ones, single bits, r - small, limb boundaries."""
+    vals = {0, 1, 2, R - 1, R - 2, R >> 1, (R >> 1) + 1}
+    for k in range(0, 254):
+        vals.add((1 << k) % R)
+        vals.add(((1 << k) - 1) % R)
+        vals.add((R - (1 << k)) % R)
+    for lo in range(0, 256, 32):
+        for hi in range(lo + 32, 257, 32):
+            v = ((1 << hi) - 1) ^ ((1 << lo) - 1)          # limbs lo/32 .. hi/32 - 1 all ones
+            vals.add(v % R)
+            vals.add((v >> 3) % R)
+    for limb in range(8):
+        vals.add((0xFFFFFFFF << (32 * limb)) % R)
+        vals.add((0x80000000 << (32 * limb)) % R)
+        vals.add((0x00000001 << (32 * limb)) % R)
+    return sorted(vals)
+
+
+def test_edge_value_patterns_against_c_oracle(engine):
+    from oracle import cport
+
+    vals = _edge_values()
+    assert len(vals) > 800
+    # arity 1: every edge value alone; arity 2: consecutive pairs and (x, x) squares of the same value
+    a1 = elems(vals).reshape(len(vals), 1, 32)
+    out, st = engine.poseidon_hash(a1)
+    want, wst = cport.poseidon_hash(a1, threads=8)
+    assert not st.any() and (out == want).all()
+    pairs = [(vals[i], vals[(i * 7 + 3) % len(vals)]) for i in range(len(vals))] + [(v, v) for v in vals]
+    a2 = elems([x for p in pairs for x in p]).reshape(len(pairs), 2, 32)
+    out, st = engine.poseidon_hash(a2)
+    want, wst = cport.poseidon_hash(a2, threads=8)
+    assert not st.any() and (out == want).all()
+    for i in (0, 5, 100, len(vals) - 1):
+        assert ints(out[i:i + 1])[0] == opos.hash(list(pairs[i]))
+
+
+def test_full_compare_2pow18_hashes(engine):
+    """Every one of 2^18 random two-input hashes against the C oracle (not a sample)."""
+    from oracle import cport
+
+    rng = np.random.default_rng(20260)
+    n = 1 << 18
+    a = rng.integers(0, 256, size=(n, 2, 32), dtype=np.uint8)
+    a[:, :, 31] &= 0x1F                                     # < 2^253 < r
+    out, st = engine.poseidon_hash(a)
+    want, wst = cport.poseidon_hash(a, threads=cport.default_threads())
+    assert not st.any() and not wst.any()
+    assert (out == want).all()
