@@ -231,36 +231,62 @@ __device__ __forceinline__ void wide_mac(Wide& w, const u32 (&a)[8], const u32 (
 // w += a^2 for a < 2^255 (every lazy value is < 2r < 2^255): 36 wide multiplies instead of 64.
 // a^2 = sum_i a_i * M_i * 2^(64 i) with M_i = a_i + 2 * (a >> 32(i+1)) * 2^32, whose limbs are
 // (a_i, a_{i+1} << 1, (2a)_{i+2}, ..., (2a)_7): the doubling of the cross terms is folded into the multiplicand.
-__device__ __forceinline__ void wide_sqr(Wide& w, const u32 (&a)[8]) {
-  u32 d[8], e[8];  // d = limbs of 2a, e_j = a_j << 1
+// Row I completes limbs 2I and 2I+1.
+struct SqrOperand {
+  u32 a[8], d[8], e[8];  // a, limbs of 2a, a_j << 1
+};
+
+__device__ __forceinline__ void sqr_prepare(SqrOperand& q, const u32 (&a)[8]) {
 #pragma unroll
   for (int j = 0; j < 8; j++) {
-    e[j] = a[j] << 1;
-    d[j] = (j == 0) ? e[0] : __funnelshift_l(a[j - 1], a[j], 1);
+    q.a[j] = a[j];
+    q.e[j] = a[j] << 1;
+    q.d[j] = (j == 0) ? q.e[0] : __funnelshift_l(a[j - 1], a[j], 1);
   }
-  // row 0 (limb offset 0): M = (a0, e1, d2, d3, d4, d5, d6, d7)
-  chain4(w.e[0], w.e[1], w.e[2], w.e[3], w.k[0], a[0], d[2], d[4], d[6], a[0]);
-  chain4(w.o[0], w.o[1], w.o[2], w.o[3], w.k[1], e[1], d[3], d[5], d[7], a[0]);
-  // row 1 (offset 2): M = (a1, e2, d3, d4, d5, d6, d7)
-  chain4(w.e[1], w.e[2], w.e[3], w.e[4], w.k[2], a[1], d[3], d[5], d[7], a[1]);
-  chain3(w.o[1], w.o[2], w.o[3], w.k[1], e[2], d[4], d[6], a[1]);
-  // row 2 (offset 4): M = (a2, e3, d4, d5, d6, d7)
-  chain3(w.e[2], w.e[3], w.e[4], w.k[2], a[2], d[4], d[6], a[2]);
-  chain3(w.o[2], w.o[3], w.o[4], w.k[3], e[3], d[5], d[7], a[2]);
-  // row 3 (offset 6): M = (a3, e4, d5, d6, d7)
-  chain3(w.e[3], w.e[4], w.e[5], w.k[4], a[3], d[5], d[7], a[3]);
-  chain2(w.o[3], w.o[4], w.k[3], e[4], d[6], a[3]);
-  // row 4 (offset 8): M = (a4, e5, d6, d7)
-  chain2(w.e[4], w.e[5], w.k[4], a[4], d[6], a[4]);
-  chain2(w.o[4], w.o[5], w.k[5], e[5], d[7], a[4]);
-  // row 5 (offset 10): M = (a5, e6, d7)
-  chain2(w.e[5], w.e[6], w.k[6], a[5], d[7], a[5]);
-  chain1(w.o[5], w.k[5], e[6], a[5]);
-  // row 6 (offset 12): M = (a6, e7)
-  chain1(w.e[6], w.k[6], a[6], a[6]);
-  chain1(w.o[6], w.k[7], e[7], a[6]);
-  // row 7 (offset 14): M = (a7)
-  chain1_nc(w.e[7], a[7], a[7]);
+}
+
+template <int I>
+__device__ __forceinline__ void sqr_row(Wide& w, const SqrOperand& q) {
+  const u32 (&a)[8] = q.a;
+  const u32 (&d)[8] = q.d;
+  const u32 (&e)[8] = q.e;
+  if constexpr (I == 0) {         // M = (a0, e1, d2, d3, d4, d5, d6, d7)
+    chain4(w.e[0], w.e[1], w.e[2], w.e[3], w.k[0], a[0], d[2], d[4], d[6], a[0]);
+    chain4(w.o[0], w.o[1], w.o[2], w.o[3], w.k[1], e[1], d[3], d[5], d[7], a[0]);
+  } else if constexpr (I == 1) {  // offset 2: M = (a1, e2, d3, d4, d5, d6, d7)
+    chain4(w.e[1], w.e[2], w.e[3], w.e[4], w.k[2], a[1], d[3], d[5], d[7], a[1]);
+    chain3(w.o[1], w.o[2], w.o[3], w.k[1], e[2], d[4], d[6], a[1]);
+  } else if constexpr (I == 2) {  // offset 4: M = (a2, e3, d4, d5, d6, d7)
+    chain3(w.e[2], w.e[3], w.e[4], w.k[2], a[2], d[4], d[6], a[2]);
+    chain3(w.o[2], w.o[3], w.o[4], w.k[3], e[3], d[5], d[7], a[2]);
+  } else if constexpr (I == 3) {  // offset 6: M = (a3, e4, d5, d6, d7)
+    chain3(w.e[3], w.e[4], w.e[5], w.k[4], a[3], d[5], d[7], a[3]);
+    chain2(w.o[3], w.o[4], w.k[3], e[4], d[6], a[3]);
+  } else if constexpr (I == 4) {  // offset 8: M = (a4, e5, d6, d7)
+    chain2(w.e[4], w.e[5], w.k[4], a[4], d[6], a[4]);
+    chain2(w.o[4], w.o[5], w.k[5], e[5], d[7], a[4]);
+  } else if constexpr (I == 5) {  // offset 10: M = (a5, e6, d7)
+    chain2(w.e[5], w.e[6], w.k[6], a[5], d[7], a[5]);
+    chain1(w.o[5], w.k[5], e[6], a[5]);
+  } else if constexpr (I == 6) {  // offset 12: M = (a6, e7)
+    chain1(w.e[6], w.k[6], a[6], a[6]);
+    chain1(w.o[6], w.k[7], e[7], a[6]);
+  } else {                        // offset 14: M = (a7)
+    chain1_nc(w.e[7], a[7], a[7]);
+  }
+}
+
+__device__ __forceinline__ void wide_sqr(Wide& w, const u32 (&a)[8]) {
+  SqrOperand q;
+  sqr_prepare(q, a);
+  sqr_row<0>(w, q);
+  sqr_row<1>(w, q);
+  sqr_row<2>(w, q);
+  sqr_row<3>(w, q);
+  sqr_row<4>(w, q);
+  sqr_row<5>(w, q);
+  sqr_row<6>(w, q);
+  sqr_row<7>(w, q);
 }
 
 // w += a * R  (places a at limbs 8..15; adds a Montgomery-form constant to a pending dot product)
@@ -311,6 +337,8 @@ __device__ __forceinline__ void redc_row(Wide& w, u32& c) {
 
 // Montgomery reduction: r = w / 2^256 mod r, not fully reduced.
 // Bound: r < w / 2^256 + r_mod.  For every call site in this engine w < 6.2 r^2 + r*2^256, so r < 3.2 r_mod < 2^256.
+__device__ __forceinline__ void wide_redc_finish(Wide& w, u32 c, u32 (&r)[8]);
+
 __device__ __forceinline__ void wide_redc(Wide& w, u32 (&r)[8]) {
   u32 c = 0;
   redc_row<0>(w, c);
@@ -321,7 +349,11 @@ __device__ __forceinline__ void wide_redc(Wide& w, u32 (&r)[8]) {
   redc_row<5>(w, c);
   redc_row<6>(w, c);
   redc_row<7>(w, c);
-  // r = E[8..15] + O[8..15] + K[8..15] + c
+  wide_redc_finish(w, c, r);
+}
+
+// after the eight reduction rows: r = E[8..15] + O[8..15] + K[8..15] + c
+__device__ __forceinline__ void wide_redc_finish(Wide& w, u32 c, u32 (&r)[8]) {
   u32 e8 = wide_limb_e<8>(w), e9 = wide_limb_e<9>(w), e10 = wide_limb_e<10>(w), e11 = wide_limb_e<11>(w);
   u32 e12 = wide_limb_e<12>(w), e13 = wide_limb_e<13>(w), e14 = wide_limb_e<14>(w), e15 = wide_limb_e<15>(w);
   u32 o8 = wide_limb_o<8>(w), o9 = wide_limb_o<9>(w), o10 = wide_limb_o<10>(w), o11 = wide_limb_o<11>(w);
@@ -406,12 +438,23 @@ __device__ __forceinline__ void cond_sub(u32 (&a)[8], const u32 (&m)[8]) {
 __device__ __forceinline__ void fr_mul(u32 (&r)[8], const u32 (&a)[8], const u32 (&b)[8]) {
   Wide w;
   wide_zero(w);
-  wide_mac(w, a, b);
-  wide_redc(w, r);
+  // product row i completes limb i, so reduction row i can follow it immediately: the serial m -> m*r -> next m chain
+  // of the reduction then overlaps with the independent product rows that come after it
+  u32 c = 0;
+  mac_row<0>(w, a, b[0]); redc_row<0>(w, c);
+  mac_row<1>(w, a, b[1]); redc_row<1>(w, c);
+  mac_row<2>(w, a, b[2]); redc_row<2>(w, c);
+  mac_row<3>(w, a, b[3]); redc_row<3>(w, c);
+  mac_row<4>(w, a, b[4]); redc_row<4>(w, c);
+  mac_row<5>(w, a, b[5]); redc_row<5>(w, c);
+  mac_row<6>(w, a, b[6]); redc_row<6>(w, c);
+  mac_row<7>(w, a, b[7]); redc_row<7>(w, c);
+  wide_redc_finish(w, c, r);
 }
 
 // r = a * a / R, a < 2r
 __device__ __forceinline__ void fr_sqr(u32 (&r)[8], const u32 (&a)[8]) {
+  // (interleaving the squaring rows with reduction rows, as fr_mul does, measured 1.5 % slower)
   Wide w;
   wide_zero(w);
   wide_sqr(w, a);

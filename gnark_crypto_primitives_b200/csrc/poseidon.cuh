@@ -121,15 +121,19 @@ __device__ __forceinline__ void poseidon_permute_const(u32 (&s)[T][8], u32 (&out
     const int nrows = (full && !last) ? T : 1;
 #pragma unroll 1
     for (int i = 0; i < nrows; i++) {
+      // lazy dot product, row-major over the terms: after product rows I of every term limb I is complete, so
+      // reduction row I follows at once and its serial chain overlaps with the product rows still to come
       Wide w;
       wide_zero(w);
-#pragma unroll
-      for (int j = 0; j < T; j++) {
-        load_const(cst, coef + j * jstride + i * 8);
-        wide_mac(w, s[j], cst);
-      }
+      u32 c = 0;
+      const u32* cf = coef + i * 8;
+#define GCP_DOT_ROW(I)                                                      \
+  _Pragma("unroll") for (int j = 0; j < T; j++) mac_row<I>(w, s[j], cf[j * jstride + I]); \
+  redc_row<I>(w, c);
+      GCP_DOT_ROW(0) GCP_DOT_ROW(1) GCP_DOT_ROW(2) GCP_DOT_ROW(3) GCP_DOT_ROW(4) GCP_DOT_ROW(5) GCP_DOT_ROW(6) GCP_DOT_ROW(7)
+#undef GCP_DOT_ROW
       if (full) rotate_left<T>(n);  // a partial round has a single row: it lands in n[T-1] directly
-      wide_redc(w, n[T - 1]);
+      wide_redc_finish(w, c, n[T - 1]);
       cond_sub(n[T - 1], P2);
     }
     if (full) {
