@@ -54,10 +54,10 @@ __device__ __forceinline__ void sigma(u32 (&x)[8]) {
 // Register-resident permutation for small T with tables in constant memory.
 // in/out: lazy Montgomery. s[0] must be the capacity element (0).
 //
-// Code-size discipline: the whole permutation is ONE loop over the 8 + RP rounds and contains exactly four
-// multiplier bodies - (a) the S-box squaring (run twice) and multiply per element, (b) one lazy dot-product row (T products + one
-// reduction), run T times per full round and once per partial round, (c) the rank-1 update multiply of the
-// partial rounds.  Elements are brought to position 0 by rotating the register file instead of unrolling over
+// Code-size discipline: the whole permutation is ONE loop over the 8 + RP rounds and contains a handful of
+// multiplier bodies - (a) the S-box squaring (run twice) and multiply per element, (b) one lazy dot-product row (T
+// products + one reduction) for the full rounds, (c) the fused partial-round body (dot row + T-1 rank-1 updates
+// advancing row by row together).  Elements are brought to position 0 by rotating the register file instead of unrolling over
 // the state index.  The first version unrolled every round body (~260 KB of SASS) and was bound by instruction
 // fetch (ncu: stall_no_instruction, icc hit rate 89 %); this one is ~20 KB and stays in the instruction cache.
 template <int T>
@@ -114,29 +114,27 @@ __device__ __forceinline__ void poseidon_permute_const(u32 (&s)[T][8], u32 (&out
       for (int l = 0; l < 8; l++) s[0][l] = y[l];
       if (full) rotate_left<T>(s);
     }
-    // (b) matrix rows as lazy dot products: full rounds n_i = sum_j m[j][i] s_j (M, or P after round 3), the last
-    // round only column 0; partial rounds the single row n = sum_j S[(2T-1)pr + j] s_j.
-    const u32* coef = full ? ((r == 3) ? P : M) : S + (2 * T - 1) * (r - 4) * 8;
-    const int jstride = full ? T * 8 : 8;
-    const int nrows = (full && !last) ? T : 1;
-#pragma unroll 1
-    for (int i = 0; i < nrows; i++) {
-      // lazy dot product, row-major over the terms: after product rows I of every term limb I is complete, so
-      // reduction row I follows at once and its serial chain overlaps with the product rows still to come
-      Wide w;
-      wide_zero(w);
-      u32 c = 0;
-      const u32* cf = coef + i * 8;
-#define GCP_DOT_ROW(I)                                                      \
-  _Pragma("unroll") for (int j = 0; j < T; j++) mac_row<I>(w, s[j], cf[j * jstride + I]); \
-  redc_row<I>(w, c);
-      GCP_DOT_ROW(0) GCP_DOT_ROW(1) GCP_DOT_ROW(2) GCP_DOT_ROW(3) GCP_DOT_ROW(4) GCP_DOT_ROW(5) GCP_DOT_ROW(6) GCP_DOT_ROW(7)
-#undef GCP_DOT_ROW
-      if (full) rotate_left<T>(n);  // a partial round has a single row: it lands in n[T-1] directly
-      wide_redc_finish(w, c, n[T - 1]);
-      cond_sub(n[T - 1], P2);
-    }
     if (full) {
+      // (b) matrix rows as lazy dot products: n_i = sum_j m[j][i] s_j (M, or P after round 3); the last round only
+      // needs column 0.  Row-major over the terms: after product rows I of every term limb I is complete, so reduction
+      // row I follows at once and its serial chain overlaps with the product rows still to come.
+      const u32* coef = (r == 3) ? P : M;
+      const int nrows = last ? 1 : T;
+#pragma unroll 1
+      for (int i = 0; i < nrows; i++) {
+        Wide w;
+        wide_zero(w);
+        u32 c = 0;
+        const u32* cf = coef + i * 8;
+#define GCP_DOT_ROW(I)                                                               \
+  _Pragma("unroll") for (int j = 0; j < T; j++) mac_row<I>(w, s[j], cf[j * T * 8 + I]); \
+  redc_row<I>(w, c);
+        GCP_DOT_ROW(0) GCP_DOT_ROW(1) GCP_DOT_ROW(2) GCP_DOT_ROW(3) GCP_DOT_ROW(4) GCP_DOT_ROW(5) GCP_DOT_ROW(6) GCP_DOT_ROW(7)
+#undef GCP_DOT_ROW
+        rotate_left<T>(n);
+        wide_redc_finish(w, c, n[T - 1]);
+        cond_sub(n[T - 1], P2);
+      }
       if (!last) {
 #pragma unroll
         for (int j = 0; j < T; j++)
@@ -144,18 +142,35 @@ __device__ __forceinline__ void poseidon_permute_const(u32 (&s)[T][8], u32 (&out
           for (int l = 0; l < 8; l++) s[j][l] = n[j][l];
       }
     } else {
-      // (c) s_k += s_0 * S[(2T-1)pr + T + k - 1], k = 1..T-1, with the post-S-box s_0 (poseidon.go:162-164);
-      // unrolled over k (T-1 multiplier bodies) so that no register rotation is needed in the hot loop
-      const u32* srow = S + ((2 * T - 1) * (r - 4) + T) * 8;
+      // partial round (poseidon.go:152-166): n0 = sum_j S[j] s_j and s_k += s_0 * S[T+k-1] all read the post-S-box state
+      // and are independent, so their T accumulators advance row by row together: T independent carry / reduction
+      // chains in flight per thread.
+      const u32* srow = S + (2 * T - 1) * (r - 4) * 8;
+      Wide wd, wk[T - 1];
+      wide_zero(wd);
+#pragma unroll
+      for (int k = 0; k < T - 1; k++) wide_zero(wk[k]);
+      u32 cd = 0, ck[T - 1];
+#pragma unroll
+      for (int k = 0; k < T - 1; k++) ck[k] = 0;
+#define GCP_PARTIAL_ROW(I)                                                                    \
+  _Pragma("unroll") for (int j = 0; j < T; j++) mac_row<I>(wd, s[j], srow[j * 8 + I]);        \
+  redc_row<I>(wd, cd);                                                                        \
+  _Pragma("unroll") for (int k = 0; k < T - 1; k++) {                                         \
+    mac_row<I>(wk[k], s[0], srow[(T + k) * 8 + I]);                                           \
+    redc_row<I>(wk[k], ck[k]);                                                                \
+  }
+      GCP_PARTIAL_ROW(0) GCP_PARTIAL_ROW(1) GCP_PARTIAL_ROW(2) GCP_PARTIAL_ROW(3)
+      GCP_PARTIAL_ROW(4) GCP_PARTIAL_ROW(5) GCP_PARTIAL_ROW(6) GCP_PARTIAL_ROW(7)
+#undef GCP_PARTIAL_ROW
 #pragma unroll
       for (int k = 1; k < T; k++) {
         u32 prod[8];
-        load_const(cst, srow + (k - 1) * 8);
-        fr_mul(prod, s[0], cst);
+        wide_redc_finish(wk[k - 1], ck[k - 1], prod);
         fr_add(s[k], s[k], prod);
       }
-#pragma unroll
-      for (int l = 0; l < 8; l++) s[0][l] = n[T - 1][l];
+      wide_redc_finish(wd, cd, s[0]);
+      cond_sub(s[0], P2);
     }
   }
 #pragma unroll
