@@ -471,14 +471,12 @@ __global__ void __launch_bounds__(TALLY_THREADS, 4) tally_partial_kernel(const u
         c_t[l] = mont ? c_t_mont[l] : c_t_std[l];
       }
       NielsPoint n;
-      u32 t[8], sm[8];
-      fr_sub(sm, ys, xs);
-      fr_mul(n.ymx, sm, c_lin);
-      fr_add(sm, ys, xs);
-      fr_mul(n.ypx, sm, c_lin);
-      fr_mul(t, xs, ys);
+      u32 t[8], dm[8], sp[8];
+      fr_sub(dm, ys, xs);
+      fr_add(sp, ys, xs);
+      fr_mul3(n.ymx, dm, c_lin, n.ypx, sp, c_lin, t, xs, ys);  // three independent products, row-interleaved
       fr_mul(n.t2d, t, c_t);
-      ext_add_niels(acc, n);
+      ext_add_niels<true>(acc, n);
     }
   }
   if (bad) atomicAdd(bad_count + col / 2, 1u);

@@ -461,6 +461,41 @@ __device__ __forceinline__ void fr_sqr(u32 (&r)[8], const u32 (&a)[8]) {
   wide_redc(w, r);
 }
 
+// Several independent multiplications advanced row by row together (CIOS order each), so that a thread has that
+// many carry / reduction chains in flight.  Used where the operands are all ready at once (curve addition formulas).
+#define GCP_MULN_ROW2(I)                                \
+  mac_row<I>(w1, a1, b1[I]); redc_row<I>(w1, c1);       \
+  mac_row<I>(w2, a2, b2[I]); redc_row<I>(w2, c2);
+__device__ __forceinline__ void fr_mul2(u32 (&r1)[8], const u32 (&a1)[8], const u32 (&b1)[8], u32 (&r2)[8], const u32 (&a2)[8],
+                                        const u32 (&b2)[8]) {
+  Wide w1, w2;
+  wide_zero(w1);
+  wide_zero(w2);
+  u32 c1 = 0, c2 = 0;
+  GCP_MULN_ROW2(0) GCP_MULN_ROW2(1) GCP_MULN_ROW2(2) GCP_MULN_ROW2(3) GCP_MULN_ROW2(4) GCP_MULN_ROW2(5) GCP_MULN_ROW2(6) GCP_MULN_ROW2(7)
+  wide_redc_finish(w1, c1, r1);
+  wide_redc_finish(w2, c2, r2);
+}
+#undef GCP_MULN_ROW2
+
+#define GCP_MULN_ROW3(I)                                \
+  mac_row<I>(w1, a1, b1[I]); redc_row<I>(w1, c1);       \
+  mac_row<I>(w2, a2, b2[I]); redc_row<I>(w2, c2);       \
+  mac_row<I>(w3, a3, b3[I]); redc_row<I>(w3, c3);
+__device__ __forceinline__ void fr_mul3(u32 (&r1)[8], const u32 (&a1)[8], const u32 (&b1)[8], u32 (&r2)[8], const u32 (&a2)[8],
+                                        const u32 (&b2)[8], u32 (&r3)[8], const u32 (&a3)[8], const u32 (&b3)[8]) {
+  Wide w1, w2, w3;
+  wide_zero(w1);
+  wide_zero(w2);
+  wide_zero(w3);
+  u32 c1 = 0, c2 = 0, c3 = 0;
+  GCP_MULN_ROW3(0) GCP_MULN_ROW3(1) GCP_MULN_ROW3(2) GCP_MULN_ROW3(3) GCP_MULN_ROW3(4) GCP_MULN_ROW3(5) GCP_MULN_ROW3(6) GCP_MULN_ROW3(7)
+  wide_redc_finish(w1, c1, r1);
+  wide_redc_finish(w2, c2, r2);
+  wide_redc_finish(w3, c3, r3);
+}
+#undef GCP_MULN_ROW3
+
 // r = a + b mod 2r
 __device__ __forceinline__ void fr_add(u32 (&r)[8], const u32 (&a)[8], const u32 (&b)[8]) {
   const u32 P2[8] = GCP_2P_LIMBS;
