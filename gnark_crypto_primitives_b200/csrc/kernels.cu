@@ -248,11 +248,8 @@ cudaError_t launch_smt_verify(const SmtArgs& a, const SmtScratch& sc, int sm_cou
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   // 4-5 resident blocks x 36 KB of staging tiles per SM: ask for the large shared-memory carve-out
-  static bool carveout_set = false;
-  if (!carveout_set) {
-    cudaFuncSetAttribute(smt_path_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    carveout_set = true;
-  }
+  // (set on every launch: the attribute is per device, and a process may drive several GPUs)
+  cudaFuncSetAttribute(smt_path_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   smt_path_kernel<<<(unsigned)((a.n + SMT_WARPS * 32 - 1) / (SMT_WARPS * 32)), SMT_WARPS * 32, 0, stream>>>(a, sc.perm, sc.lidx, sc.info);
   return cudaGetLastError();
 }
