@@ -41,6 +41,8 @@ SIGNATURES = {
     "gcp_poseidon_hash_dev": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_int, c_void_p]),
     "gcp_poseidon_multihash": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_int]),
     "gcp_poseidon_multihash_dev": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_int, c_void_p]),
+    "gcp_mimc7_hash": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_int]),
+    "gcp_mimc7_hash_dev": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_int, c_void_p]),
     "gcp_smt_verify": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     "gcp_smt_verify_dev": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -57,6 +57,7 @@ struct gcp_ctx {
   u32* d_flagPK = nullptr;    // 1 word: cached key is canonical and on the curve
   unsigned char pk_cached[64];
   int pk_cached_fmt = -1;     // -1: no key cached
+  bool have_mimc7 = false;
 
   int fail(int code, const std::string& msg) {
     err = msg;
@@ -230,6 +231,31 @@ int gcp_ctx_create(int device, const char* constants_path, gcp_ctx** out) {
     if ((e = cudaMemcpy(&flag, ctx->d_flagG, 4, cudaMemcpyDeviceToHost)) != cudaSuccess)
       return bail(ctx->cuda_fail(e, "read generator flag"));
     if (!flag) return bail(ctx->fail(GCP_ERR_CONSTANTS, "generator self-check failed (not on curve)"));
+  }
+  // MiMC7 round constants (data/mimc7_bn254.bin next to the Poseidon blob); optional: without the file MiMC7 is disabled
+  {
+    std::string mpath = path;
+    size_t k = mpath.find_last_of('/');
+    mpath = (k == std::string::npos ? std::string("") : mpath.substr(0, k + 1)) + "mimc7_bn254.bin";
+    FILE* mf = fopen(mpath.c_str(), "rb");
+    if (mf) {
+      unsigned char mb[16 + 91 * 32];
+      size_t got = fread(mb, 1, sizeof(mb), mf);
+      fclose(mf);
+      uint32_t mh[4];
+      memcpy(mh, mb, 16);
+      if (got == sizeof(mb) && mh[0] == 0x374D494Du && mh[1] == 1 && mh[2] == 91) {
+        u32* d_m = (u32*)ctx->buf(47, 91 * 32);
+        if (!d_m) return bail(ctx->fail(GCP_ERR_ALLOC, "device allocation failed"));
+        if ((e = cudaMemcpyAsync(d_m, mb + 16, 91 * 32, cudaMemcpyHostToDevice, ctx->stream[0])) != cudaSuccess ||
+            (e = launch_to_mont(d_m, 91, ctx->stream[0])) != cudaSuccess ||
+            (e = upload_mimc7_constants(d_m, ctx->stream[0])) != cudaSuccess ||
+            (e = cudaStreamSynchronize(ctx->stream[0])) != cudaSuccess)
+          return bail(ctx->cuda_fail(e, "MiMC7 constants"));
+        ctx->launches++;
+        ctx->have_mimc7 = true;
+      }
+    }
   }
   *out = ctx;
   return GCP_OK;
@@ -1158,6 +1184,52 @@ int gcp_te_to_rte(gcp_ctx* ctx, const void* points, size_t n_points, void* out, 
 }
 int gcp_rte_to_te(gcp_ctx* ctx, const void* points, size_t n_points, void* out, uint8_t* status) {
   return te_rte_host(ctx, points, n_points, out, status, 0);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// MiMC7 (hash/native/bn254/mimc7)
+// ---------------------------------------------------------------------------------------------------
+int gcp_mimc7_hash_dev(gcp_ctx* ctx, const void* d_in, int len, size_t n, void* d_out, uint8_t* d_status, int fmt,
+                       void* stream) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  int rc = check_fmt(ctx, fmt);
+  if (rc != GCP_OK) return rc;
+  if (!ctx->have_mimc7) return ctx->fail(GCP_ERR_CONSTANTS, "MiMC7 constants (data/mimc7_bn254.bin) were not found");
+  if (len < 1 || len > 62) return ctx->fail(GCP_ERR_BAD_ARG, "MiMC7 takes 1..62 inputs");  // mimc.go:9,33-38
+  if (n == 0) return GCP_OK;
+  if (!d_in || !d_out || !d_status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  CU(launch_mimc7((const u32*)d_in, len, n, (u32*)d_out, d_status, fmt, (cudaStream_t)stream), "mimc7 kernel");
+  ctx->launches++;
+  return GCP_OK;
+}
+
+int gcp_mimc7_hash(gcp_ctx* ctx, const void* in, int len, size_t n, void* out, uint8_t* status, int fmt) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  void* d[1];
+  uint8_t* d_status;
+  void* d_out;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    if (len < 1 || len > 62) return ctx->fail(GCP_ERR_BAD_ARG, "MiMC7 takes 1..62 inputs");
+    if (n == 0) return GCP_OK;
+    if (!in || !out || !status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+    Upload ins[1] = {{in, (size_t)len * 32}};
+    int rc = upload_all(ctx, ins, 1, n, d);
+    if (rc != GCP_OK) return rc;
+    d_out = ctx->buf(76, n * 32);
+    d_status = (uint8_t*)ctx->buf(78, n);
+    if (!d_out || !d_status) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+  }
+  int rc = gcp_mimc7_hash_dev(ctx, d[0], len, n, d_out, d_status, fmt, ctx->stream[0]);
+  if (rc != GCP_OK) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaMemcpyAsync(out, d_out, n * 32, cudaMemcpyDeviceToHost, ctx->stream[0]), "D2H");
+  CU(cudaMemcpyAsync(status, d_status, n, cudaMemcpyDeviceToHost, ctx->stream[0]), "D2H");
+  CU(cudaStreamSynchronize(ctx->stream[0]), "stream sync");
+  return GCP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -7,6 +7,7 @@
 #include "elgamal.cuh"
 #include "keccak.cuh"
 #include "proofs.cuh"
+#include "mimc7.cuh"
 #include "kernels.h"
 
 #include <algorithm>
@@ -387,6 +388,16 @@ cudaError_t launch_eddsa_verify(const u32* tabG, const PoseidonTable& tab6, cons
                                 cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
   eddsa_verify_kernel<<<blocks_for(n, 64), 64, 0, stream>>>(tabG, tab6, pub_a, sig_r, sig_s, msgs, n, flags, status, mont);
+  return cudaGetLastError();
+}
+
+cudaError_t upload_mimc7_constants(const u32* d_mont, cudaStream_t stream) {
+  return cudaMemcpyToSymbolAsync(c_mimc7, d_mont, sizeof(u32) * MIMC7_ROUNDS * 8, 0, cudaMemcpyDeviceToDevice, stream);
+}
+
+cudaError_t launch_mimc7(const u32* in, int len, size_t n, u32* out, u8* status, int mont, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  mimc7_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(in, len, n, out, status, mont);
   return cudaGetLastError();
 }
 

@@ -416,3 +416,19 @@ class Engine:
         """HBM-bound proof-streaming pass: lidx (uint16) and info (uint8) per proof."""
         self._check(self._lib.gcp_smt_scan_dev(self._h, n_levels, n, _dptr(d_siblings), _dptr(d_lidx), _dptr(d_info),
                                                self._stream(stream)))
+
+    # -- MiMC7 --------------------------------------------------------------------------------------
+    def mimc7_hash(self, inputs, fmt=FMT_CANONICAL):
+        """MiMC7 (hash/native/bn254/mimc7/mimc.go:47-54): (n, len, 32), 1 <= len <= 62 -> ((n, 32), status)."""
+        a = _as_elems(inputs, name="inputs")
+        if a.ndim != 3:
+            raise ValueError("inputs must have shape (n, len, 32)")
+        n, ln = a.shape[0], a.shape[1]
+        out = np.empty((n, 32), dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.gcp_mimc7_hash(self._h, _ptr(a), ln, n, _ptr(out), _ptr(status), fmt))
+        return out, status
+
+    def mimc7_hash_dev(self, d_in, length, n, d_out, d_status, fmt=FMT_CANONICAL, stream=None):
+        self._check(self._lib.gcp_mimc7_hash_dev(self._h, _dptr(d_in), length, n, _dptr(d_out), _dptr(d_status), fmt,
+                                                 self._stream(stream)))

@@ -79,6 +79,12 @@ int gcp_poseidon_multihash(gcp_ctx* ctx, const void* in, int len, size_t n, void
 int gcp_poseidon_multihash_dev(gcp_ctx* ctx, const void* d_in, int len, size_t n, void* d_out, uint8_t* d_status,
                                int fmt, void* stream);
 
+/* MiMC7 (hash/native/bn254/mimc7/mimc.go:47-87): iden3-compatible, 91 rounds of x^7, Miyaguchi-Preneel with field
+ * addition; n independent hashes of `len` inputs each, 1 <= len <= 62 (mimc.go:9). */
+int gcp_mimc7_hash(gcp_ctx* ctx, const void* in, int len, size_t n, void* out, uint8_t* status, int fmt);
+int gcp_mimc7_hash_dev(gcp_ctx* ctx, const void* d_in, int len, size_t n, void* d_out, uint8_t* d_status, int fmt,
+                       void* stream);
+
 /* ---- SMT: tree/smt/verifier.go ------------------------------------------------------------------ */
 /* smt.Verifier (verifier.go:102-121) -> VerifierWithLeafHashFlag (:171-242), n proofs of n_levels siblings.
  *   roots: n elements, or 1 element when shared_root != 0

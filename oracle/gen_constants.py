@@ -84,11 +84,29 @@ def build_blob(tables) -> bytes:
     return out
 
 
+MIMC_REF = Path("/root/reference/hash/native/bn254/mimc7/constants.go")
+MIMC_OUT = OUT.parent / "mimc7_bn254.bin"
+MIMC_MAGIC = 0x374D494D  # 'MIM7'
+
+
+def build_mimc_blob() -> bytes:
+    """hash/native/bn254/mimc7/constants.go:9-25: constants[0] = 0, constants[i] = strConstants[i-1], 91 rounds.
+    Layout: u32 magic 'MIM7', u32 version=1, u32 n=91, u32 reserved, then 91 x 32-byte little-endian elements."""
+    src = MIMC_REF.read_text()
+    cs = [int(x) for x in re.findall(r'"(\d+)"', src)]
+    assert len(cs) == 90 and all(0 <= c < R for c in cs)
+    elems = [0] + cs
+    return struct.pack("<4I", MIMC_MAGIC, 1, len(elems), 0) + b"".join(e.to_bytes(32, "little") for e in elems)
+
+
 def main():
     blob = build_blob(load_reference_tables())
     OUT.parent.mkdir(parents=True, exist_ok=True)
     OUT.write_bytes(blob)
     print(f"wrote {OUT} ({len(blob)} bytes, sha256 {hashlib.sha256(blob).hexdigest()})")
+    mblob = build_mimc_blob()
+    MIMC_OUT.write_bytes(mblob)
+    print(f"wrote {MIMC_OUT} ({len(mblob)} bytes, sha256 {hashlib.sha256(mblob).hexdigest()})")
 
 
 if __name__ == "__main__":

@@ -252,3 +252,14 @@ def test_eddsa_oracle_self_consistency():
     b8 = (5299619240641551281634865583518297030282874472190772894086521144482721001553,
           16950150798460657717958625567821834550301663161624707787222815936182638968203)
     assert ed.te_to_rte(*b8) == ed.G
+
+
+def test_mimc7_public_iden3_vectors():
+    from oracle import mimc7
+
+    # go-iden3-crypto mimc7 test vectors; the first input is the one hash/native/bn254/mimc7/mimc_test.go:37 uses
+    assert mimc7.hash([12]) == 16051049095595290701999129793867590386356047218708919933694064829788708231421
+    assert mimc7.hash([12, 45, 78, 41]) == \
+        18226366069841799622585958305961373004333097209608110160936134895615261821931
+    assert mimc7.hash([1] * 63) == 0          # mimc.go:33-38: more than 62 inputs are dropped
+    assert len(mimc7.constants()) == 91 and mimc7.constants()[0] == 0
