@@ -8,8 +8,8 @@
 //   (*Ciphertext).Add        elgamal/ciphertext.go:24-32 component-wise curve.Add;  Neg :37-46
 //   tally                    left fold of Add from NewCiphertext (ciphertext.go:16-19) — caller's loop
 // All of these are group elements given by exact field arithmetic, so any addition order / window width yields
-// the same canonical affine coordinates.  This file uses WBITS-bit windows over precomputed Niels tables
-// (tab[w][d-1] = [d * 2^(WBITS*w)] B) for both G and a shared public key, accumulates in extended coordinates,
+// the same canonical affine coordinates.  This file uses signed FB_WBITS-bit windows over precomputed Niels tables
+// (tab[w][d-1] = [d * 2^(FB_WBITS*w)] B, d = 1 .. 2^(FB_WBITS-1)) for both G and a shared public key, accumulates in extended coordinates,
 // and converts to affine with chunked Montgomery batch inversion (one Fermat inversion per BATCH_INV points).
 #pragma once
 #include "edwards.cuh"

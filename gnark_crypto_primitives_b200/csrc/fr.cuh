@@ -11,7 +11,9 @@
 //    the carry that leaves a chain is counted into a small K limb instead of rippling upwards.
 //  * The 512-bit value is   sum e[p] * 2^(64p)  +  sum o[p] * 2^(64p+32)  +  sum k[q] * 2^(32(q+8)).
 //    Several products may be accumulated before ONE Montgomery reduction (lazy dot products:
-//    Poseidon's matrix rows cost t*64 + 72 wide multiplies instead of t*136).
+//    Poseidon's matrix rows cost t*64 + 64 wide multiplies (+ 8 plain IMAD) instead of t*128 + 8t).
+//  * Product rows and reduction rows are issued in CIOS order (row i of the product, then row i of the
+//    reduction) so that the reduction's serial chain overlaps with later product rows.
 //
 // Value semantics follow gnark's test engine: every api.Add/Mul/Sub is exact arithmetic mod r
 // (/root/reference SURVEY appendix A); r literal at hash/emulated/bn254/mimc7/constants.go:18.

@@ -59,7 +59,8 @@ __device__ __forceinline__ void sigma(u32 (&x)[8]) {
 // products + one reduction) for the full rounds, (c) the fused partial-round body (dot row + T-1 rank-1 updates
 // advancing row by row together).  Elements are brought to position 0 by rotating the register file instead of unrolling over
 // the state index.  The first version unrolled every round body (~260 KB of SASS) and was bound by instruction
-// fetch (ncu: stall_no_instruction, icc hit rate 89 %); this one is ~20 KB and stays in the instruction cache.
+// fetch (ncu: stall_no_instruction, icc hit rate 89 %); this one is ~40 KB and stays in the instruction cache
+// (hit rate 99.95 %).
 template <int T>
 __device__ __forceinline__ void rotate_left(u32 (&s)[T][8]) {
 #pragma unroll
