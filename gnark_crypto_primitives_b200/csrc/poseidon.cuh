@@ -109,7 +109,10 @@ __device__ __forceinline__ void poseidon_permute_const(u32 (&s)[T][8], u32 (&out
       fr_mul(y, y, s[0]);
       if (!last) {
         load_const(cst, crow + k * 8);
-        fr_add(y, y, cst);
+        if (full || T > 3)
+          fr_add(y, y, cst);
+        else
+          add256(y, y, cst);  // partial rounds, t <= 3: left unreduced (< 2.75 r), see the bound note below
       }
 #pragma unroll
       for (int l = 0; l < 8; l++) s[0][l] = y[l];
@@ -171,7 +174,11 @@ __device__ __forceinline__ void poseidon_permute_const(u32 (&s)[T][8], u32 (&out
         fr_add(s[k], s[k], prod);
       }
       wide_redc_finish(wd, cd, s[0]);
-      cond_sub(s[0], P2);
+      // Bounds for t <= 3 (r/2^256 = 0.18904): with s_0 < 2.28 r the S-box gives x^2 < 1.98 r, x^4 < 1.74 r,
+      // x^5 < 1.75 r, so y = x^5 + c < 2.75 r; the dot row is then < (2.75 + 2 (t-1)) r^2 / 2^256 + r < 2.28 r again.
+      // Every squaring input stays below 2^255 = 2.645 r and every sum below 2^256, so neither y nor the new s_0
+      // needs a conditional subtraction on the round-to-round critical path.  t = 4 would reach 2.65 r: it reduces.
+      if constexpr (T > 3) cond_sub(s[0], P2);
     }
   }
 #pragma unroll
