@@ -194,6 +194,94 @@ def measure_extras(torch, dist, eng, g, world, rank):
     return out
 
 
+def measure_census_like(torch, eng, g, log2_n=18, seed=0xCE75):
+    """Census-like batch (SURVEY 8d secondary distribution: L ~ U[20,28] leading siblings of 160, ~10 % interior
+    zeros) end to end from HOST buffers, two ways: the dense Assignment.Siblings rows (n_levels * 32 B per proof) and
+    arbo's packed proofs expanded on the GPU (gcp_smt_verify_packed).  Same proofs, flags compared."""
+    n = 1 << log2_n
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(seed)
+    sib = rand_elems(torch, n * N_LEVELS, gen, nonzero=True).view(n, N_LEVELS, 8)
+    L = torch.randint(20, 29, (n,), device="cuda", generator=gen)
+    lvl = torch.arange(N_LEVELS, device="cuda").view(1, N_LEVELS)
+    hole = torch.rand((n, N_LEVELS), device="cuda", generator=gen) < 0.1
+    keep = (lvl < L.view(n, 1)) & (~hole | (lvl == (L.view(n, 1) - 1)))
+    sib *= keep.view(n, N_LEVELS, 1).to(torch.int32)
+    keys = rand_elems(torch, n, gen)
+    keys[:, 5:] = 0
+    vals = rand_elems(torch, n, gen)
+    roots = torch.zeros((n, 8), dtype=torch.int32, device="cuda")
+    flags = torch.empty(n, dtype=torch.uint8, device="cuda")
+    status = torch.empty(n, dtype=torch.uint8, device="cuda")
+    tmp = torch.empty((n, 8), dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream()
+    eng.smt_verify_dev(N_LEVELS, n, roots, False, sib, keys, vals, flags, status, d_out_roots=tmp, stream=stream)
+    torch.cuda.synchronize()
+    roots.copy_(tmp)
+    vals[::16, 0] ^= 2                                 # every 16th proof carries a wrong value
+    expect = np.ones(n, dtype=np.uint8)
+    expect[::16] = 0
+    # resident timing
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eng.smt_verify_dev(N_LEVELS, n, roots, False, sib, keys, vals, flags, status, stream=stream)
+    e0.record(stream)
+    for _ in range(3):
+        eng.smt_verify_dev(N_LEVELS, n, roots, False, sib, keys, vals, flags, status, stream=stream)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    resident = n / (e0.elapsed_time(e1) / 3 * 1e-3)
+    # host copies: dense rows (pinned) and the packed blob a Go caller would hold (GenProof output, back to back)
+    hs = torch.empty(sib.shape, dtype=sib.dtype).pin_memory()
+    hs.copy_(sib)
+    hk, hv, hr = (t.cpu().numpy().view(np.uint8).reshape(n, 32) for t in (keys, vals, roots))
+    dense = hs.numpy().view(np.uint8).reshape(n, N_LEVELS, 32)
+    Lh = L.cpu().numpy()
+    nz = keep.cpu().numpy()
+    bm_len = (Lh + 7) // 8
+    cnt = nz.sum(axis=1)
+    lens = 4 + bm_len + 32 * cnt
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(lens, out=offs[1:])
+    blob_t = torch.empty(int(offs[-1]), dtype=torch.uint8).pin_memory()
+    blob = blob_t.numpy()
+    bits = np.packbits(nz[:, :32], axis=1, bitorder="little")          # L <= 28: four bitmap bytes are enough
+    for i in range(n):
+        o = int(offs[i])
+        blob[o:o + 2] = np.frombuffer(int(lens[i]).to_bytes(2, "little"), dtype=np.uint8)
+        blob[o + 2:o + 4] = np.frombuffer(int(bm_len[i]).to_bytes(2, "little"), dtype=np.uint8)
+        blob[o + 4:o + 4 + bm_len[i]] = bits[i, :bm_len[i]]
+        blob[o + 4 + bm_len[i]:o + lens[i]] = dense[i, :Lh[i]][nz[i, :Lh[i]]].reshape(-1)
+    of, os_ = np.empty(n, dtype=np.uint8), np.empty(n, dtype=np.uint8)
+    lib, hctx = eng._lib, eng._h
+
+    def run_dense():
+        rc = lib.gcp_smt_verify_inclusion(hctx, N_LEVELS, n, hr.ctypes.data, 0, dense.ctypes.data, hk.ctypes.data,
+                                          hv.ctypes.data, of.ctypes.data, os_.ctypes.data, None, g.FMT_CANONICAL)
+        if rc != 0:
+            raise RuntimeError(lib.gcp_last_error(hctx))
+
+    def run_packed():
+        rc = lib.gcp_smt_verify_packed(hctx, N_LEVELS, n, hr.ctypes.data, 0, blob.ctypes.data, offs.ctypes.data, None,
+                                       None, None, hk.ctypes.data, hv.ctypes.data, None, None, of.ctypes.data,
+                                       os_.ctypes.data, None, g.FMT_CANONICAL)
+        if rc != 0:
+            raise RuntimeError(lib.gcp_last_error(hctx))
+
+    res = {"proofs": n, "mean_path_levels": float(Lh.mean()), "resident_proofs_per_s": resident,
+           "dense_h2d_bytes": int(n * (N_LEVELS + 3) * 32), "packed_h2d_bytes": int(offs[-1]) + (n + 1) * 8 + n * 96}
+    for name, fn in (("dense", run_dense), ("packed", run_packed)):
+        fn()
+        ok = bool((of == expect).all()) and not bool(os_.any())
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            fn()
+        dt = (time.perf_counter() - t0) / 3
+        res[f"{name}_e2e_proofs_per_s"] = n / dt
+        res[f"{name}_flags_ok"] = ok
+    return res
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons of one GPU every 200 ms while the timed region runs."""
 
@@ -402,6 +490,8 @@ def main():
     extras = None
     if not args.no_extras:
         extras = measure_extras(torch, dist, eng, g, world, rank)
+        if world == 1:
+            extras["census_like_e2e"] = measure_census_like(torch, eng, g)
 
     # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample) -----------------------------------
     cpu_baseline = None

@@ -48,6 +48,11 @@ SIGNATURES = {
     "gcp_smt_verify_dev": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                    c_void_p]),
+    "gcp_smt_verify_packed": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_int]),
+    "gcp_smt_unpack_siblings_dev": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p,
+                                            c_int, c_void_p]),
     "gcp_smt_scan_dev": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gcp_smt_verify_inclusion": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                          c_void_p, c_void_p, c_void_p, c_int]),

@@ -19,7 +19,7 @@ using namespace gcp;
 namespace {
 
 constexpr uint32_t BLOB_MAGIC = 0x32425350u;  // 'PSB2', written by oracle/gen_constants.py
-constexpr int N_SLOTS = 80;
+constexpr int N_SLOTS = 96;
 
 thread_local std::string g_create_error;
 
@@ -498,16 +498,20 @@ int gcp_smt_verify_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_roots
                                (cudaStream_t)stream, 2);
 }
 
-int gcp_smt_verify(gcp_ctx* ctx, int n_levels, size_t n, const void* roots, int shared_root, const void* siblings,
-                   const void* old_keys, const void* old_values, const uint8_t* is_old0, const void* keys,
-                   const void* values, const uint8_t* fnc, const uint8_t* enabled, uint8_t* out_flags,
-                   uint8_t* out_status, void* out_roots, int fmt) {
+// Host-buffer verifier: `siblings` dense (Assignment.Siblings rows), or NULL with arbo-packed proofs in
+// `packed` / `offsets` that are expanded on the device (smt_unpack_kernel) chunk by chunk.
+static int smt_verify_host(gcp_ctx* ctx, int n_levels, size_t n, const void* roots, int shared_root, const void* siblings,
+                           const uint8_t* packed, const uint64_t* offsets, const void* old_keys, const void* old_values,
+                           const uint8_t* is_old0, const void* keys, const void* values, const uint8_t* fnc,
+                           const uint8_t* enabled, uint8_t* out_flags, uint8_t* out_status, void* out_roots, int fmt) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
-  int rc = smt_check_args(ctx, n_levels, n, roots, siblings, old_keys, old_values, keys, values, out_flags, out_status,
-                          fmt);
+  const bool is_packed = siblings == nullptr;
+  int rc = smt_check_args(ctx, n_levels, n, roots, is_packed ? (const void*)packed : siblings, old_keys, old_values, keys,
+                          values, out_flags, out_status, fmt);
   if (rc != GCP_OK || n == 0) return rc;
+  if (is_packed && !offsets) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
   const size_t sib_bytes = (size_t)n_levels * 32;
   // chunk = a whole number of resident-thread waves of smt_path_kernel (5 blocks x 128 threads per SM), about 1 GB of
   // siblings, so that a chunk's launch fills the machine; two chunks are in flight on the two streams
@@ -547,7 +551,25 @@ int gcp_smt_verify(gcp_ctx* ctx, int n_levels, size_t n, const void* roots, int 
     if (!d_sib || !d_roots || !d_keys || !d_vals || !d_flags || !d_status || (old_keys && (!d_okeys || !d_ovals)) ||
         (is_old0 && !d_is0) || (fnc && !d_fnc) || (enabled && !d_en) || (out_roots && !d_oroots))
       return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
-    CU(cudaMemcpyAsync(d_sib, (const char*)siblings + off * sib_bytes, m * sib_bytes, cudaMemcpyHostToDevice, st), "H2D");
+    uint8_t* d_bad = nullptr;
+    if (is_packed) {
+      const uint64_t pbeg = offsets[off], pend = offsets[off + m];
+      if (pend < pbeg) {
+        rc = ctx->fail(GCP_ERR_BAD_ARG, "packed offsets must be non-decreasing");
+        break;
+      }
+      const size_t pbytes = (size_t)(pend - pbeg);
+      uint8_t* d_packed = (uint8_t*)ctx->buf(80 + s * 3 + 0, pbytes + 4);  // + 4: the aligned word of a last odd byte
+      uint64_t* d_off = (uint64_t*)ctx->buf(80 + s * 3 + 1, (m + 1) * 8);
+      d_bad = (uint8_t*)ctx->buf(80 + s * 3 + 2, m);
+      if (!d_packed || !d_off || !d_bad) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+      if (pbytes) CU(cudaMemcpyAsync(d_packed, packed + pbeg, pbytes, cudaMemcpyHostToDevice, st), "H2D");
+      CU(cudaMemcpyAsync(d_off, offsets + off, (m + 1) * 8, cudaMemcpyHostToDevice, st), "H2D");
+      CU(launch_smt_unpack(d_packed, d_off, pbeg, pbytes, m, n_levels, (u32*)d_sib, d_bad, fmt, st), "smt unpack kernel");
+      ctx->launches++;
+    } else {
+      CU(cudaMemcpyAsync(d_sib, (const char*)siblings + off * sib_bytes, m * sib_bytes, cudaMemcpyHostToDevice, st), "H2D");
+    }
     if (!shared_root) CU(cudaMemcpyAsync(d_roots, (const char*)roots + off * 32, m * 32, cudaMemcpyHostToDevice, st), "H2D");
     CU(cudaMemcpyAsync(d_keys, (const char*)keys + off * 32, m * 32, cudaMemcpyHostToDevice, st), "H2D");
     CU(cudaMemcpyAsync(d_vals, (const char*)values + off * 32, m * 32, cudaMemcpyHostToDevice, st), "H2D");
@@ -561,6 +583,10 @@ int gcp_smt_verify(gcp_ctx* ctx, int n_levels, size_t n, const void* roots, int 
     rc = smt_verify_dev_locked(ctx, n_levels, m, d_roots, shared_root, d_sib, d_okeys, d_ovals, d_is0, d_keys, d_vals,
                                d_fnc, d_en, d_flags, d_status, d_oroots, fmt, st, b + 12);
     if (rc != GCP_OK) break;
+    if (is_packed) {
+      CU(launch_smt_apply_bad(d_bad, m, d_flags, d_status, (u32*)d_oroots, st), "smt apply-bad kernel");
+      ctx->launches++;
+    }
     CU(cudaMemcpyAsync(out_flags + off, d_flags, m, cudaMemcpyDeviceToHost, st), "D2H");
     CU(cudaMemcpyAsync(out_status + off, d_status, m, cudaMemcpyDeviceToHost, st), "D2H");
     if (out_roots) CU(cudaMemcpyAsync((char*)out_roots + off * 32, d_oroots, m * 32, cudaMemcpyDeviceToHost, st), "D2H");
@@ -570,6 +596,40 @@ int gcp_smt_verify(gcp_ctx* ctx, int n_levels, size_t n, const void* roots, int 
   if (rc != GCP_OK) return rc;
   if (e0 != cudaSuccess) return ctx->cuda_fail(e0, "stream sync");
   if (e1 != cudaSuccess) return ctx->cuda_fail(e1, "stream sync");
+  return GCP_OK;
+}
+
+int gcp_smt_verify(gcp_ctx* ctx, int n_levels, size_t n, const void* roots, int shared_root, const void* siblings,
+                   const void* old_keys, const void* old_values, const uint8_t* is_old0, const void* keys,
+                   const void* values, const uint8_t* fnc, const uint8_t* enabled, uint8_t* out_flags,
+                   uint8_t* out_status, void* out_roots, int fmt) {
+  if (ctx && n && !siblings) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  return smt_verify_host(ctx, n_levels, n, roots, shared_root, siblings, nullptr, nullptr, old_keys, old_values, is_old0,
+                         keys, values, fnc, enabled, out_flags, out_status, out_roots, fmt);
+}
+
+int gcp_smt_verify_packed(gcp_ctx* ctx, int n_levels, size_t n, const void* roots, int shared_root,
+                          const uint8_t* packed, const uint64_t* offsets, const void* old_keys, const void* old_values,
+                          const uint8_t* is_old0, const void* keys, const void* values, const uint8_t* fnc,
+                          const uint8_t* enabled, uint8_t* out_flags, uint8_t* out_status, void* out_roots, int fmt) {
+  if (ctx && n && (!packed || !offsets)) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  return smt_verify_host(ctx, n_levels, n, roots, shared_root, nullptr, packed, offsets, old_keys, old_values, is_old0,
+                         keys, values, fnc, enabled, out_flags, out_status, out_roots, fmt);
+}
+
+int gcp_smt_unpack_siblings_dev(gcp_ctx* ctx, int n_levels, size_t n, const uint8_t* d_packed, size_t packed_bytes,
+                                const uint64_t* d_offsets, void* d_siblings, uint8_t* d_bad, int fmt, void* stream) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  if (n_levels < 2 || n_levels > 253) return ctx->fail(GCP_ERR_BAD_ARG, "n_levels must be in [2, 253]");
+  if (fmt != GCP_FMT_CANONICAL && fmt != GCP_FMT_MONTGOMERY) return ctx->fail(GCP_ERR_BAD_ARG, "bad element format");
+  if (n == 0) return GCP_OK;
+  if (!d_packed || !d_offsets || !d_siblings || !d_bad) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  CU(launch_smt_unpack(d_packed, d_offsets, 0, packed_bytes, n, n_levels, (u32*)d_siblings, d_bad, fmt,
+                       (cudaStream_t)stream),
+     "smt unpack kernel");
+  ctx->launches++;
   return GCP_OK;
 }
 

@@ -261,6 +261,29 @@ cudaError_t launch_smt_process(const SmtProcessArgs& a, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+cudaError_t launch_smt_unpack(const u8* packed, const u64* offsets, u64 base, u64 packed_bytes, size_t n, int n_levels,
+                              u32* siblings, u8* bad, int mont, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  SmtUnpackArgs a;
+  a.packed = packed;
+  a.offsets = offsets;
+  a.base = base;
+  a.packed_bytes = packed_bytes;
+  a.n = n;
+  a.n_levels = n_levels;
+  a.siblings = siblings;
+  a.bad = bad;
+  a.mont = mont;
+  smt_unpack_kernel<<<(unsigned)((n + 3) / 4), 128, 0, stream>>>(a);  // one warp per proof
+  return cudaGetLastError();
+}
+
+cudaError_t launch_smt_apply_bad(const u8* bad, size_t n, u8* flags, u8* status, u32* out_roots, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  smt_apply_bad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(bad, n, flags, status, out_roots);
+  return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------------
 // ElGamal
 // ---------------------------------------------------------------------------------------------------

@@ -20,6 +20,7 @@ enum : u8 {
   GCP_STATUS_OFF_CURVE = 4,     // public key fails AssertIsOnCurve (elgamal/encrypt.go:49)
   GCP_STATUS_ZERO_DENOM = 5,    // Edwards addition denominator is 0 (only reachable off-curve)
   GCP_STATUS_ASSERTION = 6,     // an AssertIsEqual of the gadget fails (SMT processor: old root, LevIns, states, key rule)
+  GCP_STATUS_MALFORMED = 7,     // arbo.UnpackSiblings would reject the packed proof (wrapper_arbo.go:64-67)
 };
 
 struct PoseidonTable {  // one per t, device pointers into the global-memory copy
@@ -87,6 +88,10 @@ cudaError_t launch_smt_verify(const SmtArgs& a, const SmtScratch& sc, int sm_cou
 cudaError_t launch_smt_scan(const u32* siblings, size_t n, int n_levels, u16* lidx, u8* info, u32* hist, int sm_count,
                             cudaStream_t stream);
 cudaError_t launch_smt_process(const SmtProcessArgs& a, cudaStream_t stream);
+// arbo packed siblings (absolute offsets into a blob whose byte `base` is packed[0]) -> dense rows + bad[n]
+cudaError_t launch_smt_unpack(const u8* packed, const u64* offsets, u64 base, u64 packed_bytes, size_t n, int n_levels,
+                              u32* siblings, u8* bad, int mont, cudaStream_t stream);
+cudaError_t launch_smt_apply_bad(const u8* bad, size_t n, u8* flags, u8* status, u32* out_roots, cudaStream_t stream);
 
 // ElGamal (elgamal.cuh)
 size_t fb_table_bytes();

@@ -570,4 +570,98 @@ __global__ void __launch_bounds__(128) smt_process_kernel(SmtProcessArgs a) {
   a.status[idx] = st;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// arbo packed siblings -> Assignment.Siblings rows
+// ---------------------------------------------------------------------------------------------------
+// What the callers of this path do on the CPU before they can fill smt.Assignment: arbo.UnpackSiblings on the
+// byte string GenProof returns, then pad with zeros (or cut) to `levels`
+// (/root/reference/tree/smt/wrapper_arbo.go:63-76,166-179, testutil/utils.go:152-166).  Wire format (arbo
+// PackSiblings, un-vendored dependency, restated in oracle/smt.py::pack_siblings):
+//   [u16 LE full length][u16 LE bitmap length L][L bytes bitmap, bit i = byte i/8 bit i%8][32 B LE per set bit]
+// One warp per proof; lane l expands levels l, l+32, ...  A proof arbo would reject (length field mismatch, bitmap
+// running past the string, a set bit whose 32 bytes are cut short) gets bad = GCP_STATUS_MALFORMED and an all-zero
+// row.  Siblings are canonical little-endian integers on the wire; for the Montgomery element format they are
+// converted here (a sibling >= r is stored as it is, so the verifier's scan reports it as non-canonical).
+struct SmtUnpackArgs {
+  const u8* packed;    // the chunk's packed bytes
+  const u64* offsets;  // n + 1 absolute offsets into the caller's blob
+  u64 base;            // offset of packed[0] in the caller's blob
+  u64 packed_bytes;    // bytes available behind `packed`
+  size_t n;
+  int n_levels;
+  u32* siblings;       // n x n_levels x 8
+  u8* bad;             // n
+  int mont;
+};
+
+__device__ __forceinline__ void load_unaligned32(u32 (&r)[8], const u8* p) {
+  const uintptr_t a = (uintptr_t)p;
+  const u32* w = (const u32*)(a & ~(uintptr_t)3);
+  const u32 sh = (u32)(a & 3) * 8;
+  u32 prev = __ldg(w);
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    u32 next = (k < 7 || sh) ? __ldg(w + k + 1) : 0;
+    r[k] = sh ? __funnelshift_r(prev, next, sh) : prev;
+    prev = next;
+  }
+}
+
+__global__ void __launch_bounds__(128) smt_unpack_kernel(SmtUnpackArgs a) {
+  const size_t proof = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (proof >= a.n) return;
+  const u64 beg = a.offsets[proof], end = a.offsets[proof + 1];
+  bool bad = end < beg || beg < a.base || end - a.base > a.packed_bytes;
+  const u64 len = bad ? 0 : end - beg;
+  const u8* b = a.packed + (bad ? 0 : beg - a.base);
+  u32 L = 0;
+  if (!bad) bad = len < 4 || len > 0xffff;
+  if (!bad) {
+    const u32 full = (u32)b[0] | ((u32)b[1] << 8);
+    L = (u32)b[2] | ((u32)b[3] << 8);
+    bad = full != (u32)len || 4 + (u64)L > len;
+  }
+  const u8* bitmap = b + 4;
+  const u8* data = bitmap + L;
+  const u32 dlen = bad ? 0 : (u32)len - 4 - L;
+  const u32 avail = dlen / 32;
+  if (!bad && (dlen & 31)) {
+    // arbo walks every bit of the bitmap: a set bit that starts inside the data but is cut short is an error
+    u32 cnt = 0;
+    for (u32 j = lane; j < L; j += 32) cnt += __popc((u32)bitmap[j]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    bad = cnt > avail;
+  }
+  for (int i = lane; i < a.n_levels; i += 32) {
+    u32 v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (!bad && (u32)i < 8 * L && ((bitmap[i >> 3] >> (i & 7)) & 1)) {
+      u32 rank = __popc((u32)bitmap[i >> 3] & ((1u << (i & 7)) - 1));
+      for (int j = 0; j < (i >> 3); j++) rank += __popc((u32)bitmap[j]);
+      if (rank < avail) {
+        load_unaligned32(v, data + (size_t)rank * 32);
+        if (a.mont && fr_is_canonical(v)) {
+          fr_to_mont(v, v);
+          fr_canon(v);
+        }
+      }
+    }
+    store_fr(a.siblings + (proof * (size_t)a.n_levels + i) * 8, v);
+  }
+  if (lane == 0) a.bad[proof] = bad ? GCP_STATUS_MALFORMED : 0;
+}
+
+// a malformed proof never reaches the gadget: the caller's unpack step returns an error (wrapper_arbo.go:64-67)
+__global__ void smt_apply_bad_kernel(const u8* bad, size_t n, u8* flags, u8* status, u32* out_roots) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !bad[i]) return;
+  flags[i] = 0;
+  status[i] = bad[i];
+  if (out_roots) {
+#pragma unroll
+    for (int l = 0; l < 8; l++) out_roots[i * 8 + l] = 0;
+  }
+}
+
 }  // namespace gcp

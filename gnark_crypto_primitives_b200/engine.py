@@ -180,6 +180,54 @@ class Engine:
                                              _ptr(oroots), fmt))
         return (flags, status, oroots) if want_roots else (flags, status)
 
+    def smt_verify_packed(self, roots, packed, n_levels, keys, values, offsets=None, old_keys=None, old_values=None,
+                          is_old0=None, fnc=None, enabled=None, want_roots=False, fmt=FMT_CANONICAL):
+        """smt.Verifier fed with arbo's packed proofs (what GenProof returns; the reference's callers run
+        arbo.UnpackSiblings and pad to `levels` on the CPU, tree/smt/wrapper_arbo.go:63-76).
+
+        packed: a list of byte strings, or one bytes/uint8 blob together with `offsets` (n + 1 byte offsets).
+        Returns (flags, status[, roots]); a string arbo would reject has status 7 (malformed), flag 0.
+        """
+        if offsets is None:
+            lens = np.fromiter((len(b) for b in packed), dtype=np.uint64, count=len(packed))
+            offs = np.zeros(len(packed) + 1, dtype=np.uint64)
+            np.cumsum(lens, out=offs[1:])
+            blob = np.frombuffer(b"".join(bytes(b) for b in packed), dtype=np.uint8)
+        else:
+            offs = np.ascontiguousarray(offsets, dtype=np.uint64)
+            blob = np.frombuffer(packed, dtype=np.uint8) if isinstance(packed, (bytes, bytearray)) else \
+                np.ascontiguousarray(packed, dtype=np.uint8)
+            if offs.ndim != 1 or offs.size < 1 or int(offs[-1]) > blob.size:
+                raise ValueError("offsets must hold n + 1 byte offsets into packed")
+        if blob.size == 0:
+            blob = np.zeros(1, dtype=np.uint8)
+        n = offs.size - 1
+        r = _as_elems(roots, name="roots")
+        shared = 1 if r.size == 32 and n != 1 else 0
+        if not shared:
+            r = _as_elems(r, n, "roots")
+        k = _as_elems(keys, n, "keys")
+        v = _as_elems(values, n, "values")
+        ok = _as_elems(old_keys, n, "old_keys") if old_keys is not None else None
+        ov = _as_elems(old_values, n, "old_values") if old_values is not None else None
+        i0 = _u8(is_old0, n, "is_old0")
+        fn = _u8(fnc, n, "fnc")
+        en = _u8(enabled, n, "enabled")
+        flags = np.empty(n, dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        oroots = np.empty((n, 32), dtype=np.uint8) if want_roots else None
+        self._check(self._lib.gcp_smt_verify_packed(self._h, int(n_levels), n, _ptr(r), shared, _ptr(blob), _ptr(offs),
+                                                    _ptr(ok), _ptr(ov), _ptr(i0), _ptr(k), _ptr(v), _ptr(fn), _ptr(en),
+                                                    _ptr(flags), _ptr(status), _ptr(oroots), fmt))
+        return (flags, status, oroots) if want_roots else (flags, status)
+
+    def smt_unpack_siblings_dev(self, n_levels, n, d_packed, packed_bytes, d_offsets, d_siblings, d_bad,
+                                fmt=FMT_CANONICAL, stream=None):
+        """arbo.UnpackSiblings + zero padding on device buffers (feeds smt_verify_dev)."""
+        self._check(self._lib.gcp_smt_unpack_siblings_dev(self._h, n_levels, n, _dptr(d_packed), packed_bytes,
+                                                          _dptr(d_offsets), _dptr(d_siblings), _dptr(d_bad), fmt,
+                                                          self._stream(stream)))
+
     def smt_verify_inclusion(self, roots, siblings, keys, values, want_roots=False, fmt=FMT_CANONICAL):
         """smt.InclusionVerifier (tree/smt/verifier.go:29-43)."""
         sib = _as_elems(siblings, name="siblings")

@@ -31,6 +31,7 @@ const (
 	StatusOffCurve     = 4 // elgamal/encrypt.go:49
 	StatusZeroDenom    = 5
 	StatusAssertion    = 6 // tree/smt/processor.go assertions
+	StatusMalformed    = 7 // arbo.UnpackSiblings error (tree/smt/wrapper_arbo.go:64-67)
 )
 
 // Engine owns one GPU context. Goroutines may share it (calls are serialised inside the library); use one Engine
@@ -121,6 +122,34 @@ func (e *Engine) BatchVerify(p *Proofs) (flags, status []byte, err error) {
 	err = e.err(C.gcp_smt_verify(e.ctx, C.int(p.Levels), C.size_t(n), elemPtr(p.Roots), C.int(shared), elemPtr(p.Siblings),
 		elemPtr(p.OldKeys), elemPtr(p.OldValues), bytePtr(p.IsOld0), elemPtr(p.Keys), elemPtr(p.Values), bytePtr(p.Fnc),
 		bytePtr(p.Enabled), bytePtr(flags), bytePtr(status), nil, C.GCP_FMT_MONTGOMERY))
+	return
+}
+
+// BatchVerifyPacked is BatchVerify for proofs still in arbo's packed form: packed[i] is the siblingsPacked that
+// tree.GenProof returned for Keys[i] (the reference's callers run arbo.UnpackSiblings and pad to `levels` on the CPU,
+// tree/smt/wrapper_arbo.go:63-76); p.Siblings is ignored.  status 7 = arbo.UnpackSiblings would have failed.
+func (e *Engine) BatchVerifyPacked(p *Proofs, packed [][]byte) (flags, status []byte, err error) {
+	n := len(p.Keys)
+	flags, status = make([]byte, n), make([]byte, n)
+	offsets := make([]uint64, n+1)
+	total := 0
+	for i, b := range packed {
+		total += len(b)
+		offsets[i+1] = uint64(total)
+	}
+	blob := make([]byte, 0, total+1)
+	for _, b := range packed {
+		blob = append(blob, b...)
+	}
+	blob = append(blob, 0) // never a nil pointer for an all-empty batch
+	shared := 0
+	if len(p.Roots) == 1 && n != 1 {
+		shared = 1
+	}
+	err = e.err(C.gcp_smt_verify_packed(e.ctx, C.int(p.Levels), C.size_t(n), elemPtr(p.Roots), C.int(shared), bytePtr(blob),
+		(*C.uint64_t)(unsafe.Pointer(&offsets[0])), elemPtr(p.OldKeys), elemPtr(p.OldValues), bytePtr(p.IsOld0),
+		elemPtr(p.Keys), elemPtr(p.Values), bytePtr(p.Fnc), bytePtr(p.Enabled), bytePtr(flags), bytePtr(status), nil,
+		C.GCP_FMT_MONTGOMERY))
 	return
 }
 

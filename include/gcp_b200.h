@@ -50,7 +50,8 @@ enum gcp_status {
   GCP_STATUS_NOT_BOOLEAN = 3,  /* enabled / fnc / isOld0 outside {0,1}: api.Select / api.And assertions */
   GCP_STATUS_OFF_CURVE = 4,    /* AssertIsOnCurve(pubKey), elgamal/encrypt.go:49 */
   GCP_STATUS_ZERO_DENOM = 5,   /* Edwards addition denominator 0 (reachable only with off-curve inputs) */
-  GCP_STATUS_ASSERTION = 6     /* an AssertIsEqual of the gadget fails (SMT processor, decryption checks) */
+  GCP_STATUS_ASSERTION = 6,    /* an AssertIsEqual of the gadget fails (SMT processor, decryption checks) */
+  GCP_STATUS_MALFORMED = 7     /* arbo.UnpackSiblings would reject the packed proof (tree/smt/wrapper_arbo.go:64-67) */
 };
 
 /* ---- context ------------------------------------------------------------------------------------ */
@@ -116,6 +117,26 @@ int gcp_smt_verify_exclusion(gcp_ctx* ctx, int n_levels, size_t n, const void* r
                              const void* siblings, const void* old_keys, const void* old_values,
                              const uint8_t* is_old0, const void* keys, uint8_t* out_flags, uint8_t* out_status,
                              void* out_roots, int fmt);
+
+/* The same verifier fed with arbo's PACKED proofs, i.e. the byte strings GenProof returns, which the reference's
+ * callers expand on the CPU with arbo.UnpackSiblings and pad with zeros to `levels` before they can fill
+ * smt.Assignment (tree/smt/wrapper_arbo.go:48,63-76; testutil/utils.go:143,152-166).  Here the expansion runs on
+ * the GPU, so a census-like proof crosses PCIe as ~0.8 KB instead of n_levels * 32 bytes.
+ *   packed:  the n byte strings back to back;  offsets: n + 1 byte offsets into `packed` (offsets[i+1] - offsets[i]
+ *            is the length of proof i)
+ *   wire format of one proof (arbo PackSiblings):  u16 LE total length | u16 LE bitmap length L | L bitmap bytes
+ *            (bit i = byte i/8, bit i%8: sibling i is non-zero) | 32 bytes LE per set bit
+ *   siblings are canonical little-endian integers on the wire in either `fmt`; every other element follows `fmt`.
+ * A string arbo.UnpackSiblings would reject gets status GCP_STATUS_MALFORMED, flag 0; siblings past n_levels are
+ * dropped exactly as wrapper_arbo.go:69-76 drops them.  Everything else as gcp_smt_verify. */
+int gcp_smt_verify_packed(gcp_ctx* ctx, int n_levels, size_t n, const void* roots, int shared_root,
+                          const uint8_t* packed, const uint64_t* offsets, const void* old_keys, const void* old_values,
+                          const uint8_t* is_old0, const void* keys, const void* values, const uint8_t* fnc,
+                          const uint8_t* enabled, uint8_t* out_flags, uint8_t* out_status, void* out_roots, int fmt);
+/* arbo.UnpackSiblings + zero padding on device buffers: d_siblings receives n * n_levels elements in `fmt`,
+ * d_bad n bytes (0 or GCP_STATUS_MALFORMED).  Compose with gcp_smt_verify_dev / gcp_smt_process_dev. */
+int gcp_smt_unpack_siblings_dev(gcp_ctx* ctx, int n_levels, size_t n, const uint8_t* d_packed, size_t packed_bytes,
+                                const uint64_t* d_offsets, void* d_siblings, uint8_t* d_bad, int fmt, void* stream);
 
 /* smt.Processor (tree/smt/processor.go:10-72): state transition of n independent trees/proofs.
  * fnc = (fnc0, fnc1): (1,0) insert, (0,1) update, (1,1) delete, (0,0) nop.  Output: new_roots (n elements).

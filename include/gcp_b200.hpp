@@ -96,6 +96,19 @@ inline Batch Verifier(const Engine& e, int n_levels, size_t n, const uint8_t* en
                          enabled, b.flags.data(), b.status.data(), nullptr, fmt));
   return b;
 }
+// Verifier over arbo's packed proofs (GenProof output, expanded on the GPU instead of arbo.UnpackSiblings + padding,
+// tree/smt/wrapper_arbo.go:63-76); old_keys == nullptr gives the InclusionVerifier form.
+inline Batch VerifierPacked(const Engine& e, int n_levels, size_t n, const uint8_t* roots, bool shared_root,
+                            const uint8_t* packed, const uint64_t* offsets, const uint8_t* old_keys,
+                            const uint8_t* old_values, const uint8_t* is_old0, const uint8_t* keys, const uint8_t* values,
+                            const uint8_t* fnc, const uint8_t* enabled = nullptr, int fmt = GCP_FMT_CANONICAL) {
+  Batch b;
+  b.flags.resize(n);
+  b.status.resize(n);
+  e.check(gcp_smt_verify_packed(e.raw(), n_levels, n, roots, shared_root, packed, offsets, old_keys, old_values, is_old0,
+                                keys, values, fnc, enabled, b.flags.data(), b.status.data(), nullptr, fmt));
+  return b;
+}
 // returns the new roots in `values`
 inline Batch Processor(const Engine& e, int n_levels, size_t n, const uint8_t* old_roots, const uint8_t* siblings,
                        const uint8_t* old_keys, const uint8_t* old_values, const uint8_t* is_old0, const uint8_t* new_keys,

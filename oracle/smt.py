@@ -220,12 +220,75 @@ class Tree:
                 sibs.append(self._h(node[2]))
                 node = node[1]
             depth += 1
+        packed = pack_siblings(sibs)
         sibs += [0] * (self.max_levels - len(sibs))
+        self.last_packed = packed  # arbo GenProof's siblingsPacked for the proof just generated
         if node is None:
             return dict(exists=False, old_key=0, old_value=0, is_old0=1, siblings=sibs)
         if node[1] == key:
             return dict(exists=True, old_key=key, old_value=node[2], is_old0=0, siblings=sibs)
         return dict(exists=False, old_key=node[1], old_value=node[2], is_old0=0, siblings=sibs)
+
+
+# --------------------------------------------------------------------------------------
+# arbo packed-sibling wire format (what GenProof returns and the callers unpack)
+# --------------------------------------------------------------------------------------
+STATUS_MALFORMED = 7  # arbo.UnpackSiblings would return an error (or slice out of range) on this byte string
+
+
+def pack_siblings(siblings, hash_len=32):
+    """arbo.PackSiblings (github.com/vocdoni/arbo v0.0.0-20250707215550-6dee1243bb29, un-vendored; the reference
+    only holds the call sites of its inverse: tree/smt/wrapper_arbo.go:64,166 and testutil/utils.go:153).
+    Layout:  [2 B full length, LE][2 B bitmap length L, LE][L B bitmap][32 B per non-zero sibling, LE integers]
+    bitmap bit i (byte i/8, LSB first) is set iff sibling i is non-zero.  `siblings` is the root->leaf list as
+    GenProof produces it (length = depth of the leaf, not padded).  PARITY UNPINNED: restated from the published
+    arbo source, no vector for it exists in the reference tree."""
+    bitmap = bytearray((len(siblings) + 7) // 8)
+    body = b""
+    for i, sib in enumerate(siblings):
+        if sib != 0:
+            bitmap[i // 8] |= 1 << (i % 8)
+            body += int(sib).to_bytes(hash_len, "little")
+    full = 4 + len(bitmap) + len(body)
+    if full > 0xFFFF or len(bitmap) > 0xFFFF:
+        raise ValueError("packed siblings too long")
+    return full.to_bytes(2, "little") + len(bitmap).to_bytes(2, "little") + bytes(bitmap) + body
+
+
+def unpack_siblings(b, hash_len=32):
+    """arbo.UnpackSiblings: -> list of integers (root->leaf), or None where arbo returns an error / the Go slice
+    expression would run past the data (treated alike: STATUS_MALFORMED).  Trailing clear bits after the data is
+    exhausted are not materialised (the caller pads with zeros anyway, wrapper_arbo.go:69-76)."""
+    if len(b) < 4:
+        return None
+    full = int.from_bytes(b[0:2], "little")
+    l = int.from_bytes(b[2:4], "little")
+    if full != len(b) or 4 + l > len(b):
+        return None
+    bitmap = b[4:4 + l]
+    data = b[4 + l:]
+    out = []
+    pos = 0
+    for i in range(8 * l):
+        if pos >= len(data):
+            break
+        if (bitmap[i // 8] >> (i % 8)) & 1:
+            if pos + hash_len > len(data):
+                return None
+            out.append(int.from_bytes(data[pos:pos + hash_len], "little"))
+            pos += hash_len
+        else:
+            out.append(0)
+    return out
+
+
+def assignment_siblings(packed, levels):
+    """Assignment.Siblings as wrapper_arbo.go:63-76 / testutil/utils.go:152-166 build it: unpack, then pad with
+    zeros (or silently cut) to `levels`.  -> (siblings, status)."""
+    un = unpack_siblings(packed)
+    if un is None:
+        return [0] * levels, STATUS_MALFORMED
+    return [un[i] if i < len(un) else 0 for i in range(levels)], STATUS_OK
 
 
 # --------------------------------------------------------------------------------------

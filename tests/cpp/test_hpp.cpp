@@ -42,6 +42,21 @@ int main() {
   put(key, 5);  // tree/smt/utils_test.go:27-39: key 5 must not verify where key 7 does
   v = gcp::smt::InclusionVerifier(eng, 3, 1, root.values.data(), false, sib, key, val);
   if (v.flags[0] != 0 || v.status[0] != 0) return 3;
+  // the same proof in arbo's packed form: total length 4 + 1 + 2*32, bitmap length 1, bitmap 0b011, siblings 11, 22
+  uint8_t packed[4 + 1 + 64] = {69, 0, 1, 0, 3};
+  memcpy(packed + 5, sib, 64);
+  const uint64_t offsets[2] = {0, sizeof(packed)};
+  put(key, 7);
+  v = gcp::smt::VerifierPacked(eng, 3, 1, root.values.data(), false, packed, offsets, nullptr, nullptr, nullptr, key, val,
+                               nullptr);
+  if (v.flags[0] != 1 || v.status[0] != 0) {
+    fprintf(stderr, "packed inclusion proof rejected\n");
+    return 6;
+  }
+  packed[0] = 70;  // length field mismatch: arbo.UnpackSiblings errors
+  v = gcp::smt::VerifierPacked(eng, 3, 1, root.values.data(), false, packed, offsets, nullptr, nullptr, nullptr, key, val,
+                               nullptr);
+  if (v.flags[0] != 0 || v.status[0] != GCP_STATUS_MALFORMED) return 7;
   try {
     gcp::poseidon::Hash(eng, in, 17, 1);
     return 4;
