@@ -325,7 +325,11 @@ __device__ __forceinline__ void redc_row(Wide& w, u32& c) {
     s = wide_limb_e<0>(w);
   else
     s = wide_limb_e<I>(w) + wide_limb_o<I>(w) + c;
-  // (an ALU-pipe shift-add form of this multiply was measured 1.7 % slower: it lengthens the row-to-row critical path)
+  // (an ALU-pipe shift-add form of this multiply was measured 1.7 % slower: it lengthens the row-to-row critical path;
+  //  skipping the m * P[0] product - P[0] = 2^32 - 2^28 + 1, its low word cancels s and the word carried into limb I+1
+  //  is m - (m >> 4) + [(m << 28) < m] + floor(S / 2^32), exact and parity-green - makes a reduction 56 wide multiplies
+  //  but was measured 17 % slower on Hash2 (135 -> 112 M/s): the extra compares exhaust the 7 predicate registers that
+  //  carry the chains, ptxas spills predicates into a GPR with LOP3s and the path kernel's registers go 106 -> 124.)
   u32 m = s * GCP_NP;
   mac_row<I>(w, P, m);
   // limb I of E + O + c is now 0 mod 2^32; it is either 0 or exactly 2^32
