@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(128, 4) encrypt_shared_kernel(const u32* __res
   if (!second) status[idx] = !canon ? GCP_STATUS_NONCANONICAL : (!pk_ok ? GCP_STATUS_OFF_CURVE : GCP_STATUS_OK);
 }
 
-// ---- Encrypt with a public key per item: [k]PK by double-and-add -------------------------------------------------
+// ---- Encrypt with a public key per item: [k]PK by signed 4-bit windows (edwards.cuh) -------------------------------------------------
 __global__ void __launch_bounds__(128) encrypt_per_key_kernel(const u32* __restrict__ tabG, const u32* __restrict__ pks,
                                                               const u32* __restrict__ ks, const u32* __restrict__ ms, size_t n,
                                                               u32* __restrict__ out_xyz, u8* __restrict__ status, int mont) {
@@ -235,11 +235,7 @@ __global__ void __launch_bounds__(128) encrypt_per_key_kernel(const u32* __restr
     fixed_base_accumulate(c1, k, tabG);
     ExtPoint base;
     ext_from_affine(base, px, py);
-#pragma unroll 1
-    for (int bit = 253; bit >= 0; bit--) {  // k < r < 2^254
-      ext_double(c2);
-      if ((k[bit >> 5] >> (bit & 31)) & 1u) ext_add(c2, base);
-    }
+    ext_scalar_mul_windowed(c2, base, k);  // k < r < 2^254
     fixed_base_accumulate(c2, m, tabG);
   }
   store_ext_xyz(out_xyz + idx * 48, c1);

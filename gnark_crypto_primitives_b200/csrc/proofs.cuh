@@ -11,16 +11,9 @@
 
 namespace gcp {
 
-// [k]P for an on-curve P and an integer k < 2^254: MSB-first double-and-add in extended coordinates.
-__device__ __noinline__ void ext_scalar_mul(ExtPoint& out, const ExtPoint& base, const u32 (&k)[8]) {
-  ExtPoint acc;
-  ext_identity(acc);
-#pragma unroll 1
-  for (int bit = 253; bit >= 0; bit--) {
-    ext_double(acc);
-    if ((k[bit >> 5] >> (bit & 31)) & 1u) ext_add(acc, base);
-  }
-  out = acc;
+// [k]P for an on-curve P and an integer k < 2^254: signed 4-bit windows (edwards.cuh).
+__device__ __forceinline__ void ext_scalar_mul(ExtPoint& out, const ExtPoint& base, const u32 (&k)[8]) {
+  ext_scalar_mul_windowed(out, base, k);
 }
 
 // projective equality of two extended points (Z != 0 on both sides for curve points)
