@@ -342,7 +342,8 @@ __device__ __forceinline__ void redc_row(Wide& w, u32& c) {
 }
 
 // Montgomery reduction: r = w / 2^256 mod r, not fully reduced.
-// Bound: r < w / 2^256 + r_mod.  For every call site in this engine w < 6.2 r^2 + r*2^256, so r < 3.2 r_mod < 2^256.
+// Bound: r < w / 2^256 + r_mod.  The register-resident kernels keep w < 6.2 r^2 (result < 3.2 r_mod); the generic
+// Poseidon rows go up to 22 r^2 (result < 5.2 r_mod < 2^256, see poseidon.cuh).
 __device__ __forceinline__ void wide_redc_finish(Wide& w, u32 c, u32 (&r)[8]);
 
 __device__ __forceinline__ void wide_redc(Wide& w, u32 (&r)[8]) {

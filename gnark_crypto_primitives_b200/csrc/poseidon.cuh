@@ -220,7 +220,16 @@ __device__ __forceinline__ void poseidon_hash3(u32 (&out)[8], const u32 (&a)[8],
 namespace gcp {
 
 constexpr int POSEIDON_MAX_T = 17;
-constexpr int LAZY_DOT_MAX = 5;  // terms (< 2r)*(< r) per reduction so that the result is < 2.9 r (see fr.cuh bounds)
+// Lazy dot products in the generic kernel: how many (state x constant) products share one Montgomery reduction.
+// With r / 2^256 = 0.1891, constants < r and n terms:  state < 2r:  sum < 2n r^2 must stay below 2^512 - r 2^256
+// (0.0715 n < 0.811, n <= 11) and the reduced value 0.378 n r + r below 2^256 = 5.29 r (n <= 11);  state < r (canonical):
+// 0.0357 n < 0.811 and 0.189 n + 1 < 5.29, n <= 22.  So t <= 11 takes the whole row in one reduction as it is, and
+// t = 12..17 keeps the state canonical (one conditional subtraction of r per state write) and does the same.  Two
+// conditional subtractions of 2r bring the row result (< 5.2 r) back under 2r.  (The first version reduced every 5
+// terms: 4 reductions per row at t = 17.)
+constexpr int LAZY_DOT_NONCANON_MAX = 11;
+
+__device__ __forceinline__ bool generic_state_canonical(int t) { return t > LAZY_DOT_NONCANON_MAX; }
 
 __device__ __forceinline__ void load_global_const(u32 (&r)[8], const u32* p) {
   const uint4* q = reinterpret_cast<const uint4*>(p);
@@ -229,45 +238,44 @@ __device__ __forceinline__ void load_global_const(u32 (&r)[8], const u32* p) {
   r[4] = y.x; r[5] = y.y; r[6] = y.z; r[7] = y.w;
 }
 
-// out = sum_j coef[j * stride] * s[j]  over j in [0, t)   (lazy Montgomery, < 2r)
+// out = sum_j coef[j * stride] * s[j]  over j in [0, t)   (lazy Montgomery, < 2r; < r when the state is kept canonical)
 __device__ __noinline__ void generic_dot(u32 (&out)[8], const u32 (*s)[8], const u32* coef, int stride, int t) {
   const u32 P2[8] = GCP_2P_LIMBS;
-  u32 total[8];
-#pragma unroll
-  for (int l = 0; l < 8; l++) total[l] = 0;
+  const u32 P1[8] = GCP_P_LIMBS;
+  Wide w;
+  wide_zero(w);
 #pragma unroll 1
-  for (int j0 = 0; j0 < t; j0 += LAZY_DOT_MAX) {
-    Wide w;
-    wide_zero(w);
-    int j1 = min(t, j0 + LAZY_DOT_MAX);
-#pragma unroll 1
-    for (int j = j0; j < j1; j++) {
-      u32 c[8], x[8];
-      load_global_const(c, coef + (size_t)j * stride * 8);
+  for (int j = 0; j < t; j++) {
+    u32 c[8], x[8];
+    load_global_const(c, coef + (size_t)j * stride * 8);
 #pragma unroll
-      for (int l = 0; l < 8; l++) x[l] = s[j][l];
-      wide_mac(w, x, c);
-    }
-    u32 part[8];
-    wide_redc(w, part);
-    cond_sub(part, P2);
-    fr_add(total, total, part);
+    for (int l = 0; l < 8; l++) x[l] = s[j][l];
+    wide_mac(w, x, c);
   }
+  u32 total[8];
+  wide_redc(w, total);
+  cond_sub(total, P2);
+  cond_sub(total, P2);
+  if (generic_state_canonical(t)) cond_sub(total, P1);
 #pragma unroll
   for (int l = 0; l < 8; l++) out[l] = total[l];
 }
 
-__device__ __noinline__ void generic_sigma_ark(u32 (&x)[8], const u32* c) {
+__device__ __noinline__ void generic_sigma_ark(u32 (&x)[8], const u32* c, bool canonical) {
+  const u32 P1[8] = GCP_P_LIMBS;
   u32 k[8];
   sigma(x);
   load_global_const(k, c);
   fr_add(x, x, k);
+  if (canonical) cond_sub(x, P1);
 }
 
 // s[0..t) in, lazy Montgomery, s[0] = 0.  Result in out.  poseidon.go:116-183.
 __device__ __forceinline__ void poseidon_permute_generic(u32 (*s)[8], u32 (*n)[8], u32 (&out)[8],
                                                          const PoseidonTable& tab) {
   const int t = tab.t, rp = tab.RP;
+  const bool canonical = generic_state_canonical(t);
+  const u32 P1[8] = GCP_P_LIMBS;
   u32 x[8], k[8];
 #pragma unroll 1
   for (int j = 0; j < t; j++) {
@@ -285,7 +293,7 @@ __device__ __forceinline__ void poseidon_permute_generic(u32 (*s)[8], u32 (*n)[8
       for (int r = 0; r < rp; r++) {
 #pragma unroll
         for (int l = 0; l < 8; l++) x[l] = s[0][l];
-        generic_sigma_ark(x, tab.C + (5 * t + r) * 8);
+        generic_sigma_ark(x, tab.C + (5 * t + r) * 8, canonical);
 #pragma unroll
         for (int l = 0; l < 8; l++) s[0][l] = x[l];
         const u32* srow = tab.S + (size_t)(2 * t - 1) * r * 8;
@@ -299,6 +307,7 @@ __device__ __forceinline__ void poseidon_permute_generic(u32 (*s)[8], u32 (*n)[8
 #pragma unroll
           for (int l = 0; l < 8; l++) y[l] = s[kk][l];
           fr_add(y, y, prod);
+          if (canonical) cond_sub(y, P1);
 #pragma unroll
           for (int l = 0; l < 8; l++) s[kk][l] = y[l];
         }
@@ -312,10 +321,12 @@ __device__ __forceinline__ void poseidon_permute_generic(u32 (*s)[8], u32 (*n)[8
     for (int j = 0; j < t; j++) {
 #pragma unroll
       for (int l = 0; l < 8; l++) x[l] = s[j][l];
-      if (fr < 7)
-        generic_sigma_ark(x, crow + j * 8);
-      else
+      if (fr < 7) {
+        generic_sigma_ark(x, crow + j * 8, canonical);
+      } else {
         sigma(x);
+        if (canonical) cond_sub(x, P1);
+      }
 #pragma unroll
       for (int l = 0; l < 8; l++) s[j][l] = x[l];
     }

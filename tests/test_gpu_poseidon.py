@@ -147,6 +147,27 @@ def test_edge_value_patterns_against_c_oracle(engine):
         assert ints(out[i:i + 1])[0] == opos.hash(list(pairs[i]))
 
 
+@pytest.mark.parametrize("arity", [5, 10, 11, 12, 16])
+def test_wide_arities_edge_patterns_and_bulk_against_c_oracle(engine, arity):
+    """The generic kernel takes a whole matrix row (up to 17 products) into one Montgomery reduction; t = 11 is the
+    widest row on a non-canonical (< 2r) state, t = 12..17 keep the state canonical (poseidon.cuh bound note).
+    Carry-hostile inputs (r-1, all-ones limbs, single bits) in every position plus 4096 random rows, all compared."""
+    from oracle import cport
+
+    vals = _edge_values()
+    rng = random.Random(arity)
+    rows = [[vals[(i * 13 + j * 7) % len(vals)] for j in range(arity)] for i in range(len(vals))]
+    rows += [[R - 1] * arity, [R - 2] * arity, [0] * arity, [1] * arity, [(1 << 253) - 1] * arity]
+    rows += [[rng.randrange(R) for _ in range(arity)] for _ in range(4096)]
+    a = elems([x for row in rows for x in row]).reshape(len(rows), arity, 32)
+    out, st = engine.poseidon_hash(a)
+    want, wst = cport.poseidon_hash(a, threads=cport.default_threads())
+    assert not st.any() and not wst.any()
+    assert (out == want).all()
+    for i in (0, len(vals), len(vals) + 1):
+        assert ints(out[i:i + 1])[0] == opos.hash(rows[i])
+
+
 def test_full_compare_2pow18_hashes(engine):
     """Every one of 2^18 random two-input hashes against the C oracle (not a sample)."""
     from oracle import cport
