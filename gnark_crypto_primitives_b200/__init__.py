@@ -5,10 +5,10 @@ The product is the CUDA library behind include/gcp_b200.h; this package is its t
 Importing it never touches oracle/ and never computes on the CPU.
 """
 from ._lib import (EngineError, FMT_CANONICAL, FMT_MONTGOMERY, STATUS_ASSERTION, STATUS_KEY_RANGE, STATUS_NONCANONICAL,
-                   STATUS_NOT_BOOLEAN, STATUS_OFF_CURVE, STATUS_OK, STATUS_ZERO_DENOM)
-from .engine import Engine, R, elems_to_ints, ints_to_elems
+                   STATUS_MALFORMED, STATUS_NOT_BOOLEAN, STATUS_OFF_CURVE, STATUS_OK, STATUS_ZERO_DENOM)
+from .engine import Engine, Group, R, elems_to_ints, ints_to_elems
 
 __all__ = [
-    "Engine", "EngineError", "R", "ints_to_elems", "elems_to_ints", "FMT_CANONICAL", "FMT_MONTGOMERY", "STATUS_OK",
-    "STATUS_NONCANONICAL", "STATUS_KEY_RANGE", "STATUS_NOT_BOOLEAN", "STATUS_OFF_CURVE", "STATUS_ZERO_DENOM", "STATUS_ASSERTION",
+    "Engine", "Group", "EngineError", "R", "ints_to_elems", "elems_to_ints", "FMT_CANONICAL", "FMT_MONTGOMERY", "STATUS_OK",
+    "STATUS_NONCANONICAL", "STATUS_KEY_RANGE", "STATUS_NOT_BOOLEAN", "STATUS_OFF_CURVE", "STATUS_ZERO_DENOM", "STATUS_ASSERTION", "STATUS_MALFORMED",
 ]

@@ -25,6 +25,7 @@ STATUS_NOT_BOOLEAN = 3
 STATUS_OFF_CURVE = 4
 STATUS_ZERO_DENOM = 5
 STATUS_ASSERTION = 6
+STATUS_MALFORMED = 7
 
 _u8p = POINTER(c_uint8)
 
@@ -53,6 +54,23 @@ SIGNATURES = {
                                       c_int]),
     "gcp_smt_unpack_siblings_dev": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p,
                                             c_int, c_void_p]),
+    "gcp_group_create": (c_int, [POINTER(c_int), c_int, c_char_p, POINTER(c_void_p)]),
+    "gcp_group_destroy": (None, [c_void_p]),
+    "gcp_group_last_error": (c_char_p, [c_void_p]),
+    "gcp_group_size": (c_int, [c_void_p]),
+    "gcp_group_ctx": (c_void_p, [c_void_p, c_int]),
+    "gcp_group_uses_nccl": (c_int, [c_void_p]),
+    "gcp_group_poseidon_hash": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_int]),
+    "gcp_group_smt_verify": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    "gcp_group_smt_verify_packed": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                            c_void_p, c_void_p, c_int]),
+    "gcp_group_elgamal_encrypt": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p,
+                                          c_int]),
+    "gcp_group_elgamal_tally": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_int]),
+    "gcp_group_elgamal_encrypt_tally": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p,
+                                                c_void_p, c_int]),
     "gcp_smt_scan_dev": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gcp_smt_verify_inclusion": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                          c_void_p, c_void_p, c_void_p, c_int]),

@@ -33,7 +33,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     nvcc = _nvcc()
     headers = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [PKG.parent / "include" / "gcp_b200.h"]
     objs = []
-    for name in ("kernels", "capi"):
+    for name in ("kernels", "capi", "group"):
         src = CSRC / f"{name}.cu"
         obj = CSRC / f"{name}.o"
         if force or _stale(obj, [src] + headers):

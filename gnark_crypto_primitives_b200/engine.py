@@ -480,3 +480,139 @@ class Engine:
     def mimc7_hash_dev(self, d_in, length, n, d_out, d_status, fmt=FMT_CANONICAL, stream=None):
         self._check(self._lib.gcp_mimc7_hash_dev(self._h, _dptr(d_in), length, n, _dptr(d_out), _dptr(d_status), fmt,
                                                  self._stream(stream)))
+
+
+class Group:
+    """Several GPUs of one box behind one handle (gcp_group_*, include/gcp_b200.h): the single-process form a Go host
+    uses.  Batches are sharded by contiguous index range, one host thread per device, no data-path collective; the
+    tallies all-gather their partial ciphertexts with NCCL.  Everything without a group form goes through
+    `group.engine(i)`-style per-device contexts on the C side (gcp_group_ctx)."""
+
+    def __init__(self, devices, constants_path: str = None):
+        self._lib = _lib.load()
+        devs = [int(d) for d in devices]
+        arr = (ctypes.c_int * len(devs))(*devs)
+        h = c_void_p()
+        rc = self._lib.gcp_group_create(arr, len(devs), constants_path.encode() if constants_path else None,
+                                        ctypes.byref(h))
+        if rc != 0:
+            msg = self._lib.gcp_group_last_error(None)
+            raise EngineError(rc, msg.decode() if msg else "gcp_group_create failed")
+        self._h = h
+        self.devices = devs
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gcp_group_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self._lib.gcp_group_last_error(self._h)
+            raise EngineError(rc, msg.decode() if msg else "")
+
+    @property
+    def size(self) -> int:
+        return int(self._lib.gcp_group_size(self._h))
+
+    @property
+    def uses_nccl(self) -> bool:
+        return bool(self._lib.gcp_group_uses_nccl(self._h))
+
+    def launch_counts(self):
+        return [int(self._lib.gcp_ctx_launch_count(c_void_p(self._lib.gcp_group_ctx(self._h, i))))
+                for i in range(self.size)]
+
+    def poseidon_hash(self, inputs, fmt=FMT_CANONICAL):
+        a = _as_elems(inputs, name="inputs")
+        if a.ndim != 3:
+            raise ValueError("inputs must have shape (n, arity, 32)")
+        n, arity = a.shape[0], a.shape[1]
+        out = np.empty((n, 32), dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.gcp_group_poseidon_hash(self._h, _ptr(a), arity, n, _ptr(out), _ptr(status), fmt))
+        return out, status
+
+    def smt_verify(self, roots, siblings, keys, values, old_keys=None, old_values=None, is_old0=None, fnc=None,
+                   enabled=None, want_roots=False, fmt=FMT_CANONICAL):
+        sib = _as_elems(siblings, name="siblings")
+        if sib.ndim != 3:
+            raise ValueError("siblings must have shape (n, n_levels, 32)")
+        n, n_levels = sib.shape[0], sib.shape[1]
+        r = _as_elems(roots, name="roots")
+        shared = 1 if r.size == 32 and n != 1 else 0
+        k, v = _as_elems(keys, n, "keys"), _as_elems(values, n, "values")
+        ok = _as_elems(old_keys, n, "old_keys") if old_keys is not None else None
+        ov = _as_elems(old_values, n, "old_values") if old_values is not None else None
+        i0, fn, en = _u8(is_old0, n, "is_old0"), _u8(fnc, n, "fnc"), _u8(enabled, n, "enabled")
+        flags = np.empty(n, dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        oroots = np.empty((n, 32), dtype=np.uint8) if want_roots else None
+        self._check(self._lib.gcp_group_smt_verify(self._h, n_levels, n, _ptr(r), shared, _ptr(sib), _ptr(ok), _ptr(ov),
+                                                   _ptr(i0), _ptr(k), _ptr(v), _ptr(fn), _ptr(en), _ptr(flags),
+                                                   _ptr(status), _ptr(oroots), fmt))
+        return (flags, status, oroots) if want_roots else (flags, status)
+
+    def smt_verify_packed(self, roots, packed, n_levels, keys, values, want_roots=False, fmt=FMT_CANONICAL):
+        lens = np.fromiter((len(b) for b in packed), dtype=np.uint64, count=len(packed))
+        offs = np.zeros(len(packed) + 1, dtype=np.uint64)
+        np.cumsum(lens, out=offs[1:])
+        blob = np.frombuffer(b"".join(bytes(b) for b in packed) or b"\0", dtype=np.uint8)
+        n = len(packed)
+        r = _as_elems(roots, name="roots")
+        shared = 1 if r.size == 32 and n != 1 else 0
+        k, v = _as_elems(keys, n, "keys"), _as_elems(values, n, "values")
+        flags = np.empty(n, dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        oroots = np.empty((n, 32), dtype=np.uint8) if want_roots else None
+        self._check(self._lib.gcp_group_smt_verify_packed(self._h, int(n_levels), n, _ptr(r), shared, _ptr(blob),
+                                                          _ptr(offs), None, None, None, _ptr(k), _ptr(v), None, None,
+                                                          _ptr(flags), _ptr(status), _ptr(oroots), fmt))
+        return (flags, status, oroots) if want_roots else (flags, status)
+
+    def elgamal_encrypt(self, pub_key, k, m, fmt=FMT_CANONICAL):
+        kk = _as_elems(k, name="k").reshape(-1, 32)
+        n = kk.shape[0]
+        mm = _as_elems(m, n, "m").reshape(-1, 32)
+        pk = _as_elems(pub_key, name="pub_key")
+        per_item = 0 if pk.size == 64 and (n != 1 or pk.ndim <= 2) else 1
+        out = np.empty((n, 4, 32), dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.gcp_group_elgamal_encrypt(self._h, _ptr(pk), per_item, _ptr(kk), _ptr(mm), n, _ptr(out),
+                                                        _ptr(status), fmt))
+        return out, status
+
+    def elgamal_tally(self, ct, fmt=FMT_CANONICAL):
+        c = _as_elems(ct, name="ct")
+        if c.ndim != 4 or c.shape[2] != 4:
+            raise ValueError("ct must have shape (n_ballots, n_fields, 4, 32)")
+        n_ballots, n_fields = c.shape[0], c.shape[1]
+        out = np.empty((n_fields, 4, 32), dtype=np.uint8)
+        status = np.empty(n_fields, dtype=np.uint8)
+        self._check(self._lib.gcp_group_elgamal_tally(self._h, _ptr(c), n_ballots, n_fields, _ptr(out), _ptr(status), fmt))
+        return out, status
+
+    def elgamal_encrypt_tally(self, pub_key, k, m, fmt=FMT_CANONICAL):
+        kk = _as_elems(k, name="k")
+        if kk.ndim != 3:
+            raise ValueError("k must have shape (n_ballots, n_fields, 32)")
+        n_ballots, n_fields = kk.shape[0], kk.shape[1]
+        mm = _as_elems(m, n_ballots * n_fields, "m")
+        pk = _as_elems(pub_key, 2, "pub_key")
+        out = np.empty((n_fields, 4, 32), dtype=np.uint8)
+        status = np.empty(n_fields, dtype=np.uint8)
+        self._check(self._lib.gcp_group_elgamal_encrypt_tally(self._h, _ptr(pk), _ptr(kk), _ptr(mm), n_ballots, n_fields,
+                                                              _ptr(out), _ptr(status), fmt))
+        return out, status

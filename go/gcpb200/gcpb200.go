@@ -208,3 +208,65 @@ func (e *Engine) DeriveAddresses(pub []byte) (addr []byte, err error) {
 	err = e.err(C.gcp_keccak_address(e.ctx, unsafe.Pointer(bytePtr(pub)), C.size_t(n), unsafe.Pointer(bytePtr(addr))))
 	return
 }
+
+// Group drives several GPUs of one box from this process (gcp_group_*): batches are sharded by index range, one host
+// thread per device inside the C call; the tallies all-gather their partial ciphertexts with NCCL.
+type Group struct{ grp *C.gcp_group }
+
+func NewGroup(devices []int) (*Group, error) {
+	d := make([]C.int, len(devices))
+	for i, v := range devices {
+		d[i] = C.int(v)
+	}
+	var g *C.gcp_group
+	var p *C.int
+	if len(d) > 0 {
+		p = &d[0]
+	}
+	if rc := C.gcp_group_create(p, C.int(len(d)), nil, &g); rc != 0 {
+		return nil, fmt.Errorf("gcp_b200: %s (code %d)", C.GoString(C.gcp_group_last_error(nil)), int(rc))
+	}
+	return &Group{grp: g}, nil
+}
+
+func (g *Group) Close()    { C.gcp_group_destroy(g.grp) }
+func (g *Group) Size() int { return int(C.gcp_group_size(g.grp)) }
+
+func (g *Group) err(rc C.int) error {
+	if rc == 0 {
+		return nil
+	}
+	return fmt.Errorf("gcp_b200: %s (code %d)", C.GoString(C.gcp_group_last_error(g.grp)), int(rc))
+}
+
+// BatchVerify is Engine.BatchVerify over all GPUs of the group.
+func (g *Group) BatchVerify(p *Proofs) (flags, status []byte, err error) {
+	n := len(p.Keys)
+	flags, status = make([]byte, n), make([]byte, n)
+	shared := 0
+	if len(p.Roots) == 1 && n != 1 {
+		shared = 1
+	}
+	err = g.err(C.gcp_group_smt_verify(g.grp, C.int(p.Levels), C.size_t(n), elemPtr(p.Roots), C.int(shared),
+		elemPtr(p.Siblings), elemPtr(p.OldKeys), elemPtr(p.OldValues), bytePtr(p.IsOld0), elemPtr(p.Keys), elemPtr(p.Values),
+		bytePtr(p.Fnc), bytePtr(p.Enabled), bytePtr(flags), bytePtr(status), nil, C.GCP_FMT_MONTGOMERY))
+	return
+}
+
+// Tally folds n_ballots x nFields ciphertexts over all GPUs (partial sums all-gathered with NCCL).
+func (g *Group) Tally(ct []fr.Element, nFields int) (out []fr.Element, status []byte, err error) {
+	nBallots := len(ct) / (4 * nFields)
+	out, status = make([]fr.Element, 4*nFields), make([]byte, nFields)
+	err = g.err(C.gcp_group_elgamal_tally(g.grp, elemPtr(ct), C.size_t(nBallots), C.int(nFields), elemPtr(out),
+		bytePtr(status), C.GCP_FMT_MONTGOMERY))
+	return
+}
+
+// EncryptTally is the fused Encrypt + tally over all GPUs.
+func (g *Group) EncryptTally(pubKey [2]fr.Element, k, m []fr.Element, nFields int) (out []fr.Element, status []byte, err error) {
+	nBallots := len(k) / nFields
+	out, status = make([]fr.Element, 4*nFields), make([]byte, nFields)
+	err = g.err(C.gcp_group_elgamal_encrypt_tally(g.grp, unsafe.Pointer(&pubKey[0]), elemPtr(k), elemPtr(m),
+		C.size_t(nBallots), C.int(nFields), elemPtr(out), bytePtr(status), C.GCP_FMT_MONTGOMERY))
+	return
+}

@@ -225,6 +225,41 @@ int gcp_ballot_batch_dev(gcp_ctx* ctx, int n_levels, size_t n_voters, const void
 int gcp_keccak_address(gcp_ctx* ctx, const void* pub_xy_be, size_t n, void* out_addr);
 int gcp_keccak_address_dev(gcp_ctx* ctx, const void* d_pub_xy_be, size_t n, void* d_out_addr, void* stream);
 
+/* ---- several GPUs of one box behind one handle (single-process callers: the Go host) -------------------------- */
+/* The reference has no multi-device code; its work units are independent (every gadget call touches only its own
+ * inputs), so a group shards each batch by contiguous index range [n*i/g, n*(i+1)/g) over its g devices, one host
+ * thread and one context per device, with no data-path collective.  The one exchange step is the ElGamal tally:
+ * every device folds its slice to n_fields partial ciphertexts, the partials (n_fields * 128 bytes per device) are
+ * all-gathered as bytes with ncclAllGather over NVLink / NVSwitch, and every device folds the gathered array; the
+ * result is bit-identical for any device count.  NCCL is bound at run time (libnccl.so.2); a group of more than one
+ * device cannot be created without it.  Calls on one group are serialised; per-item results land at the caller's
+ * global index. */
+typedef struct gcp_group gcp_group;
+int gcp_group_create(const int* devices, int n_devices, const char* constants_path, gcp_group** out);
+void gcp_group_destroy(gcp_group* g);
+const char* gcp_group_last_error(const gcp_group* g); /* g may be NULL: error of the last failed gcp_group_create */
+int gcp_group_size(const gcp_group* g);
+gcp_ctx* gcp_group_ctx(gcp_group* g, int i); /* device i's context, for every entry point that has no group form */
+int gcp_group_uses_nccl(const gcp_group* g); /* 1 when the partial tallies travel through ncclAllGather (g > 1) */
+/* sharded forms of gcp_poseidon_hash, gcp_smt_verify, gcp_smt_verify_packed, gcp_elgamal_encrypt (same arguments) */
+int gcp_group_poseidon_hash(gcp_group* g, const void* in, int arity, size_t n, void* out, uint8_t* status, int fmt);
+int gcp_group_smt_verify(gcp_group* g, int n_levels, size_t n, const void* roots, int shared_root, const void* siblings,
+                         const void* old_keys, const void* old_values, const uint8_t* is_old0, const void* keys,
+                         const void* values, const uint8_t* fnc, const uint8_t* enabled, uint8_t* out_flags,
+                         uint8_t* out_status, void* out_roots, int fmt);
+int gcp_group_smt_verify_packed(gcp_group* g, int n_levels, size_t n, const void* roots, int shared_root,
+                                const uint8_t* packed, const uint64_t* offsets, const void* old_keys,
+                                const void* old_values, const uint8_t* is_old0, const void* keys, const void* values,
+                                const uint8_t* fnc, const uint8_t* enabled, uint8_t* out_flags, uint8_t* out_status,
+                                void* out_roots, int fmt);
+int gcp_group_elgamal_encrypt(gcp_group* g, const void* pub_key, int pk_per_item, const void* k, const void* m, size_t n,
+                              void* out_ct, uint8_t* status, int fmt);
+/* sharded tally / fused encrypt + tally with the all-gather of the partial ciphertexts (arguments as the ctx forms) */
+int gcp_group_elgamal_tally(gcp_group* g, const void* ct, size_t n_ballots, int n_fields, void* out, uint8_t* status,
+                            int fmt);
+int gcp_group_elgamal_encrypt_tally(gcp_group* g, const void* pub_key, const void* k, const void* m, size_t n_ballots,
+                                    int n_fields, void* out, uint8_t* status, int fmt);
+
 #ifdef __cplusplus
 }
 #endif
