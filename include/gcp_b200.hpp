@@ -162,4 +162,40 @@ inline Batch Tally(const Engine& e, const uint8_t* ct, size_t n_ballots, int n_f
 }
 }  // namespace elgamal
 
+// Several GPUs of one box behind one handle (gcp_group_*): index-range shards, NCCL all-gather of the partial tallies.
+class Group {
+ public:
+  explicit Group(const std::vector<int>& devices, const char* constants_path = nullptr) {
+    int rc = gcp_group_create(devices.data(), (int)devices.size(), constants_path, &grp_);
+    if (rc != GCP_OK) throw Error(rc, gcp_group_last_error(nullptr));
+  }
+  ~Group() { gcp_group_destroy(grp_); }
+  Group(const Group&) = delete;
+  Group& operator=(const Group&) = delete;
+  gcp_group* raw() const { return grp_; }
+  int size() const { return gcp_group_size(grp_); }
+  void check(int rc) const {
+    if (rc != GCP_OK) throw Error(rc, gcp_group_last_error(grp_));
+  }
+  Batch InclusionVerifier(int n_levels, size_t n, const uint8_t* roots, bool shared_root, const uint8_t* siblings,
+                          const uint8_t* keys, const uint8_t* values, int fmt = GCP_FMT_CANONICAL) const {
+    Batch b;
+    b.flags.resize(n);
+    b.status.resize(n);
+    check(gcp_group_smt_verify(grp_, n_levels, n, roots, shared_root, siblings, nullptr, nullptr, nullptr, keys, values,
+                               nullptr, nullptr, b.flags.data(), b.status.data(), nullptr, fmt));
+    return b;
+  }
+  Batch Tally(const uint8_t* ct, size_t n_ballots, int n_fields, int fmt = GCP_FMT_CANONICAL) const {
+    Batch b;
+    b.values.resize((size_t)n_fields * 128);
+    b.status.resize(n_fields);
+    check(gcp_group_elgamal_tally(grp_, ct, n_ballots, n_fields, b.values.data(), b.status.data(), fmt));
+    return b;
+  }
+
+ private:
+  gcp_group* grp_ = nullptr;
+};
+
 }  // namespace gcp

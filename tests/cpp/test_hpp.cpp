@@ -63,6 +63,12 @@ int main() {
   } catch (const gcp::Error& e) {
     if (std::string(e.what()).find("bad inputs provided") == std::string::npos) return 5;
   }
+  {  // the same proof through a one-device group
+    gcp::Group grp({0});
+    put(key, 7);
+    gcp::Batch gv = grp.InclusionVerifier(3, 1, root.values.data(), false, sib, key, val);
+    if (grp.size() != 1 || gv.flags[0] != 1 || gv.status[0] != 0) return 8;
+  }
   printf("cpp mirror ok\n");
   return 0;
 }
