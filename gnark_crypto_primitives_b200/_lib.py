@@ -32,6 +32,8 @@ _u8p = POINTER(c_uint8)
 # name -> (restype, argtypes).  Must list every symbol include/gcp_b200.h declares (tests check this).
 SIGNATURES = {
     "gcp_device_count": (c_int, []),
+    "gcp_host_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
+    "gcp_host_free": (None, [c_void_p]),
     "gcp_ctx_create": (c_int, [c_int, c_char_p, POINTER(c_void_p)]),
     "gcp_ctx_destroy": (None, [c_void_p]),
     "gcp_last_error": (c_char_p, [c_void_p]),

@@ -125,6 +125,22 @@ void gcp_ctx_destroy(gcp_ctx* ctx) {
   delete ctx;
 }
 
+int gcp_host_alloc(size_t bytes, void** out) {
+  if (!out) return GCP_ERR_BAD_ARG;
+  *out = nullptr;
+  if (gcp_device_count() <= 0) return GCP_ERR_NO_DEVICE;
+  if (cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    *out = nullptr;
+    return GCP_ERR_ALLOC;
+  }
+  return GCP_OK;
+}
+
+void gcp_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 int gcp_ctx_create(int device, const char* constants_path, gcp_ctx** out) {
   if (!out) {
     g_create_error = "out is NULL";
@@ -530,6 +546,9 @@ static int smt_verify_host(gcp_ctx* ctx, int n_levels, size_t n, const void* roo
     if (!d_shared_root) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
     CU(cudaMemcpy(d_shared_root, roots, 32, cudaMemcpyHostToDevice), "H2D root");
   }
+  // (A ramped schedule - quarter wave, one wave, then full chunks, to shorten the one copy no kernel hides - was
+  // measured: +1 % at 2^20 dense proofs, -4 % at 2^19 and -10 % on census-like batches, where partial waves cost more
+  // than the shorter head saves.  One chunk size stays.)
   size_t k = 0;
   for (size_t off = 0; off < n && rc == GCP_OK; off += chunk, k++) {
     size_t m = std::min(chunk, n - off);

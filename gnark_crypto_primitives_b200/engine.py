@@ -66,6 +66,32 @@ def _u8(arr, n, name):
     return a
 
 
+class PinnedBuffer:
+    """Page-locked host memory from gcp_host_alloc, viewed as a numpy uint8 array (`.array`); free with close()."""
+
+    def __init__(self, nbytes: int):
+        self._lib = _lib.load()
+        p = c_void_p()
+        rc = self._lib.gcp_host_alloc(int(nbytes), ctypes.byref(p))
+        if rc != 0:
+            raise EngineError(rc, "gcp_host_alloc failed")
+        self._p = p
+        self.array = np.ctypeslib.as_array((ctypes.c_uint8 * int(nbytes)).from_address(p.value)) if nbytes else \
+            np.zeros(0, np.uint8)
+
+    def close(self):
+        if getattr(self, "_p", None):
+            self.array = None
+            self._lib.gcp_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Engine:
     def __init__(self, device: int = 0, constants_path: str = None):
         self._lib = _lib.load()

@@ -209,6 +209,18 @@ func (e *Engine) DeriveAddresses(pub []byte) (addr []byte, err error) {
 	return
 }
 
+// PinnedElements allocates n field elements in page-locked host memory (gcp_host_alloc): host-buffer calls copy from
+// it at full PCIe rate and overlap with the kernels.  Release with FreePinned(&s[0]).
+func PinnedElements(n int) ([]fr.Element, error) {
+	var p unsafe.Pointer
+	if rc := C.gcp_host_alloc(C.size_t(n*32), &p); rc != 0 {
+		return nil, fmt.Errorf("gcp_host_alloc failed (code %d)", int(rc))
+	}
+	return unsafe.Slice((*fr.Element)(p), n), nil
+}
+
+func FreePinned(first *fr.Element) { C.gcp_host_free(unsafe.Pointer(first)) }
+
 // Group drives several GPUs of one box from this process (gcp_group_*): batches are sharded by index range, one host
 // thread per device inside the C call; the tallies all-gather their partial ciphertexts with NCCL.
 type Group struct{ grp *C.gcp_group }

@@ -65,6 +65,13 @@ int gcp_ctx_device(const gcp_ctx* ctx);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 uint64_t gcp_ctx_launch_count(const gcp_ctx* ctx);
 
+/* Page-locked host memory for the caller's flat arrays (cudaHostAlloc, portable across the devices of a group).
+ * The host-buffer entry points accept any host pointer; from pinned memory their chunked copies run at full PCIe
+ * rate and overlap the kernels (bench.py's e2e figure), from pageable memory (a Go heap slice) every copy is staged
+ * by the driver.  A Go caller wraps the pointer with unsafe.Slice.  Free with gcp_host_free. */
+int gcp_host_alloc(size_t bytes, void** out);
+void gcp_host_free(void* p);
+
 /* Measures this GPU's integer-multiply pipe: sustained 32x32+64 multiply-adds per second (IMAD.WIDE.U32 carry
  * chains, the multiplier's own row primitive, no memory traffic).  bench.py uses it as the roofline denominator. */
 int gcp_probe_imad_wide(gcp_ctx* ctx, double* wide_mul_per_s);

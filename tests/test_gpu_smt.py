@@ -243,3 +243,27 @@ def test_scan_kernel_reports_path_length_and_flags(engine):
         torch.cuda.synchronize()
         assert lidx.cpu().tolist() == want_lidx, n_levels
         assert info.cpu().tolist() == want_info, n_levels
+
+
+def test_pinned_host_buffers_give_the_same_results(engine):
+    """gcp_host_alloc: the caller's arrays in page-locked memory (what bench.py's e2e uses through torch)."""
+    import gnark_crypto_primitives_b200 as g
+
+    rng = random.Random(404)
+    n_levels, n = 160, 96
+    items = [census_proof(rng, n_levels) for _ in range(n)]
+    items[7] = (items[7][0] ^ 1,) + items[7][1:]
+    sib = elems([s for it in items for s in it[1]]).reshape(n, n_levels, 32)
+    roots, keys, vals = elems(it[0] for it in items), elems(it[2] for it in items), elems(it[3] for it in items)
+    want = engine.smt_verify_inclusion(roots, sib, keys, vals)
+    buf = g.PinnedBuffer(sib.nbytes)
+    try:
+        pinned = buf.array.reshape(sib.shape)
+        pinned[...] = sib
+        got = engine.smt_verify_inclusion(roots, pinned, keys, vals)
+    finally:
+        buf.close()
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    assert int(want[0][7]) == 0 and int(want[0].sum()) == n - 1
+    empty = g.PinnedBuffer(0)
+    empty.close()

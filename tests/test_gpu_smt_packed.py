@@ -61,7 +61,7 @@ def test_packed_equals_dense_on_synthetic_batches(engine, fmt):
     element formats (siblings are canonical on the wire in either)."""
     rng = random.Random(4242 + fmt)
     n_levels = 160
-    n = 3000
+    n = 1200
     conv = (lambda v: v * RMONT % R) if fmt == FMT_MONTGOMERY else (lambda v: v)
     roots, sibs, keys, vals, packed = [], [], [], [], []
     for i in range(n):
