@@ -714,16 +714,19 @@ int gcp_smt_process_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_old_
   return GCP_OK;
 }
 
-int gcp_smt_process(gcp_ctx* ctx, int n_levels, size_t n, const void* old_roots, const void* siblings,
-                    const void* old_keys, const void* old_values, const uint8_t* is_old0, const void* new_keys,
-                    const void* new_values, const uint8_t* fnc0, const uint8_t* fnc1, void* new_roots, uint8_t* status,
-                    int fmt) {
+// Host-buffer processor: dense sibling rows, or (siblings == NULL) arbo packed proofs expanded on the device.
+static int smt_process_host(gcp_ctx* ctx, int n_levels, size_t n, const void* old_roots, const void* siblings,
+                            const uint8_t* packed, const uint64_t* offsets, const void* old_keys,
+                            const void* old_values, const uint8_t* is_old0, const void* new_keys, const void* new_values,
+                            const uint8_t* fnc0, const uint8_t* fnc1, void* new_roots, uint8_t* status, int fmt) {
   if (!ctx) return GCP_ERR_BAD_ARG;
+  const bool is_packed = siblings == nullptr;
   {
     std::lock_guard<std::mutex> lk(ctx->mu);
-    int rc = smt_process_check(ctx, n_levels, n, old_roots, siblings, old_keys, old_values, is_old0, new_keys, new_values,
-                               fnc0, fnc1, new_roots, status, fmt);
+    int rc = smt_process_check(ctx, n_levels, n, old_roots, is_packed ? (const void*)packed : siblings, old_keys,
+                               old_values, is_old0, new_keys, new_values, fnc0, fnc1, new_roots, status, fmt);
     if (rc != GCP_OK || n == 0) return rc;
+    if (is_packed && !offsets) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
   }
   const size_t sib_bytes = (size_t)n_levels * 32;
   size_t chunk = std::max<size_t>(1, std::min<size_t>(n, ((size_t)256 << 20) / sib_bytes));
@@ -731,6 +734,7 @@ int gcp_smt_process(gcp_ctx* ctx, int n_levels, size_t n, const void* old_roots,
     size_t m = std::min(chunk, n - off);
     void *d_sib, *d_e[5];
     uint8_t* d_b[4];
+    uint8_t* d_bad = nullptr;
     {
       std::lock_guard<std::mutex> lk(ctx->mu);
       CU(cudaSetDevice(ctx->device), "cudaSetDevice");
@@ -743,7 +747,21 @@ int gcp_smt_process(gcp_ctx* ctx, int n_levels, size_t n, const void* old_roots,
       cudaStream_t st = ctx->stream[0];
       const void* src_e[5] = {old_roots, old_keys, old_values, new_keys, new_values};
       const uint8_t* src_b[3] = {is_old0, fnc0, fnc1};
-      CU(cudaMemcpyAsync(d_sib, (const char*)siblings + off * sib_bytes, m * sib_bytes, cudaMemcpyHostToDevice, st), "H2D");
+      if (is_packed) {
+        const uint64_t pbeg = offsets[off], pend = offsets[off + m];
+        if (pend < pbeg) return ctx->fail(GCP_ERR_BAD_ARG, "packed offsets must be non-decreasing");
+        const size_t pbytes = (size_t)(pend - pbeg);
+        uint8_t* d_packed = (uint8_t*)ctx->buf(80, pbytes + 4);
+        uint64_t* d_off = (uint64_t*)ctx->buf(81, (m + 1) * 8);
+        d_bad = (uint8_t*)ctx->buf(82, m);
+        if (!d_packed || !d_off || !d_bad) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+        if (pbytes) CU(cudaMemcpyAsync(d_packed, packed + pbeg, pbytes, cudaMemcpyHostToDevice, st), "H2D");
+        CU(cudaMemcpyAsync(d_off, offsets + off, (m + 1) * 8, cudaMemcpyHostToDevice, st), "H2D");
+        CU(launch_smt_unpack(d_packed, d_off, pbeg, pbytes, m, n_levels, (u32*)d_sib, d_bad, fmt, st), "smt unpack kernel");
+        ctx->launches++;
+      } else {
+        CU(cudaMemcpyAsync(d_sib, (const char*)siblings + off * sib_bytes, m * sib_bytes, cudaMemcpyHostToDevice, st), "H2D");
+      }
       for (int q = 0; q < 5; q++)
         CU(cudaMemcpyAsync(d_e[q], (const char*)src_e[q] + off * 32, m * 32, cudaMemcpyHostToDevice, st), "H2D");
       for (int q = 0; q < 3; q++) CU(cudaMemcpyAsync(d_b[q], src_b[q] + off, m, cudaMemcpyHostToDevice, st), "H2D");
@@ -752,11 +770,34 @@ int gcp_smt_process(gcp_ctx* ctx, int n_levels, size_t n, const void* old_roots,
                                  ctx->slot[16].p, d_b[3], fmt, ctx->stream[0]);
     if (rc != GCP_OK) return rc;
     std::lock_guard<std::mutex> lk(ctx->mu);
+    if (is_packed) {
+      // a proof arbo.UnpackSiblings rejects never reaches the gadget: status 7, new root 0 (flags: the status array twice)
+      CU(launch_smt_apply_bad(d_bad, m, d_b[3], d_b[3], (u32*)ctx->slot[16].p, ctx->stream[0]), "smt apply-bad kernel");
+      ctx->launches++;
+    }
     CU(cudaMemcpyAsync((char*)new_roots + off * 32, ctx->slot[16].p, m * 32, cudaMemcpyDeviceToHost, ctx->stream[0]), "D2H");
     CU(cudaMemcpyAsync(status + off, d_b[3], m, cudaMemcpyDeviceToHost, ctx->stream[0]), "D2H");
     CU(cudaStreamSynchronize(ctx->stream[0]), "stream sync");
   }
   return GCP_OK;
+}
+
+int gcp_smt_process(gcp_ctx* ctx, int n_levels, size_t n, const void* old_roots, const void* siblings,
+                    const void* old_keys, const void* old_values, const uint8_t* is_old0, const void* new_keys,
+                    const void* new_values, const uint8_t* fnc0, const uint8_t* fnc1, void* new_roots, uint8_t* status,
+                    int fmt) {
+  if (ctx && n && !siblings) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  return smt_process_host(ctx, n_levels, n, old_roots, siblings, nullptr, nullptr, old_keys, old_values, is_old0,
+                          new_keys, new_values, fnc0, fnc1, new_roots, status, fmt);
+}
+
+int gcp_smt_process_packed(gcp_ctx* ctx, int n_levels, size_t n, const void* old_roots, const uint8_t* packed,
+                           const uint64_t* offsets, const void* old_keys, const void* old_values, const uint8_t* is_old0,
+                           const void* new_keys, const void* new_values, const uint8_t* fnc0, const uint8_t* fnc1,
+                           void* new_roots, uint8_t* status, int fmt) {
+  if (ctx && n && (!packed || !offsets)) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  return smt_process_host(ctx, n_levels, n, old_roots, nullptr, packed, offsets, old_keys, old_values, is_old0, new_keys,
+                          new_values, fnc0, fnc1, new_roots, status, fmt);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -429,6 +429,25 @@ class Engine:
                                               _ptr(out), _ptr(status), fmt))
         return out, status
 
+    def smt_process_packed(self, old_roots, packed, n_levels, old_keys, old_values, is_old0, new_keys, new_values,
+                           fnc0, fnc1, fmt=FMT_CANONICAL):
+        """smt.Processor over arbo packed proofs (list of byte strings) -> (new_roots (n, 32), status (n,))."""
+        n = len(packed)
+        lens = np.fromiter((len(b) for b in packed), dtype=np.uint64, count=n)
+        offs = np.zeros(n + 1, dtype=np.uint64)
+        np.cumsum(lens, out=offs[1:])
+        blob = np.frombuffer(b"".join(bytes(b) for b in packed) or b"\0", dtype=np.uint8)
+        args = [_as_elems(x, n, nm) for x, nm in ((old_roots, "old_roots"), (old_keys, "old_keys"),
+                                                  (old_values, "old_values"), (new_keys, "new_keys"),
+                                                  (new_values, "new_values"))]
+        i0, f0, f1 = _u8(is_old0, n, "is_old0"), _u8(fnc0, n, "fnc0"), _u8(fnc1, n, "fnc1")
+        out = np.empty((n, 32), dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.gcp_smt_process_packed(self._h, int(n_levels), n, _ptr(args[0]), _ptr(blob), _ptr(offs),
+                                                     _ptr(args[1]), _ptr(args[2]), _ptr(i0), _ptr(args[3]), _ptr(args[4]),
+                                                     _ptr(f0), _ptr(f1), _ptr(out), _ptr(status), fmt))
+        return out, status
+
     # -- decryption checks, coordinate conversion ----------------------------------------------------
     def elgamal_assert_decrypt(self, ct, priv_keys, msgs, fmt=FMT_CANONICAL):
         """(*Ciphertext).AssertDecrypt (elgamal/ciphertext.go:50-67) -> (flags, status)."""

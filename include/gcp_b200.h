@@ -153,6 +153,12 @@ int gcp_smt_process(gcp_ctx* ctx, int n_levels, size_t n, const void* old_roots,
                     const void* old_keys, const void* old_values, const uint8_t* is_old0, const void* new_keys,
                     const void* new_values, const uint8_t* fnc0, const uint8_t* fnc1, void* new_roots, uint8_t* status,
                     int fmt);
+/* The same with arbo packed proofs (wrapper_arbo.go:166-179 unpacks them on the CPU): see gcp_smt_verify_packed for
+ * the wire format; a string arbo.UnpackSiblings would reject gets status GCP_STATUS_MALFORMED and new_root = 0. */
+int gcp_smt_process_packed(gcp_ctx* ctx, int n_levels, size_t n, const void* old_roots, const uint8_t* packed,
+                           const uint64_t* offsets, const void* old_keys, const void* old_values, const uint8_t* is_old0,
+                           const void* new_keys, const void* new_values, const uint8_t* fnc0, const uint8_t* fnc1,
+                           void* new_roots, uint8_t* status, int fmt);
 int gcp_smt_process_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_old_roots, const void* d_siblings,
                         const void* d_old_keys, const void* d_old_values, const uint8_t* d_is_old0,
                         const void* d_new_keys, const void* d_new_values, const uint8_t* d_fnc0, const uint8_t* d_fnc1,

@@ -100,3 +100,34 @@ def test_assertion_failures(engine):
     z = dict(old_root=0, siblings=[0, 0, 0, 0], old_key=0, old_value=0, is_old0=0, new_key=0, new_value=0, fnc0=0, fnc1=0)
     roots, status, want = run(engine, [z, dict(z, is_old0=2)], 4)
     assert (roots, status) == ([0, 0], [0, 3]) and want == [(0, 0), (0, 3)]
+
+
+def test_packed_proofs_give_the_dense_results(engine):
+    """gcp_smt_process_packed: the proofs as arbo's GenProof returns them (wrapper_arbo.go:166-179 unpacks on the CPU)."""
+    rng = random.Random(166)
+    n_levels = 64
+    tree = osmt.Tree(n_levels)
+    cases, packed = [], []
+    for step in range(30):
+        k = rng.getrandbits(n_levels)
+        v = rng.randrange(R)
+        old_root = tree.root()
+        p = tree.gen_proof(k)
+        packed.append(tree.last_packed)
+        tree.add(k, v)
+        cases.append(dict(old_root=old_root, siblings=p["siblings"], old_key=p["old_key"], old_value=p["old_value"],
+                          is_old0=p["is_old0"], new_key=k, new_value=v, fnc0=1, fnc1=0))
+    cases.append(dict(cases[3]))
+    packed.append(packed[3][:-2])                                   # truncated string: arbo.UnpackSiblings errors
+    n = len(cases)
+    dense_roots, dense_status, want = run(engine, cases, n_levels)
+    out, st = engine.smt_process_packed(
+        elems(c["old_root"] for c in cases), packed, n_levels, elems(c["old_key"] for c in cases),
+        elems(c["old_value"] for c in cases), np.array([c["is_old0"] for c in cases], np.uint8),
+        elems(c["new_key"] for c in cases), elems(c["new_value"] for c in cases),
+        np.array([c["fnc0"] for c in cases], np.uint8), np.array([c["fnc1"] for c in cases], np.uint8))
+    got_roots, got_status = ints(out), [int(s) for s in st]
+    assert got_roots[:n - 1] == dense_roots[:n - 1] and got_status[:n - 1] == dense_status[:n - 1]
+    assert [(r, s) for r, s in zip(got_roots[:n - 1], got_status[:n - 1])] == want[:n - 1]
+    assert got_status[-1] == osmt.STATUS_MALFORMED and got_roots[-1] == 0
+    assert all(s == 0 for s in got_status[:n - 1])
