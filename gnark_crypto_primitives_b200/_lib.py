@@ -94,6 +94,12 @@ SIGNATURES = {
                                               c_void_p, c_int, c_void_p]),
     "gcp_keccak_address": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "gcp_keccak_address_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "gcp_ballot_batch": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_int]),
+    "gcp_group_ballot_batch": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_int]),
     "gcp_ballot_batch_dev": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "gcp_smt_process": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

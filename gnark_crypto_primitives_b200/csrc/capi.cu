@@ -1179,6 +1179,124 @@ int gcp_ballot_batch_dev(gcp_ctx* ctx, int n_levels, size_t n_voters, const void
   return encrypt_tally_dev_locked(ctx, d_k, d_m, d_flags, n_voters, n_fields, d_tally, d_tally_status, fmt, st, 44);
 }
 
+// Host-buffer form of the ballot batch: voters are streamed in chunks on the two streams (proofs dense, or arbo packed
+// when siblings == NULL), each chunk runs verifier -> masked encrypt-tally on the device, the per-chunk partial
+// ciphertexts are folded at the end.  out_flags / out_status: per voter; out_tally / out_tally_status: per field.
+int gcp_ballot_batch(gcp_ctx* ctx, int n_levels, size_t n_voters, const void* roots, int shared_root, const void* siblings,
+                     const uint8_t* packed, const uint64_t* offsets, const void* keys, const void* values,
+                     const void* pub_key, const void* k, const void* m, int n_fields, uint8_t* out_flags,
+                     uint8_t* out_status, void* out_tally, uint8_t* out_tally_status, int fmt) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  const bool is_packed = siblings == nullptr;
+  const size_t n = n_voters;
+  int rc = encrypt_tally_check(ctx, pub_key, k, m, n, n_fields, out_tally, out_tally_status, fmt);
+  if (rc != GCP_OK) return rc;
+  if (n_levels < 2 || n_levels > 253) return ctx->fail(GCP_ERR_BAD_ARG, "n_levels must be in [2, 253]");
+  if (n && (!roots || !keys || !values || !out_flags || !out_status || (is_packed && (!packed || !offsets))))
+    return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  rc = ensure_pk_table(ctx, pub_key, false, fmt, ctx->stream[0]);
+  if (rc != GCP_OK) return rc;
+  u32 pk_ok = 0;
+  CU(cudaMemcpy(&pk_ok, ctx->d_flagPK, 4, cudaMemcpyDeviceToHost), "read key flag");
+  const size_t sib_bytes = (size_t)n_levels * 32, ballot_in = (size_t)n_fields * 32, ballot_ct = (size_t)n_fields * 128;
+  const size_t wave = (size_t)ctx->sm_count * 5 * 128;
+  size_t chunk = std::max<size_t>(1, ((size_t)1 << 30) / (sib_bytes + 2 * ballot_in));
+  if (chunk > wave) chunk -= chunk % wave;
+  chunk = std::max<size_t>(1, std::min(chunk, std::max<size_t>(n, 1)));
+  if (const char* env = getenv("GCP_B200_SMT_CHUNK")) {
+    long v = atol(env);
+    if (v > 0) chunk = std::min<size_t>(std::max<size_t>(n, 1), (size_t)v);
+  }
+  const size_t n_chunks = n ? (n + chunk - 1) / chunk : 1;
+  u32* d_parts = (u32*)ctx->buf(64, n_chunks * ballot_ct);
+  uint8_t* d_part_status = (uint8_t*)ctx->buf(65, n_chunks * n_fields);
+  void* d_out = ctx->buf(66, ballot_ct);
+  uint8_t* d_tstatus = (uint8_t*)ctx->buf(67, n_fields);
+  void* d_shared_root = nullptr;
+  if (!d_parts || !d_part_status || !d_out || !d_tstatus) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+  if (shared_root && n) {
+    d_shared_root = ctx->buf(3, 32);
+    if (!d_shared_root) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+    CU(cudaMemcpy(d_shared_root, roots, 32, cudaMemcpyHostToDevice), "H2D root");
+  }
+  for (size_t c = 0; c < n_chunks; c++) {
+    const size_t off = c * chunk, cnt = n ? std::min(chunk, n - off) : 0;
+    const int s = (int)(c & 1);
+    cudaStream_t st = ctx->stream[s];
+    const int b = 10 + s * 14;
+    void* dk = ctx->buf(48 + s * 8, std::max<size_t>(cnt, 1) * ballot_in);
+    void* dm = ctx->buf(48 + s * 8 + 4, std::max<size_t>(cnt, 1) * ballot_in);
+    uint8_t* d_flags = (uint8_t*)ctx->buf(b + 9, std::max<size_t>(cnt, 1));
+    if (!dk || !dm || !d_flags) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+    if (cnt) {
+      void* d_sib = ctx->buf(b + 0, cnt * sib_bytes);
+      void* d_roots = shared_root ? d_shared_root : ctx->buf(b + 1, cnt * 32);
+      void* d_keys = ctx->buf(b + 2, cnt * 32);
+      void* d_vals = ctx->buf(b + 3, cnt * 32);
+      uint8_t* d_status = (uint8_t*)ctx->buf(b + 10, cnt);
+      if (!d_sib || !d_roots || !d_keys || !d_vals || !d_status) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+      uint8_t* d_bad = nullptr;
+      if (is_packed) {
+        const uint64_t pbeg = offsets[off], pend = offsets[off + cnt];
+        if (pend < pbeg) return ctx->fail(GCP_ERR_BAD_ARG, "packed offsets must be non-decreasing");
+        const size_t pbytes = (size_t)(pend - pbeg);
+        uint8_t* d_packed = (uint8_t*)ctx->buf(80 + s * 3 + 0, pbytes + 4);
+        uint64_t* d_off = (uint64_t*)ctx->buf(80 + s * 3 + 1, (cnt + 1) * 8);
+        d_bad = (uint8_t*)ctx->buf(80 + s * 3 + 2, cnt);
+        if (!d_packed || !d_off || !d_bad) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+        if (pbytes) CU(cudaMemcpyAsync(d_packed, packed + pbeg, pbytes, cudaMemcpyHostToDevice, st), "H2D");
+        CU(cudaMemcpyAsync(d_off, offsets + off, (cnt + 1) * 8, cudaMemcpyHostToDevice, st), "H2D");
+        CU(launch_smt_unpack(d_packed, d_off, pbeg, pbytes, cnt, n_levels, (u32*)d_sib, d_bad, fmt, st), "smt unpack kernel");
+        ctx->launches++;
+      } else {
+        CU(cudaMemcpyAsync(d_sib, (const char*)siblings + off * sib_bytes, cnt * sib_bytes, cudaMemcpyHostToDevice, st), "H2D");
+      }
+      if (!shared_root) CU(cudaMemcpyAsync(d_roots, (const char*)roots + off * 32, cnt * 32, cudaMemcpyHostToDevice, st), "H2D");
+      CU(cudaMemcpyAsync(d_keys, (const char*)keys + off * 32, cnt * 32, cudaMemcpyHostToDevice, st), "H2D");
+      CU(cudaMemcpyAsync(d_vals, (const char*)values + off * 32, cnt * 32, cudaMemcpyHostToDevice, st), "H2D");
+      CU(cudaMemcpyAsync(dk, (const char*)k + off * ballot_in, cnt * ballot_in, cudaMemcpyHostToDevice, st), "H2D");
+      CU(cudaMemcpyAsync(dm, (const char*)m + off * ballot_in, cnt * ballot_in, cudaMemcpyHostToDevice, st), "H2D");
+      rc = smt_verify_dev_locked(ctx, n_levels, cnt, d_roots, shared_root, d_sib, nullptr, nullptr, nullptr, d_keys, d_vals,
+                                 nullptr, nullptr, d_flags, d_status, nullptr, fmt, st, b + 12);
+      if (rc != GCP_OK) return rc;
+      if (is_packed) {
+        CU(launch_smt_apply_bad(d_bad, cnt, d_flags, d_status, nullptr, st), "smt apply-bad kernel");
+        ctx->launches++;
+      }
+      CU(cudaMemcpyAsync(out_flags + off, d_flags, cnt, cudaMemcpyDeviceToHost, st), "D2H");
+      CU(cudaMemcpyAsync(out_status + off, d_status, cnt, cudaMemcpyDeviceToHost, st), "D2H");
+    }
+    // flags are 0 wherever status != 0, so the flag array is the admission mask of the fold
+    rc = encrypt_tally_dev_locked(ctx, dk, dm, d_flags, cnt, n_fields, (char*)d_parts + c * ballot_ct,
+                                  d_part_status + c * n_fields, fmt, st, 48 + s * 8 + 1);
+    if (rc != GCP_OK) return rc;
+  }
+  CU(cudaStreamSynchronize(ctx->stream[0]), "stream sync");
+  CU(cudaStreamSynchronize(ctx->stream[1]), "stream sync");
+  cudaStream_t st = ctx->stream[0];
+  const void* d_final = d_parts;
+  const uint8_t* d_final_status = d_part_status;
+  if (n_chunks > 1) {
+    rc = tally_dev_locked(ctx, d_parts, n_chunks, n_fields, d_out, d_tstatus, fmt, st, 49);
+    if (rc != GCP_OK) return rc;
+    d_final = d_out;
+    d_final_status = d_tstatus;
+  }
+  std::vector<uint8_t> part_status(n_chunks * n_fields);
+  CU(cudaMemcpyAsync(out_tally, d_final, ballot_ct, cudaMemcpyDeviceToHost, st), "D2H");
+  CU(cudaMemcpyAsync(out_tally_status, d_final_status, n_fields, cudaMemcpyDeviceToHost, st), "D2H");
+  CU(cudaMemcpyAsync(part_status.data(), d_part_status, part_status.size(), cudaMemcpyDeviceToHost, st), "D2H");
+  CU(cudaStreamSynchronize(st), "stream sync");
+  for (int f = 0; f < n_fields; f++) {
+    for (size_t c = 0; c < n_chunks; c++)
+      if (part_status[c * n_fields + f] && !out_tally_status[f]) out_tally_status[f] = part_status[c * n_fields + f];
+    if (!pk_ok) out_tally_status[f] = (uint8_t)gcp::GCP_STATUS_OFF_CURVE;
+  }
+  return GCP_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Decryption checks and coordinate conversion: host-buffer forms, one chunk
 // ---------------------------------------------------------------------------------------------------

@@ -113,15 +113,23 @@ char* off(void* p, size_t bytes) { return p ? (char*)p + bytes : nullptr; }
 const uint8_t* offb(const uint8_t* p, size_t n) { return p ? p + n : nullptr; }
 uint8_t* offb(uint8_t* p, size_t n) { return p ? p + n : nullptr; }
 
-// partial[i] (host, n_fields ciphertexts + n_fields status bytes per device) -> all-gather on the devices -> fold on
-// every device -> out/status from device 0.  Called with one thread per device (the collective needs all of them).
-int exchange_and_fold(gcp_group* g, int i, const unsigned char* partial, int n_fields, void* out, uint8_t* status,
-                      int fmt) {
+// Exchange of the partial tallies, in two steps so that a device that fails BEFORE the collective never leaves the
+// others waiting inside it: (a) upload this device's partial (host, n_fields ciphertexts); (b) all-gather on the
+// devices, fold the gathered array on every device, read out/status back from device 0.  Both run with one host
+// thread per device; (b) is entered only when (a) succeeded everywhere.
+int upload_partial(gcp_group* g, int i, const unsigned char* partial, int n_fields) {
+  const size_t pb = (size_t)n_fields * kCtBytes;
+  if (cudaSetDevice(g->devices[i]) != cudaSuccess) return GCP_ERR_CUDA;
+  if (cudaMemcpyAsync(g->d_send[i], partial, pb, cudaMemcpyHostToDevice, g->stream[i]) != cudaSuccess) return GCP_ERR_CUDA;
+  if (cudaStreamSynchronize(g->stream[i]) != cudaSuccess) return GCP_ERR_CUDA;
+  return GCP_OK;
+}
+
+int gather_and_fold(gcp_group* g, int i, int n_fields, void* out, uint8_t* status, int fmt) {
   const int w = (int)g->ctx.size();
   const size_t pb = (size_t)n_fields * kCtBytes;
   if (cudaSetDevice(g->devices[i]) != cudaSuccess) return GCP_ERR_CUDA;
   cudaStream_t st = g->stream[i];
-  if (cudaMemcpyAsync(g->d_send[i], partial, pb, cudaMemcpyHostToDevice, st) != cudaSuccess) return GCP_ERR_CUDA;
   if (w > 1) {
     int nrc = g->nccl.AllGather(g->d_send[i], g->d_recv[i], pb, kNcclUint8, g->comm[i], st);
     if (nrc != 0) {
@@ -335,9 +343,9 @@ static int group_tally(gcp_group* g, size_t n_ballots, int n_fields, void* out, 
   });
   if (rc != GCP_OK) return rc;
   // phase 2: all-gather of the partials (bytes) and the final fold on every device
-  rc = for_each_device(g, [&](int i) {
-    return exchange_and_fold(g, i, partial.data() + (size_t)i * pb, n_fields, out, status, fmt);
-  });
+  rc = for_each_device(g, [&](int i) { return upload_partial(g, i, partial.data() + (size_t)i * pb, n_fields); });
+  if (rc != GCP_OK) return rc;
+  rc = for_each_device(g, [&](int i) { return gather_and_fold(g, i, n_fields, out, status, fmt); });
   if (rc != GCP_OK) return rc;
   for (int i = 0; i < w; i++)
     for (int f = 0; f < n_fields; f++)
@@ -358,6 +366,20 @@ int gcp_group_elgamal_encrypt_tally(gcp_group* g, const void* pub_key, const voi
     const size_t row = (size_t)n_fields * 32;
     return gcp_elgamal_encrypt_tally(g->ctx[i], pub_key, off(k, s.lo * row), off(m, s.lo * row), s.hi - s.lo, n_fields, p,
                                      ps, fmt);
+  });
+}
+
+int gcp_group_ballot_batch(gcp_group* g, int n_levels, size_t n_voters, const void* roots, int shared_root,
+                           const void* siblings, const uint8_t* packed, const uint64_t* offsets, const void* keys,
+                           const void* values, const void* pub_key, const void* k, const void* m, int n_fields,
+                           uint8_t* out_flags, uint8_t* out_status, void* out_tally, uint8_t* out_tally_status, int fmt) {
+  const size_t sib_row = (size_t)(n_levels > 0 ? n_levels : 0) * 32;
+  return group_tally(g, n_voters, n_fields, out_tally, out_tally_status, fmt, [&](int i, Shard s, unsigned char* p, uint8_t* ps) {
+    const size_t row = (size_t)n_fields * 32;
+    return gcp_ballot_batch(g->ctx[i], n_levels, s.hi - s.lo, shared_root ? roots : off(roots, s.lo * 32), shared_root,
+                            off(siblings, s.lo * sib_row), packed, offsets ? offsets + s.lo : nullptr, off(keys, s.lo * 32),
+                            off(values, s.lo * 32), pub_key, off(k, s.lo * row), off(m, s.lo * row), n_fields,
+                            offb(out_flags, s.lo), offb(out_status, s.lo), p, ps, fmt);
   });
 }
 

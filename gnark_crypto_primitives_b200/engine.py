@@ -66,6 +66,37 @@ def _u8(arr, n, name):
     return a
 
 
+def _ballot_batch_call(fn, handle, n_levels, roots, siblings, packed, keys, values, pub_key, k, m, fmt):
+    """Shared argument marshalling of gcp_ballot_batch / gcp_group_ballot_batch."""
+    kk = _as_elems(k, name="k")
+    if kk.ndim != 3:
+        raise ValueError("k must have shape (n_voters, n_fields, 32)")
+    n, nf = kk.shape[0], kk.shape[1]
+    mm = _as_elems(m, n * nf, "m")
+    pk = _as_elems(pub_key, 2, "pub_key")
+    r = _as_elems(roots, name="roots")
+    shared = 1 if r.size == 32 and n != 1 else 0
+    kv = _as_elems(keys, n, "keys")
+    vv = _as_elems(values, n, "values")
+    sib = blob = offs = None
+    if packed is None:
+        sib = _as_elems(siblings, n * int(n_levels), "siblings")
+    else:
+        lens = np.fromiter((len(b) for b in packed), dtype=np.uint64, count=len(packed))
+        offs = np.zeros(len(packed) + 1, dtype=np.uint64)
+        np.cumsum(lens, out=offs[1:])
+        blob = np.frombuffer(b"".join(bytes(b) for b in packed) or b"\0", dtype=np.uint8)
+        if len(packed) != n:
+            raise ValueError("one packed proof per voter")
+    flags = np.empty(n, dtype=np.uint8)
+    status = np.empty(n, dtype=np.uint8)
+    tally = np.empty((nf, 4, 32), dtype=np.uint8)
+    tstatus = np.empty(nf, dtype=np.uint8)
+    rc = fn(handle, int(n_levels), n, _ptr(r), shared, _ptr(sib), _ptr(blob), _ptr(offs), _ptr(kv), _ptr(vv), _ptr(pk),
+            _ptr(kk), _ptr(mm), nf, _ptr(flags), _ptr(status), _ptr(tally), _ptr(tstatus), fmt)
+    return rc, (flags, status, tally, tstatus)
+
+
 class PinnedBuffer:
     """Page-locked host memory from gcp_host_alloc, viewed as a numpy uint8 array (`.array`); free with close()."""
 
@@ -403,6 +434,15 @@ class Engine:
         self._check(self._lib.gcp_keccak_address_dev(self._h, _dptr(d_in), n, _dptr(d_out), self._stream(stream)))
 
     # -- end-to-end ballot batch (config 5) ---------------------------------------------------------
+    def ballot_batch(self, n_levels, roots, keys, values, pub_key, k, m, siblings=None, packed=None, fmt=FMT_CANONICAL):
+        """End-to-end ballot batch from host buffers (config 5): census proofs dense (`siblings` (n, n_levels, 32)) or
+        arbo packed (`packed`: list of byte strings); k, m: (n_voters, n_fields, 32).
+        Returns (flags, status, tally (n_fields, 4, 32), tally_status)."""
+        rc, out = _ballot_batch_call(self._lib.gcp_ballot_batch, self._h, n_levels, roots, siblings, packed, keys, values,
+                                     pub_key, k, m, fmt)
+        self._check(rc)
+        return out
+
     def ballot_batch_dev(self, n_levels, n_voters, d_roots, shared_root, d_siblings, d_keys, d_values, d_pub_key, d_k,
                          d_m, n_fields, d_flags, d_status, d_tally, d_tally_status, fmt=FMT_CANONICAL, stream=None):
         self._check(self._lib.gcp_ballot_batch_dev(self._h, n_levels, n_voters, _dptr(d_roots), int(bool(shared_root)),
@@ -638,6 +678,12 @@ class Group:
         self._check(self._lib.gcp_group_elgamal_encrypt(self._h, _ptr(pk), per_item, _ptr(kk), _ptr(mm), n, _ptr(out),
                                                         _ptr(status), fmt))
         return out, status
+
+    def ballot_batch(self, n_levels, roots, keys, values, pub_key, k, m, siblings=None, packed=None, fmt=FMT_CANONICAL):
+        rc, out = _ballot_batch_call(self._lib.gcp_group_ballot_batch, self._h, n_levels, roots, siblings, packed, keys,
+                                     values, pub_key, k, m, fmt)
+        self._check(rc)
+        return out
 
     def elgamal_tally(self, ct, fmt=FMT_CANONICAL):
         c = _as_elems(ct, name="ct")

@@ -232,6 +232,15 @@ int gcp_ballot_batch_dev(gcp_ctx* ctx, int n_levels, size_t n_voters, const void
                          const void* d_k, const void* d_m, int n_fields, uint8_t* d_flags, uint8_t* d_status,
                          void* d_tally, uint8_t* d_tally_status, int fmt, void* stream);
 
+/* Host-buffer form: voters are streamed to the device in chunks (copy of chunk k+1 overlaps the kernels of chunk
+ * k).  Census proofs are dense rows (`siblings`) or, with siblings == NULL, arbo packed strings (`packed`, `offsets`:
+ * see gcp_smt_verify_packed).  out_flags / out_status: n_voters bytes each; out_tally: n_fields ciphertexts,
+ * out_tally_status: n_fields bytes. */
+int gcp_ballot_batch(gcp_ctx* ctx, int n_levels, size_t n_voters, const void* roots, int shared_root, const void* siblings,
+                     const uint8_t* packed, const uint64_t* offsets, const void* keys, const void* values,
+                     const void* pub_key, const void* k, const void* m, int n_fields, uint8_t* out_flags,
+                     uint8_t* out_status, void* out_tally, uint8_t* out_tally_status, int fmt);
+
 /* ---- Ethereum address: ecc/secp256k1/ecdsa/address.go:14-40 ------------------------------------------- */
 /* DeriveAddress: out_addr[i] = Keccak256_legacy(pub_xy_be[i])[12:32], pub_xy_be[i] = X (32 bytes big-endian) ||
  * Y (32 bytes big-endian).  out_addr: n x 20 bytes (the bytes U8ToVar packs big-endian into one variable). */
@@ -272,6 +281,12 @@ int gcp_group_elgamal_tally(gcp_group* g, const void* ct, size_t n_ballots, int 
                             int fmt);
 int gcp_group_elgamal_encrypt_tally(gcp_group* g, const void* pub_key, const void* k, const void* m, size_t n_ballots,
                                     int n_fields, void* out, uint8_t* status, int fmt);
+/* gcp_ballot_batch over the voters sharded across the group (BASELINE config 5 at 1/2/4/8 GPUs); the per-device
+ * tallies are exchanged like gcp_group_elgamal_tally's. */
+int gcp_group_ballot_batch(gcp_group* g, int n_levels, size_t n_voters, const void* roots, int shared_root,
+                           const void* siblings, const uint8_t* packed, const uint64_t* offsets, const void* keys,
+                           const void* values, const void* pub_key, const void* k, const void* m, int n_fields,
+                           uint8_t* out_flags, uint8_t* out_status, void* out_tally, uint8_t* out_tally_status, int fmt);
 
 #ifdef __cplusplus
 }
