@@ -194,11 +194,10 @@ def measure_extras(torch, dist, eng, g, world, rank):
     return out
 
 
-def measure_census_like(torch, eng, g, log2_n=18, seed=0xCE75):
+def make_census_like(torch, eng, n, seed=0xCE75):
     """Census-like batch (SURVEY 8d secondary distribution: L ~ U[20,28] leading siblings of 160, ~10 % interior
-    zeros) end to end from HOST buffers, two ways: the dense Assignment.Siblings rows (n_levels * 32 B per proof) and
-    arbo's packed proofs expanded on the GPU (gcp_smt_verify_packed).  Same proofs, flags compared."""
-    n = 1 << log2_n
+    zeros), every 16th proof with a wrong value.  Device tensors plus the two host forms a caller can hold: dense
+    Assignment.Siblings rows (pinned) and arbo packed proofs back to back (pinned blob + offsets)."""
     gen = torch.Generator(device="cuda")
     gen.manual_seed(seed)
     sib = rand_elems(torch, n * N_LEVELS, gen, nonzero=True).view(n, N_LEVELS, 8)
@@ -221,16 +220,6 @@ def measure_census_like(torch, eng, g, log2_n=18, seed=0xCE75):
     vals[::16, 0] ^= 2                                 # every 16th proof carries a wrong value
     expect = np.ones(n, dtype=np.uint8)
     expect[::16] = 0
-    # resident timing
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    eng.smt_verify_dev(N_LEVELS, n, roots, False, sib, keys, vals, flags, status, stream=stream)
-    e0.record(stream)
-    for _ in range(3):
-        eng.smt_verify_dev(N_LEVELS, n, roots, False, sib, keys, vals, flags, status, stream=stream)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    resident = n / (e0.elapsed_time(e1) / 3 * 1e-3)
-    # host copies: dense rows (pinned) and the packed blob a Go caller would hold (GenProof output, back to back)
     hs = torch.empty(sib.shape, dtype=sib.dtype).pin_memory()
     hs.copy_(sib)
     hk, hv, hr = (t.cpu().numpy().view(np.uint8).reshape(n, 32) for t in (keys, vals, roots))
@@ -251,6 +240,27 @@ def measure_census_like(torch, eng, g, log2_n=18, seed=0xCE75):
         blob[o + 2:o + 4] = np.frombuffer(int(bm_len[i]).to_bytes(2, "little"), dtype=np.uint8)
         blob[o + 4:o + 4 + bm_len[i]] = bits[i, :bm_len[i]]
         blob[o + 4 + bm_len[i]:o + lens[i]] = dense[i, :Lh[i]][nz[i, :Lh[i]]].reshape(-1)
+    return dict(sib=sib, keys=keys, vals=vals, roots=roots, flags=flags, status=status, expect=expect, dense=dense,
+                hk=hk, hv=hv, hr=hr, blob=blob, offs=offs, mean_levels=float(Lh.mean()), _pins=(hs, blob_t))
+
+
+def measure_census_like(torch, eng, g, log2_n=18, seed=0xCE75):
+    """Census-like batch end to end from HOST buffers, two ways: the dense Assignment.Siblings rows (n_levels * 32 B
+    per proof) and arbo's packed proofs expanded on the GPU (gcp_smt_verify_packed).  Same proofs, flags compared."""
+    n = 1 << log2_n
+    c = make_census_like(torch, eng, n, seed)
+    sib, keys, vals, roots, flags, status, expect = (c[k] for k in ("sib", "keys", "vals", "roots", "flags", "status", "expect"))
+    dense, hk, hv, hr, blob, offs = (c[k] for k in ("dense", "hk", "hv", "hr", "blob", "offs"))
+    stream = torch.cuda.current_stream()
+    # resident timing
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eng.smt_verify_dev(N_LEVELS, n, roots, False, sib, keys, vals, flags, status, stream=stream)
+    e0.record(stream)
+    for _ in range(3):
+        eng.smt_verify_dev(N_LEVELS, n, roots, False, sib, keys, vals, flags, status, stream=stream)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    resident = n / (e0.elapsed_time(e1) / 3 * 1e-3)
     of, os_ = np.empty(n, dtype=np.uint8), np.empty(n, dtype=np.uint8)
     lib, hctx = eng._lib, eng._h
 
@@ -267,7 +277,7 @@ def measure_census_like(torch, eng, g, log2_n=18, seed=0xCE75):
         if rc != 0:
             raise RuntimeError(lib.gcp_last_error(hctx))
 
-    res = {"proofs": n, "mean_path_levels": float(Lh.mean()), "resident_proofs_per_s": resident,
+    res = {"proofs": n, "mean_path_levels": c["mean_levels"], "resident_proofs_per_s": resident,
            "dense_h2d_bytes": int(n * (N_LEVELS + 3) * 32), "packed_h2d_bytes": int(offs[-1]) + (n + 1) * 8 + n * 96}
     for name, fn in (("dense", run_dense), ("packed", run_packed)):
         fn()

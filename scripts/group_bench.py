@@ -7,7 +7,7 @@ import torch
 sys.path.insert(0, ".")
 import gnark_crypto_primitives_b200 as g
 from gnark_crypto_primitives_b200 import _lib
-from bench import make_batch, rand_elems, N_LEVELS
+from bench import make_batch, make_census_like, rand_elems, N_LEVELS
 
 log2_per_gpu = int(sys.argv[1]) if len(sys.argv) > 1 else 19
 visible = _lib.load().gcp_device_count()
@@ -35,6 +35,9 @@ kk = rand_elems(torch, nb_per_gpu * nf * sizes[-1], gen).cpu().numpy().view(np.u
 mm = np.zeros_like(kk); mm[:, :, 0:2] = kk[:, :, 4:6]
 sk = np.zeros((1, 32), np.uint8); sk[0, 0] = 0xB2
 pk, _ = eng0.elgamal_fixed_base_mul(sk)
+# config 5 shape: census-like packed proofs, 8 fields per voter, 2^17 voters per GPU
+nv_per_gpu = 1 << 17
+cen = make_census_like(torch, eng0, nv_per_gpu * sizes[-1])
 eng0.close()
 tallies = {}
 for s in sizes:
@@ -52,7 +55,26 @@ for s in sizes:
         out, st = grp.elgamal_encrypt_tally(pk[0], kk[:nb], mm[:nb])
         dt2 = time.perf_counter() - t0
         tallies[s] = out
-        print(json.dumps({"group_size": s, "uses_nccl": grp.uses_nccl, "proofs": n, "smt_e2e_proofs_per_s": n / dt,
+        nv = nv_per_gpu * s
+        lens = cen["offs"][:nv + 1]
+        bargs = (N_LEVELS, cen["hr"][:nv], cen["hk"][:nv], cen["hv"][:nv], pk[0], kk[:nv], mm[:nv])
+        packed_list = None
+        lib = grp._lib
+        import ctypes
+        def ballot():
+            fl = np.empty(nv, np.uint8); stv = np.empty(nv, np.uint8); tl = np.empty((nf, 4, 32), np.uint8); ts = np.empty(nf, np.uint8)
+            rc = lib.gcp_group_ballot_batch(grp._h, N_LEVELS, nv, cen["hr"].ctypes.data, 0, None, cen["blob"].ctypes.data,
+                                            cen["offs"].ctypes.data, cen["hk"].ctypes.data, cen["hv"].ctypes.data,
+                                            np.ascontiguousarray(pk[0]).ctypes.data, kk.ctypes.data, mm.ctypes.data, nf,
+                                            fl.ctypes.data, stv.ctypes.data, tl.ctypes.data, ts.ctypes.data, 0)
+            assert rc == 0, lib.gcp_group_last_error(grp._h)
+            return fl, stv, tl, ts
+        ballot()
+        t0 = time.perf_counter()
+        fl, stv, tl, ts = ballot()
+        dt3 = time.perf_counter() - t0
+        ballot_ok = bool((fl == cen["expect"][:nv]).all()) and not stv.any() and not ts.any()
+        print(json.dumps({"group_size": s, "voters": nv, "ballot_batch_e2e_voters_per_s": nv / dt3, "ballot_flags_ok": ballot_ok, "uses_nccl": grp.uses_nccl, "proofs": n, "smt_e2e_proofs_per_s": n / dt,
                           "flags_ok": ok, "ballots": nb, "fields": nf, "encrypt_tally_e2e_enc_per_s": nb * nf / dt2,
                           "tally_status_clean": not st.any()}), flush=True)
 # the tally of the first nb_per_gpu ballots must not depend on the group size
