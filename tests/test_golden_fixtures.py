@@ -51,3 +51,40 @@ def test_reference_entries_carry_the_published_values():
     m = {tuple(int(x) for x in e["in"]): int(e["out"]) for e in doc["mimc7"][:3]}
     assert m[(12,)] == 16051049095595290701999129793867590386356047218708919933694064829788708231421
     assert m[(12, 45, 78, 41)] == 18226366069841799622585958305961373004333097209608110160936134895615261821931
+
+
+def test_c_port_reproduces_the_fixtures():
+    """oracle/c (the CPU baseline of bench.py) against the stored vectors: Poseidon, the verifier, Encrypt, tally."""
+    import numpy as np
+
+    from oracle import cport
+    from tests.util import elems, ints
+
+    doc = load()
+    by_arity = {}
+    for e in doc["poseidon"]["kat"] + doc["poseidon"]["hash"]:
+        by_arity.setdefault(len(e["in"]), []).append(e)
+    for arity, es in by_arity.items():
+        out, st = cport.poseidon_hash(elems([int(x) for e in es for x in e["in"]]).reshape(len(es), arity, 32))
+        assert not st.any() and ints(out) == [int(e["out"]) for e in es]
+    for e in doc["poseidon"]["multihash"]:
+        out, st = cport.poseidon_multihash(elems([int(x) for x in e["in"]]).reshape(1, len(e["in"]), 32))
+        assert ints(out)[0] == int(e["out"])
+    smt = doc["smt"]
+    cases = [c for c in smt["verifier"] if "n_levels" not in c]
+    n = len(cases)
+    flags, status, _ = cport.smt_verify(
+        elems(int(c["root"]) for c in cases), elems([int(x) for c in cases for x in c["siblings"]]).reshape(n, smt["n_levels"], 32),
+        elems(int(c["key"]) for c in cases), elems(int(c["value"]) for c in cases),
+        old_keys=elems(int(c["old_key"]) for c in cases), old_values=elems(int(c["old_value"]) for c in cases),
+        is_old0=np.array([c["is_old0"] for c in cases], np.uint8), fnc=np.array([c["fnc"] for c in cases], np.uint8),
+        enabled=np.array([c["enabled"] for c in cases], np.uint8), literal=True)
+    assert [int(f) for f in flags] == [c["flag"] for c in cases] and [int(s) for s in status] == [c["status"] for c in cases]
+    enc = [e for e in doc["elgamal"]["encrypt"]]
+    for e in enc:
+        ct, st = cport.elgamal_encrypt(elems([int(x) for x in e["pk"]]).reshape(2, 32), elems([int(e["k"])]), elems([int(e["m"])]))
+        assert int(st[0]) == 0 and ints(ct[0]) == [int(x) for x in e["ct"]]
+    t = doc["elgamal"]["tally"]
+    nb, nf = len(t["ballots"]), len(t["ballots"][0])
+    tal, st = cport.elgamal_tally(elems([int(x) for row in t["ballots"] for c in row for x in c]).reshape(nb, nf, 4, 32))
+    assert [ints(tal[f]) for f in range(nf)] == [[int(x) for x in c] for c in t["tally"]]
