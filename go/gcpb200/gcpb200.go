@@ -17,6 +17,7 @@ import "C"
 import (
 	"errors"
 	"fmt"
+	"math/big"
 	"unsafe"
 
 	"github.com/consensys/gnark-crypto/ecc/bn254/fr"
@@ -281,4 +282,52 @@ func (g *Group) EncryptTally(pubKey [2]fr.Element, k, m []fr.Element, nFields in
 	err = g.err(C.gcp_group_elgamal_encrypt_tally(g.grp, unsafe.Pointer(&pubKey[0]), elemPtr(k), elemPtr(m),
 		C.size_t(nBallots), C.int(nFields), elemPtr(out), bytePtr(status), C.GCP_FMT_MONTGOMERY))
 	return
+}
+
+// BatchVerifyPacked is Engine.BatchVerifyPacked over all GPUs of the group.
+func (g *Group) BatchVerifyPacked(p *Proofs, packed [][]byte) (flags, status []byte, err error) {
+	n := len(p.Keys)
+	flags, status = make([]byte, n), make([]byte, n)
+	offsets := make([]uint64, n+1)
+	total := 0
+	for i, b := range packed {
+		total += len(b)
+		offsets[i+1] = uint64(total)
+	}
+	blob := make([]byte, 0, total+1)
+	for _, b := range packed {
+		blob = append(blob, b...)
+	}
+	blob = append(blob, 0)
+	shared := 0
+	if len(p.Roots) == 1 && n != 1 {
+		shared = 1
+	}
+	err = g.err(C.gcp_group_smt_verify_packed(g.grp, C.int(p.Levels), C.size_t(n), elemPtr(p.Roots), C.int(shared),
+		bytePtr(blob), (*C.uint64_t)(unsafe.Pointer(&offsets[0])), elemPtr(p.OldKeys), elemPtr(p.OldValues),
+		bytePtr(p.IsOld0), elemPtr(p.Keys), elemPtr(p.Values), bytePtr(p.Fnc), bytePtr(p.Enabled), bytePtr(flags),
+		bytePtr(status), nil, C.GCP_FMT_MONTGOMERY))
+	return
+}
+
+// PoseidonHint has the shape of a gnark solver.Hint (func(mod *big.Int, in, out []*big.Int) error; the reference
+// registers one of that shape at hash/native/bn254/poseidon2/hints.go:10): out[0] = poseidon.Hash(in...) over BN254 Fr,
+// computed by the engine.  For witness generation over many hashes prefer BatchHash: a hint call carries one hash.
+func (e *Engine) PoseidonHint(_ *big.Int, in, out []*big.Int) error {
+	if len(out) != 1 {
+		return errors.New("PoseidonHint: one output expected")
+	}
+	elems := make([]fr.Element, len(in))
+	for i, v := range in {
+		elems[i].SetBigInt(v)
+	}
+	digest, status, err := e.BatchHash(elems, len(in))
+	if err != nil {
+		return err
+	}
+	if status[0] != StatusOK {
+		return fmt.Errorf("PoseidonHint: status %d", status[0])
+	}
+	digest[0].BigInt(out[0])
+	return nil
 }
