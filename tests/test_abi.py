@@ -45,3 +45,14 @@ def test_product_never_imports_oracle():
     for path in list(pkg.glob("*.py")) + list((pkg / "csrc").glob("*")):
         if path.suffix in (".py", ".cu", ".cuh", ".h"):
             assert not pat.search(path.read_text()), path
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/gcp_b200.h must compile as C99 on its own (the cgo preamble includes nothing else) and as C++."""
+    import subprocess
+
+    src = tmp_path / "probe.c"
+    src.write_text('#include "gcp_b200.h"\nint probe(void) { return GCP_OK + GCP_FMT_MONTGOMERY + GCP_STATUS_MALFORMED; }\n')
+    for compiler, std in (("gcc", "-std=c99"), ("g++", "-std=c++17")):
+        subprocess.run([compiler, std, "-Wall", "-Wextra", "-Werror", "-pedantic", "-x", "c" if compiler == "gcc" else "c++",
+                        f"-I{ROOT / 'include'}", "-c", str(src), "-o", str(tmp_path / "probe.o")], check=True)
