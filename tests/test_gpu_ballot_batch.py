@@ -118,3 +118,15 @@ def test_host_ballot_batch_through_a_group(engine):
     one = engine.ballot_batch(*args, siblings=sib)
     for a, b in zip(out, one):
         assert np.array_equal(a, b)
+
+
+def test_host_ballot_batch_with_no_voters(engine):
+    """Empty batch: the tally is NewCiphertext (identity, identity) per field (elgamal/ciphertext.go:16-19)."""
+    nf = 2
+    pk = ed.scalar_mul(ed.G, 0xB200)
+    flags, status, tally, tstatus = engine.ballot_batch(
+        64, np.zeros((0, 32), np.uint8), np.zeros((0, 32), np.uint8), np.zeros((0, 32), np.uint8), elems(pk),
+        np.zeros((0, nf, 32), np.uint8), np.zeros((0, nf, 32), np.uint8), siblings=np.zeros((0, 64, 32), np.uint8))
+    assert flags.shape == (0,) and status.shape == (0,) and not tstatus.any()
+    for f in range(nf):
+        assert ints(tally[f]) == [0, 1, 0, 1]
