@@ -94,6 +94,8 @@ SIGNATURES = {
                                               c_void_p, c_int, c_void_p]),
     "gcp_keccak_address": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "gcp_keccak_address_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "gcp_elgamal_is_equal": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "gcp_elgamal_select": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "gcp_ballot_batch": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_int]),

@@ -1103,6 +1103,54 @@ int gcp_elgamal_neg(gcp_ctx* ctx, const void* a, size_t n, void* out, uint8_t* s
   return elgamal_host(ctx, 3, nullptr, 0, a, nullptr, n, out, status, fmt);
 }
 
+// Ciphertext.IsEqual / Select (elgamal/ciphertext.go:79-96): element-wise, HBM/PCIe-bound; chunked on the two streams.
+//   kind 0: is_equal(a, b) -> flags;  kind 1: select(sel, i1, i2) -> ciphertexts
+static int ct_elementwise_host(gcp_ctx* ctx, int kind, const uint8_t* sel, const void* a, const void* b, size_t n, void* out,
+                               uint8_t* status) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  if (n == 0) return GCP_OK;
+  if (!a || !b || !out || !status || (kind == 1 && !sel)) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  const size_t out_b = kind == 0 ? 1 : 128;
+  const size_t chunk = std::min<size_t>(n, (size_t)1 << 20);
+  size_t k = 0;
+  for (size_t off = 0; off < n; off += chunk, k++) {
+    const size_t m = std::min(chunk, n - off);
+    const int s = (int)(k & 1);
+    cudaStream_t st = ctx->stream[s];
+    const int bs = 48 + s * 8;
+    void* da = ctx->buf(bs + 0, m * 128);
+    void* db = ctx->buf(bs + 1, m * 128);
+    uint8_t* dsel = kind == 1 ? (uint8_t*)ctx->buf(bs + 2, m) : nullptr;
+    void* dout = ctx->buf(bs + 3, m * out_b);
+    uint8_t* dst = (uint8_t*)ctx->buf(bs + 4, m);
+    if (!da || !db || !dout || !dst || (kind == 1 && !dsel)) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+    CU(cudaMemcpyAsync(da, (const char*)a + off * 128, m * 128, cudaMemcpyHostToDevice, st), "H2D");
+    CU(cudaMemcpyAsync(db, (const char*)b + off * 128, m * 128, cudaMemcpyHostToDevice, st), "H2D");
+    if (kind == 1) {
+      CU(cudaMemcpyAsync(dsel, sel + off, m, cudaMemcpyHostToDevice, st), "H2D");
+      CU(launch_ct_select(dsel, (const u32*)da, (const u32*)db, m, (u32*)dout, dst, st), "select kernel");
+    } else {
+      CU(launch_ct_is_equal((const u32*)da, (const u32*)db, m, (uint8_t*)dout, dst, st), "is-equal kernel");
+    }
+    ctx->launches++;
+    CU(cudaMemcpyAsync((char*)out + off * out_b, dout, m * out_b, cudaMemcpyDeviceToHost, st), "D2H");
+    CU(cudaMemcpyAsync(status + off, dst, m, cudaMemcpyDeviceToHost, st), "D2H");
+  }
+  CU(cudaStreamSynchronize(ctx->stream[0]), "stream sync");
+  CU(cudaStreamSynchronize(ctx->stream[1]), "stream sync");
+  return GCP_OK;
+}
+
+int gcp_elgamal_is_equal(gcp_ctx* ctx, const void* a, const void* b, size_t n, uint8_t* out_flags, uint8_t* status) {
+  return ct_elementwise_host(ctx, 0, nullptr, a, b, n, out_flags, status);
+}
+int gcp_elgamal_select(gcp_ctx* ctx, const uint8_t* sel, const void* i1, const void* i2, size_t n, void* out,
+                       uint8_t* status) {
+  return ct_elementwise_host(ctx, 1, sel, i1, i2, n, out, status);
+}
+
 // Tally over host-resident ciphertexts: chunks are reduced on the device as they arrive; the per-chunk partial
 // ciphertexts are themselves tallied at the end (addition is associative, so the result does not depend on chunking).
 int gcp_elgamal_tally(gcp_ctx* ctx, const void* ct, size_t n_ballots, int n_fields, void* out, uint8_t* status, int fmt) {

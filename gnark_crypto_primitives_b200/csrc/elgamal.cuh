@@ -373,6 +373,37 @@ __global__ void ct_neg_kernel(const u32* __restrict__ a, size_t n_points, u32* _
   store_fr(out + idx * 16 + 8, y);
 }
 
+// IsEqual (ciphertext.go:79-87): 1 iff the four coordinates agree as field elements.  One thread per ciphertext.
+__global__ void ct_is_equal_kernel(const u32* __restrict__ a, const u32* __restrict__ b, size_t n, u8* __restrict__ flags,
+                                   u8* __restrict__ status) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  bool canon = true, eq = true;
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    u32 x[8], y[8];
+    load_fr(x, a + idx * 32 + c * 8);
+    load_fr(y, b + idx * 32 + c * 8);
+    canon = canon && fr_is_canonical(x) && fr_is_canonical(y);
+    eq = eq && eq256(x, y);  // canonical representatives (in either element format) are equal iff the elements are
+  }
+  flags[idx] = (canon && eq) ? 1 : 0;
+  status[idx] = canon ? GCP_STATUS_OK : GCP_STATUS_NONCANONICAL;
+}
+
+// Select (ciphertext.go:90-96): z = b ? i1 : i2 per coordinate; api.Select asserts that b is boolean.
+__global__ void ct_select_kernel(const u8* __restrict__ sel, const u32* __restrict__ i1, const u32* __restrict__ i2, size_t n,
+                                 u32* __restrict__ out, u8* __restrict__ status) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 16-byte piece: 8 per ciphertext
+  if (idx >= n * 8) return;
+  const size_t item = idx >> 3;
+  const u8 b = sel[item];
+  const uint4* src = reinterpret_cast<const uint4*>(b == 1 ? i1 : i2) + idx;
+  uint4 v = (b <= 1) ? __ldg(src) : make_uint4(0, 0, 0, 0);
+  reinterpret_cast<uint4*>(out)[idx] = v;
+  if ((idx & 7) == 0) status[item] = (b <= 1) ? GCP_STATUS_OK : GCP_STATUS_NOT_BOOLEAN;
+}
+
 // ---- Tally: sum over ballots of ct[ballot][field], per field ----------------------------------------------------
 // Each thread owns one (field, point-half) column and strides over ballots; block tree-reduction in shared
 // memory; one partial (X, Y, Z, T) per (block, field, half) to `partials` [gridDim.x][n_fields*2][32 words].

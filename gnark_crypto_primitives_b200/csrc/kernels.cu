@@ -348,6 +348,18 @@ cudaError_t launch_ct_neg(const u32* a, size_t n, u32* out, u8* status, cudaStre
   return cudaGetLastError();
 }
 
+cudaError_t launch_ct_is_equal(const u32* a, const u32* b, size_t n, u8* flags, u8* status, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  ct_is_equal_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(a, b, n, flags, status);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ct_select(const u8* sel, const u32* i1, const u32* i2, size_t n, u32* out, u8* status, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  ct_select_kernel<<<blocks_for(n * 8, 256), 256, 0, stream>>>(sel, i1, i2, n, out, status);
+  return cudaGetLastError();
+}
+
 int tally_max_blocks(size_t n_ballots, int n_fields, int sm_count) {
   int rows = (TALLY_THREADS / 2) / n_fields;  // same for both layouts: 128 / (2 n_fields) == 64 / n_fields
   size_t need = (n_ballots + rows - 1) / rows;

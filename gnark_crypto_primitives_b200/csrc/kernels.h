@@ -109,6 +109,8 @@ cudaError_t launch_normalize(const u32* xyz, size_t n_points, u32* out, u8* stat
                              cudaStream_t stream);
 cudaError_t launch_ct_add(const u32* a, const u32* b, size_t n, u32* out_xyz, u8* status, int mont, cudaStream_t stream);
 cudaError_t launch_ct_neg(const u32* a, size_t n, u32* out, u8* status, cudaStream_t stream);
+cudaError_t launch_ct_is_equal(const u32* a, const u32* b, size_t n, u8* flags, u8* status, cudaStream_t stream);
+cudaError_t launch_ct_select(const u8* sel, const u32* i1, const u32* i2, size_t n, u32* out, u8* status, cudaStream_t stream);
 cudaError_t launch_encrypt_tally(const u32* tabG, const u32* tabPK, const u32* ks, const u32* ms, const u8* mask,
                                  size_t n_ballots, int n_fields, int n_blocks, u32* partials, u32* bad_count, u32* out_xyz, u8* status, int mont,
                                  cudaStream_t stream);

@@ -373,6 +373,27 @@ class Engine:
         self._check(self._lib.gcp_elgamal_neg(self._h, _ptr(aa), n, _ptr(out), _ptr(status), fmt))
         return out, status
 
+    def elgamal_is_equal(self, a, b):
+        """(*Ciphertext).IsEqual (elgamal/ciphertext.go:79-87): (n, 4, 32) x2 -> (flags (n,), status (n,))."""
+        aa = _as_elems(a, name="a").reshape(-1, 4, 32)
+        n = aa.shape[0]
+        bb = _as_elems(b, n * 4, "b").reshape(-1, 4, 32)
+        flags = np.empty(n, dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.gcp_elgamal_is_equal(self._h, _ptr(aa), _ptr(bb), n, _ptr(flags), _ptr(status)))
+        return flags, status
+
+    def elgamal_select(self, sel, i1, i2):
+        """(*Ciphertext).Select (elgamal/ciphertext.go:90-96): out = sel ? i1 : i2 -> ((n, 4, 32), status)."""
+        aa = _as_elems(i1, name="i1").reshape(-1, 4, 32)
+        n = aa.shape[0]
+        bb = _as_elems(i2, n * 4, "i2").reshape(-1, 4, 32)
+        ss = _u8(sel, n, "sel")
+        out = np.empty((n, 4, 32), dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.gcp_elgamal_select(self._h, _ptr(ss), _ptr(aa), _ptr(bb), n, _ptr(out), _ptr(status)))
+        return out, status
+
     def elgamal_tally(self, ct, fmt=FMT_CANONICAL):
         """Fold of Ciphertext.Add over ballots per field: (n_ballots, n_fields, 4, 32) -> ((n_fields, 4, 32), status)."""
         c = _as_elems(ct, name="ct")

@@ -184,6 +184,12 @@ int gcp_elgamal_add_dev(gcp_ctx* ctx, const void* d_a, const void* d_b, size_t n
                         int fmt, void* stream);
 /* (*Ciphertext).Neg (elgamal/ciphertext.go:37-46). */
 int gcp_elgamal_neg(gcp_ctx* ctx, const void* a, size_t n, void* out, uint8_t* status, int fmt);
+/* (*Ciphertext).IsEqual (elgamal/ciphertext.go:79-87): out_flags[i] = 1 iff the four coordinates of a[i] and b[i]
+ * agree; (*Ciphertext).Select (:90-96): out[i] = sel[i] ? i1[i] : i2[i], status 3 where sel[i] is not 0/1 (api.Select
+ * asserts a boolean).  Both work on either element format (they compare / copy canonical representations). */
+int gcp_elgamal_is_equal(gcp_ctx* ctx, const void* a, const void* b, size_t n, uint8_t* out_flags, uint8_t* status);
+int gcp_elgamal_select(gcp_ctx* ctx, const uint8_t* sel, const void* i1, const void* i2, size_t n, void* out,
+                       uint8_t* status);
 /* Tally: per field f, the fold of Ciphertext.Add over ct[0..n_ballots)[f] starting from NewCiphertext
  * (ciphertext.go:16-32).  ct: n_ballots x n_fields ciphertexts; out: n_fields ciphertexts; status: n_fields bytes.
  * Inputs must be curve points (outputs of Encrypt); the reduction order is unspecified, which is exact for group

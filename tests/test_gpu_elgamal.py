@@ -218,3 +218,30 @@ def test_field_edge_patterns_through_curve_arithmetic(engine):
     ok = st == 0
     assert ok.sum() > n // 2
     assert (out[ok] == want[ok]).all()
+
+
+def test_is_equal_and_select(engine):
+    """(*Ciphertext).IsEqual / Select (elgamal/ciphertext.go:79-96)."""
+    rng = random.Random(7996)
+    n = 300
+    a = np.frombuffer(bytes(rng.getrandbits(8) for _ in range(n * 128)), dtype=np.uint8).reshape(n, 4, 32).copy()
+    a[:, :, 31] &= 0x0F                                   # canonical
+    b = a.copy()
+    for i in range(0, n, 3):                              # every third differs in one byte of one coordinate
+        b[i, i % 4, (i * 7) % 31] ^= 1 << (i % 8)
+    flags, st = engine.elgamal_is_equal(a, b)
+    assert not st.any() and [int(f) for f in flags] == [0 if i % 3 == 0 else 1 for i in range(n)]
+    a2 = a.copy()
+    a2[5, 2] = np.frombuffer(int(R).to_bytes(32, "little"), np.uint8)   # non-canonical coordinate
+    flags, st = engine.elgamal_is_equal(a2, a2)
+    assert int(st[5]) == 1 and int(flags[5]) == 0 and int(flags[6]) == 1
+    sel = np.array([i % 2 for i in range(n)], np.uint8)
+    sel[9] = 2                                            # api.Select asserts a boolean
+    out, st = engine.elgamal_select(sel, a, b)
+    for i in range(n):
+        if i == 9:
+            assert int(st[i]) == 3 and not out[i].any()
+        else:
+            assert int(st[i]) == 0 and np.array_equal(out[i], a[i] if sel[i] else b[i]), i
+    out, st = engine.elgamal_select(np.zeros(0, np.uint8), np.zeros((0, 4, 32), np.uint8), np.zeros((0, 4, 32), np.uint8))
+    assert out.shape == (0, 4, 32)
