@@ -6,8 +6,10 @@
 // Errors of the reference ("bad inputs provided", ...) surface as gcp::Error; per-item assertion failures as status
 // bytes; flags as the gadget's 0/1 result.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
+#include <initializer_list>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -63,6 +65,45 @@ inline Batch MultiHash(const Engine& e, const uint8_t* inputs, int len, size_t n
   e.check(gcp_poseidon_multihash(e.raw(), inputs, len, n, b.values.data(), b.status.data(), fmt));
   return b;
 }
+// Batched mirror of the reference's stateful hasher (hash.Hash[T], hash/hash.go:9-18; poseidon.go:94-197): every
+// Write carries one column (n elements, one per row of the batch); a Write that would exceed 16 inputs in total is
+// dropped whole and silently (poseidon.go:103-108); Sum runs all rows on the GPU.
+class Hasher {
+ public:
+  Hasher(const Engine& e, size_t n_rows, int fmt = GCP_FMT_CANONICAL) : e_(e), n_(n_rows), fmt_(fmt) {}
+  void Write(std::initializer_list<const uint8_t*> columns) {
+    if (cols_.size() + columns.size() > 16) return;
+    for (const uint8_t* c : columns) cols_.emplace_back(c, c + n_ * 32);
+  }
+  void Reset() { cols_.clear(); }
+  bool WriteSucceeded() const { return !cols_.empty(); }
+  Batch Sum() const {
+    std::vector<uint8_t> rows(n_ * cols_.size() * 32);
+    for (size_t i = 0; i < n_; i++)
+      for (size_t j = 0; j < cols_.size(); j++)
+        std::copy(cols_[j].begin() + i * 32, cols_[j].begin() + (i + 1) * 32, rows.begin() + (i * cols_.size() + j) * 32);
+    return Hash(e_, rows.data(), (int)cols_.size(), n_, fmt_);  // no input: "bad inputs provided"
+  }
+  // flags[i] = 1 iff Sum()[i] == expected[i]
+  Batch SumIsEqual(const uint8_t* expected) const {
+    Batch b = Sum();
+    b.flags.resize(n_);
+    for (size_t i = 0; i < n_; i++)
+      b.flags[i] = b.status[i] == 0 && std::equal(b.values.begin() + i * 32, b.values.begin() + (i + 1) * 32, expected + i * 32);
+    return b;
+  }
+  void AssertSumIsEqual(const uint8_t* expected) const {
+    Batch b = SumIsEqual(expected);
+    for (size_t i = 0; i < n_; i++)
+      if (!b.flags[i]) throw Error(GCP_ERR_BAD_ARG, "AssertSumIsEqual failed for row " + std::to_string(i));
+  }
+
+ private:
+  const Engine& e_;
+  size_t n_;
+  int fmt_;
+  std::vector<std::vector<uint8_t>> cols_;
+};
 }  // namespace poseidon
 
 namespace smt {

@@ -69,6 +69,23 @@ int main() {
     gcp::Batch gv = grp.InclusionVerifier(3, 1, root.values.data(), false, sib, key, val);
     if (grp.size() != 1 || gv.flags[0] != 1 || gv.status[0] != 0) return 8;
   }
+  {  // stateful hasher mirror: Write / Sum / SumIsEqual (hash/hash.go:9-18)
+    uint8_t c1[32], c2[32];
+    put(c1, 1); put(c2, 2);
+    gcp::poseidon::Hasher hs(eng, 1);
+    if (hs.WriteSucceeded()) return 9;
+    hs.Write({c1, c2});
+    gcp::Batch d = hs.Sum();
+    uint8_t two[64];
+    memcpy(two, c1, 32); memcpy(two + 32, c2, 32);
+    gcp::Batch ref = gcp::poseidon::Hash(eng, two, 2, 1);
+    if (!hs.WriteSucceeded() || d.values != ref.values || hs.SumIsEqual(ref.values.data()).flags[0] != 1) return 10;
+    const uint8_t* seventeen[17];
+    for (int i = 0; i < 17; i++) seventeen[i] = c1;
+    hs.Write({c1, c1, c1, c1, c1, c1, c1, c1, c1, c1, c1, c1, c1, c1, c1});  // 2 + 15 > 16: dropped whole
+    if (hs.Sum().values != ref.values) return 11;
+    (void)seventeen;
+  }
   printf("cpp mirror ok\n");
   return 0;
 }
