@@ -21,6 +21,7 @@ import (
 	"unsafe"
 
 	"github.com/consensys/gnark-crypto/ecc/bn254/fr"
+	"github.com/vocdoni/gnark-crypto-primitives/tree/smt"
 )
 
 // Status bytes (per item): non-zero where the reference gadget would fail an assertion.
@@ -330,4 +331,49 @@ func (e *Engine) PoseidonHint(_ *big.Int, in, out []*big.Int) error {
 	}
 	digest[0].BigInt(out[0])
 	return nil
+}
+
+func setBig(e *fr.Element, v *big.Int) {
+	if v != nil {
+		e.SetBigInt(v)
+	}
+}
+
+// FromAssignments flattens the witness records the reference's wrappers produce (smt.Assignment,
+// tree/smt/wrapper.go:20-31; filled by WrapperArbo.Proof, wrapper_arbo.go:31-79) into the arrays BatchVerify takes:
+// Fnc0 = 0 is an inclusion proof of (NewKey, NewValue), Fnc0 = 1 an exclusion proof of NewKey against
+// (OldKey, OldValue, IsOld0) - the fnc input of smt.Verifier (verifier.go:102-111).
+func FromAssignments(as []smt.Assignment) *Proofs {
+	n := len(as)
+	if n == 0 {
+		return &Proofs{}
+	}
+	levels := len(as[0].Siblings)
+	p := &Proofs{Levels: levels, Roots: make([]fr.Element, n), Siblings: make([]fr.Element, n*levels),
+		OldKeys: make([]fr.Element, n), OldValues: make([]fr.Element, n), IsOld0: make([]byte, n),
+		Keys: make([]fr.Element, n), Values: make([]fr.Element, n), Fnc: make([]byte, n)}
+	for i := range as {
+		a := &as[i]
+		setBig(&p.Roots[i], a.OldRoot)
+		for j, s := range a.Siblings {
+			setBig(&p.Siblings[i*levels+j], s)
+		}
+		setBig(&p.OldKeys[i], a.OldKey)
+		setBig(&p.OldValues[i], a.OldValue)
+		setBig(&p.Keys[i], a.NewKey)
+		setBig(&p.Values[i], a.NewValue)
+		p.IsOld0[i], p.Fnc[i] = a.IsOld0, a.Fnc0
+	}
+	return p
+}
+
+// ProcessAssignments runs smt.Processor (tree/smt/processor.go:10) over state-transition records (WrapperArbo.Set /
+// SetProof, wrapper_arbo.go:97-184) and returns the recomputed new roots; compare them with Assignment.NewRoot.
+func (e *Engine) ProcessAssignments(as []smt.Assignment) (newRoots []fr.Element, status []byte, err error) {
+	p := FromAssignments(as)
+	fnc1 := make([]byte, len(as))
+	for i := range as {
+		fnc1[i] = as[i].Fnc1
+	}
+	return e.BatchProcess(p.Levels, p.Roots, p.Siblings, p.OldKeys, p.OldValues, p.IsOld0, p.Keys, p.Values, p.Fnc, fnc1)
 }
