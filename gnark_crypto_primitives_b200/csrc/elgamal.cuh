@@ -18,11 +18,15 @@
 namespace gcp {
 
 // Signed fixed windows: a scalar is recoded into FB_WINDOWS digits in [-2^(w-1)+1, 2^(w-1)]; the table holds the
-// positive multiples only (negating a Niels point is a swap and one field negation).  w = 14: 19 windows x 8192
-// entries x 96 B = 14.9 MB per base, so the tables of G and of the election key stay L2-resident (126 MB) while a
-// scalar multiplication costs 19 mixed additions (the reference's 4-bit table, mul.go:26-72, needs up to 63).
-constexpr int FB_WBITS = 14;
-constexpr int FB_WINDOWS = (256 + FB_WBITS - 1) / FB_WBITS;      // 19 (266 bits >= 254-bit scalars + recoding carry)
+// positive multiples only (negating a Niels point is a swap and one field negation).  w = 20: 13 windows x 524 288
+// entries x 96 B = 654 MB per base, resident in HBM (180 GB), so a scalar multiplication costs 13 mixed additions
+// (the reference's 4-bit table, mul.go:26-72, needs up to 63; the first version of this file used w = 14, 19
+// additions out of a 14.9 MB L2-resident table).  A lookup is one random 96-byte read: 27 of them per ciphertext,
+// ~0.8 TB/s at 290 M ciphertexts/s, an eighth of the HBM bandwidth, prefetched one window ahead so that its latency
+// hides behind the 7-multiply addition of the current window.  Building a table (6.8 M entries) takes ~0.1 s on the
+// device, once per context for G and once per election key.
+constexpr int FB_WBITS = 20;
+constexpr int FB_WINDOWS = (256 + FB_WBITS - 1) / FB_WBITS;      // 13 (260 bits >= 254-bit scalars + recoding carry)
 constexpr int FB_HALF = 1 << (FB_WBITS - 1);
 constexpr int FB_ENTRIES = FB_HALF;                              // digits 1 .. 2^(w-1)
 constexpr size_t FB_TABLE_WORDS = (size_t)FB_WINDOWS * FB_ENTRIES * 24;  // u32 words per table (96 B entries)
@@ -114,14 +118,29 @@ __global__ void fb_table_niels_kernel(const u32* __restrict__ ext, u32* __restri
 }
 
 // acc += [k] B using B's table; k is an integer < 2^254 (a canonical Fr element used as an integer)
+__device__ __forceinline__ void fb_digit(const u32 (&k)[8], int w, u32& carry, u32& d, bool& neg) {
+  u32 raw = scalar_window<FB_WBITS>(k, w) + carry;
+  neg = raw > (u32)FB_HALF;
+  d = neg ? ((1u << FB_WBITS) - raw) : raw;
+  carry = neg ? 1u : 0u;
+}
+
+__device__ __forceinline__ void fb_prefetch(const u32* e) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(e));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(e + 16));  // a 96-byte entry may straddle two 128-byte lines
+}
+
 __device__ __forceinline__ void fixed_base_accumulate(ExtPoint& acc, const u32 (&k)[8], const u32* __restrict__ tab) {
-  u32 carry = 0;
+  u32 carry = 0, d, dn = 0;
+  bool neg, negn = false;
+  fb_digit(k, 0, carry, d, neg);
+  if (d != 0) fb_prefetch(tab + (size_t)(d - 1) * 24);
 #pragma unroll 1
   for (int w = 0; w < FB_WINDOWS; w++) {
-    u32 raw = scalar_window<FB_WBITS>(k, w) + carry;
-    bool neg = raw > (u32)FB_HALF;
-    u32 d = neg ? ((1u << FB_WBITS) - raw) : raw;
-    carry = neg ? 1u : 0u;
+    if (w + 1 < FB_WINDOWS) {  // next window's entry is on its way while this window's addition runs
+      fb_digit(k, w + 1, carry, dn, negn);
+      if (dn != 0) fb_prefetch(tab + ((size_t)(w + 1) * FB_ENTRIES + (dn - 1)) * 24);
+    }
     if (d != 0) {
       NielsPoint n;
       const u32* e = tab + ((size_t)w * FB_ENTRIES + (d - 1)) * 24;
@@ -136,6 +155,8 @@ __device__ __forceinline__ void fixed_base_accumulate(ExtPoint& acc, const u32 (
       }
       ext_add_niels(acc, n);
     }
+    d = dn;
+    neg = negn;
   }
 }
 
