@@ -22,8 +22,8 @@ namespace gcp {
 // entries x 96 B = 654 MB per base, resident in HBM (180 GB), so a scalar multiplication costs 13 mixed additions
 // (the reference's 4-bit table, mul.go:26-72, needs up to 63; the first version of this file used w = 14, 19
 // additions out of a 14.9 MB L2-resident table).  A lookup is one random 96-byte read: 27 of them per ciphertext,
-// ~0.8 TB/s at 290 M ciphertexts/s, an eighth of the HBM bandwidth, prefetched one window ahead so that its latency
-// hides behind the 7-multiply addition of the current window.  Building a table (6.8 M entries) takes ~0.1 s on the
+// ~0.8 TB/s at 290 M ciphertexts/s, an eighth of the HBM bandwidth, staged one window ahead through shared memory (cp.async) so that its
+// latency hides behind the 7-multiply addition of the current window.  Building a table (6.8 M entries) takes ~0.1 s on the
 // device, once per context for G and once per election key.
 constexpr int FB_WBITS = 20;
 constexpr int FB_WINDOWS = (256 + FB_WBITS - 1) / FB_WBITS;      // 13 (260 bits >= 254-bit scalars + recoding carry)
@@ -125,39 +125,59 @@ __device__ __forceinline__ void fb_digit(const u32 (&k)[8], int w, u32& carry, u
   carry = neg ? 1u : 0u;
 }
 
-__device__ __forceinline__ void fb_prefetch(const u32* e) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(e));
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(e + 16));  // a 96-byte entry may straddle two 128-byte lines
+// Table entries are staged through shared memory with cp.async, one window ahead: the 96-byte read of window w+1
+// (a random HBM access: the 654 MB table does not live in L2, and a `prefetch` hint is dropped on a TLB miss - measured:
+// no effect) is in flight while the 7-multiply addition of window w runs, and costs no registers.  Slot layout
+// [buffer][16-byte piece][thread]: every cp.async / LDS.128 of a warp touches 32 consecutive 16-byte words.
+constexpr int FB_STAGE_THREADS = 128;  // every kernel that calls fixed_base_accumulate has at most 128 threads per block
+
+__device__ __forceinline__ void fb_stage_issue(uint4* stage, int buf, const u32* e) {
+#pragma unroll
+  for (int c = 0; c < 6; c++) {
+    unsigned saddr = (unsigned)__cvta_generic_to_shared(stage + (buf * 6 + c) * FB_STAGE_THREADS + threadIdx.x);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(e + c * 4) : "memory");
+  }
+}
+
+__device__ __forceinline__ void fb_stage_read(u32 (&a)[8], u32 (&b)[8], u32 (&c)[8], const uint4* stage, int buf) {
+  uint4 v[6];
+#pragma unroll
+  for (int q = 0; q < 6; q++) v[q] = stage[(buf * 6 + q) * FB_STAGE_THREADS + threadIdx.x];
+  a[0] = v[0].x; a[1] = v[0].y; a[2] = v[0].z; a[3] = v[0].w; a[4] = v[1].x; a[5] = v[1].y; a[6] = v[1].z; a[7] = v[1].w;
+  b[0] = v[2].x; b[1] = v[2].y; b[2] = v[2].z; b[3] = v[2].w; b[4] = v[3].x; b[5] = v[3].y; b[6] = v[3].z; b[7] = v[3].w;
+  c[0] = v[4].x; c[1] = v[4].y; c[2] = v[4].z; c[3] = v[4].w; c[4] = v[5].x; c[5] = v[5].y; c[6] = v[5].z; c[7] = v[5].w;
 }
 
 __device__ __forceinline__ void fixed_base_accumulate(ExtPoint& acc, const u32 (&k)[8], const u32* __restrict__ tab) {
+  __shared__ uint4 stage[2 * 6 * FB_STAGE_THREADS];  // 24 KB
   u32 carry = 0, d, dn = 0;
   bool neg, negn = false;
   fb_digit(k, 0, carry, d, neg);
-  if (d != 0) fb_prefetch(tab + (size_t)(d - 1) * 24);
+  if (d != 0) fb_stage_issue(stage, 0, tab + (size_t)(d - 1) * 24);
+  asm volatile("cp.async.commit_group;" ::: "memory");
 #pragma unroll 1
   for (int w = 0; w < FB_WINDOWS; w++) {
     if (w + 1 < FB_WINDOWS) {  // next window's entry is on its way while this window's addition runs
       fb_digit(k, w + 1, carry, dn, negn);
-      if (dn != 0) fb_prefetch(tab + ((size_t)(w + 1) * FB_ENTRIES + (dn - 1)) * 24);
+      if (dn != 0) fb_stage_issue(stage, (w + 1) & 1, tab + ((size_t)(w + 1) * FB_ENTRIES + (dn - 1)) * 24);
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but the group just committed has landed
     if (d != 0) {
       NielsPoint n;
-      const u32* e = tab + ((size_t)w * FB_ENTRIES + (d - 1)) * 24;
       if (neg) {  // -(x, y) = (-x, y): swaps y-x and y+x, negates 2dxy
-        load_fr(n.ypx, e);
-        load_fr(n.ymx, e + 8);
         u32 t[8];
-        load_fr(t, e + 16);
+        fb_stage_read(n.ypx, n.ymx, t, stage, w & 1);
         fr_neg(n.t2d, t);
       } else {
-        load_niels(n, e);
+        fb_stage_read(n.ymx, n.ypx, n.t2d, stage, w & 1);
       }
       ext_add_niels(acc, n);
     }
     d = dn;
     neg = negn;
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 __device__ __forceinline__ void store_ext_xyz(u32* o, const ExtPoint& p) {
