@@ -57,7 +57,9 @@ enum gcp_status {
 /* ---- context ------------------------------------------------------------------------------------ */
 int gcp_device_count(void);
 /* Loads the Poseidon tables (constants_path == NULL: the blob next to the library, data/poseidon_bn254.bin),
- * builds the fixed-base tables on the device, creates streams and staging pools. */
+ * builds the fixed-base table of G on the device, creates streams and staging pools.  A context keeps about 2.2 GB
+ * of device memory for the ElGamal tables (G and the cached election key: 13 windows x 2^19 entries x 96 B = 654 MB
+ * each, plus the build scratch) besides its grow-only staging buffers; creation takes ~0.2 s. */
 int gcp_ctx_create(int device, const char* constants_path, gcp_ctx** out);
 void gcp_ctx_destroy(gcp_ctx* ctx);
 const char* gcp_last_error(const gcp_ctx* ctx); /* ctx may be NULL: error of the last failed gcp_ctx_create */
