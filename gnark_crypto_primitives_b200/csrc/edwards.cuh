@@ -163,16 +163,70 @@ __device__ __forceinline__ void ext_add_cached(ExtPoint& p, const CachedPoint& q
   fr_mul(p.Z, f, g);
 }
 
-// One copy of each body per kernel (code size: an inlined doubling is ~24 KB of SASS, an addition ~27 KB; the
-// window loop calls them, see the note on instruction-cache misses in poseidon.cuh).
+// Code size decides these kernels: with the doubling (~26 KB of SASS) and the addition (~27 KB) inlined even once each,
+// ncu showed the window loop fetch-bound (stall_no_instruction 1.6-2.2 per issue, instruction-cache hit rate 74-78 %,
+// FMA-heavy pipe 59-63 %).  Here both are written over ONE out-of-line multiplier and ONE out-of-line squaring
+// (operands through local memory, L1-resident): the whole loop is a few KB.
+__device__ __noinline__ void fr_mul_call(u32* r, const u32* a, const u32* b) {
+  u32 x[8], y[8], z[8];
+#pragma unroll
+  for (int l = 0; l < 8; l++) {
+    x[l] = a[l];
+    y[l] = b[l];
+  }
+  fr_mul(z, x, y);
+#pragma unroll
+  for (int l = 0; l < 8; l++) r[l] = z[l];
+}
+__device__ __noinline__ void fr_sqr_call(u32* r, const u32* a) {
+  u32 x[8], z[8];
+#pragma unroll
+  for (int l = 0; l < 8; l++) x[l] = a[l];
+  fr_sqr(z, x);
+#pragma unroll
+  for (int l = 0; l < 8; l++) r[l] = z[l];
+}
+
 __device__ __noinline__ void ext_double_call(ExtPoint& p, bool with_t) {
-  if (with_t)
-    ext_double<true>(p);
-  else
-    ext_double<false>(p);
+  u32 a[8], b[8], c[8], e[8], f[8], g[8], h[8], t[8];
+  fr_sqr_call(a, p.X);
+  fr_sqr_call(b, p.Y);
+  fr_sqr_call(t, p.Z);
+  fr_add(c, t, t);
+  fr_add(t, p.X, p.Y);
+  fr_sqr_call(e, t);
+  fr_sub(e, e, a);
+  fr_sub(e, e, b);   // E = 2XY
+  fr_sub(g, b, a);   // G = -A + B  (a = -1)
+  fr_sub(f, g, c);   // F = G - C
+  fr_add(t, a, b);
+  fr_neg(h, t);      // H = -A - B
+  fr_mul_call(p.X, e, f);
+  fr_mul_call(p.Y, g, h);
+  if (with_t) fr_mul_call(p.T, e, h);
+  fr_mul_call(p.Z, f, g);
 }
 __device__ __noinline__ void ext_add_cached_call(ExtPoint& p, const CachedPoint& q, bool negate) {
-  ext_add_cached(p, q, negate);
+  u32 a[8], b[8], c[8], d[8], e[8], f[8], g[8], h[8], t[8], u[8];
+  fr_sub(t, p.Y, p.X);
+  fr_add(u, p.Y, p.X);
+  fr_mul_call(a, t, negate ? q.ypx : q.ymx);
+  fr_mul_call(b, u, negate ? q.ymx : q.ypx);
+  fr_mul_call(c, p.T, q.t2d);
+  fr_mul_call(d, p.Z, q.z2);
+  fr_sub(e, b, a);
+  fr_sub(t, d, c);
+  fr_add(u, d, c);
+#pragma unroll
+  for (int l = 0; l < 8; l++) {
+    f[l] = negate ? u[l] : t[l];
+    g[l] = negate ? t[l] : u[l];
+  }
+  fr_add(h, b, a);
+  fr_mul_call(p.X, e, f);
+  fr_mul_call(p.Y, g, h);
+  fr_mul_call(p.T, e, h);
+  fr_mul_call(p.Z, f, g);
 }
 
 // out = [k]base for an on-curve base and an integer k < 2^254 (little-endian words)
