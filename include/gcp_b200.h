@@ -69,8 +69,9 @@ uint64_t gcp_ctx_launch_count(const gcp_ctx* ctx);
 
 /* Page-locked host memory for the caller's flat arrays (cudaHostAlloc, portable across the devices of a group).
  * The host-buffer entry points accept any host pointer; from pinned memory their chunked copies run at full PCIe
- * rate and overlap the kernels (bench.py's e2e figure), from pageable memory (a Go heap slice) every copy is staged
- * by the driver.  A Go caller wraps the pointer with unsafe.Slice.  Free with gcp_host_free. */
+ * rate and overlap the kernels (bench.py's e2e figure); from pageable memory (a Go heap slice) copies of 64 MB and more
+ * are staged through the library's own page-locked ring by several host threads (about 4 % slower than page-locked
+ * sources).  A Go caller wraps the pointer with unsafe.Slice.  Free with gcp_host_free. */
 int gcp_host_alloc(size_t bytes, void** out);
 void gcp_host_free(void* p);
 

@@ -267,3 +267,27 @@ def test_pinned_host_buffers_give_the_same_results(engine):
     assert int(want[0][7]) == 0 and int(want[0].sum()) == n - 1
     empty = g.PinnedBuffer(0)
     empty.close()
+
+
+def test_large_pageable_input_takes_the_staged_copy_path(engine, monkeypatch):
+    """Host buffers of 64 MB and more in pageable memory are copied through the library's page-locked staging ring by
+    several host threads (capi.cu: h2d_copy).  Same results as the driver-staged path, bit for bit."""
+    rng = np.random.default_rng(64)
+    n_levels, n = 160, 16384                                  # 84 MB of siblings in one chunk
+    sib = rng.integers(0, 256, size=(n, n_levels, 32), dtype=np.uint8)
+    sib[:, :, 31] &= 0x0F
+    sib[:, n_levels - 1, :] = 0
+    keys = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    keys[:, 20:] = 0                                          # < 2^160
+    vals = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    vals[:, 31] &= 0x0F
+    zero_roots = np.zeros((n, 32), np.uint8)
+    _, st, roots = engine.smt_verify_inclusion(zero_roots, sib, keys, vals, want_roots=True)
+    assert not st.any()
+    roots[::5, 0] ^= 1                                        # every fifth proof gets a wrong root
+    staged = engine.smt_verify_inclusion(roots, sib, keys, vals, want_roots=True)
+    monkeypatch.setenv("GCP_B200_NO_STAGING", "1")
+    plain = engine.smt_verify_inclusion(roots, sib, keys, vals, want_roots=True)
+    for a, b in zip(staged, plain):
+        assert np.array_equal(a, b)
+    assert [int(f) for f in staged[0][:10]] == [0, 1, 1, 1, 1, 0, 1, 1, 1, 1] and not staged[1].any()
