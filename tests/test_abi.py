@@ -56,3 +56,20 @@ def test_header_is_plain_c(tmp_path):
     for compiler, std in (("gcc", "-std=c99"), ("g++", "-std=c++17")):
         subprocess.run([compiler, std, "-Wall", "-Wextra", "-Werror", "-pedantic", "-x", "c" if compiler == "gcc" else "c++",
                         f"-I{ROOT / 'include'}", "-c", str(src), "-o", str(tmp_path / "probe.o")], check=True)
+
+
+def test_group_and_host_alloc_are_loud_without_a_device():
+    import gnark_crypto_primitives_b200 as g
+    from gnark_crypto_primitives_b200 import _lib
+
+    lib = _lib.load()
+    if lib.gcp_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(g.EngineError) as e:
+        g.Group([0])
+    assert e.value.code == _lib.GCP_ERR_NO_DEVICE and "no CPU fallback" in str(e.value)
+    with pytest.raises(g.EngineError):
+        g.PinnedBuffer(64)
+    with pytest.raises(g.EngineError) as e:
+        g.Group([])
+    assert e.value.code == _lib.GCP_ERR_BAD_ARG
