@@ -174,8 +174,11 @@ int gcp_elgamal_fixed_base_mul(gcp_ctx* ctx, const void* scalars, size_t n, void
 int gcp_elgamal_fixed_base_mul_dev(gcp_ctx* ctx, const void* d_scalars, size_t n, void* d_out_points,
                                    uint8_t* d_status, int fmt, void* stream);
 /* (*Ciphertext).Encrypt (elgamal/encrypt.go:42-64): C1 = [k]G, C2 = [m]G + [k]pubKey.  m = 0 gives EncryptedZero
- * (encrypt.go:72-94).  pub_key: one point (pk_per_item = 0, the election key; its window table is cached in the
- * context) or n points.  status 4 where AssertIsOnCurve(pubKey) would fail.  out_ct: n x (C1.X, C1.Y, C2.X, C2.Y). */
+ * (encrypt.go:72-94).  pub_key: one point (pk_per_item = 0, the election key) or n points (pk_per_item = 1).  The
+ * shared-key form builds a 654 MB window table for the key on first use (~0.1 s, cached in the context until another
+ * key is used): it is meant for many ballots under one key; for a handful of encryptions per key use the per-item
+ * form (windowed variable-base multiplication, no table).  status 4 where AssertIsOnCurve(pubKey) would fail.
+ * out_ct: n x (C1.X, C1.Y, C2.X, C2.Y). */
 int gcp_elgamal_encrypt(gcp_ctx* ctx, const void* pub_key, int pk_per_item, const void* k, const void* m, size_t n,
                         void* out_ct, uint8_t* status, int fmt);
 int gcp_elgamal_encrypt_dev(gcp_ctx* ctx, const void* d_pub_key, int pk_per_item, const void* d_k, const void* d_m,
