@@ -1418,7 +1418,7 @@ int gcp_ballot_batch(gcp_ctx* ctx, int n_levels, size_t n_voters, const void* ro
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Decryption checks and coordinate conversion: host-buffer forms, one chunk
+// Decryption checks and coordinate conversion: host-buffer forms
 // ---------------------------------------------------------------------------------------------------
 namespace {
 struct Upload {
@@ -1437,6 +1437,39 @@ static int upload_all(gcp_ctx* ctx, const Upload* ins, int n_ins, size_t n, void
   return GCP_OK;
 }
 
+// Flag-producing per-item kernels from host buffers: chunks of 2^18 items alternate between the two streams, so the
+// copies of one chunk overlap the kernel of the other (large pageable sources go through h2d_copy's staging ring).
+extern "C++" {
+template <typename Launch>
+static int per_item_pipeline(gcp_ctx* ctx, const Upload* ins, int n_ins, size_t n, uint8_t* out_flags, uint8_t* status,
+                             const char* what, Launch launch) {
+  const size_t chunk = std::min<size_t>(n, (size_t)1 << 18);
+  size_t k = 0;
+  for (size_t off = 0; off < n; off += chunk, k++) {
+    const size_t m = std::min(chunk, n - off);
+    const int s = (int)(k & 1);
+    cudaStream_t st = ctx->stream[s];
+    const int base = s ? 86 : 70;
+    void* d[8];
+    for (int i = 0; i < n_ins; i++) {
+      d[i] = ctx->buf(base + i, m * ins[i].bytes_per_item);
+      if (!d[i]) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+      GCP_TRY(h2d_copy(ctx, d[i], (const char*)ins[i].host + off * ins[i].bytes_per_item, m * ins[i].bytes_per_item, st));
+    }
+    uint8_t* d_flags = (uint8_t*)ctx->buf(s ? 92 : 77, m);
+    uint8_t* d_status = (uint8_t*)ctx->buf(s ? 93 : 78, m);
+    if (!d_flags || !d_status) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+    CU(launch(d, m, d_flags, d_status, st), what);
+    ctx->launches++;
+    CU(cudaMemcpyAsync(out_flags + off, d_flags, m, cudaMemcpyDeviceToHost, st), "D2H");
+    CU(cudaMemcpyAsync(status + off, d_status, m, cudaMemcpyDeviceToHost, st), "D2H");
+  }
+  CU(cudaStreamSynchronize(ctx->stream[0]), "stream sync");
+  CU(cudaStreamSynchronize(ctx->stream[1]), "stream sync");
+  return GCP_OK;
+}
+}  // extern "C++"
+
 int gcp_elgamal_assert_decrypt(gcp_ctx* ctx, const void* ct, const void* priv_keys, const void* msgs, size_t n,
                                uint8_t* out_flags, uint8_t* status, int fmt) {
   if (!ctx) return GCP_ERR_BAD_ARG;
@@ -1446,20 +1479,11 @@ int gcp_elgamal_assert_decrypt(gcp_ctx* ctx, const void* ct, const void* priv_ke
   if (rc != GCP_OK || n == 0) return rc;
   if (!ct || !priv_keys || !msgs || !out_flags || !status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
   Upload ins[3] = {{ct, 128}, {priv_keys, 32}, {msgs, 32}};
-  void* d[3];
-  rc = upload_all(ctx, ins, 3, n, d);
-  if (rc != GCP_OK) return rc;
-  uint8_t* d_flags = (uint8_t*)ctx->buf(77, n);
-  uint8_t* d_status = (uint8_t*)ctx->buf(78, n);
-  if (!d_flags || !d_status) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
-  cudaStream_t st = ctx->stream[0];
-  CU(launch_assert_decrypt(ctx->d_tabG, (const u32*)d[0], (const u32*)d[1], (const u32*)d[2], n, d_flags, d_status, fmt, st),
-     "assert-decrypt kernel");
-  ctx->launches++;
-  CU(cudaMemcpyAsync(out_flags, d_flags, n, cudaMemcpyDeviceToHost, st), "D2H");
-  CU(cudaMemcpyAsync(status, d_status, n, cudaMemcpyDeviceToHost, st), "D2H");
-  CU(cudaStreamSynchronize(st), "stream sync");
-  return GCP_OK;
+  return per_item_pipeline(ctx, ins, 3, n, out_flags, status, "assert-decrypt kernel",
+                           [&](void** d, size_t m, uint8_t* d_flags, uint8_t* d_status, cudaStream_t st) {
+                             return launch_assert_decrypt(ctx->d_tabG, (const u32*)d[0], (const u32*)d[1], (const u32*)d[2], m,
+                                                          d_flags, d_status, fmt, st);
+                           });
 }
 
 int gcp_elgamal_verify_decryption_proof(gcp_ctx* ctx, const void* pub_keys, const void* ct, const void* msgs,
@@ -1472,21 +1496,12 @@ int gcp_elgamal_verify_decryption_proof(gcp_ctx* ctx, const void* pub_keys, cons
   if (rc != GCP_OK || n == 0) return rc;
   if (!pub_keys || !ct || !msgs || !a1 || !a2 || !z || !out_flags || !status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
   Upload ins[6] = {{pub_keys, 64}, {ct, 128}, {msgs, 32}, {a1, 64}, {a2, 64}, {z, 32}};
-  void* d[6];
-  rc = upload_all(ctx, ins, 6, n, d);
-  if (rc != GCP_OK) return rc;
-  uint8_t* d_flags = (uint8_t*)ctx->buf(77, n);
-  uint8_t* d_status = (uint8_t*)ctx->buf(78, n);
-  if (!d_flags || !d_status) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
-  cudaStream_t st = ctx->stream[0];
-  CU(launch_decryption_proof(ctx->d_tabG, ctx->tab[13], (const u32*)d[0], (const u32*)d[1], (const u32*)d[2], (const u32*)d[3],
-                             (const u32*)d[4], (const u32*)d[5], n, d_flags, d_status, fmt, st),
-     "decryption-proof kernel");
-  ctx->launches++;
-  CU(cudaMemcpyAsync(out_flags, d_flags, n, cudaMemcpyDeviceToHost, st), "D2H");
-  CU(cudaMemcpyAsync(status, d_status, n, cudaMemcpyDeviceToHost, st), "D2H");
-  CU(cudaStreamSynchronize(st), "stream sync");
-  return GCP_OK;
+  return per_item_pipeline(ctx, ins, 6, n, out_flags, status, "decryption-proof kernel",
+                           [&](void** d, size_t m, uint8_t* d_flags, uint8_t* d_status, cudaStream_t st) {
+                             return launch_decryption_proof(ctx->d_tabG, ctx->tab[13], (const u32*)d[0], (const u32*)d[1],
+                                                            (const u32*)d[2], (const u32*)d[3], (const u32*)d[4],
+                                                            (const u32*)d[5], m, d_flags, d_status, fmt, st);
+                           });
 }
 
 int gcp_eddsa_verify(gcp_ctx* ctx, const void* pub_keys_te, const void* sig_r_te, const void* sig_s, const void* msgs,
@@ -1498,21 +1513,11 @@ int gcp_eddsa_verify(gcp_ctx* ctx, const void* pub_keys_te, const void* sig_r_te
   if (rc != GCP_OK || n == 0) return rc;
   if (!pub_keys_te || !sig_r_te || !sig_s || !msgs || !out_flags || !status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
   Upload ins[4] = {{pub_keys_te, 64}, {sig_r_te, 64}, {sig_s, 32}, {msgs, 32}};
-  void* d[4];
-  rc = upload_all(ctx, ins, 4, n, d);
-  if (rc != GCP_OK) return rc;
-  uint8_t* d_flags = (uint8_t*)ctx->buf(77, n);
-  uint8_t* d_status = (uint8_t*)ctx->buf(78, n);
-  if (!d_flags || !d_status) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
-  cudaStream_t st = ctx->stream[0];
-  CU(launch_eddsa_verify(ctx->d_tabG, ctx->tab[6], (const u32*)d[0], (const u32*)d[1], (const u32*)d[2], (const u32*)d[3], n,
-                         d_flags, d_status, fmt, st),
-     "eddsa kernel");
-  ctx->launches++;
-  CU(cudaMemcpyAsync(out_flags, d_flags, n, cudaMemcpyDeviceToHost, st), "D2H");
-  CU(cudaMemcpyAsync(status, d_status, n, cudaMemcpyDeviceToHost, st), "D2H");
-  CU(cudaStreamSynchronize(st), "stream sync");
-  return GCP_OK;
+  return per_item_pipeline(ctx, ins, 4, n, out_flags, status, "eddsa kernel",
+                           [&](void** d, size_t m, uint8_t* d_flags, uint8_t* d_status, cudaStream_t st) {
+                             return launch_eddsa_verify(ctx->d_tabG, ctx->tab[6], (const u32*)d[0], (const u32*)d[1],
+                                                        (const u32*)d[2], (const u32*)d[3], m, d_flags, d_status, fmt, st);
+                           });
 }
 
 static int te_rte_host(gcp_ctx* ctx, const void* in, size_t n_points, void* out, uint8_t* status, int to_rte) {
