@@ -46,6 +46,11 @@ SIGNATURES = {
     "gcp_poseidon_multihash_dev": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_int, c_void_p]),
     "gcp_mimc7_hash": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_int]),
     "gcp_mimc7_hash_dev": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_int, c_void_p]),
+    "gcp_poseidon2_set_round_keys": (c_int, [c_void_p, c_void_p, c_size_t, c_int]),
+    "gcp_poseidon2_hash": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_int]),
+    "gcp_poseidon2_hash_dev": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_int, c_void_p]),
+    "gcp_poseidon2_permutation": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_int]),
+    "gcp_poseidon2_permutation_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_int, c_void_p]),
     "gcp_smt_verify": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     "gcp_smt_verify_dev": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -38,7 +38,7 @@ std::string library_dir() {
 
 struct gcp_ctx {
   int device = 0;
-  std::mutex mu;
+  std::recursive_mutex mu;  // recursive: host entry points hold it for the whole call and call the *_dev entry points
   std::string err;
   cudaStream_t stream[2] = {nullptr, nullptr};
   u32* d_tables = nullptr;
@@ -59,6 +59,8 @@ struct gcp_ctx {
   unsigned char pk_cached[64];
   int pk_cached_fmt = -1;     // -1: no key cached
   bool have_mimc7 = false;
+  u32* d_p2_keys = nullptr;   // 62 Poseidon2 round keys, Montgomery form (poseidon2.cuh)
+  bool have_p2_keys = false;
   // staging ring for large host->device copies from PAGEABLE memory (see h2d_copy)
   static constexpr int STAGE_SLOTS = 4;
   static constexpr size_t STAGE_BYTES = (size_t)32 << 20;
@@ -191,7 +193,7 @@ void gcp_ctx_destroy(gcp_ctx* ctx) {
     if (ctx->stage_buf[i]) cudaFreeHost(ctx->stage_buf[i]);
   }
   if (ctx->d_tables) cudaFree(ctx->d_tables);
-  for (u32* p : {ctx->d_tabG, ctx->d_tabPK, ctx->d_fb_ext, ctx->d_base_xy, ctx->d_flagG, ctx->d_flagPK})
+  for (u32* p : {ctx->d_tabG, ctx->d_tabPK, ctx->d_fb_ext, ctx->d_base_xy, ctx->d_flagG, ctx->d_flagPK, ctx->d_p2_keys})
     if (p) cudaFree(p);
   delete ctx;
 }
@@ -344,13 +346,37 @@ int gcp_ctx_create(int device, const char* constants_path, gcp_ctx** out) {
       }
     }
   }
+  // Poseidon2 (t = 2) round keys (data/poseidon2_bn254_t2.bin); optional, and replaceable with
+  // gcp_poseidon2_set_round_keys: without either the Poseidon2 entry points fail with GCP_ERR_CONSTANTS
+  {
+    if ((e = cudaMalloc(&ctx->d_p2_keys, 62 * 32)) != cudaSuccess) return bail(ctx->cuda_fail(e, "cudaMalloc Poseidon2 keys"));
+    std::string ppath = path;
+    size_t k = ppath.find_last_of('/');
+    ppath = (k == std::string::npos ? std::string("") : ppath.substr(0, k + 1)) + "poseidon2_bn254_t2.bin";
+    FILE* pf = fopen(ppath.c_str(), "rb");
+    if (pf) {
+      unsigned char pb[16 + 62 * 32];
+      size_t got = fread(pb, 1, sizeof(pb), pf);
+      fclose(pf);
+      uint32_t ph[4];
+      memcpy(ph, pb, 16);
+      if (got == sizeof(pb) && ph[0] == 0x32534F50u && ph[1] == 1 && ph[2] == 62) {
+        if ((e = cudaMemcpyAsync(ctx->d_p2_keys, pb + 16, 62 * 32, cudaMemcpyHostToDevice, ctx->stream[0])) != cudaSuccess ||
+            (e = launch_to_mont(ctx->d_p2_keys, 62, ctx->stream[0])) != cudaSuccess ||
+            (e = cudaStreamSynchronize(ctx->stream[0])) != cudaSuccess)
+          return bail(ctx->cuda_fail(e, "Poseidon2 round keys"));
+        ctx->launches++;
+        ctx->have_p2_keys = true;
+      }
+    }
+  }
   *out = ctx;
   return GCP_OK;
 }
 
 int gcp_probe_imad_wide(gcp_ctx* ctx, double* wide_mul_per_s) {
   if (!ctx || !wide_mul_per_s) return GCP_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   int sms = 0;
   CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device), "device attribute");
@@ -439,7 +465,7 @@ static int poseidon_multihash_dev_locked(gcp_ctx* ctx, const void* d_in, int len
 int gcp_poseidon_hash_dev(gcp_ctx* ctx, const void* d_in, int arity, size_t n, void* d_out, uint8_t* d_status, int fmt,
                           void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   return poseidon_hash_dev_locked(ctx, d_in, arity, n, d_out, d_status, fmt, (cudaStream_t)stream);
 }
@@ -447,7 +473,7 @@ int gcp_poseidon_hash_dev(gcp_ctx* ctx, const void* d_in, int arity, size_t n, v
 int gcp_poseidon_multihash_dev(gcp_ctx* ctx, const void* d_in, int len, size_t n, void* d_out, uint8_t* d_status,
                                int fmt, void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   return poseidon_multihash_dev_locked(ctx, d_in, len, n, d_out, d_status, fmt, (cudaStream_t)stream, 0);
 }
@@ -456,7 +482,7 @@ int gcp_poseidon_multihash_dev(gcp_ctx* ctx, const void* d_in, int len, size_t n
 static int poseidon_host(gcp_ctx* ctx, const void* in, int len, size_t n, void* out, uint8_t* status, int fmt,
                          bool multi) {
   if (!ctx) return GCP_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   if (len < 1 || len > (multi ? 4096 : 16))
     return ctx->fail(GCP_ERR_BAD_ARG, multi ? "the maximum number of inputs supported is 4096" : "bad inputs provided");
@@ -561,7 +587,7 @@ static int smt_verify_dev_locked(gcp_ctx* ctx, int n_levels, size_t n, const voi
 int gcp_smt_scan_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_siblings, uint16_t* d_lidx, uint8_t* d_info,
                      void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   if (n_levels < 2 || n_levels > 253) return ctx->fail(GCP_ERR_BAD_ARG, "n_levels must be in [2, 253]");
   if (n == 0) return GCP_OK;
@@ -578,7 +604,7 @@ int gcp_smt_verify_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_roots
                        const uint8_t* d_enabled, uint8_t* d_out_flags, uint8_t* d_out_status, void* d_out_roots,
                        int fmt, void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   return smt_verify_dev_locked(ctx, n_levels, n, d_roots, shared_root, d_siblings, d_old_keys, d_old_values, d_is_old0,
                                d_keys, d_values, d_fnc, d_enabled, d_out_flags, d_out_status, d_out_roots, fmt,
@@ -592,7 +618,7 @@ static int smt_verify_host(gcp_ctx* ctx, int n_levels, size_t n, const void* roo
                            const uint8_t* is_old0, const void* keys, const void* values, const uint8_t* fnc,
                            const uint8_t* enabled, uint8_t* out_flags, uint8_t* out_status, void* out_roots, int fmt) {
   if (!ctx) return GCP_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   const bool is_packed = siblings == nullptr;
   int rc = smt_check_args(ctx, n_levels, n, roots, is_packed ? (const void*)packed : siblings, old_keys, old_values, keys,
@@ -711,7 +737,7 @@ int gcp_smt_verify_packed(gcp_ctx* ctx, int n_levels, size_t n, const void* root
 int gcp_smt_unpack_siblings_dev(gcp_ctx* ctx, int n_levels, size_t n, const uint8_t* d_packed, size_t packed_bytes,
                                 const uint64_t* d_offsets, void* d_siblings, uint8_t* d_bad, int fmt, void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   if (n_levels < 2 || n_levels > 253) return ctx->fail(GCP_ERR_BAD_ARG, "n_levels must be in [2, 253]");
   if (fmt != GCP_FMT_CANONICAL && fmt != GCP_FMT_MONTGOMERY) return ctx->fail(GCP_ERR_BAD_ARG, "bad element format");
@@ -761,7 +787,7 @@ int gcp_smt_process_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_old_
                         const void* d_new_keys, const void* d_new_values, const uint8_t* d_fnc0, const uint8_t* d_fnc1,
                         void* d_new_roots, uint8_t* d_status, int fmt, void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   int rc = smt_process_check(ctx, n_levels, n, d_old_roots, d_siblings, d_old_keys, d_old_values, d_is_old0, d_new_keys,
                              d_new_values, d_fnc0, d_fnc1, d_new_roots, d_status, fmt);
@@ -793,8 +819,8 @@ static int smt_process_host(gcp_ctx* ctx, int n_levels, size_t n, const void* ol
                             const uint8_t* fnc0, const uint8_t* fnc1, void* new_roots, uint8_t* status, int fmt) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   const bool is_packed = siblings == nullptr;
+  std::lock_guard<std::recursive_mutex> call_lk(ctx->mu);  // the scratch slots belong to this call until it returns
   {
-    std::lock_guard<std::mutex> lk(ctx->mu);
     int rc = smt_process_check(ctx, n_levels, n, old_roots, is_packed ? (const void*)packed : siblings, old_keys,
                                old_values, is_old0, new_keys, new_values, fnc0, fnc1, new_roots, status, fmt);
     if (rc != GCP_OK || n == 0) return rc;
@@ -808,7 +834,6 @@ static int smt_process_host(gcp_ctx* ctx, int n_levels, size_t n, const void* ol
     uint8_t* d_b[4];
     uint8_t* d_bad = nullptr;
     {
-      std::lock_guard<std::mutex> lk(ctx->mu);
       CU(cudaSetDevice(ctx->device), "cudaSetDevice");
       d_sib = ctx->buf(10, m * sib_bytes);
       for (int q = 0; q < 5; q++) d_e[q] = ctx->buf(11 + q, m * 32);
@@ -841,7 +866,6 @@ static int smt_process_host(gcp_ctx* ctx, int n_levels, size_t n, const void* ol
     int rc = gcp_smt_process_dev(ctx, n_levels, m, d_e[0], d_sib, d_e[1], d_e[2], d_b[0], d_e[3], d_e[4], d_b[1], d_b[2],
                                  ctx->slot[16].p, d_b[3], fmt, ctx->stream[0]);
     if (rc != GCP_OK) return rc;
-    std::lock_guard<std::mutex> lk(ctx->mu);
     if (is_packed) {
       // a proof arbo.UnpackSiblings rejects never reaches the gadget: status 7, new root 0 (flags: the status array twice)
       CU(launch_smt_apply_bad(d_bad, m, d_b[3], d_b[3], (u32*)ctx->slot[16].p, ctx->stream[0]), "smt apply-bad kernel");
@@ -970,7 +994,7 @@ static int tally_dev_locked(gcp_ctx* ctx, const void* d_ct, size_t n_ballots, in
 int gcp_elgamal_fixed_base_mul_dev(gcp_ctx* ctx, const void* d_scalars, size_t n, void* d_out_points, uint8_t* d_status,
                                    int fmt, void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   return fixed_base_dev_locked(ctx, d_scalars, n, d_out_points, d_status, fmt, (cudaStream_t)stream, 43);
 }
@@ -978,7 +1002,7 @@ int gcp_elgamal_fixed_base_mul_dev(gcp_ctx* ctx, const void* d_scalars, size_t n
 int gcp_elgamal_encrypt_dev(gcp_ctx* ctx, const void* d_pub_key, int pk_per_item, const void* d_k, const void* d_m,
                             size_t n, void* d_out_ct, uint8_t* d_status, int fmt, void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   if (n && !pk_per_item) {
     if (!d_pub_key) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
@@ -991,7 +1015,7 @@ int gcp_elgamal_encrypt_dev(gcp_ctx* ctx, const void* d_pub_key, int pk_per_item
 int gcp_elgamal_add_dev(gcp_ctx* ctx, const void* d_a, const void* d_b, size_t n, void* d_out, uint8_t* d_status, int fmt,
                         void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   return add_dev_locked(ctx, d_a, d_b, n, d_out, d_status, fmt, (cudaStream_t)stream, 43);
 }
@@ -999,7 +1023,7 @@ int gcp_elgamal_add_dev(gcp_ctx* ctx, const void* d_a, const void* d_b, size_t n
 int gcp_elgamal_tally_dev(gcp_ctx* ctx, const void* d_ct, size_t n_ballots, int n_fields, void* d_out, uint8_t* d_status,
                           int fmt, void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   return tally_dev_locked(ctx, d_ct, n_ballots, n_fields, d_out, d_status, fmt, (cudaStream_t)stream, 44);
 }
@@ -1033,7 +1057,7 @@ int gcp_elgamal_encrypt_tally_dev(gcp_ctx* ctx, const void* d_pub_key, const voi
                                   size_t n_ballots, int n_fields, void* d_out, uint8_t* d_status, int fmt,
                                   void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   int rc = encrypt_tally_check(ctx, d_pub_key, d_k, d_m, n_ballots, n_fields, d_out, d_status, fmt);
   if (rc != GCP_OK) return rc;
@@ -1047,7 +1071,7 @@ int gcp_elgamal_encrypt_tally_dev(gcp_ctx* ctx, const void* d_pub_key, const voi
 int gcp_elgamal_encrypt_tally(gcp_ctx* ctx, const void* pub_key, const void* k, const void* m, size_t n_ballots,
                               int n_fields, void* out, uint8_t* status, int fmt) {
   if (!ctx) return GCP_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   int rc = encrypt_tally_check(ctx, pub_key, k, m, n_ballots, n_fields, out, status, fmt);
   if (rc != GCP_OK) return rc;
@@ -1110,7 +1134,7 @@ int gcp_elgamal_encrypt_tally(gcp_ctx* ctx, const void* pub_key, const void* k, 
 static int elgamal_host(gcp_ctx* ctx, int kind, const void* pk, int pk_per_item, const void* in0, const void* in1,
                         size_t n, void* out, uint8_t* status, int fmt) {
   if (!ctx) return GCP_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   int rc = check_fmt(ctx, fmt);
   if (rc != GCP_OK || n == 0) return rc;
@@ -1180,7 +1204,7 @@ int gcp_elgamal_neg(gcp_ctx* ctx, const void* a, size_t n, void* out, uint8_t* s
 static int ct_elementwise_host(gcp_ctx* ctx, int kind, const uint8_t* sel, const void* a, const void* b, size_t n, void* out,
                                uint8_t* status) {
   if (!ctx) return GCP_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   if (n == 0) return GCP_OK;
   if (!a || !b || !out || !status || (kind == 1 && !sel)) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
@@ -1227,7 +1251,7 @@ int gcp_elgamal_select(gcp_ctx* ctx, const uint8_t* sel, const void* i1, const v
 // ciphertexts are themselves tallied at the end (addition is associative, so the result does not depend on chunking).
 int gcp_elgamal_tally(gcp_ctx* ctx, const void* ct, size_t n_ballots, int n_fields, void* out, uint8_t* status, int fmt) {
   if (!ctx) return GCP_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   int rc = check_fmt(ctx, fmt);
   if (rc != GCP_OK) return rc;
@@ -1285,7 +1309,7 @@ int gcp_ballot_batch_dev(gcp_ctx* ctx, int n_levels, size_t n_voters, const void
                          const void* d_k, const void* d_m, int n_fields, uint8_t* d_flags, uint8_t* d_status,
                          void* d_tally, uint8_t* d_tally_status, int fmt, void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   cudaStream_t st = (cudaStream_t)stream;
   int rc = encrypt_tally_check(ctx, d_pub_key, d_k, d_m, n_voters, n_fields, d_tally, d_tally_status, fmt);
@@ -1307,7 +1331,7 @@ int gcp_ballot_batch(gcp_ctx* ctx, int n_levels, size_t n_voters, const void* ro
                      const void* pub_key, const void* k, const void* m, int n_fields, uint8_t* out_flags,
                      uint8_t* out_status, void* out_tally, uint8_t* out_tally_status, int fmt) {
   if (!ctx) return GCP_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   const bool is_packed = siblings == nullptr;
   const size_t n = n_voters;
@@ -1473,7 +1497,7 @@ static int per_item_pipeline(gcp_ctx* ctx, const Upload* ins, int n_ins, size_t 
 int gcp_elgamal_assert_decrypt(gcp_ctx* ctx, const void* ct, const void* priv_keys, const void* msgs, size_t n,
                                uint8_t* out_flags, uint8_t* status, int fmt) {
   if (!ctx) return GCP_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   int rc = check_fmt(ctx, fmt);
   if (rc != GCP_OK || n == 0) return rc;
@@ -1490,7 +1514,7 @@ int gcp_elgamal_verify_decryption_proof(gcp_ctx* ctx, const void* pub_keys, cons
                                         const void* a1, const void* a2, const void* z, size_t n, uint8_t* out_flags,
                                         uint8_t* status, int fmt) {
   if (!ctx) return GCP_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   int rc = check_fmt(ctx, fmt);
   if (rc != GCP_OK || n == 0) return rc;
@@ -1507,7 +1531,7 @@ int gcp_elgamal_verify_decryption_proof(gcp_ctx* ctx, const void* pub_keys, cons
 int gcp_eddsa_verify(gcp_ctx* ctx, const void* pub_keys_te, const void* sig_r_te, const void* sig_s, const void* msgs,
                      size_t n, uint8_t* out_flags, uint8_t* status, int fmt) {
   if (!ctx) return GCP_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   int rc = check_fmt(ctx, fmt);
   if (rc != GCP_OK || n == 0) return rc;
@@ -1522,7 +1546,7 @@ int gcp_eddsa_verify(gcp_ctx* ctx, const void* pub_keys_te, const void* sig_r_te
 
 static int te_rte_host(gcp_ctx* ctx, const void* in, size_t n_points, void* out, uint8_t* status, int to_rte) {
   if (!ctx) return GCP_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   if (n_points == 0) return GCP_OK;
   if (!in || !out || !status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
@@ -1555,7 +1579,7 @@ int gcp_rte_to_te(gcp_ctx* ctx, const void* points, size_t n_points, void* out, 
 int gcp_mimc7_hash_dev(gcp_ctx* ctx, const void* d_in, int len, size_t n, void* d_out, uint8_t* d_status, int fmt,
                        void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   int rc = check_fmt(ctx, fmt);
   if (rc != GCP_OK) return rc;
@@ -1573,8 +1597,8 @@ int gcp_mimc7_hash(gcp_ctx* ctx, const void* in, int len, size_t n, void* out, u
   void* d[1];
   uint8_t* d_status;
   void* d_out;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);  // held over upload, kernel and read-back: the slots are this call's
   {
-    std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->device), "cudaSetDevice");
     if (len < 1 || len > 62) return ctx->fail(GCP_ERR_BAD_ARG, "MiMC7 takes 1..62 inputs");
     if (n == 0) return GCP_OK;
@@ -1588,7 +1612,6 @@ int gcp_mimc7_hash(gcp_ctx* ctx, const void* in, int len, size_t n, void* out, u
   }
   int rc = gcp_mimc7_hash_dev(ctx, d[0], len, n, d_out, d_status, fmt, ctx->stream[0]);
   if (rc != GCP_OK) return rc;
-  std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaMemcpyAsync(out, d_out, n * 32, cudaMemcpyDeviceToHost, ctx->stream[0]), "D2H");
   CU(cudaMemcpyAsync(status, d_status, n, cudaMemcpyDeviceToHost, ctx->stream[0]), "D2H");
   CU(cudaStreamSynchronize(ctx->stream[0]), "stream sync");
@@ -1596,11 +1619,136 @@ int gcp_mimc7_hash(gcp_ctx* ctx, const void* in, int len, size_t n, void* out, u
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Poseidon2, width 2 (hash/native/bn254/poseidon2)
+// ---------------------------------------------------------------------------------------------------
+int gcp_poseidon2_set_round_keys(gcp_ctx* ctx, const void* keys, size_t n_keys, int fmt) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  int rc = check_fmt(ctx, fmt);
+  if (rc != GCP_OK) return rc;
+  if (!keys) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  if (n_keys != 62) return ctx->fail(GCP_ERR_BAD_ARG, "Poseidon2 (t=2, rF=6, rP=50) takes 62 round keys");
+  // every key must be < r in either format (fr.Element's invariant / SetBytes reduces)
+  static const uint64_t P[4] = {0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0xb85045b68181585dull, 0x30644e72e131a029ull};
+  for (size_t i = 0; i < n_keys; i++) {
+    uint64_t w[4];
+    memcpy(w, (const char*)keys + i * 32, 32);
+    bool lt = false;
+    for (int l = 3; l >= 0; l--) {
+      if (w[l] != P[l]) {
+        lt = w[l] < P[l];
+        break;
+      }
+    }
+    if (!lt) return ctx->fail(GCP_ERR_BAD_ARG, "Poseidon2 round key >= r");
+  }
+  cudaStream_t st = ctx->stream[0];
+  CU(cudaStreamSynchronize(ctx->stream[1]), "stream sync");
+  CU(cudaMemcpyAsync(ctx->d_p2_keys, keys, 62 * 32, cudaMemcpyHostToDevice, st), "H2D");
+  if (fmt == GCP_FMT_CANONICAL) {
+    CU(launch_to_mont(ctx->d_p2_keys, 62, st), "to_mont kernel");
+    ctx->launches++;
+  }
+  CU(cudaStreamSynchronize(st), "stream sync");
+  ctx->have_p2_keys = true;
+  return GCP_OK;
+}
+
+static int p2_check(gcp_ctx* ctx, int fmt) {
+  int rc = check_fmt(ctx, fmt);
+  if (rc != GCP_OK) return rc;
+  if (!ctx->have_p2_keys)
+    return ctx->fail(GCP_ERR_CONSTANTS,
+                     "Poseidon2 round keys missing (data/poseidon2_bn254_t2.bin not found and gcp_poseidon2_set_round_keys not called)");
+  return GCP_OK;
+}
+
+int gcp_poseidon2_hash_dev(gcp_ctx* ctx, const void* d_in, int len, size_t n, void* d_out, uint8_t* d_status, int fmt,
+                           void* stream) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  int rc = p2_check(ctx, fmt);
+  if (rc != GCP_OK) return rc;
+  if (len != 2 && len != 3) return ctx->fail(GCP_ERR_BAD_ARG, "poseidon2: need 2 or 3 limbs");  // native.go:31-33
+  if (n == 0) return GCP_OK;
+  if (!d_in || !d_out || !d_status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  CU(launch_poseidon2_hash(ctx->d_p2_keys, (const u32*)d_in, len, n, (u32*)d_out, d_status, fmt, (cudaStream_t)stream),
+     "poseidon2 hash kernel");
+  ctx->launches++;
+  return GCP_OK;
+}
+
+int gcp_poseidon2_permutation_dev(gcp_ctx* ctx, const void* d_in, size_t n, void* d_out, uint8_t* d_status, int fmt,
+                                  void* stream) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  int rc = p2_check(ctx, fmt);
+  if (rc != GCP_OK) return rc;
+  if (n == 0) return GCP_OK;
+  if (!d_in || !d_out || !d_status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  CU(launch_poseidon2_permutation(ctx->d_p2_keys, (const u32*)d_in, n, (u32*)d_out, d_status, fmt, (cudaStream_t)stream),
+     "poseidon2 permutation kernel");
+  ctx->launches++;
+  return GCP_OK;
+}
+
+// host buffers; out_elems = elements written per item (1 for the hash, 2 for the permutation), len = 0 selects the permutation
+static int p2_host(gcp_ctx* ctx, const void* in, int len, size_t n, void* out, uint8_t* status, int fmt) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  const bool perm = len == 0;
+  const size_t in_bytes = perm ? 64 : (size_t)len * 32, out_bytes = perm ? 64 : 32;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);  // held for the whole call: the scratch slots are this call's
+  {
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    int rc = p2_check(ctx, fmt);
+    if (rc != GCP_OK) return rc;
+    if (!perm && len != 2 && len != 3) return ctx->fail(GCP_ERR_BAD_ARG, "poseidon2: need 2 or 3 limbs");
+    if (n == 0) return GCP_OK;
+    if (!in || !out || !status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  }
+  const size_t chunk = (size_t)1 << 20;
+  size_t k = 0;
+  for (size_t off = 0; off < n; off += chunk, k++) {
+    const size_t m = std::min(chunk, n - off);
+    const int s = (int)(k & 1);
+    void *d_in, *d_out;
+    uint8_t* d_status;
+    {
+      d_in = ctx->buf(s ? 86 : 70, m * in_bytes);
+      d_out = ctx->buf(s ? 91 : 76, m * out_bytes);
+      d_status = (uint8_t*)ctx->buf(s ? 93 : 78, m);
+      if (!d_in || !d_out || !d_status) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+      GCP_TRY(h2d_copy(ctx, d_in, (const char*)in + off * in_bytes, m * in_bytes, ctx->stream[s]));
+    }
+    int rc = perm ? gcp_poseidon2_permutation_dev(ctx, d_in, m, d_out, d_status, fmt, ctx->stream[s])
+                  : gcp_poseidon2_hash_dev(ctx, d_in, len, m, d_out, d_status, fmt, ctx->stream[s]);
+    if (rc != GCP_OK) return rc;
+    CU(cudaMemcpyAsync((char*)out + off * out_bytes, d_out, m * out_bytes, cudaMemcpyDeviceToHost, ctx->stream[s]), "D2H");
+    CU(cudaMemcpyAsync(status + off, d_status, m, cudaMemcpyDeviceToHost, ctx->stream[s]), "D2H");
+  }
+  CU(cudaStreamSynchronize(ctx->stream[0]), "stream sync");
+  CU(cudaStreamSynchronize(ctx->stream[1]), "stream sync");
+  return GCP_OK;
+}
+
+int gcp_poseidon2_hash(gcp_ctx* ctx, const void* in, int len, size_t n, void* out, uint8_t* status, int fmt) {
+  if (ctx && len == 0) return ctx->fail(GCP_ERR_BAD_ARG, "poseidon2: need 2 or 3 limbs");
+  return p2_host(ctx, in, len, n, out, status, fmt);
+}
+
+int gcp_poseidon2_permutation(gcp_ctx* ctx, const void* in, size_t n, void* out, uint8_t* status, int fmt) {
+  return p2_host(ctx, in, 0, n, out, status, fmt);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Keccak address derivation
 // ---------------------------------------------------------------------------------------------------
 int gcp_keccak_address_dev(gcp_ctx* ctx, const void* d_pub_xy_be, size_t n, void* d_out_addr, void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   if (n == 0) return GCP_OK;
   if (!d_pub_xy_be || !d_out_addr) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
@@ -1611,7 +1759,7 @@ int gcp_keccak_address_dev(gcp_ctx* ctx, const void* d_pub_xy_be, size_t n, void
 
 int gcp_keccak_address(gcp_ctx* ctx, const void* pub_xy_be, size_t n, void* out_addr) {
   if (!ctx) return GCP_ERR_BAD_ARG;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   if (n == 0) return GCP_OK;
   if (!pub_xy_be || !out_addr) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");

@@ -8,6 +8,7 @@
 #include "keccak.cuh"
 #include "proofs.cuh"
 #include "mimc7.cuh"
+#include "poseidon2.cuh"
 #include "kernels.h"
 
 #include <algorithm>
@@ -433,6 +434,20 @@ cudaError_t upload_mimc7_constants(const u32* d_mont, cudaStream_t stream) {
 cudaError_t launch_mimc7(const u32* in, int len, size_t n, u32* out, u8* status, int mont, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
   mimc7_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(in, len, n, out, status, mont);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_poseidon2_hash(const u32* keys, const u32* in, int len, size_t n, u32* out, u8* status, int mont,
+                                  cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  poseidon2_hash_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(keys, in, len, n, out, status, mont);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_poseidon2_permutation(const u32* keys, const u32* in, size_t n, u32* out, u8* status, int mont,
+                                         cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  poseidon2_permutation_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(keys, in, n, out, status, mont);
   return cudaGetLastError();
 }
 

@@ -126,6 +126,10 @@ cudaError_t launch_eddsa_verify(const u32* tabG, const PoseidonTable& tab6, cons
                                 cudaStream_t stream);
 cudaError_t upload_mimc7_constants(const u32* d_mont, cudaStream_t stream);
 cudaError_t launch_mimc7(const u32* in, int len, size_t n, u32* out, u8* status, int mont, cudaStream_t stream);
+cudaError_t launch_poseidon2_hash(const u32* keys, const u32* in, int len, size_t n, u32* out, u8* status, int mont,
+                                  cudaStream_t stream);
+cudaError_t launch_poseidon2_permutation(const u32* keys, const u32* in, size_t n, u32* out, u8* status, int mont,
+                                         cudaStream_t stream);
 int tally_max_blocks(size_t n_ballots, int n_fields, int sm_count);
 cudaError_t launch_tally(const u32* ct, size_t n_ballots, int n_fields, int n_blocks, u32* partials, u32* bad_count,
                          u32* out_xyz, u8* status, int mont, cudaStream_t stream);

@@ -587,6 +587,44 @@ class Engine:
         self._check(self._lib.gcp_mimc7_hash_dev(self._h, _dptr(d_in), length, n, _dptr(d_out), _dptr(d_status), fmt,
                                                  self._stream(stream)))
 
+    # -- Poseidon2, width 2 -------------------------------------------------------------------------
+    def poseidon2_set_round_keys(self, keys, fmt=FMT_CANONICAL):
+        """Installs the 62 round keys of poseidon2.NewPermutation(2, 6, 50) (hash/native/bn254/poseidon2/native.go:27):
+        (62, 32) uint8 in round order.  A Go host passes gnark-crypto's own Parameters.RoundKeys."""
+        a = _as_elems(keys, name="keys").reshape(-1, 32)
+        self._check(self._lib.gcp_poseidon2_set_round_keys(self._h, _ptr(a), a.shape[0], fmt))
+
+    def poseidon2_hash(self, inputs, fmt=FMT_CANONICAL):
+        """HashPoseidon2.Hash / HashPoseidon2Gnark (hash/native/bn254/poseidon2/native.go:30-63, gnark.go:18-54):
+        (n, len, 32) with len 2 (node, ordered min/max) or 3 (leaf) -> ((n, 32), status)."""
+        a = _as_elems(inputs, name="inputs")
+        if a.ndim != 3:
+            raise ValueError("inputs must have shape (n, len, 32)")
+        n, ln = a.shape[0], a.shape[1]
+        out = np.empty((n, 32), dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.gcp_poseidon2_hash(self._h, _ptr(a), ln, n, _ptr(out), _ptr(status), fmt))
+        return out, status
+
+    def poseidon2_permutation(self, states, fmt=FMT_CANONICAL):
+        """perm2.Permutation (native.go:27,55): (n, 2, 32) -> ((n, 2, 32), status)."""
+        a = _as_elems(states, name="states")
+        if a.ndim != 3 or a.shape[1] != 2:
+            raise ValueError("states must have shape (n, 2, 32)")
+        n = a.shape[0]
+        out = np.empty((n, 2, 32), dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.gcp_poseidon2_permutation(self._h, _ptr(a), n, _ptr(out), _ptr(status), fmt))
+        return out, status
+
+    def poseidon2_hash_dev(self, d_in, length, n, d_out, d_status, fmt=FMT_CANONICAL, stream=None):
+        self._check(self._lib.gcp_poseidon2_hash_dev(self._h, _dptr(d_in), length, n, _dptr(d_out), _dptr(d_status), fmt,
+                                                     self._stream(stream)))
+
+    def poseidon2_permutation_dev(self, d_in, n, d_out, d_status, fmt=FMT_CANONICAL, stream=None):
+        self._check(self._lib.gcp_poseidon2_permutation_dev(self._h, _dptr(d_in), n, _dptr(d_out), _dptr(d_status), fmt,
+                                                            self._stream(stream)))
+
 
 class Group:
     """Several GPUs of one box behind one handle (gcp_group_*, include/gcp_b200.h): the single-process form a Go host

@@ -97,6 +97,51 @@ func (e *Engine) BatchMultiHash(in []fr.Element, length int) (out []fr.Element, 
 	return
 }
 
+// InstallPoseidon2Keys hands gnark-crypto's own round keys of poseidon2.NewPermutation(2, 6, 50)
+// (hash/native/bn254/poseidon2/native.go:27) to the engine and checks one permutation against gnark-crypto, so that the
+// width-2 Poseidon2 hasher is pinned to the library the reference links at start-up rather than to a restated key
+// derivation.  params is poseidon2.NewParameters(2, 6, 50) and perm is poseidon2.NewPermutation(2, 6, 50), both from
+// github.com/consensys/gnark-crypto/ecc/bn254/fr/poseidon2.
+func (e *Engine) InstallPoseidon2Keys(roundKeys [][]fr.Element, permute func([]fr.Element) error) error {
+	flat := make([]fr.Element, 0, 62)
+	for _, row := range roundKeys {
+		flat = append(flat, row...)
+	}
+	if err := e.err(C.gcp_poseidon2_set_round_keys(e.ctx, elemPtr(flat), C.size_t(len(flat)), C.GCP_FMT_MONTGOMERY)); err != nil {
+		return err
+	}
+	var in, want, got [2]fr.Element
+	in[0].SetUint64(1)
+	in[1].SetUint64(2)
+	want = in
+	if err := permute(want[:]); err != nil {
+		return err
+	}
+	status := make([]byte, 1)
+	if err := e.err(C.gcp_poseidon2_permutation(e.ctx, unsafe.Pointer(&in[0]), 1, unsafe.Pointer(&got[0]), bytePtr(status),
+		C.GCP_FMT_MONTGOMERY)); err != nil {
+		return err
+	}
+	if status[0] != 0 || !got[0].Equal(&want[0]) || !got[1].Equal(&want[1]) {
+		return errors.New("gcpb200: Poseidon2 permutation differs from gnark-crypto's")
+	}
+	return nil
+}
+
+// BatchPoseidon2 mirrors HashPoseidon2.Hash / utils.Poseidon2Hasher (hash/native/bn254/poseidon2/native.go:30,
+// utils/hashers.go:35) over len(in)/limbs rows: limbs = 2 is an internal node (ordered min, max), limbs = 3 a leaf
+// (key, value, flag).
+func (e *Engine) BatchPoseidon2(in []fr.Element, limbs int) (out []fr.Element, status []byte, err error) {
+	if (limbs != 2 && limbs != 3) || len(in)%limbs != 0 {
+		return nil, nil, fmt.Errorf("poseidon2: need 2 or 3 limbs, got %d", limbs)
+	}
+	n := len(in) / limbs
+	out, status = make([]fr.Element, n), make([]byte, n)
+	err = e.err(C.gcp_poseidon2_hash(e.ctx, elemPtr(in), C.int(limbs), C.size_t(n), elemPtr(out), bytePtr(status),
+		C.GCP_FMT_MONTGOMERY))
+	return
+}
+
 // Proofs is the flattened form of []smt.Assignment (tree/smt/wrapper.go:20-31): Siblings holds n*Levels elements,
 // root -> leaf, zero padded; Roots holds n elements or a single shared root.
 type Proofs struct {

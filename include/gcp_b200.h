@@ -96,6 +96,26 @@ int gcp_mimc7_hash(gcp_ctx* ctx, const void* in, int len, size_t n, void* out, u
 int gcp_mimc7_hash_dev(gcp_ctx* ctx, const void* d_in, int len, size_t n, void* d_out, uint8_t* d_status, int fmt,
                        void* stream);
 
+/* Poseidon2, width 2 (hash/native/bn254/poseidon2): the Merkle-Damgard hasher HashPoseidon2.Hash (native.go:30-63) and
+ * its gadget HashPoseidon2Gnark (gnark.go:18-54) over perm2 = poseidon2.NewPermutation(2, 6, 50) (native.go:27).
+ * len = 2: internal node, the two limbs are ordered (min, max) first (native.go:42-44, MinMaxHint hints.go:10-19);
+ * len = 3: leaf (key, value, flag); any other len -> GCP_ERR_BAD_ARG ("need 2 or 3 limbs", native.go:31-33).
+ * CV_0 = 0, CV_{i+1} = Permutation([CV_i, m_i])[1] + m_i, out = CV_len.  In GCP_FMT_CANONICAL a 32-byte value >= r is
+ * reduced mod r as SafeBigInt does (native.go:37-39; status stays 0); in GCP_FMT_MONTGOMERY it is status 1.
+ * The permutation lives in gnark-crypto (un-vendored) and the reference holds no vector for it: the 62 round keys
+ * (3 full rounds x 2, 50 partial rounds x 1, 3 full rounds x 2, in round order) are DATA.  A context starts with the
+ * keys of data/poseidon2_bn254_t2.bin (the published Keccak-chain derivation restated by oracle/poseidon2.py, parity
+ * unpinned); a Go host installs poseidon2.NewParameters(2, 6, 50).RoundKeys verbatim with gcp_poseidon2_set_round_keys
+ * (n_keys must be 62, every key < r) and can compare gcp_poseidon2_permutation with perm2.Permutation at start-up. */
+int gcp_poseidon2_set_round_keys(gcp_ctx* ctx, const void* keys, size_t n_keys, int fmt);
+int gcp_poseidon2_hash(gcp_ctx* ctx, const void* in, int len, size_t n, void* out, uint8_t* status, int fmt);
+int gcp_poseidon2_hash_dev(gcp_ctx* ctx, const void* d_in, int len, size_t n, void* d_out, uint8_t* d_status, int fmt,
+                           void* stream);
+/* perm2.Permutation on n states: in/out n x 2 elements. */
+int gcp_poseidon2_permutation(gcp_ctx* ctx, const void* in, size_t n, void* out, uint8_t* status, int fmt);
+int gcp_poseidon2_permutation_dev(gcp_ctx* ctx, const void* d_in, size_t n, void* d_out, uint8_t* d_status, int fmt,
+                                  void* stream);
+
 /* ---- SMT: tree/smt/verifier.go ------------------------------------------------------------------ */
 /* smt.Verifier (verifier.go:102-121) -> VerifierWithLeafHashFlag (:171-242), n proofs of n_levels siblings.
  *   roots: n elements, or 1 element when shared_root != 0

@@ -106,6 +106,30 @@ class Hasher {
 };
 }  // namespace poseidon
 
+namespace poseidon2 {
+// HashPoseidon2.Hash / HashPoseidon2Gnark (hash/native/bn254/poseidon2/native.go:30-63, gnark.go:18-54): n rows of 2
+// limbs (internal node, ordered min/max) or 3 limbs (leaf); any other count throws "need 2 or 3 limbs".
+inline Batch Hash(const Engine& e, const uint8_t* limbs, int len, size_t n, int fmt = GCP_FMT_CANONICAL) {
+  Batch b;
+  b.values.resize(n * 32);
+  b.status.resize(n);
+  e.check(gcp_poseidon2_hash(e.raw(), limbs, len, n, b.values.data(), b.status.data(), fmt));
+  return b;
+}
+// perm2.Permutation (native.go:27,55) on n states of two elements.
+inline Batch Permutation(const Engine& e, const uint8_t* states, size_t n, int fmt = GCP_FMT_CANONICAL) {
+  Batch b;
+  b.values.resize(n * 64);
+  b.status.resize(n);
+  e.check(gcp_poseidon2_permutation(e.raw(), states, n, b.values.data(), b.status.data(), fmt));
+  return b;
+}
+// Installs gnark-crypto's own round keys (62 elements in round order); see the header.
+inline void SetRoundKeys(const Engine& e, const uint8_t* keys, size_t n_keys, int fmt = GCP_FMT_CANONICAL) {
+  e.check(gcp_poseidon2_set_round_keys(e.raw(), keys, n_keys, fmt));
+}
+}  // namespace poseidon2
+
 namespace smt {
 inline Batch InclusionVerifier(const Engine& e, int n_levels, size_t n, const uint8_t* roots, bool shared_root,
                                const uint8_t* siblings, const uint8_t* keys, const uint8_t* values,

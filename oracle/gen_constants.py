@@ -99,6 +99,21 @@ def build_mimc_blob() -> bytes:
     return struct.pack("<4I", MIMC_MAGIC, 1, len(elems), 0) + b"".join(e.to_bytes(32, "little") for e in elems)
 
 
+P2_OUT = OUT.parent / "poseidon2_bn254_t2.bin"
+P2_MAGIC = 0x32534F50  # 'POS2'
+
+
+def build_poseidon2_blob() -> bytes:
+    """Round keys of poseidon2.NewPermutation(2, 6, 50) (hash/native/bn254/poseidon2/native.go:27) as derived by
+    oracle/poseidon2.py::round_keys (gnark-crypto's published Keccak chain; PARITY UNPINNED - no vector in the reference).
+    Layout: u32 magic 'POS2', u32 version=1, u32 n=62, u32 reserved, then 62 x 32-byte little-endian elements in round
+    order (3 full rounds x 2 keys, 50 partial rounds x 1 key, 3 full rounds x 2 keys)."""
+    from oracle import poseidon2
+    flat = poseidon2.flat_round_keys()
+    assert len(flat) == 62 and all(0 <= k < R for k in flat)
+    return struct.pack("<4I", P2_MAGIC, 1, len(flat), 0) + b"".join(k.to_bytes(32, "little") for k in flat)
+
+
 def main():
     blob = build_blob(load_reference_tables())
     OUT.parent.mkdir(parents=True, exist_ok=True)
@@ -107,6 +122,9 @@ def main():
     mblob = build_mimc_blob()
     MIMC_OUT.write_bytes(mblob)
     print(f"wrote {MIMC_OUT} ({len(mblob)} bytes, sha256 {hashlib.sha256(mblob).hexdigest()})")
+    pblob = build_poseidon2_blob()
+    P2_OUT.write_bytes(pblob)
+    print(f"wrote {P2_OUT} ({len(pblob)} bytes, sha256 {hashlib.sha256(pblob).hexdigest()})")
 
 
 if __name__ == "__main__":

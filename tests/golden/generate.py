@@ -22,6 +22,7 @@ from oracle import edwards as ed  # noqa: E402
 from oracle import elgamal as eg  # noqa: E402
 from oracle import keccak  # noqa: E402
 from oracle import mimc7  # noqa: E402
+from oracle import poseidon2  # noqa: E402
 from oracle import poseidon as pos  # noqa: E402
 from oracle import smt  # noqa: E402
 from oracle.field import R  # noqa: E402
@@ -214,6 +215,22 @@ def mimc7_section(rng):
     return out
 
 
+def poseidon2_section(rng):
+    """Width-2 Poseidon2 hasher (hash/native/bn254/poseidon2): outputs of oracle/poseidon2.py - PARITY UNPINNED (the round
+    keys are restated from gnark-crypto's published derivation, no vector exists in the reference).  The keys are stored
+    so that a Go-side check can compare them with poseidon2.NewParameters(2, 6, 50).RoundKeys directly."""
+    rows = [[0, 0], [1, 2], [2, 1], [R - 1, 0], [1, 2, 1], [0, 0, 0]]
+    rows += [[rng.randrange(R) for _ in range(2 + i % 2)] for i in range(6)]
+    states = [[0, 0], [0, 1], [1, 2], [rng.randrange(R), rng.randrange(R)]]
+    return {
+        "source": "oracle (unpinned)",
+        "seed": poseidon2.seed_string(),
+        "round_keys": [S(k) for k in poseidon2.flat_round_keys()],
+        "permutation": [{"in": [S(x) for x in st], "out": [S(x) for x in poseidon2.permutation(st)]} for st in states],
+        "hash": [{"in": [S(x) for x in r], "out": S(poseidon2.hash(r))} for r in rows],
+    }
+
+
 def main():
     rng = random.Random(0xB200)
     doc = {
@@ -224,6 +241,7 @@ def main():
         "eddsa": eddsa_section(rng),
         "keccak_address": keccak_section(rng),
         "mimc7": mimc7_section(rng),
+        "poseidon2": poseidon2_section(rng),
     }
     path = Path(__file__).resolve().parent / "vectors.json"
     path.write_text(json.dumps(doc, indent=0, sort_keys=True) + "\n")

@@ -24,6 +24,7 @@ def test_fixture_file_is_reproducible_from_the_oracle():
     assert gen.eddsa_section(rng) == doc["eddsa"]
     assert gen.keccak_section(rng) == doc["keccak_address"]
     assert gen.mimc7_section(rng) == doc["mimc7"]
+    assert gen.poseidon2_section(rng) == doc["poseidon2"]
 
 
 def test_reference_entries_carry_the_published_values():

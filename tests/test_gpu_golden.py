@@ -137,3 +137,13 @@ def test_eddsa_keccak_mimc7_vectors(engine):
     for e in DOC["mimc7"]:
         out, st = engine.mimc7_hash(elems(I(e["in"])).reshape(1, len(e["in"]), 32))
         assert int(st[0]) == 0 and ints(out)[0] == int(e["out"])
+
+
+def test_poseidon2_vectors(engine):
+    p2 = DOC["poseidon2"]
+    for e in p2["hash"]:
+        out, st = engine.poseidon2_hash(elems(I(e["in"])).reshape(1, len(e["in"]), 32))
+        assert int(st[0]) == 0 and ints(out)[0] == int(e["out"])
+    states = elems([int(x) for e in p2["permutation"] for x in e["in"]]).reshape(-1, 2, 32)
+    out, st = engine.poseidon2_permutation(states)
+    assert not st.any() and ints(out) == [int(x) for e in p2["permutation"] for x in e["out"]]

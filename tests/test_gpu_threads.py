@@ -47,3 +47,59 @@ def test_two_contexts_on_one_device():
     with g.Engine(0) as a, g.Engine(0) as b:
         x = elems([1, 2]).reshape(1, 2, 32)
         assert ints(a.poseidon_hash(x)[0]) == ints(b.poseidon_hash(x)[0]) == [opos.hash([1, 2])]
+
+
+def test_host_entry_points_keep_their_scratch_for_the_whole_call(engine):
+    """gcp_mimc7_hash and gcp_smt_process used to drop the context lock between upload, kernel and read-back, so two
+    threads on one context could overwrite (or, on a re-allocation, free) each other's device buffers."""
+    import numpy as np
+
+    from oracle import mimc7 as omimc
+    from oracle import smt as osmt
+
+    rng = random.Random(123)
+    batches = []
+    for size in (7, 300, 4000):                     # different sizes: the scratch slots are re-allocated across calls
+        rows = [[rng.randrange(R) for _ in range(3)] for _ in range(size)]
+        batches.append((elems([x for r in rows for x in r]).reshape(size, 3, 32), rows))
+    want_m = [[omimc.hash(r) for r in rows[:5]] for _, rows in batches]
+
+    n_levels = 24
+    tree = osmt.Tree(n_levels)
+    cases = []
+    for _ in range(24):
+        k, v = rng.getrandbits(n_levels), rng.randrange(R)
+        p = tree.gen_proof(k)
+        if p["exists"]:
+            continue
+        cases.append(dict(old_root=tree.root(), siblings=p["siblings"], old_key=p["old_key"], old_value=p["old_value"],
+                          is_old0=p["is_old0"], new_key=k, new_value=v, fnc0=1, fnc1=0))
+        tree.add(k, v)
+    n = len(cases)
+    pargs = (elems(c["old_root"] for c in cases), elems([s for c in cases for s in c["siblings"]]).reshape(n, n_levels, 32),
+             elems(c["old_key"] for c in cases), elems(c["old_value"] for c in cases),
+             np.array([c["is_old0"] for c in cases], np.uint8), elems(c["new_key"] for c in cases),
+             elems(c["new_value"] for c in cases), np.array([c["fnc0"] for c in cases], np.uint8),
+             np.array([c["fnc1"] for c in cases], np.uint8))
+    want_roots = [c["old_root"] for c in cases[1:]] + [tree.root()]
+    errors = []
+
+    def worker(kind):
+        try:
+            for it in range(12):
+                if kind < 3:
+                    arr, _ = batches[(kind + it) % 3]
+                    out, st = engine.mimc7_hash(arr)
+                    assert not st.any() and ints(out[:5]) == want_m[(kind + it) % 3]
+                else:
+                    roots, st = engine.smt_process(*pargs)
+                    assert not st.any() and ints(roots) == want_roots
+        except Exception as exc:
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker, args=(i % 4,)) for i in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[0]

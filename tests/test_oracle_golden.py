@@ -263,3 +263,38 @@ def test_mimc7_public_iden3_vectors():
         18226366069841799622585958305961373004333097209608110160936134895615261821931
     assert mimc7.hash([1] * 63) == 0          # mimc.go:33-38: more than 62 inputs are dropped
     assert len(mimc7.constants()) == 91 and mimc7.constants()[0] == 0
+
+
+def test_poseidon2_wrapper_semantics_and_key_blob():
+    """hash/native/bn254/poseidon2: the permutation is un-vendored (PARITY UNPINNED, oracle/poseidon2.py header); what the
+    reference's own lines fix is the wrapper - arity, mod-r reduction, min/max order, the chaining rule - and that is
+    checked here, together with the committed key blob being the oracle's derivation."""
+    import struct
+    from pathlib import Path
+
+    from oracle import poseidon2 as p2
+    from oracle.field import R
+
+    with pytest.raises(ValueError):
+        p2.hash([1])                                       # native.go:31-33
+    with pytest.raises(ValueError):
+        p2.hash([1, 2, 3, 4])
+    assert p2.hash([1, 2]) == p2.hash([2, 1])              # native.go:42-44, hints.go:10-19
+    assert p2.hash([1, 2, 1]) != p2.hash([2, 1, 1])        # leaves keep their order
+    assert p2.hash([R + 1, 2]) == p2.hash([1, 2])          # native.go:37-39 (SafeBigInt)
+    # chaining rule native.go:47-61 written out for a leaf
+    cv = 0
+    for m in (11, 22, 1):
+        cv = (p2.permutation([cv, m])[1] + m) % R
+    assert p2.hash([11, 22, 1]) == cv
+    # the permutation is a bijection built from invertible layers: distinct inputs, distinct outputs; 0 is not fixed
+    outs = {tuple(p2.permutation([a, b])) for a in range(4) for b in range(4)}
+    assert len(outs) == 16 and (0, 0) not in outs
+    keys = p2.round_keys()
+    assert [len(r) for r in keys] == [2] * 3 + [1] * 50 + [2] * 3 and len(p2.flat_round_keys()) == 62
+    assert p2.unflatten(p2.flat_round_keys()) == keys
+    assert p2.seed_string() == "Poseidon2-BN254[t=2,rF=6,rP=50,d=5]"
+    blob = (Path(__file__).resolve().parent.parent / "gnark_crypto_primitives_b200" / "data" /
+            "poseidon2_bn254_t2.bin").read_bytes()
+    assert struct.unpack_from("<4I", blob) == (0x32534F50, 1, 62, 0)
+    assert [int.from_bytes(blob[16 + 32 * i:48 + 32 * i], "little") for i in range(62)] == p2.flat_round_keys()
