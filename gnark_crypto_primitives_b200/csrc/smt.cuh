@@ -332,10 +332,10 @@ __global__ void __launch_bounds__(SMT_WARPS * 32) smt_path_kernel(SmtArgs a, con
 #pragma unroll
   for (int l = 0; l < 8; l++) root_c[l] = 0;
   if (st == GCP_STATUS_OK) {
-    if (en == 0u) {
+    if (!canon) {
+      st = GCP_STATUS_NONCANONICAL;  // a sibling >= r is not a field element, whatever the selectors say
+    } else if (en == 0u) {
       flag = 1;  // every check bypassed; level[0] = 0
-    } else if (!canon) {
-      st = GCP_STATUS_NONCANONICAL;
     } else {
       if (a.mont) {
 #pragma unroll

@@ -291,3 +291,56 @@ def test_large_pageable_input_takes_the_staged_copy_path(engine, monkeypatch):
     for a, b in zip(staged, plain):
         assert np.array_equal(a, b)
     assert [int(f) for f in staged[0][:10]] == [0, 1, 1, 1, 1, 0, 1, 1, 1, 1] and not staged[1].any()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_differential_over_levels_paths_and_selectors(engine, seed):
+    """Seeded differential run against the literal gadget oracle: random n_levels in [2, 253] (not multiples of the path
+    kernel's 4-level staging chunk), every path length from 0 to n-1 mixed in ONE batch (the length sort and the warp
+    grouping see ragged neighbours), interior zero siblings, all selector values incl. non-boolean ones, keys at and past
+    2^n, elements at and past r, and correct as well as corrupted roots."""
+    rng = random.Random(1000 + seed)
+    n_levels = rng.choice([2, 5, 7, 9, 13, 17, 29, 41, 67, 101, 163, 253][seed - 1::3])
+    cases = []
+    for i in range(140):
+        L = rng.choice([0, 1, n_levels - 1, rng.randrange(n_levels), min(n_levels - 1, rng.randrange(8))])
+        sib = [0 if rng.random() < 0.15 else rng.randrange(1, R) for _ in range(L)] + [0] * (n_levels - L)
+        if L:
+            sib[L - 1] = rng.randrange(1, R)
+        key = rng.getrandbits(n_levels)
+        value = rng.randrange(R)
+        fnc, is0, enabled = rng.choice([0, 0, 1]), rng.choice([0, 0, 1]), rng.choice([1, 1, 1, 0])
+        same = rng.random() < 0.3
+        old_key = key if same else rng.getrandbits(n_levels)
+        old_value = value if same else rng.randrange(R)
+        # the root the state machine accepts for these selectors: fold from the leaf it injects
+        if fnc == 0:
+            root = osmt.fold_inclusion(sib, key, value)
+        elif is0:
+            root = osmt.verifier(1, 0, sib, old_key, old_value, 1, key, value, 1)[2]
+        else:
+            root = osmt.verifier(1, 0, sib, old_key, old_value, 0, key, value, 1)[2]
+        c = dict(enabled=enabled, root=root, siblings=sib, old_key=old_key, old_value=old_value, is_old0=is0, key=key,
+                 value=value, fnc=fnc)
+        mut = rng.randrange(12)
+        if mut == 0:
+            c["root"] = (root + 1) % R
+        elif mut == 1:
+            c["siblings"] = sib[:-1] + [rng.randrange(1, R)]            # siblings[n-1] != 0
+        elif mut == 2:
+            c["key"] = key | (1 << n_levels)                             # lowBits assertion
+        elif mut == 3:
+            c[rng.choice(["is_old0", "fnc", "enabled"])] = rng.choice([2, 3, 255])
+        elif mut == 4:
+            c[rng.choice(["root", "value", "old_value", "old_key"])] = rng.choice([R, R + 1, 2**256 - 1])
+        elif mut == 5 and n_levels > 2:
+            j = rng.randrange(n_levels - 1)
+            c["siblings"] = sib[:j] + [rng.choice([R, 2**256 - 1])] + sib[j + 1:]
+        elif mut == 6 and L:
+            j = rng.randrange(L)
+            c["siblings"] = sib[:j] + [(sib[j] + 1) % R] + sib[j + 1:]
+        cases.append(c)
+    flags, status, roots, want = run_general(engine, cases, n_levels)
+    for i, w in enumerate(want):
+        assert (int(flags[i]), int(status[i]), roots[i]) == w, (n_levels, i, cases[i])
+    assert len({w[:2] for w in want}) >= 4        # the batch really mixes flag/status outcomes

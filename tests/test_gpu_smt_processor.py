@@ -131,3 +131,43 @@ def test_packed_proofs_give_the_dense_results(engine):
     assert [(r, s) for r, s in zip(got_roots[:n - 1], got_status[:n - 1])] == want[:n - 1]
     assert got_status[-1] == osmt.STATUS_MALFORMED and got_roots[-1] == 0
     assert all(s == 0 for s in got_status[:n - 1])
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_random_differential_with_mutations(engine, seed):
+    """Seeded differential run against the literal oracle: transitions of a growing tree at an odd level count, each
+    with a random function code and a random mutation (selectors outside {0,1}, elements at and past r, keys past 2^n,
+    wrong old roots, swapped or corrupted siblings, siblings[n-1] != 0)."""
+    rng = random.Random(4000 + seed)
+    n_levels = [19, 45][seed - 1]
+    tree = osmt.Tree(n_levels)
+    cases = []
+    for step in range(60):
+        k = rng.getrandbits(n_levels)
+        v = rng.randrange(R)
+        p = tree.gen_proof(k)
+        c = dict(old_root=tree.root(), siblings=list(p["siblings"]), old_key=p["old_key"], old_value=p["old_value"],
+                 is_old0=p["is_old0"], new_key=k, new_value=v, fnc0=rng.choice([0, 1, 1]), fnc1=rng.choice([0, 0, 1]))
+        if not p["exists"]:
+            tree.add(k, v)
+        mut = rng.randrange(10)
+        if mut == 0:
+            c[rng.choice(["fnc0", "fnc1", "is_old0"])] = rng.choice([2, 7, 255])
+        elif mut == 1:
+            c[rng.choice(["old_root", "old_value", "new_value", "old_key", "new_key"])] = rng.choice([R, R + 3, 2**256 - 1])
+        elif mut == 2:
+            c[rng.choice(["old_key", "new_key"])] |= 1 << n_levels
+        elif mut == 3:
+            c["old_root"] = (c["old_root"] + 1) % R
+        elif mut == 4:
+            c["siblings"][n_levels - 1] = rng.randrange(1, R)
+        elif mut == 5:
+            j = rng.randrange(n_levels - 1)
+            c["siblings"][j] = rng.choice([R, (c["siblings"][j] + 1) % R, 0])
+        elif mut == 6:
+            c["is_old0"] ^= 1
+        cases.append(c)
+    roots, status, want = run(engine, cases, n_levels)
+    for i, w in enumerate(want):
+        assert (roots[i], status[i]) == w, (i, cases[i])
+    assert len({s for _, s in want}) >= 3
