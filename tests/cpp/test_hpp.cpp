@@ -86,6 +86,23 @@ int main() {
     if (hs.Sum().values != ref.values) return 11;
     (void)seventeen;
   }
+  {  // width-2 Poseidon2 hasher: a node is ordered (min, max), a leaf is not; wrong arity throws the reference's text
+    uint8_t ab[64], ba[64], leaf_ab[96], leaf_ba[96], one[32];
+    put(ab, 5); put(ab + 32, 9); put(ba, 9); put(ba + 32, 5); put(one, 1);
+    memcpy(leaf_ab, ab, 64); memcpy(leaf_ab + 64, one, 32);
+    memcpy(leaf_ba, ba, 64); memcpy(leaf_ba + 64, one, 32);
+    gcp::Batch n1 = gcp::poseidon2::Hash(eng, ab, 2, 1), n2 = gcp::poseidon2::Hash(eng, ba, 2, 1);
+    gcp::Batch l1 = gcp::poseidon2::Hash(eng, leaf_ab, 3, 1), l2 = gcp::poseidon2::Hash(eng, leaf_ba, 3, 1);
+    if (n1.status[0] != 0 || n1.values != n2.values || l1.values == l2.values) return 12;
+    gcp::Batch pm = gcp::poseidon2::Permutation(eng, ab, 1);
+    if (pm.values.size() != 64 || pm.status[0] != 0) return 13;
+    try {
+      gcp::poseidon2::Hash(eng, ab, 4, 1);
+      return 14;
+    } catch (const gcp::Error& e) {
+      if (std::string(e.what()).find("need 2 or 3 limbs") == std::string::npos) return 15;
+    }
+  }
   printf("cpp mirror ok\n");
   return 0;
 }

@@ -245,3 +245,75 @@ def test_is_equal_and_select(engine):
             assert int(st[i]) == 0 and np.array_equal(out[i], a[i] if sel[i] else b[i]), i
     out, st = engine.elgamal_select(np.zeros(0, np.uint8), np.zeros((0, 4, 32), np.uint8), np.zeros((0, 4, 32), np.uint8))
     assert out.shape == (0, 4, 32)
+
+
+def _window_boundary_scalars():
+    """Scalars that sit on the recoding boundaries of the engine's signed windows (20-bit fixed-base, 4-bit variable-base):
+    digits exactly half a window (the tie), all-ones runs whose carry ripples through every window, single bits at
+    window edges, and the largest canonical values."""
+    ks = set()
+    for w in (4, 20):
+        half, full = 1 << (w - 1), 1 << w
+        for i in range(0, 254, w):
+            for d in (half - 1, half, half + 1, full - 1):
+                ks.add((d << i) % R)
+            ks.add(((1 << i) - 1) % R)
+            ks.add((1 << i) % R)
+        ks.add(sum(half << i for i in range(0, 240, w)) % R)             # every digit on the tie
+        ks.add(sum((half + 1) << i for i in range(0, 240, w)) % R)
+        ks.add(sum((full - 1) << i for i in range(0, 240, 2 * w)) % R)   # alternating full / empty digits
+    ks |= {0, 1, R - 1, R - 2, ed.ORDER - 1, ed.ORDER, ed.ORDER + 1, 2 * ed.ORDER, 7 * ed.ORDER + 5, (1 << 253) - 1, 1 << 253}
+    return sorted(ks)
+
+
+def test_window_boundary_scalars_fixed_and_variable_base(engine):
+    ks = _window_boundary_scalars()
+    n = len(ks)
+    assert n > 300
+    out, st = engine.elgamal_fixed_base_mul(elems(ks))
+    assert not st.any()
+    ms = [ks[(7 * i + 3) % n] for i in range(n)]
+    # shared key (fixed-base tables for G and PK) and per-item keys (windowed variable-base) against the C oracle
+    enc, st = engine.elgamal_encrypt(elems(PK), elems(ks), elems(ms))
+    want, wst = cport.elgamal_encrypt(elems(PK), elems(ks), elems(ms), threads=8)
+    assert not st.any() and not wst.any() and (enc == want).all()
+    assert (enc[:, :2] == out).all()                                     # C1 = [k]G
+    pks = elems([c for _ in range(n) for c in PK]).reshape(n, 2, 32)
+    enc2, st2 = engine.elgamal_encrypt(pks, elems(ks), elems(ms))
+    assert not st2.any() and (enc2 == want).all()
+    # and a sample against the literal Python restatement of mul.go:76-166
+    for i in list(range(0, n, 37)) + [n - 1]:
+        assert tuple(ints(out[i])) == eg.fixed_base_scalar_mul(ks[i]), hex(ks[i])
+
+
+def test_public_keys_with_a_cofactor_component(engine):
+    """Per-item keys outside <G>: the identity, the points of order 2, 4 and 8, and sums of those with subgroup points.
+    They pass AssertIsOnCurve (encrypt.go:49), so Encrypt goes on to [k]pk; the engine must return the group-law value
+    (oracle: plain double-and-add).  SURVEY 8c lists gnark's hinted ScalarMul on such keys as an edge the reference
+    tree does not pin; the mathematical value is what is checked here."""
+    t8 = (438929327410846936349781937479275998929723622237267896546408861753155634789,
+          4826523245007015323400664741523384119579596407052839571721035538011798951543)
+    low = [ed.IDENTITY, (0, R - 1), ed.scalar_mul(t8, 2), t8, ed.scalar_mul(t8, 3), ed.scalar_mul(t8, 7)]
+    assert all(ed.is_on_curve(p) for p in low) and ed.scalar_mul(t8, 8) == ed.IDENTITY and ed.scalar_mul(t8, 4) == (0, R - 1)
+    rng = random.Random(88)
+    pks = low + [ed.add(ed.scalar_mul(ed.G, rng.randrange(1, ed.ORDER)), t) for t in low[1:]]
+    ks = [rng.randrange(R) for _ in pks]
+    ks[0], ks[1], ks[2], ks[3] = 5, 7, 6, ed.ORDER          # odd multiple of the order-2 point, multiple of l on order 8
+    ms = [rng.randrange(1 << 16) for _ in pks]
+    n = len(pks)
+    out, st = engine.elgamal_encrypt(elems([c for p in pks for c in p]).reshape(n, 2, 32), elems(ks), elems(ms))
+    assert not st.any()
+    for i in range(n):
+        assert ints(out[i]) == eg.serialize(eg.encrypt(pks[i], ks[i], ms[i])), i
+    # the same keys through the shared-key path (fixed-base table built from the key)
+    for i in (1, 3, n - 1):
+        o, s = engine.elgamal_encrypt(elems(pks[i]), elems(ks[:4]), elems(ms[:4]))
+        assert not s.any()
+        assert ct_ints(o) == [eg.serialize(eg.encrypt(pks[i], k, m)) for k, m in zip(ks[:4], ms[:4])], i
+    # ciphertext addition and tally with low-order points as operands
+    cts = [(low[i % 6], low[(i + 1) % 6]) for i in range(12)]
+    flat = elems([x for c in cts for x in eg.serialize(c)]).reshape(12, 4, 32)
+    add, st = engine.elgamal_add(flat[:6], flat[6:])
+    assert not st.any() and ct_ints(add) == [eg.serialize(eg.ct_add(a, b)) for a, b in zip(cts[:6], cts[6:])]
+    tal, st = engine.elgamal_tally(flat.reshape(12, 1, 4, 32))
+    assert not st.any() and ct_ints(tal) == [eg.serialize(eg.tally(cts))]

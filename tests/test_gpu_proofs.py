@@ -125,3 +125,75 @@ def test_eddsa_poseidon_verifier(engine):
     assert [int(f) for f in flags] == [w[0] for w in want]
     assert [int(s) == 0 for s in status] == [w[1] for w in want]
     assert [w[0] for w in want] == [1, 0, 0, 1, 0, 0, 1, 0, 0, 0] and int(status[-1]) == 4
+
+
+def test_proof_entry_points_on_edge_scalars_and_each_off_curve_operand(engine):
+    """Responses and keys above the subgroup order (the gadgets take Fr elements as integers, r > l), a maximal message,
+    every point operand off the curve in turn, non-canonical elements, and low-order commitment points."""
+    from oracle import eddsa as oeddsa
+
+    rng = random.Random(77)
+    ell = ed.ORDER
+    t2 = (0, R - 1)                                                         # order 2, on the curve
+    items = []
+    for i in range(4):
+        msg = [rng.randrange(1000), R - 1, 0, ell][i]
+        pk, ct, a1, a2, z = make_proof(rng, rng.randrange(1, ell), msg)
+        items.append((pk, ct, msg, a1, a2, z))
+        items.append((pk, ct, msg, a1, a2, z + ell))                        # same point [z]G: still valid
+        if z + 7 * ell < R:
+            items.append((pk, ct, msg, a1, a2, z + 7 * ell))
+        items.append((pk, ct, msg, ed.add(a1, t2), a2, z))                  # commitment moved by a low-order point
+        items.append((pk, ct, (msg + 1) % R, a1, a2, z))
+    pk, ct, a1, a2, z = items[0][0], items[0][1], items[0][3], items[0][4], items[0][5]
+    off = (3, 4)
+    assert not ed.is_on_curve(off)
+    n_valid_shapes = len(items)
+    items += [(off, ct, items[0][2], a1, a2, z), (pk, (off, ct[1]), items[0][2], a1, a2, z),
+              (pk, (ct[0], off), items[0][2], a1, a2, z), (pk, ct, items[0][2], off, a2, z),
+              (pk, ct, items[0][2], a1, off, z)]
+    n = len(items)
+    flags, status = engine.elgamal_verify_decryption_proof(
+        elems([c for it in items for c in it[0]]), elems([x for it in items for x in eg.serialize(it[1])]).reshape(n, 4, 32),
+        elems(it[2] for it in items), elems([c for it in items for c in it[3]]), elems([c for it in items for c in it[4]]),
+        elems(it[5] for it in items))
+    want = [1 if eg.verify_decryption_proof(*it) else 0 for it in items]
+    assert [int(f) for f in flags] == want and sum(want) >= 8
+    assert [int(s) for s in status] == [0] * n_valid_shapes + [4] * 5
+    # non-canonical response / message: status 1, flag 0
+    bad = [(pk, ct, items[0][2], a1, a2, R), (pk, ct, R + 5, a1, a2, z)]
+    f2, s2 = engine.elgamal_verify_decryption_proof(
+        elems([c for it in bad for c in it[0]]), elems([x for it in bad for x in eg.serialize(it[1])]).reshape(2, 4, 32),
+        elems(it[2] for it in bad), elems([c for it in bad for c in it[3]]), elems([c for it in bad for c in it[4]]),
+        elems(it[5] for it in bad))
+    assert [int(x) for x in f2] == [0, 0] and [int(x) for x in s2] == [1, 1]
+
+    # AssertDecrypt with private keys above the order and a key of R - 1
+    dec = []
+    for i in range(6):
+        d = rng.randrange(1, ell)
+        m = [rng.randrange(1 << 16), 0, R - 1][i % 3]
+        c = eg.encrypt(ed.scalar_mul(ed.G, d), rng.randrange(R), m)
+        dec.append((c, d + ell * (i % 4), m))                               # d, d + l, d + 2l, d + 3l: all < r
+    dec.append((dec[0][0], R - 1, dec[0][2]))
+    dec.append(((t2, dec[0][0][1]), dec[0][1], dec[0][2]))                  # C1 of order 2
+    nd = len(dec)
+    flags, status = engine.elgamal_assert_decrypt(
+        elems([x for it in dec for x in eg.serialize(it[0])]).reshape(nd, 4, 32), elems(it[1] for it in dec),
+        elems(it[2] for it in dec))
+    want = [1 if eg.assert_decrypt(*it) else 0 for it in dec]
+    assert [int(f) for f in flags] == want and want[:6] == [1] * 6 and not status.any()
+
+    # EdDSA: S above the order (types.go:37-49 reduces S mod l before the multiplication), a maximal message
+    sigs = []
+    for i in range(4):
+        msg = [rng.getrandbits(248), R - 1, 0, 1][i]
+        a, r, s = oeddsa.sign(rng.randrange(1, ell), rng.randrange(1, ell), msg)
+        sigs.append((a, r, s, msg))
+        sigs.append((a, r, s + ell, msg))
+    ns = len(sigs)
+    flags, status = engine.eddsa_verify(elems([c for it in sigs for c in it[0]]), elems([c for it in sigs for c in it[1]]),
+                                        elems(it[2] for it in sigs), elems(it[3] for it in sigs))
+    want = [oeddsa.is_valid(*it) for it in sigs]
+    assert [int(f) for f in flags] == [w[0] for w in want] and not status.any()
+    assert [w[0] for w in want] == [1] * ns

@@ -167,3 +167,44 @@ def test_unpack_dev_feeds_verify_dev(engine):
     assert not d_bad.cpu().numpy().any()
     want = elems(s for row in sibs for s in row).reshape(n, n_levels, 32)
     assert np.array_equal(d_sib.cpu().numpy(), want)
+
+
+def test_random_mutations_of_packed_strings(engine):
+    """Seeded byte-level fuzz of the wire format: header fields, bitmap bytes and lengths of honest packed proofs are
+    mutated at random; every string must get exactly what arbo.UnpackSiblings + the verifier (oracle) give - status 7
+    with flag 0 and root 0, or the verifier's result on the expanded row."""
+    rng = random.Random(2024)
+    n_levels = 24
+    roots, variants, keys, values = [], [], [], []
+    for i in range(160):
+        root, sib, key, value = census_proof(rng, n_levels, lo=1, hi=14)
+        b = bytearray(osmt.pack_siblings(strip(sib)))
+        mut = rng.randrange(8)
+        if mut == 0 and len(b):
+            b[rng.randrange(min(len(b), 4))] ^= 1 << rng.randrange(8)          # header bit flip
+        elif mut == 1 and len(b) > 4:
+            b[4 + rng.randrange(min(len(b) - 4, 3))] ^= 1 << rng.randrange(8)  # bitmap bit flip
+        elif mut == 2:
+            b = b[:rng.randrange(len(b) + 1)]                                  # truncation
+        elif mut == 3:
+            b += bytes(rng.getrandbits(8) for _ in range(rng.randrange(1, 40)))
+        elif mut == 4 and len(b) > 36:
+            j = rng.randrange(4, len(b))
+            b[j] ^= 0xFF                                                       # sibling byte (may go non-canonical)
+        elif mut == 5:
+            b = bytearray(rng.getrandbits(8) for _ in range(rng.randrange(0, 80)))
+        roots.append(root), variants.append(bytes(b)), keys.append(key), values.append(value)
+    n = len(variants)
+    flags, status, out_roots = engine.smt_verify_packed(elems(roots), variants, n_levels, elems(keys), elems(values),
+                                                        want_roots=True)
+    seen = set()
+    for i, b in enumerate(variants):
+        s_or, bad = osmt.assignment_siblings(b, n_levels)
+        if bad:
+            want = (0, osmt.STATUS_MALFORMED, 0)
+        else:
+            want = osmt.inclusion_verifier(roots[i], s_or, keys[i], values[i])
+        got = (int(flags[i]), int(status[i]), ints(out_roots[i:i + 1])[0])
+        assert got[:2] == want[:2] and (want[1] != 0 or got[2] == want[2]), (i, b.hex())
+        seen.add(want[:2])
+    assert {(1, 0), (0, 0), (0, 7)} <= seen
