@@ -292,6 +292,34 @@ def measure_census_like(torch, eng, g, log2_n=18, seed=0xCE75):
     return res
 
 
+def measure_config1(eng, g, n=1024, seed=0xB200):
+    """BASELINE configs[0]: the 2-input Poseidon hash on a batch of 1024 (the reference's own CPU-runnable case,
+    hash/native/bn254/poseidon/poseidon_test.go): one host-buffer call end to end (copies included), median of 50,
+    beside the C port of the same batch on one and on all host cores.  A parity case, reported for completeness."""
+    from oracle import cport
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 256, size=(n, 2, 32), dtype=np.uint8)
+    a[:, :, 31] &= 0x1F
+    out, st = eng.poseidon_hash(a)
+    want, _ = cport.poseidon_hash(a, threads=1)
+    times = []
+    for _ in range(50):
+        t0 = time.perf_counter()
+        eng.poseidon_hash(a)
+        times.append(time.perf_counter() - t0)
+    gpu_s = float(np.median(times))
+    cpu = {}
+    for th in (1, cport.default_threads()):
+        ts = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            cport.poseidon_hash(a, threads=th)
+            ts.append(time.perf_counter() - t0)
+        cpu[th] = float(np.median(ts))
+    return {"batch": n, "gpu_call_us": gpu_s * 1e6, "gpu_hashes_per_s": n / gpu_s,
+            "cpu_port_us": {str(k): v * 1e6 for k, v in cpu.items()}, "matches_cpu_port": bool((out == want).all() and not st.any())}
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons of one GPU every 200 ms while the timed region runs."""
 
@@ -502,6 +530,7 @@ def main():
         extras = measure_extras(torch, dist, eng, g, world, rank)
         if world == 1:
             extras["census_like_e2e"] = measure_census_like(torch, eng, g)
+            extras["config1_poseidon_batch_1024"] = measure_config1(eng, g)
 
     # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample) -----------------------------------
     cpu_baseline = None

@@ -15,6 +15,7 @@ namespace gcp {
 
 #define GCP_ED_D_MONT {0x504f718du, 0x5c3b8876u, 0x984346b4u, 0x50be2c72u, 0x59126675u, 0x4783751fu, 0xa7a1c091u, 0x305ff669u}
 #define GCP_ED_2D_MONT {0xb09ee319u, 0x74951b58u, 0xb6cd1cd7u, 0x7948709cu, 0x30a3748du, 0xd6b6a488u, 0x6e11e0f8u, 0x305b9e60u}
+#define GCP_ED_2D_R2 {0x9d9efa30u, 0xa064f144u, 0x19d4c427u, 0x338939eeu, 0x072e9f21u, 0x2483f1a5u, 0x6271a8c1u, 0x06e5885du}
 #define GCP_ED_2D_R3 {0x05326973u, 0x900e846eu, 0x05aa9436u, 0xed233c6eu, 0xb6f3823du, 0x391d5278u, 0xf9451009u, 0x1c0c9c01u}
 #define GCP_FR_ONE_MONT {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u}
 #define GCP_FR_R2 {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u}
@@ -40,8 +41,10 @@ __device__ __forceinline__ void ext_identity(ExtPoint& p) {
 // P += N (mixed addition, 7 multiplies).  CHAINS = true advances the independent products row by row together
 // (three, then two and two): +14 % in the tally kernel, whose loop has registers to spare; the window-table kernels
 // are register-bound and measured 1 % slower with it, so they keep one chain at a time.
+// z_over_r: the Niels point is that of a projectively rescaled Q = (x/R : y/R : 1/R : xy/R) (standard-form coordinates
+// read AS Montgomery representations, see tally_partial_kernel), so D = 2 Z1 Z2 is 2 Z1 / R: one reduction, no product.
 template <bool CHAINS = false>
-__device__ __forceinline__ void ext_add_niels(ExtPoint& p, const NielsPoint& n) {
+__device__ __forceinline__ void ext_add_niels(ExtPoint& p, const NielsPoint& n, bool z_over_r = false) {
   u32 a[8], b[8], c[8], d[8], e[8], f[8], g[8], h[8], t[8], u[8];
   fr_sub(t, p.Y, p.X);
   fr_add(u, p.Y, p.X);
@@ -53,6 +56,7 @@ __device__ __forceinline__ void ext_add_niels(ExtPoint& p, const NielsPoint& n) 
     fr_mul(c, p.T, n.t2d);
   }
   fr_add(d, p.Z, p.Z);
+  if (z_over_r) fr_redc(d, d);
   fr_sub(e, b, a);
   fr_sub(f, d, c);
   fr_add(g, d, c);

@@ -528,23 +528,23 @@ __global__ void __launch_bounds__(TALLY_THREADS, 4) tally_partial_kernel(const u
         bad = 1;
         continue;
       }
-      // Niels form (y - x, y + x, 2dxy) in Montgomery representation.  Standard-form inputs: (y -/+ x) * R^2 / R and
-      // x*y/R * (2d R^3) / R = 2dxy R; Montgomery inputs: the same two multiplier bodies with R and 2dR instead.
-      const u32 c_lin_std[8] = GCP_FR_R2, c_lin_mont[8] = GCP_FR_ONE_MONT;
-      const u32 c_t_std[8] = GCP_ED_2D_R3, c_t_mont[8] = GCP_ED_2D_MONT;
-      u32 c_lin[8], c_t[8];
+      // Niels form (y - x, y + x, 2d T) of the input point, two multiplies and no conversion.  Montgomery inputs are
+      // the point itself (Z = 1).  Standard-form inputs are read AS Montgomery representations: (x, y, 1, xy) then
+      // stands for the projectively rescaled point (x/R : y/R : 1/R : xy/R) - the same affine point - whose sums and
+      // differences need no product, whose T is x*y with the lost factor restored by the constant (2d R^2 instead of
+      // 2d R), and whose Z = 1/R turns D = 2 Z1 Z2 into one Montgomery reduction of 2 Z1 (ext_add_niels, z_over_r).
+      // 9 (Montgomery) / 9.5 (standard) multiplies per point instead of 11 with the inputs converted first.
+      const u32 c_t_std[8] = GCP_ED_2D_R2, c_t_mont[8] = GCP_ED_2D_MONT;
+      u32 c_t[8];
 #pragma unroll
-      for (int l = 0; l < 8; l++) {
-        c_lin[l] = mont ? c_lin_mont[l] : c_lin_std[l];
-        c_t[l] = mont ? c_t_mont[l] : c_t_std[l];
-      }
+      for (int l = 0; l < 8; l++) c_t[l] = mont ? c_t_mont[l] : c_t_std[l];
       NielsPoint n;
-      u32 t[8], dm[8], sp[8];
-      fr_sub(dm, ys, xs);
-      fr_add(sp, ys, xs);
-      fr_mul3(n.ymx, dm, c_lin, n.ypx, sp, c_lin, t, xs, ys);  // three independent products, row-interleaved
+      u32 t[8];
+      fr_sub(n.ymx, ys, xs);
+      fr_add(n.ypx, ys, xs);
+      fr_mul(t, xs, ys);
       fr_mul(n.t2d, t, c_t);
-      ext_add_niels<true>(acc, n);
+      ext_add_niels<true>(acc, n, !mont);
     }
   }
   if (bad) atomicAdd(bad_count + col / 2, 1u);

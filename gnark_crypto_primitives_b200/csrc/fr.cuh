@@ -554,6 +554,15 @@ __device__ __forceinline__ void fr_from_mont(u32 (&r)[8], const u32 (&a)[8]) {
   cond_sub(r, P1);
 }
 
+// r = a / R mod r for any a < 2^256 (one Montgomery reduction, no product); output <= r
+__device__ __forceinline__ void fr_redc(u32 (&r)[8], const u32 (&a)[8]) {
+  Wide w;
+  wide_zero(w);
+#pragma unroll
+  for (int p = 0; p < 4; p++) w.e[p] = ((u64)a[2 * p + 1] << 32) | a[2 * p];
+  wide_redc(w, r);
+}
+
 __device__ __forceinline__ bool fr_is_canonical(const u32 (&a)[8]) {  // a < r
   const u32 P1[8] = GCP_P_LIMBS;
   u32 t[8];
