@@ -233,6 +233,31 @@ __device__ __noinline__ void ext_add_cached_call(ExtPoint& p, const CachedPoint&
   fr_mul_call(p.Z, f, g);
 }
 
+// ext_add over the out-of-line multiplier (same formulas, same results): for the once-per-item additions of the proof
+// kernels, whose inlined copies (~30 KB each) are fetched from L2 by every warp that passes through them
+__device__ __noinline__ void ext_add_call(ExtPoint& p, const ExtPoint& q) {
+  const u32 d2[8] = GCP_ED_2D_MONT;
+  u32 a[8], b[8], c[8], d[8], e[8], f[8], g[8], h[8], t[8], u[8];
+  fr_sub(t, p.Y, p.X);
+  fr_sub(u, q.Y, q.X);
+  fr_mul_call(a, t, u);
+  fr_add(t, p.Y, p.X);
+  fr_add(u, q.Y, q.X);
+  fr_mul_call(b, t, u);
+  fr_mul_call(t, p.T, q.T);
+  fr_mul_call(c, t, d2);
+  fr_mul_call(t, p.Z, q.Z);
+  fr_add(d, t, t);
+  fr_sub(e, b, a);
+  fr_sub(f, d, c);
+  fr_add(g, d, c);
+  fr_add(h, b, a);
+  fr_mul_call(p.X, e, f);
+  fr_mul_call(p.Y, g, h);
+  fr_mul_call(p.T, e, h);
+  fr_mul_call(p.Z, f, g);
+}
+
 // out = [k]base for an on-curve base and an integer k < 2^254 (little-endian words)
 __device__ __noinline__ void ext_scalar_mul_windowed(ExtPoint& out, const ExtPoint& base, const u32 (&k)[8]) {
   CachedPoint tab[8];  // local memory, 1 KB per thread: [1]P .. [8]P

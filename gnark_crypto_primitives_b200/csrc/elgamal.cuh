@@ -180,6 +180,12 @@ __device__ __forceinline__ void fixed_base_accumulate(ExtPoint& acc, const u32 (
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// One out-of-line copy of the window loop for kernels that run it more than once per item or beside a lot of other code
+// (per-item-key Encrypt, the proof kernels): their inlined copies made the kernels 135-400 KB and fetch-bound.
+__device__ __noinline__ void fixed_base_accumulate_ool(ExtPoint& acc, const u32 (&k)[8], const u32* __restrict__ tab) {
+  fixed_base_accumulate(acc, k, tab);
+}
+
 __device__ __forceinline__ void store_ext_xyz(u32* o, const ExtPoint& p) {
   store_fr(o, p.X);
   store_fr(o + 8, p.Y);
@@ -273,11 +279,11 @@ __global__ void __launch_bounds__(128) encrypt_per_key_kernel(const u32* __restr
   ext_identity(c1);
   ext_identity(c2);
   if (pk_ok) {
-    fixed_base_accumulate(c1, k, tabG);
+    fixed_base_accumulate_ool(c1, k, tabG);
     ExtPoint base;
     ext_from_affine(base, px, py);
     ext_scalar_mul_windowed(c2, base, k);  // k < r < 2^254
-    fixed_base_accumulate(c2, m, tabG);
+    fixed_base_accumulate_ool(c2, m, tabG);
   }
   store_ext_xyz(out_xyz + idx * 48, c1);
   store_ext_xyz(out_xyz + idx * 48 + 24, c2);

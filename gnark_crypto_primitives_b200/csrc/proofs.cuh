@@ -17,15 +17,15 @@ __device__ __forceinline__ void ext_scalar_mul(ExtPoint& out, const ExtPoint& ba
 }
 
 // projective equality of two extended points (Z != 0 on both sides for curve points)
-__device__ __forceinline__ bool ext_equal(const ExtPoint& p, const ExtPoint& q) {
+__device__ __noinline__ bool ext_equal(const ExtPoint& p, const ExtPoint& q) {
   u32 a[8], b[8];
-  fr_mul(a, p.X, q.Z);
-  fr_mul(b, q.X, p.Z);
+  fr_mul_call(a, p.X, q.Z);
+  fr_mul_call(b, q.X, p.Z);
   fr_canon(a);
   fr_canon(b);
   if (!eq256(a, b)) return false;
-  fr_mul(a, p.Y, q.Z);
-  fr_mul(b, q.Y, p.Z);
+  fr_mul_call(a, p.Y, q.Z);
+  fr_mul_call(b, q.Y, p.Z);
   fr_canon(a);
   fr_canon(b);
   return eq256(a, b);
@@ -40,7 +40,8 @@ __device__ __forceinline__ void ext_neg(ExtPoint& p) {
 }
 
 // affine point from memory: canonical check, Montgomery conversion, on-curve check; result extended
-__device__ __forceinline__ void load_curve_point(ExtPoint& p, u32 (&x)[8], u32 (&y)[8], bool& canonical, bool& on_curve,
+// (out of line: five call sites in the decryption-proof kernel)
+__device__ __noinline__ void load_curve_point(ExtPoint& p, u32 (&x)[8], u32 (&y)[8], bool& canonical, bool& on_curve,
                                                  const u32* src, int mont) {
   u32 xs[8], ys[8];
   load_fr(xs, src);
@@ -56,6 +57,8 @@ __device__ __forceinline__ void load_curve_point(ExtPoint& p, u32 (&x)[8], u32 (
   on_curve = on_curve && ed_is_on_curve(x, y);
   ext_from_affine(p, x, y);
 }
+
+__device__ __noinline__ bool ed_is_on_curve_ool(const u32 (&x)[8], const u32 (&y)[8]) { return ed_is_on_curve(x, y); }
 
 // ---- AssertDecrypt: C1, C2 on curve;  C2 - [priv]C1 == [m]G ------------------------------------------------------
 __global__ void __launch_bounds__(128) assert_decrypt_kernel(const u32* __restrict__ tabG, const u32* __restrict__ cts,
@@ -76,9 +79,9 @@ __global__ void __launch_bounds__(128) assert_decrypt_kernel(const u32* __restri
     ExtPoint s, m;
     ext_scalar_mul(s, c1, priv);          // ciphertext.go:58
     ext_identity(m);
-    fixed_base_accumulate(m, msg, tabG);  // ciphertext.go:60
+    fixed_base_accumulate_ool(m, msg, tabG);  // ciphertext.go:60
     ext_neg(s);
-    ext_add(c2, s);                       // ciphertext.go:62
+    ext_add_call(c2, s);                       // ciphertext.go:62
     flag = ext_equal(c2, m) ? 1 : 0;      // ciphertext.go:64-65
   }
   flags[idx] = flag;
@@ -114,10 +117,10 @@ __global__ void __launch_bounds__(64) decryption_proof_kernel(const u32* __restr
     // D = C2 - [msg]G   (ciphertext.go:137-139)
     ExtPoint m, d;
     ext_identity(m);
-    fixed_base_accumulate(m, msg, tabG);
+    fixed_base_accumulate_ool(m, msg, tabG);
     ext_neg(m);
     d = c2;
-    ext_add(d, m);
+    ext_add_call(d, m);
     // affine D for the Fiat-Shamir hash
     u32 zi[8], zc[8];
     fr_copy(zc, d.Z);
@@ -126,8 +129,8 @@ __global__ void __launch_bounds__(64) decryption_proof_kernel(const u32* __restr
       st = GCP_STATUS_ZERO_DENOM;
     } else {
       fr_inv(zi, d.Z);
-      fr_mul(coords[7], d.X, zi);
-      fr_mul(coords[8], d.Y, zi);
+      fr_mul_call(coords[7], d.X, zi);
+      fr_mul_call(coords[8], d.Y, zi);
       fr_copy(coords[3], coords[1]);
       fr_copy(coords[4], coords[2]);
       fr_set_zero(coords[0]);
@@ -138,15 +141,15 @@ __global__ void __launch_bounds__(64) decryption_proof_kernel(const u32* __restr
       // z*G == A1 + e*P   (ciphertext.go:143-151)
       ExtPoint zg, ep;
       ext_identity(zg);
-      fixed_base_accumulate(zg, z, tabG);
+      fixed_base_accumulate_ool(zg, z, tabG);
       ext_scalar_mul(ep, pk, e);
-      ext_add(ep, a1);
+      ext_add_call(ep, a1);
       bool ok = ext_equal(ep, zg);
       // z*C1 == A2 + e*D   (ciphertext.go:153-166)
       ExtPoint zc1, ed;
       ext_scalar_mul(zc1, c1, z);
       ext_scalar_mul(ed, d, e);
-      ext_add(ed, a2);
+      ext_add_call(ed, a2);
       ok = ok && ext_equal(ed, zc1);
       flag = ok ? 1 : 0;
     }
@@ -178,11 +181,11 @@ __global__ void __launch_bounds__(64) eddsa_verify_kernel(const u32* __restrict_
   fr_set_zero(st6[0]);
   // RTE conversion: x * (-f); y unchanged
   u32 ax[8], ay[8], rx[8], ry[8];
-  fr_mul(rx, st6[1], negf);
+  fr_mul_call(rx, st6[1], negf);
   fr_copy(ry, st6[2]);
-  fr_mul(ax, st6[3], negf);
+  fr_mul_call(ax, st6[3], negf);
   fr_copy(ay, st6[4]);
-  bool on_curve = ed_is_on_curve(ax, ay) && ed_is_on_curve(rx, ry);  // PointToRTE, verifier.go:46
+  bool on_curve = ed_is_on_curve_ool(ax, ay) && ed_is_on_curve_ool(rx, ry);  // PointToRTE, verifier.go:46
   u8 st = !canon ? GCP_STATUS_NONCANONICAL : (!on_curve ? GCP_STATUS_OFF_CURVE : GCP_STATUS_OK);
   u8 flag = 0;
   if (st == GCP_STATUS_OK) {
@@ -191,14 +194,14 @@ __global__ void __launch_bounds__(64) eddsa_verify_kernel(const u32* __restrict_
     fr_from_mont(h, h_m);
     ExtPoint left, a, r, r1;
     ext_identity(left);
-    fixed_base_accumulate(left, s_int, tabG);  // [S] rteB8
+    fixed_base_accumulate_ool(left, s_int, tabG);  // [S] rteB8
     ext_from_affine(a, ax, ay);
     ext_from_affine(r, rx, ry);
     ext_scalar_mul(r1, a, h);
-    ext_double(r1);
-    ext_double(r1);
-    ext_double(r1);
-    ext_add(r1, r);
+    ext_double_call(r1, false);  // verifier.go:72-74: three doublings; T is only read by the addition after the last
+    ext_double_call(r1, false);
+    ext_double_call(r1, true);
+    ext_add_call(r1, r);
     flag = ext_equal(left, r1) ? 1 : 0;
   }
   flags[idx] = flag;
