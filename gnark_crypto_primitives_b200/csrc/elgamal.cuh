@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(128, 4) encrypt_shared_kernel(const u32* __res
 }
 
 // ---- Encrypt with a public key per item: [k]PK by signed 4-bit windows (edwards.cuh) -------------------------------------------------
-__global__ void __launch_bounds__(128) encrypt_per_key_kernel(const u32* __restrict__ tabG, const u32* __restrict__ pks,
+__global__ void __launch_bounds__(128, 5) encrypt_per_key_kernel(const u32* __restrict__ tabG, const u32* __restrict__ pks,
                                                               const u32* __restrict__ ks, const u32* __restrict__ ms, size_t n,
                                                               u32* __restrict__ out_xyz, u8* __restrict__ status, int mont) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -409,7 +409,7 @@ cudaError_t launch_decryption_proof(const u32* tabG, const PoseidonTable& tab13,
                                     const u32* msgs, const u32* a1s, const u32* a2s, const u32* zs, size_t n, u8* flags,
                                     u8* status, int mont, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
-  decryption_proof_kernel<<<blocks_for(n, 64), 64, 0, stream>>>(tabG, tab13, pks, cts, msgs, a1s, a2s, zs, n, flags, status, mont);
+  decryption_proof_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(tabG, tab13, pks, cts, msgs, a1s, a2s, zs, n, flags, status, mont);
   return cudaGetLastError();
 }
 
@@ -423,7 +423,7 @@ cudaError_t launch_eddsa_verify(const u32* tabG, const PoseidonTable& tab6, cons
                                 const u32* sig_s, const u32* msgs, size_t n, u8* flags, u8* status, int mont,
                                 cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
-  eddsa_verify_kernel<<<blocks_for(n, 64), 64, 0, stream>>>(tabG, tab6, pub_a, sig_r, sig_s, msgs, n, flags, status, mont);
+  eddsa_verify_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(tabG, tab6, pub_a, sig_r, sig_s, msgs, n, flags, status, mont);
   return cudaGetLastError();
 }
 

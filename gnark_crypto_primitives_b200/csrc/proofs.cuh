@@ -61,7 +61,7 @@ __device__ __noinline__ void load_curve_point(ExtPoint& p, u32 (&x)[8], u32 (&y)
 __device__ __noinline__ bool ed_is_on_curve_ool(const u32 (&x)[8], const u32 (&y)[8]) { return ed_is_on_curve(x, y); }
 
 // ---- AssertDecrypt: C1, C2 on curve;  C2 - [priv]C1 == [m]G ------------------------------------------------------
-__global__ void __launch_bounds__(128) assert_decrypt_kernel(const u32* __restrict__ tabG, const u32* __restrict__ cts,
+__global__ void __launch_bounds__(128, 5) assert_decrypt_kernel(const u32* __restrict__ tabG, const u32* __restrict__ cts,
                                                              const u32* __restrict__ privs, const u32* __restrict__ msgs, size_t n,
                                                              u8* __restrict__ flags, u8* __restrict__ status, int mont) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(128) assert_decrypt_kernel(const u32* __restri
 
 // ---- DecryptionProof.Verify -----------------------------------------------------------------------------------------
 // Inputs per item: pubkey (2), ciphertext (4), msg (1), A1 (2), A2 (2), Z (1) elements.
-__global__ void __launch_bounds__(64) decryption_proof_kernel(const u32* __restrict__ tabG, PoseidonTable tab13,
+__global__ void __launch_bounds__(128, 5) decryption_proof_kernel(const u32* __restrict__ tabG, PoseidonTable tab13,
                                                               const u32* __restrict__ pks, const u32* __restrict__ cts,
                                                               const u32* __restrict__ msgs, const u32* __restrict__ a1s,
                                                               const u32* __restrict__ a2s, const u32* __restrict__ zs, size_t n,
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(64) decryption_proof_kernel(const u32* __restr
 // ---- EdDSA-Poseidon IsValid (/root/reference/ecc/bn254/eddsa/verifier.go:55-88) ---------------------------------------
 // A, R in TE (circom/iden3) coordinates; h = Poseidon(R.x, R.y, A.x, A.y, msg) on those coordinates (t = 6);
 // A' = RTE(A), R' = RTE(R) asserted on the a = -1 curve; flag = ([S]G == 8*[h]A' + R')  (rteB8 == G, constants.go:11-18).
-__global__ void __launch_bounds__(64) eddsa_verify_kernel(const u32* __restrict__ tabG, PoseidonTable tab6,
+__global__ void __launch_bounds__(128, 5) eddsa_verify_kernel(const u32* __restrict__ tabG, PoseidonTable tab6,
                                                           const u32* __restrict__ pub_a, const u32* __restrict__ sig_r,
                                                           const u32* __restrict__ sig_s, const u32* __restrict__ msgs, size_t n,
                                                           u8* __restrict__ flags, u8* __restrict__ status, int mont) {
