@@ -16,7 +16,11 @@
  *    gcp_last_error() gives the message.  A per-item `status` byte is non-zero where the reference
  *    would have failed an ASSERTION (solver error), while `flag` outputs carry the gadget's 0/1 result;
  *    an invalid proof is flag 0 / status 0, never an error.
- *  - Thread safety: calls on one gcp_ctx are serialised internally; use one ctx per GPU.
+ *  - Thread safety: calls on one gcp_ctx are serialised internally (a host-buffer call holds the context for its
+ *    whole duration); use one ctx per GPU.  The `*_dev` variants return before their kernels have run and some of
+ *    them keep intermediate results in per-context scratch (SMT leaf hashes and sort keys, projective points before
+ *    normalisation, tally partials): work enqueued on one context through `*_dev` calls must therefore be ordered -
+ *    the same stream, or events between streams - or spread over one context per stream.
  *  - There is no CPU fallback: without a CUDA device gcp_ctx_create fails.
  */
 #ifndef GCP_B200_H
