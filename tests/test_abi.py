@@ -73,3 +73,53 @@ def test_group_and_host_alloc_are_loud_without_a_device():
     with pytest.raises(g.EngineError) as e:
         g.Group([])
     assert e.value.code == _lib.GCP_ERR_BAD_ARG
+
+
+def _c_prototypes():
+    """name -> number of parameters, parsed from the public header."""
+    text = (ROOT / "include" / "gcp_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(gcp_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        params = m.group(2).strip()
+        protos[m.group(1)] = 0 if params in ("", "void") else params.count(",") + 1
+    return protos
+
+
+def _go_calls(src):
+    """(name, argument count) of every C.gcp_* call in the Go shim (balanced-parenthesis scan, top-level commas)."""
+    calls = []
+    for m in re.finditer(r"\bC\.(gcp_[a-z0-9_]+)\(", src):
+        depth, i, commas, empty = 1, m.end(), 0, True
+        while depth:
+            ch = src[i]
+            if ch in "([{":
+                depth += 1
+            elif ch in ")]}":
+                depth -= 1
+            elif ch == "," and depth == 1:
+                commas += 1
+            if depth and not ch.isspace():
+                empty = False
+            i += 1
+        calls.append((m.group(1), 0 if empty else commas + 1))
+    return calls
+
+
+def test_go_shim_matches_the_header():
+    """The cgo shim cannot be compiled here (no Go toolchain): at least every C function it calls must be declared in
+    include/gcp_b200.h with the number of arguments the shim passes, and every C constant it names must exist."""
+    src = (ROOT / "go" / "gcpb200" / "gcpb200.go").read_text()
+    protos = _c_prototypes()
+    calls = _go_calls(src)
+    assert len(calls) >= 20
+    for name, nargs in calls:
+        assert name in protos, f"{name} is not declared in gcp_b200.h"
+        assert nargs == protos[name], f"{name}: shim passes {nargs} arguments, header declares {protos[name]}"
+    header = (ROOT / "include" / "gcp_b200.h").read_text()
+    for const in set(re.findall(r"\bC\.(GCP_[A-Z0-9_]+)\b", src)):
+        assert re.search(rf"\b{const}\b", header), const
+    # the C++ mirror calls the same ABI: same check on its gcp_* calls
+    hpp = (ROOT / "include" / "gcp_b200.hpp").read_text()
+    for name in set(re.findall(r"\b(gcp_[a-z0-9_]+)\s*\(", re.sub(r"//.*", "", hpp))):
+        assert name in protos, name
