@@ -4,6 +4,10 @@ rows on the GPU.
 
   Poseidon  hash/native/bn254/poseidon/poseidon.go:94-197   (MaxHashInputs = 16, :10-15)
   MiMC7     hash/native/bn254/mimc7/mimc.go:25-54           (maxInputs = 62, :9)
+
+and of the function-form plug `utils.Hasher` (utils/hashers.go:10): PoseidonHasher (:25-27) and Poseidon2Hasher (:35-37).
+(utils.MiMCHasher, :15-22, wraps gnark's std/hash/mimc - a different permutation that lives outside the reference tree -
+and has no mirror here.)
 """
 import numpy as np
 
@@ -77,3 +81,29 @@ class MiMC7(_BatchHasher):
 
     def _hash(self, rows):
         return self._engine.mimc7_hash(rows, fmt=self._fmt)
+
+
+def _columns(data):
+    cols = [_as_elems(d, name="data").reshape(-1, 32) for d in data]
+    if cols and any(c.shape[0] != cols[0].shape[0] for c in cols):
+        raise ValueError("every column must have one element per row of the batch")
+    return cols
+
+
+def PoseidonHasher(engine, *data, fmt=FMT_CANONICAL):
+    """utils.PoseidonHasher (utils/hashers.go:25-27) = poseidon.Hash over a batch: one (n, 32) column per argument ->
+    (digests (n, 32), status (n,)).  0 or more than 16 columns raise the engine's "bad inputs provided"."""
+    cols = _columns(data)
+    n = cols[0].shape[0] if cols else 0
+    rows = np.ascontiguousarray(np.stack(cols, axis=1)) if cols else np.zeros((n, 0, 32), dtype=np.uint8)
+    return engine.poseidon_hash(rows, fmt=fmt)
+
+
+def Poseidon2Hasher(engine, *data, fmt=FMT_CANONICAL):
+    """utils.Poseidon2Hasher (utils/hashers.go:35-37) = HashPoseidon2Gnark over a batch: 2 columns hash an internal
+    node (ordered min, max), 3 columns a leaf (key, value, flag); any other count raises "need 2 or 3 limbs"
+    (hash/native/bn254/poseidon2/gnark.go:38-40)."""
+    cols = _columns(data)
+    if len(cols) not in (2, 3):
+        raise ValueError(f"poseidon2: need 2 or 3 limbs, got {len(cols)}")
+    return engine.poseidon2_hash(np.ascontiguousarray(np.stack(cols, axis=1)), fmt=fmt)

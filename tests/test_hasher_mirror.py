@@ -55,3 +55,36 @@ def test_sum_and_sum_is_equal(engine):
     m.Write(elems([12]))
     dig, st = m.Sum()
     assert ints(dig)[0] == 16051049095595290701999129793867590386356047218708919933694064829788708231421
+
+
+def test_function_form_hashers_shape_their_rows_like_the_reference():
+    """utils/hashers.go:25-37: PoseidonHasher / Poseidon2Hasher take the inputs as separate arguments; the mirrors stack
+    one column per argument into the (n, arity, 32) rows of the engine call and keep the reference's arity errors."""
+    from gnark_crypto_primitives_b200 import hasher
+
+    seen = {}
+
+    class Recorder:
+        def poseidon_hash(self, rows, fmt=0):
+            seen["poseidon"] = (rows.copy(), fmt)
+            return "digests", "status"
+
+        def poseidon2_hash(self, rows, fmt=0):
+            seen["poseidon2"] = (rows.copy(), fmt)
+            return "digests2", "status2"
+
+    a, b, c = elems([1, 4]), elems([2, 5]), elems([3, 6])
+    assert hasher.PoseidonHasher(Recorder(), a, b, c) == ("digests", "status")
+    rows, fmt = seen["poseidon"]
+    assert rows.shape == (2, 3, 32) and fmt == 0 and ints(rows[0]) == [1, 2, 3] and ints(rows[1]) == [4, 5, 6]
+    assert hasher.Poseidon2Hasher(Recorder(), a, b, fmt=1) == ("digests2", "status2")
+    rows, fmt = seen["poseidon2"]
+    assert rows.shape == (2, 2, 32) and fmt == 1 and ints(rows[1]) == [4, 5]
+    hasher.Poseidon2Hasher(Recorder(), a, b, c)
+    assert seen["poseidon2"][0].shape == (2, 3, 32)
+    for bad in ((a,), (a, b, c, a)):
+        with pytest.raises(ValueError, match="need 2 or 3 limbs"):
+            hasher.Poseidon2Hasher(Recorder(), *bad)
+    with pytest.raises(ValueError):
+        hasher.PoseidonHasher(Recorder(), a, elems([1]))
+
