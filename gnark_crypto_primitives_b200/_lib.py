@@ -85,6 +85,10 @@ SIGNATURES = {
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     "gcp_elgamal_fixed_base_mul": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_int]),
     "gcp_elgamal_fixed_base_mul_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_int, c_void_p]),
+    "gcp_elgamal_scalar_mul": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p,
+                                       c_int]),
+    "gcp_elgamal_scalar_mul_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p,
+                                           c_int, c_void_p]),
     "gcp_elgamal_encrypt": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_int]),
     "gcp_elgamal_encrypt_dev": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p,
                                         c_int, c_void_p]),

@@ -20,7 +20,7 @@ using namespace gcp;
 namespace {
 
 constexpr uint32_t BLOB_MAGIC = 0x32425350u;  // 'PSB2', written by oracle/gen_constants.py
-constexpr int N_SLOTS = 96;
+constexpr int N_SLOTS = 128;
 
 thread_local std::string g_create_error;
 
@@ -162,6 +162,17 @@ static int h2d_copy(gcp_ctx* ctx, void* dst, const void* src, size_t bytes, cuda
     int rc_ = (call);            \
     if (rc_ != GCP_OK) return rc_; \
   } while (0)
+
+// Every host-buffer entry point holds one of these: whatever path it returns by (an allocation failure in the middle of a
+// chunk loop included), both pipeline streams have drained, so no copy into or out of the caller's buffers is still in
+// flight (the header's promise that no host pointer is used after the call returns: the cgo pointer rules).
+struct StreamGuard {
+  gcp_ctx* c;
+  ~StreamGuard() {
+    cudaStreamSynchronize(c->stream[0]);
+    cudaStreamSynchronize(c->stream[1]);
+  }
+};
 
 extern "C" {
 
@@ -484,6 +495,7 @@ static int poseidon_host(gcp_ctx* ctx, const void* in, int len, size_t n, void* 
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  StreamGuard guard{ctx};
   if (len < 1 || len > (multi ? 4096 : 16))
     return ctx->fail(GCP_ERR_BAD_ARG, multi ? "the maximum number of inputs supported is 4096" : "bad inputs provided");
   if (n == 0) return GCP_OK;
@@ -620,6 +632,7 @@ static int smt_verify_host(gcp_ctx* ctx, int n_levels, size_t n, const void* roo
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  StreamGuard guard{ctx};
   const bool is_packed = siblings == nullptr;
   int rc = smt_check_args(ctx, n_levels, n, roots, is_packed ? (const void*)packed : siblings, old_keys, old_values, keys,
                           values, out_flags, out_status, fmt);
@@ -820,6 +833,8 @@ static int smt_process_host(gcp_ctx* ctx, int n_levels, size_t n, const void* ol
   if (!ctx) return GCP_ERR_BAD_ARG;
   const bool is_packed = siblings == nullptr;
   std::lock_guard<std::recursive_mutex> call_lk(ctx->mu);  // the scratch slots belong to this call until it returns
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  StreamGuard guard{ctx};
   {
     int rc = smt_process_check(ctx, n_levels, n, old_roots, is_packed ? (const void*)packed : siblings, old_keys,
                                old_values, is_old0, new_keys, new_values, fnc0, fnc1, new_roots, status, fmt);
@@ -834,7 +849,6 @@ static int smt_process_host(gcp_ctx* ctx, int n_levels, size_t n, const void* ol
     uint8_t* d_b[4];
     uint8_t* d_bad = nullptr;
     {
-      CU(cudaSetDevice(ctx->device), "cudaSetDevice");
       d_sib = ctx->buf(10, m * sib_bytes);
       for (int q = 0; q < 5; q++) d_e[q] = ctx->buf(11 + q, m * 32);
       void* d_out = ctx->buf(16, m * 32);
@@ -941,19 +955,25 @@ static int fixed_base_dev_locked(gcp_ctx* ctx, const void* d_scalars, size_t n, 
 }
 
 static int encrypt_dev_locked(gcp_ctx* ctx, const void* d_pk, int pk_per_item, const void* d_k, const void* d_m, size_t n,
-                              void* d_out, uint8_t* d_status, int fmt, cudaStream_t st, int xyz_slot) {
+                              void* d_out, uint8_t* d_status, int fmt, cudaStream_t st, int xyz_slot, int vb_slot) {
   int rc = check_fmt(ctx, fmt);
   if (rc != GCP_OK || n == 0) return rc;
   if (!d_pk || !d_k || !d_m || !d_out || !d_status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
   u32* xyz = (u32*)ctx->buf(xyz_slot, n * 192);
   if (!xyz) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
-  if (pk_per_item)
-    CU(launch_encrypt_per_key(ctx->d_tabG, (const u32*)d_pk, (const u32*)d_k, (const u32*)d_m, n, xyz, d_status, fmt, st),
-       "encrypt kernel");
-  else
+  if (pk_per_item) {
+    u32* scratch = (u32*)ctx->buf(vb_slot, varbase_scratch_bytes(0, n));
+    if (!scratch) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+    int nl = 0;
+    CU(launch_encrypt_per_key(ctx->d_tabG, (const u32*)d_pk, (const u32*)d_k, (const u32*)d_m, n, xyz, d_status, fmt, scratch,
+                              &nl, st),
+       "encrypt kernels");
+    ctx->launches += nl - 1;
+  } else {
     CU(launch_encrypt_shared(ctx->d_tabG, ctx->d_tabPK, ctx->d_flagPK, (const u32*)d_k, (const u32*)d_m, n, xyz, d_status,
                              fmt, st),
        "encrypt kernel");
+  }
   CU(launch_normalize(xyz, 2 * n, (u32*)d_out, d_status, 2, fmt, st), "normalize kernel");
   ctx->launches += 2;
   return GCP_OK;
@@ -1009,7 +1029,7 @@ int gcp_elgamal_encrypt_dev(gcp_ctx* ctx, const void* d_pub_key, int pk_per_item
     int rc = ensure_pk_table(ctx, d_pub_key, true, fmt, (cudaStream_t)stream);
     if (rc != GCP_OK) return rc;
   }
-  return encrypt_dev_locked(ctx, d_pub_key, pk_per_item, d_k, d_m, n, d_out_ct, d_status, fmt, (cudaStream_t)stream, 43);
+  return encrypt_dev_locked(ctx, d_pub_key, pk_per_item, d_k, d_m, n, d_out_ct, d_status, fmt, (cudaStream_t)stream, 43, 98);
 }
 
 int gcp_elgamal_add_dev(gcp_ctx* ctx, const void* d_a, const void* d_b, size_t n, void* d_out, uint8_t* d_status, int fmt,
@@ -1073,6 +1093,7 @@ int gcp_elgamal_encrypt_tally(gcp_ctx* ctx, const void* pub_key, const void* k, 
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  StreamGuard guard{ctx};
   int rc = encrypt_tally_check(ctx, pub_key, k, m, n_ballots, n_fields, out, status, fmt);
   if (rc != GCP_OK) return rc;
   rc = ensure_pk_table(ctx, pub_key, false, fmt, ctx->stream[0]);
@@ -1136,6 +1157,7 @@ static int elgamal_host(gcp_ctx* ctx, int kind, const void* pk, int pk_per_item,
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  StreamGuard guard{ctx};
   int rc = check_fmt(ctx, fmt);
   if (rc != GCP_OK || n == 0) return rc;
   if (!in0 || !out || !status || ((kind == 1 || kind == 2) && !in1) || (kind == 1 && !pk))
@@ -1165,7 +1187,7 @@ static int elgamal_host(gcp_ctx* ctx, int kind, const void* pk, int pk_per_item,
     if (dpk) CU(cudaMemcpyAsync(dpk, (const char*)pk + off * 64, m * 64, cudaMemcpyHostToDevice, st), "H2D");
     switch (kind) {
       case 0: rc = fixed_base_dev_locked(ctx, d0, m, dout, dst, fmt, st, b + 5); break;
-      case 1: rc = encrypt_dev_locked(ctx, pk_per_item ? dpk : (const void*)ctx->d_base_xy, pk_per_item, d0, d1, m, dout, dst, fmt, st, b + 5); break;
+      case 1: rc = encrypt_dev_locked(ctx, pk_per_item ? dpk : (const void*)ctx->d_base_xy, pk_per_item, d0, d1, m, dout, dst, fmt, st, b + 5, 99 + s); break;
       case 2: rc = add_dev_locked(ctx, d0, d1, m, dout, dst, fmt, st, b + 5); break;
       default:
         CU(cudaMemsetAsync(dst, 0, m, st), "memset status");
@@ -1206,6 +1228,7 @@ static int ct_elementwise_host(gcp_ctx* ctx, int kind, const uint8_t* sel, const
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  StreamGuard guard{ctx};
   if (n == 0) return GCP_OK;
   if (!a || !b || !out || !status || (kind == 1 && !sel)) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
   const size_t out_b = kind == 0 ? 1 : 128;
@@ -1253,6 +1276,7 @@ int gcp_elgamal_tally(gcp_ctx* ctx, const void* ct, size_t n_ballots, int n_fiel
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  StreamGuard guard{ctx};
   int rc = check_fmt(ctx, fmt);
   if (rc != GCP_OK) return rc;
   if (n_fields < 1 || n_fields > 64) return ctx->fail(GCP_ERR_BAD_ARG, "n_fields must be in [1, 64]");
@@ -1333,6 +1357,7 @@ int gcp_ballot_batch(gcp_ctx* ctx, int n_levels, size_t n_voters, const void* ro
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  StreamGuard guard{ctx};
   const bool is_packed = siblings == nullptr;
   const size_t n = n_voters;
   int rc = encrypt_tally_check(ctx, pub_key, k, m, n, n_fields, out_tally, out_tally_status, fmt);
@@ -1483,8 +1508,7 @@ static int per_item_pipeline(gcp_ctx* ctx, const Upload* ins, int n_ins, size_t 
     uint8_t* d_flags = (uint8_t*)ctx->buf(s ? 92 : 77, m);
     uint8_t* d_status = (uint8_t*)ctx->buf(s ? 93 : 78, m);
     if (!d_flags || !d_status) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
-    CU(launch(d, m, d_flags, d_status, st), what);
-    ctx->launches++;
+    CU(launch(d, m, d_flags, d_status, s, st), what);
     CU(cudaMemcpyAsync(out_flags + off, d_flags, m, cudaMemcpyDeviceToHost, st), "D2H");
     CU(cudaMemcpyAsync(status + off, d_status, m, cudaMemcpyDeviceToHost, st), "D2H");
   }
@@ -1494,19 +1518,93 @@ static int per_item_pipeline(gcp_ctx* ctx, const Upload* ins, int n_ins, size_t 
 }
 }  // extern "C++"
 
+// curve.ScalarMul (gnark twistededwards; call sites elgamal/encrypt.go:55, ciphertext.go:58,147-160): out[i] = [s[i]]P[i],
+// or with a second base [s[i]]P[i] + [s2[i]]P2[i] in one pass that shares the doublings.
+static int scalar_mul_dev_locked(gcp_ctx* ctx, const void* d_points, const void* d_scalars, const void* d_points2,
+                                 const void* d_scalars2, size_t n, void* d_out, uint8_t* d_status, int fmt, cudaStream_t st,
+                                 int slot) {
+  int rc = check_fmt(ctx, fmt);
+  if (rc != GCP_OK || n == 0) return rc;
+  if (!d_points || !d_scalars || !d_out || !d_status || ((d_points2 == nullptr) != (d_scalars2 == nullptr)))
+    return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  const int nb = d_points2 ? 2 : 1;
+  u32* scratch = (u32*)ctx->buf(slot, scalar_mul_scratch_bytes(n, nb) + n * 128);
+  if (!scratch) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+  u32* ext = scratch + scalar_mul_scratch_bytes(n, nb) / 4;
+  int nl = 0;
+  CU(launch_scalar_mul((const u32*)d_points, (const u32*)d_scalars, (const u32*)d_points2, (const u32*)d_scalars2, n, ext,
+                       d_status, fmt, scratch, &nl, st),
+     "scalar-mul kernels");
+  CU(launch_normalize(ext, n, (u32*)d_out, d_status, 1, fmt, st, 32), "normalize kernel");
+  ctx->launches += nl + 1;
+  return GCP_OK;
+}
+
+int gcp_elgamal_scalar_mul_dev(gcp_ctx* ctx, const void* d_points, const void* d_scalars, const void* d_points2,
+                               const void* d_scalars2, size_t n, void* d_out_points, uint8_t* d_status, int fmt,
+                               void* stream) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  return scalar_mul_dev_locked(ctx, d_points, d_scalars, d_points2, d_scalars2, n, d_out_points, d_status, fmt,
+                               (cudaStream_t)stream, 98);
+}
+
+int gcp_elgamal_scalar_mul(gcp_ctx* ctx, const void* points, const void* scalars, const void* points2, const void* scalars2,
+                           size_t n, void* out_points, uint8_t* status, int fmt) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  StreamGuard guard{ctx};
+  int rc = check_fmt(ctx, fmt);
+  if (rc != GCP_OK || n == 0) return rc;
+  if (!points || !scalars || !out_points || !status || ((points2 == nullptr) != (scalars2 == nullptr)))
+    return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  const int n_ins = points2 ? 4 : 2;
+  const Upload ins[4] = {{points, 64}, {scalars, 32}, {points2, 64}, {scalars2, 32}};
+  const size_t chunk = std::min<size_t>(n, (size_t)1 << 18);
+  size_t k = 0;
+  for (size_t off = 0; off < n; off += chunk, k++) {
+    const size_t m = std::min(chunk, n - off);
+    const int s = (int)(k & 1);
+    cudaStream_t st = ctx->stream[s];
+    void* d[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < n_ins; i++) {
+      d[i] = ctx->buf((s ? 86 : 70) + i, m * ins[i].bytes_per_item);
+      if (!d[i]) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+      GCP_TRY(h2d_copy(ctx, d[i], (const char*)ins[i].host + off * ins[i].bytes_per_item, m * ins[i].bytes_per_item, st));
+    }
+    void* d_out = ctx->buf(s ? 91 : 76, m * 64);
+    uint8_t* d_status = (uint8_t*)ctx->buf(s ? 93 : 78, m);
+    if (!d_out || !d_status) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+    GCP_TRY(scalar_mul_dev_locked(ctx, d[0], d[1], d[2], d[3], m, d_out, d_status, fmt, st, 96 + s));
+    CU(cudaMemcpyAsync((char*)out_points + off * 64, d_out, m * 64, cudaMemcpyDeviceToHost, st), "D2H");
+    CU(cudaMemcpyAsync(status + off, d_status, m, cudaMemcpyDeviceToHost, st), "D2H");
+  }
+  CU(cudaStreamSynchronize(ctx->stream[0]), "stream sync");
+  CU(cudaStreamSynchronize(ctx->stream[1]), "stream sync");
+  return GCP_OK;
+}
+
 int gcp_elgamal_assert_decrypt(gcp_ctx* ctx, const void* ct, const void* priv_keys, const void* msgs, size_t n,
                                uint8_t* out_flags, uint8_t* status, int fmt) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  StreamGuard guard{ctx};
   int rc = check_fmt(ctx, fmt);
   if (rc != GCP_OK || n == 0) return rc;
   if (!ct || !priv_keys || !msgs || !out_flags || !status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
   Upload ins[3] = {{ct, 128}, {priv_keys, 32}, {msgs, 32}};
-  return per_item_pipeline(ctx, ins, 3, n, out_flags, status, "assert-decrypt kernel",
-                           [&](void** d, size_t m, uint8_t* d_flags, uint8_t* d_status, cudaStream_t st) {
-                             return launch_assert_decrypt(ctx->d_tabG, (const u32*)d[0], (const u32*)d[1], (const u32*)d[2], m,
-                                                          d_flags, d_status, fmt, st);
+  return per_item_pipeline(ctx, ins, 3, n, out_flags, status, "assert-decrypt kernels",
+                           [&](void** d, size_t m, uint8_t* d_flags, uint8_t* d_status, int s, cudaStream_t st) {
+                             u32* scratch = (u32*)ctx->buf(96 + s, varbase_scratch_bytes(1, m));
+                             if (!scratch) return cudaErrorMemoryAllocation;
+                             int nl = 0;
+                             cudaError_t e = launch_assert_decrypt(ctx->d_tabG, (const u32*)d[0], (const u32*)d[1],
+                                                                   (const u32*)d[2], m, d_flags, d_status, fmt, scratch, &nl, st);
+                             ctx->launches += nl;
+                             return e;
                            });
 }
 
@@ -1516,15 +1614,21 @@ int gcp_elgamal_verify_decryption_proof(gcp_ctx* ctx, const void* pub_keys, cons
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  StreamGuard guard{ctx};
   int rc = check_fmt(ctx, fmt);
   if (rc != GCP_OK || n == 0) return rc;
   if (!pub_keys || !ct || !msgs || !a1 || !a2 || !z || !out_flags || !status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
   Upload ins[6] = {{pub_keys, 64}, {ct, 128}, {msgs, 32}, {a1, 64}, {a2, 64}, {z, 32}};
-  return per_item_pipeline(ctx, ins, 6, n, out_flags, status, "decryption-proof kernel",
-                           [&](void** d, size_t m, uint8_t* d_flags, uint8_t* d_status, cudaStream_t st) {
-                             return launch_decryption_proof(ctx->d_tabG, ctx->tab[13], (const u32*)d[0], (const u32*)d[1],
-                                                            (const u32*)d[2], (const u32*)d[3], (const u32*)d[4],
-                                                            (const u32*)d[5], m, d_flags, d_status, fmt, st);
+  return per_item_pipeline(ctx, ins, 6, n, out_flags, status, "decryption-proof kernels",
+                           [&](void** d, size_t m, uint8_t* d_flags, uint8_t* d_status, int s, cudaStream_t st) {
+                             u32* scratch = (u32*)ctx->buf(96 + s, varbase_scratch_bytes(2, m));
+                             if (!scratch) return cudaErrorMemoryAllocation;
+                             int nl = 0;
+                             cudaError_t e = launch_decryption_proof(ctx->d_tabG, ctx->tab[13], (const u32*)d[0], (const u32*)d[1],
+                                                                     (const u32*)d[2], (const u32*)d[3], (const u32*)d[4],
+                                                                     (const u32*)d[5], m, d_flags, d_status, fmt, scratch, &nl, st);
+                             ctx->launches += nl;
+                             return e;
                            });
 }
 
@@ -1533,14 +1637,21 @@ int gcp_eddsa_verify(gcp_ctx* ctx, const void* pub_keys_te, const void* sig_r_te
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  StreamGuard guard{ctx};
   int rc = check_fmt(ctx, fmt);
   if (rc != GCP_OK || n == 0) return rc;
   if (!pub_keys_te || !sig_r_te || !sig_s || !msgs || !out_flags || !status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
   Upload ins[4] = {{pub_keys_te, 64}, {sig_r_te, 64}, {sig_s, 32}, {msgs, 32}};
-  return per_item_pipeline(ctx, ins, 4, n, out_flags, status, "eddsa kernel",
-                           [&](void** d, size_t m, uint8_t* d_flags, uint8_t* d_status, cudaStream_t st) {
-                             return launch_eddsa_verify(ctx->d_tabG, ctx->tab[6], (const u32*)d[0], (const u32*)d[1],
-                                                        (const u32*)d[2], (const u32*)d[3], m, d_flags, d_status, fmt, st);
+  return per_item_pipeline(ctx, ins, 4, n, out_flags, status, "eddsa kernels",
+                           [&](void** d, size_t m, uint8_t* d_flags, uint8_t* d_status, int s, cudaStream_t st) {
+                             u32* scratch = (u32*)ctx->buf(96 + s, varbase_scratch_bytes(3, m));
+                             if (!scratch) return cudaErrorMemoryAllocation;
+                             int nl = 0;
+                             cudaError_t e = launch_eddsa_verify(ctx->d_tabG, ctx->tab[6], (const u32*)d[0], (const u32*)d[1],
+                                                                 (const u32*)d[2], (const u32*)d[3], m, d_flags, d_status, fmt,
+                                                                 scratch, &nl, st);
+                             ctx->launches += nl;
+                             return e;
                            });
 }
 
@@ -1548,6 +1659,7 @@ static int te_rte_host(gcp_ctx* ctx, const void* in, size_t n_points, void* out,
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  StreamGuard guard{ctx};
   if (n_points == 0) return GCP_OK;
   if (!in || !out || !status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
   Upload ins[1] = {{in, 64}};
@@ -1600,6 +1712,7 @@ int gcp_mimc7_hash(gcp_ctx* ctx, const void* in, int len, size_t n, void* out, u
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);  // held over upload, kernel and read-back: the slots are this call's
   {
     CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    StreamGuard guard{ctx};
     if (len < 1 || len > 62) return ctx->fail(GCP_ERR_BAD_ARG, "MiMC7 takes 1..62 inputs");
     if (n == 0) return GCP_OK;
     if (!in || !out || !status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
@@ -1703,6 +1816,7 @@ static int p2_host(gcp_ctx* ctx, const void* in, int len, size_t n, void* out, u
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);  // held for the whole call: the scratch slots are this call's
   {
     CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    StreamGuard guard{ctx};
     int rc = p2_check(ctx, fmt);
     if (rc != GCP_OK) return rc;
     if (!perm && len != 2 && len != 3) return ctx->fail(GCP_ERR_BAD_ARG, "poseidon2: need 2 or 3 limbs");
@@ -1761,6 +1875,7 @@ int gcp_keccak_address(gcp_ctx* ctx, const void* pub_xy_be, size_t n, void* out_
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  StreamGuard guard{ctx};
   if (n == 0) return GCP_OK;
   if (!pub_xy_be || !out_addr) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
   const size_t chunk = (size_t)1 << 22;
@@ -1783,3 +1898,4 @@ int gcp_keccak_address(gcp_ctx* ctx, const void* pub_xy_be, size_t n, void* out_
 }
 
 }  // extern "C"
+

@@ -119,193 +119,6 @@ __device__ __forceinline__ void ext_double(ExtPoint& p) {
   fr_mul(p.Z, f, g);
 }
 
-// ---- variable-base scalar multiplication: signed 4-bit windows over a per-thread table -------------------------
-// curve.ScalarMul(P, k) of the reference (gnark std/algebra/native/twistededwards, un-vendored; call sites
-// /root/reference/elgamal/encrypt.go:55, elgamal/ciphertext.go:58,147-160, ecc/bn254/eddsa/verifier.go:71-80)
-// is [k]P for the integer k in [0, r).  Here: k = sum d_i 16^i with d_i in [-7, 8] (64 digits; the top one is <= 4
-// because k < 2^254), table j -> [j+1]P for j = 0..7 in "cached" form (Y-X, Y+X, 2dT, 2Z: an addition is 8
-// multiplies), MSB first: four doublings (the first three without T) and at most one table addition per digit.
-// 256 doublings + 64 additions instead of 254 + ~254 for bit-serial double-and-add on 32 divergent lanes.
-struct CachedPoint {
-  u32 ymx[8], ypx[8], t2d[8], z2[8];
-};
-
-__device__ __forceinline__ void ext_to_cached(CachedPoint& c, const ExtPoint& p) {
-  const u32 d2[8] = GCP_ED_2D_MONT;
-  fr_sub(c.ymx, p.Y, p.X);
-  fr_add(c.ypx, p.Y, p.X);
-  fr_mul(c.t2d, p.T, d2);
-  fr_add(c.z2, p.Z, p.Z);
-}
-
-// P += C or P -= C (negation of a cached point: swap ymx/ypx, negate t2d)
-__device__ __forceinline__ void ext_add_cached(ExtPoint& p, const CachedPoint& q, bool negate) {
-  u32 a[8], b[8], c[8], d[8], e[8], f[8], g[8], h[8], t[8], u[8];
-  fr_sub(t, p.Y, p.X);
-  fr_add(u, p.Y, p.X);
-#pragma unroll
-  for (int l = 0; l < 8; l++) {
-    a[l] = negate ? q.ypx[l] : q.ymx[l];
-    b[l] = negate ? q.ymx[l] : q.ypx[l];
-  }
-  fr_mul(a, t, a);
-  fr_mul(b, u, b);
-  fr_mul(c, p.T, q.t2d);
-  fr_mul(d, p.Z, q.z2);
-  fr_sub(e, b, a);
-  fr_sub(t, d, c);
-  fr_add(u, d, c);
-#pragma unroll
-  for (int l = 0; l < 8; l++) {
-    f[l] = negate ? u[l] : t[l];
-    g[l] = negate ? t[l] : u[l];
-  }
-  fr_add(h, b, a);
-  fr_mul(p.X, e, f);
-  fr_mul(p.Y, g, h);
-  fr_mul(p.T, e, h);
-  fr_mul(p.Z, f, g);
-}
-
-// Code size decides these kernels: with the doubling (~26 KB of SASS) and the addition (~27 KB) inlined even once each,
-// ncu showed the window loop fetch-bound (stall_no_instruction 1.6-2.2 per issue, instruction-cache hit rate 74-78 %,
-// FMA-heavy pipe 59-63 %).  Here both are written over ONE out-of-line multiplier and ONE out-of-line squaring
-// (operands through local memory, L1-resident): the whole loop is a few KB.
-__device__ __noinline__ void fr_mul_call(u32* r, const u32* a, const u32* b) {
-  u32 x[8], y[8], z[8];
-#pragma unroll
-  for (int l = 0; l < 8; l++) {
-    x[l] = a[l];
-    y[l] = b[l];
-  }
-  fr_mul(z, x, y);
-#pragma unroll
-  for (int l = 0; l < 8; l++) r[l] = z[l];
-}
-__device__ __noinline__ void fr_sqr_call(u32* r, const u32* a) {
-  u32 x[8], z[8];
-#pragma unroll
-  for (int l = 0; l < 8; l++) x[l] = a[l];
-  fr_sqr(z, x);
-#pragma unroll
-  for (int l = 0; l < 8; l++) r[l] = z[l];
-}
-
-__device__ __noinline__ void ext_double_call(ExtPoint& p, bool with_t) {
-  u32 a[8], b[8], c[8], e[8], f[8], g[8], h[8], t[8];
-  fr_sqr_call(a, p.X);
-  fr_sqr_call(b, p.Y);
-  fr_sqr_call(t, p.Z);
-  fr_add(c, t, t);
-  fr_add(t, p.X, p.Y);
-  fr_sqr_call(e, t);
-  fr_sub(e, e, a);
-  fr_sub(e, e, b);   // E = 2XY
-  fr_sub(g, b, a);   // G = -A + B  (a = -1)
-  fr_sub(f, g, c);   // F = G - C
-  fr_add(t, a, b);
-  fr_neg(h, t);      // H = -A - B
-  fr_mul_call(p.X, e, f);
-  fr_mul_call(p.Y, g, h);
-  if (with_t) fr_mul_call(p.T, e, h);
-  fr_mul_call(p.Z, f, g);
-}
-__device__ __noinline__ void ext_add_cached_call(ExtPoint& p, const CachedPoint& q, bool negate) {
-  u32 a[8], b[8], c[8], d[8], e[8], f[8], g[8], h[8], t[8], u[8];
-  fr_sub(t, p.Y, p.X);
-  fr_add(u, p.Y, p.X);
-  fr_mul_call(a, t, negate ? q.ypx : q.ymx);
-  fr_mul_call(b, u, negate ? q.ymx : q.ypx);
-  fr_mul_call(c, p.T, q.t2d);
-  fr_mul_call(d, p.Z, q.z2);
-  fr_sub(e, b, a);
-  fr_sub(t, d, c);
-  fr_add(u, d, c);
-#pragma unroll
-  for (int l = 0; l < 8; l++) {
-    f[l] = negate ? u[l] : t[l];
-    g[l] = negate ? t[l] : u[l];
-  }
-  fr_add(h, b, a);
-  fr_mul_call(p.X, e, f);
-  fr_mul_call(p.Y, g, h);
-  fr_mul_call(p.T, e, h);
-  fr_mul_call(p.Z, f, g);
-}
-
-// ext_add over the out-of-line multiplier (same formulas, same results): for the once-per-item additions of the proof
-// kernels, whose inlined copies (~30 KB each) are fetched from L2 by every warp that passes through them
-__device__ __noinline__ void ext_add_call(ExtPoint& p, const ExtPoint& q) {
-  const u32 d2[8] = GCP_ED_2D_MONT;
-  u32 a[8], b[8], c[8], d[8], e[8], f[8], g[8], h[8], t[8], u[8];
-  fr_sub(t, p.Y, p.X);
-  fr_sub(u, q.Y, q.X);
-  fr_mul_call(a, t, u);
-  fr_add(t, p.Y, p.X);
-  fr_add(u, q.Y, q.X);
-  fr_mul_call(b, t, u);
-  fr_mul_call(t, p.T, q.T);
-  fr_mul_call(c, t, d2);
-  fr_mul_call(t, p.Z, q.Z);
-  fr_add(d, t, t);
-  fr_sub(e, b, a);
-  fr_sub(f, d, c);
-  fr_add(g, d, c);
-  fr_add(h, b, a);
-  fr_mul_call(p.X, e, f);
-  fr_mul_call(p.Y, g, h);
-  fr_mul_call(p.T, e, h);
-  fr_mul_call(p.Z, f, g);
-}
-
-// out = [k]base for an on-curve base and an integer k < 2^254 (little-endian words)
-__device__ __noinline__ void ext_scalar_mul_windowed(ExtPoint& out, const ExtPoint& base, const u32 (&k)[8]) {
-  CachedPoint tab[8];  // local memory, 1 KB per thread: [1]P .. [8]P
-  {
-    ExtPoint m = base;
-    ext_to_cached(tab[0], m);
-#pragma unroll 1
-    for (int j = 1; j < 8; j++) {
-      if (j == 1)
-        ext_double_call(m, true);
-      else
-        ext_add_cached_call(m, tab[0], false);
-      ext_to_cached(tab[j], m);
-    }
-  }
-  // digits MSB first need the carries from below: recode once into 64 signed nibbles packed as (|d|, sign)
-  u32 mag[8], sgn[2];  // 4 bits of |d| per digit; one sign bit per digit
-#pragma unroll
-  for (int w = 0; w < 8; w++) mag[w] = 0;
-  sgn[0] = sgn[1] = 0;
-  u32 carry = 0;
-#pragma unroll
-  for (int w = 0; w < 8; w++) {
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-      u32 v = ((k[w] >> (q * 4)) & 15u) + carry;
-      carry = v > 8u ? 1u : 0u;
-      u32 m = carry ? 16u - v : v;
-      mag[w] |= m << (q * 4);
-      sgn[w >> 2] |= carry << ((w & 3) * 8 + q);
-    }
-  }
-  ExtPoint acc;
-  ext_identity(acc);
-#pragma unroll 1
-  for (int i = 63; i >= 0; i--) {
-#pragma unroll 1
-    for (int d = 0; d < 4; d++) ext_double_call(acc, d == 3);
-    u32 mw = mag[0], sw = sgn[0];
-#pragma unroll
-    for (int w = 1; w < 8; w++) mw = ((i >> 3) == w) ? mag[w] : mw;
-    sw = (i >> 5) ? sgn[1] : sw;
-    const u32 m = (mw >> ((i & 7) * 4)) & 15u;
-    if (m) ext_add_cached_call(acc, tab[m - 1], ((sw >> (i & 31)) & 1u) != 0);
-  }
-  out = acc;
-}
-
 // affine (x, y) in lazy Montgomery form -> extended
 __device__ __forceinline__ void ext_from_affine(ExtPoint& p, const u32 (&x)[8], const u32 (&y)[8]) {
   fr_copy(p.X, x);

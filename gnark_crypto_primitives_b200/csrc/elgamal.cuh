@@ -180,12 +180,6 @@ __device__ __forceinline__ void fixed_base_accumulate(ExtPoint& acc, const u32 (
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-// One out-of-line copy of the window loop for kernels that run it more than once per item or beside a lot of other code
-// (per-item-key Encrypt, the proof kernels): their inlined copies made the kernels 135-400 KB and fetch-bound.
-__device__ __noinline__ void fixed_base_accumulate_ool(ExtPoint& acc, const u32 (&k)[8], const u32* __restrict__ tab) {
-  fixed_base_accumulate(acc, k, tab);
-}
-
 __device__ __forceinline__ void store_ext_xyz(u32* o, const ExtPoint& p) {
   store_fr(o, p.X);
   store_fr(o + 8, p.Y);
@@ -254,46 +248,10 @@ __global__ void __launch_bounds__(128, 4) encrypt_shared_kernel(const u32* __res
   if (!second) status[idx] = !canon ? GCP_STATUS_NONCANONICAL : (!pk_ok ? GCP_STATUS_OFF_CURVE : GCP_STATUS_OK);
 }
 
-// ---- Encrypt with a public key per item: [k]PK by signed 4-bit windows (edwards.cuh) -------------------------------------------------
-__global__ void __launch_bounds__(128, 5) encrypt_per_key_kernel(const u32* __restrict__ tabG, const u32* __restrict__ pks,
-                                                              const u32* __restrict__ ks, const u32* __restrict__ ms, size_t n,
-                                                              u32* __restrict__ out_xyz, u8* __restrict__ status, int mont) {
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n) return;
-  bool canon = true;
-  u32 k[8], m[8], px[8], py[8], xs[8], ys[8];
-  load_scalar(k, canon, ks + idx * 8, mont);
-  load_scalar(m, canon, ms + idx * 8, mont);
-  load_fr(xs, pks + idx * 16);
-  load_fr(ys, pks + idx * 16 + 8);
-  canon = canon && fr_is_canonical(xs) && fr_is_canonical(ys);
-  if (mont) {
-    fr_copy(px, xs);
-    fr_copy(py, ys);
-  } else {
-    fr_to_mont(px, xs);
-    fr_to_mont(py, ys);
-  }
-  bool pk_ok = canon && ed_is_on_curve(px, py);
-  ExtPoint c1, c2;
-  ext_identity(c1);
-  ext_identity(c2);
-  if (pk_ok) {
-    fixed_base_accumulate_ool(c1, k, tabG);
-    ExtPoint base;
-    ext_from_affine(base, px, py);
-    ext_scalar_mul_windowed(c2, base, k);  // k < r < 2^254
-    fixed_base_accumulate_ool(c2, m, tabG);
-  }
-  store_ext_xyz(out_xyz + idx * 48, c1);
-  store_ext_xyz(out_xyz + idx * 48 + 24, c2);
-  status[idx] = !canon ? GCP_STATUS_NONCANONICAL : (!pk_ok ? GCP_STATUS_OFF_CURVE : GCP_STATUS_OK);
-}
-
 // ---- (X, Y, Z) -> canonical affine, Montgomery batch inversion over BATCH_INV points per thread ----------------
-// xyz: n_points x 24 words; out: n_points x 16 words.  status (optional) is indexed by point / pts_per_item.
+// xyz: n_points x xyz_words words (24, or 32 for extended points with T behind Z); out: n_points x 16 words.  status (optional) is indexed by point / pts_per_item.
 __global__ void __launch_bounds__(128) normalize_kernel(const u32* __restrict__ xyz, size_t n_points, u32* __restrict__ out,
-                                                        u8* __restrict__ status, int pts_per_item, int mont) {
+                                                        u8* __restrict__ status, int pts_per_item, int mont, int xyz_words) {
   size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
   if (tid >= n_points) return;
@@ -306,7 +264,7 @@ __global__ void __launch_bounds__(128) normalize_kernel(const u32* __restrict__ 
     size_t p = tid + (size_t)j * stride;
     if (p >= n_points) break;
     u32 z[8];
-    load_fr(z, xyz + p * 24 + 16);
+    load_fr(z, xyz + p * (size_t)xyz_words + 16);
     u32 zc[8];
     fr_copy(zc, z);
     fr_canon(zc);
@@ -325,7 +283,7 @@ __global__ void __launch_bounds__(128) normalize_kernel(const u32* __restrict__ 
   for (int j = cnt - 1; j >= 0; j--) {
     size_t p = tid + (size_t)j * stride;
     u32 z[8], zi[8], X[8], Y[8], x[8], y[8];
-    load_fr(z, xyz + p * 24 + 16);
+    load_fr(z, xyz + p * (size_t)xyz_words + 16);
     {
       u32 zc[8];
       fr_copy(zc, z);
@@ -341,8 +299,8 @@ __global__ void __launch_bounds__(128) normalize_kernel(const u32* __restrict__ 
     } else {
       fr_copy(zi, inv);
     }
-    load_fr(X, xyz + p * 24);
-    load_fr(Y, xyz + p * 24 + 8);
+    load_fr(X, xyz + p * (size_t)xyz_words);
+    load_fr(Y, xyz + p * (size_t)xyz_words + 8);
     fr_mul(x, X, zi);
     fr_mul(y, Y, zi);
     u32 ox[8], oy[8];

@@ -468,6 +468,26 @@ __device__ __forceinline__ void fr_sqr(u32 (&r)[8], const u32 (&a)[8]) {
   wide_redc(w, r);
 }
 
+// two independent squarings with their reductions advancing together (two chains in flight)
+__device__ __forceinline__ void fr_sqr2(u32 (&r1)[8], const u32 (&a1)[8], u32 (&r2)[8], const u32 (&a2)[8]) {
+  Wide w1, w2;
+  wide_zero(w1);
+  wide_zero(w2);
+  wide_sqr(w1, a1);
+  wide_sqr(w2, a2);
+  u32 c1 = 0, c2 = 0;
+  redc_row<0>(w1, c1); redc_row<0>(w2, c2);
+  redc_row<1>(w1, c1); redc_row<1>(w2, c2);
+  redc_row<2>(w1, c1); redc_row<2>(w2, c2);
+  redc_row<3>(w1, c1); redc_row<3>(w2, c2);
+  redc_row<4>(w1, c1); redc_row<4>(w2, c2);
+  redc_row<5>(w1, c1); redc_row<5>(w2, c2);
+  redc_row<6>(w1, c1); redc_row<6>(w2, c2);
+  redc_row<7>(w1, c1); redc_row<7>(w2, c2);
+  wide_redc_finish(w1, c1, r1);
+  wide_redc_finish(w2, c2, r2);
+}
+
 // Several independent multiplications advanced row by row together (CIOS order each), so that a thread has that
 // many carry / reduction chains in flight.  Used where the operands are all ready at once (curve addition formulas).
 #define GCP_MULN_ROW2(I)                                \
@@ -598,6 +618,14 @@ __device__ __forceinline__ void fr_set_one(u32 (&r)[8]) {
 __device__ __forceinline__ void load_fr(u32 (&r)[8], const void* p) {
   const uint4* q = reinterpret_cast<const uint4*>(p);
   uint4 x = __ldg(q), y = __ldg(q + 1);
+  r[0] = x.x; r[1] = x.y; r[2] = x.z; r[3] = x.w;
+  r[4] = y.x; r[5] = y.y; r[6] = y.z; r[7] = y.w;
+}
+
+// the same through the coherent path (for data this kernel wrote itself)
+__device__ __forceinline__ void load_fr_plain(u32 (&r)[8], const void* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 x = q[0], y = q[1];
   r[0] = x.x; r[1] = x.y; r[2] = x.z; r[3] = x.w;
   r[4] = y.x; r[5] = y.y; r[6] = y.z; r[7] = y.w;
 }

@@ -7,6 +7,7 @@
 #include "elgamal.cuh"
 #include "keccak.cuh"
 #include "proofs.cuh"
+#include "varbase.cuh"
 #include "mimc7.cuh"
 #include "poseidon2.cuh"
 #include "kernels.h"
@@ -322,18 +323,11 @@ cudaError_t launch_encrypt_shared(const u32* tabG, const u32* tabPK, const u32* 
   return cudaGetLastError();
 }
 
-cudaError_t launch_encrypt_per_key(const u32* tabG, const u32* pks, const u32* ks, const u32* ms, size_t n, u32* out_xyz,
-                                   u8* status, int mont, cudaStream_t stream) {
-  if (n == 0) return cudaSuccess;
-  encrypt_per_key_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(tabG, pks, ks, ms, n, out_xyz, status, mont);
-  return cudaGetLastError();
-}
-
 cudaError_t launch_normalize(const u32* xyz, size_t n_points, u32* out, u8* status, int pts_per_item, int mont,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, int xyz_words) {
   if (n_points == 0) return cudaSuccess;
   size_t threads = (n_points + BATCH_INV - 1) / BATCH_INV;
-  normalize_kernel<<<blocks_for(threads, 128), 128, 0, stream>>>(xyz, n_points, out, status, pts_per_item, mont);
+  normalize_kernel<<<blocks_for(threads, 128), 128, 0, stream>>>(xyz, n_points, out, status, pts_per_item, mont, xyz_words);
   return cudaGetLastError();
 }
 
@@ -398,32 +392,109 @@ cudaError_t launch_keccak_address(const u8* in, size_t n, u8* out, cudaStream_t 
   return cudaGetLastError();
 }
 
-cudaError_t launch_assert_decrypt(const u32* tabG, const u32* cts, const u32* privs, const u32* msgs, size_t n, u8* flags,
-                                  u8* status, int mont, cudaStream_t stream) {
+// ---------------------------------------------------------------------------------------------------
+// Variable-base family (varbase.cuh): pre pass -> [Poseidon batch] -> window kernel(s) -> post pass.
+// `scratch` holds the per-item intermediates (varbase_scratch_bytes), arrays laid out one after the other.
+// ---------------------------------------------------------------------------------------------------
+static cudaError_t launch_varbase_window(const u32* bases, const u32* s0, const u32* s1, int n_bases, size_t n,
+                                         const u8* status, u32* table, u32* out, cudaStream_t stream) {
+  VarbaseArgs a;
+  a.bases = bases;
+  a.scalars[0] = s0;
+  a.scalars[1] = s1 ? s1 : s0;
+  a.n_bases = n_bases;
+  a.n = n;
+  a.status = status;
+  a.table = table;
+  a.out = out;
+  const size_t smem = (size_t)VB_SLOTS * 2 * VB_THREADS * sizeof(uint4);
+  cudaFuncSetAttribute(varbase_window_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  varbase_window_kernel<<<blocks_for(n, VB_THREADS), VB_THREADS, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+// words of scratch per item: kind 0 Encrypt with per-item keys, 1 AssertDecrypt, 2 DecryptionProof.Verify, 3 EdDSA
+static constexpr size_t VB_SCRATCH_WORDS[4] = {32 + 8 + 256 + 32, 32 + 8 + 32 + 256 + 32,
+                                               96 + 32 + 32 + 64 + 8 + 8 + 512 + 32 + 32, 40 + 32 + 32 + 8 + 256 + 32};
+size_t varbase_scratch_bytes(int kind, size_t n) { return VB_SCRATCH_WORDS[kind] * sizeof(u32) * n; }
+
+// curve.ScalarMul over a batch: out (n x 32 words, extended) = [s]P (+ [s2]P2).  scratch: (32 + 8 + 256) * n_bases words per item
+size_t scalar_mul_scratch_bytes(size_t n, int n_bases) { return (size_t)(296 * n_bases) * sizeof(u32) * n; }
+cudaError_t launch_scalar_mul(const u32* points, const u32* scalars, const u32* points2, const u32* scalars2, size_t n,
+                              u32* out, u8* status, int mont, u32* scratch, int* n_launches, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
-  assert_decrypt_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(tabG, cts, privs, msgs, n, flags, status, mont);
+  const int nb = points2 ? 2 : 1;
+  u32 *bases = scratch, *k0 = bases + n * 32 * nb, *k1 = k0 + n * 8, *table = k0 + n * 8 * nb;
+  scalar_mul_pre_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(points, scalars, points2, scalars2, n, mont, status, bases, k0, k1);
+  cudaError_t e = launch_varbase_window(bases, k0, nb == 2 ? k1 : nullptr, nb, n, status, table, out, stream);
+  if (e != cudaSuccess) return e;
+  *n_launches += 2;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_encrypt_per_key(const u32* tabG, const u32* pks, const u32* ks, const u32* ms, size_t n, u32* out_xyz,
+                                   u8* status, int mont, u32* scratch, int* n_launches, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  u32 *bases = scratch, *kint = bases + n * 32, *table = kint + n * 8, *res = table + n * 256;
+  encrypt_per_key_pre_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(pks, ks, ms, n, mont, status, bases, kint);
+  cudaError_t e = launch_varbase_window(bases, kint, nullptr, 1, n, status, table, res, stream);
+  if (e != cudaSuccess) return e;
+  encrypt_per_key_finish_kernel<<<blocks_for(2 * n, 128), 128, 0, stream>>>(tabG, ks, ms, res, status, n, mont, out_xyz);
+  *n_launches += 3;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_assert_decrypt(const u32* tabG, const u32* cts, const u32* privs, const u32* msgs, size_t n, u8* flags,
+                                  u8* status, int mont, u32* scratch, int* n_launches, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  u32 *bases = scratch, *kint = bases + n * 32, *rhs = kint + n * 8, *table = rhs + n * 32, *res = table + n * 256;
+  assert_decrypt_pre_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(tabG, cts, privs, msgs, n, mont, status, bases, kint, rhs);
+  cudaError_t e = launch_varbase_window(bases, kint, nullptr, 1, n, status, table, res, stream);
+  if (e != cudaSuccess) return e;
+  ext_compare_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(res, rhs, status, n, flags);
+  *n_launches += 3;
   return cudaGetLastError();
 }
 
 cudaError_t launch_decryption_proof(const u32* tabG, const PoseidonTable& tab13, const u32* pks, const u32* cts,
                                     const u32* msgs, const u32* a1s, const u32* a2s, const u32* zs, size_t n, u8* flags,
-                                    u8* status, int mont, cudaStream_t stream) {
+                                    u8* status, int mont, u32* scratch, int* n_launches, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
-  decryption_proof_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(tabG, tab13, pks, cts, msgs, a1s, a2s, zs, n, flags, status, mont);
+  u32 *hin = scratch, *zg = hin + n * 96, *base_pk = zg + n * 32, *base2 = base_pk + n * 32, *zint = base2 + n * 64;
+  u32 *e_int = zint + n * 8, *table = e_int + n * 8, *res1 = table + n * 512, *res2 = res1 + n * 32;
+  decryption_proof_pre_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(tabG, pks, cts, msgs, a1s, a2s, zs, n, mont, status, hin,
+                                                                      zg, base_pk, base2, zint);
+  // e = MultiHash(PK, PK, C1, D, A1, A2): 12 inputs = one Hash with t = 13; Montgomery in, integer out
+  cudaError_t e = launch_poseidon(tab13, hin, e_int, nullptr, n, 1, 12, 0, 1, 1, 0, 0, stream);
+  if (e != cudaSuccess) return e;
+  e = launch_varbase_window(base_pk, e_int, nullptr, 1, n, status, table, res1, stream);
+  if (e != cudaSuccess) return e;
+  e = launch_varbase_window(base2, zint, e_int, 2, n, status, table, res2, stream);
+  if (e != cudaSuccess) return e;
+  decryption_proof_post_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(a1s, a2s, zg, res1, res2, status, n, mont, flags);
+  *n_launches += 5;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_eddsa_verify(const u32* tabG, const PoseidonTable& tab6, const u32* pub_a, const u32* sig_r,
+                                const u32* sig_s, const u32* msgs, size_t n, u8* flags, u8* status, int mont, u32* scratch,
+                                int* n_launches, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  u32 *hin = scratch, *left = hin + n * 40, *base = left + n * 32, *h_int = base + n * 32, *table = h_int + n * 8;
+  u32* res = table + n * 256;
+  eddsa_pre_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(tabG, pub_a, sig_r, sig_s, msgs, n, mont, status, hin, left, base);
+  cudaError_t e = launch_poseidon(tab6, hin, h_int, nullptr, n, 1, 5, 0, 1, 1, 0, 0, stream);
+  if (e != cudaSuccess) return e;
+  e = launch_varbase_window(base, h_int, nullptr, 1, n, status, table, res, stream);
+  if (e != cudaSuccess) return e;
+  eddsa_post_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(sig_r, left, res, status, n, mont, flags);
+  *n_launches += 4;
   return cudaGetLastError();
 }
 
 cudaError_t launch_te_rte(const u32* in, size_t n_points, u32* out, u8* status, int to_rte, cudaStream_t stream) {
   if (n_points == 0) return cudaSuccess;
   te_rte_kernel<<<blocks_for(n_points, 256), 256, 0, stream>>>(in, n_points, out, status, to_rte);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_eddsa_verify(const u32* tabG, const PoseidonTable& tab6, const u32* pub_a, const u32* sig_r,
-                                const u32* sig_s, const u32* msgs, size_t n, u8* flags, u8* status, int mont,
-                                cudaStream_t stream) {
-  if (n == 0) return cudaSuccess;
-  eddsa_verify_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(tabG, tab6, pub_a, sig_r, sig_s, msgs, n, flags, status, mont);
   return cudaGetLastError();
 }
 

@@ -103,10 +103,17 @@ cudaError_t launch_fixed_base_mul(const u32* tabG, const u32* scalars, size_t n,
                                   cudaStream_t stream);
 cudaError_t launch_encrypt_shared(const u32* tabG, const u32* tabPK, const u32* pk_flag, const u32* ks, const u32* ms,
                                   size_t n, u32* out_xyz, u8* status, int mont, cudaStream_t stream);
+// Encrypt with per-item keys, AssertDecrypt, DecryptionProof.Verify, EdDSA (varbase.cuh): several kernels per call on
+// `stream`; scratch = varbase_scratch_bytes(kind, n) bytes (kind 0..3 in that order); *n_launches is incremented
+size_t varbase_scratch_bytes(int kind, size_t n);
+// out: n x 32 words (X, Y, Z, T) at scratch_result(...); the caller normalises with xyz_words = 32
+size_t scalar_mul_scratch_bytes(size_t n, int n_bases);
+cudaError_t launch_scalar_mul(const u32* points, const u32* scalars, const u32* points2, const u32* scalars2, size_t n,
+                              u32* out_ext, u8* status, int mont, u32* scratch, int* n_launches, cudaStream_t stream);
 cudaError_t launch_encrypt_per_key(const u32* tabG, const u32* pks, const u32* ks, const u32* ms, size_t n, u32* out_xyz,
-                                   u8* status, int mont, cudaStream_t stream);
+                                   u8* status, int mont, u32* scratch, int* n_launches, cudaStream_t stream);
 cudaError_t launch_normalize(const u32* xyz, size_t n_points, u32* out, u8* status, int pts_per_item, int mont,
-                             cudaStream_t stream);
+                             cudaStream_t stream, int xyz_words = 24);
 cudaError_t launch_ct_add(const u32* a, const u32* b, size_t n, u32* out_xyz, u8* status, int mont, cudaStream_t stream);
 cudaError_t launch_ct_neg(const u32* a, size_t n, u32* out, u8* status, cudaStream_t stream);
 cudaError_t launch_ct_is_equal(const u32* a, const u32* b, size_t n, u8* flags, u8* status, cudaStream_t stream);
@@ -116,14 +123,14 @@ cudaError_t launch_encrypt_tally(const u32* tabG, const u32* tabPK, const u32* k
                                  cudaStream_t stream);
 cudaError_t launch_keccak_address(const u8* in, size_t n, u8* out, cudaStream_t stream);
 cudaError_t launch_assert_decrypt(const u32* tabG, const u32* cts, const u32* privs, const u32* msgs, size_t n, u8* flags,
-                                  u8* status, int mont, cudaStream_t stream);
+                                  u8* status, int mont, u32* scratch, int* n_launches, cudaStream_t stream);
 cudaError_t launch_decryption_proof(const u32* tabG, const PoseidonTable& tab13, const u32* pks, const u32* cts,
                                     const u32* msgs, const u32* a1s, const u32* a2s, const u32* zs, size_t n, u8* flags,
-                                    u8* status, int mont, cudaStream_t stream);
+                                    u8* status, int mont, u32* scratch, int* n_launches, cudaStream_t stream);
 cudaError_t launch_te_rte(const u32* in, size_t n_points, u32* out, u8* status, int to_rte, cudaStream_t stream);
 cudaError_t launch_eddsa_verify(const u32* tabG, const PoseidonTable& tab6, const u32* pub_a, const u32* sig_r,
-                                const u32* sig_s, const u32* msgs, size_t n, u8* flags, u8* status, int mont,
-                                cudaStream_t stream);
+                                const u32* sig_s, const u32* msgs, size_t n, u8* flags, u8* status, int mont, u32* scratch,
+                                int* n_launches, cudaStream_t stream);
 cudaError_t upload_mimc7_constants(const u32* d_mont, cudaStream_t stream);
 cudaError_t launch_mimc7(const u32* in, int len, size_t n, u32* out, u8* status, int mont, cudaStream_t stream);
 cudaError_t launch_poseidon2_hash(const u32* keys, const u32* in, int len, size_t n, u32* out, u8* status, int mont,

@@ -338,6 +338,30 @@ class Engine:
         self._check(self._lib.gcp_elgamal_fixed_base_mul(self._h, _ptr(s), n, _ptr(out), _ptr(status), fmt))
         return out, status
 
+    def elgamal_scalar_mul(self, points, scalars, points2=None, scalars2=None, fmt=FMT_CANONICAL):
+        """curve.ScalarMul over a batch (call sites elgamal/encrypt.go:55, ciphertext.go:58,147-160): [s]P, or with a
+        second base [s]P + [s2]P2 in one pass sharing the doublings.  Returns ((n, 2, 32) points, status)."""
+        s = _as_elems(scalars, name="scalars").reshape(-1, 32)
+        n = s.shape[0]
+        p = _as_elems(points, 2 * n, "points")
+        p2 = s2 = None
+        if (points2 is None) != (scalars2 is None):
+            raise ValueError("points2 and scalars2 go together")
+        if points2 is not None:
+            p2 = _as_elems(points2, 2 * n, "points2")
+            s2 = _as_elems(scalars2, n, "scalars2")
+        out = np.empty((n, 2, 32), dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.gcp_elgamal_scalar_mul(self._h, _ptr(p), _ptr(s), _ptr(p2), _ptr(s2), n, _ptr(out),
+                                                     _ptr(status), fmt))
+        return out, status
+
+    def elgamal_scalar_mul_dev(self, d_points, d_scalars, d_points2, d_scalars2, n, d_out, d_status, fmt=FMT_CANONICAL,
+                               stream=None):
+        self._check(self._lib.gcp_elgamal_scalar_mul_dev(self._h, _dptr(d_points), _dptr(d_scalars), _dptr(d_points2),
+                                                         _dptr(d_scalars2), int(n), _dptr(d_out), _dptr(d_status), fmt,
+                                                         self._stream(stream)))
+
     def elgamal_encrypt(self, pub_key, k, m, fmt=FMT_CANONICAL):
         """(*Ciphertext).Encrypt (elgamal/encrypt.go:42-64).  pub_key: (2, 32) shared or (n, 2, 32) per item.
         Returns ((n, 4, 32) ciphertexts in Serialize order, status)."""

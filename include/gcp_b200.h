@@ -197,6 +197,18 @@ int gcp_smt_process_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_old_
 int gcp_elgamal_fixed_base_mul(gcp_ctx* ctx, const void* scalars, size_t n, void* out_points, uint8_t* status, int fmt);
 int gcp_elgamal_fixed_base_mul_dev(gcp_ctx* ctx, const void* d_scalars, size_t n, void* d_out_points,
                                    uint8_t* d_status, int fmt, void* stream);
+/* curve.ScalarMul of gnark's twistededwards gadget over a batch (the variable-base multiplication the reference calls at
+ * elgamal/encrypt.go:55, elgamal/ciphertext.go:58,147-160, ecc/bn254/eddsa/verifier.go:71-80): out[i] = [scalars[i]] points[i]
+ * for scalars used as integers in [0, r).  With points2 / scalars2 (both or neither): out[i] = [scalars[i]] points[i] +
+ * [scalars2[i]] points2[i] in ONE pass that shares the doublings (Straus), the form DecryptionProof.Verify's
+ * z*C1 - e*D takes.  Points must be on the curve (status 4; the reference's callers assert it first: encrypt.go:49,
+ * ciphertext.go:53-54,131-135); points with a cofactor component are multiplied by the integer scalar.
+ * points, points2, out_points: n x (X, Y). */
+int gcp_elgamal_scalar_mul(gcp_ctx* ctx, const void* points, const void* scalars, const void* points2,
+                           const void* scalars2, size_t n, void* out_points, uint8_t* status, int fmt);
+int gcp_elgamal_scalar_mul_dev(gcp_ctx* ctx, const void* d_points, const void* d_scalars, const void* d_points2,
+                               const void* d_scalars2, size_t n, void* d_out_points, uint8_t* d_status, int fmt,
+                               void* stream);
 /* (*Ciphertext).Encrypt (elgamal/encrypt.go:42-64): C1 = [k]G, C2 = [m]G + [k]pubKey.  m = 0 gives EncryptedZero
  * (encrypt.go:72-94).  pub_key: one point (pk_per_item = 0, the election key) or n points (pk_per_item = 1).  The
  * shared-key form builds a 654 MB window table for the key on first use (~0.1 s, cached in the context until another

@@ -317,3 +317,35 @@ def test_public_keys_with_a_cofactor_component(engine):
     assert not st.any() and ct_ints(add) == [eg.serialize(eg.ct_add(a, b)) for a, b in zip(cts[:6], cts[6:])]
     tal, st = engine.elgamal_tally(flat.reshape(12, 1, 4, 32))
     assert not st.any() and ct_ints(tal) == [eg.serialize(eg.tally(cts))]
+
+
+def test_scalar_mul_single_and_double_base(engine):
+    """curve.ScalarMul on its own (call sites elgamal/encrypt.go:55, ciphertext.go:58,147-160): [s]P and the one-pass
+    [s]P + [s2]P2, window-boundary scalars and keys with a cofactor component included, both element formats."""
+    rng = random.Random(4242)
+    t8 = (438929327410846936349781937479275998929723622237267896546408861753155634789,
+          4826523245007015323400664741523384119579596407052839571721035538011798951543)
+    ks = _window_boundary_scalars()[::5] + [rng.randrange(R) for _ in range(40)]
+    n = len(ks)
+    pts = [ed.scalar_mul(ed.G, rng.randrange(1, ed.ORDER)) for _ in range(n)]
+    pts[0], pts[1], pts[2] = ed.IDENTITY, t8, ed.add(pts[2], t8)
+    out, st = engine.elgamal_scalar_mul(elems([c for p in pts for c in p]).reshape(n, 2, 32), elems(ks))
+    assert not st.any()
+    for i in range(n):
+        assert tuple(ints(out[i])) == ed.scalar_mul(pts[i], ks[i]), (i, hex(ks[i]))
+    ks2 = [ks[(3 * i + 1) % n] for i in range(n)]
+    pts2 = [pts[(5 * i + 2) % n] for i in range(n)]
+    out2, st = engine.elgamal_scalar_mul(elems([c for p in pts for c in p]).reshape(n, 2, 32), elems(ks),
+                                         elems([c for p in pts2 for c in p]).reshape(n, 2, 32), elems(ks2))
+    assert not st.any()
+    for i in range(n):
+        assert tuple(ints(out2[i])) == ed.add(ed.scalar_mul(pts[i], ks[i]), ed.scalar_mul(pts2[i], ks2[i])), i
+    # gnark-crypto element memory (Montgomery) in and out
+    mont = lambda v: (v << 256) % R  # noqa: E731
+    outm, st = engine.elgamal_scalar_mul(elems([mont(c) for p in pts for c in p]).reshape(n, 2, 32), elems([mont(k) for k in ks]),
+                                         fmt=1)
+    assert not st.any() and ints(outm) == [mont(v) for v in ints(out)]
+    # assertions: off-curve point -> status 4, non-canonical scalar -> status 1, outputs zeroed
+    bad_p = elems([1, 2, *pts[3]]).reshape(2, 2, 32)
+    o, s = engine.elgamal_scalar_mul(bad_p, elems([5, R]))
+    assert list(s) == [4, 1] and not o.any()
