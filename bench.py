@@ -56,6 +56,10 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs 3, 4, 5 and the single-process group leg")
+    ap.add_argument("--log2-ballots", type=int, default=24, help="config 3: ballots in TOTAL (x 8 fields), sharded over the GPUs")
+    ap.add_argument("--log2-addresses", type=int, default=24, help="config 4: addresses per GPU")
+    ap.add_argument("--log2-voters", type=int, default=26, help="config 5: voters in TOTAL, sharded over the GPUs")
     return ap.parse_args()
 
 
@@ -194,10 +198,491 @@ def measure_extras(torch, dist, eng, g, world, rank):
     return out
 
 
-def make_census_like(torch, eng, n, seed=0xCE75):
+# ------------------------------------------------------------------------------------------------------
+# BASELINE configs 3, 4, 5 at their stated sizes, and the single-process (gcp_group_*) leg
+# ------------------------------------------------------------------------------------------------------
+N_FIELDS = 8
+# executed work model of the ElGamal kernels: per encryption 13 + 13 signed 20-bit windows of k (C1 = [k]G,
+# [k]PK) and one non-zero window of a 16-bit m, each a mixed addition of 7 multiplies; the fused kernel never normalises
+WIDE_PER_ENCRYPTION = 27 * 7 * FR_MUL_WIDE
+# Keccak-f[1600] on 32-bit halves (keccak.cuh): per round theta 20 LOP3 + 10 SHF + 50 XOR, rho 48 SHF, chi 50 LOP3, iota 2
+ALU_PER_ADDRESS = 24 * 180 + 80          # + byte swaps of the 64-byte big-endian input and the 20-byte output
+ALU_LANES_PER_CLK_SM = 64
+
+
+def _event_ms(torch, stream, fn, iters, warm, world, dist):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(iters):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def _wall_s(torch, fn, iters, world, dist):
+    """Wall clock around blocking host-buffer calls (they return after the results are in host memory), max over ranks."""
+    fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        fn()
+    dt = (time.perf_counter() - t0) / iters
+    if world > 1:
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    return dt
+
+
+def _limb_sums(torch, x, rows, cols):
+    """(rows*cols, 8) int32 limbs -> per column the integer sum over rows, as Python ints (limbs read as unsigned)."""
+    s = (x.view(rows, cols, 8).to(torch.int64) & 0xFFFFFFFF).sum(0)          # (cols, 8) int64, < 2^57
+    return s
+
+
+def _ints_from_limb_sums(s):
+    return [sum(int(v) << (32 * l) for l, v in enumerate(row)) for row in s.cpu().tolist()]
+
+
+def _pinned_copy(torch, t):
+    h = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+    h.copy_(t)
+    return h
+
+
+def _cpu_both(fn_threads, unit, sample, cport):
+    """CPU port timed on one core and on all cores: {'value' (all cores), 'single_core', ...}."""
+    th = cport.default_threads()
+    one = fn_threads(1)
+    allc = fn_threads(th)
+    return {"value": allc, "unit": unit, "cores": th, "single_core": one, "kind": "port", "sample": sample,
+            "note": "oracle/c: a C port of the reference's plain-field path (4x64-bit Montgomery limbs, no assembly); "
+                    "gnark-crypto's ADX assembly would be ~1.5-2x faster per multiply, gnark's test engine (big.Int) ~10x slower"}
+
+
+def measure_config3(torch, dist, eng, g, world, rank, log2_ballots, peak_wide, do_cpu):
+    """BASELINE configs[2]: ElGamal encrypt + homomorphic tally of 2^24 ballots x 8 fields in TOTAL, sharded over the
+    GPUs (strong scaling: 2^24 / N ballots per rank), each rank's partial tally all-gathered (NCCL, 1 KiB per rank) and
+    folded on every rank - all inside the timed region.  Checked against the homomorphic closed form
+    sum Encrypt(pk, k_i, m_i) = Encrypt(pk, sum k_i mod l, sum m_i mod l)."""
+    from gnark_crypto_primitives_b200 import dist as gdist
+    from oracle import edwards as oed
+    from oracle import elgamal as oeg
+    from tests.util import elems, ints
+
+    stream = torch.cuda.current_stream()
+    total = 1 << log2_ballots
+    lo, hi = gdist.shard_bounds(total, world, rank)
+    nb = hi - lo
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(0xC0F3 + rank)
+    k = rand_elems(torch, nb * N_FIELDS, gen)
+    m = torch.zeros((nb * N_FIELDS, 8), dtype=torch.int32, device="cuda")
+    m[:, 0] = torch.randint(0, 1 << 16, (nb * N_FIELDS,), dtype=torch.int32, device="cuda", generator=gen)
+    pk_int = oed.scalar_mul(oed.G, 0xB200)
+    pk = torch.from_numpy(elems(pk_int)).cuda()
+    part = torch.empty((N_FIELDS, 4, 32), dtype=torch.uint8, device="cuda")
+    pst = torch.empty(N_FIELDS, dtype=torch.uint8, device="cuda")
+    res = torch.empty((N_FIELDS, 4, 32), dtype=torch.uint8, device="cuda")
+    rst = torch.empty(N_FIELDS, dtype=torch.uint8, device="cuda")
+
+    def step():
+        eng.elgamal_encrypt_tally_dev(pk, k, m, nb, N_FIELDS, part, pst, stream=stream)
+        gathered = gdist.allgather_partials(part)                         # NCCL all_gather_into_tensor, bytes
+        eng.elgamal_tally_dev(gathered, world, N_FIELDS, res, rst, stream=stream)
+
+    ms = _event_ms(torch, stream, step, iters=3, warm=2, world=world, dist=dist)
+    enc_per_s = total * N_FIELDS / (ms * 1e-3)
+    # closed form over ALL ranks' scalars
+    ks = _limb_sums(torch, k, nb, N_FIELDS)
+    msum = (m.view(nb, N_FIELDS, 8)[:, :, 0].to(torch.int64)).sum(0)
+    if world > 1:
+        dist.all_reduce(ks)
+        dist.all_reduce(msum)
+    status_clean = not bool(pst.any().item()) and not bool(rst.any().item())
+    identical = None
+    if world > 1:
+        mine = res.view(-1).to(torch.int64)
+        lo_t, hi_t = mine.clone(), mine.clone()
+        dist.all_reduce(lo_t, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi_t, op=dist.ReduceOp.MAX)
+        identical = bool(torch.equal(lo_t, hi_t))
+    out = {"workload": f"elgamal_encrypt_tally 2^{log2_ballots} ballots x {N_FIELDS} fields in total", "scaling": "strong",
+           "ballots_per_gpu": nb, "encryptions_per_s": enc_per_s, "ballots_per_s": total / (ms * 1e-3), "ms_per_step": ms,
+           "collective": f"all_gather_into_tensor of {N_FIELDS * 128} B per rank + fold of {world} x {N_FIELDS} partials on every rank, inside the timed region",
+           "status_clean": status_clean, "tally_identical_on_all_ranks": identical}
+    if rank == 0:
+        got = res.cpu().numpy()
+        ksum = _ints_from_limb_sums(ks)
+        want_ok = all(ints(got[f]) == oeg.serialize(oeg.encrypt(pk_int, ksum[f] % oed.ORDER, int(msum[f].item()) % oed.ORDER))
+                      for f in range(N_FIELDS))
+        out["tally_matches_closed_form"] = bool(want_ok)
+        achieved = WIDE_PER_ENCRYPTION * (nb * N_FIELDS) / (ms * 1e-3)     # per GPU
+        out["roofline"] = {"bound": "int-pipe", "kernel": "encrypt_tally_partial_kernel", "achieved": achieved / 1e12,
+                           "peak": peak_wide / 1e12, "unit": "T IMAD.WIDE.U32/s", "frac": achieved / peak_wide,
+                           "wide_mul_per_encryption": WIDE_PER_ENCRYPTION,
+                           "hbm_gb_per_s": nb * N_FIELDS * 64 / (ms * 1e-3) / 1e9}
+    # end to end: the same shard through gcp_elgamal_encrypt_tally from page-locked HOST scalars, then the same exchange
+    hk, hm = _pinned_copy(torch, k), _pinned_copy(torch, m)
+    h_out = np.empty((N_FIELDS, 4, 32), dtype=np.uint8)
+    h_st = np.empty(N_FIELDS, dtype=np.uint8)
+    pk_host = elems(pk_int)
+    lib, hctx = eng._lib, eng._h
+
+    def e2e_step():
+        rc = lib.gcp_elgamal_encrypt_tally(hctx, pk_host.ctypes.data, hk.data_ptr(), hm.data_ptr(), nb, N_FIELDS,
+                                           h_out.ctypes.data, h_st.ctypes.data, g.FMT_CANONICAL)
+        if rc != 0:
+            raise RuntimeError(lib.gcp_last_error(hctx))
+        if world > 1:
+            part.copy_(torch.from_numpy(h_out))
+            gathered = gdist.allgather_partials(part)
+            eng.elgamal_tally_dev(gathered, world, N_FIELDS, res, rst, stream=stream)
+            res.cpu()
+
+    dt = _wall_s(torch, e2e_step, iters=2, world=world, dist=dist)
+    out["e2e"] = {"value": total * N_FIELDS / dt, "unit": "encryptions/s", "h2d_bytes_per_step": int(nb * N_FIELDS * 64),
+                  "d2h_bytes_per_step": N_FIELDS * 129, "matches_resident": bool((h_out == part.cpu().numpy()).all()) if world == 1 else None}
+    del hk, hm, k, m
+    if rank == 0 and do_cpu:
+        from oracle import cport
+        rng = np.random.default_rng(3)
+
+        def run(threads):
+            n = 256 * threads
+            kk = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+            kk[:, 31] &= 0x0F
+            mm = np.zeros((n, 32), np.uint8)
+            mm[:, :2] = rng.integers(0, 256, size=(n, 2), dtype=np.uint8)
+            t0 = time.perf_counter()
+            ct, _ = cport.elgamal_encrypt(pk_host, kk, mm, threads=threads)
+            cport.elgamal_tally(ct.reshape(n // N_FIELDS, N_FIELDS, 4, 32), threads=threads)
+            return n / (time.perf_counter() - t0)
+        out["cpu_baseline"] = _cpu_both(run, "encryptions/s", "256 encryptions per thread (literal gadget schedule: 63 affine "
+                                        "window additions per scalar multiplication) + Ciphertext.Add fold", cport)
+    return out
+
+
+def measure_config4(torch, dist, eng, g, world, rank, log2_n, sm_mhz, do_cpu):
+    """BASELINE configs[3]: secp256k1 public key -> Keccak-256 -> Ethereum address, 2^24 per GPU (weak scaling, no
+    collective: independent units)."""
+    stream = torch.cuda.current_stream()
+    n = 1 << log2_n
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(0xADD2 + rank)
+    pub = torch.randint(0, 256, (n, 64), dtype=torch.uint8, device="cuda", generator=gen)
+    addr = torch.empty((n, 20), dtype=torch.uint8, device="cuda")
+    ms = _event_ms(torch, stream, lambda: eng.keccak_address_dev(pub, n, addr, stream=stream), iters=10, warm=3, world=world,
+                   dist=dist)
+    per_s = world * n / (ms * 1e-3)
+    out = {"workload": f"keccak_address 2^{log2_n} public keys per GPU", "scaling": "weak", "addresses_per_s": per_s,
+           "ms_per_step": ms}
+    if rank == 0:
+        from oracle import cport
+        idx = torch.arange(0, n, max(1, n // 4096), device="cuda")
+        want = cport.keccak_address(pub[idx].cpu().numpy(), threads=cport.default_threads())
+        out["sample_matches_oracle"] = bool((want == addr[idx].cpu().numpy()).all())
+        alu_peak = 148 * ALU_LANES_PER_CLK_SM * (sm_mhz or 1965.0) * 1e6
+        achieved = ALU_PER_ADDRESS * n / (ms * 1e-3)
+        out["roofline"] = {"bound": "alu-pipe", "kernel": "keccak_address_kernel", "achieved": achieved / 1e12,
+                           "peak": alu_peak / 1e12, "unit": "T ALU op/s (LOP3/SHF, modelled count per address)",
+                           "frac": achieved / alu_peak, "alu_ops_per_address_model": ALU_PER_ADDRESS,
+                           "hbm_gb_per_s": n * 84 / (ms * 1e-3) / 1e9,
+                           "note": "instruction count is a model (see profiles/ for the ncu pipe utilisation); HBM term is 4 % of peak"}
+    h_pub = _pinned_copy(torch, pub)
+    h_addr = torch.empty((n, 20), dtype=torch.uint8).pin_memory()
+    lib, hctx = eng._lib, eng._h
+
+    def e2e_step():
+        rc = lib.gcp_keccak_address(hctx, h_pub.data_ptr(), n, h_addr.data_ptr())
+        if rc != 0:
+            raise RuntimeError(lib.gcp_last_error(hctx))
+
+    dt = _wall_s(torch, e2e_step, iters=3, world=world, dist=dist)
+    out["e2e"] = {"value": world * n / dt, "unit": "addresses/s", "h2d_bytes_per_step": n * 64, "d2h_bytes_per_step": n * 20,
+                  "matches_resident": bool(torch.equal(h_addr, addr.cpu()))}
+    if rank == 0 and do_cpu:
+        from oracle import cport
+        sample = pub[: 1 << 20].cpu().numpy()
+
+        def run(threads):
+            a = sample[: (1 << 16) * threads]
+            t0 = time.perf_counter()
+            cport.keccak_address(a, threads=threads)
+            return a.shape[0] / (time.perf_counter() - t0)
+        out["cpu_baseline"] = _cpu_both(run, "addresses/s", "2^16 public keys per thread", cport)
+    return out
+
+
+def measure_config5(torch, dist, eng, g, world, rank, log2_voters, peak_wide, do_cpu):
+    """BASELINE configs[4]: end-to-end ballot batch, 2^26 voters in TOTAL sharded over the GPUs (strong scaling), per
+    voter one census inclusion proof (160 levels, census-like path lengths L ~ U[20,28]) + 8 encrypted fields folded
+    into the tally when the proof verifies.  350 GB of proofs cannot be resident: voters stream through in chunks of 2^20
+    (gcp_ballot_batch_dev per chunk; the proof chunk is generated once per rank and reused, the scalars k, m are fresh per
+    chunk), the per-chunk tallies are folded, all-gathered (NCCL) and folded again on every rank.  Only the engine calls
+    and the exchange are timed (CUDA events per chunk, summed); the synthetic-input generation between chunks is not."""
+    from gnark_crypto_primitives_b200 import dist as gdist
+    from oracle import edwards as oed
+    from oracle import elgamal as oeg
+    from tests.util import elems, ints
+
+    stream = torch.cuda.current_stream()
+    total = 1 << log2_voters
+    lo, hi = gdist.shard_bounds(total, world, rank)
+    mine = hi - lo
+    chunk = min(mine, 1 << 20)
+    n_chunks = (mine + chunk - 1) // chunk
+    c = make_census_like(torch, eng, chunk, seed=0xCE75 + rank, host_forms=False)
+    expect = torch.from_numpy(c["expect"]).cuda()
+    pk_int = oed.scalar_mul(oed.G, 0xB200)
+    pk = torch.from_numpy(elems(pk_int)).cuda()
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(0x5EED + rank)
+    parts = torch.empty((n_chunks, N_FIELDS, 4, 32), dtype=torch.uint8, device="cuda")
+    part_st = torch.empty((n_chunks, N_FIELDS), dtype=torch.uint8, device="cuda")
+    flags = torch.empty(chunk, dtype=torch.uint8, device="cuda")
+    pst = torch.empty(chunk, dtype=torch.uint8, device="cuda")
+    ksum = torch.zeros((N_FIELDS, 8), dtype=torch.int64, device="cuda")
+    msum = torch.zeros(N_FIELDS, dtype=torch.int64, device="cuda")
+    admitted = 0
+    flags_ok = True
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_chunks + 1)]
+    m = torch.zeros((chunk * N_FIELDS, 8), dtype=torch.int32, device="cuda")
+
+    def run_chunk(i, cnt, k):
+        eng.ballot_batch_dev(N_LEVELS, cnt, c["roots"], False, c["sib"], c["keys"], c["vals"], pk, k, m, N_FIELDS, flags, pst,
+                             parts[i], part_st[i], stream=stream)
+
+    # warm-up (pools, key table, clocks): one chunk, result discarded
+    k = rand_elems(torch, chunk * N_FIELDS, gen)
+    run_chunk(0, chunk, k)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    for i in range(n_chunks):
+        cnt = min(chunk, mine - i * chunk)
+        k = rand_elems(torch, chunk * N_FIELDS, gen)
+        m[:, 0] = torch.randint(0, 1 << 16, (chunk * N_FIELDS,), dtype=torch.int32, device="cuda", generator=gen)
+        ev[i][0].record(stream)
+        run_chunk(i, cnt, k)
+        ev[i][1].record(stream)
+        # bookkeeping for the closed-form check (not timed): scalars of the voters the construction admits
+        adm = expect[:cnt].to(torch.int64).view(cnt, 1, 1)
+        ksum += ((k[: cnt * N_FIELDS].view(cnt, N_FIELDS, 8).to(torch.int64) & 0xFFFFFFFF) * adm).sum(0)
+        msum += (m[: cnt * N_FIELDS].view(cnt, N_FIELDS, 8)[:, :, 0].to(torch.int64) * adm.view(cnt, 1)).sum(0)
+        admitted += int(expect[:cnt].sum().item())
+        flags_ok = flags_ok and bool(torch.equal(flags[:cnt], expect[:cnt])) and not bool(pst[:cnt].any().item())
+    res = torch.empty((N_FIELDS, 4, 32), dtype=torch.uint8, device="cuda")
+    rst = torch.empty(N_FIELDS, dtype=torch.uint8, device="cuda")
+    part = torch.empty((N_FIELDS, 4, 32), dtype=torch.uint8, device="cuda")
+    ev[n_chunks][0].record(stream)
+    eng.elgamal_tally_dev(parts, n_chunks, N_FIELDS, part, rst, stream=stream)
+    gathered = gdist.allgather_partials(part)
+    eng.elgamal_tally_dev(gathered, world, N_FIELDS, res, rst, stream=stream)
+    ev[n_chunks][1].record(stream)
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    adm_t = torch.tensor([admitted], device="cuda", dtype=torch.int64)
+    ok_t = torch.tensor([1 if flags_ok and not bool(part_st.any().item()) else 0], device="cuda", dtype=torch.int64)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.all_reduce(ksum)
+        dist.all_reduce(msum)
+        dist.all_reduce(adm_t)
+        dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+    out = {"workload": f"ballot_batch 2^{log2_voters} voters in total: census proof (160 levels, L ~ U[20,28]) + {N_FIELDS} encrypted fields per voter",
+           "scaling": "strong", "voters_per_gpu": mine, "chunk_voters": chunk, "chunks_per_gpu": n_chunks,
+           "voters_per_s": total / (ms * 1e-3), "ms_total": ms, "mean_path_levels": c["mean_levels"],
+           "admitted_voters": int(adm_t.item()), "flags_match_construction": bool(ok_t.item()),
+           "collective": f"fold of the {n_chunks} chunk tallies, all_gather of {N_FIELDS * 128} B per rank, fold on every rank: timed",
+           "inputs": "proof chunk generated once per rank (seeded) and reused; k, m fresh per chunk; every 16th voter's proof is wrong and must not be tallied"}
+    if rank == 0:
+        got = res.cpu().numpy()
+        ks = _ints_from_limb_sums(ksum)
+        out["tally_matches_closed_form"] = bool(all(
+            ints(got[f]) == oeg.serialize(oeg.encrypt(pk_int, ks[f] % oed.ORDER, int(msum[f].item()) % oed.ORDER))
+            for f in range(N_FIELDS)))
+        w3, w4 = wide_per_hash(3, 57), wide_per_hash(4, 56)
+        per_voter = c["mean_levels"] * (w3 + FR_MUL_WIDE) + w4 + 4 * FR_MUL_WIDE + N_FIELDS * WIDE_PER_ENCRYPTION * (15.0 / 16.0)
+        achieved = per_voter * mine / (ms * 1e-3)
+        out["roofline"] = {"bound": "int-pipe", "kernel": "smt_path_kernel + encrypt_tally_partial_kernel", "achieved": achieved / 1e12,
+                           "peak": peak_wide / 1e12, "unit": "T IMAD.WIDE.U32/s", "frac": achieved / peak_wide,
+                           "wide_mul_per_voter": per_voter,
+                           "hbm_gb_per_s": mine * (N_LEVELS * 32 + 96 + N_FIELDS * 64) / (ms * 1e-3) / 1e9}
+    if world > 1:
+        r64 = res.view(-1).to(torch.int64)
+        lo_t, hi_t = r64.clone(), r64.clone()
+        dist.all_reduce(lo_t, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi_t, op=dist.ReduceOp.MAX)
+        out["tally_identical_on_all_ranks"] = bool(torch.equal(lo_t, hi_t))
+    # end to end on a bounded host batch: packed census proofs + scalars in page-locked host memory through gcp_ballot_batch
+    ne = min(chunk, 1 << 19)
+    ch = make_census_like(torch, eng, ne, seed=0xCE75 + rank)
+    hk, hm = _pinned_copy(torch, k[: ne * N_FIELDS]), _pinned_copy(torch, m[: ne * N_FIELDS])
+    of, os_ = np.empty(ne, np.uint8), np.empty(ne, np.uint8)
+    ot, ots = np.empty((N_FIELDS, 4, 32), np.uint8), np.empty(N_FIELDS, np.uint8)
+    pk_host = elems(pk_int)
+    lib, hctx = eng._lib, eng._h
+
+    def e2e_step():
+        rc = lib.gcp_ballot_batch(hctx, N_LEVELS, ne, ch["hr"].ctypes.data, 0, None, ch["blob"].ctypes.data, ch["offs"].ctypes.data,
+                                  ch["hk"].ctypes.data, ch["hv"].ctypes.data, pk_host.ctypes.data, hk.data_ptr(), hm.data_ptr(),
+                                  N_FIELDS, of.ctypes.data, os_.ctypes.data, ot.ctypes.data, ots.ctypes.data, g.FMT_CANONICAL)
+        if rc != 0:
+            raise RuntimeError(lib.gcp_last_error(hctx))
+
+    dt = _wall_s(torch, e2e_step, iters=2, world=world, dist=dist)
+    out["e2e"] = {"value": world * ne / dt, "unit": "voters/s", "sample": f"{ne} voters per GPU per call (host buffers for 2^26 voters would be ~90 GB)",
+                  "h2d_bytes_per_step": int(ch["offs"][-1]) + (ne + 1) * 8 + ne * 96 + ne * N_FIELDS * 64, "d2h_bytes_per_step": 2 * ne + N_FIELDS * 129,
+                  "flags_ok": bool((of == ch["expect"]).all()) and not bool(os_.any()) and not bool(ots.any())}
+    if rank == 0 and do_cpu:
+        from oracle import cport
+
+        def run(threads):
+            nv = 64 * threads
+            roots, sib, keys, vals = cpu_sample_inputs(nv, 11)
+            rng = np.random.default_rng(5)
+            kk = rng.integers(0, 256, size=(nv * N_FIELDS, 32), dtype=np.uint8)
+            kk[:, 31] &= 0x0F
+            mm = np.zeros((nv * N_FIELDS, 32), np.uint8)
+            mm[:, :2] = rng.integers(0, 256, size=(nv * N_FIELDS, 2), dtype=np.uint8)
+            t0 = time.perf_counter()
+            cport.smt_verify(roots, sib, keys, vals, literal=True, threads=threads)
+            ct, _ = cport.elgamal_encrypt(pk_host, kk, mm, threads=threads)
+            cport.elgamal_tally(ct.reshape(nv, N_FIELDS, 4, 32), threads=threads)
+            return nv / (time.perf_counter() - t0)
+        out["cpu_baseline"] = _cpu_both(run, "voters/s", "64 voters per thread: literal 160-level verifier (160 Hash2 + 2 Hash1) + 8 "
+                                        "Encrypt + Ciphertext.Add fold", cport)
+    return out
+
+
+def measure_group(torch, dist, eng0, g, world, rank, barrier_cpu):
+    """The single-process path a Go host uses (gcp_group_*, csrc/group.cu): ONE process (rank 0) drives all `world` GPUs
+    through one handle while the other ranks wait on a CPU barrier.  Weak scaling, host buffers, wall clock around the
+    blocking calls.  SMT: page-locked dense proofs; fused encrypt+tally: page-locked scalars AND pageable scalars (staged
+    by the library's copy pool); ballot batch: packed census proofs, page-locked."""
+    out = None
+    if rank == 0:
+        from oracle import edwards as oed
+        from tests.util import elems
+
+        grp = g.Group(list(range(world)))
+        try:
+            lib, gh = grp._lib, grp._h
+            out = {"devices": world, "uses_nccl": bool(grp.uses_nccl), "copy_threads": int(lib.gcp_copy_threads())}
+
+            def timed(fn, iters=2):
+                fn()
+                t0 = time.perf_counter()
+                for _ in range(iters):
+                    fn()
+                return (time.perf_counter() - t0) / iters
+
+            # SMT, dense 160 levels, 2^17 proofs per GPU, page-locked
+            n1 = 1 << 17
+            b = make_batch(torch, eng0, n1, seed=0x6E0)
+            h = {kk: _pinned_copy(torch, b[kk]) for kk in ("sib", "keys", "vals", "roots")}
+            expect1 = b["expect"].cpu().numpy()
+            del b
+            torch.cuda.empty_cache()
+            n = n1 * world
+            big = {kk: torch.empty((world,) + tuple(v.shape), dtype=v.dtype).pin_memory() for kk, v in h.items()}
+            for kk in big:
+                big[kk][:] = h[kk]
+            of = torch.empty(n, dtype=torch.uint8).pin_memory().numpy()
+            os_ = torch.empty(n, dtype=torch.uint8).pin_memory().numpy()
+
+            def smt():
+                rc = lib.gcp_group_smt_verify(gh, N_LEVELS, n, big["roots"].data_ptr(), 0, big["sib"].data_ptr(), None, None, None,
+                                              big["keys"].data_ptr(), big["vals"].data_ptr(), None, None, of.ctypes.data,
+                                              os_.ctypes.data, None, g.FMT_CANONICAL)
+                if rc != 0:
+                    raise RuntimeError(lib.gcp_group_last_error(gh))
+            dt = timed(smt)
+            out["smt_dense_proofs_per_s"] = n / dt
+            out["smt_flags_ok"] = bool((of.reshape(world, n1) == expect1).all()) and not bool(os_.any())
+            out["smt_shape"] = f"{n1} dense 160-level proofs per GPU, page-locked host rows"
+            del big, h
+            # fused encrypt + tally with the NCCL all-gather: 2^20 ballots x 8 per GPU
+            nb1 = 1 << 20
+            nb = nb1 * world
+            rng = np.random.default_rng(0x6E1)
+            pk_host = elems(oed.scalar_mul(oed.G, 0xB200))
+            k_pin = g.PinnedBuffer(nb * N_FIELDS * 32)
+            m_pin = g.PinnedBuffer(nb * N_FIELDS * 32)
+            k_np = k_pin.array.reshape(nb * N_FIELDS, 32)
+            m_np = m_pin.array.reshape(nb * N_FIELDS, 32)
+            k_np[:] = rng.integers(0, 256, size=(1 << 16, 32), dtype=np.uint8).repeat(nb * N_FIELDS >> 16, axis=0)
+            k_np[:, 31] &= 0x0F
+            m_np[:] = 0
+            m_np[:, :2] = rng.integers(0, 256, size=(1 << 16, 2), dtype=np.uint8).repeat(nb * N_FIELDS >> 16, axis=0)
+            ot, ots = np.empty((N_FIELDS, 4, 32), np.uint8), np.empty(N_FIELDS, np.uint8)
+            ot2 = np.empty_like(ot)
+
+            def et(kp, mp, dst):
+                rc = lib.gcp_group_elgamal_encrypt_tally(gh, pk_host.ctypes.data, kp, mp, nb, N_FIELDS, dst.ctypes.data,
+                                                         ots.ctypes.data, g.FMT_CANONICAL)
+                if rc != 0:
+                    raise RuntimeError(lib.gcp_group_last_error(gh))
+            dt = timed(lambda: et(k_np.ctypes.data, m_np.ctypes.data, ot))
+            out["encrypt_tally_pinned_enc_per_s"] = nb * N_FIELDS / dt
+            k_pg, m_pg = k_np.copy(), m_np.copy()                         # pageable copies (numpy heap)
+            dt = timed(lambda: et(k_pg.ctypes.data, m_pg.ctypes.data, ot2))
+            out["encrypt_tally_pageable_enc_per_s"] = nb * N_FIELDS / dt
+            out["encrypt_tally_pageable_equals_pinned"] = bool((ot == ot2).all()) and not bool(ots.any())
+            out["encrypt_tally_shape"] = f"{nb1} ballots x {N_FIELDS} fields per GPU; partial tallies stay on the device until ncclAllGather"
+            # host memcpy bandwidth of this box (what bounds the pageable path: staging copies + DMA reads)
+            t0 = time.perf_counter()
+            np.copyto(k_pg, k_np)
+            out["host_memcpy_gb_per_s_one_thread"] = k_np.nbytes / (time.perf_counter() - t0) / 1e9
+            del k_pg, m_pg
+            # ballot batch (config 5 shape): packed census proofs, 2^17 voters per GPU
+            nv1 = 1 << 17
+            cb = make_census_like(torch, eng0, nv1, seed=0x6E2)
+            nv = nv1 * world
+            blob = np.tile(cb["blob"], world)
+            offs = np.concatenate([cb["offs"][:-1] + i * int(cb["offs"][-1]) for i in range(world)] + [np.array([world * int(cb["offs"][-1])], np.uint64)]).astype(np.uint64)
+            hk_, hv_, hr_ = (np.tile(cb[x], (world, 1)) for x in ("hk", "hv", "hr"))
+            vf, vs = np.empty(nv, np.uint8), np.empty(nv, np.uint8)
+
+            def bb():
+                rc = lib.gcp_group_ballot_batch(gh, N_LEVELS, nv, hr_.ctypes.data, 0, None, blob.ctypes.data, offs.ctypes.data,
+                                                hk_.ctypes.data, hv_.ctypes.data, pk_host.ctypes.data, k_np.ctypes.data, m_np.ctypes.data,
+                                                N_FIELDS, vf.ctypes.data, vs.ctypes.data, ot.ctypes.data, ots.ctypes.data, g.FMT_CANONICAL)
+                if rc != 0:
+                    raise RuntimeError(lib.gcp_group_last_error(gh))
+            dt = timed(bb)
+            out["ballot_batch_voters_per_s"] = nv / dt
+            out["ballot_batch_flags_ok"] = bool((vf.reshape(world, nv1) == cb["expect"]).all()) and not bool(vs.any()) and not bool(ots.any())
+            out["ballot_batch_shape"] = f"{nv1} voters per GPU: packed census proof (pageable numpy) + {N_FIELDS} fields (page-locked scalars)"
+            k_pin.close()
+            m_pin.close()
+        finally:
+            grp.close()
+    barrier_cpu()
+    return out
+
+
+def make_census_like(torch, eng, n, seed=0xCE75, host_forms=True):
     """Census-like batch (SURVEY 8d secondary distribution: L ~ U[20,28] leading siblings of 160, ~10 % interior
-    zeros), every 16th proof with a wrong value.  Device tensors plus the two host forms a caller can hold: dense
-    Assignment.Siblings rows (pinned) and arbo packed proofs back to back (pinned blob + offsets)."""
+    zeros), every 16th proof with a wrong value.  Device tensors plus (host_forms) the two host forms a caller can hold:
+    dense Assignment.Siblings rows (pinned) and arbo packed proofs back to back (blob + offsets)."""
     gen = torch.Generator(device="cuda")
     gen.manual_seed(seed)
     sib = rand_elems(torch, n * N_LEVELS, gen, nonzero=True).view(n, N_LEVELS, 8)
@@ -206,6 +691,7 @@ def make_census_like(torch, eng, n, seed=0xCE75):
     hole = torch.rand((n, N_LEVELS), device="cuda", generator=gen) < 0.1
     keep = (lvl < L.view(n, 1)) & (~hole | (lvl == (L.view(n, 1) - 1)))
     sib *= keep.view(n, N_LEVELS, 1).to(torch.int32)
+    del hole
     keys = rand_elems(torch, n, gen)
     keys[:, 5:] = 0
     vals = rand_elems(torch, n, gen)
@@ -220,12 +706,16 @@ def make_census_like(torch, eng, n, seed=0xCE75):
     vals[::16, 0] ^= 2                                 # every 16th proof carries a wrong value
     expect = np.ones(n, dtype=np.uint8)
     expect[::16] = 0
+    out = dict(sib=sib, keys=keys, vals=vals, roots=roots, flags=flags, status=status, expect=expect,
+               mean_levels=float(L.to(torch.float32).mean().item()))
+    if not host_forms:
+        return out
     hs = torch.empty(sib.shape, dtype=sib.dtype).pin_memory()
     hs.copy_(sib)
     hk, hv, hr = (t.cpu().numpy().view(np.uint8).reshape(n, 32) for t in (keys, vals, roots))
     dense = hs.numpy().view(np.uint8).reshape(n, N_LEVELS, 32)
     Lh = L.cpu().numpy()
-    nz = keep.cpu().numpy()
+    nz = keep[:, :32].cpu().numpy()                    # L <= 28: the first 32 levels hold every sibling
     bm_len = (Lh + 7) // 8
     cnt = nz.sum(axis=1)
     lens = 4 + bm_len + 32 * cnt
@@ -233,15 +723,21 @@ def make_census_like(torch, eng, n, seed=0xCE75):
     np.cumsum(lens, out=offs[1:])
     blob_t = torch.empty(int(offs[-1]), dtype=torch.uint8).pin_memory()
     blob = blob_t.numpy()
-    bits = np.packbits(nz[:, :32], axis=1, bitorder="little")          # L <= 28: four bitmap bytes are enough
-    for i in range(n):
-        o = int(offs[i])
-        blob[o:o + 2] = np.frombuffer(int(lens[i]).to_bytes(2, "little"), dtype=np.uint8)
-        blob[o + 2:o + 4] = np.frombuffer(int(bm_len[i]).to_bytes(2, "little"), dtype=np.uint8)
-        blob[o + 4:o + 4 + bm_len[i]] = bits[i, :bm_len[i]]
-        blob[o + 4 + bm_len[i]:o + lens[i]] = dense[i, :Lh[i]][nz[i, :Lh[i]]].reshape(-1)
-    return dict(sib=sib, keys=keys, vals=vals, roots=roots, flags=flags, status=status, expect=expect, dense=dense,
-                hk=hk, hv=hv, hr=hr, blob=blob, offs=offs, mean_levels=float(Lh.mean()), _pins=(hs, blob_t))
+    # arbo PackSiblings: [u16 length][u16 bitmap length][bitmap][32 B per set bit].  Vectorised over proofs: header and
+    # four bitmap bytes first (a 3-byte bitmap's fourth byte is overwritten by the data that follows), then level by level
+    o = offs[:-1].astype(np.int64)
+    bits = np.packbits(nz, axis=1, bitorder="little")
+    hdr = np.stack([lens & 0xFF, lens >> 8, bm_len & 0xFF, bm_len >> 8, bits[:, 0], bits[:, 1], bits[:, 2], bits[:, 3]], axis=1).astype(np.uint8)
+    win8 = np.lib.stride_tricks.sliding_window_view(blob, 8, writeable=True)
+    win8[o] = hdr
+    win32 = np.lib.stride_tricks.sliding_window_view(blob, 32, writeable=True)
+    data0 = o + 4 + bm_len
+    rank = np.cumsum(nz, axis=1) - nz                  # set bits before level j
+    for j in range(int(Lh.max())):
+        rows = np.nonzero(nz[:, j])[0]
+        win32[data0[rows] + 32 * rank[rows, j]] = dense[rows, j]
+    out.update(dense=dense, hk=hk, hv=hv, hr=hr, blob=blob, offs=offs, _pins=(hs, blob_t))
+    return out
 
 
 def measure_census_like(torch, eng, g, log2_n=18, seed=0xCE75):
@@ -430,10 +926,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cpu_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        cpu_group = dist.new_group(backend="gloo")        # host-side barrier for the single-process leg (no GPU work while waiting)
     else:
         torch.cuda.set_device(0)
     dev_index = torch.cuda.current_device()
@@ -474,6 +972,8 @@ def main():
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
     value = world * n / (ms_step * 1e-3)
+    nominal = (148 * 32 * clocks["sm_mhz"] * 1e6) if clocks.get("sm_mhz") else None   # 32 IMAD.WIDE lanes/clk/SM
+    peak = max(peak_wide, nominal or 0.0)
 
     # correctness of what was timed: flags vs the construction, and a sample vs the oracle
     ok_flags = bool((batch["flags"] == batch["expect"]).all().item()) and not bool(batch["status"].any().item())
@@ -525,12 +1025,36 @@ def main():
                "steps": e2e_steps, "flags_ok": bool((out_flags == batch["expect"].cpu().numpy()).all())}
 
     # ---- the other kernels of the path, device-resident, short runs (reported as extras; not the headline) -----
+    del batch
+    if e2e is not None:
+        del h, hn
+    torch.cuda.empty_cache()
     extras = None
     if not args.no_extras:
         extras = measure_extras(torch, dist, eng, g, world, rank)
         if world == 1:
             extras["census_like_e2e"] = measure_census_like(torch, eng, g)
             extras["config1_poseidon_batch_1024"] = measure_config1(eng, g)
+        torch.cuda.empty_cache()
+
+    # ---- BASELINE configs 3, 4, 5 at their stated sizes + the single-process group leg -----------------------------
+    configs = None
+    if not args.no_configs:
+        do_cpu = world == 1 and not args.no_cpu_baseline
+        configs = {}
+        configs["config3_elgamal_encrypt_tally"] = measure_config3(torch, dist, eng, g, world, rank, args.log2_ballots, peak, do_cpu)
+        torch.cuda.empty_cache()
+        configs["config4_keccak_address"] = measure_config4(torch, dist, eng, g, world, rank, args.log2_addresses,
+                                                            clocks.get("sm_mhz"), do_cpu)
+        torch.cuda.empty_cache()
+        configs["config5_ballot_batch"] = measure_config5(torch, dist, eng, g, world, rank, args.log2_voters, peak, do_cpu)
+        torch.cuda.empty_cache()
+
+        def barrier_cpu():
+            if world > 1:
+                dist.barrier(group=cpu_group)
+        barrier_cpu()
+        configs["single_process_group"] = measure_group(torch, dist, eng, g, world, rank, barrier_cpu)
 
     # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample) -----------------------------------
     cpu_baseline = None
@@ -540,8 +1064,12 @@ def main():
         run_cpu(256, threads)
         m = 1 << 14
         v = run_cpu(m, threads)
-        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": f"{m} dense 160-level proofs, literal gadget schedule (160 Hash2 + 2 Hash1 each), oracle/c on all host cores"}
+        one = run_cpu(1 << 10, 1)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "single_core": one, "kind": "port",
+                        "sample": f"{m} dense 160-level proofs on all host cores ({1 << 10} on one core), literal gadget schedule (160 Hash2 + 2 Hash1 each), oracle/c",
+                        "note": "oracle/c is a C port of the reference's plain-field path (4x64-bit Montgomery limbs, ~27 ns per Fr "
+                                "multiply, no assembly): gnark-crypto's ADX assembly would be ~1.5-2x faster, gnark's test engine "
+                                "(big.Int Mul + Mod per gate, the path BASELINE config 1 names) roughly 10x slower; no Go toolchain here"}
 
     if rank == 0:
         w3 = wide_per_hash(3, 57)
@@ -562,8 +1090,6 @@ def main():
                 traffic = float(json.load(fh)["dram_bytes_per_proof"]) * n
         except Exception:
             pass
-        nominal = (148 * 32 * clocks["sm_mhz"] * 1e6) if clocks.get("sm_mhz") else None   # 32 IMAD.WIDE lanes/clk/SM
-        peak = max(peak_wide, nominal or 0.0)
         roofline = {
             "bound": "int-pipe", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "T IMAD.WIDE.U32/s",
             "frac": achieved / peak if peak else None, "traffic": traffic,
@@ -590,7 +1116,7 @@ def main():
                        "distribution": "dense: 159 non-zero siblings, every 16th proof corrupted", "parallelism":
                        f"{world} x independent shards, no data-path collective", "l2": "inputs (5.5 GB per GPU) exceed L2"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "extras": extras, "checks": {"flags_match_construction": ok_flags, "sample_matches_oracle": parity},
+            "cpu_baseline": cpu_baseline, "extras": extras, "configs": configs, "checks": {"flags_match_construction": ok_flags, "sample_matches_oracle": parity},
         }
         print(json.dumps(out))
     if world > 1:

@@ -2,6 +2,8 @@
 // host-buffer entry points (chunked, double-buffered H2D -> kernels -> D2H pipelines on two streams).
 // There is no CPU compute path here: every value is produced by the kernels in kernels.cu.
 #include "../../include/gcp_b200.h"
+#include "hostcopy.h"
+#include "internal.h"
 #include "kernels.h"
 
 #include <dlfcn.h>
@@ -22,7 +24,24 @@ namespace {
 constexpr uint32_t BLOB_MAGIC = 0x32425350u;  // 'PSB2', written by oracle/gen_constants.py
 constexpr int N_SLOTS = 128;
 
-thread_local std::string g_create_error;
+// message of the last failed gcp_ctx_create, process-wide and mutex-guarded: a Go caller reads it with a second cgo call
+// that may run on another OS thread than the create call did (a goroutine can migrate between the two)
+std::mutex g_create_mu;
+std::string g_create_error_text;
+struct CreateError {
+  CreateError& operator=(const std::string& m) {
+    std::lock_guard<std::mutex> lk(g_create_mu);
+    g_create_error_text = m;
+    return *this;
+  }
+  CreateError& operator=(const char* m) { return *this = std::string(m); }
+  const char* c_str() const {  // a per-thread copy, so the pointer stays valid while another thread fails a create
+    thread_local std::string copy;
+    std::lock_guard<std::mutex> lk(g_create_mu);
+    copy = g_create_error_text;
+    return copy.c_str();
+  }
+} g_create_error;
 
 std::string library_dir() {
   Dl_info info;
@@ -68,6 +87,7 @@ struct gcp_ctx {
   cudaEvent_t stage_ev[STAGE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
   bool stage_used[STAGE_SLOTS] = {false, false, false, false};
   int stage_next = 0;
+  bool pool_ref = false;      // this context holds a reference on the process-wide copy pool
 
   int fail(int code, const std::string& msg) {
     err = msg;
@@ -105,14 +125,20 @@ struct gcp_ctx {
   } while (0)
 
 // Host -> device copy of a caller buffer on `st`.  Page-locked sources (gcp_host_alloc, cudaHostRegister, torch pinned
-// memory) go straight to cudaMemcpyAsync.  Large PAGEABLE sources - a Go heap slice, a numpy array - would be staged by
-// the driver on the calling thread at ~5 GB/s (measured: 583 k instead of 738 k proofs/s end to end at 2^19 dense
-// proofs); here they are copied into a ring of four 32 MB page-locked buffers by several host threads at memory
-// bandwidth and sent from there, so the copy of chunk k+1 keeps pace with the kernels of chunk k.
+// memory) go straight to cudaMemcpyAsync.  PAGEABLE sources - a Go heap slice, a numpy array - would be staged by the
+// driver on the calling thread at ~5 GB/s (measured: 583 k instead of 738 k proofs/s end to end at 2^19 dense proofs);
+// from 1 MB up they are copied into a ring of four 32 MB page-locked buffers by the process-wide copy pool
+// (hostcopy.h) at memory bandwidth and sent from there, so the copy of chunk k+1 keeps pace with the kernels of chunk k
+// and the calling thread is back at its launch loop as soon as the last slice is queued.
+static bool staging_disabled() {
+  static const bool off = getenv("GCP_B200_NO_STAGING") != nullptr;
+  return off;
+}
+
 static int h2d_copy(gcp_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStream_t st) {
   if (bytes == 0) return GCP_OK;
   bool pageable = false;
-  if (bytes >= ((size_t)64 << 20) && !getenv("GCP_B200_NO_STAGING")) {
+  if (bytes >= ((size_t)1 << 20) && !staging_disabled()) {
     cudaPointerAttributes attr;
     cudaError_t e = cudaPointerGetAttributes(&attr, src);
     if (e != cudaSuccess) cudaGetLastError();
@@ -122,8 +148,6 @@ static int h2d_copy(gcp_ctx* ctx, void* dst, const void* src, size_t bytes, cuda
     CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st), "H2D");
     return GCP_OK;
   }
-  unsigned hw = std::thread::hardware_concurrency();
-  const int n_threads = (int)std::max(1u, std::min(8u, hw ? hw / 2 : 4u));
   for (size_t off = 0; off < bytes; off += gcp_ctx::STAGE_BYTES) {
     const size_t m = std::min(gcp_ctx::STAGE_BYTES, bytes - off);
     const int slot = ctx->stage_next;
@@ -140,22 +164,42 @@ static int h2d_copy(gcp_ctx* ctx, void* dst, const void* src, size_t bytes, cuda
       }
     }
     if (ctx->stage_used[slot]) CU(cudaEventSynchronize(ctx->stage_ev[slot]), "staging event");  // its last send is done
-    char* sb = (char*)ctx->stage_buf[slot];
-    const char* sp = (const char*)src + off;
-    const size_t part = ((m + n_threads - 1) / n_threads + 4095) & ~(size_t)4095;
-    std::vector<std::thread> th;
-    for (int t = 1; t < n_threads; t++) {
-      const size_t lo = std::min(m, part * t), hi = std::min(m, part * (t + 1));
-      if (hi > lo) th.emplace_back([=] { memcpy(sb + lo, sp + lo, hi - lo); });
-    }
-    memcpy(sb, sp, std::min(m, part));
-    for (auto& t : th) t.join();
-    CU(cudaMemcpyAsync((char*)dst + off, sb, m, cudaMemcpyHostToDevice, st), "H2D");
+    CopyPool::copy(ctx->stage_buf[slot], (const char*)src + off, m);
+    CU(cudaMemcpyAsync((char*)dst + off, ctx->stage_buf[slot], m, cudaMemcpyHostToDevice, st), "H2D");
     CU(cudaEventRecord(ctx->stage_ev[slot], st), "staging event");
     ctx->stage_used[slot] = true;
   }
   return GCP_OK;
 }
+
+// Chunk schedule of the host-buffer pipelines whose kernels are resident-wave shaped (smt_path_kernel,
+// varbase_window_kernel: one thread per item, registers set the residency).  The first chunk is ONE wave, so the only
+// copy no kernel hides is short (at 2^18 census-like proofs the old ~1 GB first chunk left 20 ms of copy exposed against
+// 51 ms of compute); later chunks are `cap_waves` whole waves, and a remainder shorter than a wave joins the chunk
+// before it instead of running as a thin launch of its own.  GCP_B200_SMT_CHUNK overrides the size (tests).
+struct ChunkPlan {
+  size_t wave, cap, n, off = 0;
+  bool forced = false;
+  ChunkPlan(size_t n_items, size_t wave_items, size_t cap_items) : wave(std::max<size_t>(1, wave_items)), n(n_items) {
+    cap = std::max(wave, cap_items - cap_items % wave);
+    if (const char* env = getenv("GCP_B200_SMT_CHUNK")) {
+      long v = atol(env);
+      if (v > 0) {
+        cap = wave = (size_t)v;
+        forced = true;
+      }
+    }
+  }
+  size_t largest() const { return std::min(n, cap + wave); }
+  size_t next() {  // items of the next chunk (0: done); advances
+    const size_t left = n - off;
+    if (left == 0) return 0;
+    size_t take = off == 0 ? std::min(left, wave) : std::min(left, cap);
+    if (!forced && left - take < wave) take = left <= cap + wave ? left : take;
+    off += take;
+    return take;
+  }
+};
 
 #define GCP_TRY(call)            \
   do {                           \
@@ -206,8 +250,11 @@ void gcp_ctx_destroy(gcp_ctx* ctx) {
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   for (u32* p : {ctx->d_tabG, ctx->d_tabPK, ctx->d_fb_ext, ctx->d_base_xy, ctx->d_flagG, ctx->d_flagPK, ctx->d_p2_keys})
     if (p) cudaFree(p);
+  if (ctx->pool_ref) CopyPool::release();
   delete ctx;
 }
+
+int gcp_copy_threads(void) { return CopyPool::workers(); }
 
 int gcp_host_alloc(size_t bytes, void** out) {
   if (!out) return GCP_ERR_BAD_ARG;
@@ -277,6 +324,8 @@ int gcp_ctx_create(int device, const char* constants_path, gcp_ctx** out) {
 
   gcp_ctx* ctx = new gcp_ctx();
   ctx->device = device;
+  CopyPool::acquire();
+  ctx->pool_ref = true;
   auto bail = [&](int code) {
     g_create_error = ctx->err;
     gcp_ctx_destroy(ctx);
@@ -538,6 +587,8 @@ int gcp_poseidon_multihash(gcp_ctx* ctx, const void* in, int len, size_t n, void
 // ---------------------------------------------------------------------------------------------------
 // SMT
 // ---------------------------------------------------------------------------------------------------
+static int check_fmt(gcp_ctx* ctx, int fmt);
+
 static int smt_check_args(gcp_ctx* ctx, int n_levels, size_t n, const void* roots, const void* siblings,
                           const void* old_keys, const void* old_values, const void* keys, const void* values,
                           const uint8_t* flags, const uint8_t* status, int fmt) {
@@ -550,11 +601,17 @@ static int smt_check_args(gcp_ctx* ctx, int n_levels, size_t n, const void* root
   return GCP_OK;
 }
 
+// one scratch slot per verifier call: leaf hashes | perm | lidx | info | hist | cursor
+static size_t smt_scratch_bytes(size_t n) {
+  const size_t off_perm = n * 32, off_lidx = off_perm + n * 4, off_info = off_lidx + ((n * 2 + 15) & ~(size_t)15);
+  return off_info + ((n + 15) & ~(size_t)15) + 1024 + 1040;
+}
+
 static int smt_verify_dev_locked(gcp_ctx* ctx, int n_levels, size_t n, const void* d_roots, int shared_root,
                                  const void* d_siblings, const void* d_old_keys, const void* d_old_values,
                                  const uint8_t* d_is_old0, const void* d_keys, const void* d_values,
                                  const uint8_t* d_fnc, const uint8_t* d_enabled, uint8_t* d_flags, uint8_t* d_status,
-                                 void* d_out_roots, int fmt, cudaStream_t st, int leaf_slot) {
+                                 void* d_out_roots, int fmt, cudaStream_t st, int leaf_slot, int leaf_form = 0) {
   int rc = smt_check_args(ctx, n_levels, n, d_roots, d_siblings, d_old_keys, d_old_values, d_keys, d_values, d_flags,
                           d_status, fmt);
   if (rc != GCP_OK || n == 0) return rc;
@@ -588,6 +645,7 @@ static int smt_verify_dev_locked(gcp_ctx* ctx, int n_levels, size_t n, const voi
   a.status = d_status;
   a.out_roots = (u32*)d_out_roots;
   a.mont = fmt;
+  a.leaf_hash_form = leaf_form;
   CU(launch_smt_verify(a, sc, ctx->sm_count, st), "smt kernels");
   ctx->launches += 5;
   return GCP_OK;
@@ -623,12 +681,81 @@ int gcp_smt_verify_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_roots
                                (cudaStream_t)stream, 2);
 }
 
+int gcp_smt_verify_with_leaf_hash_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_roots, int shared_root,
+                                      const void* d_siblings, const void* d_old_keys, const void* d_hash1_old,
+                                      const uint8_t* d_is_old0, const void* d_keys, const void* d_hash1_new,
+                                      const uint8_t* d_fnc, const uint8_t* d_enabled, uint8_t* d_out_flags,
+                                      uint8_t* d_out_status, void* d_out_roots, int fmt, void* stream) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  return smt_verify_dev_locked(ctx, n_levels, n, d_roots, shared_root, d_siblings, d_old_keys, d_hash1_old, d_is_old0,
+                               d_keys, d_hash1_new, d_fnc, d_enabled, d_out_flags, d_out_status, d_out_roots, fmt,
+                               (cudaStream_t)stream, 2, 1);
+}
+
+// Hash1 of the tree (tree/smt/hash.go:10-19): H(key, values..., 1); rows are assembled on the device (scratch slot),
+// the hash is the batch Poseidon kernel with arity n_values + 2.
+static int smt_leaf_hash_dev_locked(gcp_ctx* ctx, const void* d_keys, const void* d_values, int n_values, size_t n,
+                                    void* d_out, uint8_t* d_status, int fmt, cudaStream_t st, int rows_slot) {
+  if (n_values < 0 || n_values > 14) return ctx->fail(GCP_ERR_BAD_ARG, "bad inputs provided");  // poseidon.go:41-43 via hFn
+  int rc = check_fmt(ctx, fmt);
+  if (rc != GCP_OK || n == 0) return rc;
+  if (!d_keys || !d_out || (n_values && !d_values)) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  const int arity = n_values + 2;
+  u32* rows = (u32*)ctx->buf(rows_slot, n * (size_t)arity * 32);
+  if (!rows) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+  CU(launch_smt_leaf_rows((const u32*)d_keys, (const u32*)d_values, n_values, n, rows, fmt, st), "leaf rows kernel");
+  ctx->launches++;
+  return poseidon_hash_dev_locked(ctx, rows, arity, n, d_out, d_status, fmt, st);
+}
+
+int gcp_smt_leaf_hash_dev(gcp_ctx* ctx, const void* d_keys, const void* d_values, int n_values, size_t n, void* d_out,
+                          uint8_t* d_status, int fmt, void* stream) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  return smt_leaf_hash_dev_locked(ctx, d_keys, d_values, n_values, n, d_out, d_status, fmt, (cudaStream_t)stream, 100);
+}
+
+int gcp_smt_leaf_hash(gcp_ctx* ctx, const void* keys, const void* values, int n_values, size_t n, void* out, uint8_t* status,
+                      int fmt) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  StreamGuard guard{ctx};
+  if (n_values < 0 || n_values > 14) return ctx->fail(GCP_ERR_BAD_ARG, "bad inputs provided");
+  if (n == 0) return check_fmt(ctx, fmt);
+  if (!keys || !out || (n_values && !values)) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  const size_t chunk = std::min<size_t>(n, (size_t)1 << 20), vb = (size_t)n_values * 32;
+  size_t k = 0;
+  for (size_t off = 0; off < n; off += chunk, k++) {
+    const size_t m = std::min(chunk, n - off);
+    const int s = (int)(k & 1);
+    cudaStream_t st = ctx->stream[s];
+    void* d_k = ctx->buf(4 + s * 3 + 0, chunk * 32);
+    void* d_v = ctx->buf(4 + s * 3 + 1, std::max<size_t>(chunk * vb, 16));
+    void* d_o = ctx->buf(4 + s * 3 + 2, chunk * 33);  // digests, then the status bytes
+    if (!d_k || !d_v || !d_o) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+    uint8_t* d_st = (uint8_t*)d_o + chunk * 32;
+    GCP_TRY(h2d_copy(ctx, d_k, (const char*)keys + off * 32, m * 32, st));
+    if (vb) GCP_TRY(h2d_copy(ctx, d_v, (const char*)values + off * vb, m * vb, st));
+    GCP_TRY(smt_leaf_hash_dev_locked(ctx, d_k, d_v, n_values, m, d_o, d_st, fmt, st, 101 + s));
+    CU(cudaMemcpyAsync((char*)out + off * 32, d_o, m * 32, cudaMemcpyDeviceToHost, st), "D2H");
+    if (status) CU(cudaMemcpyAsync(status + off, d_st, m, cudaMemcpyDeviceToHost, st), "D2H status");
+  }
+  CU(cudaStreamSynchronize(ctx->stream[0]), "stream sync");
+  CU(cudaStreamSynchronize(ctx->stream[1]), "stream sync");
+  return GCP_OK;
+}
+
 // Host-buffer verifier: `siblings` dense (Assignment.Siblings rows), or NULL with arbo-packed proofs in
 // `packed` / `offsets` that are expanded on the device (smt_unpack_kernel) chunk by chunk.
 static int smt_verify_host(gcp_ctx* ctx, int n_levels, size_t n, const void* roots, int shared_root, const void* siblings,
                            const uint8_t* packed, const uint64_t* offsets, const void* old_keys, const void* old_values,
                            const uint8_t* is_old0, const void* keys, const void* values, const uint8_t* fnc,
-                           const uint8_t* enabled, uint8_t* out_flags, uint8_t* out_status, void* out_roots, int fmt) {
+                           const uint8_t* enabled, uint8_t* out_flags, uint8_t* out_status, void* out_roots, int fmt,
+                           int leaf_form = 0) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
@@ -639,16 +766,7 @@ static int smt_verify_host(gcp_ctx* ctx, int n_levels, size_t n, const void* roo
   if (rc != GCP_OK || n == 0) return rc;
   if (is_packed && !offsets) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
   const size_t sib_bytes = (size_t)n_levels * 32;
-  // chunk = a whole number of resident-thread waves of smt_path_kernel (5 blocks x 128 threads per SM), about 1 GB of
-  // siblings, so that a chunk's launch fills the machine; two chunks are in flight on the two streams
-  const size_t wave = (size_t)ctx->sm_count * 5 * 128;
-  size_t chunk = std::max<size_t>(1, ((size_t)1 << 30) / sib_bytes);
-  if (chunk > wave) chunk -= chunk % wave;
-  chunk = std::min(chunk, n);
-  if (const char* env = getenv("GCP_B200_SMT_CHUNK")) {
-    long v = atol(env);
-    if (v > 0) chunk = std::min<size_t>(n, (size_t)v);
-  }
+  ChunkPlan plan(n, smt_path_wave_items(ctx->sm_count), ((size_t)1 << 30) / sib_bytes);
   // a shared root is uploaded once
   void* d_shared_root = nullptr;
   if (shared_root) {
@@ -656,27 +774,26 @@ static int smt_verify_host(gcp_ctx* ctx, int n_levels, size_t n, const void* roo
     if (!d_shared_root) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
     CU(cudaMemcpy(d_shared_root, roots, 32, cudaMemcpyHostToDevice), "H2D root");
   }
-  // (A ramped schedule - quarter wave, one wave, then full chunks, to shorten the one copy no kernel hides - was
-  // measured: +1 % at 2^20 dense proofs, -4 % at 2^19 and -10 % on census-like batches, where partial waves cost more
-  // than the shorter head saves.  One chunk size stays.)
-  size_t k = 0;
-  for (size_t off = 0; off < n && rc == GCP_OK; off += chunk, k++) {
-    size_t m = std::min(chunk, n - off);
+  size_t k = 0, off = 0;
+  for (size_t m = plan.next(); m != 0 && rc == GCP_OK; off += m, m = plan.next(), k++) {
     int s = (int)(k & 1);
     cudaStream_t st = ctx->stream[s];
     const int b = 10 + s * 14;
-    void* d_sib = ctx->buf(b + 0, m * sib_bytes);
-    void* d_roots = shared_root ? d_shared_root : ctx->buf(b + 1, m * 32);
-    void* d_keys = ctx->buf(b + 2, m * 32);
-    void* d_vals = ctx->buf(b + 3, m * 32);
-    void* d_okeys = old_keys ? ctx->buf(b + 4, m * 32) : nullptr;
-    void* d_ovals = old_keys ? ctx->buf(b + 5, m * 32) : nullptr;
-    uint8_t* d_is0 = is_old0 ? (uint8_t*)ctx->buf(b + 6, m) : nullptr;
-    uint8_t* d_fnc = fnc ? (uint8_t*)ctx->buf(b + 7, m) : nullptr;
-    uint8_t* d_en = enabled ? (uint8_t*)ctx->buf(b + 8, m) : nullptr;
-    uint8_t* d_flags = (uint8_t*)ctx->buf(b + 9, m);
-    uint8_t* d_status = (uint8_t*)ctx->buf(b + 10, m);
-    void* d_oroots = out_roots ? ctx->buf(b + 11, m * 32) : nullptr;
+    // sized for the largest chunk of the plan from the start: growing a slot later would cudaFree under running work
+    const size_t cap = plan.largest();
+    if (!ctx->buf(b + 12, smt_scratch_bytes(cap))) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+    void* d_sib = ctx->buf(b + 0, cap * sib_bytes);
+    void* d_roots = shared_root ? d_shared_root : ctx->buf(b + 1, cap * 32);
+    void* d_keys = ctx->buf(b + 2, cap * 32);
+    void* d_vals = ctx->buf(b + 3, cap * 32);
+    void* d_okeys = old_keys ? ctx->buf(b + 4, cap * 32) : nullptr;
+    void* d_ovals = old_keys ? ctx->buf(b + 5, cap * 32) : nullptr;
+    uint8_t* d_is0 = is_old0 ? (uint8_t*)ctx->buf(b + 6, cap) : nullptr;
+    uint8_t* d_fnc = fnc ? (uint8_t*)ctx->buf(b + 7, cap) : nullptr;
+    uint8_t* d_en = enabled ? (uint8_t*)ctx->buf(b + 8, cap) : nullptr;
+    uint8_t* d_flags = (uint8_t*)ctx->buf(b + 9, cap);
+    uint8_t* d_status = (uint8_t*)ctx->buf(b + 10, cap);
+    void* d_oroots = out_roots ? ctx->buf(b + 11, cap * 32) : nullptr;
     if (!d_sib || !d_roots || !d_keys || !d_vals || !d_flags || !d_status || (old_keys && (!d_okeys || !d_ovals)) ||
         (is_old0 && !d_is0) || (fnc && !d_fnc) || (enabled && !d_en) || (out_roots && !d_oroots))
       return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
@@ -692,26 +809,26 @@ static int smt_verify_host(gcp_ctx* ctx, int n_levels, size_t n, const void* roo
       uint64_t* d_off = (uint64_t*)ctx->buf(80 + s * 3 + 1, (m + 1) * 8);
       d_bad = (uint8_t*)ctx->buf(80 + s * 3 + 2, m);
       if (!d_packed || !d_off || !d_bad) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
-      if (pbytes) CU(cudaMemcpyAsync(d_packed, packed + pbeg, pbytes, cudaMemcpyHostToDevice, st), "H2D");
-      CU(cudaMemcpyAsync(d_off, offsets + off, (m + 1) * 8, cudaMemcpyHostToDevice, st), "H2D");
+      if (pbytes) GCP_TRY(h2d_copy(ctx, d_packed, packed + pbeg, pbytes, st));
+      GCP_TRY(h2d_copy(ctx, d_off, offsets + off, (m + 1) * 8, st));
       CU(launch_smt_unpack(d_packed, d_off, pbeg, pbytes, m, n_levels, (u32*)d_sib, d_bad, fmt, st), "smt unpack kernel");
       ctx->launches++;
     } else {
       rc = h2d_copy(ctx, d_sib, (const char*)siblings + off * sib_bytes, m * sib_bytes, st);
       if (rc != GCP_OK) break;
     }
-    if (!shared_root) CU(cudaMemcpyAsync(d_roots, (const char*)roots + off * 32, m * 32, cudaMemcpyHostToDevice, st), "H2D");
-    CU(cudaMemcpyAsync(d_keys, (const char*)keys + off * 32, m * 32, cudaMemcpyHostToDevice, st), "H2D");
-    CU(cudaMemcpyAsync(d_vals, (const char*)values + off * 32, m * 32, cudaMemcpyHostToDevice, st), "H2D");
+    if (!shared_root) GCP_TRY(h2d_copy(ctx, d_roots, (const char*)roots + off * 32, m * 32, st));
+    GCP_TRY(h2d_copy(ctx, d_keys, (const char*)keys + off * 32, m * 32, st));
+    GCP_TRY(h2d_copy(ctx, d_vals, (const char*)values + off * 32, m * 32, st));
     if (old_keys) {
-      CU(cudaMemcpyAsync(d_okeys, (const char*)old_keys + off * 32, m * 32, cudaMemcpyHostToDevice, st), "H2D");
-      CU(cudaMemcpyAsync(d_ovals, (const char*)old_values + off * 32, m * 32, cudaMemcpyHostToDevice, st), "H2D");
+      GCP_TRY(h2d_copy(ctx, d_okeys, (const char*)old_keys + off * 32, m * 32, st));
+      GCP_TRY(h2d_copy(ctx, d_ovals, (const char*)old_values + off * 32, m * 32, st));
     }
-    if (is_old0) CU(cudaMemcpyAsync(d_is0, is_old0 + off, m, cudaMemcpyHostToDevice, st), "H2D");
-    if (fnc) CU(cudaMemcpyAsync(d_fnc, fnc + off, m, cudaMemcpyHostToDevice, st), "H2D");
-    if (enabled) CU(cudaMemcpyAsync(d_en, enabled + off, m, cudaMemcpyHostToDevice, st), "H2D");
+    if (is_old0) GCP_TRY(h2d_copy(ctx, d_is0, is_old0 + off, m, st));
+    if (fnc) GCP_TRY(h2d_copy(ctx, d_fnc, fnc + off, m, st));
+    if (enabled) GCP_TRY(h2d_copy(ctx, d_en, enabled + off, m, st));
     rc = smt_verify_dev_locked(ctx, n_levels, m, d_roots, shared_root, d_sib, d_okeys, d_ovals, d_is0, d_keys, d_vals,
-                               d_fnc, d_en, d_flags, d_status, d_oroots, fmt, st, b + 12);
+                               d_fnc, d_en, d_flags, d_status, d_oroots, fmt, st, b + 12, leaf_form);
     if (rc != GCP_OK) break;
     if (is_packed) {
       CU(launch_smt_apply_bad(d_bad, m, d_flags, d_status, (u32*)d_oroots, st), "smt apply-bad kernel");
@@ -736,6 +853,15 @@ int gcp_smt_verify(gcp_ctx* ctx, int n_levels, size_t n, const void* roots, int 
   if (ctx && n && !siblings) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
   return smt_verify_host(ctx, n_levels, n, roots, shared_root, siblings, nullptr, nullptr, old_keys, old_values, is_old0,
                          keys, values, fnc, enabled, out_flags, out_status, out_roots, fmt);
+}
+
+int gcp_smt_verify_with_leaf_hash(gcp_ctx* ctx, int n_levels, size_t n, const void* roots, int shared_root,
+                                  const void* siblings, const void* old_keys, const void* hash1_old, const uint8_t* is_old0,
+                                  const void* keys, const void* hash1_new, const uint8_t* fnc, const uint8_t* enabled,
+                                  uint8_t* out_flags, uint8_t* out_status, void* out_roots, int fmt) {
+  if (ctx && n && !siblings) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  return smt_verify_host(ctx, n_levels, n, roots, shared_root, siblings, nullptr, nullptr, old_keys, hash1_old, is_old0, keys,
+                         hash1_new, fnc, enabled, out_flags, out_status, out_roots, fmt, 1);
 }
 
 int gcp_smt_verify_packed(gcp_ctx* ctx, int n_levels, size_t n, const void* roots, int shared_root,
@@ -795,13 +921,11 @@ static int smt_process_check(gcp_ctx* ctx, int n_levels, size_t n, const void* a
   return GCP_OK;
 }
 
-int gcp_smt_process_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_old_roots, const void* d_siblings,
-                        const void* d_old_keys, const void* d_old_values, const uint8_t* d_is_old0,
-                        const void* d_new_keys, const void* d_new_values, const uint8_t* d_fnc0, const uint8_t* d_fnc1,
-                        void* d_new_roots, uint8_t* d_status, int fmt, void* stream) {
-  if (!ctx) return GCP_ERR_BAD_ARG;
-  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+static int smt_process_dev_locked(gcp_ctx* ctx, int n_levels, size_t n, const void* d_old_roots, const void* d_siblings,
+                                  const void* d_old_keys, const void* d_old_values, const uint8_t* d_is_old0,
+                                  const void* d_new_keys, const void* d_new_values, const uint8_t* d_fnc0,
+                                  const uint8_t* d_fnc1, void* d_new_roots, uint8_t* d_status, int fmt, cudaStream_t st,
+                                  int leaf_form) {
   int rc = smt_process_check(ctx, n_levels, n, d_old_roots, d_siblings, d_old_keys, d_old_values, d_is_old0, d_new_keys,
                              d_new_values, d_fnc0, d_fnc1, d_new_roots, d_status, fmt);
   if (rc != GCP_OK || n == 0) return rc;
@@ -820,16 +944,42 @@ int gcp_smt_process_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_old_
   a.new_roots = (u32*)d_new_roots;
   a.status = d_status;
   a.mont = fmt;
-  CU(launch_smt_process(a, (cudaStream_t)stream), "smt process kernel");
+  a.leaf_hash_form = leaf_form;
+  CU(launch_smt_process(a, st), "smt process kernel");
   ctx->launches++;
   return GCP_OK;
 }
 
+int gcp_smt_process_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_old_roots, const void* d_siblings,
+                        const void* d_old_keys, const void* d_old_values, const uint8_t* d_is_old0,
+                        const void* d_new_keys, const void* d_new_values, const uint8_t* d_fnc0, const uint8_t* d_fnc1,
+                        void* d_new_roots, uint8_t* d_status, int fmt, void* stream) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  return smt_process_dev_locked(ctx, n_levels, n, d_old_roots, d_siblings, d_old_keys, d_old_values, d_is_old0, d_new_keys,
+                                d_new_values, d_fnc0, d_fnc1, d_new_roots, d_status, fmt, (cudaStream_t)stream, 0);
+}
+
+int gcp_smt_process_with_leaf_hash_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_old_roots, const void* d_siblings,
+                                       const void* d_old_keys, const void* d_hash1_old, const uint8_t* d_is_old0,
+                                       const void* d_new_keys, const void* d_hash1_new, const uint8_t* d_fnc0,
+                                       const uint8_t* d_fnc1, void* d_new_roots, uint8_t* d_status, int fmt, void* stream) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  return smt_process_dev_locked(ctx, n_levels, n, d_old_roots, d_siblings, d_old_keys, d_hash1_old, d_is_old0, d_new_keys,
+                                d_hash1_new, d_fnc0, d_fnc1, d_new_roots, d_status, fmt, (cudaStream_t)stream, 1);
+}
+
 // Host-buffer processor: dense sibling rows, or (siblings == NULL) arbo packed proofs expanded on the device.
+// post_insert: the packed strings come from GenProof AFTER the add, as in the reference's own flow
+// (wrapper_arbo.go:152-172): the last unpacked sibling is dropped where isOld0 == 0 and fnc1 == 0.
 static int smt_process_host(gcp_ctx* ctx, int n_levels, size_t n, const void* old_roots, const void* siblings,
                             const uint8_t* packed, const uint64_t* offsets, const void* old_keys,
                             const void* old_values, const uint8_t* is_old0, const void* new_keys, const void* new_values,
-                            const uint8_t* fnc0, const uint8_t* fnc1, void* new_roots, uint8_t* status, int fmt) {
+                            const uint8_t* fnc0, const uint8_t* fnc1, void* new_roots, uint8_t* status, int fmt,
+                            bool post_insert, int leaf_form = 0) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   const bool is_packed = siblings == nullptr;
   std::lock_guard<std::recursive_mutex> call_lk(ctx->mu);  // the scratch slots belong to this call until it returns
@@ -842,53 +992,57 @@ static int smt_process_host(gcp_ctx* ctx, int n_levels, size_t n, const void* ol
     if (is_packed && !offsets) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
   }
   const size_t sib_bytes = (size_t)n_levels * 32;
-  size_t chunk = std::max<size_t>(1, std::min<size_t>(n, ((size_t)256 << 20) / sib_bytes));
-  for (size_t off = 0; off < n; off += chunk) {
-    size_t m = std::min(chunk, n - off);
-    void *d_sib, *d_e[5];
+  // chunks alternate between the two streams (slot sets 10.. and 24..), so the copies of one overlap the kernel of the other
+  const size_t chunk = std::max<size_t>(1, std::min<size_t>(n, ((size_t)256 << 20) / sib_bytes));
+  size_t k = 0;
+  for (size_t off = 0; off < n; off += chunk, k++) {
+    const size_t m = std::min(chunk, n - off);
+    const int s = (int)(k & 1);
+    const int b = 10 + s * 14;
+    cudaStream_t st = ctx->stream[s];
+    void* d_sib = ctx->buf(b + 0, chunk * sib_bytes);
+    void* d_e[5];
     uint8_t* d_b[4];
+    for (int q = 0; q < 5; q++) d_e[q] = ctx->buf(b + 1 + q, chunk * 32);
+    void* d_out = ctx->buf(b + 6, chunk * 32);
+    for (int q = 0; q < 4; q++) d_b[q] = (uint8_t*)ctx->buf(b + 7 + q, chunk);
+    if (!d_sib || !d_out || !d_e[0] || !d_e[1] || !d_e[2] || !d_e[3] || !d_e[4] || !d_b[0] || !d_b[1] || !d_b[2] || !d_b[3])
+      return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+    const void* src_e[5] = {old_roots, old_keys, old_values, new_keys, new_values};
+    const uint8_t* src_b[3] = {is_old0, fnc0, fnc1};
+    for (int q = 0; q < 3; q++) GCP_TRY(h2d_copy(ctx, d_b[q], src_b[q] + off, m, st));
     uint8_t* d_bad = nullptr;
-    {
-      d_sib = ctx->buf(10, m * sib_bytes);
-      for (int q = 0; q < 5; q++) d_e[q] = ctx->buf(11 + q, m * 32);
-      void* d_out = ctx->buf(16, m * 32);
-      for (int q = 0; q < 4; q++) d_b[q] = (uint8_t*)ctx->buf(17 + q, m);
-      if (!d_sib || !d_out || !d_e[0] || !d_e[1] || !d_e[2] || !d_e[3] || !d_e[4] || !d_b[0] || !d_b[1] || !d_b[2] || !d_b[3])
-        return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
-      cudaStream_t st = ctx->stream[0];
-      const void* src_e[5] = {old_roots, old_keys, old_values, new_keys, new_values};
-      const uint8_t* src_b[3] = {is_old0, fnc0, fnc1};
-      if (is_packed) {
-        const uint64_t pbeg = offsets[off], pend = offsets[off + m];
-        if (pend < pbeg) return ctx->fail(GCP_ERR_BAD_ARG, "packed offsets must be non-decreasing");
-        const size_t pbytes = (size_t)(pend - pbeg);
-        uint8_t* d_packed = (uint8_t*)ctx->buf(80, pbytes + 4);
-        uint64_t* d_off = (uint64_t*)ctx->buf(81, (m + 1) * 8);
-        d_bad = (uint8_t*)ctx->buf(82, m);
-        if (!d_packed || !d_off || !d_bad) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
-        if (pbytes) CU(cudaMemcpyAsync(d_packed, packed + pbeg, pbytes, cudaMemcpyHostToDevice, st), "H2D");
-        CU(cudaMemcpyAsync(d_off, offsets + off, (m + 1) * 8, cudaMemcpyHostToDevice, st), "H2D");
-        CU(launch_smt_unpack(d_packed, d_off, pbeg, pbytes, m, n_levels, (u32*)d_sib, d_bad, fmt, st), "smt unpack kernel");
-        ctx->launches++;
-      } else {
-        CU(cudaMemcpyAsync(d_sib, (const char*)siblings + off * sib_bytes, m * sib_bytes, cudaMemcpyHostToDevice, st), "H2D");
-      }
-      for (int q = 0; q < 5; q++)
-        CU(cudaMemcpyAsync(d_e[q], (const char*)src_e[q] + off * 32, m * 32, cudaMemcpyHostToDevice, st), "H2D");
-      for (int q = 0; q < 3; q++) CU(cudaMemcpyAsync(d_b[q], src_b[q] + off, m, cudaMemcpyHostToDevice, st), "H2D");
+    if (is_packed) {
+      const uint64_t pbeg = offsets[off], pend = offsets[off + m];
+      if (pend < pbeg) return ctx->fail(GCP_ERR_BAD_ARG, "packed offsets must be non-decreasing");
+      const size_t pbytes = (size_t)(pend - pbeg);
+      uint8_t* d_packed = (uint8_t*)ctx->buf(80 + s * 3 + 0, pbytes + 4);
+      uint64_t* d_off = (uint64_t*)ctx->buf(80 + s * 3 + 1, (chunk + 1) * 8);
+      d_bad = (uint8_t*)ctx->buf(80 + s * 3 + 2, chunk);
+      if (!d_packed || !d_off || !d_bad) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+      if (pbytes) GCP_TRY(h2d_copy(ctx, d_packed, packed + pbeg, pbytes, st));
+      GCP_TRY(h2d_copy(ctx, d_off, offsets + off, (m + 1) * 8, st));
+      CU(launch_smt_unpack(d_packed, d_off, pbeg, pbytes, m, n_levels, (u32*)d_sib, d_bad, fmt, st,
+                           post_insert ? d_b[0] : nullptr, post_insert ? d_b[2] : nullptr),
+         "smt unpack kernel");
+      ctx->launches++;
+    } else {
+      GCP_TRY(h2d_copy(ctx, d_sib, (const char*)siblings + off * sib_bytes, m * sib_bytes, st));
     }
-    int rc = gcp_smt_process_dev(ctx, n_levels, m, d_e[0], d_sib, d_e[1], d_e[2], d_b[0], d_e[3], d_e[4], d_b[1], d_b[2],
-                                 ctx->slot[16].p, d_b[3], fmt, ctx->stream[0]);
+    for (int q = 0; q < 5; q++) GCP_TRY(h2d_copy(ctx, d_e[q], (const char*)src_e[q] + off * 32, m * 32, st));
+    int rc = smt_process_dev_locked(ctx, n_levels, m, d_e[0], d_sib, d_e[1], d_e[2], d_b[0], d_e[3], d_e[4], d_b[1], d_b[2],
+                                    d_out, d_b[3], fmt, st, leaf_form);
     if (rc != GCP_OK) return rc;
     if (is_packed) {
       // a proof arbo.UnpackSiblings rejects never reaches the gadget: status 7, new root 0 (flags: the status array twice)
-      CU(launch_smt_apply_bad(d_bad, m, d_b[3], d_b[3], (u32*)ctx->slot[16].p, ctx->stream[0]), "smt apply-bad kernel");
+      CU(launch_smt_apply_bad(d_bad, m, d_b[3], d_b[3], (u32*)d_out, st), "smt apply-bad kernel");
       ctx->launches++;
     }
-    CU(cudaMemcpyAsync((char*)new_roots + off * 32, ctx->slot[16].p, m * 32, cudaMemcpyDeviceToHost, ctx->stream[0]), "D2H");
-    CU(cudaMemcpyAsync(status + off, d_b[3], m, cudaMemcpyDeviceToHost, ctx->stream[0]), "D2H");
-    CU(cudaStreamSynchronize(ctx->stream[0]), "stream sync");
+    CU(cudaMemcpyAsync((char*)new_roots + off * 32, d_out, m * 32, cudaMemcpyDeviceToHost, st), "D2H");
+    CU(cudaMemcpyAsync(status + off, d_b[3], m, cudaMemcpyDeviceToHost, st), "D2H");
   }
+  CU(cudaStreamSynchronize(ctx->stream[0]), "stream sync");
+  CU(cudaStreamSynchronize(ctx->stream[1]), "stream sync");
   return GCP_OK;
 }
 
@@ -898,7 +1052,16 @@ int gcp_smt_process(gcp_ctx* ctx, int n_levels, size_t n, const void* old_roots,
                     int fmt) {
   if (ctx && n && !siblings) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
   return smt_process_host(ctx, n_levels, n, old_roots, siblings, nullptr, nullptr, old_keys, old_values, is_old0,
-                          new_keys, new_values, fnc0, fnc1, new_roots, status, fmt);
+                          new_keys, new_values, fnc0, fnc1, new_roots, status, fmt, false);
+}
+
+int gcp_smt_process_with_leaf_hash(gcp_ctx* ctx, int n_levels, size_t n, const void* old_roots, const void* siblings,
+                                   const void* old_keys, const void* hash1_old, const uint8_t* is_old0,
+                                   const void* new_keys, const void* hash1_new, const uint8_t* fnc0, const uint8_t* fnc1,
+                                   void* new_roots, uint8_t* status, int fmt) {
+  if (ctx && n && !siblings) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  return smt_process_host(ctx, n_levels, n, old_roots, siblings, nullptr, nullptr, old_keys, hash1_old, is_old0, new_keys,
+                          hash1_new, fnc0, fnc1, new_roots, status, fmt, false, 1);
 }
 
 int gcp_smt_process_packed(gcp_ctx* ctx, int n_levels, size_t n, const void* old_roots, const uint8_t* packed,
@@ -907,7 +1070,16 @@ int gcp_smt_process_packed(gcp_ctx* ctx, int n_levels, size_t n, const void* old
                            void* new_roots, uint8_t* status, int fmt) {
   if (ctx && n && (!packed || !offsets)) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
   return smt_process_host(ctx, n_levels, n, old_roots, nullptr, packed, offsets, old_keys, old_values, is_old0, new_keys,
-                          new_values, fnc0, fnc1, new_roots, status, fmt);
+                          new_values, fnc0, fnc1, new_roots, status, fmt, false);
+}
+
+int gcp_smt_process_arbo(gcp_ctx* ctx, int n_levels, size_t n, const void* old_roots, const uint8_t* packed,
+                         const uint64_t* offsets, const void* old_keys, const void* old_values, const uint8_t* is_old0,
+                         const void* new_keys, const void* new_values, const uint8_t* fnc0, const uint8_t* fnc1,
+                         void* new_roots, uint8_t* status, int fmt) {
+  if (ctx && n && (!packed || !offsets)) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+  return smt_process_host(ctx, n_levels, n, old_roots, nullptr, packed, offsets, old_keys, old_values, is_old0, new_keys,
+                          new_values, fnc0, fnc1, new_roots, status, fmt, true);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1083,13 +1255,48 @@ int gcp_elgamal_encrypt_tally_dev(gcp_ctx* ctx, const void* d_pub_key, const voi
   if (rc != GCP_OK) return rc;
   rc = ensure_pk_table(ctx, d_pub_key, true, fmt, (cudaStream_t)stream);
   if (rc != GCP_OK) return rc;
-  return encrypt_tally_dev_locked(ctx, d_k, d_m, nullptr, n_ballots, n_fields, d_out, d_status, fmt, (cudaStream_t)stream, 44);
+  rc = encrypt_tally_dev_locked(ctx, d_k, d_m, nullptr, n_ballots, n_fields, d_out, d_status, fmt, (cudaStream_t)stream, 44);
+  if (rc != GCP_OK) return rc;
+  // AssertIsOnCurve(pubKey) (encrypt.go:49): an off-curve or non-canonical key gives status 4 and no result on every field
+  CU(launch_tally_status_merge(nullptr, 0, n_fields, 1, ctx->d_flagPK, (u32*)d_out, d_status, (cudaStream_t)stream),
+     "tally status kernel");
+  ctx->launches++;
+  return GCP_OK;
+}
+
+// Last step of the three chunked folds (tally, encrypt-tally, ballot batch): the per-chunk partial ciphertexts
+// (n_chunks x n_fields, with their statuses, on the device; both pipeline streams drained) are folded into the result.
+// `out` / `status` are host buffers, or - for the group exchange (group.cu) - device buffers on this context's device,
+// so that a partial tally never leaves the GPU before the all-gather.  pk_flag: the cached key's on-curve flag, or
+// nullptr for a plain tally.
+static int finish_partials(gcp_ctx* ctx, u32* d_parts, uint8_t* d_part_status, size_t n_chunks, int n_fields, int fmt,
+                           const u32* pk_flag, void* out, uint8_t* status, bool out_on_device) {
+  const size_t ballot_ct = (size_t)n_fields * 128;
+  cudaStream_t st = ctx->stream[0];
+  u32* d_res = out_on_device ? (u32*)out : (u32*)ctx->buf(66, ballot_ct);
+  uint8_t* d_res_status = out_on_device ? status : (uint8_t*)ctx->buf(67, n_fields);
+  if (!d_res || !d_res_status) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+  if (n_chunks > 1) {
+    int rc = tally_dev_locked(ctx, d_parts, n_chunks, n_fields, d_res, d_res_status, fmt, st, 49);
+    if (rc != GCP_OK) return rc;
+  } else {
+    CU(cudaMemcpyAsync(d_res, d_parts, ballot_ct, cudaMemcpyDeviceToDevice, st), "D2D");
+  }
+  CU(launch_tally_status_merge(d_part_status, (int)n_chunks, n_fields, n_chunks > 1 ? 1 : 0, pk_flag, d_res, d_res_status, st),
+     "tally status kernel");
+  ctx->launches++;
+  if (!out_on_device) {
+    CU(cudaMemcpyAsync(out, d_res, ballot_ct, cudaMemcpyDeviceToHost, st), "D2H");
+    CU(cudaMemcpyAsync(status, d_res_status, n_fields, cudaMemcpyDeviceToHost, st), "D2H");
+  }
+  CU(cudaStreamSynchronize(st), "stream sync");
+  return GCP_OK;
 }
 
 // Host form: scalars are streamed in chunks, each chunk is encrypted and reduced on the device, and the per-chunk
 // partial ciphertexts are tallied at the end.  status[f] = 4 for every field when the key is off the curve.
-int gcp_elgamal_encrypt_tally(gcp_ctx* ctx, const void* pub_key, const void* k, const void* m, size_t n_ballots,
-                              int n_fields, void* out, uint8_t* status, int fmt) {
+static int encrypt_tally_host(gcp_ctx* ctx, const void* pub_key, const void* k, const void* m, size_t n_ballots, int n_fields,
+                              void* out, uint8_t* status, int fmt, bool out_on_device) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
@@ -1098,22 +1305,20 @@ int gcp_elgamal_encrypt_tally(gcp_ctx* ctx, const void* pub_key, const void* k, 
   if (rc != GCP_OK) return rc;
   rc = ensure_pk_table(ctx, pub_key, false, fmt, ctx->stream[0]);
   if (rc != GCP_OK) return rc;
-  u32 pk_ok = 0;
-  CU(cudaMemcpy(&pk_ok, ctx->d_flagPK, 4, cudaMemcpyDeviceToHost), "read key flag");
   const size_t ballot_in = (size_t)n_fields * 32, ballot_ct = (size_t)n_fields * 128;
-  size_t chunk = std::max<size_t>(1, std::min<size_t>(std::max<size_t>(n_ballots, 1), ((size_t)128 << 20) / ballot_in));
+  // 64 MB of k and of m per chunk (at 8 fields: 2^18 ballots, ~7 ms of kernel): short enough that the first copy, which
+  // nothing hides, is a few percent of a 2^24-ballot call, long enough to fill the machine (2^21 encryptions)
+  size_t chunk = std::max<size_t>(1, std::min<size_t>(std::max<size_t>(n_ballots, 1), ((size_t)64 << 20) / ballot_in));
   size_t n_chunks = n_ballots ? (n_ballots + chunk - 1) / chunk : 1;
   u32* d_parts = (u32*)ctx->buf(64, n_chunks * ballot_ct);
   uint8_t* d_part_status = (uint8_t*)ctx->buf(65, n_chunks * n_fields);
-  void* d_out = ctx->buf(66, ballot_ct);
-  uint8_t* d_status = (uint8_t*)ctx->buf(67, n_fields);
-  if (!d_parts || !d_part_status || !d_out || !d_status) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+  if (!d_parts || !d_part_status) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
   for (size_t c = 0; c < n_chunks; c++) {
     size_t off = c * chunk, cnt = n_ballots ? std::min(chunk, n_ballots - off) : 0;
     int s = (int)(c & 1);
     cudaStream_t st = ctx->stream[s];
-    void* dk = ctx->buf(48 + s * 8, std::max<size_t>(cnt, 1) * ballot_in);
-    void* dm = ctx->buf(48 + s * 8 + 4, std::max<size_t>(cnt, 1) * ballot_in);
+    void* dk = ctx->buf(48 + s * 8, std::max<size_t>(std::min(chunk, n_ballots), 1) * ballot_in);
+    void* dm = ctx->buf(48 + s * 8 + 4, std::max<size_t>(std::min(chunk, n_ballots), 1) * ballot_in);
     if (!dk || !dm) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
     if (cnt) {
       GCP_TRY(h2d_copy(ctx, dk, (const char*)k + off * ballot_in, cnt * ballot_in, st));
@@ -1125,26 +1330,12 @@ int gcp_elgamal_encrypt_tally(gcp_ctx* ctx, const void* pub_key, const void* k, 
   }
   CU(cudaStreamSynchronize(ctx->stream[0]), "stream sync");
   CU(cudaStreamSynchronize(ctx->stream[1]), "stream sync");
-  cudaStream_t st = ctx->stream[0];
-  const void* d_final = d_parts;
-  const uint8_t* d_final_status = d_part_status;
-  if (n_chunks > 1) {
-    rc = tally_dev_locked(ctx, d_parts, n_chunks, n_fields, d_out, d_status, fmt, st, 49);
-    if (rc != GCP_OK) return rc;
-    d_final = d_out;
-    d_final_status = d_status;
-  }
-  std::vector<uint8_t> part_status(n_chunks * n_fields);
-  CU(cudaMemcpyAsync(out, d_final, ballot_ct, cudaMemcpyDeviceToHost, st), "D2H");
-  CU(cudaMemcpyAsync(status, d_final_status, n_fields, cudaMemcpyDeviceToHost, st), "D2H");
-  CU(cudaMemcpyAsync(part_status.data(), d_part_status, part_status.size(), cudaMemcpyDeviceToHost, st), "D2H");
-  CU(cudaStreamSynchronize(st), "stream sync");
-  for (int f = 0; f < n_fields; f++) {
-    for (size_t c = 0; c < n_chunks; c++)
-      if (part_status[c * n_fields + f] && !status[f]) status[f] = part_status[c * n_fields + f];
-    if (!pk_ok) status[f] = (uint8_t)gcp::GCP_STATUS_OFF_CURVE;
-  }
-  return GCP_OK;
+  return finish_partials(ctx, d_parts, d_part_status, n_chunks, n_fields, fmt, ctx->d_flagPK, out, status, out_on_device);
+}
+
+int gcp_elgamal_encrypt_tally(gcp_ctx* ctx, const void* pub_key, const void* k, const void* m, size_t n_ballots,
+                              int n_fields, void* out, uint8_t* status, int fmt) {
+  return encrypt_tally_host(ctx, pub_key, k, m, n_ballots, n_fields, out, status, fmt, false);
 }
 
 // Generic host-buffer pipeline for the per-item ElGamal calls.
@@ -1168,23 +1359,27 @@ static int elgamal_host(gcp_ctx* ctx, int kind, const void* pk, int pk_per_item,
     rc = ensure_pk_table(ctx, pk, false, fmt, ctx->stream[0]);
     if (rc != GCP_OK) return rc;
   }
-  size_t chunk = std::min<size_t>(n, (size_t)1 << 20);
-  size_t k = 0;
-  for (size_t off = 0; off < n && rc == GCP_OK; off += chunk, k++) {
-    size_t m = std::min(chunk, n - off);
+  // per-item keys run the variable-base window kernel: whole resident waves of it; the other kinds are PCIe-bound and
+  // only want a short first chunk (the one copy nothing hides)
+  const bool varbase = kind == 1 && pk_per_item;
+  ChunkPlan plan(n, varbase ? varbase_wave_items(ctx->sm_count) : (size_t)1 << 18, varbase ? (size_t)1 << 18 : (size_t)1 << 20);
+  const size_t cap = plan.largest();
+  size_t k = 0, off = 0;
+  for (size_t m = plan.next(); m != 0 && rc == GCP_OK; off += m, m = plan.next(), k++) {
     int s = (int)(k & 1);
     cudaStream_t st = ctx->stream[s];
     const int b = 48 + s * 8;
-    void* d0 = ctx->buf(b + 0, m * in0_b);
-    void* d1 = in1_b ? ctx->buf(b + 1, m * in1_b) : nullptr;
-    void* dpk = (kind == 1 && pk_per_item) ? ctx->buf(b + 2, m * 64) : nullptr;
-    void* dout = ctx->buf(b + 3, m * out_b);
-    uint8_t* dst = (uint8_t*)ctx->buf(b + 4, m);
-    if (!d0 || (in1_b && !d1) || (kind == 1 && pk_per_item && !dpk) || !dout || !dst)
+    void* d0 = ctx->buf(b + 0, cap * in0_b);
+    void* d1 = in1_b ? ctx->buf(b + 1, cap * in1_b) : nullptr;
+    void* dpk = (kind == 1 && pk_per_item) ? ctx->buf(b + 2, cap * 64) : nullptr;
+    void* dout = ctx->buf(b + 3, cap * out_b);
+    uint8_t* dst = (uint8_t*)ctx->buf(b + 4, cap);
+    if (!d0 || (in1_b && !d1) || (kind == 1 && pk_per_item && !dpk) || !dout || !dst || !ctx->buf(b + 5, cap * 192) ||
+        (varbase && !ctx->buf(99 + s, varbase_scratch_bytes(0, cap))))
       return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
     GCP_TRY(h2d_copy(ctx, d0, (const char*)in0 + off * in0_b, m * in0_b, st));
     if (in1_b) GCP_TRY(h2d_copy(ctx, d1, (const char*)in1 + off * in1_b, m * in1_b, st));
-    if (dpk) CU(cudaMemcpyAsync(dpk, (const char*)pk + off * 64, m * 64, cudaMemcpyHostToDevice, st), "H2D");
+    if (dpk) GCP_TRY(h2d_copy(ctx, dpk, (const char*)pk + off * 64, m * 64, st));
     switch (kind) {
       case 0: rc = fixed_base_dev_locked(ctx, d0, m, dout, dst, fmt, st, b + 5); break;
       case 1: rc = encrypt_dev_locked(ctx, pk_per_item ? dpk : (const void*)ctx->d_base_xy, pk_per_item, d0, d1, m, dout, dst, fmt, st, b + 5, 99 + s); break;
@@ -1245,10 +1440,10 @@ static int ct_elementwise_host(gcp_ctx* ctx, int kind, const uint8_t* sel, const
     void* dout = ctx->buf(bs + 3, m * out_b);
     uint8_t* dst = (uint8_t*)ctx->buf(bs + 4, m);
     if (!da || !db || !dout || !dst || (kind == 1 && !dsel)) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
-    CU(cudaMemcpyAsync(da, (const char*)a + off * 128, m * 128, cudaMemcpyHostToDevice, st), "H2D");
-    CU(cudaMemcpyAsync(db, (const char*)b + off * 128, m * 128, cudaMemcpyHostToDevice, st), "H2D");
+    GCP_TRY(h2d_copy(ctx, da, (const char*)a + off * 128, m * 128, st));
+    GCP_TRY(h2d_copy(ctx, db, (const char*)b + off * 128, m * 128, st));
     if (kind == 1) {
-      CU(cudaMemcpyAsync(dsel, sel + off, m, cudaMemcpyHostToDevice, st), "H2D");
+      GCP_TRY(h2d_copy(ctx, dsel, sel + off, m, st));
       CU(launch_ct_select(dsel, (const u32*)da, (const u32*)db, m, (u32*)dout, dst, st), "select kernel");
     } else {
       CU(launch_ct_is_equal((const u32*)da, (const u32*)db, m, (uint8_t*)dout, dst, st), "is-equal kernel");
@@ -1272,7 +1467,8 @@ int gcp_elgamal_select(gcp_ctx* ctx, const uint8_t* sel, const void* i1, const v
 
 // Tally over host-resident ciphertexts: chunks are reduced on the device as they arrive; the per-chunk partial
 // ciphertexts are themselves tallied at the end (addition is associative, so the result does not depend on chunking).
-int gcp_elgamal_tally(gcp_ctx* ctx, const void* ct, size_t n_ballots, int n_fields, void* out, uint8_t* status, int fmt) {
+static int tally_host(gcp_ctx* ctx, const void* ct, size_t n_ballots, int n_fields, void* out, uint8_t* status, int fmt,
+                      bool out_on_device) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
@@ -1282,18 +1478,17 @@ int gcp_elgamal_tally(gcp_ctx* ctx, const void* ct, size_t n_ballots, int n_fiel
   if (n_fields < 1 || n_fields > 64) return ctx->fail(GCP_ERR_BAD_ARG, "n_fields must be in [1, 64]");
   if (!out || !status || (n_ballots && !ct)) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
   const size_t ballot_b = (size_t)n_fields * 128;
-  size_t chunk = std::max<size_t>(1, std::min<size_t>(std::max<size_t>(n_ballots, 1), ((size_t)256 << 20) / ballot_b));
+  // the kernel outruns PCIe 5:1, so the call is one long copy: 64 MB chunks keep the tail after the last copy short
+  size_t chunk = std::max<size_t>(1, std::min<size_t>(std::max<size_t>(n_ballots, 1), ((size_t)64 << 20) / ballot_b));
   size_t n_chunks = n_ballots ? (n_ballots + chunk - 1) / chunk : 1;
   u32* d_parts = (u32*)ctx->buf(64, n_chunks * ballot_b);
   uint8_t* d_part_status = (uint8_t*)ctx->buf(65, n_chunks * n_fields);
-  void* d_out = ctx->buf(66, ballot_b);
-  uint8_t* d_status = (uint8_t*)ctx->buf(67, n_fields);
-  if (!d_parts || !d_part_status || !d_out || !d_status) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+  if (!d_parts || !d_part_status) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
   for (size_t c = 0; c < n_chunks; c++) {
     size_t off = c * chunk, m = n_ballots ? std::min(chunk, n_ballots - off) : 0;
     int s = (int)(c & 1);
     cudaStream_t st = ctx->stream[s];
-    void* d_ct = ctx->buf(48 + s * 8, std::max<size_t>(m, 1) * ballot_b);
+    void* d_ct = ctx->buf(48 + s * 8, std::max<size_t>(std::min(chunk, n_ballots), 1) * ballot_b);
     if (!d_ct) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
     if (m) GCP_TRY(h2d_copy(ctx, d_ct, (const char*)ct + off * ballot_b, m * ballot_b, st));
     rc = tally_dev_locked(ctx, d_ct, m, n_fields, (char*)d_parts + c * ballot_b, d_part_status + c * n_fields, fmt, st,
@@ -1302,24 +1497,11 @@ int gcp_elgamal_tally(gcp_ctx* ctx, const void* ct, size_t n_ballots, int n_fiel
   }
   CU(cudaStreamSynchronize(ctx->stream[0]), "stream sync");
   CU(cudaStreamSynchronize(ctx->stream[1]), "stream sync");
-  cudaStream_t st = ctx->stream[0];
-  if (n_chunks == 1) {
-    CU(cudaMemcpyAsync(out, d_parts, ballot_b, cudaMemcpyDeviceToHost, st), "D2H");
-    CU(cudaMemcpyAsync(status, d_part_status, n_fields, cudaMemcpyDeviceToHost, st), "D2H");
-    CU(cudaStreamSynchronize(st), "stream sync");
-    return GCP_OK;
-  }
-  rc = tally_dev_locked(ctx, d_parts, n_chunks, n_fields, d_out, d_status, fmt, st, 49);
-  if (rc != GCP_OK) return rc;
-  std::vector<uint8_t> part_status(n_chunks * n_fields);
-  CU(cudaMemcpyAsync(out, d_out, ballot_b, cudaMemcpyDeviceToHost, st), "D2H");
-  CU(cudaMemcpyAsync(status, d_status, n_fields, cudaMemcpyDeviceToHost, st), "D2H");
-  CU(cudaMemcpyAsync(part_status.data(), d_part_status, part_status.size(), cudaMemcpyDeviceToHost, st), "D2H");
-  CU(cudaStreamSynchronize(st), "stream sync");
-  for (size_t c = 0; c < n_chunks; c++)
-    for (int f = 0; f < n_fields; f++)
-      if (part_status[c * n_fields + f] && !status[f]) status[f] = part_status[c * n_fields + f];
-  return GCP_OK;
+  return finish_partials(ctx, d_parts, d_part_status, n_chunks, n_fields, fmt, nullptr, out, status, out_on_device);
+}
+
+int gcp_elgamal_tally(gcp_ctx* ctx, const void* ct, size_t n_ballots, int n_fields, void* out, uint8_t* status, int fmt) {
+  return tally_host(ctx, ct, n_ballots, n_fields, out, status, fmt, false);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1344,16 +1526,21 @@ int gcp_ballot_batch_dev(gcp_ctx* ctx, int n_levels, size_t n_voters, const void
                              d_values, nullptr, nullptr, d_flags, d_status, nullptr, fmt, st, 2);
   if (rc != GCP_OK) return rc;
   // flags are 0 wherever status != 0 (smt_path_kernel), so the flag array is the admission mask
-  return encrypt_tally_dev_locked(ctx, d_k, d_m, d_flags, n_voters, n_fields, d_tally, d_tally_status, fmt, st, 44);
+  rc = encrypt_tally_dev_locked(ctx, d_k, d_m, d_flags, n_voters, n_fields, d_tally, d_tally_status, fmt, st, 44);
+  if (rc != GCP_OK) return rc;
+  CU(launch_tally_status_merge(nullptr, 0, n_fields, 1, ctx->d_flagPK, (u32*)d_tally, d_tally_status, st), "tally status kernel");
+  ctx->launches++;
+  return GCP_OK;
 }
 
 // Host-buffer form of the ballot batch: voters are streamed in chunks on the two streams (proofs dense, or arbo packed
 // when siblings == NULL), each chunk runs verifier -> masked encrypt-tally on the device, the per-chunk partial
 // ciphertexts are folded at the end.  out_flags / out_status: per voter; out_tally / out_tally_status: per field.
-int gcp_ballot_batch(gcp_ctx* ctx, int n_levels, size_t n_voters, const void* roots, int shared_root, const void* siblings,
-                     const uint8_t* packed, const uint64_t* offsets, const void* keys, const void* values,
-                     const void* pub_key, const void* k, const void* m, int n_fields, uint8_t* out_flags,
-                     uint8_t* out_status, void* out_tally, uint8_t* out_tally_status, int fmt) {
+static int ballot_batch_host(gcp_ctx* ctx, int n_levels, size_t n_voters, const void* roots, int shared_root,
+                             const void* siblings, const uint8_t* packed, const uint64_t* offsets, const void* keys,
+                             const void* values, const void* pub_key, const void* k, const void* m, int n_fields,
+                             uint8_t* out_flags, uint8_t* out_status, void* out_tally, uint8_t* out_tally_status, int fmt,
+                             bool tally_on_device) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
@@ -1367,64 +1554,62 @@ int gcp_ballot_batch(gcp_ctx* ctx, int n_levels, size_t n_voters, const void* ro
     return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
   rc = ensure_pk_table(ctx, pub_key, false, fmt, ctx->stream[0]);
   if (rc != GCP_OK) return rc;
-  u32 pk_ok = 0;
-  CU(cudaMemcpy(&pk_ok, ctx->d_flagPK, 4, cudaMemcpyDeviceToHost), "read key flag");
   const size_t sib_bytes = (size_t)n_levels * 32, ballot_in = (size_t)n_fields * 32, ballot_ct = (size_t)n_fields * 128;
-  const size_t wave = (size_t)ctx->sm_count * 5 * 128;
-  size_t chunk = std::max<size_t>(1, ((size_t)1 << 30) / (sib_bytes + 2 * ballot_in));
-  if (chunk > wave) chunk -= chunk % wave;
-  chunk = std::max<size_t>(1, std::min(chunk, std::max<size_t>(n, 1)));
-  if (const char* env = getenv("GCP_B200_SMT_CHUNK")) {
-    long v = atol(env);
-    if (v > 0) chunk = std::min<size_t>(std::max<size_t>(n, 1), (size_t)v);
+  ChunkPlan plan(n, smt_path_wave_items(ctx->sm_count), ((size_t)1 << 30) / (sib_bytes + 2 * ballot_in));
+  std::vector<size_t> sizes;
+  {
+    ChunkPlan walk = plan;
+    for (size_t c = walk.next(); c != 0; c = walk.next()) sizes.push_back(c);
+    if (sizes.empty()) sizes.push_back(0);
   }
-  const size_t n_chunks = n ? (n + chunk - 1) / chunk : 1;
+  const size_t n_chunks = sizes.size(), cap = std::max<size_t>(plan.largest(), 1);
   u32* d_parts = (u32*)ctx->buf(64, n_chunks * ballot_ct);
   uint8_t* d_part_status = (uint8_t*)ctx->buf(65, n_chunks * n_fields);
-  void* d_out = ctx->buf(66, ballot_ct);
-  uint8_t* d_tstatus = (uint8_t*)ctx->buf(67, n_fields);
   void* d_shared_root = nullptr;
-  if (!d_parts || !d_part_status || !d_out || !d_tstatus) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+  if (!d_parts || !d_part_status) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
   if (shared_root && n) {
     d_shared_root = ctx->buf(3, 32);
     if (!d_shared_root) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
     CU(cudaMemcpy(d_shared_root, roots, 32, cudaMemcpyHostToDevice), "H2D root");
   }
-  for (size_t c = 0; c < n_chunks; c++) {
-    const size_t off = c * chunk, cnt = n ? std::min(chunk, n - off) : 0;
+  size_t off = 0;
+  for (size_t c = 0; c < n_chunks; off += sizes[c], c++) {
+    const size_t cnt = sizes[c];
     const int s = (int)(c & 1);
     cudaStream_t st = ctx->stream[s];
     const int b = 10 + s * 14;
-    void* dk = ctx->buf(48 + s * 8, std::max<size_t>(cnt, 1) * ballot_in);
-    void* dm = ctx->buf(48 + s * 8 + 4, std::max<size_t>(cnt, 1) * ballot_in);
-    uint8_t* d_flags = (uint8_t*)ctx->buf(b + 9, std::max<size_t>(cnt, 1));
+    // every slot is sized for the largest chunk of the plan: growing one later would cudaFree under running work
+    void* dk = ctx->buf(48 + s * 8, cap * ballot_in);
+    void* dm = ctx->buf(48 + s * 8 + 4, cap * ballot_in);
+    uint8_t* d_flags = (uint8_t*)ctx->buf(b + 9, cap);
     if (!dk || !dm || !d_flags) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
     if (cnt) {
-      void* d_sib = ctx->buf(b + 0, cnt * sib_bytes);
-      void* d_roots = shared_root ? d_shared_root : ctx->buf(b + 1, cnt * 32);
-      void* d_keys = ctx->buf(b + 2, cnt * 32);
-      void* d_vals = ctx->buf(b + 3, cnt * 32);
-      uint8_t* d_status = (uint8_t*)ctx->buf(b + 10, cnt);
-      if (!d_sib || !d_roots || !d_keys || !d_vals || !d_status) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+      void* d_sib = ctx->buf(b + 0, cap * sib_bytes);
+      void* d_roots = shared_root ? d_shared_root : ctx->buf(b + 1, cap * 32);
+      void* d_keys = ctx->buf(b + 2, cap * 32);
+      void* d_vals = ctx->buf(b + 3, cap * 32);
+      uint8_t* d_status = (uint8_t*)ctx->buf(b + 10, cap);
+      if (!d_sib || !d_roots || !d_keys || !d_vals || !d_status || !ctx->buf(b + 12, smt_scratch_bytes(cap)))
+        return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
       uint8_t* d_bad = nullptr;
       if (is_packed) {
         const uint64_t pbeg = offsets[off], pend = offsets[off + cnt];
         if (pend < pbeg) return ctx->fail(GCP_ERR_BAD_ARG, "packed offsets must be non-decreasing");
         const size_t pbytes = (size_t)(pend - pbeg);
         uint8_t* d_packed = (uint8_t*)ctx->buf(80 + s * 3 + 0, pbytes + 4);
-        uint64_t* d_off = (uint64_t*)ctx->buf(80 + s * 3 + 1, (cnt + 1) * 8);
-        d_bad = (uint8_t*)ctx->buf(80 + s * 3 + 2, cnt);
+        uint64_t* d_off = (uint64_t*)ctx->buf(80 + s * 3 + 1, (cap + 1) * 8);
+        d_bad = (uint8_t*)ctx->buf(80 + s * 3 + 2, cap);
         if (!d_packed || !d_off || !d_bad) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
-        if (pbytes) CU(cudaMemcpyAsync(d_packed, packed + pbeg, pbytes, cudaMemcpyHostToDevice, st), "H2D");
-        CU(cudaMemcpyAsync(d_off, offsets + off, (cnt + 1) * 8, cudaMemcpyHostToDevice, st), "H2D");
+        if (pbytes) GCP_TRY(h2d_copy(ctx, d_packed, packed + pbeg, pbytes, st));
+        GCP_TRY(h2d_copy(ctx, d_off, offsets + off, (cnt + 1) * 8, st));
         CU(launch_smt_unpack(d_packed, d_off, pbeg, pbytes, cnt, n_levels, (u32*)d_sib, d_bad, fmt, st), "smt unpack kernel");
         ctx->launches++;
       } else {
         GCP_TRY(h2d_copy(ctx, d_sib, (const char*)siblings + off * sib_bytes, cnt * sib_bytes, st));
       }
-      if (!shared_root) CU(cudaMemcpyAsync(d_roots, (const char*)roots + off * 32, cnt * 32, cudaMemcpyHostToDevice, st), "H2D");
-      CU(cudaMemcpyAsync(d_keys, (const char*)keys + off * 32, cnt * 32, cudaMemcpyHostToDevice, st), "H2D");
-      CU(cudaMemcpyAsync(d_vals, (const char*)values + off * 32, cnt * 32, cudaMemcpyHostToDevice, st), "H2D");
+      if (!shared_root) GCP_TRY(h2d_copy(ctx, d_roots, (const char*)roots + off * 32, cnt * 32, st));
+      GCP_TRY(h2d_copy(ctx, d_keys, (const char*)keys + off * 32, cnt * 32, st));
+      GCP_TRY(h2d_copy(ctx, d_vals, (const char*)values + off * 32, cnt * 32, st));
       GCP_TRY(h2d_copy(ctx, dk, (const char*)k + off * ballot_in, cnt * ballot_in, st));
       GCP_TRY(h2d_copy(ctx, dm, (const char*)m + off * ballot_in, cnt * ballot_in, st));
       rc = smt_verify_dev_locked(ctx, n_levels, cnt, d_roots, shared_root, d_sib, nullptr, nullptr, nullptr, d_keys, d_vals,
@@ -1444,26 +1629,44 @@ int gcp_ballot_batch(gcp_ctx* ctx, int n_levels, size_t n_voters, const void* ro
   }
   CU(cudaStreamSynchronize(ctx->stream[0]), "stream sync");
   CU(cudaStreamSynchronize(ctx->stream[1]), "stream sync");
-  cudaStream_t st = ctx->stream[0];
-  const void* d_final = d_parts;
-  const uint8_t* d_final_status = d_part_status;
-  if (n_chunks > 1) {
-    rc = tally_dev_locked(ctx, d_parts, n_chunks, n_fields, d_out, d_tstatus, fmt, st, 49);
-    if (rc != GCP_OK) return rc;
-    d_final = d_out;
-    d_final_status = d_tstatus;
-  }
-  std::vector<uint8_t> part_status(n_chunks * n_fields);
-  CU(cudaMemcpyAsync(out_tally, d_final, ballot_ct, cudaMemcpyDeviceToHost, st), "D2H");
-  CU(cudaMemcpyAsync(out_tally_status, d_final_status, n_fields, cudaMemcpyDeviceToHost, st), "D2H");
-  CU(cudaMemcpyAsync(part_status.data(), d_part_status, part_status.size(), cudaMemcpyDeviceToHost, st), "D2H");
-  CU(cudaStreamSynchronize(st), "stream sync");
-  for (int f = 0; f < n_fields; f++) {
-    for (size_t c = 0; c < n_chunks; c++)
-      if (part_status[c * n_fields + f] && !out_tally_status[f]) out_tally_status[f] = part_status[c * n_fields + f];
-    if (!pk_ok) out_tally_status[f] = (uint8_t)gcp::GCP_STATUS_OFF_CURVE;
-  }
+  return finish_partials(ctx, d_parts, d_part_status, n_chunks, n_fields, fmt, ctx->d_flagPK, out_tally, out_tally_status,
+                         tally_on_device);
+}
+
+int gcp_ballot_batch(gcp_ctx* ctx, int n_levels, size_t n_voters, const void* roots, int shared_root, const void* siblings,
+                     const uint8_t* packed, const uint64_t* offsets, const void* keys, const void* values,
+                     const void* pub_key, const void* k, const void* m, int n_fields, uint8_t* out_flags,
+                     uint8_t* out_status, void* out_tally, uint8_t* out_tally_status, int fmt) {
+  return ballot_batch_host(ctx, n_levels, n_voters, roots, shared_root, siblings, packed, offsets, keys, values, pub_key, k,
+                           m, n_fields, out_flags, out_status, out_tally, out_tally_status, fmt, false);
+}
+
+// Folds that leave their result on the device, for the single-process group (group.cu): the partial tally of a device's
+// slice goes straight into the all-gather's send buffer.  Declared in internal.h, not part of the public ABI.
+int gcp_internal_tally_to_dev(gcp_ctx* ctx, const void* ct, size_t n_ballots, int n_fields, void* d_out, uint8_t* d_status,
+                              int fmt) {
+  return tally_host(ctx, ct, n_ballots, n_fields, d_out, d_status, fmt, true);
+}
+int gcp_internal_merge_status_dev(gcp_ctx* ctx, const uint8_t* d_part_status, int n_parts, int n_fields, void* d_ct,
+                                  uint8_t* d_status, void* stream) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  CU(launch_tally_status_merge(d_part_status, n_parts, n_fields, 1, nullptr, (u32*)d_ct, d_status, (cudaStream_t)stream),
+     "tally status kernel");
+  ctx->launches++;
   return GCP_OK;
+}
+int gcp_internal_encrypt_tally_to_dev(gcp_ctx* ctx, const void* pub_key, const void* k, const void* m, size_t n_ballots,
+                                      int n_fields, void* d_out, uint8_t* d_status, int fmt) {
+  return encrypt_tally_host(ctx, pub_key, k, m, n_ballots, n_fields, d_out, d_status, fmt, true);
+}
+int gcp_internal_ballot_batch_to_dev(gcp_ctx* ctx, int n_levels, size_t n_voters, const void* roots, int shared_root,
+                                     const void* siblings, const uint8_t* packed, const uint64_t* offsets, const void* keys,
+                                     const void* values, const void* pub_key, const void* k, const void* m, int n_fields,
+                                     uint8_t* out_flags, uint8_t* out_status, void* d_tally, uint8_t* d_tally_status, int fmt) {
+  return ballot_batch_host(ctx, n_levels, n_voters, roots, shared_root, siblings, packed, offsets, keys, values, pub_key, k,
+                           m, n_fields, out_flags, out_status, d_tally, d_tally_status, fmt, true);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1481,7 +1684,7 @@ static int upload_all(gcp_ctx* ctx, const Upload* ins, int n_ins, size_t n, void
   for (int i = 0; i < n_ins; i++) {
     d_ptrs[i] = ctx->buf(70 + i, n * ins[i].bytes_per_item);
     if (!d_ptrs[i]) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
-    CU(cudaMemcpyAsync(d_ptrs[i], ins[i].host, n * ins[i].bytes_per_item, cudaMemcpyHostToDevice, ctx->stream[0]), "H2D");
+    GCP_TRY(h2d_copy(ctx, d_ptrs[i], ins[i].host, n * ins[i].bytes_per_item, ctx->stream[0]));
   }
   return GCP_OK;
 }
@@ -1492,23 +1695,24 @@ extern "C++" {
 template <typename Launch>
 static int per_item_pipeline(gcp_ctx* ctx, const Upload* ins, int n_ins, size_t n, uint8_t* out_flags, uint8_t* status,
                              const char* what, Launch launch) {
-  const size_t chunk = std::min<size_t>(n, (size_t)1 << 18);
-  size_t k = 0;
-  for (size_t off = 0; off < n; off += chunk, k++) {
-    const size_t m = std::min(chunk, n - off);
+  // chunks of whole resident waves of the window kernel (the first one a single wave: its copy is the only exposed one)
+  ChunkPlan plan(n, varbase_wave_items(ctx->sm_count), (size_t)1 << 18);
+  const size_t cap = plan.largest();
+  size_t k = 0, off = 0;
+  for (size_t m = plan.next(); m != 0; off += m, m = plan.next(), k++) {
     const int s = (int)(k & 1);
     cudaStream_t st = ctx->stream[s];
     const int base = s ? 86 : 70;
     void* d[8];
     for (int i = 0; i < n_ins; i++) {
-      d[i] = ctx->buf(base + i, m * ins[i].bytes_per_item);
+      d[i] = ctx->buf(base + i, cap * ins[i].bytes_per_item);
       if (!d[i]) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
       GCP_TRY(h2d_copy(ctx, d[i], (const char*)ins[i].host + off * ins[i].bytes_per_item, m * ins[i].bytes_per_item, st));
     }
-    uint8_t* d_flags = (uint8_t*)ctx->buf(s ? 92 : 77, m);
-    uint8_t* d_status = (uint8_t*)ctx->buf(s ? 93 : 78, m);
+    uint8_t* d_flags = (uint8_t*)ctx->buf(s ? 92 : 77, cap);
+    uint8_t* d_status = (uint8_t*)ctx->buf(s ? 93 : 78, cap);
     if (!d_flags || !d_status) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
-    CU(launch(d, m, d_flags, d_status, s, st), what);
+    CU(launch(d, m, cap, d_flags, d_status, s, st), what);
     CU(cudaMemcpyAsync(out_flags + off, d_flags, m, cudaMemcpyDeviceToHost, st), "D2H");
     CU(cudaMemcpyAsync(status + off, d_status, m, cudaMemcpyDeviceToHost, st), "D2H");
   }
@@ -1597,8 +1801,8 @@ int gcp_elgamal_assert_decrypt(gcp_ctx* ctx, const void* ct, const void* priv_ke
   if (!ct || !priv_keys || !msgs || !out_flags || !status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
   Upload ins[3] = {{ct, 128}, {priv_keys, 32}, {msgs, 32}};
   return per_item_pipeline(ctx, ins, 3, n, out_flags, status, "assert-decrypt kernels",
-                           [&](void** d, size_t m, uint8_t* d_flags, uint8_t* d_status, int s, cudaStream_t st) {
-                             u32* scratch = (u32*)ctx->buf(96 + s, varbase_scratch_bytes(1, m));
+                           [&](void** d, size_t m, size_t cap, uint8_t* d_flags, uint8_t* d_status, int s, cudaStream_t st) {
+                             u32* scratch = (u32*)ctx->buf(96 + s, varbase_scratch_bytes(1, cap));
                              if (!scratch) return cudaErrorMemoryAllocation;
                              int nl = 0;
                              cudaError_t e = launch_assert_decrypt(ctx->d_tabG, (const u32*)d[0], (const u32*)d[1],
@@ -1620,8 +1824,8 @@ int gcp_elgamal_verify_decryption_proof(gcp_ctx* ctx, const void* pub_keys, cons
   if (!pub_keys || !ct || !msgs || !a1 || !a2 || !z || !out_flags || !status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
   Upload ins[6] = {{pub_keys, 64}, {ct, 128}, {msgs, 32}, {a1, 64}, {a2, 64}, {z, 32}};
   return per_item_pipeline(ctx, ins, 6, n, out_flags, status, "decryption-proof kernels",
-                           [&](void** d, size_t m, uint8_t* d_flags, uint8_t* d_status, int s, cudaStream_t st) {
-                             u32* scratch = (u32*)ctx->buf(96 + s, varbase_scratch_bytes(2, m));
+                           [&](void** d, size_t m, size_t cap, uint8_t* d_flags, uint8_t* d_status, int s, cudaStream_t st) {
+                             u32* scratch = (u32*)ctx->buf(96 + s, varbase_scratch_bytes(2, cap));
                              if (!scratch) return cudaErrorMemoryAllocation;
                              int nl = 0;
                              cudaError_t e = launch_decryption_proof(ctx->d_tabG, ctx->tab[13], (const u32*)d[0], (const u32*)d[1],
@@ -1643,8 +1847,8 @@ int gcp_eddsa_verify(gcp_ctx* ctx, const void* pub_keys_te, const void* sig_r_te
   if (!pub_keys_te || !sig_r_te || !sig_s || !msgs || !out_flags || !status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
   Upload ins[4] = {{pub_keys_te, 64}, {sig_r_te, 64}, {sig_s, 32}, {msgs, 32}};
   return per_item_pipeline(ctx, ins, 4, n, out_flags, status, "eddsa kernels",
-                           [&](void** d, size_t m, uint8_t* d_flags, uint8_t* d_status, int s, cudaStream_t st) {
-                             u32* scratch = (u32*)ctx->buf(96 + s, varbase_scratch_bytes(3, m));
+                           [&](void** d, size_t m, size_t cap, uint8_t* d_flags, uint8_t* d_status, int s, cudaStream_t st) {
+                             u32* scratch = (u32*)ctx->buf(96 + s, varbase_scratch_bytes(3, cap));
                              if (!scratch) return cudaErrorMemoryAllocation;
                              int nl = 0;
                              cudaError_t e = launch_eddsa_verify(ctx->d_tabG, ctx->tab[6], (const u32*)d[0], (const u32*)d[1],
@@ -1758,7 +1962,7 @@ int gcp_poseidon2_set_round_keys(gcp_ctx* ctx, const void* keys, size_t n_keys, 
   }
   cudaStream_t st = ctx->stream[0];
   CU(cudaStreamSynchronize(ctx->stream[1]), "stream sync");
-  CU(cudaMemcpyAsync(ctx->d_p2_keys, keys, 62 * 32, cudaMemcpyHostToDevice, st), "H2D");
+  GCP_TRY(h2d_copy(ctx, ctx->d_p2_keys, keys, 62 * 32, st));
   if (fmt == GCP_FMT_CANONICAL) {
     CU(launch_to_mont(ctx->d_p2_keys, 62, st), "to_mont kernel");
     ctx->launches++;

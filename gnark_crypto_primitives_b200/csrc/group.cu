@@ -14,6 +14,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -21,7 +22,7 @@
 #include <thread>
 #include <vector>
 
-#include "../../include/gcp_b200.h"
+#include "internal.h"
 
 namespace {
 
@@ -64,8 +65,8 @@ struct gcp_group {
   std::vector<int> devices;
   std::vector<gcp_ctx*> ctx;
   std::vector<cudaStream_t> stream;       // exchange stream per device
-  std::vector<unsigned char*> d_send;     // per device: this device's partials
-  std::vector<unsigned char*> d_recv;     // per device: gathered partials
+  std::vector<unsigned char*> d_send;     // per device: this device's partial ciphertexts | statuses (kSendStatusOff)
+  std::vector<unsigned char*> d_recv;     // per device: gathered partial ciphertexts | gathered statuses
   std::vector<unsigned char*> d_out;      // per device: final tally + status
   std::vector<ncclComm_t> comm;
   Nccl nccl;
@@ -73,37 +74,86 @@ struct gcp_group {
   std::mutex mu;  // one group call at a time (the collective must be entered by all devices together)
   std::mutex err_mu;
   std::string err;
+  // one persistent host thread per device (round 1 spawned and joined three std::thread fan-outs per call): a call
+  // publishes a job, every worker runs it for its device, the caller waits for the last one
+  std::vector<std::thread> workers;
+  std::mutex wmu;
+  std::condition_variable wcv, dcv;
+  const std::function<int(int)>* job = nullptr;
+  unsigned long long generation = 0;
+  int pending = 0;
+  std::vector<int> rcs;
+  bool stop = false;
 };
 
-static std::string g_group_create_error;
+// message of the last failed gcp_group_create: process-wide, mutex-guarded, read through a per-thread copy (a goroutine may
+// run the create call and the gcp_group_last_error(NULL) call on different OS threads)
+static std::mutex g_group_create_mu;
+static std::string g_group_create_text;
+static struct GroupCreateError {
+  GroupCreateError& operator=(const std::string& m) {
+    std::lock_guard<std::mutex> lk(g_group_create_mu);
+    g_group_create_text = m;
+    return *this;
+  }
+  GroupCreateError& operator=(const char* m) { return *this = std::string(m); }
+  const char* c_str() const {
+    thread_local std::string copy;
+    std::lock_guard<std::mutex> lk(g_group_create_mu);
+    copy = g_group_create_text;
+    return copy.c_str();
+  }
+} g_group_create_error;
 
 namespace {
-
-constexpr size_t kMaxFields = 64;
-constexpr size_t kCtBytes = 128;
 
 struct Shard {
   size_t lo, hi;
 };
 Shard shard_of(size_t n, int world, int rank) { return {n * (size_t)rank / world, n * (size_t)(rank + 1) / world}; }
 
-// run fn(i) on one host thread per device; returns the first non-zero code and records that device's message
+constexpr size_t kMaxFields = 64;
+constexpr size_t kCtBytes = 128;
+constexpr size_t kSendStatusOff = kMaxFields * kCtBytes;  // statuses sit behind the largest ciphertext block
+
+void worker_main(gcp_group* g, int i) {
+  cudaSetDevice(g->devices[i]);
+  unsigned long long seen = 0;
+  for (;;) {
+    const std::function<int(int)>* job;
+    {
+      std::unique_lock<std::mutex> lk(g->wmu);
+      g->wcv.wait(lk, [&] { return g->stop || g->generation != seen; });
+      if (g->stop) return;
+      seen = g->generation;
+      job = g->job;
+    }
+    const int rc = (*job)(i);
+    std::lock_guard<std::mutex> lk(g->wmu);
+    g->rcs[i] = rc;
+    if (--g->pending == 0) g->dcv.notify_all();
+  }
+}
+
+// run fn(i) for every device on its persistent host thread; returns the first non-zero code and records that device's message
 int for_each_device(gcp_group* g, const std::function<int(int)>& fn) {
   const int w = (int)g->ctx.size();
-  std::vector<int> rc(w, GCP_OK);
   if (w == 1) {
-    rc[0] = fn(0);
+    g->rcs[0] = fn(0);
   } else {
-    std::vector<std::thread> th;
-    th.reserve(w);
-    for (int i = 0; i < w; i++) th.emplace_back([&, i] { rc[i] = fn(i); });
-    for (auto& t : th) t.join();
+    std::unique_lock<std::mutex> lk(g->wmu);
+    g->job = &fn;
+    g->pending = w;
+    g->generation++;
+    g->wcv.notify_all();
+    g->dcv.wait(lk, [&] { return g->pending == 0; });
+    g->job = nullptr;
   }
   for (int i = 0; i < w; i++)
-    if (rc[i] != GCP_OK) {
+    if (g->rcs[i] != GCP_OK) {
       const char* m = gcp_last_error(g->ctx[i]);
       if (g->err.empty()) g->err = "device " + std::to_string(g->devices[i]) + ": " + (m ? m : "error");
-      return rc[i];
+      return g->rcs[i];
     }
   return GCP_OK;
 }
@@ -113,34 +163,33 @@ char* off(void* p, size_t bytes) { return p ? (char*)p + bytes : nullptr; }
 const uint8_t* offb(const uint8_t* p, size_t n) { return p ? p + n : nullptr; }
 uint8_t* offb(uint8_t* p, size_t n) { return p ? p + n : nullptr; }
 
-// Exchange of the partial tallies, in two steps so that a device that fails BEFORE the collective never leaves the
-// others waiting inside it: (a) upload this device's partial (host, n_fields ciphertexts); (b) all-gather on the
-// devices, fold the gathered array on every device, read out/status back from device 0.  Both run with one host
-// thread per device; (b) is entered only when (a) succeeded everywhere.
-int upload_partial(gcp_group* g, int i, const unsigned char* partial, int n_fields) {
-  const size_t pb = (size_t)n_fields * kCtBytes;
-  if (cudaSetDevice(g->devices[i]) != cudaSuccess) return GCP_ERR_CUDA;
-  if (cudaMemcpyAsync(g->d_send[i], partial, pb, cudaMemcpyHostToDevice, g->stream[i]) != cudaSuccess) return GCP_ERR_CUDA;
-  if (cudaStreamSynchronize(g->stream[i]) != cudaSuccess) return GCP_ERR_CUDA;
-  return GCP_OK;
-}
-
+// Exchange of the partial tallies.  Phase 1 (no communication) leaves device i's partial ciphertexts and their statuses in
+// d_send[i], in DEVICE memory (round 1 brought them to the host and back).  Phase 2 is entered only when phase 1
+// succeeded everywhere, so a device that fails before the collective never leaves the others waiting inside it:
+// all-gather of the ciphertext bytes and of the status bytes (ncclAllGather, NVLink), fold of the gathered
+// (devices x n_fields) array on every device, statuses merged on the device, result read back from device 0.
 int gather_and_fold(gcp_group* g, int i, int n_fields, void* out, uint8_t* status, int fmt) {
   const int w = (int)g->ctx.size();
   const size_t pb = (size_t)n_fields * kCtBytes;
   if (cudaSetDevice(g->devices[i]) != cudaSuccess) return GCP_ERR_CUDA;
   cudaStream_t st = g->stream[i];
+  unsigned char* recv_status = g->d_recv[i] + (size_t)w * kSendStatusOff;
   if (w > 1) {
     int nrc = g->nccl.AllGather(g->d_send[i], g->d_recv[i], pb, kNcclUint8, g->comm[i], st);
+    if (nrc == 0) nrc = g->nccl.AllGather(g->d_send[i] + kSendStatusOff, recv_status, (size_t)n_fields, kNcclUint8, g->comm[i], st);
     if (nrc != 0) {
       std::lock_guard<std::mutex> lk(g->err_mu);
       g->err = std::string("ncclAllGather: ") + g->nccl.GetErrorString(nrc);
       return GCP_ERR_CUDA;
     }
   } else {
-    if (cudaMemcpyAsync(g->d_recv[i], g->d_send[i], pb, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return GCP_ERR_CUDA;
+    if (cudaMemcpyAsync(g->d_recv[i], g->d_send[i], pb, cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(recv_status, g->d_send[i] + kSendStatusOff, (size_t)n_fields, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+      return GCP_ERR_CUDA;
   }
   int rc = gcp_elgamal_tally_dev(g->ctx[i], g->d_recv[i], (size_t)w, n_fields, g->d_out[i], g->d_out[i] + pb, fmt, st);
+  if (rc != GCP_OK) return rc;
+  rc = gcp_internal_merge_status_dev(g->ctx[i], recv_status, w, n_fields, g->d_out[i], g->d_out[i] + pb, st);
   if (rc != GCP_OK) return rc;
   if (i == 0) {
     if (cudaMemcpyAsync(out, g->d_out[0], pb, cudaMemcpyDeviceToHost, st) != cudaSuccess) return GCP_ERR_CUDA;
@@ -158,6 +207,12 @@ const char* gcp_group_last_error(const gcp_group* g) { return g ? g->err.c_str()
 
 void gcp_group_destroy(gcp_group* g) {
   if (!g) return;
+  {
+    std::lock_guard<std::mutex> lk(g->wmu);
+    g->stop = true;
+  }
+  g->wcv.notify_all();
+  for (auto& t : g->workers) t.join();
   for (size_t i = 0; i < g->ctx.size(); i++) {
     if (!g->ctx[i]) continue;  // never created: nothing on that device
     cudaSetDevice(g->devices[i]);
@@ -200,6 +255,7 @@ int gcp_group_create(const int* devices, int n_devices, const char* constants_pa
   g->d_recv.assign(n_devices, nullptr);
   g->d_out.assign(n_devices, nullptr);
   g->comm.assign(n_devices, nullptr);
+  g->rcs.assign(n_devices, GCP_OK);
   for (int i = 0; i < n_devices; i++) {
     int rc = gcp_ctx_create(devices[i], constants_path, &g->ctx[i]);
     if (rc != GCP_OK) {
@@ -209,7 +265,8 @@ int gcp_group_create(const int* devices, int n_devices, const char* constants_pa
     }
     const size_t pb = kMaxFields * kCtBytes;
     if (cudaSetDevice(devices[i]) != cudaSuccess || cudaStreamCreateWithFlags(&g->stream[i], cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc(&g->d_send[i], pb) != cudaSuccess || cudaMalloc(&g->d_recv[i], pb * n_devices) != cudaSuccess ||
+        cudaMalloc(&g->d_send[i], pb + kMaxFields) != cudaSuccess ||
+        cudaMalloc(&g->d_recv[i], (pb + kMaxFields) * n_devices) != cudaSuccess ||
         cudaMalloc(&g->d_out[i], pb + kMaxFields) != cudaSuccess) {
       g_group_create_error = std::string("device ") + std::to_string(devices[i]) + ": " + cudaGetErrorString(cudaGetLastError());
       gcp_group_destroy(g);
@@ -231,6 +288,7 @@ int gcp_group_create(const int* devices, int n_devices, const char* constants_pa
       return GCP_ERR_CUDA;
     }
     g->have_nccl = true;
+    for (int i = 0; i < n_devices; i++) g->workers.emplace_back(worker_main, g, i);
   }
   *out = g;
   return GCP_OK;
@@ -319,7 +377,7 @@ int gcp_group_elgamal_encrypt(gcp_group* g, const void* pub_key, int pk_per_item
   });
 }
 
-// shared body of the two tallies: `partial_fn(i, shard, host partial, host status)` folds device i's slice
+// shared body of the tallies: `partial_fn(i, shard, device partial, device status)` folds device i's slice into d_send[i]
 static int group_tally(gcp_group* g, size_t n_ballots, int n_fields, void* out, uint8_t* status, int fmt,
                        const std::function<int(int, Shard, unsigned char*, uint8_t*)>& partial_fn) {
   if (!g) return GCP_ERR_BAD_ARG;
@@ -334,29 +392,19 @@ static int group_tally(gcp_group* g, size_t n_ballots, int n_fields, void* out, 
     return GCP_ERR_BAD_ARG;
   }
   const int w = (int)g->ctx.size();
-  const size_t pb = (size_t)n_fields * kCtBytes;
-  std::vector<unsigned char> partial((size_t)w * pb);
-  std::vector<uint8_t> pstatus((size_t)w * n_fields, 0);
-  // phase 1: every device folds its slice (no communication)
+  // phase 1: every device folds its slice (no communication); the partial stays on the device
   int rc = for_each_device(g, [&](int i) {
-    return partial_fn(i, shard_of(n_ballots, w, i), partial.data() + (size_t)i * pb, pstatus.data() + (size_t)i * n_fields);
+    return partial_fn(i, shard_of(n_ballots, w, i), g->d_send[i], g->d_send[i] + kSendStatusOff);
   });
   if (rc != GCP_OK) return rc;
   // phase 2: all-gather of the partials (bytes) and the final fold on every device
-  rc = for_each_device(g, [&](int i) { return upload_partial(g, i, partial.data() + (size_t)i * pb, n_fields); });
-  if (rc != GCP_OK) return rc;
-  rc = for_each_device(g, [&](int i) { return gather_and_fold(g, i, n_fields, out, status, fmt); });
-  if (rc != GCP_OK) return rc;
-  for (int i = 0; i < w; i++)
-    for (int f = 0; f < n_fields; f++)
-      if (pstatus[(size_t)i * n_fields + f] && !status[f]) status[f] = pstatus[(size_t)i * n_fields + f];
-  return GCP_OK;
+  return for_each_device(g, [&](int i) { return gather_and_fold(g, i, n_fields, out, status, fmt); });
 }
 
 int gcp_group_elgamal_tally(gcp_group* g, const void* ct, size_t n_ballots, int n_fields, void* out, uint8_t* status,
                             int fmt) {
   return group_tally(g, n_ballots, n_fields, out, status, fmt, [&](int i, Shard s, unsigned char* p, uint8_t* ps) {
-    return gcp_elgamal_tally(g->ctx[i], off(ct, s.lo * (size_t)n_fields * kCtBytes), s.hi - s.lo, n_fields, p, ps, fmt);
+    return gcp_internal_tally_to_dev(g->ctx[i], off(ct, s.lo * (size_t)n_fields * kCtBytes), s.hi - s.lo, n_fields, p, ps, fmt);
   });
 }
 
@@ -364,8 +412,8 @@ int gcp_group_elgamal_encrypt_tally(gcp_group* g, const void* pub_key, const voi
                                     int n_fields, void* out, uint8_t* status, int fmt) {
   return group_tally(g, n_ballots, n_fields, out, status, fmt, [&](int i, Shard s, unsigned char* p, uint8_t* ps) {
     const size_t row = (size_t)n_fields * 32;
-    return gcp_elgamal_encrypt_tally(g->ctx[i], pub_key, off(k, s.lo * row), off(m, s.lo * row), s.hi - s.lo, n_fields, p,
-                                     ps, fmt);
+    return gcp_internal_encrypt_tally_to_dev(g->ctx[i], pub_key, off(k, s.lo * row), off(m, s.lo * row), s.hi - s.lo, n_fields,
+                                             p, ps, fmt);
   });
 }
 
@@ -376,10 +424,11 @@ int gcp_group_ballot_batch(gcp_group* g, int n_levels, size_t n_voters, const vo
   const size_t sib_row = (size_t)(n_levels > 0 ? n_levels : 0) * 32;
   return group_tally(g, n_voters, n_fields, out_tally, out_tally_status, fmt, [&](int i, Shard s, unsigned char* p, uint8_t* ps) {
     const size_t row = (size_t)n_fields * 32;
-    return gcp_ballot_batch(g->ctx[i], n_levels, s.hi - s.lo, shared_root ? roots : off(roots, s.lo * 32), shared_root,
-                            off(siblings, s.lo * sib_row), packed, offsets ? offsets + s.lo : nullptr, off(keys, s.lo * 32),
-                            off(values, s.lo * 32), pub_key, off(k, s.lo * row), off(m, s.lo * row), n_fields,
-                            offb(out_flags, s.lo), offb(out_status, s.lo), p, ps, fmt);
+    return gcp_internal_ballot_batch_to_dev(g->ctx[i], n_levels, s.hi - s.lo, shared_root ? roots : off(roots, s.lo * 32),
+                                            shared_root, off(siblings, s.lo * sib_row), packed,
+                                            offsets ? offsets + s.lo : nullptr, off(keys, s.lo * 32), off(values, s.lo * 32),
+                                            pub_key, off(k, s.lo * row), off(m, s.lo * row), n_fields, offb(out_flags, s.lo),
+                                            offb(out_status, s.lo), p, ps, fmt);
   });
 }
 

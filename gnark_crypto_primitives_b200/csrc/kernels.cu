@@ -257,14 +257,40 @@ cudaError_t launch_smt_verify(const SmtArgs& a, const SmtScratch& sc, int sm_cou
   return cudaGetLastError();
 }
 
+// items one resident wave of a kernel covers on the current device (blocks per SM from the occupancy calculator, not a
+// constant: round 1 sized chunks for 5 blocks per SM while the path kernel was resident at 4)
+template <typename K>
+static size_t wave_items(K kernel, int threads, size_t smem, int sm_count, int fallback_blocks) {
+  int blocks = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, threads, smem) != cudaSuccess || blocks < 1) {
+    cudaGetLastError();
+    blocks = fallback_blocks;
+  }
+  return (size_t)sm_count * blocks * threads;
+}
+
+size_t smt_path_wave_items(int sm_count) {
+  cudaFuncSetAttribute(smt_path_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  return wave_items(smt_path_kernel, SMT_WARPS * 32, 0, sm_count, 4);
+}
+
 cudaError_t launch_smt_process(const SmtProcessArgs& a, cudaStream_t stream) {
   if (a.n == 0) return cudaSuccess;
   smt_process_kernel<<<(unsigned)((a.n + 127) / 128), 128, 0, stream>>>(a);
   return cudaGetLastError();
 }
 
+cudaError_t launch_smt_leaf_rows(const u32* keys, const u32* values, int n_values, size_t n, u32* rows, int mont,
+                                 cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  const size_t total = n * (size_t)(n_values + 2);
+  smt_leaf_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(keys, values, n_values, n, rows, mont);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_smt_unpack(const u8* packed, const u64* offsets, u64 base, u64 packed_bytes, size_t n, int n_levels,
-                              u32* siblings, u8* bad, int mont, cudaStream_t stream) {
+                              u32* siblings, u8* bad, int mont, cudaStream_t stream, const u8* drop_is_old0,
+                              const u8* drop_fnc1) {
   if (n == 0) return cudaSuccess;
   SmtUnpackArgs a;
   a.packed = packed;
@@ -276,6 +302,8 @@ cudaError_t launch_smt_unpack(const u8* packed, const u64* offsets, u64 base, u6
   a.siblings = siblings;
   a.bad = bad;
   a.mont = mont;
+  a.drop_is_old0 = drop_fnc1 ? drop_is_old0 : nullptr;
+  a.drop_fnc1 = drop_is_old0 ? drop_fnc1 : nullptr;
   smt_unpack_kernel<<<(unsigned)((n + 3) / 4), 128, 0, stream>>>(a);  // one warp per proof
   return cudaGetLastError();
 }
@@ -386,6 +414,30 @@ cudaError_t launch_encrypt_tally(const u32* tabG, const u32* tabPK, const u32* k
   return cudaGetLastError();
 }
 
+// Final status of a tally, on the device: status[f] = the fold's own status (have_final) else 0, then the first non-zero
+// per-chunk status of the field, then GCP_STATUS_OFF_CURVE for every field when the cached public key failed
+// AssertIsOnCurve (elgamal/encrypt.go:49; pk_flag = nullptr for a plain tally).  A field with a status carries no result:
+// its ciphertext is zeroed.
+__global__ void tally_status_merge_kernel(const u8* __restrict__ part_status, int n_chunks, int n_fields, int have_final,
+                                          const u32* __restrict__ pk_flag, u32* __restrict__ ct, u8* __restrict__ status) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_fields) return;
+  u8 st = have_final ? status[f] : (u8)GCP_STATUS_OK;
+  for (int c = 0; c < n_chunks && st == GCP_STATUS_OK; c++) st = part_status[(size_t)c * n_fields + f];
+  if (pk_flag && *pk_flag == 0) st = GCP_STATUS_OFF_CURVE;
+  status[f] = st;
+  if (st != GCP_STATUS_OK) {
+#pragma unroll
+    for (int l = 0; l < 32; l++) ct[f * 32 + l] = 0;
+  }
+}
+
+cudaError_t launch_tally_status_merge(const u8* part_status, int n_chunks, int n_fields, int have_final, const u32* pk_flag,
+                                      u32* ct, u8* status, cudaStream_t stream) {
+  tally_status_merge_kernel<<<1, 64, 0, stream>>>(part_status, n_chunks, n_fields, have_final, pk_flag, ct, status);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_keccak_address(const u8* in, size_t n, u8* out, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
   keccak_address_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(in, n, out);
@@ -411,6 +463,11 @@ static cudaError_t launch_varbase_window(const u32* bases, const u32* s0, const 
   cudaFuncSetAttribute(varbase_window_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   varbase_window_kernel<<<blocks_for(n, VB_THREADS), VB_THREADS, smem, stream>>>(a);
   return cudaGetLastError();
+}
+
+size_t varbase_wave_items(int sm_count) {
+  cudaFuncSetAttribute(varbase_window_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  return wave_items(varbase_window_kernel, VB_THREADS, (size_t)VB_SLOTS * 2 * VB_THREADS * sizeof(uint4), sm_count, 4);
 }
 
 // words of scratch per item: kind 0 Encrypt with per-item keys, 1 AssertDecrypt, 2 DecryptionProof.Verify, 3 EdDSA

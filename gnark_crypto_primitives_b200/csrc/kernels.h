@@ -50,6 +50,7 @@ struct SmtArgs {
   u8* status;            // n
   u32* out_roots;        // n x 8 or nullptr: recomputed level[0], canonical
   int mont;              // element format: 0 canonical integers, 1 gnark-crypto Montgomery memory
+  int leaf_hash_form;    // VerifierWithLeafHash[Flag] (verifier.go:129-183): `values` / `old_values` hold hash1New / hash1Old
 };
 
 struct SmtProcessArgs {
@@ -67,6 +68,7 @@ struct SmtProcessArgs {
   u32* new_roots;         // n x 8
   u8* status;             // n
   int mont;
+  int leaf_hash_form;     // ProcessorWithLeafHash (processor.go:16): `new_values` / `old_values` hold hash1New / hash1Old
 };
 
 cudaError_t launch_to_mont(u32* d_elems, size_t n, cudaStream_t stream);
@@ -88,9 +90,18 @@ cudaError_t launch_smt_verify(const SmtArgs& a, const SmtScratch& sc, int sm_cou
 cudaError_t launch_smt_scan(const u32* siblings, size_t n, int n_levels, u16* lidx, u8* info, u32* hist, int sm_count,
                             cudaStream_t stream);
 cudaError_t launch_smt_process(const SmtProcessArgs& a, cudaStream_t stream);
+// Hash1 rows (tree/smt/hash.go:10-19): rows[i] = (key_i, values_i[0..n_values), 1), n x (n_values + 2) elements, in the
+// caller's element format; the hash itself is launch_poseidon with arity n_values + 2
+cudaError_t launch_smt_leaf_rows(const u32* keys, const u32* values, int n_values, size_t n, u32* rows, int mont,
+                                 cudaStream_t stream);
+// items covered by one resident wave of smt_path_kernel / varbase_window_kernel on the current device
+size_t smt_path_wave_items(int sm_count);
+size_t varbase_wave_items(int sm_count);
 // arbo packed siblings (absolute offsets into a blob whose byte `base` is packed[0]) -> dense rows + bad[n]
+// drop_is_old0 / drop_fnc1 (both or neither): arbo's post-insert rule, the last unpacked sibling is dropped where both are 0
 cudaError_t launch_smt_unpack(const u8* packed, const u64* offsets, u64 base, u64 packed_bytes, size_t n, int n_levels,
-                              u32* siblings, u8* bad, int mont, cudaStream_t stream);
+                              u32* siblings, u8* bad, int mont, cudaStream_t stream, const u8* drop_is_old0 = nullptr,
+                              const u8* drop_fnc1 = nullptr);
 cudaError_t launch_smt_apply_bad(const u8* bad, size_t n, u8* flags, u8* status, u32* out_roots, cudaStream_t stream);
 
 // ElGamal (elgamal.cuh)
@@ -121,6 +132,8 @@ cudaError_t launch_ct_select(const u8* sel, const u32* i1, const u32* i2, size_t
 cudaError_t launch_encrypt_tally(const u32* tabG, const u32* tabPK, const u32* ks, const u32* ms, const u8* mask,
                                  size_t n_ballots, int n_fields, int n_blocks, u32* partials, u32* bad_count, u32* out_xyz, u8* status, int mont,
                                  cudaStream_t stream);
+cudaError_t launch_tally_status_merge(const u8* part_status, int n_chunks, int n_fields, int have_final, const u32* pk_flag,
+                                      u32* ct, u8* status, cudaStream_t stream);
 cudaError_t launch_keccak_address(const u8* in, size_t n, u8* out, cudaStream_t stream);
 cudaError_t launch_assert_decrypt(const u32* tabG, const u32* cts, const u32* privs, const u32* msgs, size_t n, u8* flags,
                                   u8* status, int mont, u32* scratch, int* n_launches, cudaStream_t stream);

@@ -105,7 +105,11 @@ __global__ void __launch_bounds__(128) smt_leaf_kernel(SmtArgs a) {
           val[l] = oval[l];
         }
       }
-      poseidon_hash3(leaf, key, val, one);  // Hash1: H(key, value, 1)
+      if (a.leaf_hash_form) {
+        fr_copy(leaf, val);                   // the caller's hash1New / hash1Old (lazy Montgomery after load_elem)
+      } else {
+        poseidon_hash3(leaf, key, val, one);  // Hash1: H(key, value, 1)
+      }
     }
   }
   store_fr(a.leaf + idx * 8, leaf);
@@ -467,12 +471,16 @@ __global__ void __launch_bounds__(128) smt_process_kernel(SmtProcessArgs a) {
     if (!enabled) {
       load_fr(out, a.old_roots + idx * 8);  // nop: newRoot = oldRoot
     } else {
-      // leaf hashes (one inlined copy of the t = 4 permutation)
+      // leaf hashes (one inlined copy of the t = 4 permutation), or the caller's (ProcessorWithLeafHash)
       u32 h1old[8], h1new[8], one[8];
 #pragma unroll
       for (int l = 0; l < 8; l++) one[l] = FR_ONE[l];
+      if (a.leaf_hash_form) {
+        fr_copy(h1old, oval);
+        fr_copy(h1new, nval);
+      }
 #pragma unroll 1
-      for (int h = 0; h < 2; h++) {
+      for (int h = 0; h < 2 && !a.leaf_hash_form; h++) {
         u32 kk[8], vv[8], res[8];
 #pragma unroll
         for (int l = 0; l < 8; l++) {
@@ -570,6 +578,26 @@ __global__ void __launch_bounds__(128) smt_process_kernel(SmtProcessArgs a) {
   a.status[idx] = st;
 }
 
+// Hash1 input rows (tree/smt/hash.go:10-19): (key, values..., 1), one thread per element
+__global__ void smt_leaf_rows_kernel(const u32* __restrict__ keys, const u32* __restrict__ values, int n_values, size_t n,
+                                     u32* __restrict__ rows, int mont) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int arity = n_values + 2;
+  if (idx >= n * (size_t)arity) return;
+  const size_t item = idx / arity;
+  const int j = (int)(idx - item * arity);
+  u32 v[8];
+  if (j == 0) {
+    load_fr(v, keys + item * 8);
+  } else if (j <= n_values) {
+    load_fr(v, values + (item * (size_t)n_values + (j - 1)) * 8);
+  } else {
+#pragma unroll
+    for (int l = 0; l < 8; l++) v[l] = mont ? FR_ONE[l] : (l == 0 ? 1u : 0u);
+  }
+  store_fr(rows + idx * 8, v);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // arbo packed siblings -> Assignment.Siblings rows
 // ---------------------------------------------------------------------------------------------------
@@ -592,6 +620,10 @@ struct SmtUnpackArgs {
   u32* siblings;       // n x n_levels x 8
   u8* bad;             // n
   int mont;
+  // arbo's post-insert flow (wrapper_arbo.go:170-172): when both are given, the LAST unpacked sibling of proof i is dropped
+  // where is_old0[i] == 0 && fnc1[i] == 0 (GenProof ran after the add: that sibling is the displaced old leaf)
+  const u8* drop_is_old0;
+  const u8* drop_fnc1;
 };
 
 __device__ __forceinline__ void load_unaligned32(u32 (&r)[8], const u8* p) {
@@ -634,9 +666,22 @@ __global__ void __launch_bounds__(128) smt_unpack_kernel(SmtUnpackArgs a) {
     for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     bad = cnt > avail;
   }
+  // index of the last unpacked sibling (the highest set bit of the bitmap) where the post-insert rule drops it
+  int drop = -1;
+  if (!bad && a.drop_is_old0 && a.drop_is_old0[proof] == 0 && a.drop_fnc1[proof] == 0) {
+    int top = -1;
+    for (u32 j = lane; j < L; j += 32)
+      if (bitmap[j]) top = (int)j;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) top = max(top, __shfl_xor_sync(0xffffffffu, top, o));
+    if (top < 0)
+      bad = true;  // nothing to drop: the reference's slice expression panics on an empty sibling list
+    else
+      drop = top * 8 + (31 - __clz((u32)bitmap[top]));
+  }
   for (int i = lane; i < a.n_levels; i += 32) {
     u32 v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (!bad && (u32)i < 8 * L && ((bitmap[i >> 3] >> (i & 7)) & 1)) {
+    if (!bad && i != drop && (u32)i < 8 * L && ((bitmap[i >> 3] >> (i & 7)) & 1)) {
       u32 rank = __popc((u32)bitmap[i >> 3] & ((1u << (i & 7)) - 1));
       for (int j = 0; j < (i >> 3); j++) rank += __popc((u32)bitmap[j]);
       if (rank < avail) {

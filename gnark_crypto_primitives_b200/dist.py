@@ -51,11 +51,16 @@ def sharded_tally(local_ct: torch.Tensor, n_fields: int,
 
 
 def engine_tally_fn(engine, stream=None):
-    """tally_fn backed by Engine.elgamal_tally_dev on CUDA tensors (raises if a field reports a status)."""
+    """tally_fn backed by Engine.elgamal_tally_dev on CUDA tensors.  Raises if a field reports a status (one 8-byte
+    read-back per call): a shard with a non-canonical ciphertext would otherwise put zeroed partials into the all-gather
+    and every rank would fold them into a wrong global tally without noticing."""
     def fn(ct, n_ballots, n_fields):
         out = torch.empty((n_fields, 4, 32), dtype=torch.uint8, device=ct.device)
         status = torch.empty(n_fields, dtype=torch.uint8, device=ct.device)
         engine.elgamal_tally_dev(ct.contiguous(), n_ballots, n_fields, out, status,
                                  stream=stream if stream is not None else torch.cuda.current_stream())
+        bad = status.cpu()
+        if bool(bad.any()):
+            raise RuntimeError(f"tally status per field: {bad.tolist()} (1 = non-canonical ciphertext, 5 = zero denominator)")
         return out
     return fn

@@ -207,8 +207,43 @@ class Engine:
                                                          _dptr(d_status), fmt, self._stream(stream)))
 
     # -- SMT ----------------------------------------------------------------------------------------
+    def smt_leaf_hash(self, keys, values, fmt=FMT_CANONICAL):
+        """smt.Hash1 (tree/smt/hash.go:10-19): Poseidon(key, values..., 1).  keys: (n, 32); values: (n, n_values, 32) with
+        n_values in 0..14 ((n, 32) is one value per leaf).  Returns (hashes (n, 32), status)."""
+        k = _as_elems(keys, name="keys").reshape(-1, 32)
+        n = k.shape[0]
+        v = np.ascontiguousarray(np.asarray(values, dtype=np.uint8))
+        if v.ndim == 2 and v.shape == (n, 32):
+            v = v.reshape(n, 1, 32)
+        if v.ndim != 3 or v.shape[0] != n or v.shape[2] != 32:
+            raise ValueError("values must have shape (n, n_values, 32)")
+        n_values = v.shape[1]
+        out = np.empty((n, 32), dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.gcp_smt_leaf_hash(self._h, _ptr(k), _ptr(v) if n_values else None, n_values, n, _ptr(out),
+                                                _ptr(status), fmt))
+        return out, status
+
+    def smt_leaf_hash_dev(self, d_keys, d_values, n_values, n, d_out, d_status, fmt=FMT_CANONICAL, stream=None):
+        self._check(self._lib.gcp_smt_leaf_hash_dev(self._h, _dptr(d_keys), _dptr(d_values), int(n_values), int(n),
+                                                    _dptr(d_out), _dptr(d_status), fmt, self._stream(stream)))
+
+    def smt_verify_with_leaf_hash(self, roots, siblings, keys, hash1_new, old_keys=None, hash1_old=None, is_old0=None,
+                                  fnc=None, enabled=None, want_roots=False, fmt=FMT_CANONICAL):
+        """smt.VerifierWithLeafHashFlag (tree/smt/verifier.go:171-242) with the caller's leaf hashes."""
+        return self.smt_verify(roots, siblings, keys, hash1_new, old_keys, hash1_old, is_old0, fnc, enabled, want_roots,
+                               fmt, _fn=self._lib.gcp_smt_verify_with_leaf_hash)
+
+    def smt_verify_with_leaf_hash_dev(self, n_levels, n, d_roots, shared_root, d_siblings, d_keys, d_hash1_new, d_flags,
+                                      d_status, d_old_keys=None, d_hash1_old=None, d_is_old0=None, d_fnc=None,
+                                      d_enabled=None, d_out_roots=None, fmt=FMT_CANONICAL, stream=None):
+        self._check(self._lib.gcp_smt_verify_with_leaf_hash_dev(
+            self._h, n_levels, n, _dptr(d_roots), int(bool(shared_root)), _dptr(d_siblings), _dptr(d_old_keys),
+            _dptr(d_hash1_old), _dptr(d_is_old0), _dptr(d_keys), _dptr(d_hash1_new), _dptr(d_fnc), _dptr(d_enabled),
+            _dptr(d_flags), _dptr(d_status), _dptr(d_out_roots), fmt, self._stream(stream)))
+
     def smt_verify(self, roots, siblings, keys, values, old_keys=None, old_values=None, is_old0=None, fnc=None,
-                   enabled=None, want_roots=False, fmt=FMT_CANONICAL):
+                   enabled=None, want_roots=False, fmt=FMT_CANONICAL, _fn=None):
         """smt.Verifier (tree/smt/verifier.go:102-121) over a batch.
 
         siblings: (n, n_levels, 32); roots: (n, 32) or (32,)/(1, 32) for one shared root; keys/values: (n, 32).
@@ -232,9 +267,9 @@ class Engine:
         flags = np.empty(n, dtype=np.uint8)
         status = np.empty(n, dtype=np.uint8)
         oroots = np.empty((n, 32), dtype=np.uint8) if want_roots else None
-        self._check(self._lib.gcp_smt_verify(self._h, n_levels, n, _ptr(r), shared, _ptr(sib), _ptr(ok), _ptr(ov),
-                                             _ptr(i0), _ptr(k), _ptr(v), _ptr(fn), _ptr(en), _ptr(flags), _ptr(status),
-                                             _ptr(oroots), fmt))
+        call = _fn or self._lib.gcp_smt_verify
+        self._check(call(self._h, n_levels, n, _ptr(r), shared, _ptr(sib), _ptr(ok), _ptr(ov), _ptr(i0), _ptr(k), _ptr(v),
+                         _ptr(fn), _ptr(en), _ptr(flags), _ptr(status), _ptr(oroots), fmt))
         return (flags, status, oroots) if want_roots else (flags, status)
 
     def smt_verify_packed(self, roots, packed, n_levels, keys, values, offsets=None, old_keys=None, old_values=None,
@@ -496,8 +531,14 @@ class Engine:
                                                    _dptr(d_tally), _dptr(d_tally_status), fmt, self._stream(stream)))
 
     # -- SMT processor ------------------------------------------------------------------------------
+    def smt_process_with_leaf_hash(self, old_roots, siblings, old_keys, hash1_old, is_old0, new_keys, hash1_new, fnc0,
+                                   fnc1, fmt=FMT_CANONICAL):
+        """smt.ProcessorWithLeafHash (tree/smt/processor.go:16-72) -> (new_roots (n, 32), status (n,))."""
+        return self.smt_process(old_roots, siblings, old_keys, hash1_old, is_old0, new_keys, hash1_new, fnc0, fnc1, fmt,
+                                _fn=self._lib.gcp_smt_process_with_leaf_hash)
+
     def smt_process(self, old_roots, siblings, old_keys, old_values, is_old0, new_keys, new_values, fnc0, fnc1,
-                    fmt=FMT_CANONICAL):
+                    fmt=FMT_CANONICAL, _fn=None):
         """smt.Processor (tree/smt/processor.go:10-72) over a batch -> (new_roots (n, 32), status (n,))."""
         sib = _as_elems(siblings, name="siblings")
         if sib.ndim != 3:
@@ -509,14 +550,23 @@ class Engine:
         i0, f0, f1 = _u8(is_old0, n, "is_old0"), _u8(fnc0, n, "fnc0"), _u8(fnc1, n, "fnc1")
         out = np.empty((n, 32), dtype=np.uint8)
         status = np.empty(n, dtype=np.uint8)
-        self._check(self._lib.gcp_smt_process(self._h, n_levels, n, _ptr(args[0]), _ptr(sib), _ptr(args[1]),
-                                              _ptr(args[2]), _ptr(i0), _ptr(args[3]), _ptr(args[4]), _ptr(f0), _ptr(f1),
-                                              _ptr(out), _ptr(status), fmt))
+        call = _fn or self._lib.gcp_smt_process
+        self._check(call(self._h, n_levels, n, _ptr(args[0]), _ptr(sib), _ptr(args[1]), _ptr(args[2]), _ptr(i0),
+                         _ptr(args[3]), _ptr(args[4]), _ptr(f0), _ptr(f1), _ptr(out), _ptr(status), fmt))
         return out, status
 
+    def smt_process_arbo(self, old_roots, packed, n_levels, old_keys, old_values, is_old0, new_keys, new_values,
+                         fnc0, fnc1, fmt=FMT_CANONICAL):
+        """smt.Processor fed the way the reference's addOrUpdate builds its Assignment (wrapper_arbo.go:152-172):
+        `packed` are GenProof strings taken AFTER the change; the last unpacked sibling is dropped where
+        is_old0 == 0 and fnc1 == 0.  -> (new_roots (n, 32), status (n,))."""
+        return self.smt_process_packed(old_roots, packed, n_levels, old_keys, old_values, is_old0, new_keys, new_values,
+                                       fnc0, fnc1, fmt, _fn=self._lib.gcp_smt_process_arbo)
+
     def smt_process_packed(self, old_roots, packed, n_levels, old_keys, old_values, is_old0, new_keys, new_values,
-                           fnc0, fnc1, fmt=FMT_CANONICAL):
-        """smt.Processor over arbo packed proofs (list of byte strings) -> (new_roots (n, 32), status (n,))."""
+                           fnc0, fnc1, fmt=FMT_CANONICAL, _fn=None):
+        """smt.Processor over arbo packed proofs (list of byte strings, siblings used as they are: proofs taken BEFORE
+        the change) -> (new_roots (n, 32), status (n,))."""
         n = len(packed)
         lens = np.fromiter((len(b) for b in packed), dtype=np.uint64, count=n)
         offs = np.zeros(n + 1, dtype=np.uint64)
@@ -528,9 +578,9 @@ class Engine:
         i0, f0, f1 = _u8(is_old0, n, "is_old0"), _u8(fnc0, n, "fnc0"), _u8(fnc1, n, "fnc1")
         out = np.empty((n, 32), dtype=np.uint8)
         status = np.empty(n, dtype=np.uint8)
-        self._check(self._lib.gcp_smt_process_packed(self._h, int(n_levels), n, _ptr(args[0]), _ptr(blob), _ptr(offs),
-                                                     _ptr(args[1]), _ptr(args[2]), _ptr(i0), _ptr(args[3]), _ptr(args[4]),
-                                                     _ptr(f0), _ptr(f1), _ptr(out), _ptr(status), fmt))
+        fn = _fn or self._lib.gcp_smt_process_packed
+        self._check(fn(self._h, int(n_levels), n, _ptr(args[0]), _ptr(blob), _ptr(offs), _ptr(args[1]), _ptr(args[2]),
+                       _ptr(i0), _ptr(args[3]), _ptr(args[4]), _ptr(f0), _ptr(f1), _ptr(out), _ptr(status), fmt))
         return out, status
 
     # -- decryption checks, coordinate conversion ----------------------------------------------------

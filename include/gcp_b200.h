@@ -71,6 +71,9 @@ int gcp_ctx_device(const gcp_ctx* ctx);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 uint64_t gcp_ctx_launch_count(const gcp_ctx* ctx);
 
+/* Host threads of the process-wide staging pool (csrc/hostcopy.h): min(16, hardware threads / 2), shared by every context
+ * of the process; 0 before the first context exists.  GCP_B200_COPY_THREADS overrides it at first use. */
+int gcp_copy_threads(void);
 /* Page-locked host memory for the caller's flat arrays (cudaHostAlloc, portable across the devices of a group).
  * The host-buffer entry points accept any host pointer; from pinned memory their chunked copies run at full PCIe
  * rate and overlap the kernels (bench.py's e2e figure); from pageable memory (a Go heap slice) copies of 64 MB and more
@@ -137,6 +140,27 @@ int gcp_smt_verify_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_roots
                        const uint8_t* d_is_old0, const void* d_keys, const void* d_values, const uint8_t* d_fnc,
                        const uint8_t* d_enabled, uint8_t* d_out_flags, uint8_t* d_out_status, void* d_out_roots,
                        int fmt, void* stream);
+/* smt.VerifierWithLeafHash / VerifierWithLeafHashFlag (verifier.go:129-183): the caller supplies the leaf hashes, so a
+ * tree whose leaves carry several values (Hash1(key, values..., 1), tree/smt/hash.go:10-19) goes through the same path.
+ * Arguments as gcp_smt_verify with hash1_old / hash1_new (n elements each) in the place of old_values / values;
+ * old_keys and hash1_old are both given or both NULL (NULL,NULL: the old leaf is the new leaf).  The flag is the
+ * gadget's; VerifierWithLeafHash itself asserts it (the caller's AssertIsEqual(valid, 1)). */
+int gcp_smt_verify_with_leaf_hash(gcp_ctx* ctx, int n_levels, size_t n, const void* roots, int shared_root,
+                                  const void* siblings, const void* old_keys, const void* hash1_old, const uint8_t* is_old0,
+                                  const void* keys, const void* hash1_new, const uint8_t* fnc, const uint8_t* enabled,
+                                  uint8_t* out_flags, uint8_t* out_status, void* out_roots, int fmt);
+int gcp_smt_verify_with_leaf_hash_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_roots, int shared_root,
+                                      const void* d_siblings, const void* d_old_keys, const void* d_hash1_old,
+                                      const uint8_t* d_is_old0, const void* d_keys, const void* d_hash1_new,
+                                      const uint8_t* d_fnc, const uint8_t* d_enabled, uint8_t* d_out_flags,
+                                      uint8_t* d_out_status, void* d_out_roots, int fmt, void* stream);
+/* smt.Hash1 (tree/smt/hash.go:10-19): out[i] = Poseidon(keys[i], values[i][0 .. n_values), 1), the leaf hash of a leaf
+ * with n_values values (0 .. 14: the hasher takes at most 16 inputs, "bad inputs provided" beyond).  values: n x n_values
+ * elements (may be NULL when n_values == 0).  n_values = 1 is the leaf of smt.Verifier / smt.Processor. */
+int gcp_smt_leaf_hash(gcp_ctx* ctx, const void* keys, const void* values, int n_values, size_t n, void* out, uint8_t* status,
+                      int fmt);
+int gcp_smt_leaf_hash_dev(gcp_ctx* ctx, const void* d_keys, const void* d_values, int n_values, size_t n, void* d_out,
+                          uint8_t* d_status, int fmt, void* stream);
 /* The proof-streaming pass of the verifier on its own (LevInsFlag's inputs, lev_ins.go:43-77): per proof
  * lidx = 1 + index of the last non-zero sibling among [0, n-2] (0 if none) and info (bit 0: siblings[n-1] == 0,
  * bit 1: every sibling < r).  HBM-bound: reads n * n_levels * 32 bytes once with coalesced 128-bit loads. */
@@ -181,7 +205,21 @@ int gcp_smt_process(gcp_ctx* ctx, int n_levels, size_t n, const void* old_roots,
                     const void* new_values, const uint8_t* fnc0, const uint8_t* fnc1, void* new_roots, uint8_t* status,
                     int fmt);
 /* The same with arbo packed proofs (wrapper_arbo.go:166-179 unpacks them on the CPU): see gcp_smt_verify_packed for
- * the wire format; a string arbo.UnpackSiblings would reject gets status GCP_STATUS_MALFORMED and new_root = 0. */
+ * the wire format; a string arbo.UnpackSiblings would reject gets status GCP_STATUS_MALFORMED and new_root = 0.
+ * Two forms, which differ in WHEN the proof was generated:
+ *   gcp_smt_process_packed  the unpacked siblings are used as they are: proofs taken BEFORE the change (GenProof on
+ *                           the old tree), or any caller that has already applied arbo's post-insert rule;
+ *   gcp_smt_process_arbo    the reference's own flow, addOrUpdate (wrapper_arbo.go:152-172): GenProof runs AFTER the
+ *                           add, so for an insert beside an existing leaf the last unpacked sibling is the displaced
+ *                           old leaf and is dropped: where is_old0[i] == 0 and fnc1[i] == 0 the last sibling of the
+ *                           string is left out (a string with no sibling to drop gets GCP_STATUS_MALFORMED: the
+ *                           reference's slice expression panics there).  Feeding post-insert strings to
+ *                           gcp_smt_process_packed puts the insertion level one too deep and every such insert
+ *                           fails its old-root assertion (status 6). */
+int gcp_smt_process_arbo(gcp_ctx* ctx, int n_levels, size_t n, const void* old_roots, const uint8_t* packed,
+                         const uint64_t* offsets, const void* old_keys, const void* old_values, const uint8_t* is_old0,
+                         const void* new_keys, const void* new_values, const uint8_t* fnc0, const uint8_t* fnc1,
+                         void* new_roots, uint8_t* status, int fmt);
 int gcp_smt_process_packed(gcp_ctx* ctx, int n_levels, size_t n, const void* old_roots, const uint8_t* packed,
                            const uint64_t* offsets, const void* old_keys, const void* old_values, const uint8_t* is_old0,
                            const void* new_keys, const void* new_values, const uint8_t* fnc0, const uint8_t* fnc1,
@@ -190,6 +228,15 @@ int gcp_smt_process_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_old_
                         const void* d_old_keys, const void* d_old_values, const uint8_t* d_is_old0,
                         const void* d_new_keys, const void* d_new_values, const uint8_t* d_fnc0, const uint8_t* d_fnc1,
                         void* d_new_roots, uint8_t* d_status, int fmt, void* stream);
+/* smt.ProcessorWithLeafHash (processor.go:16-72): hash1_old / hash1_new in the place of old_values / new_values. */
+int gcp_smt_process_with_leaf_hash(gcp_ctx* ctx, int n_levels, size_t n, const void* old_roots, const void* siblings,
+                                   const void* old_keys, const void* hash1_old, const uint8_t* is_old0,
+                                   const void* new_keys, const void* hash1_new, const uint8_t* fnc0, const uint8_t* fnc1,
+                                   void* new_roots, uint8_t* status, int fmt);
+int gcp_smt_process_with_leaf_hash_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_old_roots, const void* d_siblings,
+                                       const void* d_old_keys, const void* d_hash1_old, const uint8_t* d_is_old0,
+                                       const void* d_new_keys, const void* d_hash1_new, const uint8_t* d_fnc0,
+                                       const uint8_t* d_fnc1, void* d_new_roots, uint8_t* d_status, int fmt, void* stream);
 
 /* ---- ElGamal over the a = -1 BN254 twisted Edwards curve: elgamal/ ------------------------------------ */
 /* FixedBaseScalarMulBN254 (elgamal/mul.go:76-166): out[i] = [scalars[i]] G, scalars are Fr elements used as

@@ -29,9 +29,9 @@ STATUS_KEY_RANGE = 2
 STATUS_NOT_BOOLEAN = 3
 
 
-def hash1(key, value):
-    """hash.go:10-19 with a single value: H(key, value, 1)."""
-    return poseidon.hash([key, value, 1])
+def hash1(key, *values):
+    """hash.go:10-19: H(key, values..., 1); one value per leaf in smt.Verifier / smt.Processor."""
+    return poseidon.hash([key, *values, 1])
 
 
 def hash2(l, r):
@@ -173,8 +173,8 @@ class Tree:
         got = self._hash_cache.get(hid)
         if got is not None and got[0] is node:
             return got[1]
-        if node[0] == "leaf":
-            h = hash1(node[1], node[2])
+        if node[0] == "leaf":                                  # a tuple value is a multi-value leaf: Hash1(key, values...)
+            h = hash1(node[1], *node[2]) if isinstance(node[2], tuple) else hash1(node[1], node[2])
         else:
             h = hash2(self._h(node[1]), self._h(node[2]))
         self._hash_cache[hid] = (node, h)
@@ -291,6 +291,33 @@ def assignment_siblings(packed, levels):
     return [un[i] if i < len(un) else 0 for i in range(levels)], STATUS_OK
 
 
+def arbo_add_or_update(tree, key, value):
+    """WrapperArbo.SetWithTx / addOrUpdate (tree/smt/wrapper_arbo.go:97-185) on the oracle's Tree: the Assignment the
+    reference's callers feed to smt.Processor, with its siblings taken from a proof generated AFTER the change.
+    -> dict(old_root, new_root, old_key, old_value, is_old0, new_key, new_value, fnc0, fnc1, siblings, packed, status)
+    `packed` is GenProof's siblingsPacked (post-insert); `siblings` what :166-179 make of it."""
+    old_root = tree.root()                                            # :125-129
+    found = tree.gen_proof(key)                                       # GetWithTx :135: the leaf on the key's path, if any
+    fnc0, fnc1 = (0, 1) if found["exists"] else (1, 0)                # update :113-117 / add :107-111
+    tree.add(key, value)
+    is_old0 = 1 if found["is_old0"] else 0                            # :146-150 (len(oldKeyBytes) > 0)
+    new_root = tree.root()                                            # :152-156
+    tree.gen_proof(key)                                               # :158
+    packed = tree.last_packed
+    un = unpack_siblings(packed)                                      # :166
+    status = STATUS_OK
+    if un is None:
+        un, status = [], STATUS_MALFORMED
+    elif is_old0 == 0 and fnc1 == 0:                                  # :170-172
+        if not un:
+            status = STATUS_MALFORMED                                 # the Go slice expression [0:-1] panics
+        un = un[:-1]
+    sib = [un[i] if i < len(un) else 0 for i in range(tree.max_levels)]   # :174-181
+    return dict(old_root=old_root, new_root=new_root, old_key=found["old_key"], old_value=found["old_value"],
+                is_old0=is_old0, new_key=key, new_value=value, fnc0=fnc0, fnc1=fnc1, siblings=sib, packed=packed,
+                status=status)
+
+
 # --------------------------------------------------------------------------------------
 # Processor (state transition: insert / update / delete / nop)
 # --------------------------------------------------------------------------------------
@@ -324,17 +351,24 @@ def processor_level(st_top, st_old0, st_bot, st_new1, st_upd, sibling, old1leaf,
 
 
 def processor(old_root, siblings, old_key, old_value, is_old0, new_key, new_value, fnc0, fnc1):
-    """processor.go:10-72 -> (new_root, status).  fnc = (1,0) insert, (0,1) update, (1,1) delete, (0,0) nop."""
+    """processor.go:10-14 -> (new_root, status).  fnc = (1,0) insert, (0,1) update, (1,1) delete, (0,0) nop."""
+    for v in (old_key, old_value, new_key, new_value):
+        if not (0 <= int(v) < R):
+            return 0, STATUS_NONCANONICAL
+    return processor_with_leaf_hash(old_root, siblings, old_key, hash1(old_key, old_value), is_old0, new_key,
+                                    hash1(new_key, new_value), fnc0, fnc1)
+
+
+def processor_with_leaf_hash(old_root, siblings, old_key, hash1_old, is_old0, new_key, hash1_new, fnc0, fnc1):
+    """processor.go:16-72 -> (new_root, status)."""
     n = len(siblings)
-    vals = [old_root, old_key, old_value, new_key, new_value] + list(siblings)
+    vals = [old_root, old_key, hash1_old, new_key, hash1_new] + list(siblings)
     if any(not (0 <= int(v) < R) for v in vals):
         return 0, STATUS_NONCANONICAL
     if any(b not in (0, 1) for b in (is_old0, fnc0, fnc1)):
         return 0, STATUS_NOT_BOOLEAN                                   # AssertIsBoolean / api.Select / api.And
     if (old_key >> n) or (new_key >> n):
         return 0, STATUS_KEY_RANGE                                     # lowBits, processor.go:23-24
-    hash1_old = hash1(old_key, old_value)
-    hash1_new = hash1(new_key, new_value)
     enabled = (fnc0 + fnc1 - fnc0 * fnc1) % R
     valid, lev_ins = lev_ins_flag(enabled, siblings)                   # LevIns asserts valid == 1 (lev_ins.go:16-20)
     if valid != 1:

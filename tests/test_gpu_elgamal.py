@@ -201,7 +201,42 @@ def test_fused_encrypt_tally(engine):
             assert (tal == out).all()
     # off-curve key: every field flagged
     out, st = engine.elgamal_encrypt_tally(elems((1, 2)), elems([1, 2]).reshape(1, 2, 32), elems([3, 4]).reshape(1, 2, 32))
-    assert [int(s) for s in st] == [4, 4]
+    assert [int(s) for s in st] == [4, 4] and not out.any()
+
+
+def test_device_forms_report_an_off_curve_key(engine):
+    """AssertIsOnCurve(pubKey) (encrypt.go:49) on the device-resident forms: gcp_elgamal_encrypt_tally_dev and
+    gcp_ballot_batch_dev must give status 4 and no result, not the tally under a table built from the identity."""
+    import torch
+
+    from tests.util import dense_proof
+
+    rng = random.Random(49)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    nb, nf = 5, 3
+    k = dev(elems(rng.randrange(R) for _ in range(nb * nf)))
+    m = dev(elems(rng.randrange(1 << 16) for _ in range(nb * nf)))
+    out = torch.full((nf, 4, 32), 7, dtype=torch.uint8, device="cuda")
+    st = torch.full((nf,), 9, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+    for bad_pk in ((1, 2), (R, 1)):                                          # off the curve / not a field element
+        engine.elgamal_encrypt_tally_dev(dev(elems(bad_pk)), k, m, nb, nf, out, st, stream=stream)
+        torch.cuda.synchronize()
+        assert st.tolist() == [4] * nf and not bool(out.any())
+    engine.elgamal_encrypt_tally_dev(dev(elems(PK)), k, m, nb, nf, out, st, stream=stream)
+    torch.cuda.synchronize()
+    assert st.tolist() == [0] * nf and bool(out.any())
+    # ballot batch
+    n_levels = 24
+    items = [dense_proof(rng, n_levels) for _ in range(nb)]
+    d = dict(roots=dev(elems(it[0] for it in items)), sib=dev(elems([s for it in items for s in it[1]])),
+             keys=dev(elems(it[2] for it in items)), vals=dev(elems(it[3] for it in items)))
+    flags = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    pst = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    engine.ballot_batch_dev(n_levels, nb, d["roots"], False, d["sib"], d["keys"], d["vals"], dev(elems((1, 2))), k, m, nf,
+                            flags, pst, out, st, stream=stream)
+    torch.cuda.synchronize()
+    assert flags.tolist() == [1] * nb and st.tolist() == [4] * nf and not bool(out.any())
 
 
 def test_field_edge_patterns_through_curve_arithmetic(engine):

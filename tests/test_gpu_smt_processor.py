@@ -133,6 +133,42 @@ def test_packed_proofs_give_the_dense_results(engine):
     assert all(s == 0 for s in got_status[:n - 1])
 
 
+def test_arbo_post_insert_proofs(engine):
+    """gcp_smt_process_arbo: the reference's own flow (WrapperArbo.addOrUpdate, wrapper_arbo.go:119-185) generates the
+    proof AFTER the add and drops the last unpacked sibling when isOld0 == 0 and fnc1 == 0.  The transitions must solve
+    (status 0) and give the tree's new root; the same strings through gcp_smt_process_packed (siblings as they are) fail
+    the old-root assertion for every insert beside an existing leaf."""
+    rng = random.Random(170)
+    n_levels = 48
+    tree = osmt.Tree(n_levels)
+    keys = [rng.getrandbits(n_levels) for _ in range(36)]
+    keys += [keys[3], keys[17], keys[17]]                            # updates of existing keys
+    asg = [osmt.arbo_add_or_update(tree, k, rng.randrange(R)) for k in keys]
+    assert all(a["status"] == 0 for a in asg)
+    beside = [i for i, a in enumerate(asg) if a["fnc0"] == 1 and a["is_old0"] == 0]
+    assert len(beside) >= 10 and any(a["fnc1"] == 1 for a in asg) and any(a["is_old0"] == 1 for a in asg)
+    want = [osmt.processor(a["old_root"], a["siblings"], a["old_key"], a["old_value"], a["is_old0"], a["new_key"],
+                           a["new_value"], a["fnc0"], a["fnc1"]) for a in asg]
+    assert [w[0] for w in want] == [a["new_root"] for a in asg] and all(w[1] == 0 for w in want)
+    args = (elems(a["old_root"] for a in asg), [a["packed"] for a in asg], n_levels, elems(a["old_key"] for a in asg),
+            elems(a["old_value"] for a in asg), np.array([a["is_old0"] for a in asg], np.uint8),
+            elems(a["new_key"] for a in asg), elems(a["new_value"] for a in asg),
+            np.array([a["fnc0"] for a in asg], np.uint8), np.array([a["fnc1"] for a in asg], np.uint8))
+    out, st = engine.smt_process_arbo(*args)
+    assert [int(x) for x in st] == [0] * len(asg) and ints(out) == [a["new_root"] for a in asg]
+    out2, st2 = engine.smt_process_packed(*args)
+    st2 = [int(x) for x in st2]
+    assert all(st2[i] == osmt.STATUS_ASSERTION for i in beside)
+    assert all(st2[i] == 0 for i in range(len(asg)) if i not in beside)
+    # a string with nothing to drop: the reference panics on siblingsUnpacked[0:-1]
+    empty = osmt.pack_siblings([])
+    a = asg[beside[0]]
+    out3, st3 = engine.smt_process_arbo(elems([a["old_root"]]), [empty], n_levels, elems([a["old_key"]]),
+                                        elems([a["old_value"]]), np.array([0], np.uint8), elems([a["new_key"]]),
+                                        elems([a["new_value"]]), np.array([1], np.uint8), np.array([0], np.uint8))
+    assert int(st3[0]) == osmt.STATUS_MALFORMED and ints(out3) == [0]
+
+
 @pytest.mark.parametrize("seed", [1, 2])
 def test_random_differential_with_mutations(engine, seed):
     """Seeded differential run against the literal oracle: transitions of a growing tree at an odd level count, each
