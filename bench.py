@@ -205,8 +205,9 @@ N_FIELDS = 8
 # executed work model of the ElGamal kernels: per encryption 13 + 13 signed 20-bit windows of k (C1 = [k]G,
 # [k]PK) and one non-zero window of a 16-bit m, each a mixed addition of 7 multiplies; the fused kernel never normalises
 WIDE_PER_ENCRYPTION = 27 * 7 * FR_MUL_WIDE
-# Keccak-f[1600] on 32-bit halves (keccak.cuh): per round theta 20 LOP3 + 10 SHF + 50 XOR, rho 48 SHF, chi 50 LOP3, iota 2
-ALU_PER_ADDRESS = 24 * 180 + 80          # + byte swaps of the 64-byte big-endian input and the 20-byte output
+# Keccak-f[1600] on 32-bit halves (keccak.cuh): per round 122 LOP3 (column parities 20, theta folded into rho's input 50,
+# chi 50, iota 2) + 58 SHF (rot(c, 1) 10, rho 48): the SASS of the loop body holds exactly these (cuobjdump)
+ALU_PER_ADDRESS = 24 * 180 + 40          # + index arithmetic and the loop counter
 ALU_LANES_PER_CLK_SM = 64
 
 
@@ -402,7 +403,7 @@ def measure_config4(torch, dist, eng, g, world, rank, log2_n, sm_mhz, do_cpu):
                            "peak": alu_peak / 1e12, "unit": "T ALU op/s (LOP3/SHF, modelled count per address)",
                            "frac": achieved / alu_peak, "alu_ops_per_address_model": ALU_PER_ADDRESS,
                            "hbm_gb_per_s": n * 84 / (ms * 1e-3) / 1e9,
-                           "note": "instruction count is a model (see profiles/ for the ncu pipe utilisation); HBM term is 4 % of peak"}
+                           "note": "ALU-pipe instructions counted in the SASS (122 LOP3 + 58 SHF per round); 64 ALU lanes/clk/SM; ncu pipe utilisation under profiles/; HBM term is ~5 % of peak"}
     h_pub = _pinned_copy(torch, pub)
     h_addr = torch.empty((n, 20), dtype=torch.uint8).pin_memory()
     lib, hctx = eng._lib, eng._h

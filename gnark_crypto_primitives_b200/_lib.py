@@ -17,6 +17,7 @@ GCP_ERR_ALLOC = -5
 
 FMT_CANONICAL = 0
 FMT_MONTGOMERY = 1
+COORDS_TE = 2       # or-ed into fmt: curve points on the wire are in iden3 twisted-Edwards coordinates (gcp_b200.h)
 
 STATUS_OK = 0
 STATUS_NONCANONICAL = 1

@@ -35,7 +35,27 @@ constexpr int BATCH_INV = 32;
 // ---- table construction (one-time per base point) ------------------------------------------------------
 // step 1: ext[w * FB_ENTRIES + 0] = [2^(WBITS*w)] B.  base: affine standard-form (x, y), 16 words.
 // flag[0] = 1 if B is on the curve and canonical, else 0.
-__global__ void fb_table_bases_kernel(const u32* __restrict__ base, int base_mont, u32* __restrict__ ext, u32* __restrict__ flag) {
+// iden3 / circom twisted-Edwards coordinates at the boundary (ecc/format/twistededwards.go:29-48):
+// FromTEtoRTE(x, y) = (x * (-f), y), FromRTEtoTE(x, y) = (x / (-f), y).  With GCP_COORDS_TE set in the format argument
+// every point a kernel reads is converted on load and every point it writes on store, one multiply each, so callers that
+// hold circom-side points need no separate conversion pass (and no extra PCIe round trip).  The constants are c * R:
+// mont_mul(x, c * R) = x * c in whichever representation x is in.
+#define GCP_NEG_F_MONT {0xc9603c7bu, 0x5c62c8e0u, 0x8fabc7f1u, 0xf8382911u, 0x6aa07f4du, 0x7d53da81u, 0x6ba06ab6u, 0x1da7c5b3u}
+#define GCP_NEG_F_INV_MONT {0xb1b017d8u, 0x61d380bfu, 0x8415d72eu, 0x7f5d8063u, 0x294f7a18u, 0x77e18e30u, 0x305733c2u, 0x10d2ede5u}
+__device__ __forceinline__ void te_to_rte_x(u32 (&x)[8]) {
+  const u32 negf[8] = GCP_NEG_F_MONT;
+  u32 t[8];
+  fr_mul(t, x, negf);
+  fr_copy(x, t);
+}
+__device__ __forceinline__ void rte_to_te_x(u32 (&x)[8]) {
+  const u32 negf_inv[8] = GCP_NEG_F_INV_MONT;
+  u32 t[8];
+  fr_mul(t, x, negf_inv);
+  fr_copy(x, t);
+}
+
+__global__ void fb_table_bases_kernel(const u32* __restrict__ base, int base_mont, int te, u32* __restrict__ ext, u32* __restrict__ flag) {
   int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= FB_WINDOWS) return;
   u32 xs[8], ys[8], x[8], y[8];
@@ -49,6 +69,7 @@ __global__ void fb_table_bases_kernel(const u32* __restrict__ base, int base_mon
     fr_to_mont(x, xs);
     fr_to_mont(y, ys);
   }
+  if (te) te_to_rte_x(x);
   ok = ok && ed_is_on_curve(x, y);
   if (w == 0) flag[0] = ok ? 1u : 0u;
   ExtPoint p;
@@ -251,7 +272,8 @@ __global__ void __launch_bounds__(128, 4) encrypt_shared_kernel(const u32* __res
 // ---- (X, Y, Z) -> canonical affine, Montgomery batch inversion over BATCH_INV points per thread ----------------
 // xyz: n_points x xyz_words words (24, or 32 for extended points with T behind Z); out: n_points x 16 words.  status (optional) is indexed by point / pts_per_item.
 __global__ void __launch_bounds__(128) normalize_kernel(const u32* __restrict__ xyz, size_t n_points, u32* __restrict__ out,
-                                                        u8* __restrict__ status, int pts_per_item, int mont, int xyz_words) {
+                                                        u8* __restrict__ status, int pts_per_item, int mont, int xyz_words,
+                                                        int te) {
   size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
   if (tid >= n_points) return;
@@ -303,6 +325,7 @@ __global__ void __launch_bounds__(128) normalize_kernel(const u32* __restrict__ 
     load_fr(Y, xyz + p * (size_t)xyz_words + 8);
     fr_mul(x, X, zi);
     fr_mul(y, Y, zi);
+    if (te) rte_to_te_x(x);  // results leave in iden3 coordinates
     u32 ox[8], oy[8];
     if (mont) {
       fr_copy(ox, x);
@@ -324,7 +347,7 @@ __global__ void __launch_bounds__(128) normalize_kernel(const u32* __restrict__ 
 }
 
 // ---- Ciphertext.Add / Neg, element-wise ------------------------------------------------------------------------
-__device__ __forceinline__ void load_affine_ext(ExtPoint& p, bool& canonical, const u32* src, int mont) {
+__device__ __forceinline__ void load_affine_ext(ExtPoint& p, bool& canonical, const u32* src, int mont, int te = 0) {
   u32 xs[8], ys[8], x[8], y[8];
   load_fr(xs, src);
   load_fr(ys, src + 8);
@@ -336,18 +359,19 @@ __device__ __forceinline__ void load_affine_ext(ExtPoint& p, bool& canonical, co
     fr_to_mont(x, xs);
     fr_to_mont(y, ys);
   }
+  if (te) te_to_rte_x(x);
   ext_from_affine(p, x, y);
 }
 
 // a, b: n x 32 words (ciphertexts); out_xyz: n x 2 x 24 words
 __global__ void __launch_bounds__(128) ct_add_kernel(const u32* __restrict__ a, const u32* __restrict__ b, size_t n,
-                                                     u32* __restrict__ out_xyz, u8* __restrict__ status, int mont) {
+                                                     u32* __restrict__ out_xyz, u8* __restrict__ status, int mont, int te) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= 2 * n) return;  // one thread per point
   bool canon = true;
   ExtPoint p, q;
-  load_affine_ext(p, canon, a + idx * 16, mont);
-  load_affine_ext(q, canon, b + idx * 16, mont);
+  load_affine_ext(p, canon, a + idx * 16, mont, te);
+  load_affine_ext(q, canon, b + idx * 16, mont, te);
   ext_add(p, q);  // ciphertext.go:29-30
   if (!canon) {
     ext_identity(p);
@@ -459,7 +483,7 @@ __device__ __forceinline__ void block_reduce_columns(ExtPoint& acc, u32* smem, i
 
 __global__ void __launch_bounds__(TALLY_THREADS, 4) tally_partial_kernel(const u32* __restrict__ ct, size_t n_ballots, int n_fields,
                                                                       u32* __restrict__ partials, u32* __restrict__ bad_count,
-                                                                      int mont) {
+                                                                      int mont, int te) {
   extern __shared__ u32 smem[];  // TALLY_THREADS x 32 words
   const int cols = n_fields * 2;                       // point columns per ballot
   const int rows_per_block = TALLY_THREADS / cols;     // ballots processed concurrently by one block
@@ -498,6 +522,7 @@ __global__ void __launch_bounds__(TALLY_THREADS, 4) tally_partial_kernel(const u
       // differences need no product, whose T is x*y with the lost factor restored by the constant (2d R^2 instead of
       // 2d R), and whose Z = 1/R turns D = 2 Z1 Z2 into one Montgomery reduction of 2 Z1 (ext_add_niels, z_over_r).
       // 9 (Montgomery) / 9.5 (standard) multiplies per point instead of 11 with the inputs converted first.
+      if (te) te_to_rte_x(xs);  // iden3 coordinates: x * (-f) in either representation (the constant carries the R)
       const u32 c_t_std[8] = GCP_ED_2D_R2, c_t_mont[8] = GCP_ED_2D_MONT;
       u32 c_t[8];
 #pragma unroll

@@ -13,6 +13,7 @@
 #include "kernels.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace gcp {
 
@@ -323,8 +324,8 @@ size_t fb_ext_scratch_bytes() { return (size_t)FB_WINDOWS * FB_ENTRIES * 32 * si
 static inline unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 cudaError_t launch_fb_table_build(const u32* d_base_xy, int base_mont, u32* d_ext, u32* d_tab, u32* d_flag,
-                                  cudaStream_t stream) {
-  fb_table_bases_kernel<<<1, 32, 0, stream>>>(d_base_xy, base_mont, d_ext, d_flag);
+                                  cudaStream_t stream, int te) {
+  fb_table_bases_kernel<<<1, 32, 0, stream>>>(d_base_xy, base_mont, te, d_ext, d_flag);
   const int total = FB_WINDOWS * FB_ENTRIES;
   fb_table_fill_kernel<<<blocks_for(total, 64), 64, 0, stream>>>(d_ext);
   fb_table_niels_kernel<<<blocks_for(total, 64), 64, 0, stream>>>(d_ext, d_tab);
@@ -352,16 +353,17 @@ cudaError_t launch_encrypt_shared(const u32* tabG, const u32* tabPK, const u32* 
 }
 
 cudaError_t launch_normalize(const u32* xyz, size_t n_points, u32* out, u8* status, int pts_per_item, int mont,
-                             cudaStream_t stream, int xyz_words) {
+                             cudaStream_t stream, int xyz_words, int te) {
   if (n_points == 0) return cudaSuccess;
   size_t threads = (n_points + BATCH_INV - 1) / BATCH_INV;
-  normalize_kernel<<<blocks_for(threads, 128), 128, 0, stream>>>(xyz, n_points, out, status, pts_per_item, mont, xyz_words);
+  normalize_kernel<<<blocks_for(threads, 128), 128, 0, stream>>>(xyz, n_points, out, status, pts_per_item, mont, xyz_words, te);
   return cudaGetLastError();
 }
 
-cudaError_t launch_ct_add(const u32* a, const u32* b, size_t n, u32* out_xyz, u8* status, int mont, cudaStream_t stream) {
+cudaError_t launch_ct_add(const u32* a, const u32* b, size_t n, u32* out_xyz, u8* status, int mont, cudaStream_t stream,
+                          int te) {
   if (n == 0) return cudaSuccess;
-  ct_add_kernel<<<blocks_for(2 * n, 128), 128, 0, stream>>>(a, b, n, out_xyz, status, mont);
+  ct_add_kernel<<<blocks_for(2 * n, 128), 128, 0, stream>>>(a, b, n, out_xyz, status, mont, te);
   return cudaGetLastError();
 }
 
@@ -392,11 +394,11 @@ int tally_max_blocks(size_t n_ballots, int n_fields, int sm_count) {
 
 // partials: n_blocks x (n_fields*2) x 32 words; bad_count: n_fields words (zeroed here); out_xyz: n_fields*2 x 24 words
 cudaError_t launch_tally(const u32* ct, size_t n_ballots, int n_fields, int n_blocks, u32* partials, u32* bad_count,
-                         u32* out_xyz, u8* status, int mont, cudaStream_t stream) {
+                         u32* out_xyz, u8* status, int mont, cudaStream_t stream, int te) {
   cudaError_t e = cudaMemsetAsync(bad_count, 0, sizeof(u32) * n_fields, stream);
   if (e != cudaSuccess) return e;
   tally_partial_kernel<<<n_blocks, TALLY_THREADS, TALLY_THREADS * 32 * sizeof(u32), stream>>>(ct, n_ballots, n_fields, partials,
-                                                                                              bad_count, mont);
+                                                                                              bad_count, mont, te);
   const int cols = n_fields * 2;
   tally_final_kernel<<<cols, TALLY_THREADS, 0, stream>>>(partials, n_blocks, cols, out_xyz, bad_count, status);
   return cudaGetLastError();
@@ -448,6 +450,16 @@ cudaError_t launch_keccak_address(const u8* in, size_t n, u8* out, cudaStream_t 
 // Variable-base family (varbase.cuh): pre pass -> [Poseidon batch] -> window kernel(s) -> post pass.
 // `scratch` holds the per-item intermediates (varbase_scratch_bytes), arrays laid out one after the other.
 // ---------------------------------------------------------------------------------------------------
+// resident blocks per SM the window kernel is compiled for: 4 (128 registers) or 5 (96 registers, 28 B of spills);
+// GCP_B200_VB_BLOCKS selects, for measurements
+static int varbase_min_blocks() {
+  static const int v = [] {
+    const char* e = getenv("GCP_B200_VB_BLOCKS");
+    return (e && atoi(e) == 4) ? 4 : ((e && atoi(e) == 5) ? 5 : 4);
+  }();
+  return v;
+}
+
 static cudaError_t launch_varbase_window(const u32* bases, const u32* s0, const u32* s1, int n_bases, size_t n,
                                          const u8* status, u32* table, u32* out, cudaStream_t stream) {
   VarbaseArgs a;
@@ -460,14 +472,24 @@ static cudaError_t launch_varbase_window(const u32* bases, const u32* s0, const 
   a.table = table;
   a.out = out;
   const size_t smem = (size_t)VB_SLOTS * 2 * VB_THREADS * sizeof(uint4);
-  cudaFuncSetAttribute(varbase_window_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  varbase_window_kernel<<<blocks_for(n, VB_THREADS), VB_THREADS, smem, stream>>>(a);
+  if (varbase_min_blocks() == 5) {
+    cudaFuncSetAttribute(varbase_window_kernel<5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    varbase_window_kernel<5><<<blocks_for(n, VB_THREADS), VB_THREADS, smem, stream>>>(a);
+  } else {
+    cudaFuncSetAttribute(varbase_window_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    varbase_window_kernel<4><<<blocks_for(n, VB_THREADS), VB_THREADS, smem, stream>>>(a);
+  }
   return cudaGetLastError();
 }
 
 size_t varbase_wave_items(int sm_count) {
-  cudaFuncSetAttribute(varbase_window_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  return wave_items(varbase_window_kernel, VB_THREADS, (size_t)VB_SLOTS * 2 * VB_THREADS * sizeof(uint4), sm_count, 4);
+  const size_t smem = (size_t)VB_SLOTS * 2 * VB_THREADS * sizeof(uint4);
+  if (varbase_min_blocks() == 5) {
+    cudaFuncSetAttribute(varbase_window_kernel<5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return wave_items(varbase_window_kernel<5>, VB_THREADS, smem, sm_count, 5);
+  }
+  cudaFuncSetAttribute(varbase_window_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  return wave_items(varbase_window_kernel<4>, VB_THREADS, smem, sm_count, 4);
 }
 
 // words of scratch per item: kind 0 Encrypt with per-item keys, 1 AssertDecrypt, 2 DecryptionProof.Verify, 3 EdDSA
@@ -478,11 +500,11 @@ size_t varbase_scratch_bytes(int kind, size_t n) { return VB_SCRATCH_WORDS[kind]
 // curve.ScalarMul over a batch: out (n x 32 words, extended) = [s]P (+ [s2]P2).  scratch: (32 + 8 + 256) * n_bases words per item
 size_t scalar_mul_scratch_bytes(size_t n, int n_bases) { return (size_t)(296 * n_bases) * sizeof(u32) * n; }
 cudaError_t launch_scalar_mul(const u32* points, const u32* scalars, const u32* points2, const u32* scalars2, size_t n,
-                              u32* out, u8* status, int mont, u32* scratch, int* n_launches, cudaStream_t stream) {
+                              u32* out, u8* status, int mont, u32* scratch, int* n_launches, cudaStream_t stream, int te) {
   if (n == 0) return cudaSuccess;
   const int nb = points2 ? 2 : 1;
   u32 *bases = scratch, *k0 = bases + n * 32 * nb, *k1 = k0 + n * 8, *table = k0 + n * 8 * nb;
-  scalar_mul_pre_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(points, scalars, points2, scalars2, n, mont, status, bases, k0, k1);
+  scalar_mul_pre_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(points, scalars, points2, scalars2, n, mont, te, status, bases, k0, k1);
   cudaError_t e = launch_varbase_window(bases, k0, nb == 2 ? k1 : nullptr, nb, n, status, table, out, stream);
   if (e != cudaSuccess) return e;
   *n_launches += 2;
@@ -490,10 +512,10 @@ cudaError_t launch_scalar_mul(const u32* points, const u32* scalars, const u32* 
 }
 
 cudaError_t launch_encrypt_per_key(const u32* tabG, const u32* pks, const u32* ks, const u32* ms, size_t n, u32* out_xyz,
-                                   u8* status, int mont, u32* scratch, int* n_launches, cudaStream_t stream) {
+                                   u8* status, int mont, u32* scratch, int* n_launches, cudaStream_t stream, int te) {
   if (n == 0) return cudaSuccess;
   u32 *bases = scratch, *kint = bases + n * 32, *table = kint + n * 8, *res = table + n * 256;
-  encrypt_per_key_pre_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(pks, ks, ms, n, mont, status, bases, kint);
+  encrypt_per_key_pre_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(pks, ks, ms, n, mont, te, status, bases, kint);
   cudaError_t e = launch_varbase_window(bases, kint, nullptr, 1, n, status, table, res, stream);
   if (e != cudaSuccess) return e;
   encrypt_per_key_finish_kernel<<<blocks_for(2 * n, 128), 128, 0, stream>>>(tabG, ks, ms, res, status, n, mont, out_xyz);
@@ -502,10 +524,10 @@ cudaError_t launch_encrypt_per_key(const u32* tabG, const u32* pks, const u32* k
 }
 
 cudaError_t launch_assert_decrypt(const u32* tabG, const u32* cts, const u32* privs, const u32* msgs, size_t n, u8* flags,
-                                  u8* status, int mont, u32* scratch, int* n_launches, cudaStream_t stream) {
+                                  u8* status, int mont, u32* scratch, int* n_launches, cudaStream_t stream, int te) {
   if (n == 0) return cudaSuccess;
   u32 *bases = scratch, *kint = bases + n * 32, *rhs = kint + n * 8, *table = rhs + n * 32, *res = table + n * 256;
-  assert_decrypt_pre_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(tabG, cts, privs, msgs, n, mont, status, bases, kint, rhs);
+  assert_decrypt_pre_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(tabG, cts, privs, msgs, n, mont, te, status, bases, kint, rhs);
   cudaError_t e = launch_varbase_window(bases, kint, nullptr, 1, n, status, table, res, stream);
   if (e != cudaSuccess) return e;
   ext_compare_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(res, rhs, status, n, flags);
@@ -515,12 +537,12 @@ cudaError_t launch_assert_decrypt(const u32* tabG, const u32* cts, const u32* pr
 
 cudaError_t launch_decryption_proof(const u32* tabG, const PoseidonTable& tab13, const u32* pks, const u32* cts,
                                     const u32* msgs, const u32* a1s, const u32* a2s, const u32* zs, size_t n, u8* flags,
-                                    u8* status, int mont, u32* scratch, int* n_launches, cudaStream_t stream) {
+                                    u8* status, int mont, u32* scratch, int* n_launches, cudaStream_t stream, int te) {
   if (n == 0) return cudaSuccess;
   u32 *hin = scratch, *zg = hin + n * 96, *base_pk = zg + n * 32, *base2 = base_pk + n * 32, *zint = base2 + n * 64;
   u32 *e_int = zint + n * 8, *table = e_int + n * 8, *res1 = table + n * 512, *res2 = res1 + n * 32;
-  decryption_proof_pre_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(tabG, pks, cts, msgs, a1s, a2s, zs, n, mont, status, hin,
-                                                                      zg, base_pk, base2, zint);
+  decryption_proof_pre_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(tabG, pks, cts, msgs, a1s, a2s, zs, n, mont, te, status,
+                                                                      hin, zg, base_pk, base2, zint);
   // e = MultiHash(PK, PK, C1, D, A1, A2): 12 inputs = one Hash with t = 13; Montgomery in, integer out
   cudaError_t e = launch_poseidon(tab13, hin, e_int, nullptr, n, 1, 12, 0, 1, 1, 0, 0, stream);
   if (e != cudaSuccess) return e;
@@ -528,7 +550,7 @@ cudaError_t launch_decryption_proof(const u32* tabG, const PoseidonTable& tab13,
   if (e != cudaSuccess) return e;
   e = launch_varbase_window(base2, zint, e_int, 2, n, status, table, res2, stream);
   if (e != cudaSuccess) return e;
-  decryption_proof_post_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(a1s, a2s, zg, res1, res2, status, n, mont, flags);
+  decryption_proof_post_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(a1s, a2s, zg, res1, res2, status, n, mont, te, flags);
   *n_launches += 5;
   return cudaGetLastError();
 }

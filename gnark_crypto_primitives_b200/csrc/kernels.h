@@ -108,8 +108,10 @@ cudaError_t launch_smt_apply_bad(const u8* bad, size_t n, u8* flags, u8* status,
 size_t fb_table_bytes();
 size_t fb_ext_scratch_bytes();
 cudaError_t upload_generator(u32* d_xy, cudaStream_t stream);
+// te (last argument of the point-carrying launches below): the points on the wire are in iden3 twisted-Edwards coordinates
+// (GCP_COORDS_TE): converted with one multiply on load / store (ecc/format/twistededwards.go:29-48)
 cudaError_t launch_fb_table_build(const u32* d_base_xy, int base_mont, u32* d_ext, u32* d_tab, u32* d_flag,
-                                  cudaStream_t stream);
+                                  cudaStream_t stream, int te = 0);
 cudaError_t launch_fixed_base_mul(const u32* tabG, const u32* scalars, size_t n, u32* out_xyz, u8* status, int mont,
                                   cudaStream_t stream);
 cudaError_t launch_encrypt_shared(const u32* tabG, const u32* tabPK, const u32* pk_flag, const u32* ks, const u32* ms,
@@ -120,12 +122,14 @@ size_t varbase_scratch_bytes(int kind, size_t n);
 // out: n x 32 words (X, Y, Z, T) at scratch_result(...); the caller normalises with xyz_words = 32
 size_t scalar_mul_scratch_bytes(size_t n, int n_bases);
 cudaError_t launch_scalar_mul(const u32* points, const u32* scalars, const u32* points2, const u32* scalars2, size_t n,
-                              u32* out_ext, u8* status, int mont, u32* scratch, int* n_launches, cudaStream_t stream);
+                              u32* out_ext, u8* status, int mont, u32* scratch, int* n_launches, cudaStream_t stream,
+                              int te = 0);
 cudaError_t launch_encrypt_per_key(const u32* tabG, const u32* pks, const u32* ks, const u32* ms, size_t n, u32* out_xyz,
-                                   u8* status, int mont, u32* scratch, int* n_launches, cudaStream_t stream);
+                                   u8* status, int mont, u32* scratch, int* n_launches, cudaStream_t stream, int te = 0);
 cudaError_t launch_normalize(const u32* xyz, size_t n_points, u32* out, u8* status, int pts_per_item, int mont,
-                             cudaStream_t stream, int xyz_words = 24);
-cudaError_t launch_ct_add(const u32* a, const u32* b, size_t n, u32* out_xyz, u8* status, int mont, cudaStream_t stream);
+                             cudaStream_t stream, int xyz_words = 24, int te = 0);
+cudaError_t launch_ct_add(const u32* a, const u32* b, size_t n, u32* out_xyz, u8* status, int mont, cudaStream_t stream,
+                          int te = 0);
 cudaError_t launch_ct_neg(const u32* a, size_t n, u32* out, u8* status, cudaStream_t stream);
 cudaError_t launch_ct_is_equal(const u32* a, const u32* b, size_t n, u8* flags, u8* status, cudaStream_t stream);
 cudaError_t launch_ct_select(const u8* sel, const u32* i1, const u32* i2, size_t n, u32* out, u8* status, cudaStream_t stream);
@@ -136,10 +140,10 @@ cudaError_t launch_tally_status_merge(const u8* part_status, int n_chunks, int n
                                       u32* ct, u8* status, cudaStream_t stream);
 cudaError_t launch_keccak_address(const u8* in, size_t n, u8* out, cudaStream_t stream);
 cudaError_t launch_assert_decrypt(const u32* tabG, const u32* cts, const u32* privs, const u32* msgs, size_t n, u8* flags,
-                                  u8* status, int mont, u32* scratch, int* n_launches, cudaStream_t stream);
+                                  u8* status, int mont, u32* scratch, int* n_launches, cudaStream_t stream, int te = 0);
 cudaError_t launch_decryption_proof(const u32* tabG, const PoseidonTable& tab13, const u32* pks, const u32* cts,
                                     const u32* msgs, const u32* a1s, const u32* a2s, const u32* zs, size_t n, u8* flags,
-                                    u8* status, int mont, u32* scratch, int* n_launches, cudaStream_t stream);
+                                    u8* status, int mont, u32* scratch, int* n_launches, cudaStream_t stream, int te = 0);
 cudaError_t launch_te_rte(const u32* in, size_t n_points, u32* out, u8* status, int to_rte, cudaStream_t stream);
 cudaError_t launch_eddsa_verify(const u32* tabG, const PoseidonTable& tab6, const u32* pub_a, const u32* sig_r,
                                 const u32* sig_s, const u32* msgs, size_t n, u8* flags, u8* status, int mont, u32* scratch,
@@ -152,6 +156,6 @@ cudaError_t launch_poseidon2_permutation(const u32* keys, const u32* in, size_t 
                                          cudaStream_t stream);
 int tally_max_blocks(size_t n_ballots, int n_fields, int sm_count);
 cudaError_t launch_tally(const u32* ct, size_t n_ballots, int n_fields, int n_blocks, u32* partials, u32* bad_count,
-                         u32* out_xyz, u8* status, int mont, cudaStream_t stream);
+                         u32* out_xyz, u8* status, int mont, cudaStream_t stream, int te = 0);
 
 }  // namespace gcp

@@ -13,8 +13,8 @@ __global__ void te_rte_kernel(const u32* __restrict__ in, size_t n_points, u32* 
                               int to_rte) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_points) return;
-  const u32 negf[8] = {0xc9603c7bu, 0x5c62c8e0u, 0x8fabc7f1u, 0xf8382911u, 0x6aa07f4du, 0x7d53da81u, 0x6ba06ab6u, 0x1da7c5b3u};
-  const u32 negf_inv[8] = {0xb1b017d8u, 0x61d380bfu, 0x8415d72eu, 0x7f5d8063u, 0x294f7a18u, 0x77e18e30u, 0x305733c2u, 0x10d2ede5u};
+  const u32 negf[8] = GCP_NEG_F_MONT;
+  const u32 negf_inv[8] = GCP_NEG_F_INV_MONT;
   u32 x[8], y[8], r[8];
   load_fr(x, in + idx * 16);
   load_fr(y, in + idx * 16 + 8);

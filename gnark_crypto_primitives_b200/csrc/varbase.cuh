@@ -123,7 +123,8 @@ __device__ __forceinline__ u32 vb_pick8(const u32 (&a)[8], int i) {
   return v;
 }
 
-__global__ void __launch_bounds__(VB_THREADS, 4) varbase_window_kernel(VarbaseArgs a) {
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(VB_THREADS, MIN_BLOCKS) varbase_window_kernel(VarbaseArgs a) {
   extern __shared__ uint4 vb_smem[];  // VB_SLOTS x 2 x VB_THREADS
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.n) return;
@@ -369,7 +370,7 @@ __device__ __noinline__ bool ext_equal(const ExtPoint& p, const ExtPoint& q) {
 }
 
 // affine point from memory: canonical check, Montgomery conversion, on-curve check; result extended
-__device__ __noinline__ void load_curve_point(ExtPoint& p, bool& canonical, bool& on_curve, const u32* src, int mont) {
+__device__ __noinline__ void load_curve_point(ExtPoint& p, bool& canonical, bool& on_curve, const u32* src, int mont, int te = 0) {
   u32 xs[8], ys[8], x[8], y[8];
   load_fr(xs, src);
   load_fr(ys, src + 8);
@@ -381,6 +382,7 @@ __device__ __noinline__ void load_curve_point(ExtPoint& p, bool& canonical, bool
     fr_to_mont(x, xs);
     fr_to_mont(y, ys);
   }
+  if (te) te_to_rte_x(x);
   on_curve = on_curve && ed_is_on_curve(x, y);
   ext_from_affine(p, x, y);
 }
@@ -392,8 +394,8 @@ __device__ __noinline__ void ext_add_ool(ExtPoint& p, const ExtPoint& q) { ext_a
 // bases and integer scalars for the window kernel; bases: n x n_bases x 32 words.
 __global__ void __launch_bounds__(128) scalar_mul_pre_kernel(const u32* __restrict__ points, const u32* __restrict__ scalars,
                                                              const u32* __restrict__ points2, const u32* __restrict__ scalars2,
-                                                             size_t n, int mont, u8* __restrict__ status, u32* __restrict__ bases,
-                                                             u32* __restrict__ k0, u32* __restrict__ k1) {
+                                                             size_t n, int mont, int te, u8* __restrict__ status,
+                                                             u32* __restrict__ bases, u32* __restrict__ k0, u32* __restrict__ k1) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   const int nb = points2 ? 2 : 1;
@@ -402,7 +404,7 @@ __global__ void __launch_bounds__(128) scalar_mul_pre_kernel(const u32* __restri
   for (int b = 0; b < nb; b++) {
     ExtPoint p;
     u32 k[8];
-    load_curve_point(p, canon, on_curve, (b ? points2 : points) + idx * 16, mont);
+    load_curve_point(p, canon, on_curve, (b ? points2 : points) + idx * 16, mont, te);
     load_scalar(k, canon, (b ? scalars2 : scalars) + idx * 8, mont);
     store_ext(bases + (idx * nb + b) * 32, p);
     store_fr((b ? k1 : k0) + idx * 8, k);
@@ -414,7 +416,7 @@ __global__ void __launch_bounds__(128) scalar_mul_pre_kernel(const u32* __restri
 // pre: AssertIsOnCurve(pubKey) (:49), k as an integer; window kernel: S = [k]pubKey (:55); finish: C1 = [k]G (:52),
 // C2 = [m]G + S (:58-61), one thread per point (whole warps per half), then normalize_kernel.
 __global__ void __launch_bounds__(128) encrypt_per_key_pre_kernel(const u32* __restrict__ pks, const u32* __restrict__ ks,
-                                                                  const u32* __restrict__ ms, size_t n, int mont,
+                                                                  const u32* __restrict__ ms, size_t n, int mont, int te,
                                                                   u8* __restrict__ status, u32* __restrict__ bases,
                                                                   u32* __restrict__ kint) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -424,7 +426,7 @@ __global__ void __launch_bounds__(128) encrypt_per_key_pre_kernel(const u32* __r
   load_scalar(k, canon, ks + idx * 8, mont);
   load_scalar(m, canon, ms + idx * 8, mont);
   ExtPoint pk;
-  load_curve_point(pk, canon, on_curve, pks + idx * 16, mont);
+  load_curve_point(pk, canon, on_curve, pks + idx * 16, mont, te);
   status[idx] = !canon ? GCP_STATUS_NONCANONICAL : (!on_curve ? GCP_STATUS_OFF_CURVE : GCP_STATUS_OK);
   store_ext(bases + idx * 32, pk);
   store_fr(kint + idx * 8, k);
@@ -454,7 +456,7 @@ __global__ void __launch_bounds__(128, 4) encrypt_per_key_finish_kernel(const u3
 // pre: rhs = C2 - [m]G;  window kernel: S = [priv]C1;  post: flag = (S == rhs)
 __global__ void __launch_bounds__(128, 4) assert_decrypt_pre_kernel(const u32* __restrict__ tabG, const u32* __restrict__ cts,
                                                                  const u32* __restrict__ privs, const u32* __restrict__ msgs,
-                                                                 size_t n, int mont, u8* __restrict__ status,
+                                                                 size_t n, int mont, int te, u8* __restrict__ status,
                                                                  u32* __restrict__ bases, u32* __restrict__ kint,
                                                                  u32* __restrict__ rhs) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -462,8 +464,8 @@ __global__ void __launch_bounds__(128, 4) assert_decrypt_pre_kernel(const u32* _
   bool canon = true, on_curve = true;
   ExtPoint c1, c2;
   u32 priv[8], msg[8];
-  load_curve_point(c1, canon, on_curve, cts + idx * 32, mont);
-  load_curve_point(c2, canon, on_curve, cts + idx * 32 + 16, mont);
+  load_curve_point(c1, canon, on_curve, cts + idx * 32, mont, te);
+  load_curve_point(c2, canon, on_curve, cts + idx * 32 + 16, mont, te);
   load_scalar(priv, canon, privs + idx * 8, mont);
   load_scalar(msg, canon, msgs + idx * 8, mont);
   const u8 st = !canon ? GCP_STATUS_NONCANONICAL : (!on_curve ? GCP_STATUS_OFF_CURVE : GCP_STATUS_OK);
@@ -501,7 +503,7 @@ __global__ void __launch_bounds__(128) ext_compare_kernel(const u32* __restrict_
 __global__ void __launch_bounds__(128, 4) decryption_proof_pre_kernel(const u32* __restrict__ tabG, const u32* __restrict__ pks,
                                                                    const u32* __restrict__ cts, const u32* __restrict__ msgs,
                                                                    const u32* __restrict__ a1s, const u32* __restrict__ a2s,
-                                                                   const u32* __restrict__ zs, size_t n, int mont,
+                                                                   const u32* __restrict__ zs, size_t n, int mont, int te,
                                                                    u8* __restrict__ status, u32* __restrict__ hash_in,
                                                                    u32* __restrict__ zg, u32* __restrict__ base_pk,
                                                                    u32* __restrict__ base_c1_d, u32* __restrict__ zint) {
@@ -516,7 +518,7 @@ __global__ void __launch_bounds__(128, 4) decryption_proof_pre_kernel(const u32*
   for (int which = 0; which < 4; which++) {  // PK, C1, A1, A2
     const u32* src = which == 0 ? pks + idx * 16 : (which == 1 ? cts + idx * 32 : (which == 2 ? a1s + idx * 16 : a2s + idx * 16));
     ExtPoint p;
-    load_curve_point(p, canon, on_curve, src, mont);
+    load_curve_point(p, canon, on_curve, src, mont, te);
     // hash input positions (elements): PK at 0,1 and 2,3; C1 at 4,5; (D at 6,7); A1 at 8,9; A2 at 10,11
     const int pos = which == 0 ? 0 : (which == 1 ? 4 : (which == 2 ? 8 : 10));
     u32 cx[8], cy[8];
@@ -534,7 +536,7 @@ __global__ void __launch_bounds__(128, 4) decryption_proof_pre_kernel(const u32*
       store_ext(base_c1_d + idx * 64, p);
     }
   }
-  load_curve_point(c2, canon, on_curve, cts + idx * 32 + 16, mont);
+  load_curve_point(c2, canon, on_curve, cts + idx * 32 + 16, mont, te);
   load_scalar(msg, canon, msgs + idx * 8, mont);
   load_scalar(z, canon, zs + idx * 8, mont);
   u8 st = !canon ? GCP_STATUS_NONCANONICAL : (!on_curve ? GCP_STATUS_OFF_CURVE : GCP_STATUS_OK);
@@ -572,19 +574,19 @@ __global__ void __launch_bounds__(128, 4) decryption_proof_pre_kernel(const u32*
 __global__ void __launch_bounds__(128) decryption_proof_post_kernel(const u32* __restrict__ a1s, const u32* __restrict__ a2s,
                                                                     const u32* __restrict__ zg, const u32* __restrict__ epk,
                                                                     const u32* __restrict__ zc1_ed, const u8* __restrict__ status,
-                                                                    size_t n, int mont, u8* __restrict__ flags) {
+                                                                    size_t n, int mont, int te, u8* __restrict__ flags) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   u8 flag = 0;
   if (status[idx] == GCP_STATUS_OK) {
     bool c = true, oc = true;
     ExtPoint a, l, r;
-    load_curve_point(a, c, oc, a1s + idx * 16, mont);
+    load_curve_point(a, c, oc, a1s + idx * 16, mont, te);
     load_ext(r, epk + idx * 32);
     ext_add_ool(r, a);  // A1 + e*P
     load_ext(l, zg + idx * 32);
     bool ok = ext_equal(l, r);
-    load_curve_point(a, c, oc, a2s + idx * 16, mont);
+    load_curve_point(a, c, oc, a2s + idx * 16, mont, te);
     load_ext(l, zc1_ed + idx * 32);  // z*C1 - e*D
     ok = ok && ext_equal(l, a);
     flag = ok ? 1 : 0;
@@ -595,7 +597,6 @@ __global__ void __launch_bounds__(128) decryption_proof_post_kernel(const u32* _
 // ---- EdDSA-Poseidon IsValid (/root/reference/ecc/bn254/eddsa/verifier.go:55-88) ----------------------------------------
 // A, R in TE (circom/iden3) coordinates; h = Poseidon(R.x, R.y, A.x, A.y, msg) on those coordinates (t = 6);
 // A' = RTE(A), R' = RTE(R) asserted on the a = -1 curve; flag = ([S]G == 8*[h]A' + R')  (rteB8 == G, constants.go:11-18).
-#define GCP_NEG_F_MONT {0xc9603c7bu, 0x5c62c8e0u, 0x8fabc7f1u, 0xf8382911u, 0x6aa07f4du, 0x7d53da81u, 0x6ba06ab6u, 0x1da7c5b3u}
 
 __global__ void __launch_bounds__(128, 4) eddsa_pre_kernel(const u32* __restrict__ tabG, const u32* __restrict__ pub_a,
                                                         const u32* __restrict__ sig_r, const u32* __restrict__ sig_s,

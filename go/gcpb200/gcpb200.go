@@ -211,6 +211,66 @@ func (e *Engine) BatchProcess(levels int, oldRoots, siblings, oldKeys, oldValues
 	return
 }
 
+// BatchProcessWithLeafHash mirrors smt.ProcessorWithLeafHash (tree/smt/processor.go:16): the caller supplies
+// hash1Old / hash1New (e.g. from BatchHash1 for leaves with several values).
+func (e *Engine) BatchProcessWithLeafHash(levels int, oldRoots, siblings, oldKeys, hash1Old []fr.Element, isOld0 []byte,
+	newKeys, hash1New []fr.Element, fnc0, fnc1 []byte) (newRoots []fr.Element, status []byte, err error) {
+	n := len(newKeys)
+	newRoots, status = make([]fr.Element, n), make([]byte, n)
+	err = e.err(C.gcp_smt_process_with_leaf_hash(e.ctx, C.int(levels), C.size_t(n), elemPtr(oldRoots), elemPtr(siblings),
+		elemPtr(oldKeys), elemPtr(hash1Old), bytePtr(isOld0), elemPtr(newKeys), elemPtr(hash1New), bytePtr(fnc0), bytePtr(fnc1),
+		elemPtr(newRoots), bytePtr(status), C.GCP_FMT_MONTGOMERY))
+	return
+}
+
+// BatchProcessArbo is smt.Processor fed the way WrapperArbo.addOrUpdate feeds it (tree/smt/wrapper_arbo.go:152-172):
+// packed[i] is the siblingsPacked of a GenProof taken AFTER the add/update; where isOld0[i] == 0 and fnc1[i] == 0 the last
+// unpacked sibling (the displaced old leaf) is dropped, as :170-172 do, before the row is padded to `levels`.
+func (e *Engine) BatchProcessArbo(levels int, oldRoots []fr.Element, packed [][]byte, oldKeys, oldValues []fr.Element,
+	isOld0 []byte, newKeys, newValues []fr.Element, fnc0, fnc1 []byte) (newRoots []fr.Element, status []byte, err error) {
+	n := len(newKeys)
+	newRoots, status = make([]fr.Element, n), make([]byte, n)
+	offsets := make([]uint64, n+1)
+	total := 0
+	for i, b := range packed {
+		total += len(b)
+		offsets[i+1] = uint64(total)
+	}
+	blob := make([]byte, 0, total+1)
+	for _, b := range packed {
+		blob = append(blob, b...)
+	}
+	blob = append(blob, 0)
+	err = e.err(C.gcp_smt_process_arbo(e.ctx, C.int(levels), C.size_t(n), elemPtr(oldRoots), bytePtr(blob),
+		(*C.uint64_t)(unsafe.Pointer(&offsets[0])), elemPtr(oldKeys), elemPtr(oldValues), bytePtr(isOld0), elemPtr(newKeys),
+		elemPtr(newValues), bytePtr(fnc0), bytePtr(fnc1), elemPtr(newRoots), bytePtr(status), C.GCP_FMT_MONTGOMERY))
+	return
+}
+
+// BatchHash1 mirrors smt.Hash1 (tree/smt/hash.go:10-19): out[i] = Poseidon(keys[i], values[i*nValues : (i+1)*nValues]..., 1).
+func (e *Engine) BatchHash1(keys, values []fr.Element, nValues int) (out []fr.Element, status []byte, err error) {
+	n := len(keys)
+	out, status = make([]fr.Element, n), make([]byte, n)
+	err = e.err(C.gcp_smt_leaf_hash(e.ctx, elemPtr(keys), elemPtr(values), C.int(nValues), C.size_t(n), elemPtr(out),
+		bytePtr(status), C.GCP_FMT_MONTGOMERY))
+	return
+}
+
+// BatchVerifyWithLeafHash mirrors smt.VerifierWithLeafHashFlag (tree/smt/verifier.go:171): p.OldValues / p.Values carry
+// hash1Old / hash1New.  smt.VerifierWithLeafHash (:129) is this plus the caller's check that every flag is 1.
+func (e *Engine) BatchVerifyWithLeafHash(p *Proofs) (flags, status []byte, err error) {
+	n := len(p.Keys)
+	flags, status = make([]byte, n), make([]byte, n)
+	shared := 0
+	if len(p.Roots) == 1 && n != 1 {
+		shared = 1
+	}
+	err = e.err(C.gcp_smt_verify_with_leaf_hash(e.ctx, C.int(p.Levels), C.size_t(n), elemPtr(p.Roots), C.int(shared),
+		elemPtr(p.Siblings), elemPtr(p.OldKeys), elemPtr(p.OldValues), bytePtr(p.IsOld0), elemPtr(p.Keys), elemPtr(p.Values),
+		bytePtr(p.Fnc), bytePtr(p.Enabled), bytePtr(flags), bytePtr(status), nil, C.GCP_FMT_MONTGOMERY))
+	return
+}
+
 // BatchEncrypt mirrors (*Ciphertext).Encrypt (elgamal/encrypt.go:42) with one shared public key (X, Y).
 // Ciphertexts come back as 4 elements each in Serialize() order: C1.X, C1.Y, C2.X, C2.Y (ciphertext.go:98-105).
 func (e *Engine) BatchEncrypt(pubKey [2]fr.Element, k, m []fr.Element) (ct []fr.Element, status []byte, err error) {

@@ -45,6 +45,13 @@ enum gcp_error {
 };
 
 enum gcp_format { GCP_FMT_CANONICAL = 0, GCP_FMT_MONTGOMERY = 1 };
+/* Or-ed into `fmt` of the gcp_elgamal_* / gcp_ballot_batch* / gcp_group_elgamal_* entry points (every call that reads or
+ * writes curve points, EdDSA excepted: its points are TE by definition): the points on the wire are in iden3 / circom
+ * twisted-Edwards coordinates, (x_TE, y) with x_RTE = x_TE * (-f) (FromTEtoRTE / FromRTEtoTE,
+ * ecc/format/twistededwards.go:29-48).  They are converted inside the kernels (one multiply per point read or written),
+ * so the call equals te_to_rte on every input point, the RTE call, rte_to_te on every output point - without the two extra
+ * passes over PCIe.  On-curve assertions apply to the converted point.  Scalars and SMT elements are unaffected. */
+enum gcp_coords { GCP_COORDS_RTE = 0, GCP_COORDS_TE = 2 };
 
 /* per-item status bytes */
 enum gcp_status {

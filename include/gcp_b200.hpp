@@ -185,6 +185,51 @@ inline Batch Processor(const Engine& e, int n_levels, size_t n, const uint8_t* o
                           fnc1, b.values.data(), b.status.data(), fmt));
   return b;
 }
+// smt.ProcessorWithLeafHash (processor.go:16): hash1_old / hash1_new in the place of the values
+inline Batch ProcessorWithLeafHash(const Engine& e, int n_levels, size_t n, const uint8_t* old_roots, const uint8_t* siblings,
+                                   const uint8_t* old_keys, const uint8_t* hash1_old, const uint8_t* is_old0,
+                                   const uint8_t* new_keys, const uint8_t* hash1_new, const uint8_t* fnc0, const uint8_t* fnc1,
+                                   int fmt = GCP_FMT_CANONICAL) {
+  Batch b;
+  b.values.resize(n * 32);
+  b.status.resize(n);
+  e.check(gcp_smt_process_with_leaf_hash(e.raw(), n_levels, n, old_roots, siblings, old_keys, hash1_old, is_old0, new_keys,
+                                         hash1_new, fnc0, fnc1, b.values.data(), b.status.data(), fmt));
+  return b;
+}
+// smt.Processor fed as WrapperArbo.addOrUpdate feeds it (wrapper_arbo.go:152-172): packed proofs generated AFTER the change
+inline Batch ProcessorArbo(const Engine& e, int n_levels, size_t n, const uint8_t* old_roots, const uint8_t* packed,
+                           const uint64_t* offsets, const uint8_t* old_keys, const uint8_t* old_values, const uint8_t* is_old0,
+                           const uint8_t* new_keys, const uint8_t* new_values, const uint8_t* fnc0, const uint8_t* fnc1,
+                           int fmt = GCP_FMT_CANONICAL) {
+  Batch b;
+  b.values.resize(n * 32);
+  b.status.resize(n);
+  e.check(gcp_smt_process_arbo(e.raw(), n_levels, n, old_roots, packed, offsets, old_keys, old_values, is_old0, new_keys,
+                               new_values, fnc0, fnc1, b.values.data(), b.status.data(), fmt));
+  return b;
+}
+// smt.Hash1 (hash.go:10-19): H(key, values..., 1), n_values values per leaf; digests in `values`
+inline Batch Hash1(const Engine& e, const uint8_t* keys, const uint8_t* values, int n_values, size_t n,
+                   int fmt = GCP_FMT_CANONICAL) {
+  Batch b;
+  b.values.resize(n * 32);
+  b.status.resize(n);
+  e.check(gcp_smt_leaf_hash(e.raw(), keys, values, n_values, n, b.values.data(), b.status.data(), fmt));
+  return b;
+}
+// smt.VerifierWithLeafHashFlag (verifier.go:171-242); VerifierWithLeafHash (:129-147) asserts the flag
+inline Batch VerifierWithLeafHashFlag(const Engine& e, int n_levels, size_t n, const uint8_t* enabled, const uint8_t* roots,
+                                      bool shared_root, const uint8_t* siblings, const uint8_t* old_keys,
+                                      const uint8_t* hash1_old, const uint8_t* is_old0, const uint8_t* keys,
+                                      const uint8_t* hash1_new, const uint8_t* fnc, int fmt = GCP_FMT_CANONICAL) {
+  Batch b;
+  b.flags.resize(n);
+  b.status.resize(n);
+  e.check(gcp_smt_verify_with_leaf_hash(e.raw(), n_levels, n, roots, shared_root, siblings, old_keys, hash1_old, is_old0, keys,
+                                        hash1_new, fnc, enabled, b.flags.data(), b.status.data(), nullptr, fmt));
+  return b;
+}
 }  // namespace smt
 
 namespace elgamal {

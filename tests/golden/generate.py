@@ -25,6 +25,7 @@ from oracle import mimc7  # noqa: E402
 from oracle import poseidon2  # noqa: E402
 from oracle import poseidon as pos  # noqa: E402
 from oracle import smt  # noqa: E402
+from oracle import smt as osmt  # noqa: E402
 from oracle.field import R  # noqa: E402
 
 S = str  # big integers travel as decimal strings
@@ -121,6 +122,51 @@ def pt(p):
     return [S(p[0]), S(p[1])]
 
 
+def smt_leaf_hash_section():
+    """Leaf-hash forms (verifier.go:129-183, processor.go:16, hash.go:10-19) on a tree with three values per leaf, and
+    the reference's post-insert processor flow (wrapper_arbo.go:119-185)."""
+    rng = random.Random(0xB202)
+    n_levels, n_values = 24, 3
+    tree = osmt.Tree(n_levels)
+    leaves = {}
+    while len(leaves) < 9:
+        leaves[rng.getrandbits(n_levels)] = tuple(rng.randrange(R) for _ in range(n_values))
+    for k, v in leaves.items():
+        tree.add(k, v)
+    root = tree.root()
+    hash1 = [{"key": S(k), "values": [S(x) for x in v], "hash": S(osmt.hash1(k, *v))} for k, v in leaves.items()]
+    hash1.append({"key": S(5), "values": [], "hash": S(osmt.hash1(5))})
+    cases = []
+    for k, v in list(leaves.items())[:5]:
+        p = tree.gen_proof(k)
+        for vals in (v, v[:2] + ((v[2] + 1) % R,)):
+            h = osmt.hash1(k, *vals)
+            f, st, lv = osmt.verifier_with_leaf_hash_flag(1, root, p["siblings"], k, h, 0, k, h, 0)
+            cases.append({"root": S(root), "siblings": [S(x) for x in p["siblings"]], "old_key": S(k), "hash1_old": S(h),
+                          "is_old0": 0, "key": S(k), "hash1_new": S(h), "fnc": 0, "flag": f, "status": st, "level0": S(lv)})
+    for _ in range(6):
+        k = rng.getrandbits(n_levels)
+        if k in leaves:
+            continue
+        p = tree.gen_proof(k)
+        ho = osmt.hash1(p["old_key"], *p["old_value"]) if p["is_old0"] == 0 else 0
+        hn = osmt.hash1(k, 0, 0, 0)
+        f, st, lv = osmt.verifier_with_leaf_hash_flag(1, root, p["siblings"], p["old_key"], ho, p["is_old0"], k, hn, 1)
+        cases.append({"root": S(root), "siblings": [S(x) for x in p["siblings"]], "old_key": S(p["old_key"]), "hash1_old": S(ho),
+                      "is_old0": p["is_old0"], "key": S(k), "hash1_new": S(hn), "fnc": 1, "flag": f, "status": st, "level0": S(lv)})
+    t2 = osmt.Tree(n_levels)
+    arbo = []
+    ks = [rng.getrandbits(n_levels) for _ in range(10)]
+    ks += [ks[2], ks[7]]
+    for k in ks:
+        a = osmt.arbo_add_or_update(t2, k, rng.randrange(R))
+        arbo.append({"old_root": S(a["old_root"]), "new_root": S(a["new_root"]), "old_key": S(a["old_key"]),
+                     "old_value": S(a["old_value"]), "is_old0": a["is_old0"], "new_key": S(a["new_key"]),
+                     "new_value": S(a["new_value"]), "fnc0": a["fnc0"], "fnc1": a["fnc1"], "packed": a["packed"].hex(),
+                     "siblings": [S(x) for x in a["siblings"]]})
+    return {"n_levels": n_levels, "hash1": hash1, "verifier_with_leaf_hash": cases, "processor_arbo": arbo}
+
+
 def elgamal_section(rng):
     out = {}
     # elgamal/ciphertext_test.go:289-303 (literal in the reference)
@@ -183,6 +229,19 @@ def elgamal_section(rng):
     tp = (20284931487578954787250358776722960153090567235942462656834196519767860852891,
           21185575020764391300398134415668786804224896114060668011215204645513129497221)
     out["te_to_rte"] = [{"te": pt(p), "rte": pt(ed.te_to_rte(*p))} for p in (b8, tp)]
+    # GCP_COORDS_TE: the same gadgets with every point in iden3 coordinates at the boundary (own generator: the sections
+    # after this one keep their vectors)
+    r2 = random.Random(0xB201)
+    te = lambda p: ed.rte_to_te(*p)
+    te_ct = lambda c: [S(x) for q in c for x in te(q)]
+    pk3 = ed.scalar_mul(ed.G, r2.randrange(1, ed.ORDER))
+    nb2, nf2 = 4, 2
+    ks2 = [[r2.randrange(R) for _ in range(nf2)] for _ in range(nb2)]
+    ms2 = [[r2.randrange(1 << 16) for _ in range(nf2)] for _ in range(nb2)]
+    b2 = [[eg.encrypt(pk3, ks2[b][f], ms2[b][f]) for f in range(nf2)] for b in range(nb2)]
+    out["te_coords"] = {"pk_te": pt(te(pk3)), "k": [[S(x) for x in r] for r in ks2], "m": [[S(x) for x in r] for r in ms2],
+                        "ballots_te": [[te_ct(c) for c in row] for row in b2],
+                        "tally_te": [te_ct(eg.tally([b2[b][f] for b in range(nb2)])) for f in range(nf2)]}
     return out
 
 
@@ -237,6 +296,7 @@ def main():
         "_about": "generated by tests/golden/generate.py from oracle/*.py (seed 0xB200); integers are decimal strings",
         "poseidon": poseidon_section(rng),
         "smt": smt_section(rng),
+        "smt_leaf_hash": smt_leaf_hash_section(),
         "elgamal": elgamal_section(rng),
         "eddsa": eddsa_section(rng),
         "keccak_address": keccak_section(rng),

@@ -123,6 +123,47 @@ def test_elgamal_vectors(engine):
     assert not st.any() and all(ints(rte[i]) == I(e["rte"]) for i, e in enumerate(tr))
     back, st = engine.rte_to_te(rte)
     assert all(ints(back[i]) == I(e["te"]) for i, e in enumerate(tr))
+    # GCP_COORDS_TE: iden3 coordinates at the boundary
+    import gnark_crypto_primitives_b200 as g
+    tc = eg["te_coords"]
+    nb, nf = len(tc["ballots_te"]), len(tc["ballots_te"][0])
+    k = elems([int(x) for row in tc["k"] for x in row])
+    m = elems([int(x) for row in tc["m"] for x in row])
+    pk_te = elems(I(tc["pk_te"])).reshape(2, 32)
+    ct, st = engine.elgamal_encrypt(pk_te, k, m, fmt=g.COORDS_TE)
+    want = [I(c) for row in tc["ballots_te"] for c in row]
+    assert not st.any() and [ints(c) for c in ct] == want
+    tal, st = engine.elgamal_tally(ct.reshape(nb, nf, 4, 32), fmt=g.COORDS_TE)
+    assert not st.any() and [ints(t) for t in tal] == [I(c) for c in tc["tally_te"]]
+    tal2, st = engine.elgamal_encrypt_tally(pk_te, k.reshape(nb, nf, 32), m.reshape(nb, nf, 32), fmt=g.COORDS_TE)
+    assert not st.any() and np.array_equal(tal, tal2)
+
+
+def test_smt_leaf_hash_and_arbo_vectors(engine):
+    doc = DOC["smt_leaf_hash"]
+    n_levels = doc["n_levels"]
+    for nv in sorted({len(e["values"]) for e in doc["hash1"]}):
+        rows = [e for e in doc["hash1"] if len(e["values"]) == nv]
+        vals = elems([int(x) for e in rows for x in e["values"]]).reshape(len(rows), nv, 32) if nv else \
+            np.zeros((len(rows), 0, 32), np.uint8)
+        out, st = engine.smt_leaf_hash(elems(int(e["key"]) for e in rows), vals)
+        assert not st.any() and ints(out) == [int(e["hash"]) for e in rows]
+    vc = doc["verifier_with_leaf_hash"]
+    n = len(vc)
+    flags, status, roots = engine.smt_verify_with_leaf_hash(
+        elems(int(c["root"]) for c in vc), elems([int(x) for c in vc for x in c["siblings"]]).reshape(n, n_levels, 32),
+        elems(int(c["key"]) for c in vc), elems(int(c["hash1_new"]) for c in vc),
+        old_keys=elems(int(c["old_key"]) for c in vc), hash1_old=elems(int(c["hash1_old"]) for c in vc),
+        is_old0=np.array([c["is_old0"] for c in vc], np.uint8), fnc=np.array([c["fnc"] for c in vc], np.uint8), want_roots=True)
+    assert [int(f) for f in flags] == [c["flag"] for c in vc] and [int(x) for x in status] == [c["status"] for c in vc]
+    assert ints(roots) == [int(c["level0"]) for c in vc]
+    pa = doc["processor_arbo"]
+    u8 = lambda name: np.array([c[name] for c in pa], np.uint8)
+    out, st = engine.smt_process_arbo(elems(int(c["old_root"]) for c in pa), [bytes.fromhex(c["packed"]) for c in pa], n_levels,
+                                      elems(int(c["old_key"]) for c in pa), elems(int(c["old_value"]) for c in pa), u8("is_old0"),
+                                      elems(int(c["new_key"]) for c in pa), elems(int(c["new_value"]) for c in pa), u8("fnc0"),
+                                      u8("fnc1"))
+    assert not st.any() and ints(out) == [int(c["new_root"]) for c in pa]
 
 
 def test_eddsa_keccak_mimc7_vectors(engine):
