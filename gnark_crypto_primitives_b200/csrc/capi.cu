@@ -1032,7 +1032,7 @@ static int smt_process_dev_locked(gcp_ctx* ctx, int n_levels, size_t n, const vo
                                   const void* d_old_keys, const void* d_old_values, const uint8_t* d_is_old0,
                                   const void* d_new_keys, const void* d_new_values, const uint8_t* d_fnc0,
                                   const uint8_t* d_fnc1, void* d_new_roots, uint8_t* d_status, int fmt, cudaStream_t st,
-                                  int leaf_form) {
+                                  int leaf_form, int scratch_slot) {
   int rc = smt_process_check(ctx, n_levels, n, d_old_roots, d_siblings, d_old_keys, d_old_values, d_is_old0, d_new_keys,
                              d_new_values, d_fnc0, d_fnc1, d_new_roots, d_status, fmt);
   if (rc != GCP_OK || n == 0) return rc;
@@ -1052,8 +1052,28 @@ static int smt_process_dev_locked(gcp_ctx* ctx, int n_levels, size_t n, const vo
   a.status = d_status;
   a.mont = fmt;
   a.leaf_hash_form = leaf_form;
-  CU(launch_smt_process(a, st), "smt process kernel");
-  ctx->launches++;
+  // from 1024 transitions up: the verifier's pipeline (scan, sort by path length, prep, two-chain path kernel); below that
+  // (and with GCP_B200_PROCESS_NAIVE set, for measurements) one thread per transition
+  static const bool naive = getenv("GCP_B200_PROCESS_NAIVE") != nullptr;
+  if (n < 1024 || naive) {
+    CU(launch_smt_process(a, nullptr, nullptr, nullptr, ctx->sm_count, st), "smt process kernel");
+    ctx->launches++;
+    return GCP_OK;
+  }
+  if (n > 0xffffffffull) return ctx->fail(GCP_ERR_BAD_ARG, "at most 2^32 - 1 transitions per call");
+  const size_t base_bytes = smt_scratch_bytes(n);
+  char* scratch = (char*)ctx->buf(scratch_slot, base_bytes + n * 32);
+  if (!scratch) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed (smt scratch)");
+  const size_t off_perm = n * 32, off_lidx = off_perm + n * 4, off_info = off_lidx + ((n * 2 + 15) & ~(size_t)15);
+  const size_t off_hist = off_info + ((n + 15) & ~(size_t)15), off_cur = off_hist + 1024;
+  SmtScratch sc;
+  sc.perm = (u32*)(scratch + off_perm);
+  sc.lidx = (u16*)(scratch + off_lidx);
+  sc.info = (u8*)(scratch + off_info);
+  sc.hist = (u32*)(scratch + off_hist);
+  sc.cursor = (u32*)(scratch + off_cur);
+  CU(launch_smt_process(a, &sc, (u32*)scratch, (u32*)(scratch + base_bytes), ctx->sm_count, st), "smt process kernels");
+  ctx->launches += 5;
   return GCP_OK;
 }
 
@@ -1065,7 +1085,7 @@ int gcp_smt_process_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_old_
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   return smt_process_dev_locked(ctx, n_levels, n, d_old_roots, d_siblings, d_old_keys, d_old_values, d_is_old0, d_new_keys,
-                                d_new_values, d_fnc0, d_fnc1, d_new_roots, d_status, fmt, (cudaStream_t)stream, 0);
+                                d_new_values, d_fnc0, d_fnc1, d_new_roots, d_status, fmt, (cudaStream_t)stream, 0, 103);
 }
 
 int gcp_smt_process_with_leaf_hash_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_old_roots, const void* d_siblings,
@@ -1076,7 +1096,7 @@ int gcp_smt_process_with_leaf_hash_dev(gcp_ctx* ctx, int n_levels, size_t n, con
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device), "cudaSetDevice");
   return smt_process_dev_locked(ctx, n_levels, n, d_old_roots, d_siblings, d_old_keys, d_hash1_old, d_is_old0, d_new_keys,
-                                d_hash1_new, d_fnc0, d_fnc1, d_new_roots, d_status, fmt, (cudaStream_t)stream, 1);
+                                d_hash1_new, d_fnc0, d_fnc1, d_new_roots, d_status, fmt, (cudaStream_t)stream, 1, 103);
 }
 
 // Host-buffer processor: dense sibling rows, or (siblings == NULL) arbo packed proofs expanded on the device.
@@ -1138,7 +1158,7 @@ static int smt_process_host(gcp_ctx* ctx, int n_levels, size_t n, const void* ol
     }
     for (int q = 0; q < 5; q++) GCP_TRY(h2d_copy(ctx, d_e[q], (const char*)src_e[q] + off * 32, m * 32, st));
     int rc = smt_process_dev_locked(ctx, n_levels, m, d_e[0], d_sib, d_e[1], d_e[2], d_b[0], d_e[3], d_e[4], d_b[1], d_b[2],
-                                    d_out, d_b[3], fmt, st, leaf_form);
+                                    d_out, d_b[3], fmt, st, leaf_form, b + 12);
     if (rc != GCP_OK) return rc;
     if (is_packed) {
       // a proof arbo.UnpackSiblings rejects never reaches the gadget: status 7, new root 0 (flags: the status array twice)

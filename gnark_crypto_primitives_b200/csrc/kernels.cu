@@ -3,6 +3,7 @@
 // the C ABI, chunking and memory pools are in capi.cu.
 #include "fr.cuh"
 #include "poseidon.cuh"
+#include "poseidon_lanes.cuh"
 #include "smt.cuh"
 #include "elgamal.cuh"
 #include "keccak.cuh"
@@ -201,6 +202,14 @@ __global__ void __launch_bounds__(128) poseidon_generic_kernel(PoseidonTable tab
   store_fr(out + (item * g.out_item_stride + chunk) * 8, h);
 }
 
+// batches up to this many two-input hashes take the three-lanes-per-hash latency layout (one warp per scheduler partition up
+// to 592 x 10 hashes; beyond ~4 k the throughput layout wins); GCP_B200_NO_LANES=1 keeps the one-thread layout (measurements)
+constexpr size_t POSEIDON_LANES_MAX = 4096;
+static bool poseidon_lanes_disabled() {
+  static const bool off = getenv("GCP_B200_NO_LANES") != nullptr;
+  return off;
+}
+
 cudaError_t launch_poseidon(const PoseidonTable& tab, const u32* in, u32* out, u8* status, size_t n_items,
                             int chunks_per_item, size_t in_item_stride, size_t in_chunk_stride,
                             size_t out_item_stride, int in_mont, int out_mont, int final_level,
@@ -216,6 +225,14 @@ cudaError_t launch_poseidon(const PoseidonTable& tab, const u32* in, u32* out, u
   g.final_level = final_level;
   if (g.total == 0) return cudaSuccess;
   unsigned blocks = (unsigned)((g.total + 127) / 128);
+  if (tab.t == 3 && g.total <= POSEIDON_LANES_MAX && !poseidon_lanes_disabled()) {
+    // small batch: the latency layout, three lanes per hash (poseidon_lanes.cuh); 10 hashes per one-warp block
+    HashGeomLanes gl{g.total, g.chunks_per_item, g.in_item_stride, g.in_chunk_stride, g.out_item_stride, g.in_mont, g.out_mont,
+                     g.final_level};
+    poseidon_hash2_lanes_kernel<<<(unsigned)((g.total + PL_GROUPS_PER_WARP - 1) / PL_GROUPS_PER_WARP), 32, 0, stream>>>(
+        tab.C, in, out, status, gl);
+    return cudaGetLastError();
+  }
   if (tab.t == 3)
     poseidon_fixed_kernel<3><<<blocks, 128, 0, stream>>>(in, out, status, g);
   else if (tab.t == 4)
@@ -275,9 +292,36 @@ size_t smt_path_wave_items(int sm_count) {
   return wave_items(smt_path_kernel, SMT_WARPS * 32, 0, sm_count, 4);
 }
 
-cudaError_t launch_smt_process(const SmtProcessArgs& a, cudaStream_t stream) {
+// scratch: the verifier's (perm, lidx, info, hist, cursor) plus two accumulators per item; nullptr: thread-per-proof form
+cudaError_t launch_smt_process(const SmtProcessArgs& a, const SmtScratch* sc, u32* acc_old, u32* acc_new, int sm_count,
+                               cudaStream_t stream) {
   if (a.n == 0) return cudaSuccess;
-  smt_process_kernel<<<(unsigned)((a.n + 127) / 128), 128, 0, stream>>>(a);
+  if (!sc) {
+    smt_process_kernel<<<(unsigned)((a.n + 127) / 128), 128, 0, stream>>>(a);
+    return cudaGetLastError();
+  }
+  cudaError_t e = cudaMemsetAsync(sc->hist, 0, 256 * sizeof(u32), stream);
+  if (e != cudaSuccess) return e;
+  e = launch_smt_scan(a.siblings, a.n, a.n_levels, sc->lidx, sc->info, sc->hist, sm_count, stream);
+  if (e != cudaSuccess) return e;
+  smt_sort_prefix_kernel<<<1, 256, 0, stream>>>(sc->hist, sc->cursor, (u32)a.n);
+  smt_sort_scatter_kernel<<<(unsigned)((a.n + 255) / 256), 256, 0, stream>>>(sc->lidx, a.n, sc->cursor, sc->perm);
+  smt_process_prep_kernel<<<(unsigned)((a.n + 127) / 128), 128, 0, stream>>>(a, sc->lidx, sc->info, acc_old, acc_new);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  // 4 resident blocks per SM (128 registers, ~80 B of spills) or 3 (148 registers, none): GCP_B200_PROC_BLOCKS, for measurements
+  static const int min_blocks = [] {
+    const char* env = getenv("GCP_B200_PROC_BLOCKS");
+    return (env && atoi(env) == 3) ? 3 : 4;
+  }();
+  const unsigned grid = (unsigned)((a.n + SMT_WARPS * 32 - 1) / (SMT_WARPS * 32));
+  if (min_blocks == 3) {
+    cudaFuncSetAttribute(smt_process_path_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    smt_process_path_kernel<3><<<grid, SMT_WARPS * 32, 0, stream>>>(a, sc->perm, sc->lidx, acc_old, acc_new);
+  } else {
+    cudaFuncSetAttribute(smt_process_path_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    smt_process_path_kernel<4><<<grid, SMT_WARPS * 32, 0, stream>>>(a, sc->perm, sc->lidx, acc_old, acc_new);
+  }
   return cudaGetLastError();
 }
 

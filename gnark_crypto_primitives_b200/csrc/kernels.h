@@ -71,13 +71,6 @@ struct SmtProcessArgs {
   int leaf_hash_form;     // ProcessorWithLeafHash (processor.go:16): `new_values` / `old_values` hold hash1New / hash1Old
 };
 
-cudaError_t launch_to_mont(u32* d_elems, size_t n, cudaStream_t stream);
-cudaError_t upload_const_tables(const u32* d_t3, const u32* d_t4, cudaStream_t stream);
-cudaError_t launch_poseidon(const PoseidonTable& tab, const u32* in, u32* out, u8* status, size_t n_items,
-                            int chunks_per_item, size_t in_item_stride, size_t in_chunk_stride,
-                            size_t out_item_stride, int in_mont, int out_mont, int final_level,
-                            cudaStream_t stream);
-double launch_imad_probe(u32* d_out, int blocks, u32 seed, cudaStream_t stream);
 // scratch: perm (n x u32), lidx (n x u16), info (n x u8), hist (256 x u32), cursor (256 x u32)
 struct SmtScratch {
   u32* perm;
@@ -86,10 +79,20 @@ struct SmtScratch {
   u32* hist;
   u32* cursor;
 };
+
+cudaError_t launch_to_mont(u32* d_elems, size_t n, cudaStream_t stream);
+cudaError_t upload_const_tables(const u32* d_t3, const u32* d_t4, cudaStream_t stream);
+cudaError_t launch_poseidon(const PoseidonTable& tab, const u32* in, u32* out, u8* status, size_t n_items,
+                            int chunks_per_item, size_t in_item_stride, size_t in_chunk_stride,
+                            size_t out_item_stride, int in_mont, int out_mont, int final_level,
+                            cudaStream_t stream);
+double launch_imad_probe(u32* d_out, int blocks, u32 seed, cudaStream_t stream);
 cudaError_t launch_smt_verify(const SmtArgs& a, const SmtScratch& sc, int sm_count, cudaStream_t stream);
 cudaError_t launch_smt_scan(const u32* siblings, size_t n, int n_levels, u16* lidx, u8* info, u32* hist, int sm_count,
                             cudaStream_t stream);
-cudaError_t launch_smt_process(const SmtProcessArgs& a, cudaStream_t stream);
+// sc + acc_old/acc_new (n x 8 words each): the scan / sort / prep / path pipeline; sc == nullptr: one thread per proof
+cudaError_t launch_smt_process(const SmtProcessArgs& a, const SmtScratch* sc, u32* acc_old, u32* acc_new, int sm_count,
+                               cudaStream_t stream);
 // Hash1 rows (tree/smt/hash.go:10-19): rows[i] = (key_i, values_i[0..n_values), 1), n x (n_values + 2) elements, in the
 // caller's element format; the hash itself is launch_poseidon with arity n_values + 2
 cudaError_t launch_smt_leaf_rows(const u32* keys, const u32* values, int n_values, size_t n, u32* rows, int mont,

@@ -578,6 +578,216 @@ __global__ void __launch_bounds__(128) smt_process_kernel(SmtProcessArgs a) {
   a.status[idx] = st;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Processor on the verifier's pipeline: scan (HBM-bound, lidx / last-zero / canonical per proof) -> counting sort by
+// lidx -> prep (validation, leaf hashes, the levels below the insertion level, which need no sibling) -> path (both
+// chains folded over the sibling levels by warps of equal path length, siblings staged with cp.async).  The
+// thread-per-proof kernel above re-read every sibling twice with 32-byte strided loads and diverged over the path
+// length; it stays as the reference form for tiny batches (launch_smt_process picks).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) smt_process_prep_kernel(SmtProcessArgs a, const u16* __restrict__ lidx_arr,
+                                                               const u8* __restrict__ info_arr, u32* __restrict__ acc_old_out,
+                                                               u32* __restrict__ acc_new_out) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.n) return;
+  const int n = a.n_levels;
+  const u32 fnc0 = a.fnc0[idx], fnc1 = a.fnc1[idx], is0 = a.is_old0[idx];
+  u8 st = GCP_STATUS_OK;
+  if ((fnc0 | fnc1 | is0) > 1u) st = GCP_STATUS_NOT_BOOLEAN;
+  const bool enabled = (fnc0 | fnc1) != 0;
+  bool canon = true;
+  u32 okey[8], oval[8], nkey[8], nval[8], oroot[8];
+  load_elem(okey, canon, a.old_keys + idx * 8, a.mont);
+  load_elem(oval, canon, a.old_values + idx * 8, a.mont);
+  load_elem(nkey, canon, a.new_keys + idx * 8, a.mont);
+  load_elem(nval, canon, a.new_values + idx * 8, a.mont);
+  load_fr(oroot, a.old_roots + idx * 8);
+  canon = canon && fr_is_canonical(oroot);
+  u32 ok_int[8], nk_int[8];
+  key_integer(ok_int, a.old_keys + idx * 8, a.mont);
+  key_integer(nk_int, a.new_keys + idx * 8, a.mont);
+  const u32 info = info_arr[idx];
+  const int lidx = (int)lidx_arr[idx];
+  canon = canon && (info & SMT_INFO_CANONICAL) != 0;
+  const bool last_zero = (info & SMT_INFO_LAST_ZERO) != 0;
+  if (st == GCP_STATUS_OK && !canon) st = GCP_STATUS_NONCANONICAL;
+  if (st == GCP_STATUS_OK && !(key_in_range(ok_int, n) && key_in_range(nk_int, n))) st = GCP_STATUS_KEY_RANGE;
+  if (st == GCP_STATUS_OK && enabled && !last_zero) st = GCP_STATUS_ASSERTION;  // LevIns (lev_ins.go:16-20)
+  const bool keys_equal = eq256(ok_int, nk_int);
+  if (st == GCP_STATUS_OK && fnc0 == 0u && fnc1 == 1u && !keys_equal) st = GCP_STATUS_ASSERTION;  // processor.go:64-70
+  int jterm = lidx;
+  if (st == GCP_STATUS_OK && enabled && fnc0 == 1u && is0 == 0u) {
+    jterm = -1;
+    for (int i = lidx; i < n; i++) {
+      if (((ok_int[i >> 5] ^ nk_int[i >> 5]) >> (i & 31)) & 1u) {
+        jterm = i;
+        break;
+      }
+    }
+    if (jterm < 0) st = GCP_STATUS_ASSERTION;  // no terminal state: processor.go:47
+  }
+  u32 acc_old[8], acc_new[8];
+  fr_set_zero(acc_old);
+  fr_set_zero(acc_new);
+  if (st == GCP_STATUS_OK && enabled) {
+    u32 h1old[8], h1new[8], one[8];
+#pragma unroll
+    for (int l = 0; l < 8; l++) one[l] = FR_ONE[l];
+    if (a.leaf_hash_form) {
+      fr_copy(h1old, oval);
+      fr_copy(h1new, nval);
+    }
+#pragma unroll 1
+    for (int h = 0; h < 2 && !a.leaf_hash_form; h++) {
+      u32 kk[8], vv[8], res[8];
+#pragma unroll
+      for (int l = 0; l < 8; l++) {
+        kk[l] = h ? nkey[l] : okey[l];
+        vv[l] = h ? nval[l] : oval[l];
+      }
+      poseidon_hash3(res, kk, vv, one);
+#pragma unroll
+      for (int l = 0; l < 8; l++) {
+        if (h)
+          h1new[l] = res[l];
+        else
+          h1old[l] = res[l];
+      }
+    }
+    const bool is_upd = (fnc0 == 0u), is_old0 = (fnc0 == 1u && is0 == 1u);
+    fr_copy(acc_new, h1new);
+    if (!is_old0) fr_copy(acc_old, h1old);  // old0: the old chain starts from the empty slot (0)
+    if (!is_upd && !is_old0) {
+      // new1 at jterm: new = H(sw(b; hash1New, hash1Old)); bot on jterm-1 .. lidx: new = H(sw(b; new, 0)); the old chain
+      // keeps hash1Old through these levels
+      for (int i = jterm; i >= lidx; i--) {
+        const u32 bit = (nk_int[i >> 5] >> (i & 31)) & 1u;
+        u32 other[8], lft[8], rgt[8];
+        if (i == jterm)
+          fr_copy(other, h1old);
+        else
+          fr_set_zero(other);
+#pragma unroll
+        for (int l = 0; l < 8; l++) {
+          lft[l] = bit ? other[l] : acc_new[l];
+          rgt[l] = bit ? acc_new[l] : other[l];
+        }
+        poseidon_hash2(acc_new, lft, rgt);
+      }
+    }
+  }
+  store_fr(acc_old_out + idx * 8, acc_old);
+  store_fr(acc_new_out + idx * 8, acc_new);
+  a.status[idx] = st;
+}
+
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(SMT_WARPS * 32, MIN_BLOCKS) smt_process_path_kernel(SmtProcessArgs a, const u32* __restrict__ perm,
+                                                                       const u16* __restrict__ lidx_arr,
+                                                                       const u32* __restrict__ acc_old_in,
+                                                                       const u32* __restrict__ acc_new_in) {
+  __shared__ __align__(16) u32 tiles[2][SMT_WARPS][32 * SMT_ROW_WORDS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t warp_base = (size_t)blockIdx.x * blockDim.x + warp * 32;
+  if (warp_base >= a.n) return;
+  const bool in_range = warp_base + lane < a.n;
+  const size_t idx = in_range ? perm[warp_base + lane] : 0;
+  const int n = a.n_levels;
+  u8 st = in_range ? a.status[idx] : (u8)GCP_STATUS_NONCANONICAL;
+  const u32 fnc0 = a.fnc0[idx], fnc1 = a.fnc1[idx];
+  const bool enabled = (fnc0 | fnc1) != 0;
+  const int lidx = in_range ? (int)lidx_arr[idx] : 0;
+  const bool live = in_range && st == GCP_STATUS_OK && enabled;
+  u32 acc[2][8];  // [0] old chain, [1] new chain
+  load_fr(acc[0], acc_old_in + idx * 8);
+  load_fr(acc[1], acc_new_in + idx * 8);
+  u32 key[8];
+  key_integer(key, a.new_keys + idx * 8, a.mont);
+  int warp_top = live ? lidx : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) warp_top = max(warp_top, __shfl_xor_sync(0xffffffffu, warp_top, o));
+  const int first_chunk = (warp_top + SMT_CH - 1) / SMT_CH - 1;
+  if (first_chunk >= 0) smt_stage_chunk(tiles[first_chunk & 1][warp], a.siblings, (u32)idx, live, n, first_chunk, lane);
+#pragma unroll 1
+  for (int c = first_chunk; c >= 0; c--) {
+    if (c > 0) {
+      smt_stage_chunk(tiles[(c - 1) & 1][warp], a.siblings, (u32)idx, live, n, c - 1, lane);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+    const u32* row = tiles[c & 1][warp] + lane * SMT_ROW_WORDS;
+    const int hi = min(n, c * SMT_CH + SMT_CH) - 1;
+#pragma unroll 1
+    for (int i = hi; i >= c * SMT_CH; i--) {
+      if (!live || i >= lidx) continue;
+      u32 s[8];
+      {
+        const uint4* q = reinterpret_cast<const uint4*>(row + (i - c * SMT_CH) * 8);
+        uint4 v0 = q[0], v1 = q[1];
+        u32 x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        if (a.mont)
+          fr_copy(s, x);
+        else
+          fr_to_mont(s, x);
+      }
+      const u32 bit = (key[i >> 5] >> (i & 31)) & 1u;
+      // top level: old_i = H(sw(b; old_{i+1}, sib)), new_i = H(sw(b; new_{i+1}, sib)); one inlined copy of Hash2
+#pragma unroll 1
+      for (int h = 0; h < 2; h++) {
+        u32 lft[8], rgt[8];
+#pragma unroll
+        for (int l = 0; l < 8; l++) {
+          const u32 child = h ? acc[1][l] : acc[0][l];
+          lft[l] = bit ? s[l] : child;
+          rgt[l] = bit ? child : s[l];
+        }
+        u32 res[8];
+        poseidon_hash2(res, lft, rgt);
+#pragma unroll
+        for (int l = 0; l < 8; l++) {
+          if (h)
+            acc[1][l] = res[l];
+          else
+            acc[0][l] = res[l];
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (!in_range) return;
+  u32 out[8];
+  fr_set_zero(out);
+  if (st == GCP_STATUS_OK) {
+    if (!enabled) {
+      load_fr(out, a.old_roots + idx * 8);  // nop: newRoot = oldRoot
+    } else {
+      u32 old_c[8], new_c[8], oroot[8];
+      load_fr(oroot, a.old_roots + idx * 8);
+      if (a.mont) {
+        fr_copy(old_c, acc[0]);
+        fr_copy(new_c, acc[1]);
+        fr_canon(old_c);
+        fr_canon(new_c);
+      } else {
+        fr_from_mont(old_c, acc[0]);
+        fr_from_mont(new_c, acc[1]);
+      }
+      const bool both = (fnc0 & fnc1) != 0;
+      const bool match = both ? eq256(new_c, oroot) : eq256(old_c, oroot);  // ForceEqualIfEnabled, processor.go:60
+      if (!match) {
+        st = GCP_STATUS_ASSERTION;
+      } else {
+#pragma unroll
+        for (int l = 0; l < 8; l++) out[l] = both ? old_c[l] : new_c[l];
+      }
+    }
+  }
+  store_fr(a.new_roots + idx * 8, out);
+  a.status[idx] = st;
+}
+
 // Hash1 input rows (tree/smt/hash.go:10-19): (key, values..., 1), one thread per element
 __global__ void smt_leaf_rows_kernel(const u32* __restrict__ keys, const u32* __restrict__ values, int n_values, size_t n,
                                      u32* __restrict__ rows, int mont) {

@@ -78,6 +78,31 @@ if "process" in SECTIONS or "verify" in SECTIONS:
                  status6_frac=float((stt == 6).float().mean().item()))
         del sib
 
+if "process" in SECTIONS:
+    # ragged path lengths (census-like: L ~ U[20,28], ~10 % interior zeros): updates with a matching old root, so status 0
+    from bench import make_census_like
+    n = 1 << 18
+    c = make_census_like(torch, eng, n, host_forms=False)
+    c["vals"][::16, 0] ^= 2                                   # undo the bench's corruption: every proof valid
+    z = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    o = torch.ones(n, dtype=torch.uint8, device="cuda")
+    nv = rand_elems(torch, n, gen)
+    out = torch.empty((n, 8), dtype=torch.int32, device="cuda")
+    stt = torch.empty(n, dtype=torch.uint8, device="cuda")
+    flags = torch.empty(n, dtype=torch.uint8, device="cuda")
+
+    def run():
+        rc = eng._lib.gcp_smt_process_dev(eng._h, N_LEVELS, n, _dptr(c["roots"]), _dptr(c["sib"]), _dptr(c["keys"]), _dptr(c["vals"]),
+                                          _dptr(z), _dptr(c["keys"]), _dptr(nv), _dptr(z), _dptr(o), _dptr(out), _dptr(stt), 0,
+                                          eng._stream(st))
+        assert rc == 0
+    ms = timeit(run)
+    ok = float((stt == 0).float().mean().item())
+    msv = timeit(lambda: eng.smt_verify_dev(N_LEVELS, n, c["roots"], False, c["sib"], c["keys"], c["vals"], flags, stt, stream=st))
+    emit(kernel="smt_process_update_census_like", n=n, mean_path=c["mean_levels"], ms=ms, per_s=n / ms * 1e3, status0_frac=ok,
+         verifier_per_s=n / msv * 1e3, ratio_to_verifier=msv / ms)
+    del c
+
 if "hashes" in SECTIONS:
     n = 1 << 22
     inp = rand_elems(torch, 2 * n, gen)
@@ -86,7 +111,7 @@ if "hashes" in SECTIONS:
     ms = timeit(lambda: eng.poseidon_hash_dev(inp, 2, n, dig, stt, stream=st))
     emit(kernel="poseidon_hash2", n=n, ms=ms, per_s=n / ms * 1e3)
     del inp
-    for nsmall in (1024,):
+    for nsmall in (256, 1024, 4096, 8192):
         a = np.random.default_rng(1).integers(0, 256, size=(nsmall, 2, 32), dtype=np.uint8)
         a[:, :, 31] &= 0x1F
         eng.poseidon_hash(a)
@@ -95,7 +120,13 @@ if "hashes" in SECTIONS:
             t0 = time.perf_counter()
             eng.poseidon_hash(a)
             ts.append(time.perf_counter() - t0)
-        emit(kernel="poseidon_hash2_host_call", n=nsmall, us=float(np.median(ts)) * 1e6)
+        d_in = torch.from_numpy(a).cuda()
+        d_out = torch.empty((nsmall, 32), dtype=torch.uint8, device="cuda")
+        d_st = torch.empty(nsmall, dtype=torch.uint8, device="cuda")
+        ms = timeit(lambda: eng.poseidon_hash_dev(d_in, 2, nsmall, d_out, d_st, stream=st), iters=20, warm=3)
+        import os
+        emit(kernel="poseidon_hash2_host_call", n=nsmall, us=float(np.median(ts)) * 1e6, kernel_only_us=ms * 1e3,
+             lanes_layout=(os.environ.get("GCP_B200_NO_LANES") is None and nsmall <= 4096))
 
 if "add" in SECTIONS or "tally" in SECTIONS:
     nf = 8

@@ -169,16 +169,13 @@ def test_arbo_post_insert_proofs(engine):
     assert int(st3[0]) == osmt.STATUS_MALFORMED and ints(out3) == [0]
 
 
-@pytest.mark.parametrize("seed", [1, 2])
-def test_random_differential_with_mutations(engine, seed):
-    """Seeded differential run against the literal oracle: transitions of a growing tree at an odd level count, each
-    with a random function code and a random mutation (selectors outside {0,1}, elements at and past r, keys past 2^n,
-    wrong old roots, swapped or corrupted siblings, siblings[n-1] != 0)."""
+def differential_cases(seed, n_levels, steps=60):
+    """Transitions of a growing tree, each with a random function code and a random mutation (selectors outside {0,1},
+    elements at and past r, keys past 2^n, wrong old roots, swapped or corrupted siblings, siblings[n-1] != 0)."""
     rng = random.Random(4000 + seed)
-    n_levels = [19, 45][seed - 1]
     tree = osmt.Tree(n_levels)
     cases = []
-    for step in range(60):
+    for step in range(steps):
         k = rng.getrandbits(n_levels)
         v = rng.randrange(R)
         p = tree.gen_proof(k)
@@ -203,7 +200,64 @@ def test_random_differential_with_mutations(engine, seed):
         elif mut == 6:
             c["is_old0"] ^= 1
         cases.append(c)
+    return cases
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_random_differential_with_mutations(engine, seed):
+    """Seeded differential run against the literal oracle at an odd level count."""
+    n_levels = [19, 45][seed - 1]
+    cases = differential_cases(seed, n_levels)
     roots, status, want = run(engine, cases, n_levels)
     for i, w in enumerate(want):
         assert (roots[i], status[i]) == w, (i, cases[i])
     assert len({s for _, s in want}) >= 3
+
+
+def test_pipeline_form_on_a_large_mixed_batch(engine):
+    """From 1024 transitions up the processor runs on the verifier's pipeline (scan, sort by path length, prep kernel,
+    two-chain path kernel with staged siblings).  A shuffled batch of 1 500 transitions - honest inserts / updates /
+    deletes / nops of a growing tree and every kind of mutated one, path lengths from 0 up - must give exactly the
+    oracle's (new root, status) per item, i.e. what the one-thread-per-transition kernel gives on the same items."""
+    n_levels = 37
+    base = differential_cases(7, n_levels, steps=150)
+    # honest transitions of a second tree, incl. deletes (an insert read backwards) and inserts below a shared prefix
+    rng = random.Random(99)
+    tree = osmt.Tree(n_levels)
+    for step in range(100):
+        k = rng.getrandbits(n_levels) if step % 5 else (rng.getrandbits(6) | (1 << 20))   # clustered keys: deep splits
+        v = rng.randrange(R)
+        p = tree.gen_proof(k)
+        if p["exists"]:
+            continue
+        old_root = tree.root()
+        tree.add(k, v)
+        ins = dict(old_root=old_root, siblings=p["siblings"], old_key=p["old_key"], old_value=p["old_value"],
+                   is_old0=p["is_old0"], new_key=k, new_value=v, fnc0=1, fnc1=0)
+        base.append(ins)
+        base.append(dict(ins, old_root=tree.root(), fnc1=1))                              # delete
+    want_base = [osmt.processor(c["old_root"], c["siblings"], c["old_key"], c["old_value"], c["is_old0"], c["new_key"],
+                                c["new_value"], c["fnc0"], c["fnc1"]) for c in base]
+    assert sum(1 for w in want_base if w[1] == 0) > 150 and len({w[1] for w in want_base}) >= 4
+    order = [rng.randrange(len(base)) for _ in range(1500)]
+    cases = [base[i] for i in order]
+    n = len(cases)
+    sib = elems([s for c in cases for s in c["siblings"]]).reshape(n, n_levels, 32)
+    out, st = engine.smt_process(elems(c["old_root"] for c in cases), sib, elems(c["old_key"] for c in cases),
+                                 elems(c["old_value"] for c in cases), np.array([c["is_old0"] for c in cases], np.uint8),
+                                 elems(c["new_key"] for c in cases), elems(c["new_value"] for c in cases),
+                                 np.array([c["fnc0"] for c in cases], np.uint8), np.array([c["fnc1"] for c in cases], np.uint8))
+    got = list(zip(ints(out), [int(x) for x in st]))
+    assert got == [want_base[i] for i in order]
+    # the same batch in gnark-crypto's Montgomery memory
+    import gnark_crypto_primitives_b200 as g
+    rm = (1 << 256) % R
+    mont = lambda vals: elems((int(v) * rm) % R if int(v) < R else int(v) for v in vals)
+    out_m, st_m = engine.smt_process(mont(c["old_root"] for c in cases), mont(s for c in cases for s in c["siblings"]).reshape(n, n_levels, 32),
+                                     mont(c["old_key"] for c in cases), mont(c["old_value"] for c in cases),
+                                     np.array([c["is_old0"] for c in cases], np.uint8), mont(c["new_key"] for c in cases),
+                                     mont(c["new_value"] for c in cases), np.array([c["fnc0"] for c in cases], np.uint8),
+                                     np.array([c["fnc1"] for c in cases], np.uint8), fmt=g.FMT_MONTGOMERY)
+    ok = [i for i in range(n) if got[i][1] == 0]
+    assert [int(st_m[i]) for i in ok] == [0] * len(ok)
+    assert [ints(out_m[i:i + 1])[0] for i in ok] == [(got[i][0] * rm) % R for i in ok]
