@@ -139,6 +139,24 @@ struct gcp_ctx {
   }
 };
 
+// The thread's current CUDA device is the caller's business (torch, another library, a Go thread that also drives other
+// GPUs): every entry point selects its context's device for the duration of the call and puts the previous one back.
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) {
+      cudaGetLastError();
+      prev = -1;
+    }
+    ok = cudaSetDevice(device) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 #define CU(call, what)                                   \
   do {                                                   \
     cudaError_t e_ = (call);                             \
@@ -337,7 +355,7 @@ uint64_t gcp_ctx_launch_count(const gcp_ctx* ctx) { return ctx ? ctx->launches :
 
 void gcp_ctx_destroy(gcp_ctx* ctx) {
   if (!ctx) return;
-  cudaSetDevice(ctx->device);
+  DeviceGuard device_guard(ctx->device);
   for (auto& s : ctx->stream)
     if (s) {
       cudaStreamSynchronize(s);
@@ -439,7 +457,8 @@ int gcp_ctx_create(int device, const char* constants_path, gcp_ctx** out) {
     return code;
   };
   cudaError_t e;
-  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(ctx->cuda_fail(e, "cudaSetDevice"));
+  DeviceGuard device_guard(device);
+  if (!device_guard.ok) return bail(ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed"));
   for (auto& s : ctx->stream)
     if ((e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)) != cudaSuccess)
       return bail(ctx->cuda_fail(e, "cudaStreamCreate"));
@@ -544,7 +563,8 @@ int gcp_ctx_create(int device, const char* constants_path, gcp_ctx** out) {
 int gcp_probe_imad_wide(gcp_ctx* ctx, double* wide_mul_per_s) {
   if (!ctx || !wide_mul_per_s) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   int sms = 0;
   CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device), "device attribute");
   const int blocks = sms * 8;
@@ -633,7 +653,8 @@ int gcp_poseidon_hash_dev(gcp_ctx* ctx, const void* d_in, int arity, size_t n, v
                           void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   return poseidon_hash_dev_locked(ctx, d_in, arity, n, d_out, d_status, fmt, (cudaStream_t)stream);
 }
 
@@ -641,7 +662,8 @@ int gcp_poseidon_multihash_dev(gcp_ctx* ctx, const void* d_in, int len, size_t n
                                int fmt, void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   return poseidon_multihash_dev_locked(ctx, d_in, len, n, d_out, d_status, fmt, (cudaStream_t)stream, 0);
 }
 
@@ -650,7 +672,8 @@ static int poseidon_host(gcp_ctx* ctx, const void* in, int len, size_t n, void* 
                          bool multi) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   StreamGuard guard{ctx};
   if (len < 1 || len > (multi ? 4096 : 16))
     return ctx->fail(GCP_ERR_BAD_ARG, multi ? "the maximum number of inputs supported is 4096" : "bad inputs provided");
@@ -765,7 +788,8 @@ int gcp_smt_scan_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_sibling
                      void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   if (n_levels < 2 || n_levels > 253) return ctx->fail(GCP_ERR_BAD_ARG, "n_levels must be in [2, 253]");
   if (n == 0) return GCP_OK;
   if (!d_siblings || !d_lidx || !d_info) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
@@ -782,7 +806,8 @@ int gcp_smt_verify_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_roots
                        int fmt, void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   return smt_verify_dev_locked(ctx, n_levels, n, d_roots, shared_root, d_siblings, d_old_keys, d_old_values, d_is_old0,
                                d_keys, d_values, d_fnc, d_enabled, d_out_flags, d_out_status, d_out_roots, fmt,
                                (cudaStream_t)stream, 2);
@@ -795,7 +820,8 @@ int gcp_smt_verify_with_leaf_hash_dev(gcp_ctx* ctx, int n_levels, size_t n, cons
                                       uint8_t* d_out_status, void* d_out_roots, int fmt, void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   return smt_verify_dev_locked(ctx, n_levels, n, d_roots, shared_root, d_siblings, d_old_keys, d_hash1_old, d_is_old0,
                                d_keys, d_hash1_new, d_fnc, d_enabled, d_out_flags, d_out_status, d_out_roots, fmt,
                                (cudaStream_t)stream, 2, 1);
@@ -821,7 +847,8 @@ int gcp_smt_leaf_hash_dev(gcp_ctx* ctx, const void* d_keys, const void* d_values
                           uint8_t* d_status, int fmt, void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   return smt_leaf_hash_dev_locked(ctx, d_keys, d_values, n_values, n, d_out, d_status, fmt, (cudaStream_t)stream, 100);
 }
 
@@ -829,7 +856,8 @@ int gcp_smt_leaf_hash(gcp_ctx* ctx, const void* keys, const void* values, int n_
                       int fmt) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   StreamGuard guard{ctx};
   if (n_values < 0 || n_values > 14) return ctx->fail(GCP_ERR_BAD_ARG, "bad inputs provided");
   if (n == 0) return check_fmt(ctx, fmt);
@@ -865,7 +893,8 @@ static int smt_verify_host(gcp_ctx* ctx, int n_levels, size_t n, const void* roo
                            int leaf_form = 0) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   StreamGuard guard{ctx};
   const bool is_packed = siblings == nullptr;
   int rc = smt_check_args(ctx, n_levels, n, roots, is_packed ? (const void*)packed : siblings, old_keys, old_values, keys,
@@ -984,7 +1013,8 @@ int gcp_smt_unpack_siblings_dev(gcp_ctx* ctx, int n_levels, size_t n, const uint
                                 const uint64_t* d_offsets, void* d_siblings, uint8_t* d_bad, int fmt, void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   if (n_levels < 2 || n_levels > 253) return ctx->fail(GCP_ERR_BAD_ARG, "n_levels must be in [2, 253]");
   if (fmt != GCP_FMT_CANONICAL && fmt != GCP_FMT_MONTGOMERY) return ctx->fail(GCP_ERR_BAD_ARG, "bad element format");
   if (n == 0) return GCP_OK;
@@ -1083,7 +1113,8 @@ int gcp_smt_process_dev(gcp_ctx* ctx, int n_levels, size_t n, const void* d_old_
                         void* d_new_roots, uint8_t* d_status, int fmt, void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   return smt_process_dev_locked(ctx, n_levels, n, d_old_roots, d_siblings, d_old_keys, d_old_values, d_is_old0, d_new_keys,
                                 d_new_values, d_fnc0, d_fnc1, d_new_roots, d_status, fmt, (cudaStream_t)stream, 0, 103);
 }
@@ -1094,7 +1125,8 @@ int gcp_smt_process_with_leaf_hash_dev(gcp_ctx* ctx, int n_levels, size_t n, con
                                        const uint8_t* d_fnc1, void* d_new_roots, uint8_t* d_status, int fmt, void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   return smt_process_dev_locked(ctx, n_levels, n, d_old_roots, d_siblings, d_old_keys, d_hash1_old, d_is_old0, d_new_keys,
                                 d_hash1_new, d_fnc0, d_fnc1, d_new_roots, d_status, fmt, (cudaStream_t)stream, 1, 103);
 }
@@ -1110,7 +1142,8 @@ static int smt_process_host(gcp_ctx* ctx, int n_levels, size_t n, const void* ol
   if (!ctx) return GCP_ERR_BAD_ARG;
   const bool is_packed = siblings == nullptr;
   std::lock_guard<std::recursive_mutex> call_lk(ctx->mu);  // the scratch slots belong to this call until it returns
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   StreamGuard guard{ctx};
   {
     int rc = smt_process_check(ctx, n_levels, n, old_roots, is_packed ? (const void*)packed : siblings, old_keys,
@@ -1324,7 +1357,8 @@ int gcp_elgamal_fixed_base_mul_dev(gcp_ctx* ctx, const void* d_scalars, size_t n
                                    int fmt, void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   return fixed_base_dev_locked(ctx, d_scalars, n, d_out_points, d_status, fmt, (cudaStream_t)stream, 43);
 }
 
@@ -1332,7 +1366,8 @@ int gcp_elgamal_encrypt_dev(gcp_ctx* ctx, const void* d_pub_key, int pk_per_item
                             size_t n, void* d_out_ct, uint8_t* d_status, int fmt, void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   if (n && !pk_per_item) {
     if (!d_pub_key) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
     int rc = ensure_pk_table(ctx, d_pub_key, true, fmt, (cudaStream_t)stream);
@@ -1345,7 +1380,8 @@ int gcp_elgamal_add_dev(gcp_ctx* ctx, const void* d_a, const void* d_b, size_t n
                         void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   return add_dev_locked(ctx, d_a, d_b, n, d_out, d_status, fmt, (cudaStream_t)stream, 43);
 }
 
@@ -1353,7 +1389,8 @@ int gcp_elgamal_tally_dev(gcp_ctx* ctx, const void* d_ct, size_t n_ballots, int 
                           int fmt, void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   return tally_dev_locked(ctx, d_ct, n_ballots, n_fields, d_out, d_status, fmt, (cudaStream_t)stream, 44);
 }
 
@@ -1387,7 +1424,8 @@ int gcp_elgamal_encrypt_tally_dev(gcp_ctx* ctx, const void* d_pub_key, const voi
                                   void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   int rc = encrypt_tally_check(ctx, d_pub_key, d_k, d_m, n_ballots, n_fields, d_out, d_status, fmt);
   if (rc != GCP_OK) return rc;
   rc = ensure_pk_table(ctx, d_pub_key, true, fmt, (cudaStream_t)stream);
@@ -1436,7 +1474,8 @@ static int encrypt_tally_host(gcp_ctx* ctx, const void* pub_key, const void* k, 
                               void* out, uint8_t* status, int fmt, bool out_on_device) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   StreamGuard guard{ctx};
   int rc = encrypt_tally_check(ctx, pub_key, k, m, n_ballots, n_fields, out, status, fmt);
   if (rc != GCP_OK) return rc;
@@ -1484,7 +1523,8 @@ static int elgamal_host(gcp_ctx* ctx, int kind, const void* pk, int pk_per_item,
                         size_t n, void* out, uint8_t* status, int fmt) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   StreamGuard guard{ctx};
   int rc = check_fmt_points(ctx, fmt);
   if (rc != GCP_OK || n == 0) return rc;
@@ -1559,7 +1599,8 @@ static int ct_elementwise_host(gcp_ctx* ctx, int kind, const uint8_t* sel, const
                                uint8_t* status) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   StreamGuard guard{ctx};
   if (n == 0) return GCP_OK;
   if (!a || !b || !out || !status || (kind == 1 && !sel)) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
@@ -1608,7 +1649,8 @@ static int tally_host(gcp_ctx* ctx, const void* ct, size_t n_ballots, int n_fiel
                       bool out_on_device) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   StreamGuard guard{ctx};
   int rc = check_fmt_points(ctx, fmt);
   if (rc != GCP_OK) return rc;
@@ -1653,7 +1695,8 @@ int gcp_ballot_batch_dev(gcp_ctx* ctx, int n_levels, size_t n_voters, const void
                          void* d_tally, uint8_t* d_tally_status, int fmt, void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   cudaStream_t st = (cudaStream_t)stream;
   int rc = encrypt_tally_check(ctx, d_pub_key, d_k, d_m, n_voters, n_fields, d_tally, d_tally_status, fmt);
   if (rc != GCP_OK) return rc;
@@ -1680,7 +1723,8 @@ static int ballot_batch_host(gcp_ctx* ctx, int n_levels, size_t n_voters, const 
                              bool tally_on_device) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   StreamGuard guard{ctx};
   const bool is_packed = siblings == nullptr;
   const size_t n = n_voters;
@@ -1788,7 +1832,8 @@ int gcp_internal_merge_status_dev(gcp_ctx* ctx, const uint8_t* d_part_status, in
                                   uint8_t* d_status, void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   CU(launch_tally_status_merge(d_part_status, n_parts, n_fields, 1, nullptr, (u32*)d_ct, d_status, (cudaStream_t)stream),
      "tally status kernel");
   ctx->launches++;
@@ -1886,7 +1931,8 @@ int gcp_elgamal_scalar_mul_dev(gcp_ctx* ctx, const void* d_points, const void* d
                                void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   return scalar_mul_dev_locked(ctx, d_points, d_scalars, d_points2, d_scalars2, n, d_out_points, d_status, fmt,
                                (cudaStream_t)stream, 98);
 }
@@ -1895,7 +1941,8 @@ int gcp_elgamal_scalar_mul(gcp_ctx* ctx, const void* points, const void* scalars
                            size_t n, void* out_points, uint8_t* status, int fmt) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   StreamGuard guard{ctx};
   int rc = check_fmt_points(ctx, fmt);
   if (rc != GCP_OK || n == 0) return rc;
@@ -1931,7 +1978,8 @@ int gcp_elgamal_assert_decrypt(gcp_ctx* ctx, const void* ct, const void* priv_ke
                                uint8_t* out_flags, uint8_t* status, int fmt) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   StreamGuard guard{ctx};
   int rc = check_fmt_points(ctx, fmt);
   if (rc != GCP_OK || n == 0) return rc;
@@ -1955,7 +2003,8 @@ int gcp_elgamal_verify_decryption_proof(gcp_ctx* ctx, const void* pub_keys, cons
                                         uint8_t* status, int fmt) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   StreamGuard guard{ctx};
   int rc = check_fmt_points(ctx, fmt);
   if (rc != GCP_OK || n == 0) return rc;
@@ -1979,7 +2028,8 @@ int gcp_eddsa_verify(gcp_ctx* ctx, const void* pub_keys_te, const void* sig_r_te
                      size_t n, uint8_t* out_flags, uint8_t* status, int fmt) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   StreamGuard guard{ctx};
   int rc = check_fmt(ctx, fmt);
   if (rc != GCP_OK || n == 0) return rc;
@@ -2001,7 +2051,8 @@ int gcp_eddsa_verify(gcp_ctx* ctx, const void* pub_keys_te, const void* sig_r_te
 static int te_rte_host(gcp_ctx* ctx, const void* in, size_t n_points, void* out, uint8_t* status, int to_rte) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   StreamGuard guard{ctx};
   if (n_points == 0) return GCP_OK;
   if (!in || !out || !status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
@@ -2035,7 +2086,8 @@ int gcp_mimc7_hash_dev(gcp_ctx* ctx, const void* d_in, int len, size_t n, void* 
                        void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   int rc = check_fmt(ctx, fmt);
   if (rc != GCP_OK) return rc;
   if (!ctx->have_mimc7) return ctx->fail(GCP_ERR_CONSTANTS, "MiMC7 constants (data/mimc7_bn254.bin) were not found");
@@ -2050,7 +2102,8 @@ int gcp_mimc7_hash_dev(gcp_ctx* ctx, const void* d_in, int len, size_t n, void* 
 int gcp_mimc7_hash(gcp_ctx* ctx, const void* in, int len, size_t n, void* out, uint8_t* status, int fmt) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);  // held over upload, kernel and read-back: the slots are this call's
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   StreamGuard guard{ctx};
   if (len < 1 || len > 62) return ctx->fail(GCP_ERR_BAD_ARG, "MiMC7 takes 1..62 inputs");
   if (n == 0) return GCP_OK;
@@ -2076,7 +2129,8 @@ int gcp_mimc7_hash(gcp_ctx* ctx, const void* in, int len, size_t n, void* out, u
 int gcp_poseidon2_set_round_keys(gcp_ctx* ctx, const void* keys, size_t n_keys, int fmt) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   int rc = check_fmt(ctx, fmt);
   if (rc != GCP_OK) return rc;
   if (!keys) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
@@ -2120,7 +2174,8 @@ int gcp_poseidon2_hash_dev(gcp_ctx* ctx, const void* d_in, int len, size_t n, vo
                            void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   int rc = p2_check(ctx, fmt);
   if (rc != GCP_OK) return rc;
   if (len != 2 && len != 3) return ctx->fail(GCP_ERR_BAD_ARG, "poseidon2: need 2 or 3 limbs");  // native.go:31-33
@@ -2136,7 +2191,8 @@ int gcp_poseidon2_permutation_dev(gcp_ctx* ctx, const void* d_in, size_t n, void
                                   void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   int rc = p2_check(ctx, fmt);
   if (rc != GCP_OK) return rc;
   if (n == 0) return GCP_OK;
@@ -2153,7 +2209,8 @@ static int p2_host(gcp_ctx* ctx, const void* in, int len, size_t n, void* out, u
   const bool perm = len == 0;
   const size_t in_bytes = perm ? 64 : (size_t)len * 32, out_bytes = perm ? 64 : 32;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);  // held for the whole call: the scratch slots are this call's
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   StreamGuard guard{ctx};
   {
     int rc = p2_check(ctx, fmt);
@@ -2202,7 +2259,8 @@ int gcp_poseidon2_permutation(gcp_ctx* ctx, const void* in, size_t n, void* out,
 int gcp_keccak_address_dev(gcp_ctx* ctx, const void* d_pub_xy_be, size_t n, void* d_out_addr, void* stream) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   if (n == 0) return GCP_OK;
   if (!d_pub_xy_be || !d_out_addr) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
   CU(launch_keccak_address((const u8*)d_pub_xy_be, n, (u8*)d_out_addr, (cudaStream_t)stream), "keccak kernel");
@@ -2213,7 +2271,8 @@ int gcp_keccak_address_dev(gcp_ctx* ctx, const void* d_pub_xy_be, size_t n, void
 int gcp_keccak_address(gcp_ctx* ctx, const void* pub_xy_be, size_t n, void* out_addr) {
   if (!ctx) return GCP_ERR_BAD_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   StreamGuard guard{ctx};
   if (n == 0) return GCP_OK;
   if (!pub_xy_be || !out_addr) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");

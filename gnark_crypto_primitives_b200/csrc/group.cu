@@ -168,9 +168,24 @@ uint8_t* offb(uint8_t* p, size_t n) { return p ? p + n : nullptr; }
 // succeeded everywhere, so a device that fails before the collective never leaves the others waiting inside it:
 // all-gather of the ciphertext bytes and of the status bytes (ncclAllGather, NVLink), fold of the gathered
 // (devices x n_fields) array on every device, statuses merged on the device, result read back from device 0.
+// the calling thread's current device is put back on every path (a one-device group runs on the caller's thread)
+struct DevGuard {
+  int prev = -1;
+  DevGuard() {
+    if (cudaGetDevice(&prev) != cudaSuccess) {
+      cudaGetLastError();
+      prev = -1;
+    }
+  }
+  ~DevGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 int gather_and_fold(gcp_group* g, int i, int n_fields, void* out, uint8_t* status, int fmt) {
   const int w = (int)g->ctx.size();
   const size_t pb = (size_t)n_fields * kCtBytes;
+  DevGuard dev_guard;
   if (cudaSetDevice(g->devices[i]) != cudaSuccess) return GCP_ERR_CUDA;
   cudaStream_t st = g->stream[i];
   unsigned char* recv_status = g->d_recv[i] + (size_t)w * kSendStatusOff;
@@ -207,6 +222,7 @@ const char* gcp_group_last_error(const gcp_group* g) { return g ? g->err.c_str()
 
 void gcp_group_destroy(gcp_group* g) {
   if (!g) return;
+  DevGuard dev_guard;
   {
     std::lock_guard<std::mutex> lk(g->wmu);
     g->stop = true;
@@ -247,6 +263,7 @@ int gcp_group_create(const int* devices, int n_devices, const char* constants_pa
         g_group_create_error = "a device may appear only once in a group";
         return GCP_ERR_BAD_ARG;
       }
+  DevGuard dev_guard;
   gcp_group* g = new gcp_group;
   g->devices.assign(devices, devices + n_devices);
   g->ctx.assign(n_devices, nullptr);

@@ -15,13 +15,16 @@ eng = g.Engine(0)
 gen = torch.Generator(device="cuda")
 gen.manual_seed(21)
 st = torch.cuda.current_stream()
-which = set(sys.argv[1:]) or {"keccak", "mimc7", "poseidon2", "unpack", "process", "add", "tally", "fused"}
+which = set(sys.argv[1:]) or {"keccak", "mimc7", "poseidon2", "unpack", "process", "add", "tally", "fused", "lanes"}
 u8 = lambda *shape: torch.empty(shape, dtype=torch.uint8, device="cuda")
 
 if "keccak" in which:
     n = 1 << 22
     pub = torch.randint(0, 256, (n, 64), dtype=torch.uint8, device="cuda", generator=gen)
     eng.keccak_address_dev(pub, n, u8(n, 20), stream=st)
+if "lanes" in which:
+    n = 1024                                       # BASELINE config 1: the three-lanes-per-hash latency layout
+    eng.poseidon_hash_dev(rand_elems(torch, 2 * n, gen), 2, n, u8(n, 32), u8(n), stream=st)
 if "mimc7" in which:
     n = 1 << 20
     eng.mimc7_hash_dev(rand_elems(torch, 2 * n, gen), 2, n, u8(n, 32), u8(n), stream=st)

@@ -118,9 +118,14 @@ def test_group_of_two_devices_is_bit_identical_to_one():
     w = workload(rng)
     with g.Group([0]) as one:
         base = run_all(one, *w)
+    import torch
+    torch.cuda.set_device(0)
     with g.Group([0, 1]) as two:
         assert two.size == 2 and two.uses_nccl
+        # creating contexts on other devices must not move the caller's current device (torch keeps allocating on 0)
+        assert torch.cuda.current_device() == 0
         res = run_all(two, *w)
+        assert torch.cuda.current_device() == 0
         assert all(c > 0 for c in two.launch_counts())
         # fewer ballots than devices: one shard is empty
         k1 = elems([5, 6, 7]).reshape(1, 3, 32)
