@@ -587,6 +587,10 @@ def measure_group(torch, dist, eng0, g, world, rank, barrier_cpu):
         try:
             lib, gh = grp._lib, grp._h
             out = {"devices": world, "uses_nccl": bool(grp.uses_nccl), "copy_threads": int(lib.gcp_copy_threads())}
+            import ctypes
+            bw = ctypes.c_double(0.0)
+            if lib.gcp_copy_probe(1 << 30, ctypes.byref(bw)) == 0:
+                out["host_staging_gb_per_s_pool"] = bw.value       # pageable -> page-locked through the copy pool
 
             def timed(fn, iters=2):
                 fn()
@@ -595,8 +599,8 @@ def measure_group(torch, dist, eng0, g, world, rank, barrier_cpu):
                     fn()
                 return (time.perf_counter() - t0) / iters
 
-            # SMT, dense 160 levels, 2^17 proofs per GPU, page-locked
-            n1 = 1 << 17
+            # SMT, dense 160 levels, 2^18 proofs per GPU, page-locked
+            n1 = 1 << 18
             b = make_batch(torch, eng0, n1, seed=0x6E0)
             h = {kk: _pinned_copy(torch, b[kk]) for kk in ("sib", "keys", "vals", "roots")}
             expect1 = b["expect"].cpu().numpy()

@@ -69,6 +69,7 @@ SIGNATURES = {
                                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                    c_int, c_void_p]),
     "gcp_copy_threads": (c_int, []),
+    "gcp_copy_probe": (c_int, [c_size_t, POINTER(ctypes.c_double)]),
     "gcp_smt_verify_packed": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_int]),

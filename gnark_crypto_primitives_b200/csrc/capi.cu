@@ -323,7 +323,12 @@ struct ChunkPlan {
   size_t next() {  // items of the next chunk (0: done); advances
     const size_t left = n - off;
     if (left == 0) return 0;
-    size_t take = off == 0 ? std::min(left, wave) : std::min(left, cap);
+    static const size_t first_div = [] {
+      const char* env = getenv("GCP_B200_FIRST_DIV");
+      long v = env ? atol(env) : 1;
+      return (size_t)(v >= 1 && v <= 64 ? v : 1);
+    }();
+    size_t take = off == 0 ? std::min(left, std::max<size_t>(1, wave / first_div)) : std::min(left, cap);
     if (!forced && left - take < wave) take = left <= cap + wave ? left : take;
     off += take;
     return take;
@@ -380,6 +385,39 @@ void gcp_ctx_destroy(gcp_ctx* ctx) {
 }
 
 int gcp_copy_threads(void) { return CopyPool::workers(); }
+
+// Bandwidth of the staging path on this host: pageable memory -> page-locked memory through the copy pool, GB/s (what
+// bounds the host-buffer calls when their inputs live in ordinary memory and the kernels outrun it).
+int gcp_copy_probe(size_t bytes, double* gb_per_s) {
+  if (!gb_per_s || bytes < ((size_t)1 << 20)) return GCP_ERR_BAD_ARG;
+  *gb_per_s = 0;
+  if (gcp_device_count() <= 0) return GCP_ERR_NO_DEVICE;
+  void* dst = nullptr;
+  if (cudaHostAlloc(&dst, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return GCP_ERR_ALLOC;
+  }
+  char* src = (char*)malloc(bytes);
+  if (!src) {
+    cudaFreeHost(dst);
+    return GCP_ERR_ALLOC;
+  }
+  memset(src, 1, bytes);
+  CopyPool::acquire();
+  CopyPool::copy(dst, src, bytes);  // warm: faults the destination in
+  double best = 0;
+  for (int it = 0; it < 3; it++) {
+    auto t0 = std::chrono::steady_clock::now();
+    CopyPool::copy(dst, src, bytes);
+    double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (dt > 0) best = std::max(best, (double)bytes / dt / 1e9);
+  }
+  CopyPool::release();
+  free(src);
+  cudaFreeHost(dst);
+  *gb_per_s = best;
+  return GCP_OK;
+}
 
 int gcp_host_alloc(size_t bytes, void** out) {
   if (!out) return GCP_ERR_BAD_ARG;

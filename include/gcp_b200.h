@@ -81,6 +81,9 @@ uint64_t gcp_ctx_launch_count(const gcp_ctx* ctx);
 /* Host threads of the process-wide staging pool (csrc/hostcopy.h): min(16, hardware threads / 2), shared by every context
  * of the process; 0 before the first context exists.  GCP_B200_COPY_THREADS overrides it at first use. */
 int gcp_copy_threads(void);
+/* Measured bandwidth (GB/s) of that staging path on this host: `bytes` (>= 1 MB) of pageable memory copied into page-locked
+ * memory by the pool.  A host-buffer call whose kernels outrun it is bound by this figure, not by the GPU. */
+int gcp_copy_probe(size_t bytes, double* gb_per_s);
 /* Page-locked host memory for the caller's flat arrays (cudaHostAlloc, portable across the devices of a group).
  * The host-buffer entry points accept any host pointer; from pinned memory their chunked copies run at full PCIe
  * rate and overlap the kernels (bench.py's e2e figure); from pageable memory (a Go heap slice) copies of 64 MB and more
