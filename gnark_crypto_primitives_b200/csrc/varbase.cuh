@@ -44,8 +44,14 @@ constexpr int VB_TABLE_WORDS = 8 * 32;  // per (task, base): entries [1..8]P x (
 //   LDQ  slots f1..f1+3 <- the thread's table entry (Y-X and Y+X exchanged where the digit is negative: -(x, y) = (-x, y))
 //   STQ  the thread's table entry <- slots f2..f2+3
 // Every op reads all of its operands before it writes, so destinations may alias sources.
+// Fused ops with fixed slots (round 2: 29 of the 49 ops of a window were add-type ops, each a round trip of its operands
+// through shared memory; now 26 ops per window):
+//   SQR2 with f3 != 0 also stores f2 + f5 to f3 before squaring (the doubling's X + Y)
+//   DBLMID  A 4, B 5, C' 6, E' 7  ->  E 7 = E' - A - B, F 6 = (B - A) - 2 C', G 8 = B - A, H 4 = -(A + B)
+//   ADDMID  A 4, B 5, C 6, D 7 (C negated where the digit is negative)  ->  E 8 = B - A, H 4 = B + A, F 9 = D - C, G 6 = D + C
+//   LDQB    LDQ into 6..9 and (Y - X, Y + X) into 4, 5
 enum : u32 { VB_MUL = 0, VB_MUL2 = 1, VB_SQR2 = 2, VB_BFLY = 3, VB_ADD = 4, VB_SUB = 5, VB_SUB3 = 6, VB_NEG = 7, VB_CNEG = 8,
-             VB_LDQ = 9, VB_STQ = 10 };
+             VB_LDQ = 9, VB_STQ = 10, VB_DBLMID = 11, VB_ADDMID = 12, VB_LDQB = 13 };
 // stored pre-decoded, 16 bytes per op (one LDC.128): {op, off1 | off2 << 16, off3 | off4 << 16, off5 | off6 << 16} with
 // off = slot * 4096, the byte offset of the slot inside the register file (2 halves x 128 threads x 16 bytes)
 #define VB_OFF(slot) ((u32)(slot) * (2u * VB_THREADS * 16u))
@@ -55,22 +61,19 @@ enum : u32 { VB_MUL = 0, VB_MUL2 = 1, VB_SQR2 = 2, VB_BFLY = 3, VB_ADD = 4, VB_S
 
 // slots: 0 X, 1 Y, 2 Z, 3 T, 4..9 temporaries, 10 the constant 2d
 constexpr int VB_SLOT_2D = 10;
-constexpr int VB_PROG_DBL = 0, VB_PROG_DBL_T = 10, VB_PROG_DBL_LEN = 10;  // without / with T (T is dead before another doubling)
-constexpr int VB_PROG_ADD = 20, VB_PROG_ADD_LEN = 9;
-constexpr int VB_PROG_CACHE = 29, VB_PROG_CACHE_LEN = 4;
+constexpr int VB_PROG_DBL = 0, VB_PROG_DBL_T = 5, VB_PROG_DBL_LEN = 5;  // without / with T (T is dead before another doubling)
+constexpr int VB_PROG_ADD = 10, VB_PROG_ADD_LEN = 6;
+constexpr int VB_PROG_CACHE = 16, VB_PROG_CACHE_LEN = 4;
 // P = 2P (dbl-2008-hwcd, a = -1): A = X^2, B = Y^2, C = 2 Z^2, E = (X+Y)^2 - A - B, G = B - A, F = G - C, H = -(A+B);
-// X = E F, Y = G H, Z = F G, T = E H.   slots: A 4, B 5, C 6, E 7, G 8, then F 6, H 4
-#define VB_DBL_HEAD                                                                                                        \
-  VB_OP(VB_ADD, 3, 0, 1), VB_OP2(VB_SQR2, 4, 0, 0, 5, 1, 0), VB_OP2(VB_SQR2, 6, 2, 0, 7, 3, 0), VB_OP(VB_ADD, 6, 6, 6),    \
-      VB_OP2(VB_SUB3, 7, 7, 4, 5, 0, 0), VB_OP2(VB_BFLY, 8, 5, 4, 4, 0, 0), VB_OP(VB_SUB, 6, 8, 6), VB_OP(VB_NEG, 4, 4, 0), \
-      VB_OP2(VB_MUL2, 0, 7, 6, 1, 8, 4)
-__device__ __constant__ uint4 c_vb_prog[34] = {
+// X = E F, Y = G H, Z = F G, T = E H.   slots: A 4, B 5, C' 6, E' 7, then E 7, F 6, G 8, H 4
+#define VB_DBL_HEAD \
+  VB_OP2(VB_SQR2, 4, 0, 3, 5, 1, 0), VB_OP2(VB_SQR2, 6, 2, 0, 7, 3, 0), VB_OP(VB_DBLMID, 0, 0, 0), VB_OP2(VB_MUL2, 0, 7, 6, 1, 8, 4)
+__device__ __constant__ uint4 c_vb_prog[21] = {
     VB_DBL_HEAD, VB_OP(VB_MUL, 2, 6, 8),
     VB_DBL_HEAD, VB_OP2(VB_MUL2, 2, 6, 8, 3, 7, 4),
     // P += Q (add-2008-hwcd-3, Q cached in slots 6..9): A = (Y-X) q0, B = (Y+X) q1, C = T q2, D = Z q3,
     // E = B - A, H = B + A, F = D - C, G = D + C;  X = E F, Y = G H, T = E H, Z = F G
-    VB_OP(VB_LDQ, 6, 0, 0), VB_OP2(VB_BFLY, 4, 1, 0, 5, 0, 0), VB_OP2(VB_MUL2, 4, 4, 6, 5, 5, 7), VB_OP2(VB_MUL2, 6, 3, 8, 7, 2, 9),
-    VB_OP(VB_CNEG, 6, 6, 0), VB_OP2(VB_BFLY, 8, 5, 4, 4, 0, 0), VB_OP2(VB_BFLY, 9, 7, 6, 6, 0, 0),
+    VB_OP(VB_LDQB, 0, 0, 0), VB_OP2(VB_MUL2, 4, 4, 6, 5, 5, 7), VB_OP2(VB_MUL2, 6, 3, 8, 7, 2, 9), VB_OP(VB_ADDMID, 0, 0, 0),
     VB_OP2(VB_MUL2, 0, 8, 9, 1, 6, 4), VB_OP2(VB_MUL2, 3, 8, 4, 2, 9, 6),
     // table entry <- cached(P) = (Y-X, Y+X, 2d T, 2Z)
     VB_OP2(VB_BFLY, 4, 1, 0, 5, 0, 0), VB_OP(VB_MUL, 6, 3, VB_SLOT_2D), VB_OP(VB_ADD, 7, 2, 2), VB_OP(VB_STQ, 0, 4, 0),
@@ -235,6 +238,10 @@ __global__ void __launch_bounds__(VB_THREADS, MIN_BLOCKS) varbase_window_kernel(
           u32 x1[8], x2[8], r1[8], r2[8];
           vb_ld(x1, s2);
           vb_ld(x2, s5);
+          if (cur.z & 0xffffu) {  // also f3 = f2 + f5 (the doubling's X + Y, squared by the next op)
+            fr_add(r1, x1, x2);
+            vb_st(s3, r1);
+          }
           fr_sqr2(r1, x1, r2, x2);
           vb_st(s1, r1);
           vb_st(s4, r2);
@@ -292,6 +299,61 @@ __global__ void __launch_bounds__(VB_THREADS, MIN_BLOCKS) varbase_window_kernel(
           vb_ld(x, s2);
           fr_neg(r, x);
           vb_st(s1, r);
+          break;
+        }
+        case VB_DBLMID: {
+          u32 a[8], b[8], c[8], e[8], t[8];
+          vb_ld(a, rf_sa + VB_OFF(4));
+          vb_ld(b, rf_sa + VB_OFF(5));
+          vb_ld(e, rf_sa + VB_OFF(7));
+          fr_sub(t, e, a);
+          fr_sub(e, t, b);
+          vb_st(rf_sa + VB_OFF(7), e);   // E = (X+Y)^2 - A - B
+          fr_sub(e, b, a);
+          vb_st(rf_sa + VB_OFF(8), e);   // G = B - A
+          vb_ld(c, rf_sa + VB_OFF(6));
+          fr_add(t, c, c);
+          fr_sub(c, e, t);
+          vb_st(rf_sa + VB_OFF(6), c);   // F = G - 2 Z^2
+          fr_add(t, a, b);
+          fr_neg(a, t);
+          vb_st(rf_sa + VB_OFF(4), a);   // H = -(A + B)
+          break;
+        }
+        case VB_ADDMID: {
+          u32 a[8], b[8], c[8], d[8], t[8];
+          vb_ld(a, rf_sa + VB_OFF(4));
+          vb_ld(b, rf_sa + VB_OFF(5));
+          fr_sub(t, b, a);
+          vb_st(rf_sa + VB_OFF(8), t);   // E = B - A
+          fr_add(t, b, a);
+          vb_st(rf_sa + VB_OFF(4), t);   // H = B + A
+          vb_ld(c, rf_sa + VB_OFF(6));
+          vb_ld(d, rf_sa + VB_OFF(7));
+          if (neg) {                     // -Q: its 2dT changes sign
+            fr_neg(t, c);
+            fr_copy(c, t);
+          }
+          fr_sub(t, d, c);
+          vb_st(rf_sa + VB_OFF(9), t);   // F = D - C
+          fr_add(t, d, c);
+          vb_st(rf_sa + VB_OFF(6), t);   // G = D + C
+          break;
+        }
+        case VB_LDQB: {
+          u32 x[8], y[8], t[8];
+          vb_ld(x, rf_sa + VB_OFF(0));
+          vb_ld(y, rf_sa + VB_OFF(1));
+          fr_sub(t, y, x);
+          vb_st(rf_sa + VB_OFF(4), t);
+          fr_add(t, y, x);
+          vb_st(rf_sa + VB_OFF(5), t);
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            u32 v[8];
+            load_fr_plain(v, q + ((neg && c < 2) ? (c ^ 1) : c) * 8);
+            vb_st(rf_sa + VB_OFF(6 + c), v);
+          }
           break;
         }
         case VB_LDQ: {
