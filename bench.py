@@ -1091,7 +1091,7 @@ def main():
             hbm_src = "fallback"
         traffic = None
         try:   # DRAM bytes per proof measured by ncu (committed capture), scaled to this launch
-            with open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")) as fh:
+            with open(os.path.join(ROOT, "profiles", "r02_dram_traffic.json")) as fh:
                 traffic = float(json.load(fh)["dram_bytes_per_proof"]) * n
         except Exception:
             pass
@@ -1099,7 +1099,7 @@ def main():
             "bound": "int-pipe", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "T IMAD.WIDE.U32/s",
             "frac": achieved / peak if peak else None, "traffic": traffic,
             "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture "
-                            "(profiles/r01_dram_traffic.json), scaled by proofs per launch; algorithmic bytes are in hbm",
+                            "(profiles/r02_dram_traffic.json), scaled by proofs per launch; algorithmic bytes are in hbm",
             "peak_source": "max(gcp_probe_imad_wide measured in this run, 32 lanes/clk/SM x 148 SMs x sampled SM clock); "
                            "the per-clock rate is measured by bench_micro/imad_peak.cu",
             "probe_measured": peak_wide / 1e12, "peak_nominal_at_sampled_clock": nominal / 1e12 if nominal else None,

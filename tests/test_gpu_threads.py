@@ -103,3 +103,46 @@ def test_host_entry_points_keep_their_scratch_for_the_whole_call(engine):
     for t in threads:
         t.join()
     assert not errors, errors[0]
+
+
+def test_contexts_share_the_copy_pool_from_several_threads():
+    """Three contexts on one device driven by three host threads with PAGEABLE inputs of several MB and pageable outputs:
+    every upload goes through the process-wide copy pool (csrc/hostcopy.h) and the page-locked staging ring, every result
+    through the page-locked output arena / ring (d2h_copy).  Results must equal the single-threaded ones, call after call."""
+    import numpy as np
+
+    import gnark_crypto_primitives_b200 as g
+    from gnark_crypto_primitives_b200 import _lib
+
+    rng = np.random.default_rng(5)
+    n = 1 << 16
+    hin = rng.integers(0, 256, size=(n, 2, 32), dtype=np.uint8)       # 4 MB: staged (>= 1 MB), out 2 MB: arena
+    hin[:, :, 31] &= 0x0F
+    big = rng.integers(0, 256, size=(3 * n, 4, 32), dtype=np.uint8)   # 25 MB in, 25 MB out: the output ring
+    big[:, :, 31] &= 0x0F
+    with g.Engine(0) as ref:
+        want_hash, _ = ref.poseidon_hash(hin)
+        want_neg, st = ref.elgamal_neg(big)
+        assert not st.any()
+    assert _lib.load().gcp_copy_threads() >= 1
+    errors = []
+
+    def worker(i):
+        try:
+            with g.Engine(0) as eng:
+                for it in range(4):
+                    if (i + it) % 2:
+                        out, st = eng.poseidon_hash(hin)
+                        assert not st.any() and (out == want_hash).all()
+                    else:
+                        out, st = eng.elgamal_neg(big)
+                        assert not st.any() and (out == want_neg).all()
+        except Exception as exc:
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(3)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[0]
