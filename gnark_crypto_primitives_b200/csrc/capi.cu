@@ -2,6 +2,7 @@
 // host-buffer entry points (chunked, double-buffered H2D -> kernels -> D2H pipelines on two streams).
 // There is no CPU compute path here: every value is produced by the kernels in kernels.cu.
 #include "../../include/gcp_b200.h"
+#include "chunkplan.h"
 #include "hostcopy.h"
 #include "internal.h"
 #include "kernels.h"
@@ -300,40 +301,6 @@ StreamGuard::~StreamGuard() {
   cudaStreamSynchronize(c->stream[1]);
   flush_outputs(c);  // results parked in page-locked memory reach the caller's buffers before the call returns
 }
-
-// Chunk schedule of the host-buffer pipelines whose kernels are resident-wave shaped (smt_path_kernel,
-// varbase_window_kernel: one thread per item, registers set the residency).  The first chunk is ONE wave, so the only
-// copy no kernel hides is short (at 2^18 census-like proofs the old ~1 GB first chunk left 20 ms of copy exposed against
-// 51 ms of compute); later chunks are `cap_waves` whole waves, and a remainder shorter than a wave joins the chunk
-// before it instead of running as a thin launch of its own.  GCP_B200_SMT_CHUNK overrides the size (tests).
-struct ChunkPlan {
-  size_t wave, cap, n, off = 0;
-  bool forced = false;
-  ChunkPlan(size_t n_items, size_t wave_items, size_t cap_items) : wave(std::max<size_t>(1, wave_items)), n(n_items) {
-    cap = std::max(wave, cap_items - cap_items % wave);
-    if (const char* env = getenv("GCP_B200_SMT_CHUNK")) {
-      long v = atol(env);
-      if (v > 0) {
-        cap = wave = (size_t)v;
-        forced = true;
-      }
-    }
-  }
-  size_t largest() const { return std::min(n, cap + wave); }
-  size_t next() {  // items of the next chunk (0: done); advances
-    const size_t left = n - off;
-    if (left == 0) return 0;
-    static const size_t first_div = [] {
-      const char* env = getenv("GCP_B200_FIRST_DIV");
-      long v = env ? atol(env) : 1;
-      return (size_t)(v >= 1 && v <= 64 ? v : 1);
-    }();
-    size_t take = off == 0 ? std::min(left, std::max<size_t>(1, wave / first_div)) : std::min(left, cap);
-    if (!forced && left - take < wave) take = left <= cap + wave ? left : take;
-    off += take;
-    return take;
-  }
-};
 
 #define GCP_TRY(call)            \
   do {                           \
