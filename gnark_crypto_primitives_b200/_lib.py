@@ -17,6 +17,8 @@ GCP_ERR_ALLOC = -5
 
 FMT_CANONICAL = 0
 FMT_MONTGOMERY = 1
+HASHER_POSEIDON = 0  # utils.PoseidonHasher (default)
+HASHER_POSEIDON2 = 1  # utils.Poseidon2Hasher: the width-2 Merkle-Damgard hasher (gcp_ctx_set_smt_hasher)
 COORDS_TE = 2       # or-ed into fmt: curve points on the wire are in iden3 twisted-Edwards coordinates (gcp_b200.h)
 
 STATUS_OK = 0
@@ -68,6 +70,8 @@ SIGNATURES = {
     "gcp_smt_process_with_leaf_hash_dev": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p,
                                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                    c_int, c_void_p]),
+    "gcp_ctx_set_smt_hasher": (c_int, [c_void_p, c_int]),
+    "gcp_ctx_smt_hasher": (c_int, [c_void_p]),
     "gcp_copy_threads": (c_int, []),
     "gcp_copy_probe": (c_int, [c_size_t, POINTER(ctypes.c_double)]),
     "gcp_smt_verify_packed": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,

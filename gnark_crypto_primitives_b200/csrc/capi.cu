@@ -81,6 +81,7 @@ struct gcp_ctx {
   bool have_mimc7 = false;
   u32* d_p2_keys = nullptr;   // 62 Poseidon2 round keys, Montgomery form (poseidon2.cuh)
   bool have_p2_keys = false;
+  int smt_hasher = GCP_HASHER_POSEIDON;  // the utils.Hasher plug of the tree/smt gadgets (gcp_ctx_set_smt_hasher)
   // staging ring for large host->device copies from PAGEABLE memory (see h2d_copy)
   static constexpr int STAGE_SLOTS = 4;
   static constexpr size_t STAGE_BYTES = (size_t)32 << 20;
@@ -324,6 +325,21 @@ int gcp_device_count(void) {
 const char* gcp_last_error(const gcp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 int gcp_ctx_device(const gcp_ctx* ctx) { return ctx ? ctx->device : -1; }
 uint64_t gcp_ctx_launch_count(const gcp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int gcp_ctx_smt_hasher(const gcp_ctx* ctx) { return ctx ? ctx->smt_hasher : -1; }
+
+int gcp_ctx_set_smt_hasher(gcp_ctx* ctx, int hasher) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (hasher != GCP_HASHER_POSEIDON && hasher != GCP_HASHER_POSEIDON2)
+    return ctx->fail(GCP_ERR_BAD_ARG, "unknown hasher (GCP_HASHER_POSEIDON or GCP_HASHER_POSEIDON2)");
+  if (hasher == GCP_HASHER_POSEIDON2 && !ctx->have_p2_keys)
+    return ctx->fail(GCP_ERR_CONSTANTS,
+                     "Poseidon2 round keys missing (data/poseidon2_bn254_t2.bin not found and gcp_poseidon2_set_round_keys not called)");
+  // queued work of the two pipeline streams was launched with the previous plug: nothing to wait for, the plug is a launch argument
+  ctx->smt_hasher = hasher;
+  return GCP_OK;
+}
 
 void gcp_ctx_destroy(gcp_ctx* ctx) {
   if (!ctx) return;
@@ -781,6 +797,8 @@ static int smt_verify_dev_locked(gcp_ctx* ctx, int n_levels, size_t n, const voi
   a.out_roots = (u32*)d_out_roots;
   a.mont = fmt;
   a.leaf_hash_form = leaf_form;
+  a.hasher = ctx->smt_hasher;
+  a.hkeys = ctx->d_p2_keys;
   CU(launch_smt_verify(a, sc, ctx->sm_count, st), "smt kernels");
   ctx->launches += 5;
   return GCP_OK;
@@ -843,8 +861,16 @@ static int smt_leaf_hash_dev_locked(gcp_ctx* ctx, const void* d_keys, const void
   const int arity = n_values + 2;
   u32* rows = (u32*)ctx->buf(rows_slot, n * (size_t)arity * 32);
   if (!rows) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+  if (ctx->smt_hasher == GCP_HASHER_POSEIDON2 && (arity != 2 && arity != 3))
+    return ctx->fail(GCP_ERR_BAD_ARG, "poseidon2: need 2 or 3 limbs");  // native.go:31-33 through utils.Poseidon2Hasher
   CU(launch_smt_leaf_rows((const u32*)d_keys, (const u32*)d_values, n_values, n, rows, fmt, st), "leaf rows kernel");
   ctx->launches++;
+  if (ctx->smt_hasher == GCP_HASHER_POSEIDON2) {
+    if (!d_status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
+    CU(launch_poseidon2_hash(ctx->d_p2_keys, rows, arity, n, (u32*)d_out, d_status, fmt, st), "poseidon2 hash kernel");
+    ctx->launches++;
+    return GCP_OK;
+  }
   return poseidon_hash_dev_locked(ctx, rows, arity, n, d_out, d_status, fmt, st);
 }
 
@@ -1087,6 +1113,8 @@ static int smt_process_dev_locked(gcp_ctx* ctx, int n_levels, size_t n, const vo
   a.status = d_status;
   a.mont = fmt;
   a.leaf_hash_form = leaf_form;
+  a.hasher = ctx->smt_hasher;
+  a.hkeys = ctx->d_p2_keys;
   // from 1024 transitions up: the verifier's pipeline (scan, sort by path length, prep, two-chain path kernel); below that
   // (and with GCP_B200_PROCESS_NAIVE set, for measurements) one thread per transition
   static const bool naive = getenv("GCP_B200_PROCESS_NAIVE") != nullptr;

@@ -265,13 +265,18 @@ cudaError_t launch_smt_verify(const SmtArgs& a, const SmtScratch& sc, int sm_cou
   unsigned blocks256 = (unsigned)((a.n + 255) / 256);
   smt_sort_scatter_kernel<<<blocks256, 256, 0, stream>>>(sc.lidx, a.n, sc.cursor, sc.perm);
   unsigned blocks = (unsigned)((a.n + 127) / 128);
-  smt_leaf_kernel<<<blocks, 128, 0, stream>>>(a);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
+  const unsigned path_blocks = (unsigned)((a.n + SMT_WARPS * 32 - 1) / (SMT_WARPS * 32));
   // 4-5 resident blocks x 36 KB of staging tiles per SM: ask for the large shared-memory carve-out
   // (set on every launch: the attribute is per device, and a process may drive several GPUs)
-  cudaFuncSetAttribute(smt_path_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  smt_path_kernel<<<(unsigned)((a.n + SMT_WARPS * 32 - 1) / (SMT_WARPS * 32)), SMT_WARPS * 32, 0, stream>>>(a, sc.perm, sc.lidx, sc.info);
+  if (a.hasher == 1) {
+    smt_leaf_kernel<1><<<blocks, 128, 0, stream>>>(a);
+    cudaFuncSetAttribute(smt_path_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    smt_path_kernel<1><<<path_blocks, SMT_WARPS * 32, 0, stream>>>(a, sc.perm, sc.lidx, sc.info);
+  } else {
+    smt_leaf_kernel<0><<<blocks, 128, 0, stream>>>(a);
+    cudaFuncSetAttribute(smt_path_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    smt_path_kernel<0><<<path_blocks, SMT_WARPS * 32, 0, stream>>>(a, sc.perm, sc.lidx, sc.info);
+  }
   return cudaGetLastError();
 }
 
@@ -288,8 +293,8 @@ static size_t wave_items(K kernel, int threads, size_t smem, int sm_count, int f
 }
 
 size_t smt_path_wave_items(int sm_count) {
-  cudaFuncSetAttribute(smt_path_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  return wave_items(smt_path_kernel, SMT_WARPS * 32, 0, sm_count, 4);
+  cudaFuncSetAttribute(smt_path_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  return wave_items(smt_path_kernel<0>, SMT_WARPS * 32, 0, sm_count, 4);
 }
 
 // scratch: the verifier's (perm, lidx, info, hist, cursor) plus two accumulators per item; nullptr: thread-per-proof form
@@ -297,7 +302,10 @@ cudaError_t launch_smt_process(const SmtProcessArgs& a, const SmtScratch* sc, u3
                                cudaStream_t stream) {
   if (a.n == 0) return cudaSuccess;
   if (!sc) {
-    smt_process_kernel<<<(unsigned)((a.n + 127) / 128), 128, 0, stream>>>(a);
+    if (a.hasher == 1)
+      smt_process_kernel<1><<<(unsigned)((a.n + 127) / 128), 128, 0, stream>>>(a);
+    else
+      smt_process_kernel<0><<<(unsigned)((a.n + 127) / 128), 128, 0, stream>>>(a);
     return cudaGetLastError();
   }
   cudaError_t e = cudaMemsetAsync(sc->hist, 0, 256 * sizeof(u32), stream);
@@ -306,7 +314,10 @@ cudaError_t launch_smt_process(const SmtProcessArgs& a, const SmtScratch* sc, u3
   if (e != cudaSuccess) return e;
   smt_sort_prefix_kernel<<<1, 256, 0, stream>>>(sc->hist, sc->cursor, (u32)a.n);
   smt_sort_scatter_kernel<<<(unsigned)((a.n + 255) / 256), 256, 0, stream>>>(sc->lidx, a.n, sc->cursor, sc->perm);
-  smt_process_prep_kernel<<<(unsigned)((a.n + 127) / 128), 128, 0, stream>>>(a, sc->lidx, sc->info, acc_old, acc_new);
+  if (a.hasher == 1)
+    smt_process_prep_kernel<1><<<(unsigned)((a.n + 127) / 128), 128, 0, stream>>>(a, sc->lidx, sc->info, acc_old, acc_new);
+  else
+    smt_process_prep_kernel<0><<<(unsigned)((a.n + 127) / 128), 128, 0, stream>>>(a, sc->lidx, sc->info, acc_old, acc_new);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   // 4 resident blocks per SM (128 registers, ~80 B of spills) or 3 (148 registers, none): GCP_B200_PROC_BLOCKS, for measurements
@@ -315,12 +326,15 @@ cudaError_t launch_smt_process(const SmtProcessArgs& a, const SmtScratch* sc, u3
     return (env && atoi(env) == 3) ? 3 : 4;
   }();
   const unsigned grid = (unsigned)((a.n + SMT_WARPS * 32 - 1) / (SMT_WARPS * 32));
-  if (min_blocks == 3) {
-    cudaFuncSetAttribute(smt_process_path_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    smt_process_path_kernel<3><<<grid, SMT_WARPS * 32, 0, stream>>>(a, sc->perm, sc->lidx, acc_old, acc_new);
+  if (a.hasher == 1) {
+    cudaFuncSetAttribute(smt_process_path_kernel<4, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    smt_process_path_kernel<4, 1><<<grid, SMT_WARPS * 32, 0, stream>>>(a, sc->perm, sc->lidx, acc_old, acc_new);
+  } else if (min_blocks == 3) {
+    cudaFuncSetAttribute(smt_process_path_kernel<3, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    smt_process_path_kernel<3, 0><<<grid, SMT_WARPS * 32, 0, stream>>>(a, sc->perm, sc->lidx, acc_old, acc_new);
   } else {
-    cudaFuncSetAttribute(smt_process_path_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    smt_process_path_kernel<4><<<grid, SMT_WARPS * 32, 0, stream>>>(a, sc->perm, sc->lidx, acc_old, acc_new);
+    cudaFuncSetAttribute(smt_process_path_kernel<4, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    smt_process_path_kernel<4, 0><<<grid, SMT_WARPS * 32, 0, stream>>>(a, sc->perm, sc->lidx, acc_old, acc_new);
   }
   return cudaGetLastError();
 }

@@ -51,6 +51,8 @@ struct SmtArgs {
   u32* out_roots;        // n x 8 or nullptr: recomputed level[0], canonical
   int mont;              // element format: 0 canonical integers, 1 gnark-crypto Montgomery memory
   int leaf_hash_form;    // VerifierWithLeafHash[Flag] (verifier.go:129-183): `values` / `old_values` hold hash1New / hash1Old
+  int hasher;            // utils.Hasher plug: 0 PoseidonHasher, 1 Poseidon2Hasher (utils/hashers.go:25-37)
+  const u32* hkeys;      // hasher 1: the context's 62 Poseidon2 round keys (Montgomery form)
 };
 
 struct SmtProcessArgs {
@@ -69,6 +71,8 @@ struct SmtProcessArgs {
   u8* status;             // n
   int mont;
   int leaf_hash_form;     // ProcessorWithLeafHash (processor.go:16): `new_values` / `old_values` hold hash1New / hash1Old
+  int hasher;             // as in SmtArgs
+  const u32* hkeys;
 };
 
 // scratch: perm (n x u32), lidx (n x u16), info (n x u8), hist (256 x u32), cursor (256 x u32)

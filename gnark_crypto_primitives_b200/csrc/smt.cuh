@@ -17,10 +17,59 @@
 // this kernel hashes lidx levels.  Assertions of the gadget (key < 2^n, boolean selectors) become status codes.
 #pragma once
 #include "poseidon.cuh"
+#include "poseidon2.cuh"
 #include "kernels.h"
 
 namespace gcp {
 
+
+// The tree's hash function is a plug in the reference (utils.Hasher, utils/hashers.go:10; every gadget of tree/smt takes
+// hFn).  HASHER 0: PoseidonHasher (:25-27), the hash of arbo's circomlib-compatible trees and the default;
+// HASHER 1: Poseidon2Hasher (:35-37) = HashPoseidon2Gnark (hash/native/bn254/poseidon2/gnark.go:18-54), the width-2
+// Merkle-Damgard hasher: a node hashes its two children ordered (min, max) (the MinMax hint, :34-44), a leaf hashes
+// (key, value, 1) in that order; its round keys are the context's (poseidon2.cuh; permutation parity unpinned).
+__device__ __forceinline__ void p2_absorb(u32 (&cv)[8], const u32 (&m)[8], const u32* __restrict__ hk) {
+  u32 s1[8];
+  fr_copy(s1, m);
+  poseidon2_permute(cv, s1, hk);  // native.go:47-61: st = {cv, m}; Permutation; cv = st[1] + m
+  fr_add(cv, s1, m);
+}
+
+template <int HASHER>
+__device__ __forceinline__ void smt_hash2(u32 (&out)[8], const u32 (&l)[8], const u32 (&r)[8], const u32* __restrict__ hk) {
+  if constexpr (HASHER == 0) {
+    poseidon_hash2(out, l, r);
+  } else {
+    u32 ls[8], rs[8];
+    fr_from_mont(ls, l);  // canonical integers: the order is on the values, not on their representations
+    fr_from_mont(rs, r);
+    const bool swap = lt256(rs, ls);
+    u32 cv[8], m[8];
+    fr_set_zero(cv);
+#pragma unroll
+    for (int i = 0; i < 8; i++) m[i] = swap ? r[i] : l[i];
+    p2_absorb(cv, m, hk);
+#pragma unroll
+    for (int i = 0; i < 8; i++) m[i] = swap ? l[i] : r[i];
+    p2_absorb(cv, m, hk);
+    fr_copy(out, cv);
+  }
+}
+
+template <int HASHER>
+__device__ __forceinline__ void smt_hash1(u32 (&out)[8], const u32 (&key)[8], const u32 (&val)[8], const u32 (&one)[8],
+                                          const u32* __restrict__ hk) {
+  if constexpr (HASHER == 0) {
+    poseidon_hash3(out, key, val, one);
+  } else {
+    u32 cv[8];
+    fr_set_zero(cv);
+    p2_absorb(cv, key, hk);
+    p2_absorb(cv, val, hk);
+    p2_absorb(cv, one, hk);
+    fr_copy(out, cv);
+  }
+}
 
 __device__ __forceinline__ void load_elem(u32 (&m)[8], bool& canonical, const u32* p, int mont) {
   u32 x[8];
@@ -47,6 +96,7 @@ __device__ __forceinline__ void key_integer(u32 (&k)[8], const u32* p, int mont)
 }
 
 // Pass 1: validate selectors / key range, pick the leaf the state machine will inject and hash it (t = 4).
+template <int HASHER>
 __global__ void __launch_bounds__(128) smt_leaf_kernel(SmtArgs a) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.n) return;
@@ -108,7 +158,7 @@ __global__ void __launch_bounds__(128) smt_leaf_kernel(SmtArgs a) {
       if (a.leaf_hash_form) {
         fr_copy(leaf, val);                   // the caller's hash1New / hash1Old (lazy Montgomery after load_elem)
       } else {
-        poseidon_hash3(leaf, key, val, one);  // Hash1: H(key, value, 1)
+        smt_hash1<HASHER>(leaf, key, val, one, a.hkeys);  // Hash1: H(key, value, 1)
       }
     }
   }
@@ -259,6 +309,7 @@ __device__ __forceinline__ void smt_stage_chunk(u32* tile, const u32* __restrict
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+template <int HASHER>
 __global__ void __launch_bounds__(SMT_WARPS * 32) smt_path_kernel(SmtArgs a, const u32* __restrict__ perm, const u16* __restrict__ lidx_arr,
                                                        const u8* __restrict__ info_arr) {
   __shared__ __align__(16) u32 tiles[2][SMT_WARPS][32 * SMT_ROW_WORDS];
@@ -325,7 +376,7 @@ __global__ void __launch_bounds__(SMT_WARPS * 32) smt_path_kernel(SmtArgs a, con
         lft[l] = bit ? s[l] : acc[l];
         rgt[l] = bit ? acc[l] : s[l];
       }
-      poseidon_hash2(acc, lft, rgt);
+      smt_hash2<HASHER>(acc, lft, rgt, a.hkeys);
     }
     __syncwarp();  // everyone is done with this buffer before it is refilled two chunks later
   }
@@ -404,6 +455,7 @@ __device__ __forceinline__ bool key_in_range(const u32 (&ki)[8], int n_levels) {
   return hi == 0;
 }
 
+template <int HASHER>
 __global__ void __launch_bounds__(128) smt_process_kernel(SmtProcessArgs a) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.n) return;
@@ -487,7 +539,7 @@ __global__ void __launch_bounds__(128) smt_process_kernel(SmtProcessArgs a) {
           kk[l] = h ? nkey[l] : okey[l];
           vv[l] = h ? nval[l] : oval[l];
         }
-        poseidon_hash3(res, kk, vv, one);
+        smt_hash1<HASHER>(res, kk, vv, one, a.hkeys);
 #pragma unroll
         for (int l = 0; l < 8; l++) {
           if (h)
@@ -547,7 +599,7 @@ __global__ void __launch_bounds__(128) smt_process_kernel(SmtProcessArgs a) {
             lft[l] = bit ? other[l] : child[l];
             rgt[l] = bit ? child[l] : other[l];
           }
-          poseidon_hash2(res, lft, rgt);
+          smt_hash2<HASHER>(res, lft, rgt, a.hkeys);
           if (h == 0)
             fr_copy(acc_old, res);
           else
@@ -585,6 +637,7 @@ __global__ void __launch_bounds__(128) smt_process_kernel(SmtProcessArgs a) {
 // thread-per-proof kernel above re-read every sibling twice with 32-byte strided loads and diverged over the path
 // length; it stays as the reference form for tiny batches (launch_smt_process picks).
 // ---------------------------------------------------------------------------------------------------------
+template <int HASHER>
 __global__ void __launch_bounds__(128) smt_process_prep_kernel(SmtProcessArgs a, const u16* __restrict__ lidx_arr,
                                                                const u8* __restrict__ info_arr, u32* __restrict__ acc_old_out,
                                                                u32* __restrict__ acc_new_out) {
@@ -645,7 +698,7 @@ __global__ void __launch_bounds__(128) smt_process_prep_kernel(SmtProcessArgs a,
         kk[l] = h ? nkey[l] : okey[l];
         vv[l] = h ? nval[l] : oval[l];
       }
-      poseidon_hash3(res, kk, vv, one);
+      smt_hash1<HASHER>(res, kk, vv, one, a.hkeys);
 #pragma unroll
       for (int l = 0; l < 8; l++) {
         if (h)
@@ -672,7 +725,7 @@ __global__ void __launch_bounds__(128) smt_process_prep_kernel(SmtProcessArgs a,
           lft[l] = bit ? other[l] : acc_new[l];
           rgt[l] = bit ? acc_new[l] : other[l];
         }
-        poseidon_hash2(acc_new, lft, rgt);
+        smt_hash2<HASHER>(acc_new, lft, rgt, a.hkeys);
       }
     }
   }
@@ -681,7 +734,7 @@ __global__ void __launch_bounds__(128) smt_process_prep_kernel(SmtProcessArgs a,
   a.status[idx] = st;
 }
 
-template <int MIN_BLOCKS>
+template <int MIN_BLOCKS, int HASHER>
 __global__ void __launch_bounds__(SMT_WARPS * 32, MIN_BLOCKS) smt_process_path_kernel(SmtProcessArgs a, const u32* __restrict__ perm,
                                                                        const u16* __restrict__ lidx_arr,
                                                                        const u32* __restrict__ acc_old_in,
@@ -744,7 +797,7 @@ __global__ void __launch_bounds__(SMT_WARPS * 32, MIN_BLOCKS) smt_process_path_k
           rgt[l] = bit ? child : s[l];
         }
         u32 res[8];
-        poseidon_hash2(res, lft, rgt);
+        smt_hash2<HASHER>(res, lft, rgt, a.hkeys);
 #pragma unroll
         for (int l = 0; l < 8; l++) {
           if (h)

@@ -207,6 +207,15 @@ class Engine:
                                                          _dptr(d_status), fmt, self._stream(stream)))
 
     # -- SMT ----------------------------------------------------------------------------------------
+    def set_smt_hasher(self, hasher: int):
+        """The utils.Hasher plug of the tree/smt gadgets (utils/hashers.go:10-37) for every SMT call of this engine:
+        _lib.HASHER_POSEIDON (default) or _lib.HASHER_POSEIDON2."""
+        self._check(self._lib.gcp_ctx_set_smt_hasher(self._h, int(hasher)))
+
+    @property
+    def smt_hasher(self) -> int:
+        return int(self._lib.gcp_ctx_smt_hasher(self._h))
+
     def smt_leaf_hash(self, keys, values, fmt=FMT_CANONICAL):
         """smt.Hash1 (tree/smt/hash.go:10-19): Poseidon(key, values..., 1).  keys: (n, 32); values: (n, n_values, 32) with
         n_values in 0..14 ((n, 32) is one value per leaf).  Returns (hashes (n, 32), status)."""

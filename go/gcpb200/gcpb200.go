@@ -211,6 +211,17 @@ func (e *Engine) BatchProcess(levels int, oldRoots, siblings, oldKeys, oldValues
 	return
 }
 
+// SetSMTHasher selects the utils.Hasher plug (utils/hashers.go:10-37) for every SMT call of this engine: the gadgets of
+// tree/smt take hFn per call, an Engine carries it.  poseidon2 = false: utils.PoseidonHasher (default); true:
+// utils.Poseidon2Hasher (call InstallPoseidon2Keys first, so that the round keys are gnark-crypto's own).
+func (e *Engine) SetSMTHasher(poseidon2 bool) error {
+	h := C.int(C.GCP_HASHER_POSEIDON)
+	if poseidon2 {
+		h = C.int(C.GCP_HASHER_POSEIDON2)
+	}
+	return e.err(C.gcp_ctx_set_smt_hasher(e.ctx, h))
+}
+
 // BatchProcessWithLeafHash mirrors smt.ProcessorWithLeafHash (tree/smt/processor.go:16): the caller supplies
 // hash1Old / hash1New (e.g. from BatchHash1 for leaves with several values).
 func (e *Engine) BatchProcessWithLeafHash(levels int, oldRoots, siblings, oldKeys, hash1Old []fr.Element, isOld0 []byte,

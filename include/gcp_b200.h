@@ -134,6 +134,19 @@ int gcp_poseidon2_permutation_dev(gcp_ctx* ctx, const void* d_in, size_t n, void
                                   void* stream);
 
 /* ---- SMT: tree/smt/verifier.go ------------------------------------------------------------------ */
+/* The tree's hash function is a plug in the reference: `type Hasher func(frontend.API, ...frontend.Variable)`
+ * (utils/hashers.go:10), handed to every gadget of tree/smt as hFn.  A context carries the plug for all of its
+ * gcp_smt_* / gcp_ballot_batch* calls:
+ *   GCP_HASHER_POSEIDON   utils.PoseidonHasher (:25-27): circomlib Poseidon, the hash of arbo's circom-compatible trees.  Default.
+ *   GCP_HASHER_POSEIDON2  utils.Poseidon2Hasher (:35-37) = HashPoseidon2Gnark (hash/native/bn254/poseidon2/gnark.go:18-54):
+ *                         the width-2 Merkle-Damgard hasher; a node hashes its children ordered (min, max), a leaf hashes
+ *                         (key, value, 1); leaves with other than one value are "need 2 or 3 limbs" errors.  Uses the
+ *                         context's round keys (gcp_poseidon2_set_round_keys; parity of the default key blob unpinned).
+ * utils.MiMCHasher (:15-23) is gnark's std/hash/mimc, which lives outside the reference tree and is not implemented. */
+enum gcp_hasher { GCP_HASHER_POSEIDON = 0, GCP_HASHER_POSEIDON2 = 1 };
+int gcp_ctx_set_smt_hasher(gcp_ctx* ctx, int hasher);
+int gcp_ctx_smt_hasher(const gcp_ctx* ctx);
+
 /* smt.Verifier (verifier.go:102-121) -> VerifierWithLeafHashFlag (:171-242), n proofs of n_levels siblings.
  *   roots: n elements, or 1 element when shared_root != 0
  *   siblings: n * n_levels elements, root -> leaf, zero padded (Assignment.Siblings, wrapper.go:20-31)

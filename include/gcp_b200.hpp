@@ -185,6 +185,10 @@ inline Batch Processor(const Engine& e, int n_levels, size_t n, const uint8_t* o
                           fnc1, b.values.data(), b.status.data(), fmt));
   return b;
 }
+// the hFn utils.Hasher argument of the tree/smt gadgets (utils/hashers.go:10-37): carried by the engine
+inline void SetHasher(const Engine& e, int hasher /* GCP_HASHER_POSEIDON | GCP_HASHER_POSEIDON2 */) {
+  e.check(gcp_ctx_set_smt_hasher(e.raw(), hasher));
+}
 // smt.ProcessorWithLeafHash (processor.go:16): hash1_old / hash1_new in the place of the values
 inline Batch ProcessorWithLeafHash(const Engine& e, int n_levels, size_t n, const uint8_t* old_roots, const uint8_t* siblings,
                                    const uint8_t* old_keys, const uint8_t* hash1_old, const uint8_t* is_old0,
