@@ -43,6 +43,8 @@ type Engine struct{ ctx *C.gcp_ctx }
 // New creates a context on the given CUDA device. There is no CPU fallback: without a GPU this fails.
 func New(device int) (*Engine, error) {
 	var ctx *C.gcp_ctx
+	// The creation error text is process-wide in the library (mutex-guarded, readable from any thread), so the two cgo
+	// calls below may land on different OS threads; another goroutine failing a create in between can still replace it.
 	if rc := C.gcp_ctx_create(C.int(device), nil, &ctx); rc != 0 {
 		return nil, fmt.Errorf("gcp_ctx_create: %s", C.GoString(C.gcp_last_error(nil)))
 	}
