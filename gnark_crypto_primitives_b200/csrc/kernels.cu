@@ -9,6 +9,7 @@
 #include "keccak.cuh"
 #include "proofs.cuh"
 #include "varbase.cuh"
+#include "varbase_reg.cuh"
 #include "mimc7.cuh"
 #include "poseidon2.cuh"
 #include "kernels.h"
@@ -518,6 +519,16 @@ static int varbase_min_blocks() {
   return v;
 }
 
+// GCP_B200_VB_IMPL=reg: the register-resident window kernel with out-of-line multipliers (varbase_reg.cuh) instead of the
+// shared-memory interpreter
+static bool varbase_reg_form() {
+  static const bool v = [] {
+    const char* e = getenv("GCP_B200_VB_IMPL");
+    return e && e[0] == 'r';
+  }();
+  return v;
+}
+
 static cudaError_t launch_varbase_window(const u32* bases, const u32* s0, const u32* s1, int n_bases, size_t n,
                                          const u8* status, u32* table, u32* out, cudaStream_t stream) {
   VarbaseArgs a;
@@ -530,7 +541,9 @@ static cudaError_t launch_varbase_window(const u32* bases, const u32* s0, const 
   a.table = table;
   a.out = out;
   const size_t smem = (size_t)VB_SLOTS * 2 * VB_THREADS * sizeof(uint4);
-  if (varbase_min_blocks() == 5) {
+  if (varbase_reg_form()) {
+    varbase_window_reg_kernel<4><<<blocks_for(n, VB_THREADS), VB_THREADS, 0, stream>>>(a);
+  } else if (varbase_min_blocks() == 5) {
     cudaFuncSetAttribute(varbase_window_kernel<5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     varbase_window_kernel<5><<<blocks_for(n, VB_THREADS), VB_THREADS, smem, stream>>>(a);
   } else {
@@ -542,6 +555,7 @@ static cudaError_t launch_varbase_window(const u32* bases, const u32* s0, const 
 
 size_t varbase_wave_items(int sm_count) {
   const size_t smem = (size_t)VB_SLOTS * 2 * VB_THREADS * sizeof(uint4);
+  if (varbase_reg_form()) return wave_items(varbase_window_reg_kernel<4>, VB_THREADS, 0, sm_count, 4);
   if (varbase_min_blocks() == 5) {
     cudaFuncSetAttribute(varbase_window_kernel<5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     return wave_items(varbase_window_kernel<5>, VB_THREADS, smem, sm_count, 5);
