@@ -1515,9 +1515,19 @@ static int encrypt_tally_host(gcp_ctx* ctx, const void* pub_key, const void* k, 
   rc = ensure_pk_table(ctx, pub_key, false, fmt, ctx->stream[0]);
   if (rc != GCP_OK) return rc;
   const size_t ballot_in = (size_t)n_fields * 32, ballot_ct = (size_t)n_fields * 128;
-  // 64 MB of k and of m per chunk (at 8 fields: 2^18 ballots, ~7 ms of kernel): short enough that the first copy, which
-  // nothing hides, is a few percent of a 2^24-ballot call, long enough to fill the machine (2^21 encryptions)
-  size_t chunk = std::max<size_t>(1, std::min<size_t>(std::max<size_t>(n_ballots, 1), ((size_t)64 << 20) / ballot_in));
+  // Chunk = 1/16 of the call, between 64 MB and 256 MB of k (and as much of m).  Every chunk costs ~0.4 ms of small kernels
+  // (second-stage fold, normalisation) and the first chunk's copy is the one nothing hides, so large calls want large
+  // chunks and small calls small ones; measured at 2^23 ballots x 8 from page-locked memory
+  // (profiles/r02_encrypt_tally_chunk_sweep.jsonl): 16 / 64 / 256 / 512 MB chunks -> 253 / 276 / 286 / 282 M enc/s (309 M resident).
+  static const size_t forced_mb = [] {
+    const char* env = getenv("GCP_B200_ET_CHUNK_MB");
+    long v = env ? atol(env) : 0;
+    return (size_t)(v >= 1 && v <= 4096 ? v : 0);
+  }();
+  const size_t total_bytes = n_ballots * ballot_in;
+  const size_t chunk_bytes = forced_mb ? (forced_mb << 20)
+                                       : std::min<size_t>((size_t)256 << 20, std::max<size_t>((size_t)64 << 20, total_bytes / 16));
+  size_t chunk = std::max<size_t>(1, std::min<size_t>(std::max<size_t>(n_ballots, 1), chunk_bytes / ballot_in));
   size_t n_chunks = n_ballots ? (n_ballots + chunk - 1) / chunk : 1;
   u32* d_parts = (u32*)ctx->buf(64, n_chunks * ballot_ct);
   uint8_t* d_part_status = (uint8_t*)ctx->buf(65, n_chunks * n_fields);
