@@ -138,3 +138,30 @@ def test_group_of_two_devices_is_bit_identical_to_one():
             assert np.array_equal(a, b), key
     assert np.array_equal(t_small[0], t_small_one[0]) and not t_small[1].any()
     check_against_oracle(res, *w)
+
+
+def test_group_tally_in_iden3_coordinates_and_status_merge():
+    """GCP_COORDS_TE through the group forms (every visible device): key in TE, tally out in TE, equal to the conversion of
+    the RTE result; a shard with a non-canonical scalar marks its field in the merged status (the statuses travel with the
+    partial ciphertexts through the all-gather) and that field's ciphertext is zeroed."""
+    rng = random.Random(83)
+    devices = list(range(min(n_gpus(), 2)))
+    nb, nf = 37, 3
+    pk = ed.scalar_mul(ed.G, rng.randrange(1, ed.ORDER))
+    ks = [[rng.randrange(R) for _ in range(nf)] for _ in range(nb)]
+    ms = [[rng.randrange(1 << 16) for _ in range(nf)] for _ in range(nb)]
+    k = elems([x for r in ks for x in r]).reshape(nb, nf, 32)
+    m = elems([x for r in ms for x in r]).reshape(nb, nf, 32)
+    with g.Group(devices) as grp:
+        t_rte, st0 = grp.elgamal_encrypt_tally(elems(pk), k, m)
+        t_te, st1 = grp.elgamal_encrypt_tally(elems(ed.rte_to_te(*pk)), k, m, fmt=g.COORDS_TE)
+        assert not st0.any() and not st1.any()
+        for f in range(nf):
+            w = ints(t_rte[f])
+            assert ints(t_te[f]) == [c for p in ((w[0], w[1]), (w[2], w[3])) for c in ed.rte_to_te(*p)]
+        # the last ballot (it lands in the last device's shard) carries k >= r in field 1
+        k_bad = k.copy()
+        k_bad[nb - 1, 1] = elems([R + 5])[0]
+        t_bad, st_bad = grp.elgamal_encrypt_tally(elems(pk), k_bad, m)
+        assert [int(s) for s in st_bad] == [0, g.STATUS_NONCANONICAL, 0]
+        assert not t_bad[1].any() and (t_bad[0] == t_rte[0]).all() and (t_bad[2] == t_rte[2]).all()
