@@ -933,7 +933,7 @@ static int smt_verify_host(gcp_ctx* ctx, int n_levels, size_t n, const void* roo
   if (rc != GCP_OK || n == 0) return rc;
   if (is_packed && !offsets) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
   const size_t sib_bytes = (size_t)n_levels * 32;
-  ChunkPlan plan(n, smt_path_wave_items(ctx->sm_count), ((size_t)1 << 30) / sib_bytes);
+  ChunkPlan plan(n, smt_path_wave_items(ctx->sm_count), ((size_t)1 << 30) / sib_bytes, true);
   // a shared root is uploaded once
   void* d_shared_root = nullptr;
   if (shared_root) {
@@ -1779,7 +1779,7 @@ static int ballot_batch_host(gcp_ctx* ctx, int n_levels, size_t n_voters, const 
   rc = ensure_pk_table(ctx, pub_key, false, fmt, ctx->stream[0]);
   if (rc != GCP_OK) return rc;
   const size_t sib_bytes = (size_t)n_levels * 32, ballot_in = (size_t)n_fields * 32, ballot_ct = (size_t)n_fields * 128;
-  ChunkPlan plan(n, smt_path_wave_items(ctx->sm_count), ((size_t)1 << 30) / (sib_bytes + 2 * ballot_in));
+  ChunkPlan plan(n, smt_path_wave_items(ctx->sm_count), ((size_t)1 << 30) / (sib_bytes + 2 * ballot_in), true);
   std::vector<size_t> sizes;
   {
     ChunkPlan walk = plan;

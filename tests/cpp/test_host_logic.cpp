@@ -21,10 +21,11 @@ static int test_chunk_plan() {
   const size_t waves[] = {1, 7, 128, 75776, 94720};
   const size_t caps[] = {1, 100, 209715, 262144, 1u << 20};
   const size_t ns[] = {0, 1, 2, 127, 128, 129, 75775, 75776, 75777, 151552, 200000, 262144, 524288, 1u << 20, (1u << 20) + 3};
+  for (int second = 0; second < 2; second++)
   for (size_t wave : waves)
     for (size_t cap : caps)
       for (size_t n : ns) {
-        gcp::ChunkPlan plan(n, wave, cap);
+        gcp::ChunkPlan plan(n, wave, cap, second != 0);
         const size_t largest = plan.largest();
         const size_t cap_eff = std::max(wave, cap - cap % wave);
         std::vector<size_t> sizes;
@@ -39,7 +40,8 @@ static int test_chunk_plan() {
         for (size_t i = 0; i < sizes.size(); i++) {
           CHECK(sizes[i] >= 1 && sizes[i] <= largest);            // the slots are sized for largest()
           if (i == 0 && sizes.size() > 1) CHECK(sizes[0] == wave);                    // one wave first
-          if (i > 0 && i + 1 < sizes.size()) CHECK(sizes[i] == cap_eff);             // whole waves in the middle
+          if (i == 1 && sizes.size() > 2 && second) CHECK(sizes[1] == wave);          // and one more where asked: its copy hides under the first
+          if (i > (second ? 1u : 0u) && i + 1 < sizes.size()) CHECK(sizes[i] == cap_eff);   // whole waves in the middle
           if (i + 1 == sizes.size() && sizes.size() > 1) CHECK(sizes[i] >= wave);    // no thin launch at the end
         }
         if (n <= wave) CHECK(sizes.size() == (n ? 1u : 0u));
