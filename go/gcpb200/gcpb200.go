@@ -329,6 +329,200 @@ func (e *Engine) DeriveAddresses(pub []byte) (addr []byte, err error) {
 	return
 }
 
+// packBlob lays byte strings back to back: the (blob, offsets) form of the packed-proof entry points.
+func packBlob(packed [][]byte) (blob []byte, offsets []uint64) {
+	offsets = make([]uint64, len(packed)+1)
+	total := 0
+	for i, b := range packed {
+		total += len(b)
+		offsets[i+1] = uint64(total)
+	}
+	blob = make([]byte, 0, total+1)
+	for _, b := range packed {
+		blob = append(blob, b...)
+	}
+	blob = append(blob, 0) // never a nil pointer for an all-empty batch
+	return
+}
+
+// CoordsTE is or-ed into the format of the point-carrying calls below (fmtOf): points on the wire are in iden3 / circom
+// twisted-Edwards coordinates and are converted inside the kernels (format.FromTEtoRTE / FromRTEtoTE,
+// ecc/format/twistededwards.go:29-48).
+type Coords int
+
+const (
+	CoordsRTE Coords = 0
+	CoordsTE  Coords = Coords(C.GCP_COORDS_TE)
+)
+
+func fmtOf(c Coords) C.int { return C.int(C.GCP_FMT_MONTGOMERY) | C.int(c) }
+
+// BatchInclusionVerify mirrors smt.InclusionVerifier (tree/smt/verifier.go:29).
+func (e *Engine) BatchInclusionVerify(levels int, roots, siblings, keys, values []fr.Element) (flags, status []byte, err error) {
+	n := len(keys)
+	flags, status = make([]byte, n), make([]byte, n)
+	shared := 0
+	if len(roots) == 1 && n != 1 {
+		shared = 1
+	}
+	err = e.err(C.gcp_smt_verify_inclusion(e.ctx, C.int(levels), C.size_t(n), elemPtr(roots), C.int(shared), elemPtr(siblings),
+		elemPtr(keys), elemPtr(values), bytePtr(flags), bytePtr(status), nil, C.GCP_FMT_MONTGOMERY))
+	return
+}
+
+// BatchExclusionVerify mirrors smt.ExclusionVerifier (tree/smt/verifier.go:66).
+func (e *Engine) BatchExclusionVerify(levels int, roots, siblings, oldKeys, oldValues []fr.Element, isOld0 []byte,
+	keys []fr.Element) (flags, status []byte, err error) {
+	n := len(keys)
+	flags, status = make([]byte, n), make([]byte, n)
+	shared := 0
+	if len(roots) == 1 && n != 1 {
+		shared = 1
+	}
+	err = e.err(C.gcp_smt_verify_exclusion(e.ctx, C.int(levels), C.size_t(n), elemPtr(roots), C.int(shared), elemPtr(siblings),
+		elemPtr(oldKeys), elemPtr(oldValues), bytePtr(isOld0), elemPtr(keys), bytePtr(flags), bytePtr(status), nil,
+		C.GCP_FMT_MONTGOMERY))
+	return
+}
+
+// BatchProcessPacked is BatchProcess over arbo packed proofs taken BEFORE the change (see BatchProcessArbo for the
+// reference's own post-insert flow).
+func (e *Engine) BatchProcessPacked(levels int, oldRoots []fr.Element, packed [][]byte, oldKeys, oldValues []fr.Element,
+	isOld0 []byte, newKeys, newValues []fr.Element, fnc0, fnc1 []byte) (newRoots []fr.Element, status []byte, err error) {
+	n := len(newKeys)
+	newRoots, status = make([]fr.Element, n), make([]byte, n)
+	blob, offsets := packBlob(packed)
+	err = e.err(C.gcp_smt_process_packed(e.ctx, C.int(levels), C.size_t(n), elemPtr(oldRoots), bytePtr(blob),
+		(*C.uint64_t)(unsafe.Pointer(&offsets[0])), elemPtr(oldKeys), elemPtr(oldValues), bytePtr(isOld0), elemPtr(newKeys),
+		elemPtr(newValues), bytePtr(fnc0), bytePtr(fnc1), elemPtr(newRoots), bytePtr(status), C.GCP_FMT_MONTGOMERY))
+	return
+}
+
+// FixedBaseScalarMul mirrors FixedBaseScalarMulBN254 (elgamal/mul.go:76): points come back as (X, Y) pairs.
+func (e *Engine) FixedBaseScalarMul(scalars []fr.Element, c Coords) (points []fr.Element, status []byte, err error) {
+	n := len(scalars)
+	points, status = make([]fr.Element, 2*n), make([]byte, n)
+	err = e.err(C.gcp_elgamal_fixed_base_mul(e.ctx, elemPtr(scalars), C.size_t(n), elemPtr(points), bytePtr(status), fmtOf(c)))
+	return
+}
+
+// ScalarMul mirrors curve.ScalarMul (gnark twistededwards; elgamal/encrypt.go:55): out[i] = [scalars[i]] points[i], or with a
+// second base [s]P + [s2]P2 in one pass (points2 / scalars2 both nil or both given).
+func (e *Engine) ScalarMul(points, scalars, points2, scalars2 []fr.Element, c Coords) (out []fr.Element, status []byte, err error) {
+	n := len(scalars)
+	out, status = make([]fr.Element, 2*n), make([]byte, n)
+	err = e.err(C.gcp_elgamal_scalar_mul(e.ctx, elemPtr(points), elemPtr(scalars), elemPtr(points2), elemPtr(scalars2),
+		C.size_t(n), elemPtr(out), bytePtr(status), fmtOf(c)))
+	return
+}
+
+// BatchEncryptPerKey mirrors (*Ciphertext).Encrypt (elgamal/encrypt.go:42) with one public key per item.
+func (e *Engine) BatchEncryptPerKey(pubKeys, k, m []fr.Element, c Coords) (ct []fr.Element, status []byte, err error) {
+	n := len(k)
+	ct, status = make([]fr.Element, 4*n), make([]byte, n)
+	err = e.err(C.gcp_elgamal_encrypt(e.ctx, elemPtr(pubKeys), 1, elemPtr(k), elemPtr(m), C.size_t(n), elemPtr(ct),
+		bytePtr(status), fmtOf(c)))
+	return
+}
+
+// CiphertextNeg mirrors (*Ciphertext).Neg (elgamal/ciphertext.go:37).
+func (e *Engine) CiphertextNeg(a []fr.Element) (out []fr.Element, status []byte, err error) {
+	n := len(a) / 4
+	out, status = make([]fr.Element, 4*n), make([]byte, n)
+	err = e.err(C.gcp_elgamal_neg(e.ctx, elemPtr(a), C.size_t(n), elemPtr(out), bytePtr(status), C.GCP_FMT_MONTGOMERY))
+	return
+}
+
+// CiphertextIsEqual mirrors (*Ciphertext).IsEqual (elgamal/ciphertext.go:79).
+func (e *Engine) CiphertextIsEqual(a, b []fr.Element) (flags, status []byte, err error) {
+	n := len(a) / 4
+	flags, status = make([]byte, n), make([]byte, n)
+	err = e.err(C.gcp_elgamal_is_equal(e.ctx, elemPtr(a), elemPtr(b), C.size_t(n), bytePtr(flags), bytePtr(status)))
+	return
+}
+
+// CiphertextSelect mirrors (*Ciphertext).Select (elgamal/ciphertext.go:90): out[i] = sel[i] ? i1[i] : i2[i].
+func (e *Engine) CiphertextSelect(sel []byte, i1, i2 []fr.Element) (out []fr.Element, status []byte, err error) {
+	n := len(sel)
+	out, status = make([]fr.Element, 4*n), make([]byte, n)
+	err = e.err(C.gcp_elgamal_select(e.ctx, bytePtr(sel), elemPtr(i1), elemPtr(i2), C.size_t(n), elemPtr(out), bytePtr(status)))
+	return
+}
+
+// AssertDecrypt mirrors (*Ciphertext).AssertDecrypt (elgamal/ciphertext.go:50): flags[i] = the gadget's assertions hold.
+func (e *Engine) AssertDecrypt(ct, privKeys, msgs []fr.Element, c Coords) (flags, status []byte, err error) {
+	n := len(privKeys)
+	flags, status = make([]byte, n), make([]byte, n)
+	err = e.err(C.gcp_elgamal_assert_decrypt(e.ctx, elemPtr(ct), elemPtr(privKeys), elemPtr(msgs), C.size_t(n), bytePtr(flags),
+		bytePtr(status), fmtOf(c)))
+	return
+}
+
+// VerifyDecryptionProofs mirrors DecryptionProof.Verify (elgamal/ciphertext.go:124) with hFn = poseidon.MultiHash.
+func (e *Engine) VerifyDecryptionProofs(pubKeys, ct, msgs, a1, a2, z []fr.Element, c Coords) (flags, status []byte, err error) {
+	n := len(z)
+	flags, status = make([]byte, n), make([]byte, n)
+	err = e.err(C.gcp_elgamal_verify_decryption_proof(e.ctx, elemPtr(pubKeys), elemPtr(ct), elemPtr(msgs), elemPtr(a1),
+		elemPtr(a2), elemPtr(z), C.size_t(n), bytePtr(flags), bytePtr(status), fmtOf(c)))
+	return
+}
+
+// EdDSAVerify mirrors eddsa.Verifier.IsValid (ecc/bn254/eddsa/verifier.go:55): A and R in iden3 (TE) coordinates.
+func (e *Engine) EdDSAVerify(pubKeysTE, sigRTE, sigS, msgs []fr.Element) (flags, status []byte, err error) {
+	n := len(sigS)
+	flags, status = make([]byte, n), make([]byte, n)
+	err = e.err(C.gcp_eddsa_verify(e.ctx, elemPtr(pubKeysTE), elemPtr(sigRTE), elemPtr(sigS), elemPtr(msgs), C.size_t(n),
+		bytePtr(flags), bytePtr(status), C.GCP_FMT_MONTGOMERY))
+	return
+}
+
+// FromTEtoRTE / FromRTEtoTE mirror ecc/format/twistededwards.go:29-48 over n points (X, Y pairs).  These are canonical-form
+// helpers: the elements cross the boundary as canonical little-endian integers (fr.Element.Bytes reversed), not as
+// fr.Element memory; a caller that holds fr.Elements uses the CoordsTE flag of the ElGamal calls instead.
+func (e *Engine) FromTEtoRTE(pointsLE []byte) (out []byte, status []byte, err error) {
+	n := len(pointsLE) / 64
+	out, status = make([]byte, 64*n), make([]byte, n)
+	err = e.err(C.gcp_te_to_rte(e.ctx, unsafe.Pointer(bytePtr(pointsLE)), C.size_t(n), unsafe.Pointer(bytePtr(out)), bytePtr(status)))
+	return
+}
+func (e *Engine) FromRTEtoTE(pointsLE []byte) (out []byte, status []byte, err error) {
+	n := len(pointsLE) / 64
+	out, status = make([]byte, 64*n), make([]byte, n)
+	err = e.err(C.gcp_rte_to_te(e.ctx, unsafe.Pointer(bytePtr(pointsLE)), C.size_t(n), unsafe.Pointer(bytePtr(out)), bytePtr(status)))
+	return
+}
+
+// BatchMiMC7 mirrors mimc7 New / Write / Sum (hash/native/bn254/mimc7/mimc.go:47) over rows of `length` inputs (1..62).
+func (e *Engine) BatchMiMC7(in []fr.Element, length int) (out []fr.Element, status []byte, err error) {
+	if length <= 0 || len(in)%length != 0 {
+		return nil, nil, errors.New("bad inputs provided")
+	}
+	n := len(in) / length
+	out, status = make([]fr.Element, n), make([]byte, n)
+	err = e.err(C.gcp_mimc7_hash(e.ctx, elemPtr(in), C.int(length), C.size_t(n), elemPtr(out), bytePtr(status),
+		C.GCP_FMT_MONTGOMERY))
+	return
+}
+
+// BallotBatch is the end-to-end voter batch (BASELINE config 5): per voter one census inclusion proof (arbo packed strings)
+// and nFields encrypted values; the ciphertexts of the voters whose proof verifies are folded.  flags / status per voter,
+// tally (4 * nFields elements) and tallyStatus per field.
+func (e *Engine) BallotBatch(levels int, roots []fr.Element, packed [][]byte, keys, values []fr.Element, pubKey [2]fr.Element,
+	k, m []fr.Element, nFields int, c Coords) (flags, status []byte, tally []fr.Element, tallyStatus []byte, err error) {
+	n := len(keys)
+	flags, status = make([]byte, n), make([]byte, n)
+	tally, tallyStatus = make([]fr.Element, 4*nFields), make([]byte, nFields)
+	blob, offsets := packBlob(packed)
+	shared := 0
+	if len(roots) == 1 && n != 1 {
+		shared = 1
+	}
+	err = e.err(C.gcp_ballot_batch(e.ctx, C.int(levels), C.size_t(n), elemPtr(roots), C.int(shared), nil, bytePtr(blob),
+		(*C.uint64_t)(unsafe.Pointer(&offsets[0])), elemPtr(keys), elemPtr(values), unsafe.Pointer(&pubKey[0]), elemPtr(k),
+		elemPtr(m), C.int(nFields), bytePtr(flags), bytePtr(status), elemPtr(tally), bytePtr(tallyStatus), fmtOf(c)))
+	return
+}
+
 // PinnedElements allocates n field elements in page-locked host memory (gcp_host_alloc): host-buffer calls copy from
 // it at full PCIe rate and overlap with the kernels.  Release with FreePinned(&s[0]).
 func PinnedElements(n int) ([]fr.Element, error) {
@@ -402,6 +596,47 @@ func (g *Group) EncryptTally(pubKey [2]fr.Element, k, m []fr.Element, nFields in
 		C.size_t(nBallots), C.int(nFields), elemPtr(out), bytePtr(status), C.GCP_FMT_MONTGOMERY))
 	return
 }
+
+// BatchHash is Engine.BatchHash over all GPUs of the group.
+func (g *Group) BatchHash(in []fr.Element, arity int) (out []fr.Element, status []byte, err error) {
+	if arity <= 0 || len(in)%arity != 0 {
+		return nil, nil, errors.New("bad inputs provided")
+	}
+	n := len(in) / arity
+	out, status = make([]fr.Element, n), make([]byte, n)
+	err = g.err(C.gcp_group_poseidon_hash(g.grp, elemPtr(in), C.int(arity), C.size_t(n), elemPtr(out), bytePtr(status),
+		C.GCP_FMT_MONTGOMERY))
+	return
+}
+
+// BatchEncrypt is Engine.BatchEncrypt (one shared key) over all GPUs of the group.
+func (g *Group) BatchEncrypt(pubKey [2]fr.Element, k, m []fr.Element) (ct []fr.Element, status []byte, err error) {
+	n := len(k)
+	ct, status = make([]fr.Element, 4*n), make([]byte, n)
+	err = g.err(C.gcp_group_elgamal_encrypt(g.grp, unsafe.Pointer(&pubKey[0]), 0, elemPtr(k), elemPtr(m), C.size_t(n),
+		elemPtr(ct), bytePtr(status), C.GCP_FMT_MONTGOMERY))
+	return
+}
+
+// BallotBatch is Engine.BallotBatch over all GPUs: voters sharded by index range, partial tallies all-gathered on the devices.
+func (g *Group) BallotBatch(levels int, roots []fr.Element, packed [][]byte, keys, values []fr.Element, pubKey [2]fr.Element,
+	k, m []fr.Element, nFields int) (flags, status []byte, tally []fr.Element, tallyStatus []byte, err error) {
+	n := len(keys)
+	flags, status = make([]byte, n), make([]byte, n)
+	tally, tallyStatus = make([]fr.Element, 4*nFields), make([]byte, nFields)
+	blob, offsets := packBlob(packed)
+	shared := 0
+	if len(roots) == 1 && n != 1 {
+		shared = 1
+	}
+	err = g.err(C.gcp_group_ballot_batch(g.grp, C.int(levels), C.size_t(n), elemPtr(roots), C.int(shared), nil, bytePtr(blob),
+		(*C.uint64_t)(unsafe.Pointer(&offsets[0])), elemPtr(keys), elemPtr(values), unsafe.Pointer(&pubKey[0]), elemPtr(k),
+		elemPtr(m), C.int(nFields), bytePtr(flags), bytePtr(status), elemPtr(tally), bytePtr(tallyStatus), C.GCP_FMT_MONTGOMERY))
+	return
+}
+
+// UsesNCCL reports whether the group exchanges its partial tallies with ncclAllGather (more than one device).
+func (g *Group) UsesNCCL() bool { return C.gcp_group_uses_nccl(g.grp) != 0 }
 
 // BatchVerifyPacked is Engine.BatchVerifyPacked over all GPUs of the group.
 func (g *Group) BatchVerifyPacked(p *Proofs, packed [][]byte) (flags, status []byte, err error) {
