@@ -10,6 +10,7 @@
 #include "proofs.cuh"
 #include "varbase.cuh"
 #include "varbase_reg.cuh"
+#include "varbase_flat.cuh"
 #include "mimc7.cuh"
 #include "poseidon2.cuh"
 #include "kernels.h"
@@ -519,15 +520,17 @@ static int varbase_min_blocks() {
   return v;
 }
 
-// GCP_B200_VB_IMPL=reg: the register-resident window kernel with out-of-line multipliers (varbase_reg.cuh) instead of the
-// shared-memory interpreter
-static bool varbase_reg_form() {
-  static const bool v = [] {
+// The window kernel: the flat interpreter (varbase_flat.cuh) unless GCP_B200_VB_IMPL selects, for measurements, `interp`
+// (the step-structured interpreter of varbase.cuh) or `reg` (the register-resident kernel with out-of-line multipliers,
+// varbase_reg.cuh)
+static int varbase_impl() {  // 0 flat, 1 interp, 2 reg
+  static const int v = [] {
     const char* e = getenv("GCP_B200_VB_IMPL");
-    return e && e[0] == 'r';
+    return (e && e[0] == 'r') ? 2 : ((e && e[0] == 'i') ? 1 : 0);
   }();
   return v;
 }
+static bool varbase_reg_form() { return varbase_impl() == 2; }
 
 static cudaError_t launch_varbase_window(const u32* bases, const u32* s0, const u32* s1, int n_bases, size_t n,
                                          const u8* status, u32* table, u32* out, cudaStream_t stream) {
@@ -543,6 +546,10 @@ static cudaError_t launch_varbase_window(const u32* bases, const u32* s0, const 
   const size_t smem = (size_t)VB_SLOTS * 2 * VB_THREADS * sizeof(uint4);
   if (varbase_reg_form()) {
     varbase_window_reg_kernel<4><<<blocks_for(n, VB_THREADS), VB_THREADS, 0, stream>>>(a);
+  } else if (varbase_impl() == 0) {
+    cudaFuncSetAttribute(varbase_flat_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VF_SMEM_BYTES);
+    cudaFuncSetAttribute(varbase_flat_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    varbase_flat_kernel<4><<<blocks_for(n, VB_THREADS), VB_THREADS, VF_SMEM_BYTES, stream>>>(a);
   } else if (varbase_min_blocks() == 5) {
     cudaFuncSetAttribute(varbase_window_kernel<5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     varbase_window_kernel<5><<<blocks_for(n, VB_THREADS), VB_THREADS, smem, stream>>>(a);
@@ -556,6 +563,11 @@ static cudaError_t launch_varbase_window(const u32* bases, const u32* s0, const 
 size_t varbase_wave_items(int sm_count) {
   const size_t smem = (size_t)VB_SLOTS * 2 * VB_THREADS * sizeof(uint4);
   if (varbase_reg_form()) return wave_items(varbase_window_reg_kernel<4>, VB_THREADS, 0, sm_count, 4);
+  if (varbase_impl() == 0) {
+    cudaFuncSetAttribute(varbase_flat_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VF_SMEM_BYTES);
+    cudaFuncSetAttribute(varbase_flat_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return wave_items(varbase_flat_kernel<4>, VB_THREADS, VF_SMEM_BYTES, sm_count, 4);
+  }
   if (varbase_min_blocks() == 5) {
     cudaFuncSetAttribute(varbase_window_kernel<5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     return wave_items(varbase_window_kernel<5>, VB_THREADS, smem, sm_count, 5);
