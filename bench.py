@@ -202,9 +202,20 @@ def measure_extras(torch, dist, eng, g, world, rank):
 # BASELINE configs 3, 4, 5 at their stated sizes, and the single-process (gcp_group_*) leg
 # ------------------------------------------------------------------------------------------------------
 N_FIELDS = 8
-# executed work model of the ElGamal kernels: per encryption 13 + 13 signed 20-bit windows of k (C1 = [k]G,
-# [k]PK) and one non-zero window of a 16-bit m, each a mixed addition of 7 multiplies; the fused kernel never normalises
-WIDE_PER_ENCRYPTION = 27 * 7 * FR_MUL_WIDE
+# Window width of the fixed-base tables the ElGamal legs run with (gcp_ctx_set_fixed_base_window): 24 bits = 8.9 GB per
+# base, 11 windows.  The library's own default is 20 bits (654 MB, 13 windows) until a base has served 2^27 multiplications;
+# the bench pins the width so that no table is rebuilt inside a timed region.
+FB_WINDOW_BITS = 24
+
+
+def wide_per_encryption(bits=None):
+    """Executed work model of the ElGamal kernels: per encryption W + W signed windows of k (C1 = [k]G,
+    [k]PK; W = ceil(256 / bits)) and one non-zero window of a 16-bit m, each a mixed addition of 7 multiplies; the fused
+    kernel never normalises."""
+    bits = bits or FB_WINDOW_BITS
+    return (2 * ((256 + bits - 1) // bits) + 1) * 7 * FR_MUL_WIDE
+
+
 # Keccak-f[1600] on 32-bit halves (keccak.cuh): per round 122 LOP3 (column parities 20, theta folded into rho's input 50,
 # chi 50, iota 2) + 58 SHF (rot(c, 1) 10, rho 48): the SASS of the loop body holds exactly these (cuobjdump)
 ALU_PER_ADDRESS = 24 * 180 + 40          # + index arithmetic and the loop counter
@@ -332,10 +343,10 @@ def measure_config3(torch, dist, eng, g, world, rank, log2_ballots, peak_wide, d
         want_ok = all(ints(got[f]) == oeg.serialize(oeg.encrypt(pk_int, ksum[f] % oed.ORDER, int(msum[f].item()) % oed.ORDER))
                       for f in range(N_FIELDS))
         out["tally_matches_closed_form"] = bool(want_ok)
-        achieved = WIDE_PER_ENCRYPTION * (nb * N_FIELDS) / (ms * 1e-3)     # per GPU
+        achieved = wide_per_encryption() * (nb * N_FIELDS) / (ms * 1e-3)     # per GPU
         out["roofline"] = {"bound": "int-pipe", "kernel": "encrypt_tally_partial_kernel", "achieved": achieved / 1e12,
                            "peak": peak_wide / 1e12, "unit": "T IMAD.WIDE.U32/s", "frac": achieved / peak_wide,
-                           "wide_mul_per_encryption": WIDE_PER_ENCRYPTION,
+                           "wide_mul_per_encryption": wide_per_encryption(), "fixed_base_window_bits": FB_WINDOW_BITS,
                            "hbm_gb_per_s": nb * N_FIELDS * 64 / (ms * 1e-3) / 1e9}
     # end to end: the same shard through gcp_elgamal_encrypt_tally from page-locked HOST scalars, then the same exchange
     hk, hm = _pinned_copy(torch, k), _pinned_copy(torch, m)
@@ -520,11 +531,11 @@ def measure_config5(torch, dist, eng, g, world, rank, log2_voters, peak_wide, do
             ints(got[f]) == oeg.serialize(oeg.encrypt(pk_int, ks[f] % oed.ORDER, int(msum[f].item()) % oed.ORDER))
             for f in range(N_FIELDS)))
         w3, w4 = wide_per_hash(3, 57), wide_per_hash(4, 56)
-        per_voter = c["mean_levels"] * (w3 + FR_MUL_WIDE) + w4 + 4 * FR_MUL_WIDE + N_FIELDS * WIDE_PER_ENCRYPTION * (15.0 / 16.0)
+        per_voter = c["mean_levels"] * (w3 + FR_MUL_WIDE) + w4 + 4 * FR_MUL_WIDE + N_FIELDS * wide_per_encryption() * (15.0 / 16.0)
         achieved = per_voter * mine / (ms * 1e-3)
         out["roofline"] = {"bound": "int-pipe", "kernel": "smt_path_kernel + encrypt_tally_partial_kernel", "achieved": achieved / 1e12,
                            "peak": peak_wide / 1e12, "unit": "T IMAD.WIDE.U32/s", "frac": achieved / peak_wide,
-                           "wide_mul_per_voter": per_voter,
+                           "wide_mul_per_voter": per_voter, "fixed_base_window_bits": FB_WINDOW_BITS,
                            "hbm_gb_per_s": mine * (N_LEVELS * 32 + 96 + N_FIELDS * 64) / (ms * 1e-3) / 1e9}
     if world > 1:
         r64 = res.view(-1).to(torch.int64)
@@ -941,6 +952,7 @@ def main():
         torch.cuda.set_device(0)
     dev_index = torch.cuda.current_device()
     eng = g.Engine(dev_index)
+    eng.set_fixed_base_window(FB_WINDOW_BITS)
     n = 1 << args.log2_proofs
     stream = torch.cuda.current_stream()
 
@@ -1037,6 +1049,7 @@ def main():
     extras = None
     if not args.no_extras:
         extras = measure_extras(torch, dist, eng, g, world, rank)
+        extras["fixed_base_window_bits"] = FB_WINDOW_BITS
         if world == 1:
             extras["census_like_e2e"] = measure_census_like(torch, eng, g)
             extras["config1_poseidon_batch_1024"] = measure_config1(eng, g)

@@ -72,6 +72,8 @@ SIGNATURES = {
                                                    c_int, c_void_p]),
     "gcp_ctx_set_smt_hasher": (c_int, [c_void_p, c_int]),
     "gcp_ctx_smt_hasher": (c_int, [c_void_p]),
+    "gcp_ctx_set_fixed_base_window": (c_int, [c_void_p, c_int]),
+    "gcp_ctx_fixed_base_window": (c_int, [c_void_p, c_int]),
     "gcp_copy_threads": (c_int, []),
     "gcp_copy_probe": (c_int, [c_size_t, POINTER(ctypes.c_double)]),
     "gcp_smt_verify_packed": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -70,9 +70,20 @@ struct gcp_ctx {
   uint64_t launches = 0;
   int sm_count = 0;
   // ElGamal: Niels tables of G and of the cached shared public key
+  // (d_tabG / d_tabPK point at the ENTRIES of the tables, which is what the kernels take; fb[] owns the allocations)
   u32* d_tabG = nullptr;
   u32* d_tabPK = nullptr;
-  u32* d_fb_ext = nullptr;    // extended-coordinate scratch for table construction
+  struct FbTable {
+    u32* alloc = nullptr;     // header + entries
+    int cap_bits = 0;         // window width the allocation can hold
+    int wbits = 0;            // window width of the table it holds now
+    uint64_t uses = 0;        // scalar multiplications served by the base it holds
+  } fb[2];                    // 0: G, 1: the cached shared public key
+  int fb_forced_bits = 0;     // gcp_ctx_set_fixed_base_window; 0: widen a table once its base has repaid the build
+  int fb_wide_bits = 24;      // GCP_B200_FB_WBITS
+  uint64_t fb_widen_at = (uint64_t)1 << 27;  // GCP_B200_FB_WIDEN_AT
+  bool fb_wide_failed = false;               // the wide allocation did not fit: stay narrow
+  u32* d_fb_small = nullptr;  // table-construction scratch (fb_small_scratch_bytes)
   u32* d_base_xy = nullptr;   // 16 words: base point being tabulated
   u32* d_flagG = nullptr;     // 1 word
   u32* d_flagPK = nullptr;    // 1 word: cached key is canonical and on the curve
@@ -356,7 +367,7 @@ void gcp_ctx_destroy(gcp_ctx* ctx) {
     if (ctx->stage_buf[i]) cudaFreeHost(ctx->stage_buf[i]);
   }
   if (ctx->d_tables) cudaFree(ctx->d_tables);
-  for (u32* p : {ctx->d_tabG, ctx->d_tabPK, ctx->d_fb_ext, ctx->d_base_xy, ctx->d_flagG, ctx->d_flagPK, ctx->d_p2_keys})
+  for (u32* p : {ctx->fb[0].alloc, ctx->fb[1].alloc, ctx->d_fb_small, ctx->d_base_xy, ctx->d_flagG, ctx->d_flagPK, ctx->d_p2_keys})
     if (p) cudaFree(p);
   if (ctx->out_arena) cudaFreeHost(ctx->out_arena);
   for (auto& o : ctx->out_slot) {
@@ -416,6 +427,64 @@ int gcp_host_alloc(size_t bytes, void** out) {
 
 void gcp_host_free(void* p) {
   if (p) cudaFreeHost(p);
+}
+
+// ---- fixed-base tables (elgamal.cuh) ---------------------------------------------------------------------------------
+// Every table starts FB_NARROW_BITS wide (654 MB, ~2 ms to build).  A base that has served fb_widen_at scalar
+// multiplications (default 2^27: the 8.9 GB, ~45 ms build of the 24-bit table is repaid by its 12-15 % shorter
+// multiplications at about that point) gets the wide table; gcp_ctx_set_fixed_base_window forces one width.
+static constexpr int FB_NARROW_BITS = 20;
+
+// Builds the table of the point in ctx->d_base_xy (which = 1) or of the generator (which = 0) at `wbits`; the streams must
+// be idle.  A wider table than the allocation holds is built beside the old one and swapped in.
+static int fb_build_table(gcp_ctx* ctx, int which, int wbits, int base_mont, int te, cudaStream_t st) {
+  gcp_ctx::FbTable& t = ctx->fb[which];
+  cudaError_t e;
+  u32* fresh = nullptr;
+  if (wbits > t.cap_bits) {
+    if ((e = cudaMalloc(&fresh, fb_table_bytes(wbits))) != cudaSuccess) {
+      cudaGetLastError();
+      if (!t.alloc) return ctx->cuda_fail(e, "cudaMalloc fixed-base table");
+      ctx->fb_wide_failed = true;  // no room for the wide table: keep multiplying out of the one we have
+      if (which == 0) return GCP_OK;
+      wbits = t.cap_bits;
+    }
+  }
+  u32* dst = fresh ? fresh : t.alloc;
+  if (which == 0 && (e = upload_generator(ctx->d_base_xy, st)) != cudaSuccess) return ctx->cuda_fail(e, "upload generator");
+  if ((e = launch_fb_table_build(ctx->d_base_xy, base_mont, ctx->d_fb_small, dst, which ? ctx->d_flagPK : ctx->d_flagG, st, te,
+                                 wbits)) != cudaSuccess ||
+      (e = cudaStreamSynchronize(st)) != cudaSuccess) {
+    if (fresh) cudaFree(fresh);
+    return ctx->cuda_fail(e, "fixed-base table build");
+  }
+  ctx->launches += 4;
+  if (fresh) {
+    if (t.alloc) cudaFree(t.alloc);
+    t.alloc = fresh;
+    t.cap_bits = wbits;
+  }
+  t.wbits = wbits;
+  (which ? ctx->d_tabPK : ctx->d_tabG) = fb_table_entries(t.alloc);
+  return GCP_OK;
+}
+
+static int fb_wanted_bits(const gcp_ctx* ctx, uint64_t uses) {
+  if (ctx->fb_forced_bits) return ctx->fb_forced_bits;
+  return (uses >= ctx->fb_widen_at && !ctx->fb_wide_failed) ? ctx->fb_wide_bits : FB_NARROW_BITS;
+}
+
+// `n` more multiplications by G are about to be queued on `st`: widen G's table if it has earned it
+static int fb_note_g_use(gcp_ctx* ctx, uint64_t n, cudaStream_t st) {
+  gcp_ctx::FbTable& t = ctx->fb[0];
+  t.uses += n;
+  const int want = fb_wanted_bits(ctx, t.uses);
+  if (want == t.wbits || (want < t.wbits && !ctx->fb_forced_bits)) return GCP_OK;
+  cudaError_t e;  // work queued earlier may still read the table
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess || (e = cudaStreamSynchronize(ctx->stream[0])) != cudaSuccess ||
+      (e = cudaStreamSynchronize(ctx->stream[1])) != cudaSuccess)
+    return ctx->cuda_fail(e, "stream sync");
+  return fb_build_table(ctx, 0, want, 0, 0, st);
 }
 
 int gcp_ctx_create(int device, const char* constants_path, gcp_ctx** out) {
@@ -511,17 +580,20 @@ int gcp_ctx_create(int device, const char* constants_path, gcp_ctx** out) {
   // fixed-base table of the generator G (elgamal/mul.go:26-72 restated with wider windows), built on the device
   if ((e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess)
     return bail(ctx->cuda_fail(e, "device attribute"));
-  if ((e = cudaMalloc(&ctx->d_tabG, fb_table_bytes())) != cudaSuccess ||
-      (e = cudaMalloc(&ctx->d_tabPK, fb_table_bytes())) != cudaSuccess ||
-      (e = cudaMalloc(&ctx->d_fb_ext, fb_ext_scratch_bytes())) != cudaSuccess ||
+  if (const char* v = getenv("GCP_B200_FB_WBITS")) {
+    const int b = atoi(v);
+    if (b >= FB_NARROW_BITS && b <= 26) ctx->fb_wide_bits = b;
+  }
+  if (const char* v = getenv("GCP_B200_FB_WIDEN_AT")) ctx->fb_widen_at = strtoull(v, nullptr, 10);
+  if ((e = cudaMalloc(&ctx->d_fb_small, fb_small_scratch_bytes())) != cudaSuccess ||
       (e = cudaMalloc(&ctx->d_base_xy, 64)) != cudaSuccess || (e = cudaMalloc(&ctx->d_flagG, 4)) != cudaSuccess ||
       (e = cudaMalloc(&ctx->d_flagPK, 4)) != cudaSuccess)
-    return bail(ctx->cuda_fail(e, "cudaMalloc fixed-base tables"));
-  if ((e = upload_generator(ctx->d_base_xy, ctx->stream[0])) != cudaSuccess ||
-      (e = launch_fb_table_build(ctx->d_base_xy, 0, ctx->d_fb_ext, ctx->d_tabG, ctx->d_flagG, ctx->stream[0])) != cudaSuccess)
-    return bail(ctx->cuda_fail(e, "fixed-base table build"));
-  ctx->launches += 3;
-  if ((e = cudaStreamSynchronize(ctx->stream[0])) != cudaSuccess) return bail(ctx->cuda_fail(e, "ctx init sync"));
+    return bail(ctx->cuda_fail(e, "cudaMalloc fixed-base scratch"));
+  {
+    int rc = fb_build_table(ctx, 0, FB_NARROW_BITS, 0, 0, ctx->stream[0]);
+    if (rc == GCP_OK) rc = fb_build_table(ctx, 1, FB_NARROW_BITS, 0, 0, ctx->stream[0]);  // a valid table (of G) until a key arrives
+    if (rc != GCP_OK) return bail(rc);
+  }
   {
     u32 flag = 0;
     if ((e = cudaMemcpy(&flag, ctx->d_flagG, 4, cudaMemcpyDeviceToHost)) != cudaSuccess)
@@ -1291,8 +1363,9 @@ static int check_fmt_points(gcp_ctx* ctx, int fmt) {
 static inline int elem_fmt(int fmt) { return fmt & GCP_FMT_MONTGOMERY; }
 static inline int coords_te(int fmt) { return (fmt & GCP_COORDS_TE) ? 1 : 0; }
 
-// Make d_tabPK the table of the given shared public key (64 bytes, host or device memory).
-static int ensure_pk_table(gcp_ctx* ctx, const void* pk, bool pk_on_device, int fmt, cudaStream_t st) {
+// Make d_tabPK the table of the given shared public key (64 bytes, host or device memory); `uses` multiplications by it
+// (and as many by G) are about to be queued.
+static int ensure_pk_table(gcp_ctx* ctx, const void* pk, bool pk_on_device, int fmt, cudaStream_t st, uint64_t uses) {
   unsigned char host_pk[64];
   if (pk_on_device) {
     CU(cudaMemcpyAsync(host_pk, pk, 64, cudaMemcpyDeviceToHost, st), "D2H public key");
@@ -1300,19 +1373,42 @@ static int ensure_pk_table(gcp_ctx* ctx, const void* pk, bool pk_on_device, int 
   } else {
     memcpy(host_pk, pk, 64);
   }
-  if (ctx->pk_cached_fmt == fmt && memcmp(host_pk, ctx->pk_cached, 64) == 0) return GCP_OK;
+  int rc = fb_note_g_use(ctx, uses, st);
+  if (rc != GCP_OK) return rc;
+  gcp_ctx::FbTable& t = ctx->fb[1];
+  const bool same = ctx->pk_cached_fmt == fmt && memcmp(host_pk, ctx->pk_cached, 64) == 0;
+  t.uses = same ? t.uses + uses : uses;
+  const int want = fb_wanted_bits(ctx, t.uses);
+  if (same && (want == t.wbits || (want < t.wbits && !ctx->fb_forced_bits))) return GCP_OK;
   ctx->pk_cached_fmt = -1;
   // the previous table may still be in use by work queued on the other stream
+  CU(cudaStreamSynchronize(st), "stream sync");
   CU(cudaStreamSynchronize(ctx->stream[0]), "stream sync");
   CU(cudaStreamSynchronize(ctx->stream[1]), "stream sync");
   CU(cudaMemcpyAsync(ctx->d_base_xy, host_pk, 64, cudaMemcpyHostToDevice, st), "H2D public key");
-  CU(launch_fb_table_build(ctx->d_base_xy, elem_fmt(fmt), ctx->d_fb_ext, ctx->d_tabPK, ctx->d_flagPK, st, coords_te(fmt)),
-     "public-key table build");
-  ctx->launches += 3;
-  CU(cudaStreamSynchronize(st), "public-key table build");
+  rc = fb_build_table(ctx, 1, want, elem_fmt(fmt), coords_te(fmt), st);
+  if (rc != GCP_OK) return rc;
   memcpy(ctx->pk_cached, host_pk, 64);
   ctx->pk_cached_fmt = fmt;
   return GCP_OK;
+}
+
+int gcp_ctx_set_fixed_base_window(gcp_ctx* ctx, int window_bits) {
+  if (!ctx) return GCP_ERR_BAD_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (window_bits != 0 && (window_bits < 8 || window_bits > 26))
+    return ctx->fail(GCP_ERR_BAD_ARG, "fixed-base window must be 0 (automatic) or 8..26 bits");
+  DeviceGuard device_guard(ctx->device);
+  if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
+  ctx->fb_forced_bits = window_bits;
+  ctx->fb_wide_failed = false;
+  if (window_bits == 0) return GCP_OK;  // the tables in place stay until their use counts ask for another width
+  return fb_note_g_use(ctx, 0, ctx->stream[0]);  // the key's table follows at its next use (ensure_pk_table)
+}
+
+int gcp_ctx_fixed_base_window(const gcp_ctx* ctx, int which) {
+  if (!ctx || which < 0 || which > 1) return GCP_ERR_BAD_ARG;
+  return ctx->fb[which].wbits;
 }
 
 static int fixed_base_dev_locked(gcp_ctx* ctx, const void* d_scalars, size_t n, void* d_out, uint8_t* d_status, int fmt,
@@ -1322,6 +1418,8 @@ static int fixed_base_dev_locked(gcp_ctx* ctx, const void* d_scalars, size_t n, 
   if (!d_scalars || !d_out || !d_status) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
   u32* xyz = (u32*)ctx->buf(xyz_slot, n * 96);
   if (!xyz) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
+  rc = fb_note_g_use(ctx, n, st);
+  if (rc != GCP_OK) return rc;
   CU(launch_fixed_base_mul(ctx->d_tabG, (const u32*)d_scalars, n, xyz, d_status, elem_fmt(fmt), st), "fixed-base kernel");
   CU(launch_normalize(xyz, n, (u32*)d_out, d_status, 1, elem_fmt(fmt), st, 24, coords_te(fmt)), "normalize kernel");
   ctx->launches += 2;
@@ -1403,7 +1501,7 @@ int gcp_elgamal_encrypt_dev(gcp_ctx* ctx, const void* d_pub_key, int pk_per_item
   if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   if (n && !pk_per_item) {
     if (!d_pub_key) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
-    int rc = ensure_pk_table(ctx, d_pub_key, true, fmt, (cudaStream_t)stream);
+    int rc = ensure_pk_table(ctx, d_pub_key, true, fmt, (cudaStream_t)stream, n);
     if (rc != GCP_OK) return rc;
   }
   return encrypt_dev_locked(ctx, d_pub_key, pk_per_item, d_k, d_m, n, d_out_ct, d_status, fmt, (cudaStream_t)stream, 43, 98);
@@ -1461,7 +1559,7 @@ int gcp_elgamal_encrypt_tally_dev(gcp_ctx* ctx, const void* d_pub_key, const voi
   if (!device_guard.ok) return ctx->fail(GCP_ERR_CUDA, "cudaSetDevice failed");
   int rc = encrypt_tally_check(ctx, d_pub_key, d_k, d_m, n_ballots, n_fields, d_out, d_status, fmt);
   if (rc != GCP_OK) return rc;
-  rc = ensure_pk_table(ctx, d_pub_key, true, fmt, (cudaStream_t)stream);
+  rc = ensure_pk_table(ctx, d_pub_key, true, fmt, (cudaStream_t)stream, (uint64_t)n_ballots * n_fields);
   if (rc != GCP_OK) return rc;
   rc = encrypt_tally_dev_locked(ctx, d_k, d_m, nullptr, n_ballots, n_fields, d_out, d_status, fmt, (cudaStream_t)stream, 44);
   if (rc != GCP_OK) return rc;
@@ -1512,7 +1610,7 @@ static int encrypt_tally_host(gcp_ctx* ctx, const void* pub_key, const void* k, 
   StreamGuard guard{ctx};
   int rc = encrypt_tally_check(ctx, pub_key, k, m, n_ballots, n_fields, out, status, fmt);
   if (rc != GCP_OK) return rc;
-  rc = ensure_pk_table(ctx, pub_key, false, fmt, ctx->stream[0]);
+  rc = ensure_pk_table(ctx, pub_key, false, fmt, ctx->stream[0], (uint64_t)n_ballots * n_fields);
   if (rc != GCP_OK) return rc;
   const size_t ballot_in = (size_t)n_fields * 32, ballot_ct = (size_t)n_fields * 128;
   // Chunk = 1/16 of the call, between 64 MB and 256 MB of k (and as much of m).  Every chunk costs ~0.4 ms of small kernels
@@ -1576,7 +1674,7 @@ static int elgamal_host(gcp_ctx* ctx, int kind, const void* pk, int pk_per_item,
   const size_t in0_b = (kind <= 1) ? 32 : 128, in1_b = (kind == 1) ? 32 : (kind == 2 ? 128 : 0);
   const size_t out_b = (kind == 0) ? 64 : 128;
   if (kind == 1 && !pk_per_item) {
-    rc = ensure_pk_table(ctx, pk, false, fmt, ctx->stream[0]);
+    rc = ensure_pk_table(ctx, pk, false, fmt, ctx->stream[0], n);
     if (rc != GCP_OK) return rc;
   }
   // per-item keys run the variable-base window kernel: whole resident waves of it; the other kinds are PCIe-bound and
@@ -1743,7 +1841,7 @@ int gcp_ballot_batch_dev(gcp_ctx* ctx, int n_levels, size_t n_voters, const void
   cudaStream_t st = (cudaStream_t)stream;
   int rc = encrypt_tally_check(ctx, d_pub_key, d_k, d_m, n_voters, n_fields, d_tally, d_tally_status, fmt);
   if (rc != GCP_OK) return rc;
-  rc = ensure_pk_table(ctx, d_pub_key, true, fmt, st);
+  rc = ensure_pk_table(ctx, d_pub_key, true, fmt, st, (uint64_t)n_voters * n_fields);
   if (rc != GCP_OK) return rc;
   rc = smt_verify_dev_locked(ctx, n_levels, n_voters, d_roots, shared_root, d_siblings, nullptr, nullptr, nullptr, d_keys,
                              d_values, nullptr, nullptr, d_flags, d_status, nullptr, elem_fmt(fmt), st, 2);
@@ -1776,7 +1874,7 @@ static int ballot_batch_host(gcp_ctx* ctx, int n_levels, size_t n_voters, const 
   if (n_levels < 2 || n_levels > 253) return ctx->fail(GCP_ERR_BAD_ARG, "n_levels must be in [2, 253]");
   if (n && (!roots || !keys || !values || !out_flags || !out_status || (is_packed && (!packed || !offsets))))
     return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
-  rc = ensure_pk_table(ctx, pub_key, false, fmt, ctx->stream[0]);
+  rc = ensure_pk_table(ctx, pub_key, false, fmt, ctx->stream[0], (uint64_t)n * n_fields);
   if (rc != GCP_OK) return rc;
   const size_t sib_bytes = (size_t)n_levels * 32, ballot_in = (size_t)n_fields * 32, ballot_ct = (size_t)n_fields * 128;
   ChunkPlan plan(n, smt_path_wave_items(ctx->sm_count), ((size_t)1 << 30) / (sib_bytes + 2 * ballot_in), true);

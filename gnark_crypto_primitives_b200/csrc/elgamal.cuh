@@ -8,8 +8,8 @@
 //   (*Ciphertext).Add        elgamal/ciphertext.go:24-32 component-wise curve.Add;  Neg :37-46
 //   tally                    left fold of Add from NewCiphertext (ciphertext.go:16-19) — caller's loop
 // All of these are group elements given by exact field arithmetic, so any addition order / window width yields
-// the same canonical affine coordinates.  This file uses signed FB_WBITS-bit windows over precomputed Niels tables
-// (tab[w][d-1] = [d * 2^(FB_WBITS*w)] B, d = 1 .. 2^(FB_WBITS-1)) for both G and a shared public key, accumulates in extended coordinates,
+// the same canonical affine coordinates.  This file uses signed w-bit windows over precomputed Niels tables
+// (tab[i][d-1] = [d * 2^(w*i)] B, d = 1 .. 2^(w-1), w = 20 or 24) for both G and a shared public key, accumulates in extended coordinates,
 // and converts to affine with chunked Montgomery batch inversion (one Fermat inversion per BATCH_INV points).
 #pragma once
 #include "edwards.cuh"
@@ -17,24 +17,33 @@
 
 namespace gcp {
 
-// Signed fixed windows: a scalar is recoded into FB_WINDOWS digits in [-2^(w-1)+1, 2^(w-1)]; the table holds the
-// positive multiples only (negating a Niels point is a swap and one field negation).  w = 20: 13 windows x 524 288
-// entries x 96 B = 654 MB per base, resident in HBM (180 GB), so a scalar multiplication costs 13 mixed additions
-// (the reference's 4-bit table, mul.go:26-72, needs up to 63; the first version of this file used w = 14, 19
-// additions out of a 14.9 MB L2-resident table).  A lookup is one random 96-byte read: 27 of them per ciphertext,
-// ~0.8 TB/s at 290 M ciphertexts/s, an eighth of the HBM bandwidth, staged one window ahead through shared memory (cp.async) so that its
-// latency hides behind the 7-multiply addition of the current window.  Building a table (6.8 M entries) takes ~0.1 s on the
-// device, once per context for G and once per election key.
-constexpr int FB_WBITS = 20;
-constexpr int FB_WINDOWS = (256 + FB_WBITS - 1) / FB_WBITS;      // 13 (260 bits >= 254-bit scalars + recoding carry)
-constexpr int FB_HALF = 1 << (FB_WBITS - 1);
-constexpr int FB_ENTRIES = FB_HALF;                              // digits 1 .. 2^(w-1)
-constexpr size_t FB_TABLE_WORDS = (size_t)FB_WINDOWS * FB_ENTRIES * 24;  // u32 words per table (96 B entries)
+// Signed fixed windows: a scalar is recoded into digits in [-2^(w-1)+1, 2^(w-1)]; the table holds the positive
+// multiples only (negating a Niels point is a swap and one field negation).  The window width w is a property of the
+// TABLE (a 128-byte header in front of the entries: {w, windows, entries per window}), so every kernel that takes a
+// table pointer works with any width and a context can replace a table by a wider one while it runs:
+//   w = 20: 13 windows x 2^19 entries x 96 B = 654 MB per base, 13 mixed additions per scalar multiplication (the
+//           reference's 4-bit table, mul.go:26-72, needs up to 63; the first version of this file used w = 14, 19
+//           additions out of a 14.9 MB L2-resident table); built in ~2 ms, the width every table starts with;
+//   w = 24: 11 windows x 2^23 entries = 8.9 GB per base, 11 additions: fused encrypt + tally 308 -> 351 M enc/s on
+//           2^24 ballots x 8 fields (w = 22: 332 M, w = 26 with 32 GB per base: 339 M - its random reads start to
+//           cost more than the saved addition, profiles/r02_fixed_base_window_sweep.jsonl); ~45 ms to build, used once
+//           a base has served enough multiplications to repay that (capi.cu: fb_note_use).  180 GB of HBM per GPU is
+//           what makes a 9 GB table per base a reasonable trade.
+// A lookup is one random 96-byte read (23-27 of them per ciphertext, ~0.8 TB/s, an eighth of the HBM bandwidth), staged
+// one window ahead through shared memory (cp.async) so that its latency hides behind the 7-multiply addition of the
+// current window.
+constexpr int FB_MIN_WBITS = 8, FB_MAX_WBITS = 26;
+constexpr int FB_HEADER_WORDS = FB_TABLE_HEADER_WORDS;  // kernels.h
+__host__ __device__ inline int fb_windows(int wbits) { return (256 + wbits - 1) / wbits; }  // 254-bit scalars + recoding carry
+__host__ __device__ inline int fb_lo_bits(int wbits) { return wbits / 2; }
+// small tables per window (table construction): [j] B_w for j < 2^lo and [j 2^lo] B_w for j <= 2^(w-1-lo)
+__host__ __device__ inline int fb_small_per_window(int wbits) {
+  return (1 << fb_lo_bits(wbits)) + (1 << (wbits - 1 - fb_lo_bits(wbits))) + 1;
+}
 constexpr int BATCH_INV = 32;
 
 // ---- table construction (one-time per base point) ------------------------------------------------------
-// step 1: ext[w * FB_ENTRIES + 0] = [2^(WBITS*w)] B.  base: affine standard-form (x, y), 16 words.
-// flag[0] = 1 if B is on the curve and canonical, else 0.
+// base: affine (x, y), 16 words, standard or Montgomery form.  flag[0] = 1 if B is on the curve and canonical, else 0.
 // iden3 / circom twisted-Edwards coordinates at the boundary (ecc/format/twistededwards.go:29-48):
 // FromTEtoRTE(x, y) = (x * (-f), y), FromRTEtoTE(x, y) = (x / (-f), y).  With GCP_COORDS_TE set in the format argument
 // every point a kernel reads is converted on load and every point it writes on store, one multiply each, so callers that
@@ -55,9 +64,18 @@ __device__ __forceinline__ void rte_to_te_x(u32 (&x)[8]) {
   fr_copy(x, t);
 }
 
-__global__ void fb_table_bases_kernel(const u32* __restrict__ base, int base_mont, int te, u32* __restrict__ ext, u32* __restrict__ flag) {
+// Table construction, four launches (round 1 built every entry by its own double-and-add and inverted every Z by its own
+// Fermat chain: ~70 k wide multiplies per entry, 0.1 s for w = 20; now ~3 k per entry):
+//   bases   B_w = [2^(w_bits w)] B per window, the header, flag[0] = 1 iff B is canonical and on the curve
+//   small   per window [j] B_w (j < 2^lo) and [j 2^lo] B_w (j <= 2^(w_bits-1-lo)) by double-and-add (a few thousand entries)
+//   sum     entry d = hi 2^lo + lo  is  [hi 2^lo] B_w + [lo] B_w: ONE unified addition per entry, (X, Y, Z) written into
+//           the entry's own 96 bytes
+//   niels   in place: Montgomery batch inversion over 32 strided entries per thread, (y-x, y+x, 2dxy) canonical
+// small: windows x 32 words (the B_w) followed by windows x fb_small_per_window x 32 words.
+__global__ void fb_table_bases_kernel(const u32* __restrict__ base, int base_mont, int te, u32* __restrict__ small,
+                                      u32* __restrict__ header, u32* __restrict__ flag, int wbits) {
   int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= FB_WINDOWS) return;
+  if (w >= fb_windows(wbits)) return;
   u32 xs[8], ys[8], x[8], y[8];
   load_fr(xs, base);
   load_fr(ys, base + 8);
@@ -71,78 +89,147 @@ __global__ void fb_table_bases_kernel(const u32* __restrict__ base, int base_mon
   }
   if (te) te_to_rte_x(x);
   ok = ok && ed_is_on_curve(x, y);
-  if (w == 0) flag[0] = ok ? 1u : 0u;
+  if (w == 0) {
+    flag[0] = ok ? 1u : 0u;
+    header[0] = (u32)wbits;
+    header[1] = (u32)fb_windows(wbits);
+    header[2] = 1u << (wbits - 1);
+  }
   ExtPoint p;
   if (ok)
     ext_from_affine(p, x, y);
   else
     ext_identity(p);  // keeps every later kernel well defined; results are masked by the flag
 #pragma unroll 1
-  for (int i = 0; i < w * FB_WBITS; i++) ext_double(p);
-  u32* o = ext + (size_t)w * FB_ENTRIES * 32;
+  for (int i = 0; i < w * wbits; i++) ext_double(p);
+  u32* o = small + (size_t)w * 32;
   store_fr(o, p.X);
   store_fr(o + 8, p.Y);
   store_fr(o + 16, p.Z);
   store_fr(o + 24, p.T);
 }
 
-// step 2: ext[w][d-1] = [d] ext[w][0] for d = 2..FB_ENTRIES (double-and-add on d, FB_WBITS bits: d <= 2^(w-1))
-__global__ void fb_table_fill_kernel(u32* __restrict__ ext) {
+__global__ void fb_table_small_kernel(u32* __restrict__ small, int wbits) {
+  const int windows = fb_windows(wbits), per = fb_small_per_window(wbits), lo_bits = fb_lo_bits(wbits);
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= FB_WINDOWS * FB_ENTRIES) return;
-  int w = idx / FB_ENTRIES, d = idx % FB_ENTRIES + 1;
-  if (d == 1) return;
+  if (idx >= windows * per) return;
+  const int w = idx / per, j = idx % per;
+  const u32 scalar = j < (1 << lo_bits) ? (u32)j : (u32)(j - (1 << lo_bits)) << lo_bits;
   ExtPoint b, acc;
-  const u32* s = ext + (size_t)w * FB_ENTRIES * 32;
+  const u32* s = small + (size_t)w * 32;
   load_fr(b.X, s);
   load_fr(b.Y, s + 8);
   load_fr(b.Z, s + 16);
   load_fr(b.T, s + 24);
   ext_identity(acc);
 #pragma unroll 1
-  for (int bit = FB_WBITS - 1; bit >= 0; bit--) {
+  for (int bit = wbits - 1; bit >= 0; bit--) {
     ext_double(acc);
-    if ((d >> bit) & 1) ext_add(acc, b);
+    if ((scalar >> bit) & 1u) ext_add(acc, b);
   }
-  u32* o = ext + (size_t)idx * 32;
+  u32* o = small + ((size_t)windows + idx) * 32;
   store_fr(o, acc.X);
   store_fr(o + 8, acc.Y);
   store_fr(o + 16, acc.Z);
   store_fr(o + 24, acc.T);
 }
 
-// step 3: extended -> Niels (y-x, y+x, 2dxy), canonical Montgomery.  (step 2 must have completed: separate launch)
-__global__ void fb_table_niels_kernel(const u32* __restrict__ ext, u32* __restrict__ tab) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= FB_WINDOWS * FB_ENTRIES) return;
-  const u32* s = ext + (size_t)idx * 32;
-  u32 X[8], Y[8], Z[8], zi[8], x[8], y[8], t[8];
+__global__ void __launch_bounds__(128) fb_table_sum_kernel(const u32* __restrict__ small, u32* __restrict__ tab, int wbits) {
+  const int windows = fb_windows(wbits), per = fb_small_per_window(wbits), lo_bits = fb_lo_bits(wbits);
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= ((size_t)windows << (wbits - 1))) return;
+  const int w = (int)(idx >> (wbits - 1));
+  const u32 d = (u32)(idx & (((size_t)1 << (wbits - 1)) - 1)) + 1u;
+  const u32 hi = d >> lo_bits, lo = d & ((1u << lo_bits) - 1u);
+  const u32* sw = small + ((size_t)windows + (size_t)w * per) * 32;
+  ExtPoint p, q;
+  const u32* sp = sw + ((size_t)(1u << lo_bits) + hi) * 32;
+  const u32* sq = sw + (size_t)lo * 32;
+  load_fr(p.X, sp);
+  load_fr(p.Y, sp + 8);
+  load_fr(p.Z, sp + 16);
+  load_fr(p.T, sp + 24);
+  load_fr(q.X, sq);
+  load_fr(q.Y, sq + 8);
+  load_fr(q.Z, sq + 16);
+  load_fr(q.T, sq + 24);
+  ext_add(p, q);
+  u32* o = tab + idx * 24;
+  store_fr(o, p.X);
+  store_fr(o + 8, p.Y);
+  store_fr(o + 16, p.Z);
+}
+
+// (X, Y, Z) -> Niels (y-x, y+x, 2dxy), canonical Montgomery, in place.  Every entry is read and written by one thread only.
+__global__ void __launch_bounds__(128) fb_table_niels_kernel(u32* __restrict__ tab, size_t total) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  if (tid >= total) return;
+  u32 pre[BATCH_INV][8];  // prefix products (local memory)
+  u32 acc[8];
+  fr_set_one(acc);
+  int cnt = 0;
+#pragma unroll 1
+  for (int j = 0; j < BATCH_INV; j++) {
+    const size_t p = tid + (size_t)j * stride;
+    if (p >= total) break;
+    u32 z[8];
+    load_fr_plain(z, tab + p * 24 + 16);
+    fr_mul(acc, acc, z);  // Z != 0: the addition law is complete on the curve, and an off-curve base was replaced by O
+#pragma unroll
+    for (int l = 0; l < 8; l++) pre[j][l] = acc[l];
+    cnt++;
+  }
+  u32 inv[8];
+  fr_inv(inv, acc);
   const u32 d2[8] = GCP_ED_2D_MONT;
-  load_fr(X, s);
-  load_fr(Y, s + 8);
-  load_fr(Z, s + 16);
-  fr_inv(zi, Z);
-  fr_mul(x, X, zi);
-  fr_mul(y, Y, zi);
-  NielsPoint n;
-  fr_sub(n.ymx, y, x);
-  fr_add(n.ypx, y, x);
-  fr_mul(t, x, y);
-  fr_mul(n.t2d, t, d2);
-  fr_canon(n.ymx);
-  fr_canon(n.ypx);
-  fr_canon(n.t2d);
-  u32* o = tab + (size_t)idx * 24;
-  store_fr(o, n.ymx);
-  store_fr(o + 8, n.ypx);
-  store_fr(o + 16, n.t2d);
+#pragma unroll 1
+  for (int j = cnt - 1; j >= 0; j--) {
+    const size_t p = tid + (size_t)j * stride;
+    u32* e = tab + p * 24;
+    u32 z[8], zi[8], X[8], Y[8], x[8], y[8], t[8];
+    if (j > 0) {
+      u32 prev[8];
+#pragma unroll
+      for (int l = 0; l < 8; l++) prev[l] = pre[j - 1][l];
+      load_fr_plain(z, e + 16);
+      fr_mul(zi, inv, prev);  // 1 / z_j
+      fr_mul(inv, inv, z);    // 1 / (z_0 ... z_{j-1})
+    } else {
+      fr_copy(zi, inv);
+    }
+    load_fr_plain(X, e);
+    load_fr_plain(Y, e + 8);
+    fr_mul(x, X, zi);
+    fr_mul(y, Y, zi);
+    NielsPoint n;
+    fr_sub(n.ymx, y, x);
+    fr_add(n.ypx, y, x);
+    fr_mul(t, x, y);
+    fr_mul(n.t2d, t, d2);
+    fr_canon(n.ymx);
+    fr_canon(n.ypx);
+    fr_canon(n.t2d);
+    store_fr(e, n.ymx);
+    store_fr(e + 8, n.ypx);
+    store_fr(e + 16, n.t2d);
+  }
+}
+
+// window at bit offset `bit`, wbits (<= 26) bits wide, of a 256-bit little-endian scalar.  The limb index is dynamic: the
+// scalar lives in 32 bytes of local memory (two L1-resident loads per window), which costs less than the registers or the
+// select chains that keeping it in registers would (measured both: +8 registers spill in the encrypt kernels)
+__device__ __forceinline__ u32 fb_scalar_window(const u32 (&k)[8], int bit, int wbits) {
+  const int limb = bit >> 5, sh = bit & 31;
+  const u32 lo = k[limb], hi = (limb + 1 < 8) ? k[limb + 1] : 0u;
+  return __funnelshift_r(lo, hi, sh) & ((1u << wbits) - 1u);
 }
 
 // acc += [k] B using B's table; k is an integer < 2^254 (a canonical Fr element used as an integer)
-__device__ __forceinline__ void fb_digit(const u32 (&k)[8], int w, u32& carry, u32& d, bool& neg) {
-  u32 raw = scalar_window<FB_WBITS>(k, w) + carry;
-  neg = raw > (u32)FB_HALF;
-  d = neg ? ((1u << FB_WBITS) - raw) : raw;
+__device__ __forceinline__ void fb_digit(const u32 (&k)[8], int w, int wbits, u32& carry, u32& d, bool& neg) {
+  u32 raw = fb_scalar_window(k, w * wbits, wbits) + carry;
+  neg = raw > (1u << (wbits - 1));
+  d = neg ? ((1u << wbits) - raw) : raw;
   carry = neg ? 1u : 0u;
 }
 
@@ -171,16 +258,22 @@ __device__ __forceinline__ void fb_stage_read(u32 (&a)[8], u32 (&b)[8], u32 (&c)
 
 __device__ __forceinline__ void fixed_base_accumulate(ExtPoint& acc, const u32 (&k)[8], const u32* __restrict__ tab) {
   __shared__ uint4 stage[2 * 6 * FB_STAGE_THREADS];  // 24 KB
+  // the table's header gives the width; the only loop state beyond round 1's (w, tab) is that one register: the window
+  // count is "while the next window starts below bit 256" and the table pointer advances by one window per iteration
+  const int wbits = (int)__ldg(tab - FB_HEADER_WORDS);
   u32 carry = 0, d, dn = 0;
   bool neg, negn = false;
-  fb_digit(k, 0, carry, d, neg);
+  fb_digit(k, 0, wbits, carry, d, neg);
   if (d != 0) fb_stage_issue(stage, 0, tab + (size_t)(d - 1) * 24);
   asm volatile("cp.async.commit_group;" ::: "memory");
+  int w = 0;
 #pragma unroll 1
-  for (int w = 0; w < FB_WINDOWS; w++) {
-    if (w + 1 < FB_WINDOWS) {  // next window's entry is on its way while this window's addition runs
-      fb_digit(k, w + 1, carry, dn, negn);
-      if (dn != 0) fb_stage_issue(stage, (w + 1) & 1, tab + ((size_t)(w + 1) * FB_ENTRIES + (dn - 1)) * 24);
+  do {
+    const bool more = (w + 1) * wbits < 256;
+    if (more) {  // next window's entry is on its way while this window's addition runs
+      tab += (size_t)24 << (wbits - 1);
+      fb_digit(k, w + 1, wbits, carry, dn, negn);
+      if (dn != 0) fb_stage_issue(stage, (w + 1) & 1, tab + (size_t)(dn - 1) * 24);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but the group just committed has landed
@@ -197,7 +290,8 @@ __device__ __forceinline__ void fixed_base_accumulate(ExtPoint& acc, const u32 (
     }
     d = dn;
     neg = negn;
-  }
+    w++;
+  } while (w * wbits < 256);
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
@@ -574,21 +668,27 @@ __global__ void __launch_bounds__(TALLY_THREADS, 4) encrypt_tally_partial_kernel
 #pragma unroll 1
     for (; b < n_ballots; b += bstride) {
       if (mask && mask[b] == 0) continue;  // ballot not admitted (e.g. census proof flag 0)
-      bool canon = true;
-      u32 k[8], m[8];
-      load_scalar(k, canon, ks + (b * n_fields + field) * 8, mont);
-      load_scalar(m, canon, ms + (b * n_fields + field) * 8, mont);
-      if (!canon) {
-        bad = 1;
-        continue;
+      const u32* kp = ks + (b * n_fields + field) * 8;
+      const u32* mp = ms + (b * n_fields + field) * 8;
+      {  // both scalars are checked before anything is added; each is loaded again by the pass that multiplies by it (an
+         // L1 hit), so that neither is live across the other's window loop (the kernel sits at its 128-register cap)
+        u32 t[8];
+        load_fr(t, kp);
+        bool canon = fr_is_canonical(t);
+        load_fr(t, mp);
+        canon = canon && fr_is_canonical(t);
+        if (!canon) {
+          bad = 1;
+          continue;
+        }
       }
       const int n_pass = half ? 2 : 1;       // one inlined copy of the window loop (see encrypt_shared_kernel)
 #pragma unroll 1
       for (int pass = 0; pass < n_pass; pass++) {
         const u32* tab = (half && pass == 0) ? tabPK : tabG;
         u32 sc[8];
-#pragma unroll
-        for (int l = 0; l < 8; l++) sc[l] = (pass == 0) ? k[l] : m[l];
+        bool canon = true;
+        load_scalar(sc, canon, pass == 0 ? kp : mp, mont);
         fixed_base_accumulate(acc, sc, tab);
       }
     }

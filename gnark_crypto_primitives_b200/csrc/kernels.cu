@@ -378,17 +378,30 @@ cudaError_t launch_smt_apply_bad(const u8* bad, size_t n, u8* flags, u8* status,
 // ---------------------------------------------------------------------------------------------------
 // ElGamal
 // ---------------------------------------------------------------------------------------------------
-size_t fb_table_bytes() { return FB_TABLE_WORDS * sizeof(u32); }
-size_t fb_ext_scratch_bytes() { return (size_t)FB_WINDOWS * FB_ENTRIES * 32 * sizeof(u32); }
+size_t fb_table_bytes(int wbits) {  // header + entries
+  return ((size_t)FB_HEADER_WORDS + ((size_t)fb_windows(wbits) << (wbits - 1)) * 24) * sizeof(u32);
+}
+size_t fb_small_scratch_bytes() {  // table-construction scratch, sized for the widest window
+  size_t m = 0;
+  for (int w = FB_MIN_WBITS; w <= FB_MAX_WBITS; w++) {
+    size_t b = (size_t)fb_windows(w) * (1 + (size_t)fb_small_per_window(w)) * 32 * sizeof(u32);
+    m = b > m ? b : m;
+  }
+  return m;
+}
 
 static inline unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
-cudaError_t launch_fb_table_build(const u32* d_base_xy, int base_mont, u32* d_ext, u32* d_tab, u32* d_flag,
-                                  cudaStream_t stream, int te) {
-  fb_table_bases_kernel<<<1, 32, 0, stream>>>(d_base_xy, base_mont, te, d_ext, d_flag);
-  const int total = FB_WINDOWS * FB_ENTRIES;
-  fb_table_fill_kernel<<<blocks_for(total, 64), 64, 0, stream>>>(d_ext);
-  fb_table_niels_kernel<<<blocks_for(total, 64), 64, 0, stream>>>(d_ext, d_tab);
+// d_table: fb_table_bytes(wbits) bytes; kernels take d_table + FB_HEADER_WORDS (fb_table_entries)
+cudaError_t launch_fb_table_build(const u32* d_base_xy, int base_mont, u32* d_small, u32* d_table, u32* d_flag,
+                                  cudaStream_t stream, int te, int wbits) {
+  if (wbits < FB_MIN_WBITS || wbits > FB_MAX_WBITS) return cudaErrorInvalidValue;
+  u32* entries = d_table + FB_HEADER_WORDS;
+  const size_t total = (size_t)fb_windows(wbits) << (wbits - 1);
+  fb_table_bases_kernel<<<1, 32, 0, stream>>>(d_base_xy, base_mont, te, d_small, d_table, d_flag, wbits);
+  fb_table_small_kernel<<<blocks_for((size_t)fb_windows(wbits) * fb_small_per_window(wbits), 64), 64, 0, stream>>>(d_small, wbits);
+  fb_table_sum_kernel<<<blocks_for(total, 128), 128, 0, stream>>>(d_small, entries, wbits);
+  fb_table_niels_kernel<<<blocks_for((total + BATCH_INV - 1) / BATCH_INV, 128), 128, 0, stream>>>(entries, total);
   return cudaGetLastError();
 }
 

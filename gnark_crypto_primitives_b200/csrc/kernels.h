@@ -112,13 +112,18 @@ cudaError_t launch_smt_unpack(const u8* packed, const u64* offsets, u64 base, u6
 cudaError_t launch_smt_apply_bad(const u8* bad, size_t n, u8* flags, u8* status, u32* out_roots, cudaStream_t stream);
 
 // ElGamal (elgamal.cuh)
-size_t fb_table_bytes();
-size_t fb_ext_scratch_bytes();
+// A fixed-base table is a 128-byte header {window bits, windows, entries per window} followed by the Niels entries; kernels
+// take the pointer to the entries (fb_table_entries) and read the width from the header, so tables of different widths
+// can be in use side by side.
+constexpr int FB_TABLE_HEADER_WORDS = 32;
+inline uint32_t* fb_table_entries(uint32_t* d_table) { return d_table ? d_table + FB_TABLE_HEADER_WORDS : nullptr; }
+size_t fb_table_bytes(int wbits);
+size_t fb_small_scratch_bytes();
 cudaError_t upload_generator(u32* d_xy, cudaStream_t stream);
 // te (last argument of the point-carrying launches below): the points on the wire are in iden3 twisted-Edwards coordinates
 // (GCP_COORDS_TE): converted with one multiply on load / store (ecc/format/twistededwards.go:29-48)
-cudaError_t launch_fb_table_build(const u32* d_base_xy, int base_mont, u32* d_ext, u32* d_tab, u32* d_flag,
-                                  cudaStream_t stream, int te = 0);
+cudaError_t launch_fb_table_build(const u32* d_base_xy, int base_mont, u32* d_small, u32* d_table, u32* d_flag,
+                                  cudaStream_t stream, int te, int wbits);
 cudaError_t launch_fixed_base_mul(const u32* tabG, const u32* scalars, size_t n, u32* out_xyz, u8* status, int mont,
                                   cudaStream_t stream);
 cudaError_t launch_encrypt_shared(const u32* tabG, const u32* tabPK, const u32* pk_flag, const u32* ks, const u32* ms,

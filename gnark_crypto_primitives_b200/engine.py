@@ -206,6 +206,16 @@ class Engine:
         self._check(self._lib.gcp_poseidon_multihash_dev(self._h, _dptr(d_in), length, n, _dptr(d_out),
                                                          _dptr(d_status), fmt, self._stream(stream)))
 
+    # -- fixed-base tables ----------------------------------------------------------------------------
+    def set_fixed_base_window(self, window_bits: int):
+        """Window width of the precomputed tables of G and the shared public key (elgamal/mul.go:26-72 has 4-bit windows):
+        8..26 bits, or 0 for the automatic choice (20 bits, 24 once a base has served 2^27 multiplications)."""
+        self._check(self._lib.gcp_ctx_set_fixed_base_window(self._h, int(window_bits)))
+
+    def fixed_base_window(self, which: int = 0) -> int:
+        """Current window width of G's (0) or the cached public key's (1) table."""
+        return int(self._lib.gcp_ctx_fixed_base_window(self._h, int(which)))
+
     # -- SMT ----------------------------------------------------------------------------------------
     def set_smt_hasher(self, hasher: int):
         """The utils.Hasher plug of the tree/smt gadgets (utils/hashers.go:10-37) for every SMT call of this engine:

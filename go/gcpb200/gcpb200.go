@@ -213,6 +213,13 @@ func (e *Engine) BatchProcess(levels int, oldRoots, siblings, oldKeys, oldValues
 	return
 }
 
+// SetFixedBaseWindow fixes the window width (8..26 bits; 0 = automatic: 20 bits, 24 once a base has served 2^27
+// multiplications) of the precomputed tables behind FixedBaseScalarMulBN254 and Encrypt (elgamal/mul.go:26-72 uses 4-bit
+// windows).  Results do not depend on it; 24 bits cost 8.9 GB of device memory per base.
+func (e *Engine) SetFixedBaseWindow(bits int) error {
+	return e.err(C.gcp_ctx_set_fixed_base_window(e.ctx, C.int(bits)))
+}
+
 // SetSMTHasher selects the utils.Hasher plug (utils/hashers.go:10-37) for every SMT call of this engine: the gadgets of
 // tree/smt take hFn per call, an Engine carries it.  poseidon2 = false: utils.PoseidonHasher (default); true:
 // utils.Poseidon2Hasher (call InstallPoseidon2Keys first, so that the round keys are gnark-crypto's own).

@@ -262,6 +262,14 @@ int gcp_smt_process_with_leaf_hash_dev(gcp_ctx* ctx, int n_levels, size_t n, con
                                        const uint8_t* d_fnc1, void* d_new_roots, uint8_t* d_status, int fmt, void* stream);
 
 /* ---- ElGamal over the a = -1 BN254 twisted Edwards curve: elgamal/ ------------------------------------ */
+/* Multiplications by G and by the shared public key run out of precomputed window tables in device memory (the reference's
+ * table, elgamal/mul.go:26-72, has 4-bit windows).  A table starts with 20-bit windows (654 MB, 13 additions per
+ * multiplication) and is rebuilt with 24-bit windows (8.9 GB, 11 additions, ~45 ms) once its base has served 2^27
+ * multiplications; results do not depend on the width.  gcp_ctx_set_fixed_base_window fixes the width of both tables
+ * (8..26 bits; 0 restores the automatic choice): G's table is rebuilt at once, the key's at its next use.
+ * gcp_ctx_fixed_base_window returns the current width of G's (which = 0) or the cached key's (which = 1) table. */
+int gcp_ctx_set_fixed_base_window(gcp_ctx* ctx, int window_bits);
+int gcp_ctx_fixed_base_window(const gcp_ctx* ctx, int which);
 /* FixedBaseScalarMulBN254 (elgamal/mul.go:76-166): out[i] = [scalars[i]] G, scalars are Fr elements used as
  * integers in [0, r).  out_points: n x (X, Y). */
 int gcp_elgamal_fixed_base_mul(gcp_ctx* ctx, const void* scalars, size_t n, void* out_points, uint8_t* status, int fmt);

@@ -185,6 +185,8 @@ inline Batch Processor(const Engine& e, int n_levels, size_t n, const uint8_t* o
                           fnc1, b.values.data(), b.status.data(), fmt));
   return b;
 }
+// window width of the precomputed tables behind FixedBaseScalarMulBN254 / Encrypt (elgamal/mul.go:26-72): 8..26, 0 = automatic
+inline void SetFixedBaseWindow(const Engine& e, int window_bits) { e.check(gcp_ctx_set_fixed_base_window(e.raw(), window_bits)); }
 // the hFn utils.Hasher argument of the tree/smt gadgets (utils/hashers.go:10-37): carried by the engine
 inline void SetHasher(const Engine& e, int hasher /* GCP_HASHER_POSEIDON | GCP_HASHER_POSEIDON2 */) {
   e.check(gcp_ctx_set_smt_hasher(e.raw(), hasher));
