@@ -596,6 +596,7 @@ def measure_group(torch, dist, eng0, g, world, rank, barrier_cpu):
 
         grp = g.Group(list(range(world)))
         try:
+            grp.set_fixed_base_window(FB_WINDOW_BITS)
             lib, gh = grp._lib, grp._h
             out = {"devices": world, "uses_nccl": bool(grp.uses_nccl), "copy_threads": int(lib.gcp_copy_threads())}
             import ctypes

@@ -772,6 +772,15 @@ class Group:
         return [int(self._lib.gcp_ctx_launch_count(c_void_p(self._lib.gcp_group_ctx(self._h, i))))
                 for i in range(self.size)]
 
+    def set_fixed_base_window(self, window_bits: int):
+        """gcp_ctx_set_fixed_base_window on every device's context (gcp_group_ctx)."""
+        for i in range(self.size):
+            ctx = c_void_p(self._lib.gcp_group_ctx(self._h, i))
+            rc = self._lib.gcp_ctx_set_fixed_base_window(ctx, int(window_bits))
+            if rc != 0:
+                msg = self._lib.gcp_last_error(ctx)
+                raise EngineError(rc, msg.decode() if msg else "")
+
     def poseidon_hash(self, inputs, fmt=FMT_CANONICAL):
         a = _as_elems(inputs, name="inputs")
         if a.ndim != 3:

@@ -267,7 +267,8 @@ int gcp_smt_process_with_leaf_hash_dev(gcp_ctx* ctx, int n_levels, size_t n, con
  * multiplication) and is rebuilt with 24-bit windows (8.9 GB, 11 additions, ~45 ms) once its base has served 2^27
  * multiplications; results do not depend on the width.  gcp_ctx_set_fixed_base_window fixes the width of both tables
  * (8..26 bits; 0 restores the automatic choice): G's table is rebuilt at once, the key's at its next use.
- * gcp_ctx_fixed_base_window returns the current width of G's (which = 0) or the cached key's (which = 1) table. */
+ * gcp_ctx_fixed_base_window returns the current width of G's (which = 0) or the cached key's (which = 1) table.  For a
+ * group, call it on every device's context (gcp_group_ctx). */
 int gcp_ctx_set_fixed_base_window(gcp_ctx* ctx, int window_bits);
 int gcp_ctx_fixed_base_window(const gcp_ctx* ctx, int which);
 /* FixedBaseScalarMulBN254 (elgamal/mul.go:76-166): out[i] = [scalars[i]] G, scalars are Fr elements used as
