@@ -19,6 +19,7 @@ FMT_CANONICAL = 0
 FMT_MONTGOMERY = 1
 HASHER_POSEIDON = 0  # utils.PoseidonHasher (default)
 HASHER_POSEIDON2 = 1  # utils.Poseidon2Hasher: the width-2 Merkle-Damgard hasher (gcp_ctx_set_smt_hasher)
+MSG_U64 = 4         # or-ed into fmt of the fused tallies: messages are little-endian uint64 (8 bytes), not field elements
 COORDS_TE = 2       # or-ed into fmt: curve points on the wire are in iden3 twisted-Edwards coordinates (gcp_b200.h)
 
 STATUS_OK = 0

@@ -1361,11 +1361,13 @@ static int check_fmt_points(gcp_ctx* ctx, int fmt) {
   return GCP_OK;
 }
 static inline int elem_fmt(int fmt) { return fmt & GCP_FMT_MONTGOMERY; }
+static inline size_t msg_bytes(int fmt) { return (fmt & GCP_MSG_U64) ? 8 : 32; }  // per message of the fused tallies
 static inline int coords_te(int fmt) { return (fmt & GCP_COORDS_TE) ? 1 : 0; }
 
 // Make d_tabPK the table of the given shared public key (64 bytes, host or device memory); `uses` multiplications by it
 // (and as many by G) are about to be queued.
 static int ensure_pk_table(gcp_ctx* ctx, const void* pk, bool pk_on_device, int fmt, cudaStream_t st, uint64_t uses) {
+  fmt &= GCP_FMT_MONTGOMERY | GCP_COORDS_TE;  // what the key's table depends on
   unsigned char host_pk[64];
   if (pk_on_device) {
     CU(cudaMemcpyAsync(host_pk, pk, 64, cudaMemcpyDeviceToHost, st), "D2H public key");
@@ -1534,7 +1536,7 @@ static int encrypt_tally_dev_locked(gcp_ctx* ctx, const void* d_k, const void* d
   u32* xyz = (u32*)ctx->buf(slot_base + 2, (size_t)cols * 96);
   if (!partials || !bad || !xyz) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
   CU(launch_encrypt_tally(ctx->d_tabG, ctx->d_tabPK, (const u32*)d_k, (const u32*)d_m, d_mask, n_ballots, n_fields, n_blocks,
-                          partials, bad, xyz, d_status, elem_fmt(fmt), st),
+                          partials, bad, xyz, d_status, elem_fmt(fmt), st, (int)(msg_bytes(fmt) / 4)),
      "encrypt-tally kernels");
   CU(launch_normalize(xyz, (size_t)cols, (u32*)d_out, d_status, 2, elem_fmt(fmt), st, 24, coords_te(fmt)), "normalize kernel");
   ctx->launches += 3;
@@ -1543,7 +1545,7 @@ static int encrypt_tally_dev_locked(gcp_ctx* ctx, const void* d_k, const void* d
 
 static int encrypt_tally_check(gcp_ctx* ctx, const void* pk, const void* k, const void* m, size_t n_ballots,
                                int n_fields, const void* out, const void* status, int fmt) {
-  int rc = check_fmt_points(ctx, fmt);
+  int rc = check_fmt_points(ctx, fmt & ~GCP_MSG_U64);  // the fused tallies also take GCP_MSG_U64
   if (rc != GCP_OK) return rc;
   if (n_fields < 1 || n_fields > 64) return ctx->fail(GCP_ERR_BAD_ARG, "n_fields must be in [1, 64]");
   if (!pk || !out || !status || (n_ballots && (!k || !m))) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
@@ -1577,6 +1579,7 @@ int gcp_elgamal_encrypt_tally_dev(gcp_ctx* ctx, const void* d_pub_key, const voi
 // nullptr for a plain tally.
 static int finish_partials(gcp_ctx* ctx, u32* d_parts, uint8_t* d_part_status, size_t n_chunks, int n_fields, int fmt,
                            const u32* pk_flag, void* out, uint8_t* status, bool out_on_device) {
+  fmt &= ~GCP_MSG_U64;  // the partials are ciphertexts
   const size_t ballot_ct = (size_t)n_fields * 128;
   cudaStream_t st = ctx->stream[0];
   u32* d_res = out_on_device ? (u32*)out : (u32*)ctx->buf(66, ballot_ct);
@@ -1612,7 +1615,7 @@ static int encrypt_tally_host(gcp_ctx* ctx, const void* pub_key, const void* k, 
   if (rc != GCP_OK) return rc;
   rc = ensure_pk_table(ctx, pub_key, false, fmt, ctx->stream[0], (uint64_t)n_ballots * n_fields);
   if (rc != GCP_OK) return rc;
-  const size_t ballot_in = (size_t)n_fields * 32, ballot_ct = (size_t)n_fields * 128;
+  const size_t ballot_in = (size_t)n_fields * 32, ballot_m = (size_t)n_fields * msg_bytes(fmt), ballot_ct = (size_t)n_fields * 128;
   // Chunk = 1/16 of the call, between 64 MB and 256 MB of k (and as much of m).  Every chunk costs ~0.4 ms of small kernels
   // (second-stage fold, normalisation) and the first chunk's copy is the one nothing hides, so large calls want large
   // chunks and small calls small ones; measured at 2^23 ballots x 8 from page-locked memory
@@ -1635,11 +1638,11 @@ static int encrypt_tally_host(gcp_ctx* ctx, const void* pub_key, const void* k, 
     int s = (int)(c & 1);
     cudaStream_t st = ctx->stream[s];
     void* dk = ctx->buf(48 + s * 8, std::max<size_t>(std::min(chunk, n_ballots), 1) * ballot_in);
-    void* dm = ctx->buf(48 + s * 8 + 4, std::max<size_t>(std::min(chunk, n_ballots), 1) * ballot_in);
+    void* dm = ctx->buf(48 + s * 8 + 4, std::max<size_t>(std::min(chunk, n_ballots), 1) * ballot_m);
     if (!dk || !dm) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
     if (cnt) {
       GCP_TRY(h2d_copy(ctx, dk, (const char*)k + off * ballot_in, cnt * ballot_in, st));
-      GCP_TRY(h2d_copy(ctx, dm, (const char*)m + off * ballot_in, cnt * ballot_in, st));
+      GCP_TRY(h2d_copy(ctx, dm, (const char*)m + off * ballot_m, cnt * ballot_m, st));
     }
     rc = encrypt_tally_dev_locked(ctx, dk, dm, nullptr, cnt, n_fields, (char*)d_parts + c * ballot_ct, d_part_status + c * n_fields,
                                   fmt, st, 48 + s * 8 + 1);
@@ -1877,7 +1880,8 @@ static int ballot_batch_host(gcp_ctx* ctx, int n_levels, size_t n_voters, const 
   rc = ensure_pk_table(ctx, pub_key, false, fmt, ctx->stream[0], (uint64_t)n * n_fields);
   if (rc != GCP_OK) return rc;
   const size_t sib_bytes = (size_t)n_levels * 32, ballot_in = (size_t)n_fields * 32, ballot_ct = (size_t)n_fields * 128;
-  ChunkPlan plan(n, smt_path_wave_items(ctx->sm_count), ((size_t)1 << 30) / (sib_bytes + 2 * ballot_in), true);
+  const size_t ballot_m = (size_t)n_fields * msg_bytes(fmt);
+  ChunkPlan plan(n, smt_path_wave_items(ctx->sm_count), ((size_t)1 << 30) / (sib_bytes + ballot_in + ballot_m), true);
   std::vector<size_t> sizes;
   {
     ChunkPlan walk = plan;
@@ -1902,7 +1906,7 @@ static int ballot_batch_host(gcp_ctx* ctx, int n_levels, size_t n_voters, const 
     const int b = 10 + s * 14;
     // every slot is sized for the largest chunk of the plan: growing one later would cudaFree under running work
     void* dk = ctx->buf(48 + s * 8, cap * ballot_in);
-    void* dm = ctx->buf(48 + s * 8 + 4, cap * ballot_in);
+    void* dm = ctx->buf(48 + s * 8 + 4, cap * ballot_m);
     uint8_t* d_flags = (uint8_t*)ctx->buf(b + 9, cap);
     if (!dk || !dm || !d_flags) return ctx->fail(GCP_ERR_ALLOC, "device allocation failed");
     if (cnt) {
@@ -1933,7 +1937,7 @@ static int ballot_batch_host(gcp_ctx* ctx, int n_levels, size_t n_voters, const 
       GCP_TRY(h2d_copy(ctx, d_keys, (const char*)keys + off * 32, cnt * 32, st));
       GCP_TRY(h2d_copy(ctx, d_vals, (const char*)values + off * 32, cnt * 32, st));
       GCP_TRY(h2d_copy(ctx, dk, (const char*)k + off * ballot_in, cnt * ballot_in, st));
-      GCP_TRY(h2d_copy(ctx, dm, (const char*)m + off * ballot_in, cnt * ballot_in, st));
+      GCP_TRY(h2d_copy(ctx, dm, (const char*)m + off * ballot_m, cnt * ballot_m, st));
       rc = smt_verify_dev_locked(ctx, n_levels, cnt, d_roots, shared_root, d_sib, nullptr, nullptr, nullptr, d_keys, d_vals,
                                  nullptr, nullptr, d_flags, d_status, nullptr, elem_fmt(fmt), st, b + 12);
       if (rc != GCP_OK) return rc;

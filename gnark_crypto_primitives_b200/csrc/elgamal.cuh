@@ -645,11 +645,14 @@ __global__ void __launch_bounds__(TALLY_THREADS, 4) tally_partial_kernel(const u
 // [k]G into the C1 column or [k]PK + [m]G into the C2 column of its field; same reduction as tally_partial_kernel.
 // ks / ms: n_ballots x n_fields scalars.  bad_count[f] counts non-canonical scalars of field f.
 // mask (optional): n_ballots bytes, a ballot is summed only where mask[b] != 0.
+template <int M_WORDS>
 __global__ void __launch_bounds__(TALLY_THREADS, 4) encrypt_tally_partial_kernel(const u32* __restrict__ tabG, const u32* __restrict__ tabPK,
                                                                               const u32* __restrict__ ks, const u32* __restrict__ ms,
                                                                               const u8* __restrict__ mask, size_t n_ballots, int n_fields,
                                                                               u32* __restrict__ partials, u32* __restrict__ bad_count, int mont) {
   extern __shared__ u32 smem[];
+  // M_WORDS: 8 = the messages are field elements like k; 2 = little-endian uint64 integers (GCP_MSG_U64).  A template
+  // parameter: as a run-time argument it cost the field-element form 7 % (the kernel sits at its 128-register cap)
   // thread layout: the first half of the block (whole warps) computes C1 columns, the second half C2 columns, so a
   // warp never mixes the two branches; inside a half, thread = row * n_fields + field
   constexpr int HALF_THREADS = TALLY_THREADS / 2;
@@ -669,14 +672,16 @@ __global__ void __launch_bounds__(TALLY_THREADS, 4) encrypt_tally_partial_kernel
     for (; b < n_ballots; b += bstride) {
       if (mask && mask[b] == 0) continue;  // ballot not admitted (e.g. census proof flag 0)
       const u32* kp = ks + (b * n_fields + field) * 8;
-      const u32* mp = ms + (b * n_fields + field) * 8;
+      const u32* mp = ms + (b * n_fields + field) * (size_t)M_WORDS;
       {  // both scalars are checked before anything is added; each is loaded again by the pass that multiplies by it (an
          // L1 hit), so that neither is live across the other's window loop (the kernel sits at its 128-register cap)
         u32 t[8];
         load_fr(t, kp);
         bool canon = fr_is_canonical(t);
-        load_fr(t, mp);
-        canon = canon && fr_is_canonical(t);
+        if constexpr (M_WORDS == 8) {
+          load_fr(t, mp);
+          canon = canon && fr_is_canonical(t);
+        }
         if (!canon) {
           bad = 1;
           continue;
@@ -688,7 +693,18 @@ __global__ void __launch_bounds__(TALLY_THREADS, 4) encrypt_tally_partial_kernel
         const u32* tab = (half && pass == 0) ? tabPK : tabG;
         u32 sc[8];
         bool canon = true;
-        load_scalar(sc, canon, pass == 0 ? kp : mp, mont);
+        if constexpr (M_WORDS == 8) {
+          load_scalar(sc, canon, pass == 0 ? kp : mp, mont);
+        } else {
+          if (pass == 0) {
+            load_scalar(sc, canon, kp, mont);
+          } else {
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(mp));
+            fr_set_zero(sc);
+            sc[0] = v.x;
+            sc[1] = v.y;
+          }
+        }
         fixed_base_accumulate(acc, sc, tab);
       }
     }

@@ -415,7 +415,7 @@ static int group_tally(gcp_group* g, size_t n_ballots, int n_fields, void* out, 
   });
   if (rc != GCP_OK) return rc;
   // phase 2: all-gather of the partials (bytes) and the final fold on every device
-  return for_each_device(g, [&](int i) { return gather_and_fold(g, i, n_fields, out, status, fmt); });
+  return for_each_device(g, [&](int i) { return gather_and_fold(g, i, n_fields, out, status, fmt & ~GCP_MSG_U64); });  // partials are ciphertexts
 }
 
 int gcp_group_elgamal_tally(gcp_group* g, const void* ct, size_t n_ballots, int n_fields, void* out, uint8_t* status,
@@ -428,8 +428,8 @@ int gcp_group_elgamal_tally(gcp_group* g, const void* ct, size_t n_ballots, int 
 int gcp_group_elgamal_encrypt_tally(gcp_group* g, const void* pub_key, const void* k, const void* m, size_t n_ballots,
                                     int n_fields, void* out, uint8_t* status, int fmt) {
   return group_tally(g, n_ballots, n_fields, out, status, fmt, [&](int i, Shard s, unsigned char* p, uint8_t* ps) {
-    const size_t row = (size_t)n_fields * 32;
-    return gcp_internal_encrypt_tally_to_dev(g->ctx[i], pub_key, off(k, s.lo * row), off(m, s.lo * row), s.hi - s.lo, n_fields,
+    const size_t row = (size_t)n_fields * 32, mrow = (size_t)n_fields * ((fmt & GCP_MSG_U64) ? 8 : 32);
+    return gcp_internal_encrypt_tally_to_dev(g->ctx[i], pub_key, off(k, s.lo * row), off(m, s.lo * mrow), s.hi - s.lo, n_fields,
                                              p, ps, fmt);
   });
 }
@@ -440,11 +440,11 @@ int gcp_group_ballot_batch(gcp_group* g, int n_levels, size_t n_voters, const vo
                            uint8_t* out_flags, uint8_t* out_status, void* out_tally, uint8_t* out_tally_status, int fmt) {
   const size_t sib_row = (size_t)(n_levels > 0 ? n_levels : 0) * 32;
   return group_tally(g, n_voters, n_fields, out_tally, out_tally_status, fmt, [&](int i, Shard s, unsigned char* p, uint8_t* ps) {
-    const size_t row = (size_t)n_fields * 32;
+    const size_t row = (size_t)n_fields * 32, mrow = (size_t)n_fields * ((fmt & GCP_MSG_U64) ? 8 : 32);
     return gcp_internal_ballot_batch_to_dev(g->ctx[i], n_levels, s.hi - s.lo, shared_root ? roots : off(roots, s.lo * 32),
                                             shared_root, off(siblings, s.lo * sib_row), packed,
                                             offsets ? offsets + s.lo : nullptr, off(keys, s.lo * 32), off(values, s.lo * 32),
-                                            pub_key, off(k, s.lo * row), off(m, s.lo * row), n_fields, offb(out_flags, s.lo),
+                                            pub_key, off(k, s.lo * row), off(m, s.lo * mrow), n_fields, offb(out_flags, s.lo),
                                             offb(out_status, s.lo), p, ps, fmt);
   });
 }

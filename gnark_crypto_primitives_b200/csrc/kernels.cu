@@ -479,11 +479,15 @@ cudaError_t launch_tally(const u32* ct, size_t n_ballots, int n_fields, int n_bl
 
 cudaError_t launch_encrypt_tally(const u32* tabG, const u32* tabPK, const u32* ks, const u32* ms, const u8* mask,
                                  size_t n_ballots, int n_fields, int n_blocks, u32* partials, u32* bad_count, u32* out_xyz, u8* status, int mont,
-                                 cudaStream_t stream) {
+                                 cudaStream_t stream, int m_words) {
   cudaError_t e = cudaMemsetAsync(bad_count, 0, sizeof(u32) * n_fields, stream);
   if (e != cudaSuccess) return e;
-  encrypt_tally_partial_kernel<<<n_blocks, TALLY_THREADS, TALLY_THREADS * 32 * sizeof(u32), stream>>>(
-      tabG, tabPK, ks, ms, mask, n_ballots, n_fields, partials, bad_count, mont);
+  if (m_words == 2)
+    encrypt_tally_partial_kernel<2><<<n_blocks, TALLY_THREADS, TALLY_THREADS * 32 * sizeof(u32), stream>>>(
+        tabG, tabPK, ks, ms, mask, n_ballots, n_fields, partials, bad_count, mont);
+  else
+    encrypt_tally_partial_kernel<8><<<n_blocks, TALLY_THREADS, TALLY_THREADS * 32 * sizeof(u32), stream>>>(
+        tabG, tabPK, ks, ms, mask, n_ballots, n_fields, partials, bad_count, mont);
   const int cols = n_fields * 2;
   tally_final_kernel<<<cols, TALLY_THREADS, 0, stream>>>(partials, n_blocks, cols, out_xyz, bad_count, status);
   return cudaGetLastError();

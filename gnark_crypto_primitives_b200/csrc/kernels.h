@@ -147,7 +147,7 @@ cudaError_t launch_ct_is_equal(const u32* a, const u32* b, size_t n, u8* flags, 
 cudaError_t launch_ct_select(const u8* sel, const u32* i1, const u32* i2, size_t n, u32* out, u8* status, cudaStream_t stream);
 cudaError_t launch_encrypt_tally(const u32* tabG, const u32* tabPK, const u32* ks, const u32* ms, const u8* mask,
                                  size_t n_ballots, int n_fields, int n_blocks, u32* partials, u32* bad_count, u32* out_xyz, u8* status, int mont,
-                                 cudaStream_t stream);
+                                 cudaStream_t stream, int m_words = 8);
 cudaError_t launch_tally_status_merge(const u8* part_status, int n_chunks, int n_fields, int have_final, const u32* pk_flag,
                                       u32* ct, u8* status, cudaStream_t stream);
 cudaError_t launch_keccak_address(const u8* in, size_t n, u8* out, cudaStream_t stream);

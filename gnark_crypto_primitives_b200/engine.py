@@ -42,6 +42,18 @@ def _as_elems(arr, n_expected=None, name="array"):
     return a
 
 
+def _as_msgs(m, n_expected, fmt):
+    """The messages of the fused tallies: field elements, or with MSG_U64 in fmt one uint64 each."""
+    if not (fmt & _lib.MSG_U64):
+        return _as_elems(m, n_expected, "m")
+    a = np.ascontiguousarray(m)
+    if a.dtype != np.uint64:
+        raise TypeError(f"m: MSG_U64 expects uint64 values, got {a.dtype}")
+    if a.size != n_expected:
+        raise ValueError(f"m: expected {n_expected} values, got {a.size}")
+    return a
+
+
 def _ptr(a):
     if a is None:
         return None
@@ -72,7 +84,7 @@ def _ballot_batch_call(fn, handle, n_levels, roots, siblings, packed, keys, valu
     if kk.ndim != 3:
         raise ValueError("k must have shape (n_voters, n_fields, 32)")
     n, nf = kk.shape[0], kk.shape[1]
-    mm = _as_elems(m, n * nf, "m")
+    mm = _as_msgs(m, n * nf, fmt)
     pk = _as_elems(pub_key, 2, "pub_key")
     r = _as_elems(roots, name="roots")
     shared = 1 if r.size == 32 and n != 1 else 0
@@ -501,12 +513,13 @@ class Engine:
                                                     _dptr(d_status), fmt, self._stream(stream)))
 
     def elgamal_encrypt_tally(self, pub_key, k, m, fmt=FMT_CANONICAL):
-        """Fused Encrypt + tally.  k, m: (n_ballots, n_fields, 32) -> ((n_fields, 4, 32), status (n_fields,))."""
+        """Fused Encrypt + tally.  k, m: (n_ballots, n_fields, 32) -> ((n_fields, 4, 32), status (n_fields,)).
+        With _lib.MSG_U64 or-ed into fmt, m is a uint64 array (n_ballots, n_fields): 40 instead of 64 bytes per encryption."""
         kk = _as_elems(k, name="k")
         if kk.ndim != 3:
             raise ValueError("k must have shape (n_ballots, n_fields, 32)")
         nb, nf = kk.shape[0], kk.shape[1]
-        mm = _as_elems(m, nb * nf, "m")
+        mm = _as_msgs(m, nb * nf, fmt)
         pk = _as_elems(pub_key, 2, "pub_key")
         out = np.empty((nf, 4, 32), dtype=np.uint8)
         status = np.empty(nf, dtype=np.uint8)
@@ -861,7 +874,7 @@ class Group:
         if kk.ndim != 3:
             raise ValueError("k must have shape (n_ballots, n_fields, 32)")
         n_ballots, n_fields = kk.shape[0], kk.shape[1]
-        mm = _as_elems(m, n_ballots * n_fields, "m")
+        mm = _as_msgs(m, n_ballots * n_fields, fmt)
         pk = _as_elems(pub_key, 2, "pub_key")
         out = np.empty((n_fields, 4, 32), dtype=np.uint8)
         status = np.empty(n_fields, dtype=np.uint8)

@@ -52,6 +52,11 @@ enum gcp_format { GCP_FMT_CANONICAL = 0, GCP_FMT_MONTGOMERY = 1 };
  * so the call equals te_to_rte on every input point, the RTE call, rte_to_te on every output point - without the two extra
  * passes over PCIe.  On-curve assertions apply to the converted point.  Scalars and SMT elements are unaffected. */
 enum gcp_coords { GCP_COORDS_RTE = 0, GCP_COORDS_TE = 2 };
+/* Or-ed into the format argument of the fused tallies (gcp_elgamal_encrypt_tally*, gcp_ballot_batch*, their group forms):
+ * the messages m are little-endian uint64 values, 8 bytes each, instead of 32-byte field elements (ballot fields are small
+ * integers; the scalars k stay field elements).  40 instead of 64 bytes per encryption cross PCIe, which is what bounds
+ * these calls once several GPUs are fed from one host.  The messages are integers in either element format. */
+enum gcp_msg { GCP_MSG_FR = 0, GCP_MSG_U64 = 4 };
 
 /* per-item status bytes */
 enum gcp_status {
