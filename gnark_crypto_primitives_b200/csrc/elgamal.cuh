@@ -41,6 +41,7 @@ __host__ __device__ inline int fb_small_per_window(int wbits) {
   return (1 << fb_lo_bits(wbits)) + (1 << (wbits - 1 - fb_lo_bits(wbits))) + 1;
 }
 constexpr int BATCH_INV = 32;
+constexpr int BATCH_INV_MAX = 128;  // normalize_kernel on large batches
 
 // ---- table construction (one-time per base point) ------------------------------------------------------
 // base: affine (x, y), 16 words, standard or Montgomery form.  flag[0] = 1 if B is on the curve and canonical, else 0.
@@ -256,40 +257,70 @@ __device__ __forceinline__ void fb_stage_read(u32 (&a)[8], u32 (&b)[8], u32 (&c)
   c[0] = v[4].x; c[1] = v[4].y; c[2] = v[4].z; c[3] = v[4].w; c[4] = v[5].x; c[5] = v[5].y; c[6] = v[5].z; c[7] = v[5].w;
 }
 
+// How many windows ahead the table reads run (FB_AHEAD + 1 staging buffers of 12 KB per block).  One window ahead hides
+// ~7 us of addition behind each read; with 24-bit tables (8.9 GB per base, TLB and DRAM-page misses on every read) ncu
+// still showed 0.37 long-scoreboard stalls per issue, so the depth is a build-time number that was measured.
+#ifndef GCP_FB_AHEAD
+#define GCP_FB_AHEAD 1
+#endif
+constexpr int FB_AHEAD = GCP_FB_AHEAD;
+constexpr int FB_BUFS = FB_AHEAD + 1;
+static_assert(FB_AHEAD >= 1 && FB_AHEAD <= 3, "staging depth");
+
 __device__ __forceinline__ void fixed_base_accumulate(ExtPoint& acc, const u32 (&k)[8], const u32* __restrict__ tab) {
-  __shared__ uint4 stage[2 * 6 * FB_STAGE_THREADS];  // 24 KB
+  __shared__ uint4 stage[FB_BUFS * 6 * FB_STAGE_THREADS];
   // the table's header gives the width; the only loop state beyond round 1's (w, tab) is that one register: the window
   // count is "while the next window starts below bit 256" and the table pointer advances by one window per iteration
   const int wbits = (int)__ldg(tab - FB_HEADER_WORDS);
-  u32 carry = 0, d, dn = 0;
-  bool neg, negn = false;
-  fb_digit(k, 0, wbits, carry, d, neg);
-  if (d != 0) fb_stage_issue(stage, 0, tab + (size_t)(d - 1) * 24);
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  int w = 0;
-#pragma unroll 1
-  do {
-    const bool more = (w + 1) * wbits < 256;
-    if (more) {  // next window's entry is on its way while this window's addition runs
-      tab += (size_t)24 << (wbits - 1);
-      fb_digit(k, w + 1, wbits, carry, dn, negn);
-      if (dn != 0) fb_stage_issue(stage, (w + 1) & 1, tab + (size_t)(dn - 1) * 24);
+  const size_t wstep = (size_t)24 << (wbits - 1);
+  u32 carry = 0;
+  u32 dq[FB_AHEAD];   // digits of the windows in flight, oldest first
+  bool nq[FB_AHEAD];
+#pragma unroll
+  for (int i = 0; i < FB_AHEAD; i++) {
+    dq[i] = 0;
+    nq[i] = false;
+    if (i * wbits < 256) {
+      fb_digit(k, i, wbits, carry, dq[i], nq[i]);
+      if (dq[i] != 0) fb_stage_issue(stage, i, tab + (size_t)(dq[i] - 1) * 24);
+      tab += wstep;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but the group just committed has landed
+  }
+  int w = 0, rbuf = 0, wbuf = FB_AHEAD;  // buffer of window w / of window w + FB_AHEAD
+#pragma unroll 1
+  do {
+    u32 dn = 0;
+    bool negn = false;
+    if ((w + FB_AHEAD) * wbits < 256) {  // a later window's entry is on its way while this window's addition runs
+      fb_digit(k, w + FB_AHEAD, wbits, carry, dn, negn);
+      if (dn != 0) fb_stage_issue(stage, wbuf, tab + (size_t)(dn - 1) * 24);
+      tab += wstep;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group %0;" ::"n"(FB_AHEAD) : "memory");  // all but the FB_AHEAD newest groups have landed
+    const u32 d = dq[0];
+    const bool neg = nq[0];
     if (d != 0) {
       NielsPoint n;
       if (neg) {  // -(x, y) = (-x, y): swaps y-x and y+x, negates 2dxy
         u32 t[8];
-        fb_stage_read(n.ypx, n.ymx, t, stage, w & 1);
+        fb_stage_read(n.ypx, n.ymx, t, stage, rbuf);
         fr_neg(n.t2d, t);
       } else {
-        fb_stage_read(n.ymx, n.ypx, n.t2d, stage, w & 1);
+        fb_stage_read(n.ymx, n.ypx, n.t2d, stage, rbuf);
       }
       ext_add_niels(acc, n);
     }
-    d = dn;
-    neg = negn;
+#pragma unroll
+    for (int i = 0; i + 1 < FB_AHEAD; i++) {
+      dq[i] = dq[i + 1];
+      nq[i] = nq[i + 1];
+    }
+    dq[FB_AHEAD - 1] = dn;
+    nq[FB_AHEAD - 1] = negn;
+    rbuf = (rbuf + 1 == FB_BUFS) ? 0 : rbuf + 1;
+    wbuf = (wbuf + 1 == FB_BUFS) ? 0 : wbuf + 1;
     w++;
   } while (w * wbits < 256);
   asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -365,18 +396,21 @@ __global__ void __launch_bounds__(128, 4) encrypt_shared_kernel(const u32* __res
 
 // ---- (X, Y, Z) -> canonical affine, Montgomery batch inversion over BATCH_INV points per thread ----------------
 // xyz: n_points x xyz_words words (24, or 32 for extended points with T behind Z); out: n_points x 16 words.  status (optional) is indexed by point / pts_per_item.
+// `per` (<= BATCH_INV_MAX) points share one inversion: the launcher raises it above BATCH_INV once the batch is large
+// enough to fill the machine anyway.  A Fermat inversion is ~325 multiplications: 10 per point at 32 points per thread
+// (39 % of a Ciphertext.Add, 9 % of an Encrypt), 2.5 at 128; the prefix products cost 32 bytes of local memory per point.
 __global__ void __launch_bounds__(128) normalize_kernel(const u32* __restrict__ xyz, size_t n_points, u32* __restrict__ out,
                                                         u8* __restrict__ status, int pts_per_item, int mont, int xyz_words,
-                                                        int te) {
+                                                        int te, int per) {
   size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
   if (tid >= n_points) return;
-  u32 pre[BATCH_INV][8];  // prefix products (local memory)
+  u32 pre[BATCH_INV_MAX][8];  // prefix products (local memory)
   u32 acc[8];
   fr_set_one(acc);
   int cnt = 0;
 #pragma unroll 1
-  for (int j = 0; j < BATCH_INV; j++) {
+  for (int j = 0; j < per; j++) {
     size_t p = tid + (size_t)j * stride;
     if (p >= n_points) break;
     u32 z[8];

@@ -428,8 +428,21 @@ cudaError_t launch_encrypt_shared(const u32* tabG, const u32* tabPK, const u32* 
 cudaError_t launch_normalize(const u32* xyz, size_t n_points, u32* out, u8* status, int pts_per_item, int mont,
                              cudaStream_t stream, int xyz_words, int te) {
   if (n_points == 0) return cudaSuccess;
-  size_t threads = (n_points + BATCH_INV - 1) / BATCH_INV;
-  normalize_kernel<<<blocks_for(threads, 128), 128, 0, stream>>>(xyz, n_points, out, status, pts_per_item, mont, xyz_words, te);
+  // points per inversion: 32 until the batch is big enough for ~640 threads on every SM at that ratio, then up to 128
+  static const size_t fill = []() {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return (size_t)sms * 640;
+  }();
+  size_t per = (n_points + fill - 1) / fill;
+  per = per < (size_t)BATCH_INV ? (size_t)BATCH_INV : (per > (size_t)BATCH_INV_MAX ? (size_t)BATCH_INV_MAX : per);
+  if (const char* e = getenv("GCP_B200_NORM_PER")) {  // measurements
+    long v = atol(e);
+    if (v >= 1 && v <= BATCH_INV_MAX) per = (size_t)v;
+  }
+  size_t threads = (n_points + per - 1) / per;
+  normalize_kernel<<<blocks_for(threads, 128), 128, 0, stream>>>(xyz, n_points, out, status, pts_per_item, mont, xyz_words, te,
+                                                                 (int)per);
   return cudaGetLastError();
 }
 
@@ -482,6 +495,15 @@ cudaError_t launch_encrypt_tally(const u32* tabG, const u32* tabPK, const u32* k
                                  cudaStream_t stream, int m_words) {
   cudaError_t e = cudaMemsetAsync(bad_count, 0, sizeof(u32) * n_fields, stream);
   if (e != cudaSuccess) return e;
+  if (FB_BUFS > 2) {  // static staging buffers + the dynamic reduction tile exceed 48 KB: opt in (once per process)
+    static const bool opted = []() {
+      const int dyn = TALLY_THREADS * 32 * sizeof(u32);
+      cudaFuncSetAttribute(encrypt_tally_partial_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+      cudaFuncSetAttribute(encrypt_tally_partial_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+      return true;
+    }();
+    (void)opted;
+  }
   if (m_words == 2)
     encrypt_tally_partial_kernel<2><<<n_blocks, TALLY_THREADS, TALLY_THREADS * 32 * sizeof(u32), stream>>>(
         tabG, tabPK, ks, ms, mask, n_ballots, n_fields, partials, bad_count, mont);
