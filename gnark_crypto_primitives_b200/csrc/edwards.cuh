@@ -127,6 +127,31 @@ __device__ __forceinline__ void ext_from_affine(ExtPoint& p, const u32 (&x)[8], 
   fr_mul(p.T, x, y);
 }
 
+// Out-of-line multiplier bodies with operands and results as structs BY VALUE (the CUDA ABI hands them over in
+// registers: no local memory).  Used where one shared body beats inlined copies (varbase_reg.cuh; measured per kernel).
+struct E8 {
+  u32 v[8];
+};
+struct E16 {
+  u32 a[8], b[8];
+};
+
+__device__ __noinline__ E16 fr_mul2_ool(E16 x, E16 y) {  // (x.a * y.a, x.b * y.b)
+  E16 r;
+  fr_mul2(r.a, x.a, y.a, r.b, x.b, y.b);
+  return r;
+}
+__device__ __noinline__ E16 fr_sqr2_ool(E16 x) {  // (x.a^2, x.b^2)
+  E16 r;
+  fr_sqr2(r.a, x.a, r.b, x.b);
+  return r;
+}
+__device__ __noinline__ E8 fr_mul_ool(E8 a, E8 b) {
+  E8 r;
+  fr_mul(r.v, a.v, b.v);
+  return r;
+}
+
 // a^(r-2): Fermat inversion by square-and-multiply over the fixed exponent (0 -> 0).
 __device__ __noinline__ void fr_inv(u32 (&r)[8], const u32 (&a)[8]) {
   const u32 e[8] = {0xefffffffu, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};

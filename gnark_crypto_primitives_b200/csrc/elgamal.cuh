@@ -405,16 +405,23 @@ __global__ void __launch_bounds__(128) normalize_kernel(const u32* __restrict__ 
   size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
   if (tid >= n_points) return;
+  // Both passes are a serial chain of multiplications fed by loads nothing else depends on; left to themselves the loads
+  // of iteration j are issued at its top and the chain waits a DRAM latency per point (ncu: 1.9 long-scoreboard stalls per
+  // issue).  Forward: the next Z is loaded into registers before the current multiplication.  Backward: the next record
+  // (X | Y | Z, 96 contiguous bytes) is staged through shared memory with cp.async, like the fixed-base table entries.
+  __shared__ uint4 stage[2 * 6 * FB_STAGE_THREADS];
   u32 pre[BATCH_INV_MAX][8];  // prefix products (local memory)
-  u32 acc[8];
+  u32 acc[8], zn[8];
   fr_set_one(acc);
   int cnt = 0;
+  load_fr(zn, xyz + tid * (size_t)xyz_words + 16);
 #pragma unroll 1
   for (int j = 0; j < per; j++) {
     size_t p = tid + (size_t)j * stride;
     if (p >= n_points) break;
     u32 z[8];
-    load_fr(z, xyz + p * (size_t)xyz_words + 16);
+    fr_copy(z, zn);
+    if (j + 1 < per && p + stride < n_points) load_fr(zn, xyz + (p + stride) * (size_t)xyz_words + 16);
     u32 zc[8];
     fr_copy(zc, z);
     fr_canon(zc);
@@ -429,11 +436,16 @@ __global__ void __launch_bounds__(128) normalize_kernel(const u32* __restrict__ 
   }
   u32 inv[8];
   fr_inv(inv, acc);
+  fb_stage_issue(stage, (cnt - 1) & 1, xyz + (tid + (size_t)(cnt - 1) * stride) * (size_t)xyz_words);
+  asm volatile("cp.async.commit_group;" ::: "memory");
 #pragma unroll 1
   for (int j = cnt - 1; j >= 0; j--) {
     size_t p = tid + (size_t)j * stride;
     u32 z[8], zi[8], X[8], Y[8], x[8], y[8];
-    load_fr(z, xyz + p * (size_t)xyz_words + 16);
+    if (j > 0) fb_stage_issue(stage, (j - 1) & 1, xyz + (p - stride) * (size_t)xyz_words);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    fb_stage_read(X, Y, z, stage, j & 1);
     {
       u32 zc[8];
       fr_copy(zc, z);
@@ -449,21 +461,15 @@ __global__ void __launch_bounds__(128) normalize_kernel(const u32* __restrict__ 
     } else {
       fr_copy(zi, inv);
     }
-    load_fr(X, xyz + p * (size_t)xyz_words);
-    load_fr(Y, xyz + p * (size_t)xyz_words + 8);
+    if (!mont) fr_from_mont(zi, zi);  // standard-form output: take the factor R off 1 / z once instead of off x and y
     fr_mul(x, X, zi);
     fr_mul(y, Y, zi);
-    if (te) rte_to_te_x(x);  // results leave in iden3 coordinates
+    if (te) rte_to_te_x(x);  // results leave in iden3 coordinates (a product with a Montgomery-form constant keeps the form)
     u32 ox[8], oy[8];
-    if (mont) {
-      fr_copy(ox, x);
-      fr_copy(oy, y);
-      fr_canon(ox);
-      fr_canon(oy);
-    } else {
-      fr_from_mont(ox, x);
-      fr_from_mont(oy, y);
-    }
+    fr_copy(ox, x);
+    fr_copy(oy, y);
+    fr_canon(ox);
+    fr_canon(oy);
     bool bad = status && status[p / pts_per_item] != GCP_STATUS_OK;
     if (bad) {
       fr_set_zero(ox);
@@ -475,34 +481,63 @@ __global__ void __launch_bounds__(128) normalize_kernel(const u32* __restrict__ 
 }
 
 // ---- Ciphertext.Add / Neg, element-wise ------------------------------------------------------------------------
-__device__ __forceinline__ void load_affine_ext(ExtPoint& p, bool& canonical, const u32* src, int mont, int te = 0) {
-  u32 xs[8], ys[8], x[8], y[8];
-  load_fr(xs, src);
-  load_fr(ys, src + 8);
-  canonical = canonical && fr_is_canonical(xs) && fr_is_canonical(ys);
-  if (mont) {
-    fr_copy(x, xs);
-    fr_copy(y, ys);
-  } else {
-    fr_to_mont(x, xs);
-    fr_to_mont(y, ys);
-  }
-  if (te) te_to_rte_x(x);
-  ext_from_affine(p, x, y);
-}
-
-// a, b: n x 32 words (ciphertexts); out_xyz: n x 2 x 24 words
+// a, b: n x 32 words (ciphertexts); out_xyz: n x 2 x 24 words.  One thread per point pair, 9 multiplications:
+// the unified addition on two AFFINE inputs without the T output (A, B, x1 y1, x2 y2, their product, times 2d, X, Y, Z;
+// D = 2 Z1 Z2 is a constant) instead of two ext_from_affine + ext_add (11), and no conversion of standard-form inputs
+// (4 more): every product below is a Montgomery product of the values AS READ, so with standard-form inputs each of
+// A, B, C, D carries the same factor 1 / R (C through the constant 2d R^3, D as the constant 2 / R) and X : Y : Z is the
+// same projective point; normalize_kernel divides the factor out.  Same rational function as the reference's affine law
+// (ciphertext.go:29-30): it never uses the curve equation, and Z = 0 exactly when an affine denominator is 0.
+#define GCP_FR_TWO_MONT {0x9ffffff6u, 0x592c6838u, 0x3ec19a53u, 0x6df8ed2bu, 0xf0f28c5cu, 0xccdd46deu, 0x340fbe5eu, 0x1c14ef83u}
+#define GCP_FR_TWO_OVER_R {0xdb62329cu, 0xb8b7400au, 0xc223d90fu, 0x121deb53u, 0x5d70babau, 0x904c1bc9u, 0x058aaa39u, 0x2bd7f2a3u}
 __global__ void __launch_bounds__(128) ct_add_kernel(const u32* __restrict__ a, const u32* __restrict__ b, size_t n,
                                                      u32* __restrict__ out_xyz, u8* __restrict__ status, int mont, int te) {
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 2 * n) return;  // one thread per point
-  bool canon = true;
-  ExtPoint p, q;
-  load_affine_ext(p, canon, a + idx * 16, mont, te);
-  load_affine_ext(q, canon, b + idx * 16, mont, te);
-  ext_add(p, q);  // ciphertext.go:29-30
+  // One point per thread.  A per-thread loop over several points (so that the resident warps share what the instruction
+  // cache holds of the ~30 KB of inlined multiplier bodies: ncu shows 2.8 no-instruction stalls per issue) was measured:
+  // 1.55 against 1.44 ms per 2^23 points - the body is too large for a loop to keep it cached (the tally loop's lesson);
+  // the out-of-line multiplier bodies of edwards.cuh (fr_mul2_ool / fr_mul_ool, ~10 KB of code instead of 30): 1.42 ms, the
+  // argument moves cost what the fetch stalls did.  The inlined form stays.
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 2 * n) return;
+  u32 x1[8], y1[8], x2[8], y2[8];
+  load_fr(x1, a + idx * 16);
+  load_fr(y1, a + idx * 16 + 8);
+  load_fr(x2, b + idx * 16);
+  load_fr(y2, b + idx * 16 + 8);
+  const bool canon = fr_is_canonical(x1) && fr_is_canonical(y1) && fr_is_canonical(x2) && fr_is_canonical(y2);
+  if (te) {  // iden3 coordinates: x_RTE = x_TE * (-f), in whichever form the values are
+    te_to_rte_x(x1);
+    te_to_rte_x(x2);
+  }
+  ExtPoint p;
+  {
+    const u32 k_m[8] = GCP_ED_2D_MONT, k_s[8] = GCP_ED_2D_R3, d_m[8] = GCP_FR_TWO_MONT, d_s[8] = GCP_FR_TWO_OVER_R;
+    u32 kc[8], d[8];
+#pragma unroll
+    for (int l = 0; l < 8; l++) {
+      kc[l] = mont ? k_m[l] : k_s[l];
+      d[l] = mont ? d_m[l] : d_s[l];
+    }
+    u32 t[8], u[8], v[8], w[8], A[8], B[8], c[8], e[8], f[8], g[8], h[8];
+    fr_sub(t, y1, x1);
+    fr_sub(u, y2, x2);
+    fr_add(v, y1, x1);
+    fr_add(w, y2, x2);
+    fr_mul2(A, t, u, B, v, w);
+    fr_mul2(t, x1, y1, u, x2, y2);
+    fr_mul(c, t, u);
+    fr_mul(c, c, kc);
+    fr_sub(e, B, A);
+    fr_sub(f, d, c);
+    fr_add(g, d, c);
+    fr_add(h, B, A);
+    fr_mul2(p.X, e, f, p.Y, g, h);
+    fr_mul(p.Z, f, g);
+  }
   if (!canon) {
-    ext_identity(p);
+    fr_set_zero(p.X);
+    fr_set_one(p.Y);
+    fr_set_one(p.Z);
     status[idx / 2] = GCP_STATUS_NONCANONICAL;  // benign race: both halves write the same value
   }
   store_ext_xyz(out_xyz + idx * 24, p);

@@ -425,10 +425,9 @@ cudaError_t launch_encrypt_shared(const u32* tabG, const u32* tabPK, const u32* 
   return cudaGetLastError();
 }
 
-cudaError_t launch_normalize(const u32* xyz, size_t n_points, u32* out, u8* status, int pts_per_item, int mont,
-                             cudaStream_t stream, int xyz_words, int te) {
-  if (n_points == 0) return cudaSuccess;
-  // points per inversion: 32 until the batch is big enough for ~640 threads on every SM at that ratio, then up to 128
+// points per thread of normalize_kernel (= points per inversion): 32 until the batch is big enough for
+// ~640 threads on every SM at that ratio, then up to 128
+static size_t points_per_thread(size_t n_points) {
   static const size_t fill = []() {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -440,6 +439,13 @@ cudaError_t launch_normalize(const u32* xyz, size_t n_points, u32* out, u8* stat
     long v = atol(e);
     if (v >= 1 && v <= BATCH_INV_MAX) per = (size_t)v;
   }
+  return per;
+}
+
+cudaError_t launch_normalize(const u32* xyz, size_t n_points, u32* out, u8* status, int pts_per_item, int mont,
+                             cudaStream_t stream, int xyz_words, int te) {
+  if (n_points == 0) return cudaSuccess;
+  const size_t per = points_per_thread(n_points);
   size_t threads = (n_points + per - 1) / per;
   normalize_kernel<<<blocks_for(threads, 128), 128, 0, stream>>>(xyz, n_points, out, status, pts_per_item, mont, xyz_words, te,
                                                                  (int)per);

@@ -13,29 +13,6 @@
 
 namespace gcp {
 
-struct E8 {
-  u32 v[8];
-};
-struct E16 {
-  u32 a[8], b[8];
-};
-
-__device__ __noinline__ E16 fr_mul2_ool(E16 x, E16 y) {  // (x.a * y.a, x.b * y.b)
-  E16 r;
-  fr_mul2(r.a, x.a, y.a, r.b, x.b, y.b);
-  return r;
-}
-__device__ __noinline__ E16 fr_sqr2_ool(E16 x) {  // (x.a^2, x.b^2)
-  E16 r;
-  fr_sqr2(r.a, x.a, r.b, x.b);
-  return r;
-}
-__device__ __noinline__ E8 fr_mul_ool(E8 a, E8 b) {
-  E8 r;
-  fr_mul(r.v, a.v, b.v);
-  return r;
-}
-
 // P = 2P (dbl-2008-hwcd, a = -1); with_t = false leaves T stale (the next operation is another doubling)
 __device__ __forceinline__ void vr_double(ExtPoint& p, bool with_t) {
   E16 in, sq1, sq2;
