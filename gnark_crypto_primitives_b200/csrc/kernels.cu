@@ -39,8 +39,33 @@ cudaError_t launch_to_mont(u32* d_elems, size_t n, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+// d_q = S_q[1] S_{q-1}[3] + S_q[2] S_{q-1}[4] for q = 2, 4, ..., 56 (poseidon.cuh, t = 3 pair schedule); t3: the t = 3
+// table in Montgomery form, C | S | M | P
+__global__ void pos3_pair_kernel(const u32* __restrict__ t3) {
+  const int p = threadIdx.x;
+  if (p >= POS3_PAIR_COUNT) return;
+  const u32* srow = t3 + (size_t)((8 * 3 + 57) + 5 * (2 * p + 2)) * 8;
+  const u32* prow = srow - 5 * 8;
+  u32 a[8], b[8], c1[8], c2[8], t1[8], t2[8];
+  load_fr(a, srow + 8);
+  load_fr(b, srow + 16);
+  load_fr(c1, prow + 24);
+  load_fr(c2, prow + 32);
+  fr_mul(t1, a, c1);
+  fr_mul(t2, b, c2);
+  fr_add(t1, t1, t2);
+  fr_canon(t1);
+  store_fr(g_pos3_pair + p * 8, t1);
+}
+
 cudaError_t upload_const_tables(const u32* d_t3, const u32* d_t4, cudaStream_t stream) {
   cudaError_t e = cudaMemcpyToSymbolAsync(c_pos3, d_t3, sizeof(u32) * POS3_ELEMS * 8, 0, cudaMemcpyDeviceToDevice, stream);
+  if (e != cudaSuccess) return e;
+  pos3_pair_kernel<<<1, 32, 0, stream>>>(d_t3);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  void* d_pair = nullptr;
+  if ((e = cudaGetSymbolAddress(&d_pair, g_pos3_pair)) != cudaSuccess) return e;
+  e = cudaMemcpyToSymbolAsync(c_pos3_pair, d_pair, sizeof(u32) * POS3_PAIR_COUNT * 8, 0, cudaMemcpyDeviceToDevice, stream);
   if (e != cudaSuccess) return e;
   return cudaMemcpyToSymbolAsync(c_pos4, d_t4, sizeof(u32) * POS4_ELEMS * 8, 0, cudaMemcpyDeviceToDevice, stream);
 }
@@ -139,7 +164,7 @@ __global__ void __launch_bounds__(128) poseidon_fixed_kernel(const u32* __restri
     }
   }
   u32 h[8];
-  poseidon_permute_const<T>(s, h);
+  poseidon_permute_const<T, true>(s, h);  // t = 3: partial rounds in pairs (poseidon.cuh)
   if (g.out_mont) {
     fr_canon(h);
   } else {

@@ -23,6 +23,14 @@ constexpr int POSEIDON_RP[16] = {56, 57, 56, 60, 60, 63, 64, 63, 60, 66, 60, 65,
 constexpr int POS3_ELEMS = (8 * 3 + 57) + 5 * 57 + 9 + 9;  // 384
 constexpr int POS4_ELEMS = (8 * 4 + 56) + 7 * 56 + 16 + 16;  // 512
 __device__ __constant__ u32 c_pos3[POS3_ELEMS * 8];
+// t = 3 pair schedule (below): one derived constant per pair of partial rounds, d_q = S_q[1] c_{q-1,1} + S_q[2] c_{q-1,2}
+// for q = 2, 4, ..., 56 (c_{q,k} = S_q[t+k-1] is the rank-1 coefficient), computed on the device from the uploaded table.
+#ifndef GCP_POS3_PAIRS
+#define GCP_POS3_PAIRS 1
+#endif
+constexpr int POS3_PAIR_COUNT = (57 - 1) / 2;  // 28
+__device__ __constant__ u32 c_pos3_pair[POS3_PAIR_COUNT * 8];
+__device__ u32 g_pos3_pair[POS3_PAIR_COUNT * 8];
 __device__ __constant__ u32 c_pos4[POS4_ELEMS * 8];
 
 template <int T>
@@ -72,7 +80,7 @@ __device__ __forceinline__ void rotate_left(u32 (&s)[T][8]) {
   }
 }
 
-template <int T>
+template <int T, bool PAIR_SCHEDULE = false>
 __device__ __forceinline__ void poseidon_permute_const(u32 (&s)[T][8], u32 (&out)[8]) {
   constexpr int RP = ConstTab<T>::RP;
   const u32* C = ConstTab<T>::base();
@@ -89,11 +97,33 @@ __device__ __forceinline__ void poseidon_permute_const(u32 (&s)[T][8], u32 (&out
     fr_add(s[j], s[j], cst);
   }
 
+  // t = 3, partial rounds in PAIRS (bit-identical values, 64 fewer wide multiplies per round on average).  A partial
+  // round is s0' = <S[0..t), (x, s1, s2)>, s_k += x c_k with x the S-boxed s0: t + (t-1) products and t reductions.  The
+  // s_k of round A are only ever read by round B's dot row and rank-1 update, and both are linear in them:
+  //   round A:  x0 = sbox(s0);  s0 = S_A0 x0 + S_A1 s1 + S_A2 s2                       3 products, 1 reduction
+  //   round B:  x1 = sbox(s0);  s0 = S_B0 x1 + S_B1 s1 + S_B2 s2 + d x0                4 products, 1 reduction
+  //             s_k += c_Ak x0 + c_Bk x1   (k = 1, 2)                                  4 products, 2 reductions
+  // with d = S_B1 c_A1 + S_B2 c_A2 precomputed: 11 products + 4 reductions instead of 10 + 6 per two rounds (one unit =
+  // 64 wide multiplies).  RP = 57 is odd: the first partial round runs as a B round with x0 = 0.  Round A's dot row is
+  // the full rounds' row body with stride 1.  Bounds (r / 2^256 = 0.18904, products of values a r and b r reduce to
+  // < (0.18904 sum(a b) + 1) r): x0 is kept canonical (< r, off the critical path), y = x^5 + c < 2.89 r unreduced,
+  // after A: s0 < (2.89 + 2 + 2) 0.189 + 1 = 2.31 r, after B: s0 < (2.77 + 2 + 2 + 1) 0.189 + 1 = 2.47 r - every squaring
+  // input stays below 2^255 = 2.645 r; the rank-1 sum is < (1 + 2.89) 0.189 + 1 = 1.74 r, added to s_k < 2 r and brought
+  // back under 2 r by fr_add.
+  // Used by the batch kernel only (PAIR_SCHEDULE): Hash2 135.5 -> 137.5 M/s.  Inside smt_path_kernel the eight registers
+  // of x0 and the longer round-B body do not fit four blocks per SM: 158 registers, or 128 with 60 B of spills, and the
+  // dense proofs go 786 -> 764 k / 773 k per second at 2^17 (profiles/r02_poseidon_pair_schedule.jsonl), so the tree
+  // kernels keep one round per iteration.
+  constexpr bool PAIRS = (T == 3) && PAIR_SCHEDULE && (GCP_POS3_PAIRS != 0);
+  u32 xh[8];  // canonical x0 of the pending round A (0: none)
+#pragma unroll
+  for (int l = 0; l < 8; l++) xh[l] = 0;
   u32 n[T][8];
 #pragma unroll 1
   for (int r = 0; r < 8 + RP; r++) {
     const bool full = (r < 4) || (r >= 4 + RP);
     const bool last = (r == 7 + RP);
+    const bool phase_a = PAIRS && !full && (((r - 4) & 1) != 0);
     // round constants added after the S-box: full rounds c[(r+1)T + j] (first half), c[(r+1)T + RP - ... ] (second
     // half, poseidon.go:172), partial rounds c[5T + (r-4)] (poseidon.go:154); none in the last round.
     const u32* crow = (r < 4) ? C + (r + 1) * T * 8 : (full ? C + ((r - RP + 1) * T + RP) * 8 : C + (5 * T + (r - 4)) * 8);
@@ -118,33 +148,77 @@ __device__ __forceinline__ void poseidon_permute_const(u32 (&s)[T][8], u32 (&out
       for (int l = 0; l < 8; l++) s[0][l] = y[l];
       if (full) rotate_left<T>(s);
     }
-    if (full) {
+    if (full || phase_a) {
       // (b) matrix rows as lazy dot products: n_i = sum_j m[j][i] s_j (M, or P after round 3); the last round only
       // needs column 0.  Row-major over the terms: after product rows I of every term limb I is complete, so reduction
-      // row I follows at once and its serial chain overlaps with the product rows still to come.
-      const u32* coef = (r == 3) ? P : M;
-      const int nrows = last ? 1 : T;
+      // row I follows at once and its serial chain overlaps with the product rows still to come.  Round A of a pair
+      // (t = 3) is ONE such row over S[0..t) (coefficient stride 1), result to s0 without the conditional subtraction.
+      const u32* coef = full ? ((r == 3) ? P : M) : S + (2 * T - 1) * (r - 4) * 8;
+      const int cstride = full ? T * 8 : 8;
+      const int nrows = (last || phase_a) ? 1 : T;
+      if (phase_a) {
+        const u32 P1[8] = GCP_P_LIMBS;
+#pragma unroll
+        for (int l = 0; l < 8; l++) xh[l] = s[0][l];
+        cond_sub(xh, P2);
+        cond_sub(xh, P1);
+      }
 #pragma unroll 1
       for (int i = 0; i < nrows; i++) {
         Wide w;
         wide_zero(w);
         u32 c = 0;
         const u32* cf = coef + i * 8;
-#define GCP_DOT_ROW(I)                                                               \
-  _Pragma("unroll") for (int j = 0; j < T; j++) mac_row<I>(w, s[j], cf[j * T * 8 + I]); \
+#define GCP_DOT_ROW(I)                                                                  \
+  _Pragma("unroll") for (int j = 0; j < T; j++) mac_row<I>(w, s[j], cf[j * cstride + I]); \
   redc_row<I>(w, c);
         GCP_DOT_ROW(0) GCP_DOT_ROW(1) GCP_DOT_ROW(2) GCP_DOT_ROW(3) GCP_DOT_ROW(4) GCP_DOT_ROW(5) GCP_DOT_ROW(6) GCP_DOT_ROW(7)
 #undef GCP_DOT_ROW
         rotate_left<T>(n);
         wide_redc_finish(w, c, n[T - 1]);
-        cond_sub(n[T - 1], P2);
+        if (!phase_a) cond_sub(n[T - 1], P2);
       }
-      if (!last) {
+      if (phase_a) {
+#pragma unroll
+        for (int l = 0; l < 8; l++) s[0][l] = n[T - 1][l];
+      } else if (!last) {
 #pragma unroll
         for (int j = 0; j < T; j++)
 #pragma unroll
           for (int l = 0; l < 8; l++) s[j][l] = n[j][l];
       }
+    } else if constexpr (PAIRS) {
+      // round B of a pair (or the single first partial round, xh = 0): see the schedule above
+      const int q = r - 4;
+      const u32* srow = S + (2 * T - 1) * q * 8;
+      const u32* prow = srow - (2 * T - 1) * 8;  // round A's row (q = 0: the tail of C, multiplied by xh = 0)
+      const u32* dq = c_pos3_pair + (q >= 2 ? (q / 2 - 1) : 0) * 8;
+      Wide wd, wk[T - 1];
+      wide_zero(wd);
+#pragma unroll
+      for (int k = 0; k < T - 1; k++) wide_zero(wk[k]);
+      u32 cd = 0, ck[T - 1];
+#pragma unroll
+      for (int k = 0; k < T - 1; k++) ck[k] = 0;
+#define GCP_PAIR_ROW(I)                                                                       \
+  _Pragma("unroll") for (int j = 0; j < T; j++) mac_row<I>(wd, s[j], srow[j * 8 + I]);        \
+  mac_row<I>(wd, xh, dq[I]);                                                                  \
+  redc_row<I>(wd, cd);                                                                        \
+  _Pragma("unroll") for (int k = 0; k < T - 1; k++) {                                         \
+    mac_row<I>(wk[k], s[0], srow[(T + k) * 8 + I]);                                           \
+    mac_row<I>(wk[k], xh, prow[(T + k) * 8 + I]);                                             \
+    redc_row<I>(wk[k], ck[k]);                                                                \
+  }
+      GCP_PAIR_ROW(0) GCP_PAIR_ROW(1) GCP_PAIR_ROW(2) GCP_PAIR_ROW(3)
+      GCP_PAIR_ROW(4) GCP_PAIR_ROW(5) GCP_PAIR_ROW(6) GCP_PAIR_ROW(7)
+#undef GCP_PAIR_ROW
+#pragma unroll
+      for (int k = 1; k < T; k++) {
+        u32 prod[8];
+        wide_redc_finish(wk[k - 1], ck[k - 1], prod);
+        fr_add(s[k], s[k], prod);
+      }
+      wide_redc_finish(wd, cd, s[0]);
     } else {
       // partial round (poseidon.go:152-166): n0 = sum_j S[j] s_j and s_k += s_0 * S[T+k-1] all read the post-S-box state
       // and are independent, so their T accumulators advance row by row together: T independent carry / reduction
