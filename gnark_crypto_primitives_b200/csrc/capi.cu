@@ -62,6 +62,7 @@ struct gcp_ctx {
   std::string err;
   cudaStream_t stream[2] = {nullptr, nullptr};
   u32* d_tables = nullptr;
+  u32* d_pair_tables = nullptr;  // 18 x 40 elements: PoseidonTable::D
   PoseidonTable tab[18];  // index by t
   struct Buf {
     void* p = nullptr;
@@ -367,6 +368,7 @@ void gcp_ctx_destroy(gcp_ctx* ctx) {
     if (ctx->stage_buf[i]) cudaFreeHost(ctx->stage_buf[i]);
   }
   if (ctx->d_tables) cudaFree(ctx->d_tables);
+  if (ctx->d_pair_tables) cudaFree(ctx->d_pair_tables);
   for (u32* p : {ctx->fb[0].alloc, ctx->fb[1].alloc, ctx->d_fb_small, ctx->d_base_xy, ctx->d_flagG, ctx->d_flagPK, ctx->d_p2_keys})
     if (p) cudaFree(p);
   if (ctx->out_arena) cudaFreeHost(ctx->out_arena);
@@ -577,6 +579,18 @@ int gcp_ctx_create(int device, const char* constants_path, gcp_ctx** out) {
   }
   if ((e = upload_const_tables(ctx->tab[3].C, ctx->tab[4].C, ctx->stream[0])) != cudaSuccess)
     return bail(ctx->cuda_fail(e, "constant-memory upload"));
+  // derived constants of the partial-round pairs, one table of RP / 2 elements per t (poseidon.cuh)
+  if ((e = cudaMalloc(&ctx->d_pair_tables, (size_t)18 * 40 * 32)) != cudaSuccess)
+    return bail(ctx->cuda_fail(e, "cudaMalloc pair constants"));
+  for (int t = 2; t <= 17; t++) {
+    PoseidonTable& pt = ctx->tab[t];
+    if (pt.RP / 2 > 40) return bail(ctx->fail(GCP_ERR_CONSTANTS, "more partial rounds than the pair table holds"));
+    u32* d = ctx->d_pair_tables + (size_t)t * 40 * 8;
+    if ((e = launch_poseidon_pair_constants(pt, d, ctx->stream[0])) != cudaSuccess)
+      return bail(ctx->cuda_fail(e, "pair-constant kernel"));
+    pt.D = d;
+    ctx->launches++;
+  }
   // fixed-base table of the generator G (elgamal/mul.go:26-72 restated with wider windows), built on the device
   if ((e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess)
     return bail(ctx->cuda_fail(e, "device attribute"));

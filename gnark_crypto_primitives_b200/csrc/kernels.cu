@@ -39,6 +39,31 @@ cudaError_t launch_to_mont(u32* d_elems, size_t n, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+__global__ void poseidon_pair_constants_kernel(PoseidonTable tab, u32* __restrict__ out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= tab.RP / 2) return;
+  const int t = tab.t;
+  const u32* srow_a = tab.S + (size_t)(2 * t - 1) * ((tab.RP & 1) + 2 * p) * 8;
+  const u32* srow_b = srow_a + (2 * t - 1) * 8;
+  u32 acc[8];
+  fr_set_zero(acc);
+#pragma unroll 1
+  for (int k = 1; k < t; k++) {
+    u32 a[8], c[8], m[8];
+    load_fr(a, srow_b + k * 8);
+    load_fr(c, srow_a + (t + k - 1) * 8);
+    fr_mul(m, a, c);
+    fr_add(acc, acc, m);
+  }
+  fr_canon(acc);
+  store_fr(out + p * 8, acc);
+}
+
+cudaError_t launch_poseidon_pair_constants(const PoseidonTable& tab, u32* d_out, cudaStream_t stream) {
+  poseidon_pair_constants_kernel<<<1, 64, 0, stream>>>(tab, d_out);
+  return cudaGetLastError();
+}
+
 // d_q = S_q[1] S_{q-1}[3] + S_q[2] S_{q-1}[4] for q = 2, 4, ..., 56 (poseidon.cuh, t = 3 pair schedule); t3: the t = 3
 // table in Montgomery form, C | S | M | P
 __global__ void pos3_pair_kernel(const u32* __restrict__ t3) {

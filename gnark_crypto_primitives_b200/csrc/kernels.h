@@ -28,6 +28,7 @@ struct PoseidonTable {  // one per t, device pointers into the global-memory cop
   const u32* S;
   const u32* M;
   const u32* P;
+  const u32* D;  // RP / 2 derived constants of the partial-round pairs (poseidon.cuh), built on the device
   int RP;
   int t;
 };
@@ -86,6 +87,8 @@ struct SmtScratch {
 
 cudaError_t launch_to_mont(u32* d_elems, size_t n, cudaStream_t stream);
 cudaError_t upload_const_tables(const u32* d_t3, const u32* d_t4, cudaStream_t stream);
+// D[p] = sum_k S_B[k] S_A[t+k-1] for the p-th pair of partial rounds (A = (RP & 1) + 2p, B = A + 1); d_out: RP / 2 elements
+cudaError_t launch_poseidon_pair_constants(const PoseidonTable& tab, u32* d_out, cudaStream_t stream);
 cudaError_t launch_poseidon(const PoseidonTable& tab, const u32* in, u32* out, u8* status, size_t n_items,
                             int chunks_per_item, size_t in_item_stride, size_t in_chunk_stride,
                             size_t out_item_stride, int in_mont, int out_mont, int final_level,

@@ -301,7 +301,9 @@ constexpr int POSEIDON_MAX_T = 17;
 // t = 12..17 keeps the state canonical (one conditional subtraction of r per state write) and does the same.  Two
 // conditional subtractions of 2r bring the row result (< 5.2 r) back under 2r.  (The first version reduced every 5
 // terms: 4 reductions per row at t = 17.)
-constexpr int LAZY_DOT_NONCANON_MAX = 11;
+// Round B of a partial-round pair (below) adds one term (a canonical value times a constant) to its dot row: with the
+// state < 2r that is (2t + 1) r^2, so the non-canonical form now stops at t = 10.
+constexpr int LAZY_DOT_NONCANON_MAX = 10;
 
 __device__ __forceinline__ bool generic_state_canonical(int t) { return t > LAZY_DOT_NONCANON_MAX; }
 
@@ -313,7 +315,9 @@ __device__ __forceinline__ void load_global_const(u32 (&r)[8], const u32* p) {
 }
 
 // out = sum_j coef[j * stride] * s[j]  over j in [0, t)   (lazy Montgomery, < 2r; < r when the state is kept canonical)
-__device__ __noinline__ void generic_dot(u32 (&out)[8], const u32 (*s)[8], const u32* coef, int stride, int t) {
+// ex_c != nullptr: one more term ex_x * ex_c (ex_x canonical: round B of a partial-round pair)
+__device__ __noinline__ void generic_dot(u32 (&out)[8], const u32 (*s)[8], const u32* coef, int stride, int t,
+                                         const u32* ex_x = nullptr, const u32* ex_c = nullptr) {
   const u32 P2[8] = GCP_2P_LIMBS;
   const u32 P1[8] = GCP_P_LIMBS;
   Wide w;
@@ -324,6 +328,13 @@ __device__ __noinline__ void generic_dot(u32 (&out)[8], const u32 (*s)[8], const
     load_global_const(c, coef + (size_t)j * stride * 8);
 #pragma unroll
     for (int l = 0; l < 8; l++) x[l] = s[j][l];
+    wide_mac(w, x, c);
+  }
+  if (ex_c) {
+    u32 c[8], x[8];
+    load_global_const(c, ex_c);
+#pragma unroll
+    for (int l = 0; l < 8; l++) x[l] = ex_x[l];
     wide_mac(w, x, c);
   }
   u32 total[8];
@@ -363,14 +374,20 @@ __device__ __forceinline__ void poseidon_permute_generic(u32 (*s)[8], u32 (*n)[8
 #pragma unroll 1
   for (int fr = 0; fr < 8; fr++) {
     if (fr == 4) {
-#pragma unroll 1
-      for (int r = 0; r < rp; r++) {
+      // Partial rounds in PAIRS (the schedule of poseidon_permute_const, for every t; t - 2 units of 64 wide multiplies
+      // saved per two rounds: 13 % of the partial rounds at t = 13).  Round A: x0 = sbox(s0), s0 = <S_A[0..t), state>, the
+      // rank-1 update is NOT applied.  Round B: x1 = sbox(s0), s0 = <S_B[0..t), state> + d x0 with the derived constant
+      // d = sum_k S_B[k] c_A[k] (tab.D, one per pair), then s_k += c_A[k] x0 + c_B[k] x1 as one two-term product with one
+      // reduction.  An odd RP starts with one ordinary round.  x0 is kept canonical (the extra dot term's bound above;
+      // the two-term product is < 3 r^2, its reduction < 1.57 r, added to s_k < 2r by fr_add).
+      int r = 0;
+      if (rp & 1) {
 #pragma unroll
         for (int l = 0; l < 8; l++) x[l] = s[0][l];
-        generic_sigma_ark(x, tab.C + (5 * t + r) * 8, canonical);
+        generic_sigma_ark(x, tab.C + (5 * t) * 8, canonical);
 #pragma unroll
         for (int l = 0; l < 8; l++) s[0][l] = x[l];
-        const u32* srow = tab.S + (size_t)(2 * t - 1) * r * 8;
+        const u32* srow = tab.S;
         u32 n0[8];
         generic_dot(n0, s, srow, 1, t);
 #pragma unroll 1
@@ -378,6 +395,53 @@ __device__ __forceinline__ void poseidon_permute_generic(u32 (*s)[8], u32 (*n)[8
           u32 prod[8], y[8];
           load_global_const(k, srow + (t + kk - 1) * 8);
           fr_mul(prod, x, k);
+#pragma unroll
+          for (int l = 0; l < 8; l++) y[l] = s[kk][l];
+          fr_add(y, y, prod);
+          if (canonical) cond_sub(y, P1);
+#pragma unroll
+          for (int l = 0; l < 8; l++) s[kk][l] = y[l];
+        }
+#pragma unroll
+        for (int l = 0; l < 8; l++) s[0][l] = n0[l];
+        r = 1;
+      }
+      const u32* dpair = tab.D;
+#pragma unroll 1
+      for (; r < rp; r += 2, dpair += 8) {
+        u32 x0[8], n0[8];
+        const u32* srow_a = tab.S + (size_t)(2 * t - 1) * r * 8;
+        const u32* srow_b = srow_a + (2 * t - 1) * 8;
+        // round A
+#pragma unroll
+        for (int l = 0; l < 8; l++) x[l] = s[0][l];
+        generic_sigma_ark(x, tab.C + (5 * t + r) * 8, canonical);
+#pragma unroll
+        for (int l = 0; l < 8; l++) s[0][l] = x[l];
+        generic_dot(n0, s, srow_a, 1, t);
+#pragma unroll
+        for (int l = 0; l < 8; l++) {
+          x0[l] = x[l];
+          s[0][l] = n0[l];
+        }
+        if (!canonical) cond_sub(x0, P1);  // x < 2r -> canonical
+        // round B
+#pragma unroll
+        for (int l = 0; l < 8; l++) x[l] = s[0][l];
+        generic_sigma_ark(x, tab.C + (5 * t + r + 1) * 8, canonical);
+#pragma unroll
+        for (int l = 0; l < 8; l++) s[0][l] = x[l];
+        generic_dot(n0, s, srow_b, 1, t, x0, dpair);
+#pragma unroll 1
+        for (int kk = 1; kk < t; kk++) {
+          u32 prod[8], y[8], ca[8], cb[8];
+          load_global_const(ca, srow_a + (t + kk - 1) * 8);
+          load_global_const(cb, srow_b + (t + kk - 1) * 8);
+          Wide w;
+          wide_zero(w);
+          wide_mac(w, x0, ca);
+          wide_mac(w, x, cb);
+          wide_redc(w, prod);
 #pragma unroll
           for (int l = 0; l < 8; l++) y[l] = s[kk][l];
           fr_add(y, y, prod);
