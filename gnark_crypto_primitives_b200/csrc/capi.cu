@@ -63,6 +63,9 @@ struct gcp_ctx {
   cudaStream_t stream[2] = {nullptr, nullptr};
   u32* d_tables = nullptr;
   u32* d_pair_tables = nullptr;  // 18 x 40 elements: PoseidonTable::D
+  // small host-buffer hash batches: page-locked memory mapped into the device's address space (inputs | results | status)
+  char* small_h = nullptr;
+  char* small_d = nullptr;
   PoseidonTable tab[18];  // index by t
   struct Buf {
     void* p = nullptr;
@@ -369,6 +372,7 @@ void gcp_ctx_destroy(gcp_ctx* ctx) {
   }
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   if (ctx->d_pair_tables) cudaFree(ctx->d_pair_tables);
+  if (ctx->small_h) cudaFreeHost(ctx->small_h);
   for (u32* p : {ctx->fb[0].alloc, ctx->fb[1].alloc, ctx->d_fb_small, ctx->d_base_xy, ctx->d_flagG, ctx->d_flagPK, ctx->d_p2_keys})
     if (p) cudaFree(p);
   if (ctx->out_arena) cudaFreeHost(ctx->out_arena);
@@ -775,6 +779,14 @@ int gcp_poseidon_multihash_dev(gcp_ctx* ctx, const void* d_in, int len, size_t n
 }
 
 // Host-buffer form: chunks of items, two streams alternate so that the copy of chunk k+1 overlaps the kernels of chunk k.
+constexpr size_t SMALL_HASH_IN_BYTES = (size_t)256 << 10;
+constexpr size_t SMALL_HASH_MAX_N = SMALL_HASH_IN_BYTES / 32;  // arity 1
+constexpr size_t SMALL_HASH_OUT_BYTES = SMALL_HASH_MAX_N * 32;
+static bool small_path_disabled() {
+  static const bool off = getenv("GCP_B200_NO_ZEROCOPY") != nullptr;  // measurements
+  return off;
+}
+
 static int poseidon_host(gcp_ctx* ctx, const void* in, int len, size_t n, void* out, uint8_t* status, int fmt,
                          bool multi) {
   if (!ctx) return GCP_ERR_BAD_ARG;
@@ -787,6 +799,39 @@ static int poseidon_host(gcp_ctx* ctx, const void* in, int len, size_t n, void* 
   if (n == 0) return GCP_OK;
   if (!in || !out) return ctx->fail(GCP_ERR_BAD_ARG, "null buffer");
   const size_t item_bytes = (size_t)len * 32;
+  // Small batches (BASELINE config 1: 1024 Hash2 = 64 KB in, 32 KB out) are latency, not bandwidth: three staged copies, two
+  // stream synchronisations and the status memset cost ~75 us around a 154 us kernel.  Up to 256 KB of inputs the kernel
+  // reads them from, and writes its results to, page-locked host memory mapped into its address space (zero-copy): one
+  // CPU memcpy each way, one launch, one synchronisation.
+  if (!multi && n * item_bytes <= SMALL_HASH_IN_BYTES && !small_path_disabled()) {
+    if (!ctx->small_h) {
+      cudaError_t e = cudaHostAlloc((void**)&ctx->small_h, SMALL_HASH_IN_BYTES + SMALL_HASH_OUT_BYTES + SMALL_HASH_MAX_N,
+                                    cudaHostAllocMapped);
+      if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&ctx->small_d, ctx->small_h, 0);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (ctx->small_h) cudaFreeHost(ctx->small_h);
+        ctx->small_h = ctx->small_d = nullptr;
+      }
+    }
+    if (ctx->small_h) {
+      if (fmt != GCP_FMT_CANONICAL && fmt != GCP_FMT_MONTGOMERY) return ctx->fail(GCP_ERR_BAD_ARG, "bad element format");
+      char* h_out = ctx->small_h + SMALL_HASH_IN_BYTES;
+      char* h_st = h_out + SMALL_HASH_OUT_BYTES;
+      memcpy(ctx->small_h, in, n * item_bytes);
+      memset(h_st, 0, n);
+      cudaStream_t st = ctx->stream[0];
+      CU(launch_poseidon(ctx->tab[len + 1], (const u32*)ctx->small_d, (u32*)(ctx->small_d + SMALL_HASH_IN_BYTES),
+                         (uint8_t*)(ctx->small_d + SMALL_HASH_IN_BYTES + SMALL_HASH_OUT_BYTES), n, 1, (size_t)len, 0, 1, fmt, fmt,
+                         1, st),
+         "poseidon kernel");
+      ctx->launches++;
+      CU(cudaStreamSynchronize(st), "stream sync");
+      memcpy(out, h_out, n * 32);
+      if (status) memcpy(status, h_st, n);
+      return GCP_OK;
+    }
+  }
   size_t chunk = std::max<size_t>(1, std::min<size_t>(n, ((size_t)256 << 20) / item_bytes));
   int rc = GCP_OK;
   size_t k = 0;
