@@ -43,6 +43,11 @@ def wide_per_hash(t, rp):
     full_sigma = 8 * t * sbox                            # 8 full rounds
     dense_mix = 7 * t * (t * 64 + 64) + (t * 64 + 64)    # 7 matrix mixes + last column, lazy dot: t*64 + one reduction
     partial = rp * (sbox + (t * 64 + 64) + (t - 1) * FR_MUL_WIDE)
+    if t == 3:
+        # partial rounds in pairs (poseidon.cuh; batch kernel and, out of line, the tree kernels): per pair 11 products + 4
+        # reductions instead of 10 + 6; the first of the 57 rounds runs as a round B with x0 = 0 (8 products, 3 reductions)
+        pairs, single = divmod(rp, 2)
+        partial = rp * sbox + pairs * (11 + 4) * 64 + single * (8 + 3) * 64
     return full_sigma + dense_mix + partial
 
 

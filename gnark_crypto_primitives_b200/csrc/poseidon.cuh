@@ -110,10 +110,10 @@ __device__ __forceinline__ void poseidon_permute_const(u32 (&s)[T][8], u32 (&out
   // after A: s0 < (2.89 + 2 + 2) 0.189 + 1 = 2.31 r, after B: s0 < (2.77 + 2 + 2 + 1) 0.189 + 1 = 2.47 r - every squaring
   // input stays below 2^255 = 2.645 r; the rank-1 sum is < (1 + 2.89) 0.189 + 1 = 1.74 r, added to s_k < 2 r and brought
   // back under 2 r by fr_add.
-  // Used by the batch kernel only (PAIR_SCHEDULE): Hash2 135.5 -> 137.5 M/s.  Inside smt_path_kernel the eight registers
-  // of x0 and the longer round-B body do not fit four blocks per SM: 158 registers, or 128 with 60 B of spills, and the
-  // dense proofs go 786 -> 764 k / 773 k per second at 2^17 (profiles/r02_poseidon_pair_schedule.jsonl), so the tree
-  // kernels keep one round per iteration.
+  // PAIR_SCHEDULE: the batch kernel (Hash2 135.5 -> 137.5 M/s) and, through the out-of-line poseidon_hash2_pairs_ool of
+  // smt.cuh, the tree kernels.  INLINED into smt_path_kernel the eight registers of x0 and the longer round-B body do not
+  // fit four blocks per SM (158 registers, or 128 with 4.6 % more executed instructions: dense proofs 786 -> 764 / 773 k
+  // per second at 2^17, profiles/r02_poseidon_pair_schedule.jsonl).
   constexpr bool PAIRS = (T == 3) && PAIR_SCHEDULE && (GCP_POS3_PAIRS != 0);
   u32 xh[8];  // canonical x0 of the pending round A (0: none)
 #pragma unroll
@@ -268,7 +268,10 @@ __device__ __forceinline__ void poseidon_hash2(u32 (&out)[8], const u32 (&l)[8],
     s[1][i] = l[i];
     s[2][i] = r[i];
   }
-  poseidon_permute_const<3>(s, out);
+#ifndef GCP_SMT_PAIRS
+#define GCP_SMT_PAIRS 0  // the tree kernels keep one partial round per iteration (measured: see poseidon_permute_const)
+#endif
+  poseidon_permute_const<3, (GCP_SMT_PAIRS != 0)>(s, out);
 }
 
 // Poseidon(a, b, c) — Hash1 (tree/smt/hash.go:10-19) is poseidon_hash3(key, value, 1).

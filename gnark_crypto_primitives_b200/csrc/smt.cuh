@@ -35,10 +35,42 @@ __device__ __forceinline__ void p2_absorb(u32 (&cv)[8], const u32 (&m)[8], const
   fr_add(cv, s1, m);
 }
 
+// Hash2 of the tree kernels: the pair-schedule permutation (poseidon.cuh: 59 784 instead of 61 384 wide multiplies) as an
+// OUT-OF-LINE function whose operands and result are structs passed by value (registers).  Inlined into smt_path_kernel the
+// same body lost 1.7 % (capped at 128 registers ptxas spends 6 k more non-multiply instructions per hash on it, ncu:
+// profiles/r02_smt_pair_schedule_ncu.csv; uncapped it takes 158 registers, three blocks per SM); as a function it keeps its
+// own register allocation - the one poseidon_fixed_kernel<3> gets - and the caller's per-level state is saved around one
+// call per level (140 B of stack traffic per 60 k multiplies).  Dense proofs 786 -> 797 k/s at 2^17, census-like
+// 5.13 -> 5.22 M/s, processor 2.48 -> 2.57 M transitions/s.  GCP_SMT_HASH2_INLINE restores the inlined one-round form.
+#ifndef GCP_SMT_HASH2_INLINE
+struct SmtE8 {
+  u32 v[8];
+};
+__device__ __noinline__ SmtE8 poseidon_hash2_pairs_ool(SmtE8 l, SmtE8 r) {
+  u32 s[3][8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    s[0][i] = 0;
+    s[1][i] = l.v[i];
+    s[2][i] = r.v[i];
+  }
+  SmtE8 o;
+  poseidon_permute_const<3, true>(s, o.v);
+  return o;
+}
+#endif
 template <int HASHER>
 __device__ __forceinline__ void smt_hash2(u32 (&out)[8], const u32 (&l)[8], const u32 (&r)[8], const u32* __restrict__ hk) {
   if constexpr (HASHER == 0) {
+#ifndef GCP_SMT_HASH2_INLINE
+    SmtE8 a, b;
+    fr_copy(a.v, l);
+    fr_copy(b.v, r);
+    a = poseidon_hash2_pairs_ool(a, b);
+    fr_copy(out, a.v);
+#else
     poseidon_hash2(out, l, r);
+#endif
   } else {
     u32 ls[8], rs[8];
     fr_from_mont(ls, l);  // canonical integers: the order is on the values, not on their representations
@@ -309,8 +341,14 @@ __device__ __forceinline__ void smt_stage_chunk(u32* tile, const u32* __restrict
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+// four blocks per SM (128 registers).  With the inlined Hash2 (GCP_SMT_HASH2_INLINE) ptxas lands on 128 by itself and a
+// bound of 1 would make it take 136.
+#ifndef GCP_SMT_PATH_MIN_BLOCKS
+#define GCP_SMT_PATH_MIN_BLOCKS 4
+#endif
+#define GCP_SMT_PATH_BOUNDS __launch_bounds__(SMT_WARPS * 32, GCP_SMT_PATH_MIN_BLOCKS)
 template <int HASHER>
-__global__ void __launch_bounds__(SMT_WARPS * 32) smt_path_kernel(SmtArgs a, const u32* __restrict__ perm, const u16* __restrict__ lidx_arr,
+__global__ void GCP_SMT_PATH_BOUNDS smt_path_kernel(SmtArgs a, const u32* __restrict__ perm, const u16* __restrict__ lidx_arr,
                                                        const u8* __restrict__ info_arr) {
   __shared__ __align__(16) u32 tiles[2][SMT_WARPS][32 * SMT_ROW_WORDS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
