@@ -27,5 +27,7 @@ def test_work_model_matches_kernel_structure():
     import bench
 
     # x^5 = 2 squarings (100 wide) + 1 multiply (128); a lazy dot row = t*64 + 64; rank-1 updates = 128 each
-    assert bench.wide_per_hash(3, 57) == 8 * 3 * 328 + 7 * 3 * 256 + 256 + 57 * (328 + 256 + 2 * 128) == 61384
-    assert bench.wide_per_hash(4, 56) == 77568
+    # t = 3 (poseidon.cuh, partial rounds in pairs): 28 pairs of 11 products + 4 reductions, the first of the 57 rounds as
+    # a round B with x0 = 0 (8 products + 3 reductions); one round at a time it was 57 * (328 + 256 + 2 * 128): 61 384
+    assert bench.wide_per_hash(3, 57) == 8 * 3 * 328 + 7 * 3 * 256 + 256 + 57 * 328 + 28 * 15 * 64 + 11 * 64 == 59784
+    assert bench.wide_per_hash(4, 56) == 8 * 4 * 328 + 7 * 4 * 320 + 320 + 56 * (328 + 320 + 3 * 128) == 77568
