@@ -10,7 +10,8 @@
 // All of these are group elements given by exact field arithmetic, so any addition order / window width yields
 // the same canonical affine coordinates.  This file uses signed w-bit windows over precomputed Niels tables
 // (tab[i][d-1] = [d * 2^(w*i)] B, d = 1 .. 2^(w-1), w = 20 or 24) for both G and a shared public key, accumulates in extended coordinates,
-// and converts to affine with chunked Montgomery batch inversion (one Fermat inversion per BATCH_INV points).
+// and converts to affine with chunked Montgomery batch inversion (one Fermat inversion per BATCH_INV ... BATCH_INV_MAX
+// points, the launcher's choice: normalize_kernel).
 #pragma once
 #include "edwards.cuh"
 #include "kernels.h"

@@ -103,7 +103,9 @@ int gcp_probe_imad_wide(gcp_ctx* ctx, double* wide_mul_per_s);
 
 /* ---- Poseidon: hash/native/bn254/poseidon/poseidon.go ------------------------------------------- */
 /* poseidon.Hash (poseidon.go:38-45, Sum :116-183): n independent hashes of `arity` inputs each.
- * in: n*arity elements, out: n elements.  arity outside 1..16 -> GCP_ERR_BAD_ARG ("bad inputs provided"). */
+ * in: n*arity elements, out: n elements.  arity outside 1..16 -> GCP_ERR_BAD_ARG ("bad inputs provided").
+ * Host-buffer calls with at most 256 KB of inputs (BASELINE config 1: 1024 x 2) are latency-shaped: the kernel reads
+ * and writes page-locked memory mapped into the device (one memcpy each way inside the library, no staged copies). */
 int gcp_poseidon_hash(gcp_ctx* ctx, const void* in, int arity, size_t n, void* out, uint8_t* status, int fmt);
 int gcp_poseidon_hash_dev(gcp_ctx* ctx, const void* d_in, int arity, size_t n, void* d_out, uint8_t* d_status,
                           int fmt, void* stream);
