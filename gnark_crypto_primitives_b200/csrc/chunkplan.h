@@ -47,4 +47,18 @@ struct ChunkPlan {
   }
 };
 
+// Points per thread of normalize_kernel (= points that share one Fermat inversion, ~325 multiplications): per_min until the
+// batch is big enough for ~640 threads on every SM at that ratio, then as many as keep that many threads busy, up to
+// per_max.  GCP_B200_NORM_PER forces a ratio in [1, per_max] (measurements, tests).
+inline size_t normalize_points_per_thread(size_t n_points, int sm_count, size_t per_min, size_t per_max) {
+  const size_t fill = (size_t)std::max(1, sm_count) * 640;
+  size_t per = (n_points + fill - 1) / fill;
+  per = per < per_min ? per_min : (per > per_max ? per_max : per);
+  if (const char* e = getenv("GCP_B200_NORM_PER")) {
+    long v = atol(e);
+    if (v >= 1 && (size_t)v <= per_max) per = (size_t)v;
+  }
+  return per;
+}
+
 }  // namespace gcp

@@ -14,6 +14,7 @@
 #include "mimc7.cuh"
 #include "poseidon2.cuh"
 #include "kernels.h"
+#include "chunkplan.h"
 
 #include <algorithm>
 #include <cstdlib>
@@ -475,21 +476,14 @@ cudaError_t launch_encrypt_shared(const u32* tabG, const u32* tabPK, const u32* 
   return cudaGetLastError();
 }
 
-// points per thread of normalize_kernel (= points per inversion): 32 until the batch is big enough for
-// ~640 threads on every SM at that ratio, then up to 128
+// points per thread of normalize_kernel: chunkplan.h (host logic, unit-tested without a GPU)
 static size_t points_per_thread(size_t n_points) {
-  static const size_t fill = []() {
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return (size_t)sms * 640;
+  static const int sms = []() {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
   }();
-  size_t per = (n_points + fill - 1) / fill;
-  per = per < (size_t)BATCH_INV ? (size_t)BATCH_INV : (per > (size_t)BATCH_INV_MAX ? (size_t)BATCH_INV_MAX : per);
-  if (const char* e = getenv("GCP_B200_NORM_PER")) {  // measurements
-    long v = atol(e);
-    if (v >= 1 && v <= BATCH_INV_MAX) per = (size_t)v;
-  }
-  return per;
+  return normalize_points_per_thread(n_points, sms, BATCH_INV, BATCH_INV_MAX);
 }
 
 cudaError_t launch_normalize(const u32* xyz, size_t n_points, u32* out, u8* status, int pts_per_item, int mont,

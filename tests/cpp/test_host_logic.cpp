@@ -85,7 +85,39 @@ static int test_copy_pool() {
   return 0;
 }
 
+// normalize_kernel's points per Fermat inversion (chunkplan.h): 32 on small batches, then what keeps ~640 threads per SM
+// busy, at most 128; the forced ratio of the measurements and the parity tests
+static int test_normalize_points_per_thread() {
+  unsetenv("GCP_B200_NORM_PER");
+  const int sms = 148;
+  const size_t fill = (size_t)sms * 640;
+  CHECK(gcp::normalize_points_per_thread(0, sms, 32, 128) == 32);
+  CHECK(gcp::normalize_points_per_thread(1, sms, 32, 128) == 32);
+  CHECK(gcp::normalize_points_per_thread(32 * fill, sms, 32, 128) == 32);
+  CHECK(gcp::normalize_points_per_thread(32 * fill + 1, sms, 32, 128) == 33);
+  CHECK(gcp::normalize_points_per_thread((size_t)1 << 23, sms, 32, 128) == 89);  // 2^22 ciphertexts: 88.6 -> 89
+  CHECK(gcp::normalize_points_per_thread(128 * fill, sms, 32, 128) == 128);
+  CHECK(gcp::normalize_points_per_thread((size_t)1 << 30, sms, 32, 128) == 128);
+  CHECK(gcp::normalize_points_per_thread(1000, 0, 32, 128) == 32);               // a silly SM count does not divide by 0
+  for (size_t n : {(size_t)1, (size_t)4096, (size_t)1 << 22, (size_t)1 << 27}) {
+    const size_t per = gcp::normalize_points_per_thread(n, sms, 32, 128);
+    CHECK(per >= 32 && per <= 128);
+    CHECK(per * ((n + per - 1) / per) >= n);  // the launch covers every point
+  }
+  setenv("GCP_B200_NORM_PER", "7", 1);
+  CHECK(gcp::normalize_points_per_thread((size_t)1 << 23, sms, 32, 128) == 7);
+  setenv("GCP_B200_NORM_PER", "128", 1);
+  CHECK(gcp::normalize_points_per_thread(10, sms, 32, 128) == 128);
+  setenv("GCP_B200_NORM_PER", "129", 1);  // out of range: ignored
+  CHECK(gcp::normalize_points_per_thread(10, sms, 32, 128) == 32);
+  setenv("GCP_B200_NORM_PER", "0", 1);
+  CHECK(gcp::normalize_points_per_thread(10, sms, 32, 128) == 32);
+  unsetenv("GCP_B200_NORM_PER");
+  return 0;
+}
+
 int main() {
+  if (test_normalize_points_per_thread()) return 1;
   if (test_chunk_plan()) return 1;
   if (test_copy_pool()) return 1;
   printf("host logic ok\n");
